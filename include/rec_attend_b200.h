@@ -1,0 +1,239 @@
+/*
+ * rec_attend_b200.h — C ABI of librecattend_b200.so (hand-written sm_100a CUDA).
+ *
+ * The drop-in boundary for the recurrent-attention decoding hot path of
+ * renmengye/rec-attend-public.  Plain pointers and sizes only (no torch / TF types).
+ * Conventions:
+ *   - every `ra_*` entry point returns 0 on success or a negative RA_ERR_* code; nothing
+ *     here aborts the process (the reference's LOG(FATAL) paths become status codes);
+ *   - unless the name ends in `_host`, all data pointers are DEVICE pointers to contiguous
+ *     row-major fp32 (int32 where noted) owned by the caller; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream) and is
+ *     asynchronous; the entry points are stateless and re-entrant;
+ *   - `_host` variants take HOST pointers, do their own H2D/D2H copies and synchronise
+ *     before returning (this is what a TF-style CPU custom-op shim binds);
+ *   - layouts follow the reference: images/features NHWC, mask stacks [B,T,H,W], index 0
+ *     of any 2-vector is y (rows), index 1 is x (cols).
+ * Reference citations are relative to the reference repository root.
+ */
+#ifndef REC_ATTEND_B200_H_
+#define REC_ATTEND_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RA_OK 0
+#define RA_ERR_INVALID_ARG (-1)
+#define RA_ERR_CUDA (-2)
+#define RA_ERR_UNSUPPORTED (-3)
+#define RA_ERR_NO_DEVICE (-4)
+
+/* per-example status bits written by ra_hungarian_f32 */
+#define RA_HUNG_ST_OUTER_CAP 1 /* 1000 outer rounds reached: unfinished matching returned,
+                                  like the reference's LOG(ERROR) path (hungarian.cc:362-377) */
+
+#define RA_HUNG_MAX_N 64 /* nx, ny <= 64 (vertex sets are 64-bit masks) */
+
+/* Library / device probe. ra_version() = 10000*major + 100*minor + patch. */
+int ra_version(void);
+int ra_device_count(void);
+/* Last CUDA error string seen by this thread inside the library ("" if none). */
+const char *ra_last_error(void);
+
+/* --------------------------------------------------------------------------------------
+ * Hungarian matching — replaces the TF custom op
+ *   REGISTER_OP("Hungarian").Input("weights: float").Output("matching: float")
+ *       .Output("cover_x: float").Output("cover_y: float")            (hungarian.cc:26-30)
+ * registered for DEVICE_CPU only (hungarian.cc:540) and called as
+ *   hungarian_module.hungarian(W)[0]                                   (modellib.py:406).
+ * W [B,nx,ny] (B = 1 for the rank-2 form, hungarian.cc:58-60) -> M [B,nx,ny] in {0,1},
+ * cover_x [B,nx] (op shape [B,nx,1]), cover_y [B,ny] (op shape [B,1,ny]).
+ * status [B] int32 (may be NULL) receives RA_HUNG_ST_* bits.
+ * One warp per example; results are bit-identical to the reference algorithm wherever the
+ * reference terminates (its 1000-pop BFS abort, hungarian.cc:124-127, does not exist here).
+ * -------------------------------------------------------------------------------------- */
+int ra_hungarian_f32(const float *W, int B, int nx, int ny, float *M, float *cover_x, float *cover_y,
+                     int32_t *status, void *stream);
+int ra_hungarian_f32_host(const float *W, int B, int nx, int ny, float *M, float *cover_x, float *cover_y,
+                          int32_t *status);
+
+/* f_segm_match (modellib.py:382-415): W = floor(iou*mx*my*1e6+0.5)/1e6 + 1e-5, Hungarian,
+ * mask again.  iou [B,T,T] (rows = outputs, cols = ground truth), s_gt [B,T] -> match [B,T,T].
+ * weights_out (may be NULL) receives the fp32 matrix handed to the matcher. */
+int ra_segm_match_f32(const float *iou, const float *s_gt, int B, int T, float *match, float *weights_out,
+                      int32_t *status, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Convolution block — nnlib.py:214-255 (run_cnn) and :339-402 (run_dcnn) in eval mode:
+ *   y = act( (conv(x) ) * scale + shift ), optional 2x2 max-pool; BN(eval)+bias are folded
+ *   into per-channel scale/shift by the caller (nnlib.py:119, eps 1e-3).
+ * x1 [B,Hin,Win,C1] (+ optional x2 [B,Hin,Win,C2], channel-concatenated after x1, the
+ * skip connection of nnlib.py:362-367), w [3,3,C1+C2,Cout] in HWIO order (for transposed
+ * layers the caller passes the flipped/transposed filter), 3x3, SAME.
+ * upsample = 1: plain conv (stride 1).  upsample = 2: conv2d_transpose stride 2
+ * (nnlib.py:372-376): the input is zero-inserted to 2Hin x 2Win and the window starts 2
+ * before the output pixel.  pool in {1,2}; relu in {0,1}.
+ * y [B,Hout/pool,Wout/pool,Cout].  add_to (may be NULL) [B,Hout,Wout,Cout] is added to the
+ * raw convolution before scale/shift (used to split the first controller layer into a
+ * static part and a per-step canvas part, full_model.py:640-663).
+ * -------------------------------------------------------------------------------------- */
+int ra_conv3x3_f32(const float *x1, int C1, const float *x2, int C2, const float *w, const float *scale,
+                   const float *shift, const float *add_to, int B, int Hin, int Win, int Cout, int upsample,
+                   int pool, int relu, float *y, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Controller step — full_model.py:668-725 / box_model.py:417-470: 5 soft-attention glimpse
+ * read-outs of the controller feature map, LSTM (nnlib.py:637-649, state reset to 0),
+ * glimpse MLP + softmax (nnlib.py:476-493), controller head, box-parameter maths
+ * (modellib.py:752-856).  One launch per decode step for the whole batch.
+ * feat [B,P,Cf] (P = h'w', p = y*w'+x).  Weights in the reference's layouts:
+ * lstm_wx [4][Cf][Hd], lstm_wh [4][Hd][Hd], lstm_b [4][Hd] in gate order i,f,o,u;
+ * gmlp_w0 [Hd,Hd], gmlp_b0 [Hd], gmlp_w1 [Hd,P], gmlp_b1 [P]; cmlp_w [Hd,9], cmlp_b [9].
+ * Outputs: h_out [B,Hd]; ctrl_out [B,9]; glimpse_map [B,n_iter,P];
+ * box [B,RA_BOX_STRIDE] = see RA_BOX_* offsets.
+ * flags: RA_CTRL_* bits.
+ * -------------------------------------------------------------------------------------- */
+#define RA_CTRL_SQUASH 1      /* squash_ctrl_params (full_model.py:695-697) */
+#define RA_CTRL_FIXED_VAR 2   /* fixed_var (:702-703) */
+#define RA_CTRL_DYNAMIC_VAR 4 /* dynamic_var (:708-709) */
+#define RA_CTRL_FIXED_GAMMA 8 /* fixed_gamma (:711-713) */
+
+#define RA_BOX_CTR_Y 0
+#define RA_BOX_CTR_X 1
+#define RA_BOX_SIZE_Y 2
+#define RA_BOX_SIZE_X 3
+#define RA_BOX_LGVAR_Y 4
+#define RA_BOX_LGVAR_X 5
+#define RA_BOX_GAMMA_ATTN 6 /* exp(lg_gamma_attn) */
+#define RA_BOX_GAMMA_BOX 7  /* exp(lg_gamma_box) */
+#define RA_BOX_GAMMA_Y 8    /* exp(lg_gamma_y) */
+#define RA_BOX_TL_Y 9       /* ctr - size/2 (modellib.py:850-852) */
+#define RA_BOX_TL_X 10
+#define RA_BOX_BR_Y 11      /* ctr + size/2 */
+#define RA_BOX_BR_X 12
+#define RA_BOX_STRIDE 16
+
+int ra_controller_step_f32(const float *feat, int B, int P, int Cf, int Hd, int n_iter, const float *lstm_wx,
+                           const float *lstm_wh, const float *lstm_b, const float *gmlp_w0, const float *gmlp_b0,
+                           const float *gmlp_w1, const float *gmlp_b1, const float *cmlp_w, const float *cmlp_b,
+                           int inp_height, int inp_width, int filter_height, int filter_width, int flags,
+                           float *h_out, float *ctrl_out, float *glimpse_map, float *box, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Gaussian attention filters — modellib.get_gaussian_filter (modellib.py:581-612), built
+ * once per decode step from `box` (RA_BOX_* layout) as tap-major profiles
+ *   fy [B,F,H], fx [B,F,W]:  f[b,t,l] = exp(-(l-mu_t)^2 / (2 e^{lg_var})) / sqrt(2 pi e^{lg_var}),
+ *   mu_t = ctr + (size+1)/F * (t - (F-1)/2)
+ * (the reference's [B,L,F] filter transposed) plus the support band of every tap:
+ * band [B,2,F,2] int32 = (lo, hi) inclusive pixel range per axis (0 = y, 1 = x) and tap;
+ * entries whose exponent is below -30 are stored as exact zeros.
+ * -------------------------------------------------------------------------------------- */
+int ra_gaussian_filters_f32(const float *box, int B, int H, int W, int F, float *fy, float *fx, int32_t *band,
+                            void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Gaussian glimpse — modellib.extract_patch (modellib.py:615-641) as called at
+ * full_model.py:788-789:
+ *   x_patch[b,i,j,d] = gamma_attn[b] * sum_{y,x} fy[b,i,y] X[b,y,x,d] fx[b,j,x]
+ * X is given as the two channel groups that the reference concatenates
+ * (full_model.py:645-660): xs [B,H,W,Cs] step-invariant channels and canvas [B,H,W]
+ * (either may be absent: Cs = 0 / canvas = NULL).  chan_map [Cs+1] int32 gives, for every
+ * source channel (xs 0..Cs-1, then the canvas), its channel position in the reference's
+ * concat order.  x_patch [B,F,F,Cs+1].  tmp: caller workspace of B*F*W*(Cs+1) floats.
+ * W must be a multiple of 4.
+ * -------------------------------------------------------------------------------------- */
+int ra_gaussian_extract_f32(const float *xs, int Cs, const float *canvas, const int32_t *chan_map,
+                            const float *box, const float *fy, const float *fx, const int32_t *band, int B, int H,
+                            int W, int F, float *tmp, float *x_patch, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Paste-back — extract_patch(., Fy^T, Fx^T, 1) as used for the attention box
+ * (full_model.py:738-741) and the mask (:810-818), fused with the canvas update (:845):
+ *   attn_box[b,y,x] = sigmoid(gamma_box * sum_ij fy[i,y] fx[j,x] - 5)
+ *   y_out[b,y,x]    = sigmoid(gamma_y * sum_ij fy[i,y] P[b,i,j] fx[j,x] - 5) [* (1-canvas)]
+ *   canvas          = max(canvas, y_out)
+ * patch [B,F,F] (may be NULL: attention box only, box_model.py:484-487); attn_box may be
+ * NULL (mask only).  attn_box / y_out are written at [b*out_bstride + y*W + x]
+ * (out_bstride = T*H*W lets the caller write step t of a [B,T,H,W] stack in place);
+ * canvas [B,H,W] is updated in place.
+ * -------------------------------------------------------------------------------------- */
+int ra_paste_back_f32(const float *patch, const float *box, const float *fy, const float *fx, int B, int H, int W,
+                      int F, int disable_overwrite, float *attn_box, float *y_out, size_t out_bstride, float *canvas,
+                      void *stream);
+
+/* Score head, full_model.py:821-822: s = sigmoid(w . concat(h, core) + b); h [B,Hd],
+ * core [B,Cd] (may be NULL with Cd = 0: box_model.py:508-511), w [Hd+Cd], s_out at
+ * s_out[b*s_stride]. */
+int ra_score_f32(const float *h, int Hd, const float *core, int Cd, const float *w, const float *bias, int B,
+                 float *s_out, int s_stride, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Ground-truth boxes — modellib.get_gt_box (modellib.py:663-701) with get_idx_map /
+ * get_filled_box_idx (:704-749).  y_gt [B,T,H,W] -> top_left [B,T,2], bot_right [B,T,2]
+ * (after the empty-mask fix-up, :697-699), rect [B,T,4] = (tl_y, tl_x, br_y, br_x) BEFORE
+ * the fix-up (what the filled box is drawn from, :694; may be NULL), box [B,T,H,W] (filled
+ * rectangle, may be NULL), area [B,T] = sum of y_gt (may be NULL).
+ * -------------------------------------------------------------------------------------- */
+int ra_gt_box_f32(const float *y_gt, int B, int T, int H, int W, float padding_ratio, float min_padding,
+                  float *top_left, float *bot_right, float *rect, float *box, float *area, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Pairwise soft IoU / DICE — modellib.f_iou(pairwise=True) (modellib.py:138-153) with
+ * f_inter / f_union (:104-114, eps 1e-5 added per pixel) and f_dice (:81-97).
+ * a [B,N,HW], b [B,M,HW] -> iou [B,N,M]; dice (may be NULL) [B,N,M].
+ * hard_threshold > 0 binarises a on the fly (a > thr), full_model.py:1063.
+ * b_rect (may be NULL) [B,M,4] = (tl_y,tl_x,br_y,br_x) as written by ra_gt_box_f32: when
+ * given, b is not read and is taken as the rectangle indicator tl <= idx <= br (the filled
+ * GT boxes of full_model.py:931).  H*W must be a multiple of 4; N, M <= 39.
+ * partial: caller workspace of ra_pairwise_iou_workspace(B,N,M,HW) floats.
+ * -------------------------------------------------------------------------------------- */
+size_t ra_pairwise_iou_workspace(int B, int N, int M, int HW);
+int ra_pairwise_iou_f32(const float *a, const float *b, const float *b_rect, int B, int N, int M, int H, int W,
+                        float hard_threshold, float *partial, float *iou, float *dice, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Loss block — full_model.py:942-1081 (fixed_order = False, loss fns = 'iou'):
+ * scalars out[RA_LOSS_*] from iou matrices, matchings, s_out, s_gt, GT areas.
+ * -------------------------------------------------------------------------------------- */
+#define RA_LOSS_BOX 0
+#define RA_LOSS_SEGM 1
+#define RA_LOSS_CONF 2
+#define RA_LOSS_IOU_SOFT 3
+#define RA_LOSS_IOU_HARD 4
+#define RA_LOSS_WT_COV_SOFT 5
+#define RA_LOSS_UNWT_COV_SOFT 6
+#define RA_LOSS_WT_COV_HARD 7
+#define RA_LOSS_UNWT_COV_HARD 8
+#define RA_LOSS_DICE 9
+#define RA_LOSS_COUNT_ACC 10
+#define RA_LOSS_DIC 11
+#define RA_LOSS_DIC_ABS 12
+#define RA_LOSS_TOTAL 13 /* box + segm + mix*conf + weight_decay_term */
+#define RA_LOSS_COUNT 16
+int ra_loss_block_f32(const float *iou_box, const float *match_box, const float *iou_soft, const float *match,
+                      const float *iou_hard, const float *dice_hard, const float *s_out, const float *s_gt,
+                      const float *gt_area, int B, int T, float loss_mix_ratio, float weight_decay_term,
+                      float *out, void *stream);
+
+/* Greedy GT interaction of box_model.py:484-504 for one decode step: iou_t[b,m] =
+ * f_inter(attn_box_t, box_gt_m)/f_union (rectangle form of box_gt), grd = one-hot of the row
+ * max with ties sharing 1/k (modellib.py:366-379), canvas = max(canvas,
+ * sum_m grd*y_gt_m*(1-noise)).  attn_box_t at attn_box[b*box_bstride + p]; noise may be NULL;
+ * grd_ws: caller workspace of B*T floats (receives the greedy match). */
+int ra_box_gt_step_f32(const float *attn_box, size_t box_bstride, const float *gt_rect, const float *y_gt,
+                       const float *noise, size_t noise_bstride, int B, int T, int H, int W, float *iou_t,
+                       int iou_bstride, float *grd_ws, float *canvas, void *stream);
+
+/* out[b,h,w,:] = concat(a[..,:Ca], b[..,:Cb], c[..,:Cc]) over npix = B*H*W pixels — the
+ * step-invariant part of the input stack of full_model.py:640-661 (Cb, Cc may be 0). */
+int ra_concat_channels_f32(const float *a, int Ca, const float *b, int Cb, const float *c, int Cc, size_t npix,
+                           float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REC_ATTEND_B200_H_ */

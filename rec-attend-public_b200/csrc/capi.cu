@@ -1,0 +1,37 @@
+// Library-level entry points and error plumbing of librecattend_b200.so.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ra {
+
+static thread_local char g_last_error[256] = "";
+
+void set_last_error(const char *what, cudaError_t e) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+}
+
+int finish_launch(const char *what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error(what, e);
+    return RA_ERR_CUDA;
+  }
+  return RA_OK;
+}
+
+}  // namespace ra
+
+extern "C" int ra_version(void) { return 10000 * 0 + 100 * 1 + 0; }
+
+extern "C" int ra_device_count(void) {
+  int n = 0;
+  const cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    ra::set_last_error("cudaGetDeviceCount", e);
+    return 0;
+  }
+  return n;
+}
+
+extern "C" const char *ra_last_error(void) { return ra::g_last_error; }

@@ -1,0 +1,286 @@
+// 3x3 SAME convolution block on CUDA cores (fp32, NHWC), fused with the folded
+// bias + batch-norm(eval) scale/shift, ReLU and 2x2 max-pool epilogue.
+// One kernel serves nnlib.run_cnn (nnlib.py:214-255), nnlib.run_dcnn (nnlib.py:339-402:
+// transposed conv = conv over a zero-inserted input with the flipped filter, skip
+// concat = second input pointer) and the per-step canvas half of the first controller layer
+// (add_to = the step-invariant half, computed once per forward).
+//
+// Tiling: a CTA owns a TH x TW tile of output pixels and CB output channels.  Each thread
+// owns a 2x2 pixel quad (= one max-pool window) x CT output channels, i.e. 4*CT fp32
+// accumulators; a warp spans 32 quads with the SAME channel group so the filter reads are
+// shared-memory broadcasts and the input reads are conflict-free float2's from a
+// channel-planar tile [CK][TH+2][TW+4].  Per input channel a thread issues 8 LDS.64 + 18
+// LDS.128 for 288 FMAs.
+#include "common.cuh"
+
+namespace {
+
+struct ConvParams {
+  const float *x1;
+  const float *x2;
+  const float *w;
+  const float *scale;
+  const float *shift;
+  const float *add_to;
+  float *y;
+  int C1, C2, Cin, Cout;
+  int B, Hin, Win, Hout, Wout;
+  int up, pool, relu;
+  int THG, TWG, NCG, CK;  // quads per tile (rows, cols), channel groups per CTA, channels per chunk
+  int tiles_x, tiles_y, cout_blocks;
+};
+
+template <int CT>
+__global__ void __launch_bounds__(256) conv3x3_kernel(ConvParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int TH = 2 * p.THG, TW = 2 * p.TWG;
+  const int TWP = TW + 4;
+  const int CB = p.NCG * CT;
+  const int in_elems = ((p.CK * (TH + 2) * TWP + 3) / 4) * 4;
+  float *in_s = smem;
+  float *w_s = smem + in_elems;
+
+  int bid = blockIdx.x;
+  const int tile_x = bid % p.tiles_x;
+  bid /= p.tiles_x;
+  const int tile_y = bid % p.tiles_y;
+  bid /= p.tiles_y;
+  const int cob = bid % p.cout_blocks;
+  const int b = bid / p.cout_blocks;
+
+  const int quads = p.THG * p.TWG;
+  const int tid = threadIdx.x;
+  const int pg = tid % quads;
+  const int cg = tid / quads;
+  const int gy = pg / p.TWG, gx = pg % p.TWG;
+  const int oy0 = tile_y * TH, ox0 = tile_x * TW;
+  const int co0 = cob * CB + cg * CT;  // first output channel of this thread
+  const bool co_ok = co0 < p.Cout;
+
+  float acc[4][CT];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < CT; ++j) acc[q][j] = 0.f;
+
+  const int nthreads = blockDim.x;
+  const int tile_elems = (TH + 2) * (TW + 2) * p.CK;
+  const int w_elems = p.CK * 9 * CB;
+
+  for (int c0 = 0; c0 < p.Cin; c0 += p.CK) {
+    __syncthreads();
+    // ---- stage the input tile (channel fastest in global, channel-planar in shared)
+    for (int idx = tid; idx < tile_elems; idx += nthreads) {
+      const int c = idx % p.CK;
+      const int pix = idx / p.CK;
+      const int col = pix % (TW + 2), r = pix / (TW + 2);
+      const int vy = oy0 - p.up + r, vx = ox0 - p.up + col;  // virtual (zero-inserted) coordinates
+      const int cc = c0 + c;
+      float v = 0.f;
+      if (cc < p.Cin && vy >= 0 && vx >= 0 && vy < p.Hout && vx < p.Wout) {
+        int iy = vy, ix = vx;
+        bool on = true;
+        if (p.up == 2) {
+          on = ((vy | vx) & 1) == 0;
+          iy >>= 1;
+          ix >>= 1;
+        }
+        if (on) {
+          const size_t pixoff = ((size_t)b * p.Hin + iy) * p.Win + ix;
+          v = (cc < p.C1) ? __ldg(p.x1 + pixoff * p.C1 + cc) : __ldg(p.x2 + pixoff * p.C2 + (cc - p.C1));
+        }
+      }
+      in_s[(c * (TH + 2) + r) * TWP + col] = v;
+    }
+    // ---- stage the filter slice [CK][9][CB]
+    for (int idx = tid; idx < w_elems; idx += nthreads) {
+      const int cb = idx % CB;
+      const int k = (idx / CB) % 9;
+      const int c = idx / (CB * 9);
+      const int cc = c0 + c, co = cob * CB + cb;
+      float v = 0.f;
+      if (cc < p.Cin && co < p.Cout) v = __ldg(p.w + ((size_t)k * p.Cin + cc) * p.Cout + co);
+      w_s[idx] = v;
+    }
+    __syncthreads();
+
+    if (cg < p.NCG) {
+      const int ck = min(p.CK, p.Cin - c0);
+      for (int c = 0; c < ck; ++c) {
+        const float *ip = in_s + (c * (TH + 2) + 2 * gy) * TWP + 2 * gx;
+        float in[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float2 a = *reinterpret_cast<const float2 *>(ip + r * TWP);
+          const float2 bq = *reinterpret_cast<const float2 *>(ip + r * TWP + 2);
+          in[r][0] = a.x;
+          in[r][1] = a.y;
+          in[r][2] = bq.x;
+          in[r][3] = bq.y;
+        }
+        const float *wp = w_s + (c * 9) * CB + cg * CT;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            float wv[CT];
+            if (CT % 4 == 0) {
+#pragma unroll
+              for (int j = 0; j < CT; j += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(wp + (ky * 3 + kx) * CB + j);
+                wv[j] = t.x;
+                wv[j + 1] = t.y;
+                wv[j + 2] = t.z;
+                wv[j + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CT; ++j) wv[j] = wp[(ky * 3 + kx) * CB + j];
+            }
+#pragma unroll
+            for (int j = 0; j < CT; ++j) {
+              acc[0][j] = fmaf(in[ky][kx], wv[j], acc[0][j]);
+              acc[1][j] = fmaf(in[ky][kx + 1], wv[j], acc[1][j]);
+              acc[2][j] = fmaf(in[ky + 1][kx], wv[j], acc[2][j]);
+              acc[3][j] = fmaf(in[ky + 1][kx + 1], wv[j], acc[3][j]);
+            }
+          }
+      }
+    }
+  }
+
+  // ---- epilogue: (+add_to) * scale + shift, ReLU, 2x2 max-pool
+  if (cg >= p.NCG || !co_ok) return;
+  const int oy = oy0 + 2 * gy, ox = ox0 + 2 * gx;
+  float sc[CT], sh[CT];
+#pragma unroll
+  for (int j = 0; j < CT; ++j) {
+    const bool ok = co0 + j < p.Cout;
+    sc[j] = ok ? p.scale[co0 + j] : 0.f;
+    sh[j] = ok ? p.shift[co0 + j] : 0.f;
+  }
+  float pooled[CT];
+#pragma unroll
+  for (int j = 0; j < CT; ++j) pooled[j] = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int py = oy + (q >> 1), px = ox + (q & 1);
+    if (py >= p.Hout || px >= p.Wout) continue;
+    const size_t off = (((size_t)b * p.Hout + py) * p.Wout + px) * p.Cout + co0;
+#pragma unroll
+    for (int j = 0; j < CT; ++j) {
+      if (co0 + j >= p.Cout) continue;
+      float v = acc[q][j];
+      if (p.add_to != nullptr) v += p.add_to[off + j];
+      v = fmaf(v, sc[j], sh[j]);
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.pool == 2)
+        pooled[j] = fmaxf(pooled[j], v);
+      else
+        p.y[off + j] = v;
+    }
+  }
+  if (p.pool == 2 && oy < p.Hout && ox < p.Wout) {
+    const size_t off = (((size_t)b * (p.Hout / 2) + (oy >> 1)) * (p.Wout / 2) + (ox >> 1)) * p.Cout + co0;
+#pragma unroll
+    for (int j = 0; j < CT; ++j)
+      if (co0 + j < p.Cout) p.y[off + j] = pooled[j];
+  }
+}
+
+// out[b,h,w,:] = concat(a[b,h,w,:Ca], bsrc[...,:Cb], c[...,:Cc]) — builds the step-invariant
+// input stack of full_model.py:640-661 once per forward.
+__global__ void concat_channels_kernel(const float *__restrict__ a, int Ca, const float *__restrict__ bsrc, int Cb,
+                                       const float *__restrict__ c, int Cc, size_t npix, float *__restrict__ out) {
+  const int Ct = Ca + Cb + Cc;
+  const size_t total = npix * Ct;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / Ct;
+    const int ch = (int)(i - pix * Ct);
+    float v;
+    if (ch < Ca)
+      v = a[pix * Ca + ch];
+    else if (ch < Ca + Cb)
+      v = bsrc[pix * Cb + (ch - Ca)];
+    else
+      v = c[pix * Cc + (ch - Ca - Cb)];
+    out[i] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int ra_conv3x3_f32(const float *x1, int C1, const float *x2, int C2, const float *w, const float *scale,
+                              const float *shift, const float *add_to, int B, int Hin, int Win, int Cout, int upsample,
+                              int pool, int relu, float *y, void *stream) {
+  if (!x1 || !w || !scale || !shift || !y || C1 < 1 || C2 < 0 || (C2 > 0 && !x2) || B < 0 || Hin < 1 || Win < 1 ||
+      Cout < 1)
+    return RA_ERR_INVALID_ARG;
+  if ((upsample != 1 && upsample != 2) || (pool != 1 && pool != 2)) return RA_ERR_UNSUPPORTED;
+  ConvParams p;
+  p.x1 = x1;
+  p.x2 = x2;
+  p.w = w;
+  p.scale = scale;
+  p.shift = shift;
+  p.add_to = add_to;
+  p.y = y;
+  p.C1 = C1;
+  p.C2 = C2;
+  p.Cin = C1 + C2;
+  p.Cout = Cout;
+  p.B = B;
+  p.Hin = Hin;
+  p.Win = Win;
+  p.Hout = Hin * upsample;
+  p.Wout = Win * upsample;
+  p.up = upsample;
+  p.pool = pool;
+  p.relu = relu;
+  if (pool == 2 && ((p.Hout | p.Wout) & 1)) return RA_ERR_UNSUPPORTED;  // even sizes only
+  if (B == 0) return RA_OK;
+
+  const bool ct8 = (Cout % 8) == 0;
+  const int CT = ct8 ? 8 : 1;
+  const int groups = (Cout + CT - 1) / CT;
+  if (p.Hout >= 64 && p.Wout >= 64) {
+    p.THG = 8;
+    p.TWG = 16;
+  } else if (p.Wout >= 32) {
+    p.THG = 4;
+    p.TWG = 16;
+  } else {
+    p.THG = 4;
+    p.TWG = 8;
+  }
+  const int quads = p.THG * p.TWG;
+  p.NCG = 256 / quads;
+  if (p.NCG > groups) p.NCG = groups;
+  p.CK = p.Cin < 8 ? p.Cin : 8;
+  const int TH = 2 * p.THG, TW = 2 * p.TWG, CB = p.NCG * CT;
+  p.tiles_x = (p.Wout + TW - 1) / TW;
+  p.tiles_y = (p.Hout + TH - 1) / TH;
+  p.cout_blocks = (Cout + CB - 1) / CB;
+  const size_t in_elems = ((size_t)(p.CK * (TH + 2) * (TW + 4) + 3) / 4) * 4;
+  const size_t smem = (in_elems + (size_t)p.CK * 9 * CB) * sizeof(float);
+  const long long nblocks = (long long)p.tiles_x * p.tiles_y * p.cout_blocks * B;
+  if (nblocks > 0x7fffffffLL) return RA_ERR_UNSUPPORTED;
+  const int threads = quads * p.NCG;
+  cudaStream_t s = ra::as_stream(stream);
+  if (ct8)
+    conv3x3_kernel<8><<<(unsigned)nblocks, threads, smem, s>>>(p);
+  else
+    conv3x3_kernel<1><<<(unsigned)nblocks, threads, smem, s>>>(p);
+  return ra::finish_launch("conv3x3_kernel");
+}
+
+extern "C" int ra_concat_channels_f32(const float *a, int Ca, const float *b, int Cb, const float *c, int Cc,
+                                      size_t npix, float *out, void *stream) {
+  if (!a || Ca < 1 || Cb < 0 || Cc < 0 || (Cb > 0 && !b) || (Cc > 0 && !c) || !out) return RA_ERR_INVALID_ARG;
+  if (npix == 0) return RA_OK;
+  const size_t total = npix * (size_t)(Ca + Cb + Cc);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ra::kNumSMs * 16) blocks = (size_t)ra::kNumSMs * 16;
+  concat_channels_kernel<<<(unsigned)blocks, 256, 0, ra::as_stream(stream)>>>(a, Ca, b, Cb, c, Cc, npix, out);
+  return ra::finish_launch("concat_channels_kernel");
+}

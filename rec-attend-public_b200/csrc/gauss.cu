@@ -1,0 +1,331 @@
+// DRAW-style separable Gaussian attention: filter construction, glimpse extraction and
+// paste-back — modellib.get_gaussian_filter (modellib.py:581-612), modellib.extract_patch
+// (:615-641) as used at full_model.py:728-741 (attention box), :788-789 (glimpse) and
+// :810-818,845 (mask paste-back + canvas update).
+//
+// The reference materialises dense [B,L,F] filters and runs 2 batched GEMMs per channel.
+// Here the filters are built once per step as tap-major profiles fy [B,F,H], fx [B,F,W]
+// together with each tap's support band: entries with exp argument below -kCut are exactly
+// zero (their sum over a whole row is below fp32 resolution of the kept terms), so every
+// consumer only walks the band — the work is proportional to sigma, the HBM traffic to one
+// pass over the image.
+//   glimpse:   tmp[b,i,(x,d)] = sum_{y in band_i} fy[i,y] X[b,y,(x,d)]         (row pass)
+//              patch[b,i,j,d] = gamma * sum_{x in band_j} tmp[b,i,(x,d)] fx[j,x]  (column pass)
+//   paste-back: out[b,y,x] = sum_j (sum_i fy[i,y] P[i,j]) fx[j,x], then the fused epilogue.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kCut = 30.0f;  // drop filter entries below exp(-30) ~ 9e-14 of the tap's peak
+constexpr int kMaxF = 64;
+
+// ------------------------------------------------------------------ filter construction
+__global__ void build_filters_kernel(const float *__restrict__ box, int H, int W, int F, float *__restrict__ fy,
+                                     float *__restrict__ fx, int *__restrict__ band) {
+  const int b = blockIdx.x;
+  const float *bo = box + (size_t)b * RA_BOX_STRIDE;
+  for (int axis = 0; axis < 2; ++axis) {
+    const int L = axis == 0 ? H : W;
+    float *f = axis == 0 ? fy + (size_t)b * F * H : fx + (size_t)b * F * W;
+    const float ctr = bo[RA_BOX_CTR_Y + axis];
+    const float size = bo[RA_BOX_SIZE_Y + axis];
+    const float var = expf(bo[RA_BOX_LGVAR_Y + axis]);
+    // modellib.py:610: 1 / sqrt(exp(lg_var)) / sqrt(2*pi)
+    const float norm = 1.0f / sqrtf(var) / sqrtf(2.0f * 3.14159265358979323846f);
+    const float step = (size + 1.0f) / (float)F;  // modellib.py:599
+    for (int idx = threadIdx.x; idx < F * L; idx += blockDim.x) {
+      const int t = idx / L, l = idx - t * L;
+      const float mu = ctr + step * ((float)t - (float)(F - 1) / 2.0f);
+      const float d = (float)l - mu;
+      const float e = ((-0.5f * d) * d) / var;  // modellib.py:611
+      f[idx] = (e >= -kCut) ? norm * expf(e) : 0.f;
+    }
+    // support band of every tap (a superset of the non-zero entries; empty if hi < lo)
+    for (int t = threadIdx.x; t < F; t += blockDim.x) {
+      const float mu = ctr + step * ((float)t - (float)(F - 1) / 2.0f);
+      const float R = sqrtf(2.0f * var * kCut) + 1.0f;
+      float lo = ceilf(mu - R), hi = floorf(mu + R);
+      int ilo = 0, ihi = L - 1;
+      if (lo == lo && hi == hi) {  // not NaN
+        lo = fminf(fmaxf(lo, 0.f), (float)L);
+        hi = fmaxf(fminf(hi, (float)(L - 1)), -1.f);
+        ilo = (int)lo;
+        ihi = (int)hi;
+      }
+      int *bd = band + (((size_t)b * 2 + axis) * F + t) * 2;
+      bd[0] = ilo;
+      bd[1] = ihi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ glimpse: row pass
+// src viewed as [B][H][rowlen] (rowlen = W*D, any D); tmp [B][F][rowlen].
+// grid (chunks of 4*blockDim floats, F/IB tap groups, B).
+template <int IB>
+__global__ void __launch_bounds__(128) extract_rows_kernel(const float *__restrict__ src, int H, int rowlen,
+                                                           const float *__restrict__ fy, const int *__restrict__ band,
+                                                           int F, float *__restrict__ tmp) {
+  extern __shared__ float wsm[];  // [IB][H]
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * IB;
+  const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int *bd = band + ((size_t)b * 2 + 0) * F * 2;
+  int ylo = H, yhi = -1;
+#pragma unroll
+  for (int k = 0; k < IB; ++k) {
+    if (i0 + k < F) {
+      const int lo = bd[(i0 + k) * 2], hi = bd[(i0 + k) * 2 + 1];
+      if (hi >= lo) {
+        ylo = min(ylo, lo);
+        yhi = max(yhi, hi);
+      }
+    }
+  }
+  const int ny = yhi - ylo + 1;
+  for (int idx = threadIdx.x; idx < IB * max(ny, 0); idx += blockDim.x) {
+    const int k = idx / ny, yy = idx - k * ny;
+    wsm[k * H + yy] = (i0 + k < F) ? fy[((size_t)b * F + i0 + k) * H + ylo + yy] : 0.f;
+  }
+  __syncthreads();
+  if (e0 >= rowlen) return;
+
+  float4 acc[IB];
+#pragma unroll
+  for (int k = 0; k < IB; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float *sp = src + ((size_t)b * H + ylo) * rowlen + e0;
+  int yy = 0;
+  for (; yy + 2 <= ny; yy += 2) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(sp + (size_t)yy * rowlen));
+    const float4 v1 = __ldg(reinterpret_cast<const float4 *>(sp + (size_t)(yy + 1) * rowlen));
+#pragma unroll
+    for (int k = 0; k < IB; ++k) {
+      const float w0 = wsm[k * H + yy], w1 = wsm[k * H + yy + 1];
+      acc[k].x = fmaf(w0, v0.x, acc[k].x);
+      acc[k].y = fmaf(w0, v0.y, acc[k].y);
+      acc[k].z = fmaf(w0, v0.z, acc[k].z);
+      acc[k].w = fmaf(w0, v0.w, acc[k].w);
+      acc[k].x = fmaf(w1, v1.x, acc[k].x);
+      acc[k].y = fmaf(w1, v1.y, acc[k].y);
+      acc[k].z = fmaf(w1, v1.z, acc[k].z);
+      acc[k].w = fmaf(w1, v1.w, acc[k].w);
+    }
+  }
+  for (; yy < ny; ++yy) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(sp + (size_t)yy * rowlen));
+#pragma unroll
+    for (int k = 0; k < IB; ++k) {
+      const float w0 = wsm[k * H + yy];
+      acc[k].x = fmaf(w0, v0.x, acc[k].x);
+      acc[k].y = fmaf(w0, v0.y, acc[k].y);
+      acc[k].z = fmaf(w0, v0.z, acc[k].z);
+      acc[k].w = fmaf(w0, v0.w, acc[k].w);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < IB; ++k)
+    if (i0 + k < F) *reinterpret_cast<float4 *>(tmp + ((size_t)b * F + i0 + k) * rowlen + e0) = acc[k];
+}
+
+// ------------------------------------------------------------------ glimpse: column pass
+// grid (F taps i, B); slab [W][D] of tmp rows in the reference's channel order.
+__global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restrict__ tmp_s, int Cs,
+                                                           const float *__restrict__ tmp_c,
+                                                           const int *__restrict__ chan_map,
+                                                           const float *__restrict__ fx, const int *__restrict__ band,
+                                                           const float *__restrict__ box, int W, int F,
+                                                           float *__restrict__ patch) {
+  extern __shared__ float slab[];  // [W][D]
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int D = Cs + (tmp_c != nullptr ? 1 : 0);
+  if (Cs > 0) {
+    const float *ts = tmp_s + ((size_t)b * F + i) * (size_t)W * Cs;
+    for (int idx = threadIdx.x; idx < W * Cs; idx += blockDim.x) {
+      const int x = idx / Cs, c = idx - x * Cs;
+      slab[x * D + chan_map[c]] = ts[idx];
+    }
+  }
+  if (tmp_c != nullptr) {
+    const float *tc = tmp_c + ((size_t)b * F + i) * W;
+    const int cc = chan_map[Cs];
+    for (int x = threadIdx.x; x < W; x += blockDim.x) slab[x * D + cc] = tc[x];
+  }
+  __syncthreads();
+  const float gamma = box[(size_t)b * RA_BOX_STRIDE + RA_BOX_GAMMA_ATTN];
+  const int *bd = band + ((size_t)b * 2 + 1) * F * 2;
+  const float *fxb = fx + (size_t)b * F * W;
+  for (int idx = threadIdx.x; idx < F * D; idx += blockDim.x) {
+    const int j = idx / D, d = idx - j * D;
+    const int lo = bd[j * 2], hi = bd[j * 2 + 1];
+    float a0 = 0.f, a1 = 0.f;
+    int x = lo;
+    for (; x + 1 <= hi; x += 2) {
+      a0 = fmaf(slab[x * D + d], fxb[(size_t)j * W + x], a0);
+      a1 = fmaf(slab[(x + 1) * D + d], fxb[(size_t)j * W + x + 1], a1);
+    }
+    if (x <= hi) a0 = fmaf(slab[x * D + d], fxb[(size_t)j * W + x], a0);
+    patch[(((size_t)b * F + i) * F + j) * D + d] = gamma * (a0 + a1);  // full_model.py:788
+  }
+}
+
+// ------------------------------------------------------------------ paste-back
+constexpr int kPbTY = 8;
+constexpr int kPbTX = 128;
+
+__global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict__ patch,
+                                                         const float *__restrict__ fy, const float *__restrict__ fx,
+                                                         const float *__restrict__ box, int H, int W, int F,
+                                                         int disable_overwrite, float *__restrict__ attn_box,
+                                                         float *__restrict__ y_out, size_t out_bstride,
+                                                         float *__restrict__ canvas) {
+  __shared__ float P_s[kMaxF * kMaxF];       // patch [F][F]
+  __shared__ float wy_s[kPbTY][kMaxF];       // fy[i][y] for the tile rows
+  __shared__ float t2_s[kPbTY][kMaxF + 1];   // sum_i fy[i][y] P[i][j]
+  __shared__ float sy_s[kPbTY];              // sum_i fy[i][y]
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * kPbTY, x0 = blockIdx.x * kPbTX;
+  const int tid = threadIdx.x;
+  const float *bo = box + (size_t)b * RA_BOX_STRIDE;
+  const bool has_patch = patch != nullptr;
+
+  if (has_patch)
+    for (int idx = tid; idx < F * F; idx += blockDim.x) P_s[idx] = patch[(size_t)b * F * F + idx];
+  for (int idx = tid; idx < kPbTY * F; idx += blockDim.x) {
+    const int ty = idx / F, i = idx - ty * F;
+    const int y = y0 + ty;
+    wy_s[ty][i] = (y < H) ? fy[((size_t)b * F + i) * H + y] : 0.f;
+  }
+  __syncthreads();
+  if (has_patch) {
+    for (int idx = tid; idx < kPbTY * F; idx += blockDim.x) {
+      const int ty = idx / F, j = idx - ty * F;
+      float a = 0.f;
+      for (int i = 0; i < F; ++i) a = fmaf(wy_s[ty][i], P_s[i * F + j], a);
+      t2_s[ty][j] = a;
+    }
+  }
+  if (tid < kPbTY) {
+    float a = 0.f;
+    for (int i = 0; i < F; ++i) a += wy_s[tid][i];
+    sy_s[tid] = a;
+  }
+  __syncthreads();
+
+  const int col = tid % kPbTX, rh = tid / kPbTX;  // 2 row-halves of 4 rows
+  const int x = x0 + col;
+  // taps whose band can reach column x (analytic superset; entries outside a band are 0)
+  int jlo = 0, jhi = F - 1;
+  {
+    const float ctr = bo[RA_BOX_CTR_X], size = bo[RA_BOX_SIZE_X];
+    const float var = expf(bo[RA_BOX_LGVAR_X]);
+    const float step = (size + 1.0f) / (float)F;
+    const float R = sqrtf(2.0f * var * kCut) + 1.0f;
+    const float half = (float)(F - 1) / 2.0f;
+    const float a = ((float)x - R - ctr) / step + half, c = ((float)x + R - ctr) / step + half;
+    if (a == a && c == c && fabsf(a) < 1e9f && fabsf(c) < 1e9f) {
+      jlo = max(0, (int)floorf(a));
+      jhi = min(F - 1, (int)ceilf(c));
+    }
+  }
+  // warp-uniform tap range so that t2_s reads are broadcasts
+  for (int o = 16; o > 0; o >>= 1) {
+    jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+    jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+  }
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float sx = 0.f;
+  if (x < W) {
+    const float *fxp = fx + (size_t)b * F * W + x;
+    for (int j = jlo; j <= jhi; ++j) {
+      const float wx = __ldg(fxp + (size_t)j * W);
+      sx += wx;
+      if (has_patch) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(t2_s[rh * 4 + r][j], wx, acc[r]);
+      }
+    }
+    const float g_box = bo[RA_BOX_GAMMA_BOX], g_y = bo[RA_BOX_GAMMA_Y];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int y = y0 + rh * 4 + r;
+      if (y >= H) continue;
+      const size_t pix = (size_t)y * W + x;
+      if (attn_box != nullptr)  // full_model.py:738-741
+        attn_box[(size_t)b * out_bstride + pix] = ra::sigmoidf_acc(g_box * (sy_s[rh * 4 + r] * sx) - 5.0f);
+      if (has_patch) {  // full_model.py:810-818, 845
+        const size_t cpix = (size_t)b * H * W + pix;
+        const float cv = canvas[cpix];
+        float v = ra::sigmoidf_acc(g_y * acc[r] - 5.0f);
+        if (disable_overwrite) v *= (1.0f - cv);
+        y_out[(size_t)b * out_bstride + pix] = v;
+        canvas[cpix] = fmaxf(cv, v);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ra_gaussian_filters_f32(const float *box, int B, int H, int W, int F, float *fy, float *fx,
+                                       int32_t *band, void *stream) {
+  if (!box || !fy || !fx || !band || B < 0 || H < 1 || W < 1 || F < 1) return RA_ERR_INVALID_ARG;
+  if (F > kMaxF) return RA_ERR_UNSUPPORTED;
+  if (B == 0) return RA_OK;
+  build_filters_kernel<<<B, 256, 0, ra::as_stream(stream)>>>(box, H, W, F, fy, fx, band);
+  return ra::finish_launch("build_filters_kernel");
+}
+
+extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *canvas, const int32_t *chan_map,
+                                       const float *box, const float *fy, const float *fx, const int32_t *band, int B,
+                                       int H, int W, int F, float *tmp, float *x_patch, void *stream) {
+  if (!chan_map || !box || !fy || !fx || !band || !tmp || !x_patch || B < 0 || Cs < 0 || (Cs > 0 && !xs) ||
+      (Cs == 0 && !canvas))
+    return RA_ERR_INVALID_ARG;
+  if (F > kMaxF || (W % 4) != 0) return RA_ERR_UNSUPPORTED;
+  if (B == 0) return RA_OK;
+  cudaStream_t s = ra::as_stream(stream);
+  constexpr int IB = 4;
+  const int groups = (F + IB - 1) / IB;
+  float *tmp_s = tmp;
+  float *tmp_c = tmp + (size_t)B * F * W * Cs;
+  const size_t smem_rows = (size_t)IB * H * sizeof(float);
+  if (Cs > 0) {
+    const int rowlen = W * Cs;
+    dim3 grid((rowlen / 4 + 127) / 128, groups, B);
+    extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(xs, H, rowlen, fy, band, F, tmp_s);
+  }
+  if (canvas != nullptr) {
+    dim3 grid((W / 4 + 127) / 128, groups, B);
+    extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(canvas, H, W, fy, band, F, tmp_c);
+  }
+  const int D = Cs + (canvas != nullptr ? 1 : 0);
+  const size_t smem_cols = (size_t)W * D * sizeof(float);
+  if (smem_cols > 200 * 1024) return RA_ERR_UNSUPPORTED;
+  static size_t attr_bytes = 48 * 1024;
+  if (smem_cols > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(extract_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      ra::set_last_error("cudaFuncSetAttribute(extract_cols_kernel)", e);
+      return RA_ERR_CUDA;
+    }
+    attr_bytes = 200 * 1024;
+  }
+  extract_cols_kernel<<<dim3(F, B), 256, smem_cols, s>>>(Cs > 0 ? tmp_s : nullptr, Cs,
+                                                         canvas != nullptr ? tmp_c : nullptr, chan_map, fx, band, box,
+                                                         W, F, x_patch);
+  return ra::finish_launch("gaussian_extract");
+}
+
+extern "C" int ra_paste_back_f32(const float *patch, const float *box, const float *fy, const float *fx, int B, int H,
+                                 int W, int F, int disable_overwrite, float *attn_box, float *y_out,
+                                 size_t out_bstride, float *canvas, void *stream) {
+  if (!box || !fy || !fx || B < 0 || H < 1 || W < 1) return RA_ERR_INVALID_ARG;
+  if (patch != nullptr && (!y_out || !canvas)) return RA_ERR_INVALID_ARG;
+  if (patch == nullptr && attn_box == nullptr) return RA_ERR_INVALID_ARG;
+  if (F > kMaxF) return RA_ERR_UNSUPPORTED;
+  if (B == 0) return RA_OK;
+  dim3 grid((W + kPbTX - 1) / kPbTX, (H + kPbTY - 1) / kPbTY, B);
+  paste_back_kernel<<<grid, 256, 0, ra::as_stream(stream)>>>(patch, fy, fx, box, H, W, F, disable_overwrite, attn_box,
+                                                             y_out, out_bstride, canvas);
+  return ra::finish_launch("paste_back_kernel");
+}

@@ -1,0 +1,530 @@
+// Loss-side kernels of the hot path: ground-truth attention boxes, pairwise soft IoU / DICE,
+// the scalar loss block, the score head and the box model's per-step ground-truth interaction.
+// modellib.py:71-155 (f_dice/f_inter/f_union/f_iou), :268-339 (coverage, conf loss),
+// :366-379 (greedy match), :482-511 (count metrics), :663-749 (GT boxes);
+// full_model.py:821-822 (score), :916-1081 (loss block); box_model.py:484-504.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ GT boxes
+// One CTA per (b,t) mask: a single pass for the four index extrema and the area, then the
+// padded rectangle and (optionally) the filled box.  The reference materialises five
+// [B,T,H,W,2] temporaries for this (modellib.py:679-686,745-747).
+__global__ void __launch_bounds__(256) gt_box_kernel(const float *__restrict__ y_gt, int H, int W, float padding_ratio,
+                                                     float min_padding, float *__restrict__ top_left,
+                                                     float *__restrict__ bot_right, float *__restrict__ rect,
+                                                     float *__restrict__ box, float *__restrict__ area) {
+  __shared__ float red[32];
+  __shared__ float res[8];
+  const size_t m = blockIdx.x;
+  const float *g = y_gt + m * (size_t)H * W;
+  const float hw = (float)(H * W);
+  float mny = INFINITY, mnx = INFINITY, mxy = -INFINITY, mxx = -INFINITY, sum = 0.f;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const float v = g[i];
+    const float fy = (float)(i / W), fx = (float)(i % W);
+    const float off = (1.0f - v) * hw;  // modellib.py:682-683
+    mny = fminf(mny, fy + off);
+    mnx = fminf(mnx, fx + off);
+    mxy = fmaxf(mxy, fy * v);
+    mxx = fmaxf(mxx, fx * v);
+    sum += v;
+  }
+  mny = ra::block_min(mny, red);
+  mnx = ra::block_min(mnx, red);
+  mxy = ra::block_max(mxy, red);
+  mxx = ra::block_max(mxx, red);
+  sum = ra::block_sum(sum, red);
+  if (threadIdx.x == 0) {
+    float tl[2] = {mny, mnx}, br[2] = {mxy, mxx};
+    const float nz = sum > 0.f ? 1.f : 0.f;
+    for (int d = 0; d < 2; ++d) {
+      const float size = br[d] - tl[d];
+      const float pad = fmaxf(padding_ratio * size, min_padding);  // modellib.py:689-693 (shift ratio 0)
+      tl[d] -= pad;
+      br[d] += pad;
+      res[d] = tl[d];
+      res[2 + d] = br[d];
+      top_left[m * 2 + d] = tl[d] * nz;  // modellib.py:697-699
+      bot_right[m * 2 + d] = nz * br[d] + (1.f - nz) * (2.f * min_padding);
+    }
+    if (rect != nullptr) {
+      rect[m * 4 + 0] = tl[0];
+      rect[m * 4 + 1] = tl[1];
+      rect[m * 4 + 2] = br[0];
+      rect[m * 4 + 3] = br[1];
+    }
+    if (area != nullptr) area[m] = sum;
+  }
+  if (box == nullptr) return;
+  __syncthreads();
+  const float ty = res[0], tx = res[1], by = res[2], bx = res[3];
+  float *o = box + m * (size_t)H * W;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const float fy = (float)(i / W), fx = (float)(i % W);
+    o[i] = (fy >= ty && fx >= tx && fy <= by && fx <= bx) ? 1.f : 0.f;  // modellib.py:745-747
+  }
+}
+
+// ------------------------------------------------------------------ pairwise IoU
+// C[n][m] = sum_k A[n][k] B[m][k] with a ones row appended to both operands, so row N / column
+// M of C carry sum(b_m) / sum(a_n).  Split-K over the pixels: a CTA stages KC pixels of all
+// rows in shared memory; thread (nb, mb, ks) owns a 6x6 block of C over its k-slice.
+constexpr int kR = 6;     // register block
+constexpr int kKC = 256;  // pixels per staged chunk
+constexpr int kPad = 4;
+
+struct IouParams {
+  const float *a;
+  const float *b;
+  const float *b_rect;
+  float *partial;
+  int N, M, H, W;
+  int NB, MB;    // register blocks along n and m
+  int KS;        // k-slices per CTA
+  int chunks_per_cta;
+  int ctas_per_ex;
+  float hard_thr;
+};
+
+__global__ void __launch_bounds__(256) pairwise_iou_kernel(IouParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int NP = p.NB * kR, MP = p.MB * kR;
+  const int ld = kKC + kPad;
+  float *A_s = smem;            // [NP][ld]
+  float *B_s = smem + NP * ld;  // [MP][ld]
+  const int b = blockIdx.y;
+  const int HW = p.H * p.W;
+  const int tid = threadIdx.x;
+  const int ks = tid % p.KS;
+  const int blk = tid / p.KS;
+  const int nb = blk / p.MB, mb = blk % p.MB;
+  const bool active = blk < p.NB * p.MB;
+
+  float acc[kR][kR];
+#pragma unroll
+  for (int i = 0; i < kR; ++i)
+#pragma unroll
+    for (int j = 0; j < kR; ++j) acc[i][j] = 0.f;
+
+  const int chunk0 = blockIdx.x * p.chunks_per_cta;
+  for (int ch = 0; ch < p.chunks_per_cta; ++ch) {
+    const int k0 = (chunk0 + ch) * kKC;
+    if (k0 >= HW) break;
+    __syncthreads();
+    // stage A rows (N real rows, the ones row, zero padding)
+    for (int idx = tid; idx < NP * (kKC / 4); idx += blockDim.x) {
+      const int r = idx / (kKC / 4), q = (idx - r * (kKC / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = k0 + q;
+      if (k < HW) {
+        if (r < p.N) {
+          v = __ldcs(reinterpret_cast<const float4 *>(p.a + ((size_t)b * p.N + r) * HW + k));
+          if (p.hard_thr > 0.f) {
+            v.x = v.x > p.hard_thr ? 1.f : 0.f;
+            v.y = v.y > p.hard_thr ? 1.f : 0.f;
+            v.z = v.z > p.hard_thr ? 1.f : 0.f;
+            v.w = v.w > p.hard_thr ? 1.f : 0.f;
+          }
+        } else if (r == p.N) {
+          v = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      }
+      *reinterpret_cast<float4 *>(A_s + r * ld + q) = v;
+    }
+    for (int idx = tid; idx < MP * (kKC / 4); idx += blockDim.x) {
+      const int r = idx / (kKC / 4), q = (idx - r * (kKC / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = k0 + q;
+      if (k < HW) {
+        if (r < p.M) {
+          if (p.b_rect != nullptr) {
+            const float *rc = p.b_rect + ((size_t)b * p.M + r) * 4;
+            const float ty = rc[0], tx = rc[1], by = rc[2], bx = rc[3];
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float fy = (float)((k + e) / p.W), fx = (float)((k + e) % p.W);
+              o[e] = (fy >= ty && fx >= tx && fy <= by && fx <= bx) ? 1.f : 0.f;
+            }
+            v = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            v = __ldcs(reinterpret_cast<const float4 *>(p.b + ((size_t)b * p.M + r) * HW + k));
+          }
+        } else if (r == p.M) {
+          v = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      }
+      *reinterpret_cast<float4 *>(B_s + r * ld + q) = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int q = ks * 4; q < kKC; q += p.KS * 4) {
+        float4 av[kR], bv[kR];
+#pragma unroll
+        for (int i = 0; i < kR; ++i) av[i] = *reinterpret_cast<const float4 *>(A_s + (nb * kR + i) * ld + q);
+#pragma unroll
+        for (int j = 0; j < kR; ++j) bv[j] = *reinterpret_cast<const float4 *>(B_s + (mb * kR + j) * ld + q);
+#pragma unroll
+        for (int i = 0; i < kR; ++i)
+#pragma unroll
+          for (int j = 0; j < kR; ++j) {
+            acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
+            acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
+            acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
+            acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+          }
+      }
+    }
+  }
+  // reduce the KS k-slices of every (nb, mb) block through shared memory, fixed order
+  __syncthreads();
+  float *red = smem;  // [blocks][KS][36] fits: blocks*KS <= 256 -> 256*36 floats
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < kR; ++i)
+#pragma unroll
+      for (int j = 0; j < kR; ++j) red[((size_t)blk * p.KS + ks) * (kR * kR) + i * kR + j] = acc[i][j];
+  }
+  __syncthreads();
+  float *out = p.partial + ((size_t)b * p.ctas_per_ex + blockIdx.x) * NP * MP;
+  for (int idx = tid; idx < NP * MP; idx += blockDim.x) {
+    const int n = idx / MP, m = idx - n * MP;
+    const int bk = (n / kR) * p.MB + (m / kR);
+    const int e = (n % kR) * kR + (m % kR);
+    float s = 0.f;
+    for (int k = 0; k < p.KS; ++k) s += red[((size_t)bk * p.KS + k) * (kR * kR) + e];
+    out[idx] = s;
+  }
+}
+
+__global__ void pairwise_iou_finalize_kernel(const float *__restrict__ partial, int N, int M, int NP, int MP,
+                                             int ctas_per_ex, float hw_eps, float *__restrict__ iou,
+                                             float *__restrict__ dice) {
+  const int b = blockIdx.x;
+  __shared__ float C[40 * 40];
+  for (int idx = threadIdx.x; idx < NP * MP; idx += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < ctas_per_ex; ++c) s += partial[((size_t)b * ctas_per_ex + c) * NP * MP + idx];
+    C[idx] = s;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
+    const int n = idx / M, m = idx - n * M;
+    const float inter = C[n * MP + m];
+    const float sa = C[n * MP + M];  // a_n . ones
+    const float sb = C[N * MP + m];  // ones . b_m
+    // modellib.py:110-114: sum(a + b - a*b + eps) over the pixels
+    iou[((size_t)b * N + n) * M + m] = inter / (sa + sb - inter + hw_eps);
+    // modellib.py:90-95: 2*inter / (sum(a + 1e-5) + sum(b + 1e-5))
+    if (dice != nullptr) dice[((size_t)b * N + n) * M + m] = 2.f * inter / ((sa + hw_eps) + (sb + hw_eps));
+  }
+}
+
+// ------------------------------------------------------------------ loss block
+__global__ void __launch_bounds__(256) loss_block_kernel(const float *__restrict__ iou_box,
+                                                         const float *__restrict__ match_box,
+                                                         const float *__restrict__ iou_soft,
+                                                         const float *__restrict__ match,
+                                                         const float *__restrict__ iou_hard,
+                                                         const float *__restrict__ dice_hard,
+                                                         const float *__restrict__ s_out,
+                                                         const float *__restrict__ s_gt,
+                                                         const float *__restrict__ gt_area, int B, int T,
+                                                         float mix, float wd_term, float *__restrict__ out) {
+  __shared__ float red[32];
+  float v[RA_LOSS_COUNT];
+#pragma unroll
+  for (int k = 0; k < RA_LOSS_COUNT; ++k) v[k] = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const size_t o2 = (size_t)b * T * T, o1 = (size_t)b * T;
+    float s_ib = 0.f, c_b = 0.f, s_is = 0.f, c_s = 0.f, s_ih = 0.f, s_d = 0.f;
+    for (int k = 0; k < T * T; ++k) {
+      const float mb = match_box[o2 + k], ms = match[o2 + k];
+      s_ib += iou_box[o2 + k] * mb;
+      c_b += mb;
+      s_is += iou_soft[o2 + k] * ms;
+      c_s += ms;
+      if (iou_hard != nullptr) s_ih += iou_hard[o2 + k] * ms;
+      if (dice_hard != nullptr) s_d += dice_hard[o2 + k] * ms;
+    }
+    c_b = fmaxf(c_b, 1.f);  // full_model.py:944,994
+    c_s = fmaxf(c_s, 1.f);
+    v[RA_LOSS_BOX] -= s_ib / c_b;
+    v[RA_LOSS_IOU_SOFT] += s_is / c_s;
+    v[RA_LOSS_IOU_HARD] += s_ih / c_s;
+    v[RA_LOSS_DICE] += s_d / c_s;
+    // coverage (modellib.py:268-313)
+    float tot = 0.f;
+    for (int m = 0; m < T; ++m) tot += gt_area[o1 + m];
+    float wcs = 0.f, ucs = 0.f, wch = 0.f, uch = 0.f;
+    for (int m = 0; m < T; ++m) {
+      float cs = -INFINITY, chd = -INFINITY;
+      for (int n = 0; n < T; ++n) {
+        cs = fmaxf(cs, iou_soft[o2 + n * T + m]);
+        if (iou_hard != nullptr) chd = fmaxf(chd, iou_hard[o2 + n * T + m]);
+      }
+      const float ar = gt_area[o1 + m];
+      const float wt = ar / (tot + (ar == 0.f ? 1.f : 0.f));
+      wcs += cs * wt;
+      ucs += cs;
+      if (iou_hard != nullptr) {
+        wch += chd * wt;
+        uch += chd;
+      }
+    }
+    v[RA_LOSS_WT_COV_SOFT] += wcs;
+    v[RA_LOSS_UNWT_COV_SOFT] += ucs / c_s;
+    v[RA_LOSS_WT_COV_HARD] += wch;
+    v[RA_LOSS_UNWT_COV_HARD] += uch / c_s;
+    // confidence loss with cumulative min / reversed cumulative max (modellib.py:316-339,430-437)
+    float conf = 0.f;
+    {
+      float run_min = INFINITY;
+      float cnt_out = 0.f, cnt_gt = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const float s = s_out[o1 + t];
+        run_min = fminf(run_min, s);
+        float gsum = 0.f;
+        for (int m = 0; m < T; ++m) gsum += match[o2 + t * T + m];
+        float run_max = -INFINITY;
+        for (int u = t; u < T; ++u) run_max = fmaxf(run_max, s_out[o1 + u]);
+        conf += -gsum * logf(run_min + 1e-5f) - (1.f - gsum) * logf(1.f - run_max + 1e-5f);
+        cnt_out += s > 0.5f ? 1.f : 0.f;
+        cnt_gt += s_gt[o1 + t];
+      }
+      v[RA_LOSS_COUNT_ACC] += (cnt_out == cnt_gt) ? 1.f : 0.f;
+      v[RA_LOSS_DIC] += cnt_out - cnt_gt;
+      v[RA_LOSS_DIC_ABS] += fabsf(cnt_out - cnt_gt);
+    }
+    v[RA_LOSS_CONF] += conf;
+  }
+  const float fB = (float)B;
+#pragma unroll
+  for (int k = 0; k < RA_LOSS_COUNT; ++k) v[k] = ra::block_sum(v[k], red);
+  if (threadIdx.x == 0) {
+    out[RA_LOSS_BOX] = v[RA_LOSS_BOX] / fB;
+    out[RA_LOSS_IOU_SOFT] = v[RA_LOSS_IOU_SOFT] / fB;
+    out[RA_LOSS_SEGM] = -out[RA_LOSS_IOU_SOFT];
+    out[RA_LOSS_CONF] = v[RA_LOSS_CONF] / fB / (float)T;
+    out[RA_LOSS_IOU_HARD] = v[RA_LOSS_IOU_HARD] / fB;
+    out[RA_LOSS_WT_COV_SOFT] = v[RA_LOSS_WT_COV_SOFT] / fB;
+    out[RA_LOSS_UNWT_COV_SOFT] = v[RA_LOSS_UNWT_COV_SOFT] / fB;
+    out[RA_LOSS_WT_COV_HARD] = v[RA_LOSS_WT_COV_HARD] / fB;
+    out[RA_LOSS_UNWT_COV_HARD] = v[RA_LOSS_UNWT_COV_HARD] / fB;
+    out[RA_LOSS_DICE] = v[RA_LOSS_DICE] / fB;
+    out[RA_LOSS_COUNT_ACC] = v[RA_LOSS_COUNT_ACC] / fB;
+    out[RA_LOSS_DIC] = v[RA_LOSS_DIC] / fB;
+    out[RA_LOSS_DIC_ABS] = v[RA_LOSS_DIC_ABS] / fB;
+    out[RA_LOSS_TOTAL] = out[RA_LOSS_BOX] + out[RA_LOSS_SEGM] + mix * out[RA_LOSS_CONF] + wd_term;
+    out[14] = 0.f;
+    out[15] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ score head
+__global__ void score_kernel(const float *__restrict__ h, int Hd, const float *__restrict__ core, int Cd,
+                             const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ s_out,
+                             int s_stride) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float a = 0.f;
+  for (int k = threadIdx.x; k < Hd; k += blockDim.x) a = fmaf(h[(size_t)b * Hd + k], w[k], a);
+  for (int k = threadIdx.x; k < Cd; k += blockDim.x) a = fmaf(core[(size_t)b * Cd + k], w[Hd + k], a);
+  a = ra::block_sum(a, red);
+  if (threadIdx.x == 0) s_out[(size_t)b * s_stride] = ra::sigmoidf_acc(a + bias[0]);
+}
+
+// ------------------------------------------------------------------ box model GT interaction
+// Phase 1: per example, soft IoU of this step's attention box against every GT rectangle.
+__global__ void __launch_bounds__(256) box_gt_iou_kernel(const float *__restrict__ attn_box, size_t box_bstride,
+                                                         const float *__restrict__ gt_rect, int T, int H, int W,
+                                                         float *__restrict__ iou_t, int iou_bstride,
+                                                         float *__restrict__ grd) {
+  extern __shared__ float sm[];  // [T] inter, [T] rect area, then scratch
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float *inter_s = sm, *area_s = sm + T, *rc_s = sm + 2 * T;  // rc_s [T][4]
+  for (int i = threadIdx.x; i < T * 4; i += blockDim.x) rc_s[i] = gt_rect[(size_t)b * T * 4 + i];
+  for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const float *bx = attn_box + (size_t)b * box_bstride;
+  float tot = 0.f;
+  // thread-private accumulation over a strided set of pixels, one GT at a time is too slow;
+  // instead each thread walks its pixels and adds to per-GT shared accumulators at the end
+  for (int m0 = 0; m0 < T; m0 += 8) {
+    float in8[8], ar8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) in8[e] = ar8[e] = 0.f;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+      const float v = bx[i];
+      const float fy = (float)(i / W), fx = (float)(i % W);
+      if (m0 == 0) tot += v;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (m0 + e < T) {
+          const float *rc = rc_s + (m0 + e) * 4;
+          const bool in = fy >= rc[0] && fx >= rc[1] && fy <= rc[2] && fx <= rc[3];
+          in8[e] += in ? v : 0.f;
+          ar8[e] += in ? 1.f : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float s1 = ra::block_sum(in8[e], red);
+      const float s2 = ra::block_sum(ar8[e], red);
+      if (threadIdx.x == 0 && m0 + e < T) {
+        inter_s[m0 + e] = s1;
+        area_s[m0 + e] = s2;
+      }
+    }
+  }
+  tot = ra::block_sum(tot, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float hw_eps = (float)(H * W) * 1e-5f;
+    float mx = -INFINITY;
+    for (int m = 0; m < T; ++m) {
+      const float v = inter_s[m] / (tot + area_s[m] - inter_s[m] + hw_eps);  // box_model.py:494-495
+      iou_t[(size_t)b * iou_bstride + m] = v;
+      inter_s[m] = v;
+      mx = fmaxf(mx, v);
+    }
+    float cnt = 0.f;  // modellib.py:366-379 with matched == 0
+    for (int m = 0; m < T; ++m) cnt += (inter_s[m] == mx) ? 1.f : 0.f;
+    for (int m = 0; m < T; ++m) grd[(size_t)b * T + m] = (inter_s[m] == mx) ? 1.f / cnt : 0.f;
+  }
+}
+
+// Phase 2: canvas = max(canvas, sum_m grd[m] * y_gt[m] * (1 - noise))   (box_model.py:497-503)
+__global__ void box_gt_canvas_kernel(const float *__restrict__ grd, const float *__restrict__ y_gt,
+                                     const float *__restrict__ noise, size_t noise_bstride, int T, int HW,
+                                     float *__restrict__ canvas) {
+  const int b = blockIdx.y;
+  __shared__ float g_s[64];
+  for (int m = threadIdx.x; m < T; m += blockDim.x) g_s[m] = grd[(size_t)b * T + m];
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int m = 0; m < T; ++m) {
+      const float g = g_s[m];
+      if (g != 0.f) v += g * y_gt[((size_t)b * T + m) * HW + i];
+    }
+    if (noise != nullptr) v = v - v * noise[(size_t)b * noise_bstride + i];
+    const size_t ci = (size_t)b * HW + i;
+    canvas[ci] = fmaxf(canvas[ci], v);
+  }
+}
+
+int iou_plan(int N, int M, int HW, IouParams *p) {
+  const int rows = (N > M ? N : M) + 1;
+  const int nb = (rows + kR - 1) / kR;
+  if (nb * kR > 40) return RA_ERR_UNSUPPORTED;
+  p->NB = p->MB = nb;
+  p->KS = 256 / (nb * nb);
+  if (p->KS > 64) p->KS = 64;
+  if (p->KS < 1) return RA_ERR_UNSUPPORTED;
+  const int chunks = (HW + kKC - 1) / kKC;
+  p->ctas_per_ex = chunks < 32 ? chunks : 32;
+  p->chunks_per_cta = (chunks + p->ctas_per_ex - 1) / p->ctas_per_ex;
+  p->ctas_per_ex = (chunks + p->chunks_per_cta - 1) / p->chunks_per_cta;
+  return RA_OK;
+}
+
+}  // namespace
+
+extern "C" int ra_gt_box_f32(const float *y_gt, int B, int T, int H, int W, float padding_ratio, float min_padding,
+                             float *top_left, float *bot_right, float *rect, float *box, float *area, void *stream) {
+  if (!y_gt || !top_left || !bot_right || B < 0 || T < 1 || H < 1 || W < 1) return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  gt_box_kernel<<<B * T, 256, 0, ra::as_stream(stream)>>>(y_gt, H, W, padding_ratio, min_padding, top_left, bot_right,
+                                                          rect, box, area);
+  return ra::finish_launch("gt_box_kernel");
+}
+
+extern "C" size_t ra_pairwise_iou_workspace(int B, int N, int M, int HW) {
+  IouParams p;
+  if (iou_plan(N, M, HW, &p) != RA_OK) return 0;
+  return (size_t)B * p.ctas_per_ex * (p.NB * kR) * (p.MB * kR);
+}
+
+extern "C" int ra_pairwise_iou_f32(const float *a, const float *b, const float *b_rect, int B, int N, int M, int H,
+                                   int W, float hard_threshold, float *partial, float *iou, float *dice, void *stream) {
+  if (!a || (!b && !b_rect) || !partial || !iou || B < 0 || N < 1 || M < 1 || H < 1 || W < 1)
+    return RA_ERR_INVALID_ARG;
+  if (((size_t)H * W) % 4 != 0) return RA_ERR_UNSUPPORTED;
+  IouParams p;
+  int rc = iou_plan(N, M, H * W, &p);
+  if (rc != RA_OK) return rc;
+  if (B == 0) return RA_OK;
+  p.a = a;
+  p.b = b;
+  p.b_rect = b_rect;
+  p.partial = partial;
+  p.N = N;
+  p.M = M;
+  p.H = H;
+  p.W = W;
+  p.hard_thr = hard_threshold;
+  const int NP = p.NB * kR, MP = p.MB * kR;
+  size_t smem = (size_t)(NP + MP) * (kKC + kPad) * sizeof(float);
+  const size_t red_bytes = (size_t)256 * kR * kR * sizeof(float);
+  if (smem < red_bytes) smem = red_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pairwise_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) {
+      ra::set_last_error("cudaFuncSetAttribute(pairwise_iou_kernel)", e);
+      return RA_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaStream_t s = ra::as_stream(stream);
+  const int threads = p.NB * p.MB * p.KS;
+  pairwise_iou_kernel<<<dim3(p.ctas_per_ex, B), threads, smem, s>>>(p);
+  rc = ra::finish_launch("pairwise_iou_kernel");
+  if (rc != RA_OK) return rc;
+  pairwise_iou_finalize_kernel<<<B, 256, 0, s>>>(partial, N, M, NP, MP, p.ctas_per_ex, (float)(H * W) * 1e-5f, iou,
+                                                 dice);
+  return ra::finish_launch("pairwise_iou_finalize_kernel");
+}
+
+extern "C" int ra_loss_block_f32(const float *iou_box, const float *match_box, const float *iou_soft,
+                                 const float *match, const float *iou_hard, const float *dice_hard,
+                                 const float *s_out, const float *s_gt, const float *gt_area, int B, int T,
+                                 float loss_mix_ratio, float weight_decay_term, float *out, void *stream) {
+  if (!iou_box || !match_box || !iou_soft || !match || !s_out || !s_gt || !gt_area || !out || B < 1 || T < 1)
+    return RA_ERR_INVALID_ARG;
+  loss_block_kernel<<<1, 256, 0, ra::as_stream(stream)>>>(iou_box, match_box, iou_soft, match, iou_hard, dice_hard,
+                                                          s_out, s_gt, gt_area, B, T, loss_mix_ratio,
+                                                          weight_decay_term, out);
+  return ra::finish_launch("loss_block_kernel");
+}
+
+extern "C" int ra_score_f32(const float *h, int Hd, const float *core, int Cd, const float *w, const float *bias,
+                            int B, float *s_out, int s_stride, void *stream) {
+  if (!h || !w || !bias || !s_out || Hd < 1 || Cd < 0 || (Cd > 0 && !core) || B < 0) return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  score_kernel<<<B, 256, 0, ra::as_stream(stream)>>>(h, Hd, core, Cd, w, bias, s_out, s_stride);
+  return ra::finish_launch("score_kernel");
+}
+
+extern "C" int ra_box_gt_step_f32(const float *attn_box, size_t box_bstride, const float *gt_rect, const float *y_gt,
+                                  const float *noise, size_t noise_bstride, int B, int T, int H, int W, float *iou_t,
+                                  int iou_bstride, float *grd_ws, float *canvas, void *stream) {
+  if (!attn_box || !gt_rect || !y_gt || !iou_t || !grd_ws || !canvas || B < 0 || T < 1 || T > 64)
+    return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  cudaStream_t s = ra::as_stream(stream);
+  box_gt_iou_kernel<<<B, 256, (size_t)(6 * T) * sizeof(float), s>>>(attn_box, box_bstride, gt_rect, T, H, W, iou_t,
+                                                                    iou_bstride, grd_ws);
+  int rc = ra::finish_launch("box_gt_iou_kernel");
+  if (rc != RA_OK) return rc;
+  const int HW = H * W;
+  int bx = (HW + 255) / 256;
+  if (bx > 64) bx = 64;
+  box_gt_canvas_kernel<<<dim3(bx, B), 256, 0, s>>>(grd_ws, y_gt, noise, noise_bstride, T, HW, canvas);
+  return ra::finish_launch("box_gt_canvas_kernel");
+}

@@ -1,0 +1,383 @@
+"""Host side of the recurrent-attention model — the drop-in for ``full_model.get_model``
+(full_model.py:13) and ``box_model.get_model`` (box_model.py:11) in eval mode.
+
+Same contract as the reference: an ``opt`` dict in (full_model_train.py:581-658), named
+inputs (``x [B,H,W,3]``, ``y_gt [B,T,H,W]``, ``s_gt [B,T]``, optional ``d_in [B,H,W,8]``,
+``y_in [B,H,W,C]``) and named outputs (``y_out``, ``s_out``, ``attn_box``, ``match``, ``loss`` …,
+full_model.py:853-910,941-1081), weights imported by the flat ``weights.h5`` key names
+(full_model_read.py:32-70).  Python only sequences launches: every FLOP runs in
+librecattend_b200.so through the C ABI (ops.py); torch provides device memory, streams and
+(optionally) CUDA-graph capture of the whole T-step decode.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .config import input_depths
+from .synthetic import dcnn_skip_channels
+
+BN_EPS = 1e-3  # nnlib.py:119
+
+LOSS_KEYS = _lib.LOSS_NAMES
+
+
+def _fold_bn(weights, scope, layer, T, bias):
+  """Eval-mode batch norm (nnlib.py:113-119) + conv bias folded into y = conv*scale + shift,
+  one row per decode step (the reference keeps a separate BN copy per step, nnlib.py:212-254)."""
+  scale = np.empty((T, bias.shape[0]), np.float32)
+  shift = np.empty((T, bias.shape[0]), np.float32)
+  for t in range(T):
+    k = '{}_{}_{}_'.format(scope, layer, t)
+    inv = (1.0 / np.sqrt(weights[k + 'ema_var'].astype(np.float32) + np.float32(BN_EPS))).astype(np.float32)
+    inv = inv * weights[k + 'gamma'].astype(np.float32)
+    scale[t] = inv
+    shift[t] = weights[k + 'beta'] - weights[k + 'ema_mean'] * inv + bias * inv
+  return scale, shift
+
+
+def _deconv_to_conv(w):
+  """conv2d_transpose filter [kh,kw,Cout,Cin] (nnlib.py:320-325,372-376) -> the HWIO filter of
+  the equivalent stride-1 convolution over the (zero-inserted) input: spatial flip + swap."""
+  return np.ascontiguousarray(w[::-1, ::-1].transpose(0, 1, 3, 2)).astype(np.float32)
+
+
+class _ModelBase(object):
+
+  def __init__(self, opt, device=None):
+    self.opt = dict(opt)
+    if not torch.cuda.is_available():
+      raise _lib.RecAttendError('rec_attend_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    _lib.lib()  # fail loudly now if the extension is missing
+    self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    o = self.opt
+    self.T, self.H, self.W = o['timespan'], o['inp_height'], o['inp_width']
+    self.F = o['filter_height']
+    if o['filter_width'] != self.F:
+      raise _lib.RecAttendError('square attention filters only')
+    self.Hd = o['ctrl_rnn_hid_dim']
+    self.n_iter = o['num_ctrl_rnn_iter']
+    if o['num_ctrl_mlp_layers'] != 1 or o['num_glimpse_mlp_layers'] != 2:
+      raise _lib.RecAttendError('unsupported controller/glimpse MLP depth (all shipped configs use 1 / 2)')
+    if not o.get('use_bn', True):
+      raise _lib.RecAttendError('use_bn=False is not used by any shipped config')
+    if o.get('fixed_order', False):
+      raise _lib.RecAttendError('fixed_order is not on the hot path (no shipped config uses it)')
+    self.add_d = bool(o.get('add_d_out', False))
+    self.nsc = o.get('num_semantic_classes', 1)
+    self.D = input_depths(o)[0]
+    self.Cs = self.D - 1  # step-invariant channels: x (3) [+ d_in (8) + y_in (nsc)]
+    # reference concat order is x, canvas, d_in, y_in (full_model.py:643-658)
+    self.static_idx = [0, 1, 2] + list(range(4, self.D))
+    self.chan_map = torch.tensor(self.static_idx + [3], dtype=torch.int32, device=self.device)
+    flags = 0
+    if o.get('squash_ctrl_params', False):
+      flags |= _lib.CTRL_SQUASH
+    if self._fixed_var():
+      flags |= _lib.CTRL_FIXED_VAR
+    if o.get('dynamic_var', False):
+      flags |= _lib.CTRL_DYNAMIC_VAR
+    if self._fixed_gamma():
+      flags |= _lib.CTRL_FIXED_GAMMA
+    self.ctrl_flags = flags
+    self.ctrl_pool = list(o['ctrl_cnn_pool'])
+    sub = int(np.prod(self.ctrl_pool))
+    self.gh, self.gw = self.H // sub, self.W // sub
+    self.P = self.gh * self.gw
+    self.w = None
+    self.wd_term = 0.0
+    self._bufs = {}
+
+  def _fixed_var(self):
+    return bool(self.opt.get('fixed_var', False))
+
+  def _fixed_gamma(self):
+    return bool(self.opt.get('fixed_gamma', False))
+
+  # ------------------------------------------------------------------ weights
+  def _dev(self, a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+
+  def _load_controller(self, weights):
+    T = self.T
+    w = {}
+    n = len(self.opt['ctrl_cnn_filter_size'])
+    w0 = np.asarray(weights['ctrl_cnn_w_0'], np.float32)
+    if w0.shape[2] != self.D:
+      raise _lib.RecAttendError('ctrl_cnn_w_0 has {} input channels, expected {}'.format(w0.shape[2], self.D))
+    w['ccnn_w0_static'] = self._dev(w0[:, :, self.static_idx, :])
+    w['ccnn_w0_canvas'] = self._dev(w0[:, :, 3:4, :])
+    c0 = w0.shape[3]
+    w['one_c0'] = torch.ones(c0, device=self.device)
+    w['zero_c0'] = torch.zeros(c0, device=self.device)
+    for i in range(n):
+      wi = np.asarray(weights['ctrl_cnn_w_%d' % i], np.float32)
+      if i > 0:
+        w['ccnn_w%d' % i] = self._dev(wi)
+      sc, sh = _fold_bn(weights, 'ctrl_cnn', i, T, np.asarray(weights['ctrl_cnn_b_%d' % i], np.float32))
+      w['ccnn_scale%d' % i] = self._dev(sc)
+      w['ccnn_shift%d' % i] = self._dev(sh)
+    gates = 'ifou'  # kernel gate order i, f, o, u
+    w['lstm_wx'] = self._dev(np.stack([weights['ctrl_lstm_w_x' + g] for g in gates]))
+    w['lstm_wh'] = self._dev(np.stack([weights['ctrl_lstm_w_h' + g] for g in gates]))
+    w['lstm_b'] = self._dev(np.stack([weights['ctrl_lstm_b_' + g] for g in gates]))
+    for k in ('glimpse_mlp_w_0', 'glimpse_mlp_b_0', 'glimpse_mlp_w_1', 'glimpse_mlp_b_1', 'ctrl_mlp_w_0',
+              'ctrl_mlp_b_0', 'score_mlp_b_0'):
+      w[k] = self._dev(weights[k])
+    w['score_mlp_w_0'] = self._dev(np.asarray(weights['score_mlp_w_0'], np.float32).reshape(-1))
+    if w['glimpse_mlp_w_1'].shape[1] != self.P:
+      raise _lib.RecAttendError('glimpse_mlp_w_1 maps to {} positions, the feature map has {}'.format(
+          w['glimpse_mlp_w_1'].shape[1], self.P))
+    return w
+
+  def _weight_decay_term(self, weights):
+    """nnlib.py:59-61: sum over conv/mlp/lstm weight matrices of wd * ||w||^2 / 2 (a constant
+    of the weights; computed once on the host in float64 then rounded)."""
+    wd = float(self.opt['weight_decay'])
+    tot = 0.0
+    for k, v in weights.items():
+      if '_w_' in k and not k.endswith(('_beta', '_gamma', '_ema_mean', '_ema_var')):
+        v = np.asarray(v, np.float32)
+        tot += wd * float(np.sum(v.astype(np.float64)**2)) / 2.0
+    return tot
+
+  def export_weights(self):
+    """The weights as loaded (reference key schema, TF layouts)."""
+    return {k: np.array(v) for k, v in self._raw_weights.items()}
+
+  # ------------------------------------------------------------------ shared pieces
+  def _inputs(self, batch):
+    def dev(v):
+      if isinstance(v, np.ndarray):
+        v = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+      return v.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    x = dev(batch['x'])
+    B = x.shape[0]
+    if tuple(x.shape) != (B, self.H, self.W, 3):
+      raise _lib.RecAttendError('x must be [B,{},{},3], got {}'.format(self.H, self.W, tuple(x.shape)))
+    d_in = y_in = None
+    if self.add_d:
+      d_in, y_in = dev(batch['d_in']), dev(batch['y_in'])
+      if tuple(d_in.shape) != (B, self.H, self.W, 8) or tuple(y_in.shape) != (B, self.H, self.W, self.nsc):
+        raise _lib.RecAttendError('d_in / y_in have the wrong shape')
+    y_gt = dev(batch['y_gt']) if 'y_gt' in batch else None
+    s_gt = dev(batch['s_gt']) if 's_gt' in batch else None
+    return x, d_in, y_in, y_gt, s_gt
+
+  def _buffers(self, B):
+    if B not in self._bufs:
+      self._bufs[B] = self._alloc(B)
+    return self._bufs[B]
+
+  def _alloc_controller(self, B, bufs):
+    dev, T, H, W = self.device, self.T, self.H, self.W
+    f32 = torch.float32
+    bufs['xs'] = torch.empty((B, H, W, self.Cs), device=dev, dtype=f32)
+    c0 = self.opt['ctrl_cnn_depth'][0]
+    bufs['static_pre'] = torch.empty((B, H, W, c0), device=dev, dtype=f32)
+    bufs['canvas'] = torch.empty((B, H, W), device=dev, dtype=f32)
+    h, w = H, W
+    bufs['ccnn'] = []
+    for i, (ch, pl) in enumerate(zip(self.opt['ctrl_cnn_depth'], self.ctrl_pool)):
+      h, w = h // pl, w // pl
+      bufs['ccnn'].append(torch.empty((B, h, w, ch), device=dev, dtype=f32))
+    bufs['h_all'] = torch.empty((T, B, self.Hd), device=dev, dtype=f32)
+    bufs['ctrl_out_all'] = torch.empty((T, B, 9), device=dev, dtype=f32)
+    bufs['gmap_all'] = torch.empty((T, B, self.n_iter, self.P), device=dev, dtype=f32)
+    bufs['box_all'] = torch.empty((T, B, _lib.BOX_STRIDE), device=dev, dtype=f32)
+    bufs['fy'] = torch.empty((B, self.F, H), device=dev, dtype=f32)
+    bufs['fx'] = torch.empty((B, self.F, W), device=dev, dtype=f32)
+    bufs['band'] = torch.empty((B, 2, self.F, 2), device=dev, dtype=torch.int32)
+    bufs['attn_box'] = torch.empty((B, T, H, W), device=dev, dtype=f32)
+    bufs['s_out'] = torch.empty((B, T), device=dev, dtype=f32)
+
+  def _prepare(self, bufs, x, d_in, y_in):
+    """Step-invariant work, once per forward: the static input stack and the static half of
+    the first controller layer (conv is linear in its input channels; only the canvas
+    channel changes between decode steps, full_model.py:640-663)."""
+    w = self.w
+    ops.concat_channels(x, d_in, y_in, out=bufs['xs'])
+    ops.conv3x3_block(bufs['xs'], w['ccnn_w0_static'], w['one_c0'], w['zero_c0'], pool=1, relu=False,
+                      out=bufs['static_pre'])
+    bufs['canvas'].zero_()  # full_model.py:239
+
+  def _controller(self, bufs, t):
+    """full_model.py:663-725: controller CNN (BN copy t) + glimpse LSTM + head -> box params."""
+    w = self.w
+    B, H, W = bufs['canvas'].shape
+    cv = bufs['canvas'].view(B, H, W, 1)
+    ops.conv3x3_block(cv, w['ccnn_w0_canvas'], w['ccnn_scale0'][t], w['ccnn_shift0'][t], pool=self.ctrl_pool[0],
+                      relu=True, add_to=bufs['static_pre'], out=bufs['ccnn'][0])
+    for i in range(1, len(self.ctrl_pool)):
+      ops.conv3x3_block(bufs['ccnn'][i - 1], w['ccnn_w%d' % i], w['ccnn_scale%d' % i][t], w['ccnn_shift%d' % i][t],
+                        pool=self.ctrl_pool[i], relu=True, out=bufs['ccnn'][i])
+    feat = bufs['ccnn'][-1].view(B, self.P, -1)
+    ops.controller_step(feat, w['lstm_wx'], w['lstm_wh'], w['lstm_b'], w['glimpse_mlp_w_0'], w['glimpse_mlp_b_0'],
+                        w['glimpse_mlp_w_1'], w['glimpse_mlp_b_1'], w['ctrl_mlp_w_0'], w['ctrl_mlp_b_0'], self.H,
+                        self.W, self.F, self.F, self.ctrl_flags, n_iter=self.n_iter, h_out=bufs['h_all'][t],
+                        ctrl_out=bufs['ctrl_out_all'][t], glimpse_map=bufs['gmap_all'][t], box=bufs['box_all'][t])
+    ops.get_gaussian_filter(bufs['box_all'][t], self.H, self.W, self.F, fy=bufs['fy'], fx=bufs['fx'],
+                            band=bufs['band'])
+
+  def _controller_outputs(self, bufs, out):
+    box = bufs['box_all'].permute(1, 0, 2)  # [B,T,12]
+    ctr = box[:, :, _lib.BOX_CTR_Y:_lib.BOX_CTR_X + 1]
+    size = box[:, :, _lib.BOX_SIZE_Y:_lib.BOX_SIZE_X + 1]
+    out['attn_ctr'] = ctr.contiguous()
+    out['attn_size'] = size.contiguous()
+    out['attn_top_left'] = box[:, :, _lib.BOX_TL_Y:_lib.BOX_TL_X + 1].contiguous()
+    out['attn_bot_right'] = box[:, :, _lib.BOX_BR_Y:_lib.BOX_BR_X + 1].contiguous()
+    out['attn_lg_var'] = box[:, :, _lib.BOX_LGVAR_Y:_lib.BOX_LGVAR_X + 1].contiguous()
+    out['ctrl_out'] = bufs['ctrl_out_all'].permute(1, 0, 2).contiguous()
+    out['h_ctrl'] = bufs['h_all'].permute(1, 0, 2).contiguous()
+    B = box.shape[0]
+    out['ctrl_rnn_glimpse_map'] = bufs['gmap_all'].permute(1, 0, 2, 3).reshape(B, self.T, self.n_iter, self.gh,
+                                                                              self.gw)
+    out['attn_box'] = bufs['attn_box']
+    out['s_out'] = bufs['s_out']
+    out['canvas'] = bufs['canvas'].view(B, self.H, self.W, 1)
+
+
+class FullModel(_ModelBase):
+  """``full_model.get_model(opt)`` replacement (eval mode: phase_train=False)."""
+
+  def __init__(self, opt, device=None):
+    super(FullModel, self).__init__(opt, device)
+    o = self.opt
+    for k in ('ctrl_add_inp', 'ctrl_add_canvas', 'attn_add_inp', 'attn_add_canvas'):
+      if not o.get(k, True):
+        raise _lib.RecAttendError('{}=False is not used by any shipped config'.format(k))
+    for k in ('ctrl_add_d_out', 'ctrl_add_y_out', 'attn_add_d_out', 'attn_add_y_out', 'add_y_out'):
+      if bool(o.get(k, self.add_d)) != self.add_d:
+        raise _lib.RecAttendError('mixed d_out/y_out input flags are not used by any shipped config')
+    if o['segm_loss_fn'] != 'iou' or o['box_loss_fn'] != 'iou':
+      raise _lib.RecAttendError("only the 'iou' losses are supported (SURVEY §9.13)")
+    self.attn_pool = list(o['attn_cnn_pool'])
+    self.dcnn_pool = list(o['attn_dcnn_pool'])
+    self.skip_ch = dcnn_skip_channels(o)
+    self.use_skip = bool(o.get('add_skip_conn', True))
+    self.disable_overwrite = bool(o.get('disable_overwrite', True))  # full_model.py:117-120
+    self.min_padding = float(o['padding'] + 4)  # full_model.py:567
+
+  def load_weights(self, weights):
+    T = self.T
+    self._raw_weights = {k: np.asarray(v, np.float32) for k, v in weights.items()}
+    w = self._load_controller(weights)
+    for i in range(len(self.attn_pool)):
+      w['acnn_w%d' % i] = self._dev(weights['attn_cnn_w_%d' % i])
+      sc, sh = _fold_bn(weights, 'attn_cnn', i, T, np.asarray(weights['attn_cnn_b_%d' % i], np.float32))
+      w['acnn_scale%d' % i], w['acnn_shift%d' % i] = self._dev(sc), self._dev(sh)
+    for i in range(len(self.dcnn_pool)):
+      w['adcnn_w%d' % i] = self._dev(_deconv_to_conv(np.asarray(weights['attn_dcnn_w_%d' % i], np.float32)))
+      sc, sh = _fold_bn(weights, 'attn_dcnn', i, T, np.asarray(weights['attn_dcnn_b_%d' % i], np.float32))
+      w['adcnn_scale%d' % i], w['adcnn_shift%d' % i] = self._dev(sc), self._dev(sh)
+    self.w = w
+    self.wd_term = self._weight_decay_term(weights)
+    return self
+
+  def _alloc(self, B):
+    dev, T, H, W, F = self.device, self.T, self.H, self.W, self.F
+    f32 = torch.float32
+    bufs = {}
+    self._alloc_controller(B, bufs)
+    bufs['extract_tmp'] = torch.empty((B * F * W * self.D,), device=dev, dtype=f32)
+    bufs['x_patch_all'] = torch.empty((T, B, F, F, self.D), device=dev, dtype=f32)
+    bufs['y_patch_all'] = torch.empty((T, B, F, F, 1), device=dev, dtype=f32)
+    s = F
+    bufs['acnn'] = []
+    for ch, pl in zip(self.opt['attn_cnn_depth'], self.attn_pool):
+      s = s // pl
+      bufs['acnn'].append(torch.empty((B, s, s, ch), device=dev, dtype=f32))
+    bufs['adcnn'] = []
+    for ch, pl in zip(self.opt['attn_dcnn_depth'][:-1], self.dcnn_pool[:-1]):
+      s = s * pl
+      bufs['adcnn'].append(torch.empty((B, s, s, ch), device=dev, dtype=f32))
+    bufs['y_out'] = torch.empty((B, T, H, W), device=dev, dtype=f32)
+    return bufs
+
+  def _decode(self, bufs, B):
+    """The T-step decode loop, full_model.py:638-848 (eval mode)."""
+    w = self.w
+    T, H, W, F = self.T, self.H, self.W, self.F
+    thw = T * H * W
+    for t in range(T):
+      self._controller(bufs, t)
+      box_t = bufs['box_all'][t]
+      x_patch = bufs['x_patch_all'][t]
+      ops.extract_patch(bufs['xs'], bufs['canvas'], self.chan_map, box_t, bufs['fy'], bufs['fx'], bufs['band'],
+                        tmp=bufs['extract_tmp'], out=x_patch)
+      prev = x_patch
+      for i, pl in enumerate(self.attn_pool):  # full_model.py:792
+        ops.conv3x3_block(prev, w['acnn_w%d' % i], w['acnn_scale%d' % i][t], w['acnn_shift%d' % i][t], pool=pl,
+                          relu=True, out=bufs['acnn'][i])
+        prev = bufs['acnn'][i]
+      core = bufs['acnn'][-1]
+      ops.score(bufs['h_all'][t], core, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
+      # full_model.py:797-807: skip list [None, h_acnn[4..0], x_patch]
+      skips = [None] + (bufs['acnn'][::-1][1:] + [x_patch])
+      prev = core
+      n_d = len(self.dcnn_pool)
+      for i, pl in enumerate(self.dcnn_pool):
+        sk = skips[i] if (self.use_skip and self.skip_ch[i] > 0) else None
+        dst = bufs['y_patch_all'][t] if i == n_d - 1 else bufs['adcnn'][i]
+        ops.conv3x3_block(prev, w['adcnn_w%d' % i], w['adcnn_scale%d' % i][t], w['adcnn_shift%d' % i][t], pool=1,
+                          relu=True, x2=sk, upsample=pl, out=dst)
+        prev = dst
+      ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],
+                     attn_box=bufs['attn_box'][:, t], y_out=bufs['y_out'][:, t], out_bstride=thw,
+                     disable_overwrite=self.disable_overwrite)
+
+  def _loss(self, bufs, y_gt, s_gt, out, want_gt_box):
+    """full_model.py:916-1081 (matching on soft IoU, 'iou' losses, hard statistics)."""
+    o = self.opt
+    tl, br, box_gt, rect, area = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'],
+                                                min_padding=self.min_padding, want_box=want_gt_box)
+    iou_box = ops.f_iou(bufs['attn_box'], None, b_rect=rect)
+    match_box = ops.f_segm_match(iou_box, s_gt)
+    iou_soft = ops.f_iou(bufs['y_out'], y_gt)
+    match = ops.f_segm_match(iou_soft, s_gt)
+    iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
+    scal = ops.loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice, bufs['s_out'], s_gt, area,
+                          o['loss_mix_ratio'], self.wd_term)
+    out.update({
+        'attn_top_left_gt': tl, 'attn_bot_right_gt': br,
+        'iou_soft_box_pairwise': iou_box, 'match_box': match_box, 'iou_soft_pairwise': iou_soft, 'match': match,
+        'iou_hard_pairwise': iou_hard, 'loss_scalars': scal
+    })
+    if box_gt is not None:
+      out['attn_box_gt'] = box_gt
+
+  def forward(self, batch, outputs=None, phase_train=False, with_loss=True):
+    """``sess.run([model[k] for k in outputs], feed_dict)`` of runner.py:98-105.
+    Returns a dict of CUDA tensors (all keys when ``outputs`` is None)."""
+    if phase_train:
+      raise _lib.RecAttendError('training-mode forward (batch-stat BN, knob) is a later row of the scope table')
+    if self.w is None:
+      raise _lib.RecAttendError('load_weights() first')
+    x, d_in, y_in, y_gt, s_gt = self._inputs(batch)
+    B = x.shape[0]
+    bufs = self._buffers(B)
+    self._prepare(bufs, x, d_in, y_in)
+    self._decode(bufs, B)
+    out = {}
+    self._controller_outputs(bufs, out)
+    out['y_out'] = bufs['y_out']
+    want = None if outputs is None else set(outputs)
+    if want is None or 'x_patch' in want:
+      out['x_patch'] = bufs['x_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
+    if want is None or 'y_out_patch' in want:
+      out['y_out_patch'] = bufs['y_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
+    if with_loss and y_gt is not None:
+      self._loss(bufs, y_gt, s_gt, out, want_gt_box=(want is None or 'attn_box_gt' in want))
+      scal = out['loss_scalars']
+      for i, k in enumerate(LOSS_KEYS):
+        out[k] = scal[i]
+    if want is not None:
+      out = {k: out[k] for k in outputs}
+    return out
+
+
+def get_model(opt, is_training=True, device=None):
+  """Same call as the reference's ``full_model.get_model(opt, is_training)``; returns the
+  model object instead of a dict of TF tensors."""
+  return FullModel(opt, device=device)

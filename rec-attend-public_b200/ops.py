@@ -1,0 +1,238 @@
+"""Operator-level host mirror of the reference's modellib.py / nnlib.py for the hot path.
+
+Same names and argument meaning as the reference functions they replace; every call goes
+through the C ABI of librecattend_b200.so on the current CUDA stream (torch is used only for
+device memory and streams).  Inputs must be fp32 CUDA tensors; there is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_c = ctypes
+
+
+def _stream():
+  return _c.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+  if t is None:
+    return _c.c_void_p(0)
+  return _c.c_void_p(t.data_ptr())
+
+
+def _chk(*tensors):
+  for t in tensors:
+    if t is None:
+      continue
+    if not t.is_cuda:
+      raise _lib.RecAttendError('rec_attend_b200 ops need CUDA tensors (no CPU fallback)')
+    if not t.is_contiguous():
+      raise _lib.RecAttendError('rec_attend_b200 ops need contiguous tensors')
+    if t.dtype not in (torch.float32, torch.int32):
+      raise _lib.RecAttendError('rec_attend_b200 ops are fp32 (int32 for index tensors)')
+
+
+# ----------------------------------------------------------------------------- matching
+def hungarian(weights):
+  """``hungarian_module.hungarian(W)`` (hungarian.cc:26-30, modellib.py:406).
+  W [B,nx,ny] or [nx,ny] -> (matching, cover_x [..,nx,1], cover_y [..,1,ny]); the extra
+  attribute-free 4th return is the int32 status word per example."""
+  _chk(weights)
+  if weights.dim() == 2:
+    w3 = weights.unsqueeze(0)
+  elif weights.dim() == 3:
+    w3 = weights
+  else:
+    raise ValueError('Must have dimension 3 or 2.')  # hungarian.cc:61-64
+  B, nx, ny = w3.shape
+  M = torch.empty_like(w3)
+  cx = torch.empty((B, nx, 1), device=w3.device, dtype=torch.float32)
+  cy = torch.empty((B, 1, ny), device=w3.device, dtype=torch.float32)
+  st = torch.zeros((B,), device=w3.device, dtype=torch.int32)
+  _lib.call('ra_hungarian_f32', _p(w3), B, nx, ny, _p(M), _p(cx), _p(cy), _p(st), _stream())
+  if weights.dim() == 2:
+    return M[0], cx[0], cy[0], st
+  return M, cx, cy, st
+
+
+def f_segm_match(iou, s_gt, return_weights=False):
+  """modellib.f_segm_match (modellib.py:382-415): iou [B,T,T], s_gt [B,T] -> match [B,T,T]."""
+  _chk(iou, s_gt)
+  B, T, T2 = iou.shape
+  assert T == T2 and tuple(s_gt.shape) == (B, T)
+  match = torch.empty_like(iou)
+  w = torch.empty_like(iou) if return_weights else None
+  st = torch.zeros((B,), device=iou.device, dtype=torch.int32)
+  _lib.call('ra_segm_match_f32', _p(iou), _p(s_gt), B, T, _p(match), _p(w), _p(st), _stream())
+  if return_weights:
+    return match, w, st
+  return match
+
+
+# ----------------------------------------------------------------------------- conv blocks
+def conv3x3_block(x, w, scale, shift, pool=1, relu=True, x2=None, upsample=1, add_to=None, out=None):
+  """One fused layer of nnlib.run_cnn / run_dcnn in eval mode (nnlib.py:229-253, :372-400).
+  x [B,H,W,C1] (+x2 [B,H,W,C2]), w [3,3,C1+C2,Cout] HWIO conv-form filter."""
+  _chk(x, w, scale, shift, x2, add_to, out)
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  Cout = w.shape[3]
+  assert tuple(w.shape) == (3, 3, C1 + C2, Cout), (tuple(w.shape), C1, C2)
+  Ho, Wo = H * upsample // pool, W * upsample // pool
+  if out is None:
+    out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+  assert tuple(out.shape) == (B, Ho, Wo, Cout)
+  _lib.call('ra_conv3x3_f32', _p(x), C1, _p(x2), C2, _p(w), _p(scale), _p(shift), _p(add_to), B, H, W, Cout,
+            upsample, pool, 1 if relu else 0, _p(out), _stream())
+  return out
+
+
+def concat_channels(a, b=None, c=None, out=None):
+  _chk(a, b, c, out)
+  B, H, W, Ca = a.shape
+  Cb = 0 if b is None else b.shape[3]
+  Cc = 0 if c is None else c.shape[3]
+  if out is None:
+    out = torch.empty((B, H, W, Ca + Cb + Cc), device=a.device, dtype=torch.float32)
+  _lib.call('ra_concat_channels_f32', _p(a), Ca, _p(b), Cb, _p(c), Cc, B * H * W, _p(out), _stream())
+  return out
+
+
+# ----------------------------------------------------------------------------- controller
+def controller_step(feat, lstm_wx, lstm_wh, lstm_b, gmlp_w0, gmlp_b0, gmlp_w1, gmlp_b1, cmlp_w, cmlp_b, inp_height,
+                    inp_width, filter_height, filter_width, flags, n_iter=5, h_out=None, ctrl_out=None,
+                    glimpse_map=None, box=None):
+  """full_model.py:668-725: feat [B,P,Cf] -> (h [B,256], ctrl_out [B,9], glimpse_map [B,n_iter,P], box [B,12])."""
+  _chk(feat, lstm_wx, lstm_wh, lstm_b, gmlp_w0, gmlp_b0, gmlp_w1, gmlp_b1, cmlp_w, cmlp_b)
+  B, P, Cf = feat.shape
+  Hd = lstm_wh.shape[-1]
+  dev = feat.device
+  if h_out is None:
+    h_out = torch.empty((B, Hd), device=dev, dtype=torch.float32)
+  if ctrl_out is None:
+    ctrl_out = torch.empty((B, 9), device=dev, dtype=torch.float32)
+  if glimpse_map is None:
+    glimpse_map = torch.empty((B, n_iter, P), device=dev, dtype=torch.float32)
+  if box is None:
+    box = torch.empty((B, _lib.BOX_STRIDE), device=dev, dtype=torch.float32)
+  _chk(h_out, ctrl_out, glimpse_map, box)
+  _lib.call('ra_controller_step_f32', _p(feat), B, P, Cf, Hd, n_iter, _p(lstm_wx), _p(lstm_wh), _p(lstm_b),
+            _p(gmlp_w0), _p(gmlp_b0), _p(gmlp_w1), _p(gmlp_b1), _p(cmlp_w), _p(cmlp_b), inp_height, inp_width,
+            filter_height, filter_width, flags, _p(h_out), _p(ctrl_out), _p(glimpse_map), _p(box), _stream())
+  return h_out, ctrl_out, glimpse_map, box
+
+
+# ----------------------------------------------------------------------------- attention
+def get_gaussian_filter(box, H, W, F, fy=None, fx=None, band=None):
+  """modellib.get_gaussian_filter (modellib.py:581-612) for both axes at once.
+  Returns tap-major fy [B,F,H], fx [B,F,W] and the tap support bands [B,2,F,2] int32."""
+  _chk(box, fy, fx, band)
+  B = box.shape[0]
+  dev = box.device
+  if fy is None:
+    fy = torch.empty((B, F, H), device=dev, dtype=torch.float32)
+  if fx is None:
+    fx = torch.empty((B, F, W), device=dev, dtype=torch.float32)
+  if band is None:
+    band = torch.empty((B, 2, F, 2), device=dev, dtype=torch.int32)
+  _lib.call('ra_gaussian_filters_f32', _p(box), B, H, W, F, _p(fy), _p(fx), _p(band), _stream())
+  return fy, fx, band
+
+
+def extract_patch(xs, canvas, chan_map, box, fy, fx, band, tmp=None, out=None):
+  """modellib.extract_patch (modellib.py:615-641) with the attention gain of
+  full_model.py:788: xs [B,H,W,Cs] + canvas [B,H,W] -> x_patch [B,F,F,Cs+1]."""
+  _chk(xs, canvas, chan_map, box, fy, fx, band, tmp, out)
+  B, F, H = fy.shape
+  W = fx.shape[2]
+  Cs = 0 if xs is None else xs.shape[3]
+  D = Cs + (1 if canvas is not None else 0)
+  dev = fy.device
+  if tmp is None:
+    tmp = torch.empty((B * F * W * D,), device=dev, dtype=torch.float32)
+  if out is None:
+    out = torch.empty((B, F, F, D), device=dev, dtype=torch.float32)
+  assert tmp.numel() >= B * F * W * D and tuple(out.shape) == (B, F, F, D)
+  _lib.call('ra_gaussian_extract_f32', _p(xs), Cs, _p(canvas), _p(chan_map), _p(box), _p(fy), _p(fx), _p(band), B,
+            H, W, F, _p(tmp), _p(out), _stream())
+  return out
+
+
+def paste_back(patch, box, fy, fx, canvas, attn_box=None, y_out=None, out_bstride=None, disable_overwrite=False):
+  """full_model.py:738-741 (attention box), :810-818 (mask) and :845 (canvas = max) fused.
+  attn_box / y_out may be views of step t of a [B,T,H,W] stack (pass out_bstride = T*H*W)."""
+  B, F, H = fy.shape
+  W = fx.shape[2]
+  if out_bstride is None:
+    out_bstride = H * W
+  _chk(patch, box, fy, fx, canvas)
+  _lib.call('ra_paste_back_f32', _p(patch), _p(box), _p(fy), _p(fx), B, H, W, F, 1 if disable_overwrite else 0,
+            _p(attn_box), _p(y_out), out_bstride, _p(canvas), _stream())
+
+
+def score(h, core, w, bias, s_out, s_stride):
+  """full_model.py:821-822 / box_model.py:508-511."""
+  _chk(h, core, w, bias)
+  B, Hd = h.shape
+  Cd = 0 if core is None else core.numel() // B
+  _lib.call('ra_score_f32', _p(h), Hd, _p(core), Cd, _p(w), _p(bias), B, _p(s_out), s_stride, _stream())
+
+
+# ----------------------------------------------------------------------------- loss side
+def get_gt_box(y_gt, padding_ratio=0.0, min_padding=10.0, want_box=True):
+  """modellib.get_gt_box (modellib.py:663-701), center_shift_ratio = 0.
+  Returns top_left [B,T,2], bot_right [B,T,2], box [B,T,H,W] or None, rect [B,T,4], area [B,T]."""
+  _chk(y_gt)
+  B, T, H, W = y_gt.shape
+  dev = y_gt.device
+  tl = torch.empty((B, T, 2), device=dev, dtype=torch.float32)
+  br = torch.empty((B, T, 2), device=dev, dtype=torch.float32)
+  rect = torch.empty((B, T, 4), device=dev, dtype=torch.float32)
+  area = torch.empty((B, T), device=dev, dtype=torch.float32)
+  box = torch.empty((B, T, H, W), device=dev, dtype=torch.float32) if want_box else None
+  _lib.call('ra_gt_box_f32', _p(y_gt), B, T, H, W, float(padding_ratio), float(min_padding), _p(tl), _p(br),
+            _p(rect), _p(box), _p(area), _stream())
+  return tl, br, box, rect, area
+
+
+def f_iou(a, b=None, pairwise=True, b_rect=None, hard_threshold=0.0, want_dice=False, H=None, W=None):
+  """modellib.f_iou(a, b, timespan, pairwise=True) (modellib.py:138-153): a [B,N,H,W],
+  b [B,M,H,W] (or b_rect [B,M,4] rectangles) -> iou [B,N,M] (and f_dice, :81-97)."""
+  assert pairwise, 'only the pairwise form is on the hot path'
+  _chk(a, b, b_rect)
+  B, N, H, W = a.shape
+  M = b.shape[1] if b is not None else b_rect.shape[1]
+  dev = a.device
+  n_ws = _lib.lib().ra_pairwise_iou_workspace(B, N, M, H * W)
+  if n_ws == 0:
+    raise _lib.RecAttendError('ra_pairwise_iou: unsupported N/M')
+  ws = torch.empty((n_ws,), device=dev, dtype=torch.float32)
+  iou = torch.empty((B, N, M), device=dev, dtype=torch.float32)
+  dice = torch.empty((B, N, M), device=dev, dtype=torch.float32) if want_dice else None
+  _lib.call('ra_pairwise_iou_f32', _p(a), _p(b), _p(b_rect), B, N, M, H, W, float(hard_threshold), _p(ws), _p(iou),
+            _p(dice), _stream())
+  if want_dice:
+    return iou, dice
+  return iou
+
+
+def loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice_hard, s_out, s_gt, gt_area, loss_mix_ratio,
+               weight_decay_term):
+  """full_model.py:942-1081 scalars -> dict keyed like the reference's model dict."""
+  _chk(iou_box, match_box, iou_soft, match, iou_hard, dice_hard, s_out, s_gt, gt_area)
+  B, T = s_out.shape
+  out = torch.empty((_lib.LOSS_COUNT,), device=s_out.device, dtype=torch.float32)
+  _lib.call('ra_loss_block_f32', _p(iou_box), _p(match_box), _p(iou_soft), _p(match), _p(iou_hard), _p(dice_hard),
+            _p(s_out), _p(s_gt), _p(gt_area), B, T, float(loss_mix_ratio), float(weight_decay_term), _p(out),
+            _stream())
+  return out
+
+
+def box_gt_step(attn_box_t, box_bstride, gt_rect, y_gt, noise_t, noise_bstride, iou_t, iou_bstride, grd_ws, canvas):
+  """box_model.py:484-504 for one decode step (greedy GT match drives the canvas)."""
+  B, T, H, W = y_gt.shape
+  _lib.call('ra_box_gt_step_f32', _p(attn_box_t), box_bstride, _p(gt_rect), _p(y_gt), _p(noise_t), noise_bstride, B,
+            T, H, W, _p(iou_t), iou_bstride, _p(grd_ws), _p(canvas), _stream())

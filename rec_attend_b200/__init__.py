@@ -1,0 +1,12 @@
+"""Import alias: the product package lives in ``rec-attend-public_b200/`` (a directory name
+Python cannot import directly); this shim loads it under the name ``rec_attend_b200``."""
+import importlib.util as _ilu
+import os as _os
+import sys as _sys
+
+_PKG_DIR = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), 'rec-attend-public_b200')
+_spec = _ilu.spec_from_file_location(__name__, _os.path.join(_PKG_DIR, '__init__.py'),
+                                     submodule_search_locations=[_PKG_DIR])
+_mod = _ilu.module_from_spec(_spec)
+_sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,394 @@
+"""GPU parity tests, operator level: every C-ABI entry point of librecattend_b200.so against
+the CPU oracle (oracle/) on identical seeded inputs.  Integer/assignment results are
+bit-exact; fp32 results within the tolerance written next to each assert."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import hungarian as OH
+from oracle import model as OM
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'hungarian_kat.json')
+TOL = 1e-4  # operator-level fp32 tolerance (summation order only); the model-level bar is 1e-3
+
+
+@pytest.fixture(scope='module')
+def ops(cuda):
+  from rec_attend_b200 import ops as _ops
+  return _ops
+
+
+def _g(a):
+  return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ----------------------------------------------------------------------------- Hungarian
+def test_hungarian_golden_vectors(ops):
+  for case in json.load(open(GOLD))['cases']:
+    W = np.frombuffer(bytes.fromhex(case['W_f32_hex']), np.float32).reshape(case['shape'])
+    M, cx, cy, st = ops.hungarian(_g(W))
+    Mo, cxo, cyo = OH.hungarian(W)
+    assert (M.cpu().numpy() == Mo).all(), case['name']
+    assert (cx.cpu().numpy() == cxo).all() and (cy.cpu().numpy() == cyo).all(), case['name']
+    assert int(st.max()) == 0
+    if case['kind'] == 'known_answer':
+      assert (M.cpu().numpy() == np.array(case['M'], np.float32)).all()
+
+
+def test_hungarian_random_bit_exact(ops):
+  from test_hungarian_oracle import _random_weights
+  rng = np.random.default_rng(11)
+  for it in range(60):
+    kind = it % 5
+    nx, ny = int(rng.integers(1, 34)), int(rng.integers(1, 34))
+    if it % 3 == 0:
+      ny = nx
+    if it % 20 == 0:
+      nx = ny = 64
+    if it % 20 == 1:
+      nx, ny = 64, 40
+    B = 48
+    W = _random_weights(rng, kind, B, nx, ny)
+    M, cx, cy, st = ops.hungarian(_g(W))
+    Mo, cxo, cyo, info = OH.hungarian(W, return_info=True)
+    assert (M.cpu().numpy() == Mo).all(), (kind, nx, ny)
+    assert (cx.cpu().numpy() == cxo).all() and (cy.cpu().numpy() == cyo).all(), (kind, nx, ny)
+    assert ((st.cpu().numpy() & 1) == (info['status'] & 1)).all()
+
+
+def test_hungarian_errors_and_edges(ops):
+  from rec_attend_b200 import _lib
+  with pytest.raises(ValueError):
+    ops.hungarian(torch.zeros(3, device='cuda'))
+  with pytest.raises(_lib.RecAttendError):
+    ops.hungarian(torch.zeros(1, 65, 65, device='cuda'))
+  M, cx, cy, st = ops.hungarian(torch.zeros(0, 4, 4, device='cuda'))
+  assert M.shape == (0, 4, 4)
+  # 1x1 and all-equal weights
+  M, _, _, _ = ops.hungarian(_g(np.array([[0.3]], np.float32)))
+  assert float(M[0, 0]) == 1.0
+  W = np.full((2, 5, 5), 1e-5, np.float32)
+  M, cx, cy, _ = ops.hungarian(_g(W))
+  Mo, cxo, cyo = OH.hungarian(W)
+  assert (M.cpu().numpy() == Mo).all()
+
+
+def test_hungarian_host_entry_point(cuda):
+  import ctypes
+  from rec_attend_b200 import _lib
+  rng = np.random.default_rng(5)
+  W = rng.random((6, 7, 9)).astype(np.float32)
+  M = np.zeros_like(W)
+  cx = np.zeros((6, 7), np.float32)
+  cy = np.zeros((6, 9), np.float32)
+  st = np.zeros((6,), np.int32)
+  vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+  _lib.call('ra_hungarian_f32_host', vp(W), 6, 7, 9, vp(M), vp(cx), vp(cy), vp(st))
+  Mo, cxo, cyo = OH.hungarian(W)
+  assert (M == Mo).all() and (cx == cxo[..., 0]).all() and (cy == cyo[:, 0]).all()
+
+
+def test_segm_match(ops):
+  rng = np.random.default_rng(2)
+  B, T = 16, 20
+  iou = (rng.random((B, T, T))**3).astype(np.float32)
+  s_gt = np.zeros((B, T), np.float32)
+  for b in range(B):
+    s_gt[b, :rng.integers(0, T + 1)] = 1
+  match, w, st = ops.f_segm_match(_g(iou), _g(s_gt), return_weights=True)
+  wo = OM.segm_match_weights(torch.from_numpy(iou), torch.from_numpy(s_gt)).numpy()
+  assert (w.cpu().numpy() == wo).all(), 'the fp32 matrix handed to the matcher must be bit-identical'
+  mo = OM.f_segm_match(torch.from_numpy(iou), torch.from_numpy(s_gt)).numpy()
+  assert (match.cpu().numpy() == mo).all()
+
+
+# ----------------------------------------------------------------------------- conv blocks
+CONV_CASES = [
+    # B, H, W, C1, C2, Cout, up, pool, relu, add_to
+    (2, 32, 64, 13, 0, 16, 1, 2, 1, False),
+    (2, 64, 64, 1, 0, 16, 1, 2, 1, True),
+    (1, 128, 128, 4, 0, 8, 1, 1, 1, False),
+    (2, 24, 24, 32, 0, 64, 1, 2, 1, False),
+    (2, 12, 12, 64, 0, 96, 1, 2, 1, False),
+    (2, 6, 6, 96, 0, 64, 2, 1, 1, False),
+    (2, 12, 12, 64, 64, 64, 1, 1, 1, False),
+    (2, 24, 24, 32, 32, 16, 2, 1, 1, False),
+    (2, 48, 48, 16, 13, 1, 1, 1, 1, False),
+    (1, 16, 16, 12, 0, 16, 1, 1, 0, False),
+    (1, 70, 34, 8, 0, 8, 1, 2, 1, False),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv3x3_block(ops, case):
+  B, H, W, C1, C2, Cout, up, pool, relu, use_add = case
+  rng = np.random.default_rng(hash(case) % 2**31)
+  x1 = rng.standard_normal((B, H, W, C1)).astype(np.float32)
+  x2 = rng.standard_normal((B, H, W, C2)).astype(np.float32) if C2 else None
+  Cin = C1 + C2
+  scale = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+  shift = rng.standard_normal(Cout).astype(np.float32)
+  xin = torch.from_numpy(x1 if x2 is None else np.concatenate([x1, x2], 3))
+  if up == 1:
+    w = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    ref = OM.conv2d_same(xin, torch.from_numpy(w), torch.zeros(Cout))
+    w_dev = w
+  else:
+    from rec_attend_b200.full_model import _deconv_to_conv
+    wt = (rng.standard_normal((3, 3, Cout, Cin)) / np.sqrt(9 * Cin)).astype(np.float32)
+    ref = OM.conv2d_transpose_same(xin, torch.from_numpy(wt), torch.zeros(Cout), up)
+    w_dev = _deconv_to_conv(wt)
+  add = None
+  if use_add:
+    add = rng.standard_normal(tuple(ref.shape)).astype(np.float32)
+    ref = ref + torch.from_numpy(add)
+  ref = ref * torch.from_numpy(scale) + torch.from_numpy(shift)
+  if relu:
+    ref = torch.relu(ref)
+  if pool == 2:
+    ref = OM.max_pool_same(ref, 2)
+  out = ops.conv3x3_block(_g(x1), _g(w_dev), _g(scale), _g(shift), pool=pool, relu=bool(relu),
+                          x2=None if x2 is None else _g(x2), upsample=up, add_to=None if add is None else _g(add))
+  assert tuple(out.shape) == tuple(ref.shape)
+  assert rel_err(out.cpu().numpy(), ref.numpy()) < TOL
+
+
+def test_deconv_stride1_matches_transposed_conv(ops):
+  from rec_attend_b200.full_model import _deconv_to_conv
+  rng = np.random.default_rng(9)
+  x = rng.standard_normal((2, 12, 12, 16)).astype(np.float32)
+  wt = rng.standard_normal((3, 3, 8, 16)).astype(np.float32) / 12
+  ref = OM.conv2d_transpose_same(torch.from_numpy(x), torch.from_numpy(wt), torch.zeros(8), 1)
+  one, zero = torch.ones(8, device='cuda'), torch.zeros(8, device='cuda')
+  out = ops.conv3x3_block(_g(x), _g(_deconv_to_conv(wt)), one, zero, pool=1, relu=False, upsample=1)
+  assert rel_err(out.cpu().numpy(), ref.numpy()) < TOL
+
+
+def test_concat_channels(ops):
+  rng = np.random.default_rng(1)
+  a, b, c = (rng.random((2, 5, 7, k)).astype(np.float32) for k in (3, 8, 1))
+  out = ops.concat_channels(_g(a), _g(b), _g(c))
+  assert (out.cpu().numpy() == np.concatenate([a, b, c], 3)).all()
+  out = ops.concat_channels(_g(a))
+  assert (out.cpu().numpy() == a).all()
+
+
+# ----------------------------------------------------------------------------- controller
+@pytest.mark.parametrize('arch,H,W', [('kitti', 64, 128), ('cvppp', 128, 128), ('cityscapes', 512, 1024)])
+def test_controller_step(ops, arch, H, W):
+  import rec_attend_b200 as ra
+  from rec_attend_b200 import _lib
+  opt = ra.config.full_model_opt(arch, H, W, 3)
+  w = ra.synthetic.make_weights(opt, seed=77)
+  wt = {k: torch.from_numpy(v) for k, v in w.items()}
+  B = 3
+  gh, gw = H // 32, W // 32
+  P, Cf, Hd = gh * gw, 64, 256
+  rng = np.random.default_rng(4)
+  feat = np.maximum(rng.standard_normal((B, P, Cf)), 0).astype(np.float32)
+  # oracle: the part of controller_step after the CNN
+  state = torch.zeros(B, 2 * Hd)
+  gmap = torch.ones(B, P, 1) / P
+  gmaps = []
+  f = torch.from_numpy(feat)
+  for it in range(5):
+    gmaps.append(gmap[:, :, 0])
+    state = OM.lstm_step((f * gmap).sum(1), state, wt, Hd)
+    h = state[:, Hd:]
+    if it < 4:
+      gmap = OM.run_mlp(h, wt, 'glimpse_mlp', ['relu', 'softmax'])[-1].unsqueeze(2)
+  ctrl = OM.run_mlp(h, wt, 'ctrl_mlp', [None])[-1]
+  flags = 0
+  if opt['dynamic_var']:
+    flags |= _lib.CTRL_DYNAMIC_VAR
+  if opt['fixed_gamma']:
+    flags |= _lib.CTRL_FIXED_GAMMA
+  gates = 'ifou'
+  h_out, ctrl_out, gm, box = ops.controller_step(
+      _g(feat), _g(np.stack([w['ctrl_lstm_w_x' + g] for g in gates])),
+      _g(np.stack([w['ctrl_lstm_w_h' + g] for g in gates])), _g(np.stack([w['ctrl_lstm_b_' + g] for g in gates])),
+      _g(w['glimpse_mlp_w_0']), _g(w['glimpse_mlp_b_0']), _g(w['glimpse_mlp_w_1']), _g(w['glimpse_mlp_b_1']),
+      _g(w['ctrl_mlp_w_0']), _g(w['ctrl_mlp_b_0']), H, W, 48, 48, flags)
+  assert rel_err(h_out.cpu().numpy(), h.numpy()) < TOL
+  assert rel_err(ctrl_out.cpu().numpy(), ctrl.numpy()) < TOL
+  assert rel_err(gm.cpu().numpy(), torch.stack(gmaps, 1).numpy()) < TOL
+  box = box.cpu().numpy()
+  img = np.array([H, W], np.float32)
+  ctr = (ctrl[:, 0:2].numpy() + 1) * img / 2
+  size = np.exp(ctrl[:, 2:4].numpy()) * img
+  assert rel_err(box[:, 0:2], ctr) < TOL and rel_err(box[:, 2:4], size) < TOL
+  lgv = ctrl[:, 4:6].numpy() if opt['dynamic_var'] else np.log(size) - np.log(48.0)
+  assert np.abs(box[:, 4:6] - lgv).max() < 1e-4
+  g_attn = np.ones(B) if opt['fixed_gamma'] else np.exp(ctrl[:, 6].numpy())
+  g_y = np.full(B, np.exp(2.0)) if opt['fixed_gamma'] else np.exp(ctrl[:, 8].numpy())
+  assert rel_err(box[:, 6], g_attn) < TOL and rel_err(box[:, 7], np.exp(ctrl[:, 7].numpy())) < TOL
+  assert rel_err(box[:, 8], g_y) < TOL
+  assert rel_err(box[:, 9:11], ctr - size / 2) < TOL and rel_err(box[:, 11:13], ctr + size / 2) < TOL
+
+
+# ----------------------------------------------------------------------------- attention
+def _boxes(rng, B, H, W, dense=False):
+  from rec_attend_b200 import _lib
+  box = np.zeros((B, _lib.BOX_STRIDE), np.float32)
+  box[:, 0] = rng.uniform(-0.1 * H, 1.1 * H, B)
+  box[:, 1] = rng.uniform(-0.1 * W, 1.1 * W, B)
+  box[:, 2] = rng.uniform(0.05 * H, 1.3 * H, B)
+  box[:, 3] = rng.uniform(0.05 * W, 1.3 * W, B)
+  box[:, 4:6] = rng.uniform(-1.0, 2.5, (B, 2)) if not dense else rng.uniform(5.0, 7.0, (B, 2))
+  box[:, 6] = rng.uniform(0.5, 2.0, B)
+  box[:, 7] = rng.uniform(20, 200, B)
+  box[:, 8] = rng.uniform(5, 50, B)
+  return box
+
+
+@pytest.mark.parametrize('H,W,Cs,dense', [(64, 128, 12, False), (128, 128, 3, False), (32, 64, 12, True),
+                                          (64, 64, 20, False)])
+def test_gaussian_filters_extract_paste(ops, H, W, Cs, dense):
+  rng = np.random.default_rng(H * 1000 + W + Cs)
+  B, F = 3, 48
+  D = Cs + 1
+  box = _boxes(rng, B, H, W, dense)
+  bt = torch.from_numpy(box)
+  fy, fx, band = ops.get_gaussian_filter(_g(box), H, W, F)
+  fy_o = OM.get_gaussian_filter(bt[:, 0], bt[:, 2], bt[:, 4], H, F)  # [B,H,F]
+  fx_o = OM.get_gaussian_filter(bt[:, 1], bt[:, 3], bt[:, 5], W, F)
+  assert rel_err(fy.cpu().numpy(), fy_o.transpose(1, 2).numpy()) < TOL
+  assert rel_err(fx.cpu().numpy(), fx_o.transpose(1, 2).numpy()) < TOL
+  # glimpse
+  static_idx = [0, 1, 2] + list(range(4, D))
+  chan_map = torch.tensor(static_idx + [3], dtype=torch.int32, device='cuda')
+  xs = rng.random((B, H, W, Cs)).astype(np.float32)
+  canvas = rng.random((B, H, W)).astype(np.float32)
+  full = np.zeros((B, H, W, D), np.float32)
+  full[..., static_idx] = xs
+  full[..., 3] = canvas
+  patch = ops.extract_patch(_g(xs), _g(canvas), chan_map, _g(box), fy, fx, band)
+  ref = bt[:, 6].view(-1, 1, 1, 1) * OM.extract_patch(torch.from_numpy(full), fy_o, fx_o, D)
+  assert rel_err(patch.cpu().numpy(), ref.numpy()) < TOL
+  # paste-back + canvas update, both overwrite modes
+  P = np.maximum(rng.standard_normal((B, F, F)), 0).astype(np.float32)
+  for dis in (False, True):
+    cv = _g(canvas.copy())
+    T = 2
+    attn_box = torch.zeros((B, T, H, W), device='cuda')
+    y_out = torch.zeros((B, T, H, W), device='cuda')
+    ops.paste_back(_g(P), _g(box), fy, fx, cv, attn_box=attn_box[:, 1], y_out=y_out[:, 1], out_bstride=T * H * W,
+                   disable_overwrite=dis)
+    y_ref = OM.extract_patch(torch.from_numpy(P).unsqueeze(3), fy_o.transpose(1, 2), fx_o.transpose(1, 2), 1)[..., 0]
+    y_ref = torch.sigmoid(bt[:, 8].view(-1, 1, 1) * y_ref - 5.0)
+    if dis:
+      y_ref = y_ref * (1 - torch.from_numpy(canvas))
+    ones = torch.ones(B, F, F, 1) * bt[:, 7].view(-1, 1, 1, 1)
+    b_ref = torch.sigmoid(
+        OM.extract_patch(ones, fy_o.transpose(1, 2), fx_o.transpose(1, 2), 1)[..., 0] - 5.0)
+    assert rel_err(y_out[:, 1].cpu().numpy(), y_ref.numpy()) < TOL
+    assert rel_err(attn_box[:, 1].cpu().numpy(), b_ref.numpy()) < TOL
+    assert float(y_out[:, 0].abs().max()) == 0.0 and float(attn_box[:, 0].abs().max()) == 0.0
+    assert rel_err(cv.cpu().numpy(), torch.maximum(torch.from_numpy(canvas), y_ref).numpy()) < TOL
+  # attention box only (box model)
+  only = torch.zeros((B, 1, H, W), device='cuda')
+  ops.paste_back(None, _g(box), fy, fx, None, attn_box=only[:, 0], y_out=None, out_bstride=H * W)
+  assert rel_err(only[:, 0].cpu().numpy(), b_ref.numpy()) < TOL
+
+
+def test_score(ops):
+  rng = np.random.default_rng(8)
+  B, Hd, Cd, T = 5, 256, 3456, 4
+  h = rng.standard_normal((B, Hd)).astype(np.float32)
+  core = rng.standard_normal((B, 6, 6, 96)).astype(np.float32)
+  w = (rng.standard_normal(Hd + Cd) / 60).astype(np.float32)
+  bias = np.array([0.1], np.float32)
+  s = torch.zeros((B, T), device='cuda')
+  ops.score(_g(h), _g(core), _g(w), _g(bias), s[:, 2], T)
+  ref = 1 / (1 + np.exp(-(np.concatenate([h, core.reshape(B, -1)], 1) @ w + bias[0])))
+  assert rel_err(s[:, 2].cpu().numpy(), ref) < TOL and float(s[:, 0].abs().max()) == 0
+
+
+# ----------------------------------------------------------------------------- loss side
+def _masks(rng, B, T, H, W):
+  import rec_attend_b200 as ra
+  opt = {'inp_height': H, 'inp_width': W, 'timespan': T}
+  b = ra.synthetic.make_batch(opt, B, seed=int(rng.integers(1 << 30)))
+  return b['y_gt'], b['s_gt']
+
+
+def test_gt_box(ops):
+  rng = np.random.default_rng(3)
+  B, T, H, W = 3, 6, 64, 96
+  y_gt, _ = _masks(rng, B, T, H, W)
+  y_gt[0, 2] = 0  # an empty mask in the middle (modellib.py:696-699)
+  tl, br, box, rect, area = ops.get_gt_box(_g(y_gt), padding_ratio=0.2, min_padding=20.0)
+  tlo, bro, boxo = OM.get_gt_box(torch.from_numpy(y_gt), padding_ratio=0.2, min_padding=20.0)
+  assert (tl.cpu().numpy() == tlo.numpy()).all() and (br.cpu().numpy() == bro.numpy()).all()
+  assert (box.cpu().numpy() == boxo.numpy()).all()
+  assert (area.cpu().numpy() == y_gt.sum((2, 3))).all()
+
+
+@pytest.mark.parametrize('T,H,W', [(8, 32, 48), (20, 64, 64), (32, 32, 64)])
+def test_pairwise_iou(ops, T, H, W):
+  rng = np.random.default_rng(T)
+  B = 3
+  y_gt, _ = _masks(rng, B, T, H, W)
+  a = rng.random((B, T, H, W)).astype(np.float32)**2
+  iou = ops.f_iou(_g(a), _g(y_gt))
+  ref = OM.f_iou_pairwise(torch.from_numpy(a), torch.from_numpy(y_gt))
+  assert rel_err(iou.cpu().numpy(), ref.numpy()) < TOL
+  ih, dice = ops.f_iou(_g(a), _g(y_gt), hard_threshold=0.5, want_dice=True)
+  ah = torch.from_numpy((a > 0.5).astype(np.float32))
+  assert rel_err(ih.cpu().numpy(), OM.f_iou_pairwise(ah, torch.from_numpy(y_gt)).numpy()) < TOL
+  assert rel_err(dice.cpu().numpy(), OM.f_dice_pairwise(ah, torch.from_numpy(y_gt)).numpy()) < TOL
+  # rectangle form of b == the filled GT boxes
+  tl, br, box, rect, _ = ops.get_gt_box(_g(y_gt), padding_ratio=0.2, min_padding=4.0)
+  i1 = ops.f_iou(_g(a), box)
+  i2 = ops.f_iou(_g(a), None, b_rect=rect)
+  assert (i1 == i2).all()
+
+
+def test_loss_block(ops):
+  import rec_attend_b200 as ra
+  from rec_attend_b200 import _lib
+  rng = np.random.default_rng(6)
+  B, T, H, W = 4, 6, 32, 48
+  y_gt, s_gt = _masks(rng, B, T, H, W)
+  y_out = rng.random((B, T, H, W)).astype(np.float32)
+  attn_box = rng.random((B, T, H, W)).astype(np.float32)
+  s_out = rng.random((B, T)).astype(np.float32)
+  opt = ra.config.full_model_opt('kitti', H, W, T)
+  model = {'y_out': torch.from_numpy(y_out), 'attn_box': torch.from_numpy(attn_box), 's_out': torch.from_numpy(s_out)}
+  ref = OM.full_model_loss(opt, {}, model, torch.from_numpy(y_gt), torch.from_numpy(s_gt))
+  g = lambda k: _g(ref[k].numpy())
+  area = _g(y_gt.sum((2, 3)))
+  scal = ops.loss_block(g('iou_soft_box_pairwise'), g('match_box'), g('iou_soft_pairwise'), g('match'),
+                        g('iou_hard_pairwise'), _g(OM.f_dice_pairwise(torch.from_numpy((y_out > 0.5).astype(np.float32)),
+                                                                       torch.from_numpy(y_gt)).numpy()),
+                        _g(s_out), _g(s_gt), area, 1.0, 0.0).cpu().numpy()
+  for i, k in enumerate(_lib.LOSS_NAMES):
+    assert abs(float(scal[i]) - float(ref[k])) <= 1e-5 * max(1.0, abs(float(ref[k]))), (k, scal[i], float(ref[k]))
+
+
+def test_box_gt_step(ops):
+  rng = np.random.default_rng(12)
+  B, T, H, W = 3, 5, 32, 64
+  y_gt, _ = _masks(rng, B, T, H, W)
+  tl, br, boxgt, rect, _ = ops.get_gt_box(_g(y_gt), padding_ratio=0.2, min_padding=10.0)
+  attn = rng.random((B, 1, H, W)).astype(np.float32)
+  noise = (rng.random((B, H, W)) * 0.3).astype(np.float32)
+  canvas0 = (rng.random((B, H, W)) * 0.2).astype(np.float32)
+  canvas = _g(canvas0.copy())
+  iou_t = torch.zeros((B, T), device='cuda')
+  grd = torch.zeros((B, T), device='cuda')
+  ops.box_gt_step(_g(attn), H * W, rect, _g(y_gt), _g(noise), H * W, iou_t, T, grd, canvas)
+  a = torch.from_numpy(attn)
+  bg = boxgt.cpu()
+  ref_iou = OM.f_inter(a, bg) / OM.f_union(a, bg)
+  assert rel_err(iou_t.cpu().numpy(), ref_iou.numpy()) < TOL
+  g = OM.f_greedy_match(ref_iou, torch.zeros(B, T))
+  y_sel = (g.view(B, T, 1, 1) * torch.from_numpy(y_gt)).sum(1)
+  y_sel = y_sel - y_sel * torch.from_numpy(noise)
+  assert rel_err(canvas.cpu().numpy(), torch.maximum(y_sel, torch.from_numpy(canvas0)).numpy()) < TOL
