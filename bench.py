@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the recurrent-attention decoding hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config IDX]
+
+A "step" is one full eval-mode forward of the model over one synthetic batch: the T-step
+decode loop (controller CNN + glimpse LSTM + Gaussian glimpse + patch CNN + deconv mask head
++ paste-back/canvas) plus the matching loss block (pairwise IoU, Hungarian, losses).
+Metric: instance-masks/sec = (masks produced by all ranks) / (max-over-ranks device time).
+Default workload = BASELINE.json configs[2] (KITTI-arch 256x512, T=20, B=32 per GPU), the
+configuration the metric is quoted on; it fits one GPU.  Multi-GPU: one process per GPU
+(torchrun), the batch shards with no data-path collective (eval forward) -> weak scaling.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the roofline accounting.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+
+def load_peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return {'hbm_gbs': float(d['hbm_gbs']), 'bf16_tflops': float(d['bf16_tflops']), 'source': 'measured'}
+  return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'source': 'fallback'}
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index = index
+    self.lines = []
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
+      self.thread = threading.Thread(target=self._read)
+      self.thread.daemon = True
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for l in self.lines:
+      f = [t.strip() for t in l.split(',')]
+      if len(f) < 7:
+        continue
+      try:
+        sm.append(float(f[0]))
+        mx.append(float(f[1]))
+      except ValueError:
+        continue
+      for n, v in zip(names, f[3:7]):
+        if v.lower().startswith('active'):
+          reasons.add(n)
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------- roofline model
+def kernel_algorithmic_work(opt, B):
+  """Algorithmic bytes / flops PER LAUNCH of the HBM-/tensor-bound kernels.
+  Keys are the C-ABI entry points (one decode step of B images per launch unless noted)."""
+  H, W, T, F = opt['inp_height'], opt['inp_width'], opt['timespan'], opt['filter_height']
+  from rec_attend_b200.config import input_depths
+  D = input_depths(opt)[0]
+  c0 = opt['ctrl_cnn_depth'][0]
+  p0 = opt['ctrl_cnn_pool'][0]
+  work = {
+      # (H*W*D + F^2*D)*4 per image-step
+      'ra_gaussian_extract_f32': {'bytes': B * (H * W * D + F * F * D) * 4.0},
+      # (F^2 + 3*H*W)*4 (read patch + read canvas + write y_out + write canvas) + H*W*4 (attn_box write)
+      'ra_paste_back_f32': {'bytes': B * (F * F + 4 * H * W) * 4.0},
+      # pairwise IoU: 2*B*T*H*W*4 per call
+      'ra_pairwise_iou_f32': {'bytes': 2.0 * B * T * H * W * 4, 'flops': 2.0 * B * T * T * H * W},
+      'ra_gt_box_f32': {'bytes': 1.0 * B * T * H * W * 4},
+  }
+  # controller CNN: flops per decode step (all 8 layers, as the reference computes them)
+  ch = [D] + list(opt['ctrl_cnn_depth'])
+  h, w, fl = H, W, 0.0
+  for i, pl in enumerate(opt['ctrl_cnn_pool']):
+    fl += 2.0 * h * w * ch[i + 1] * 9 * ch[i]
+    h, w = h // pl, w // pl
+  work['ctrl_cnn_step'] = {'flops': B * fl,
+                           'bytes': B * (H * W * (c0 + 1) + (H // p0) * (W // p0) * c0) * 4.0}
+  return work
+
+
+class OpTimer(object):
+  """CUDA-event timing of every C-ABI call (on the stream the kernels are launched on)."""
+
+  def __init__(self, torch, lib_mod):
+    self.torch = torch
+    self.lib_mod = lib_mod
+    self.records = []
+    self.orig = None
+
+  def __enter__(self):
+    self.orig = self.lib_mod.call
+    torch = self.torch
+
+    def timed_call(name, *args):
+      e0 = torch.cuda.Event(enable_timing=True)
+      e1 = torch.cuda.Event(enable_timing=True)
+      e0.record()
+      self.orig(name, *args)
+      e1.record()
+      self.records.append((name, args, e0, e1, self.lib_mod.TAG))
+
+    self.lib_mod.call = timed_call
+    return self
+
+  def __exit__(self, *a):
+    self.lib_mod.call = self.orig
+
+  def summary(self):
+    self.torch.cuda.synchronize()
+    agg = {}
+    for name, args, e0, e1, tag in self.records:
+      key = name
+      if name == 'ra_conv3x3_f32':
+        # args: x1,C1,x2,C2,w,scale,shift,add_to,B,Hin,Win,Cout,up,pool,relu,y,stream
+        key = '{}:conv3x3[{}x{} {}+{}->{} up{} pool{}]'.format(tag, args[9], args[10], args[1], args[3], args[11],
+                                                             args[12], args[13])
+      d = agg.setdefault(key, {'entry': name, 'tag': tag, 'ms': 0.0, 'n': 0})
+      d['ms'] += e0.elapsed_time(e1)
+      d['n'] += 1
+    return agg
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_reference_time(opt, B_sample, steps, warmup, seed=1234):
+  """The reference's CPU implementation of the path = the structure-faithful oracle
+  (PyTorch-CPU restatement + C restatement of hungarian.cc), all host threads."""
+  import torch
+  import rec_attend_b200.config  # noqa: F401  (pure-python config/synthetic only; no CUDA)
+  from rec_attend_b200 import synthetic
+  from oracle import model as OM
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  batch = synthetic.make_batch(opt, B_sample, seed=seed)
+  weights = synthetic.make_weights(opt)
+  times = []
+  for i in range(warmup + steps):
+    t0 = time.perf_counter()
+    with torch.no_grad():
+      OM.full_model_forward(opt, weights, batch)
+    dt = time.perf_counter() - t0
+    if i >= warmup:
+      times.append(dt)
+  return sum(times) / len(times), cores
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return 0
+  from rec_attend_b200 import config
+  cfg = config.BASELINE_CONFIGS[args.config]
+  opt = config.baseline_opt(args.config)
+  B_sample = args.ref_batch
+  sec, cores = cpu_reference_time(opt, B_sample, max(1, args.steps), max(0, args.warmup))
+  masks = B_sample * cfg['T']
+  val = masks / sec
+  line = {
+      'impl': 'reference', 'metric': 'instance-masks/sec', 'value': val, 'unit': 'masks/s', 'n_gpus': args.gpus,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': cfg['name'], 'sample': 'B={} of the workload batch, full T={} decode + loss block'.format(
+          B_sample, cfg['T'])},
+      'cpu_baseline': {'value': val, 'unit': 'masks/s', 'cores': cores, 'kind': 'port',
+                       'sample': 'oracle (PyTorch-CPU restatement + C hungarian), B={} x T={} at {}x{}'.format(
+                           B_sample, cfg['T'], cfg['H'], cfg['W'])},
+      'e2e': {'value': val, 'unit': 'masks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line))
+  return 0
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  from rec_attend_b200 import _lib, config, synthetic
+  from rec_attend_b200.full_model import FullModel
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+  cfg = config.BASELINE_CONFIGS[args.config]
+  if cfg['model'] != 'full':
+    raise SystemExit('bench.py times the full model; the box model (config 4) is a parity-test case')
+  opt = config.baseline_opt(args.config)
+  B = args.batch or cfg['B']
+  T = cfg['T']
+  batch_np = synthetic.make_batch(opt, B, seed=1234 + args.config + 1000 * rank)
+  weights = synthetic.make_weights(opt)
+  model = FullModel(opt).load_weights(weights)
+  lib = _lib.lib()
+
+  # device-resident inputs for `value`; pinned host copies for `e2e`
+  dev_batch = {k: torch.from_numpy(v).cuda() for k, v in batch_np.items()}
+  pinned = {k: torch.from_numpy(v).pin_memory() for k, v in batch_np.items()}
+  fetch = ['loss', 'segm_loss', 'box_loss', 'conf_loss', 'iou_soft', 's_out', 'match']
+  host_out = {}
+
+  def step_device():
+    return model.forward(dev_batch, outputs=fetch)
+
+  def step_e2e():
+    # public API call with HOST buffers: H2D of every input, forward, D2H of the step's results
+    out = model.forward(pinned, outputs=fetch)
+    for k, v in out.items():
+      if k not in host_out:
+        host_out[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+      host_out[k].copy_(v, non_blocking=True)
+    return out
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    n0 = lib.ra_launch_count()
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.ra_launch_count() - n0
+    if world > 1:
+      t = torch.tensor([ms], device='cuda')
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms, launches
+
+  for _ in range(max(3, args.warmup)):
+    step_device()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  ms, launches = timed(step_device, args.steps)
+  clocks = sampler.stop() if rank == 0 else None
+  for _ in range(2):
+    step_e2e()
+  ms_e2e, _ = timed(step_e2e, args.steps)
+
+  masks_per_step = world * B * T
+  value = masks_per_step / (ms / args.steps / 1e3)
+  e2e_value = masks_per_step / (ms_e2e / args.steps / 1e3)
+  h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+  d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+
+  line = None
+  if rank == 0:
+    # ---- per-kernel device times (CUDA events around every C-ABI call, one extra instrumented step)
+    peaks = load_peaks()
+    with OpTimer(torch, _lib) as ot:
+      step_device()
+    agg = ot.summary()
+    work = kernel_algorithmic_work(opt, B)
+    total_ms = sum(d['ms'] for d in agg.values())
+    groups = {}
+    for key, d in agg.items():
+      g = d['entry']
+      if g == 'ra_conv3x3_f32':
+        g = 'ra_conv3x3_f32:' + d['tag']
+      gg = groups.setdefault(g, {'ms': 0.0, 'n': 0})
+      gg['ms'] += d['ms']
+      gg['n'] += d['n']
+    kernels = {}
+    for g, d in sorted(groups.items(), key=lambda kv: -kv[1]['ms']):
+      ent = {'ms_per_step': round(d['ms'], 4), 'launches': d['n'], 'share': round(d['ms'] / total_ms, 4)}
+      if g in work and 'bytes' in work[g]:
+        gbs = work[g]['bytes'] / (d['ms'] / d['n'] / 1e3) / 1e9
+        ent['achieved_gbs'] = round(gbs, 1)
+        ent['hbm_frac'] = round(gbs / peaks['hbm_gbs'], 4)
+      kernels[g] = ent
+    # controller-CNN as a group: flops of the 8 conv layers of one decode step / their time
+    ccnn_ms = sum(d['ms'] for k, d in agg.items() if d['entry'] == 'ra_conv3x3_f32' and d['tag'] == 'ctrl_cnn')
+    conv_tflops = work['ctrl_cnn_step']['flops'] * T / (ccnn_ms / 1e3) / 1e12 if ccnn_ms > 0 else 0.0
+    dom = max(groups.items(), key=lambda kv: kv[1]['ms'])[0]
+    if dom.startswith('ra_conv3x3_f32'):
+      roofline = {
+          'kernel': 'conv3x3_kernel (controller CNN, 8 layers x T steps; fp32 CUDA cores)', 'bound': 'tensor',
+          'achieved': round(conv_tflops, 3), 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+          'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': None,
+          'peak_source': peaks['source'] + ' (cuBLAS bf16 burst)',
+          'note': 'flops = the reference\'s 8 conv layers per decode step (the linear split of layer 0 does fewer)'
+      }
+    else:
+      k = kernels[dom]
+      roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': k.get('achieved_gbs'), 'peak': peaks['hbm_gbs'],
+                  'unit': 'GB/s', 'frac': k.get('hbm_frac'), 'traffic': None, 'peak_source': peaks['source']}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+      sec, cores = cpu_reference_time(opt, args.ref_batch, 2, 1)
+      cpu_baseline = {
+          'value': args.ref_batch * T / sec, 'unit': 'masks/s', 'cores': cores, 'kind': 'port',
+          'sample': 'oracle (PyTorch-CPU restatement + C hungarian), B={} x T={} at {}x{}, mean of 2 runs after 1 warm-up'.format(
+              args.ref_batch, T, cfg['H'], cfg['W'])
+      }
+    line = {
+        'metric': 'instance-masks/sec', 'value': value, 'unit': 'masks/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': cfg['name'], 'arch': cfg['arch'], 'batch_per_gpu': B, 'timespan': T,
+                   'height': cfg['H'], 'width': cfg['W'], 'parallelism': 'dp{}'.format(world),
+                   'l2': 'inputs {:.0f} MB + per-step working set exceed the 126 MB L2'.format(h2d / 1e6),
+                   'step': 'eval forward (T-step decode) + matching loss block'},
+        'e2e': {'value': e2e_value, 'unit': 'masks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': ms_e2e / args.steps, 'fetch': fetch},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': roofline,
+        'kernels': kernels,
+        'cpu_baseline': cpu_baseline,
+    }
+    print(json.dumps(line))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  return 0
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--config', type=int, default=2, help='index into BASELINE.json configs (default 2: KITTI 256x512 T=20 B=32)')
+  ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch size')
+  ap.add_argument('--ref-batch', type=int, default=4, help='batch size of the bounded CPU-baseline sample')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    return run_reference(args)
+  return run_ours(args)
+
+
+if __name__ == '__main__':
+  sys.exit(main())

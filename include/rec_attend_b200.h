@@ -43,6 +43,8 @@ int ra_version(void);
 int ra_device_count(void);
 /* Last CUDA error string seen by this thread inside the library ("" if none). */
 const char *ra_last_error(void);
+/* Number of kernels this library has launched in this process (monotonic). */
+unsigned long long ra_launch_count(void);
 
 /* --------------------------------------------------------------------------------------
  * Hungarian matching — replaces the TF custom op

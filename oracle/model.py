@@ -461,8 +461,9 @@ def full_model_forward(opt, weights, batch, with_loss=True):
     out['h_ctrl'].append(c['h'].unsqueeze(1))
 
   model = {k: torch.cat(v, 1) for k, v in out.items()}
-  gm = model.pop('glimpse_map')
-  model['ctrl_rnn_glimpse_map'] = gm.reshape(B, T, gm.shape[2], -1)
+  gm = model.pop('glimpse_map')  # full_model.py:897-907: [B, T, n_iter, h', w']
+  sub = int(np.prod(opt['ctrl_cnn_pool']))
+  model['ctrl_rnn_glimpse_map'] = gm.reshape(B, T, gm.shape[2], H // sub, W // sub)
   model['canvas'] = canvas
   if not with_loss:
     return model
@@ -581,8 +582,9 @@ def box_model_forward(opt, weights, batch, canvas_noise=None):
     out['glimpse_map'].append(c['glimpse_map'].unsqueeze(1))
     out['ctrl_out'].append(c['ctrl_out'].unsqueeze(1))
   model = {k: torch.cat(v, 1) for k, v in out.items()}
-  gm = model.pop('glimpse_map')
-  model['ctrl_rnn_glimpse_map'] = gm.reshape(B, T, gm.shape[2], -1)
+  gm = model.pop('glimpse_map')  # full_model.py:897-907: [B, T, n_iter, h', w']
+  sub = int(np.prod(opt['ctrl_cnn_pool']))
+  model['ctrl_rnn_glimpse_map'] = gm.reshape(B, T, gm.shape[2], H // sub, W // sub)
   model['canvas'] = canvas
   model['attn_top_left_gt'], model['attn_bot_right_gt'], model['attn_box_gt'] = tl_gt, br_gt, box_gt
 

@@ -47,9 +47,11 @@ _SIGNATURES = {
     'ra_box_gt_step_f32': [_P, _Z, _P, _P, _P, _Z, _I, _I, _I, _I, _P, _I, _P, _P, _P],
     'ra_concat_channels_f32': [_P, _I, _P, _I, _P, _I, _Z, _P, _P],
 }
-EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last_error', 'ra_pairwise_iou_workspace'])
+EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last_error', 'ra_launch_count',
+                                         'ra_pairwise_iou_workspace'])
 
 _lib = None
+TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
 
 
 class RecAttendError(RuntimeError):
@@ -71,6 +73,7 @@ def lib():
     l.ra_version.restype = _I
     l.ra_device_count.restype = _I
     l.ra_last_error.restype = ctypes.c_char_p
+    l.ra_launch_count.restype = ctypes.c_ulonglong
     l.ra_pairwise_iou_workspace.argtypes = [_I, _I, _I, _I]
     l.ra_pairwise_iou_workspace.restype = _Z
     _lib = l

@@ -6,12 +6,14 @@
 namespace ra {
 
 static thread_local char g_last_error[256] = "";
+static unsigned long long g_launches = 0;  // kernels launched by this library (bench.py's gpu_launches)
 
 void set_last_error(const char *what, cudaError_t e) {
   snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
 }
 
 int finish_launch(const char *what) {
+  __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error(what, e);
@@ -35,3 +37,5 @@ extern "C" int ra_device_count(void) {
 }
 
 extern "C" const char *ra_last_error(void) { return ra::g_last_error; }
+
+extern "C" unsigned long long ra_launch_count(void) { return __atomic_load_n(&ra::g_launches, __ATOMIC_RELAXED); }

@@ -293,10 +293,14 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
     const int rowlen = W * Cs;
     dim3 grid((rowlen / 4 + 127) / 128, groups, B);
     extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(xs, H, rowlen, fy, band, F, tmp_s);
+    const int rc = ra::finish_launch("extract_rows_kernel");
+    if (rc != RA_OK) return rc;
   }
   if (canvas != nullptr) {
     dim3 grid((W / 4 + 127) / 128, groups, B);
     extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(canvas, H, W, fy, band, F, tmp_c);
+    const int rc = ra::finish_launch("extract_rows_kernel");
+    if (rc != RA_OK) return rc;
   }
   const int D = Cs + (canvas != nullptr ? 1 : 0);
   const size_t smem_cols = (size_t)W * D * sizeof(float);
@@ -313,7 +317,7 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
   extract_cols_kernel<<<dim3(F, B), 256, smem_cols, s>>>(Cs > 0 ? tmp_s : nullptr, Cs,
                                                          canvas != nullptr ? tmp_c : nullptr, chan_map, fx, band, box,
                                                          W, F, x_patch);
-  return ra::finish_launch("gaussian_extract");
+  return ra::finish_launch("extract_cols_kernel");
 }
 
 extern "C" int ra_paste_back_f32(const float *patch, const float *box, const float *fy, const float *fx, int B, int H,

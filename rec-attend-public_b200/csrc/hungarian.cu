@@ -266,9 +266,10 @@ __global__ void __launch_bounds__(32) hungarian_kernel(const float *__restrict__
 
 int launch(const float *W, const float *s_gt, int B, int nx, int ny, float *M, float *cx, float *cy, float *w_out,
            int32_t *status, cudaStream_t stream) {
-  if (B < 0 || nx < 1 || ny < 1 || W == nullptr || M == nullptr) return RA_ERR_INVALID_ARG;
+  if (B < 0 || nx < 1 || ny < 1) return RA_ERR_INVALID_ARG;
   if (nx > kMaxN || ny > kMaxN) return RA_ERR_UNSUPPORTED;
-  if (B == 0) return RA_OK;
+  if (B == 0) return RA_OK;  // empty batch: nothing to read or write
+  if (W == nullptr || M == nullptr) return RA_ERR_INVALID_ARG;
   const size_t smem = sizeof(WarpScratch) + (size_t)nx * ny * sizeof(float);
   hungarian_kernel<<<B, 32, smem, stream>>>(W, s_gt, nx, ny, M, cx, cy, w_out, status);
   return ra::finish_launch("hungarian_kernel");
@@ -289,9 +290,10 @@ extern "C" int ra_segm_match_f32(const float *iou, const float *s_gt, int B, int
 
 extern "C" int ra_hungarian_f32_host(const float *W, int B, int nx, int ny, float *M, float *cover_x, float *cover_y,
                                      int32_t *status) {
-  if (B < 0 || nx < 1 || ny < 1 || W == nullptr || M == nullptr) return RA_ERR_INVALID_ARG;
+  if (B < 0 || nx < 1 || ny < 1) return RA_ERR_INVALID_ARG;
   if (nx > kMaxN || ny > kMaxN) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
+  if (W == nullptr || M == nullptr) return RA_ERR_INVALID_ARG;
   const size_t nW = (size_t)B * nx * ny, nX = (size_t)B * nx, nY = (size_t)B * ny;
   float *d = nullptr;
   int32_t *dst = nullptr;

@@ -196,6 +196,7 @@ class _ModelBase(object):
     the first controller layer (conv is linear in its input channels; only the canvas
     channel changes between decode steps, full_model.py:640-663)."""
     w = self.w
+    _lib.TAG = 'prepare'
     ops.concat_channels(x, d_in, y_in, out=bufs['xs'])
     ops.conv3x3_block(bufs['xs'], w['ccnn_w0_static'], w['one_c0'], w['zero_c0'], pool=1, relu=False,
                       out=bufs['static_pre'])
@@ -206,12 +207,14 @@ class _ModelBase(object):
     w = self.w
     B, H, W = bufs['canvas'].shape
     cv = bufs['canvas'].view(B, H, W, 1)
+    _lib.TAG = 'ctrl_cnn'
     ops.conv3x3_block(cv, w['ccnn_w0_canvas'], w['ccnn_scale0'][t], w['ccnn_shift0'][t], pool=self.ctrl_pool[0],
                       relu=True, add_to=bufs['static_pre'], out=bufs['ccnn'][0])
     for i in range(1, len(self.ctrl_pool)):
       ops.conv3x3_block(bufs['ccnn'][i - 1], w['ccnn_w%d' % i], w['ccnn_scale%d' % i][t], w['ccnn_shift%d' % i][t],
                         pool=self.ctrl_pool[i], relu=True, out=bufs['ccnn'][i])
     feat = bufs['ccnn'][-1].view(B, self.P, -1)
+    _lib.TAG = 'controller'
     ops.controller_step(feat, w['lstm_wx'], w['lstm_wh'], w['lstm_b'], w['glimpse_mlp_w_0'], w['glimpse_mlp_b_0'],
                         w['glimpse_mlp_w_1'], w['glimpse_mlp_b_1'], w['ctrl_mlp_w_0'], w['ctrl_mlp_b_0'], self.H,
                         self.W, self.F, self.F, self.ctrl_flags, n_iter=self.n_iter, h_out=bufs['h_all'][t],
@@ -304,9 +307,11 @@ class FullModel(_ModelBase):
       self._controller(bufs, t)
       box_t = bufs['box_all'][t]
       x_patch = bufs['x_patch_all'][t]
+      _lib.TAG = 'extract'
       ops.extract_patch(bufs['xs'], bufs['canvas'], self.chan_map, box_t, bufs['fy'], bufs['fx'], bufs['band'],
                         tmp=bufs['extract_tmp'], out=x_patch)
       prev = x_patch
+      _lib.TAG = 'attn_cnn'
       for i, pl in enumerate(self.attn_pool):  # full_model.py:792
         ops.conv3x3_block(prev, w['acnn_w%d' % i], w['acnn_scale%d' % i][t], w['acnn_shift%d' % i][t], pool=pl,
                           relu=True, out=bufs['acnn'][i])
@@ -317,12 +322,14 @@ class FullModel(_ModelBase):
       skips = [None] + (bufs['acnn'][::-1][1:] + [x_patch])
       prev = core
       n_d = len(self.dcnn_pool)
+      _lib.TAG = 'attn_dcnn'
       for i, pl in enumerate(self.dcnn_pool):
         sk = skips[i] if (self.use_skip and self.skip_ch[i] > 0) else None
         dst = bufs['y_patch_all'][t] if i == n_d - 1 else bufs['adcnn'][i]
         ops.conv3x3_block(prev, w['adcnn_w%d' % i], w['adcnn_scale%d' % i][t], w['adcnn_shift%d' % i][t], pool=1,
                           relu=True, x2=sk, upsample=pl, out=dst)
         prev = dst
+      _lib.TAG = 'paste_back'
       ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],
                      attn_box=bufs['attn_box'][:, t], y_out=bufs['y_out'][:, t], out_bstride=thw,
                      disable_overwrite=self.disable_overwrite)
@@ -330,6 +337,7 @@ class FullModel(_ModelBase):
   def _loss(self, bufs, y_gt, s_gt, out, want_gt_box):
     """full_model.py:916-1081 (matching on soft IoU, 'iou' losses, hard statistics)."""
     o = self.opt
+    _lib.TAG = 'loss'
     tl, br, box_gt, rect, area = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'],
                                                 min_padding=self.min_padding, want_box=want_gt_box)
     iou_box = ops.f_iou(bufs['attn_box'], None, b_rect=rect)
