@@ -152,6 +152,10 @@ class OpTimer(object):
         # args: x1,C1,x2,C2,w,scale,shift,add_to,B,Hin,Win,Cout,up,pool,relu,y,stream
         key = '{}:conv3x3[{}x{} {}+{}->{} up{} pool{}]'.format(tag, args[9], args[10], args[1], args[3], args[11],
                                                              args[12], args[13])
+      if name == 'ra_conv3x3_umma_f32':
+        # args: x1,C1,x2,C2,wpack,scale,shift,B,Hin,Win,Cout,up,pool,relu,y,stream
+        key = '{}:conv3x3_umma[{}x{} {}+{}->{} up{} pool{}]'.format(tag, args[8], args[9], args[1], args[3], args[10],
+                                                                  args[11], args[12])
       d = agg.setdefault(key, {'entry': name, 'tag': tag, 'ms': 0.0, 'n': 0})
       d['ms'] += e0.elapsed_time(e1)
       d['n'] += 1
@@ -304,8 +308,8 @@ def run_ours(args):
     groups = {}
     for key, d in agg.items():
       g = d['entry']
-      if g == 'ra_conv3x3_f32':
-        g = 'ra_conv3x3_f32:' + d['tag']
+      if g in ('ra_conv3x3_f32', 'ra_conv3x3_umma_f32'):
+        g = g + ':' + d['tag']
       gg = groups.setdefault(g, {'ms': 0.0, 'n': 0})
       gg['ms'] += d['ms']
       gg['n'] += d['n']
@@ -318,12 +322,14 @@ def run_ours(args):
         ent['hbm_frac'] = round(gbs / peaks['hbm_gbs'], 4)
       kernels[g] = ent
     # controller-CNN as a group: flops of the 8 conv layers of one decode step / their time
-    ccnn_ms = sum(d['ms'] for k, d in agg.items() if d['entry'] == 'ra_conv3x3_f32' and d['tag'] == 'ctrl_cnn')
+    ccnn_ms = sum(d['ms'] for k, d in agg.items()
+                  if d['entry'] in ('ra_conv3x3_f32', 'ra_conv3x3_umma_f32') and d['tag'] == 'ctrl_cnn')
     conv_tflops = work['ctrl_cnn_step']['flops'] * T / (ccnn_ms / 1e3) / 1e12 if ccnn_ms > 0 else 0.0
     dom = max(groups.items(), key=lambda kv: kv[1]['ms'])[0]
-    if dom.startswith('ra_conv3x3_f32'):
+    if dom.startswith('ra_conv3x3'):
       roofline = {
-          'kernel': 'conv3x3_kernel (controller CNN, 8 layers x T steps; fp32 CUDA cores)', 'bound': 'tensor',
+          'kernel': 'conv3x3_umma_kernel (controller CNN layers, tcgen05 kind::tf32 x3 split; group = ' + dom + ')',
+          'bound': 'tensor',
           'achieved': round(conv_tflops, 3), 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
           'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': None,
           'peak_source': peaks['source'] + ' (cuBLAS bf16 burst)',
@@ -342,6 +348,8 @@ def run_ours(args):
           'sample': 'oracle (PyTorch-CPU restatement + C hungarian), B={} x T={} at {}x{}, mean of 2 runs after 1 warm-up'.format(
               args.ref_batch, T, cfg['H'], cfg['W'])
       }
+    layers = {k: {'ms': round(d['ms'], 4), 'n': d['n']} for k, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
+              if 'conv3x3' in k}
     line = {
         'metric': 'instance-masks/sec', 'value': value, 'unit': 'masks/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -356,6 +364,7 @@ def run_ours(args):
         'clocks': clocks,
         'roofline': roofline,
         'kernels': kernels,
+        'conv_layers': layers,
         'cpu_baseline': cpu_baseline,
     }
     print(json.dumps(line))

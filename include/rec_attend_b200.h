@@ -87,6 +87,29 @@ int ra_conv3x3_f32(const float *x1, int C1, const float *x2, int C2, const float
                    const float *shift, const float *add_to, int B, int Hin, int Win, int Cout, int upsample,
                    int pool, int relu, float *y, void *stream);
 
+/* First controller layer, per-step half (full_model.py:640-663): the layer is linear in its
+ * input channels and only the canvas channel changes between decode steps, so
+ *   y = pool(relu((pre + conv3x3(canvas; w)) * scale + shift))
+ * with pre [B,H,W,C0] = the raw convolution of the step-invariant channels (computed once per
+ * forward), canvas [B,H,W], w [3,3,1,C0].  C0 % 4 == 0, pool in {1,2}.  y [B,H/pool,W/pool,C0]. */
+int ra_canvas_conv_f32(const float *pre, const float *canvas, const float *w, const float *scale,
+                       const float *shift, int B, int H, int W, int C0, int pool, int relu, float *y, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * The same convolution block on the tcgen05 tensor cores (kind::tf32, accumulators in TMEM)
+ * with the 3xTF32 split (hi*hi + hi*lo + lo*hi, ~2^-21 relative) that the 1e-3 parity bar
+ * needs.  Arguments as ra_conv3x3_f32 except: no add_to, and the filter is pre-packed by the
+ * caller into the kernel's shared-memory image
+ *   wpack [n_chunks][9 taps][2 (hi, lo)][KC/4][NP][4]
+ * (element [ch][tap][h][c4][n][j] = hi/lo part of w[tap][ch*KC + 4*c4 + j][n], zero padded),
+ * with KC, NP, n_chunks given by ra_conv3x3_umma_plan for the layer's (Cin, Cout, output size,
+ * pool).  Supported: Cout <= 256, output width >= 8 and even.
+ * -------------------------------------------------------------------------------------- */
+int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int *KC, int *NP, int *n_chunks);
+int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int C2, const float *wpack, const float *scale,
+                        const float *shift, int B, int Hin, int Win, int Cout, int upsample, int pool, int relu,
+                        float *y, void *stream);
+
 /* --------------------------------------------------------------------------------------
  * Controller step — full_model.py:668-725 / box_model.py:417-470: 5 soft-attention glimpse
  * read-outs of the controller feature map, LSTM (nnlib.py:637-649, state reset to 0),

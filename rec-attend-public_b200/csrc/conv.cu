@@ -188,6 +188,85 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvParams p) {
   }
 }
 
+// First controller layer, per-step half (full_model.py:640-663).  conv(concat(x, canvas, d, y)) is
+// linear in its input channels and only the canvas changes between decode steps, so the
+// step-invariant channels are convolved once per forward (pre [B,H,W,C0]) and every step adds
+// the 1-channel canvas convolution: y = pool(relu((pre + conv(canvas)) * scale + shift)).
+// HBM-bound: one read of pre, one of the canvas, one write of the pooled map.  A thread owns
+// one pooled pixel x 4 channels: a 4x4 canvas patch (L1), 4 float4 of pre, 9x4 weights in
+// registers.
+template <int POOL>
+__global__ void __launch_bounds__(256) canvas_conv_kernel(const float *__restrict__ pre,
+                                                          const float *__restrict__ canvas,
+                                                          const float *__restrict__ w, const float *__restrict__ scale,
+                                                          const float *__restrict__ shift, int B, int H, int W, int C0,
+                                                          int relu, float *__restrict__ y) {
+  const int cg_n = C0 >> 2;
+  const int Ho = H / POOL, Wo = W / POOL;
+  const size_t total = (size_t)B * Ho * Wo * cg_n;
+  const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cg = (int)(gid % cg_n);
+  size_t pix = gid / cg_n;
+  const int ox = (int)(pix % Wo);
+  pix /= Wo;
+  const int oy = (int)(pix % Ho);
+  const int b = (int)(pix / Ho);
+  const int c = cg * 4;
+
+  float4 wk[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wk[k] = __ldg(reinterpret_cast<const float4 *>(w + k * C0 + c));
+  const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
+
+  // canvas patch (POOL+2)^2 around the POOL x POOL window, zero padded (SAME)
+  float cv[POOL + 2][POOL + 2];
+  const float *cb = canvas + (size_t)b * H * W;
+  const int y0 = oy * POOL - 1, x0 = ox * POOL - 1;
+#pragma unroll
+  for (int r = 0; r < POOL + 2; ++r)
+#pragma unroll
+    for (int q = 0; q < POOL + 2; ++q) {
+      const int yy = y0 + r, xx = x0 + q;
+      cv[r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(cb + (size_t)yy * W + xx) : 0.f;
+    }
+  float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int py = 0; py < POOL; ++py)
+#pragma unroll
+    for (int px = 0; px < POOL; ++px) {
+      const int yy = oy * POOL + py, xx = ox * POOL + px;
+      float4 a = __ldcs(reinterpret_cast<const float4 *>(pre + (((size_t)b * H + yy) * W + xx) * C0 + c));
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = cv[py + ky][px + kx];
+          const float4 ww = wk[ky * 3 + kx];
+          a.x = fmaf(v, ww.x, a.x);
+          a.y = fmaf(v, ww.y, a.y);
+          a.z = fmaf(v, ww.z, a.z);
+          a.w = fmaf(v, ww.w, a.w);
+        }
+      a.x = fmaf(a.x, sc.x, sh.x);
+      a.y = fmaf(a.y, sc.y, sh.y);
+      a.z = fmaf(a.z, sc.z, sh.z);
+      a.w = fmaf(a.w, sc.w, sh.w);
+      if (relu) {
+        a.x = fmaxf(a.x, 0.f);
+        a.y = fmaxf(a.y, 0.f);
+        a.z = fmaxf(a.z, 0.f);
+        a.w = fmaxf(a.w, 0.f);
+      }
+      best.x = fmaxf(best.x, a.x);
+      best.y = fmaxf(best.y, a.y);
+      best.z = fmaxf(best.z, a.z);
+      best.w = fmaxf(best.w, a.w);
+    }
+  *reinterpret_cast<float4 *>(y + (((size_t)b * Ho + oy) * Wo + ox) * C0 + c) = best;
+}
+
 // out[b,h,w,:] = concat(a[b,h,w,:Ca], bsrc[...,:Cb], c[...,:Cc]) — builds the step-invariant
 // input stack of full_model.py:640-661 once per forward.
 __global__ void concat_channels_kernel(const float *__restrict__ a, int Ca, const float *__restrict__ bsrc, int Cb,
@@ -283,4 +362,22 @@ extern "C" int ra_concat_channels_f32(const float *a, int Ca, const float *b, in
   if (blocks > (size_t)ra::kNumSMs * 16) blocks = (size_t)ra::kNumSMs * 16;
   concat_channels_kernel<<<(unsigned)blocks, 256, 0, ra::as_stream(stream)>>>(a, Ca, b, Cb, c, Cc, npix, out);
   return ra::finish_launch("concat_channels_kernel");
+}
+
+extern "C" int ra_canvas_conv_f32(const float *pre, const float *canvas, const float *w, const float *scale,
+                                  const float *shift, int B, int H, int W, int C0, int pool, int relu, float *y,
+                                  void *stream) {
+  if (!pre || !canvas || !w || !scale || !shift || !y || B < 0 || H < 1 || W < 1 || C0 < 1) return RA_ERR_INVALID_ARG;
+  if ((C0 & 3) != 0 || (pool != 1 && pool != 2)) return RA_ERR_UNSUPPORTED;
+  if (pool == 2 && ((H | W) & 1)) return RA_ERR_UNSUPPORTED;
+  if (B == 0) return RA_OK;
+  const size_t total = (size_t)B * (H / pool) * (W / pool) * (C0 / 4);
+  const size_t blocks = (total + 255) / 256;
+  if (blocks > 0x7fffffffULL) return RA_ERR_UNSUPPORTED;
+  cudaStream_t s = ra::as_stream(stream);
+  if (pool == 2)
+    canvas_conv_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
+  else
+    canvas_conv_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
+  return ra::finish_launch("canvas_conv_kernel");
 }

@@ -104,15 +104,17 @@ class _ModelBase(object):
     w0 = np.asarray(weights['ctrl_cnn_w_0'], np.float32)
     if w0.shape[2] != self.D:
       raise _lib.RecAttendError('ctrl_cnn_w_0 has {} input channels, expected {}'.format(w0.shape[2], self.D))
-    w['ccnn_w0_static'] = self._dev(w0[:, :, self.static_idx, :])
     w['ccnn_w0_canvas'] = self._dev(w0[:, :, 3:4, :])
     c0 = w0.shape[3]
     w['one_c0'] = torch.ones(c0, device=self.device)
     w['zero_c0'] = torch.zeros(c0, device=self.device)
+    h, wd_ = self.H, self.W
+    w['ccnn_w0_static_umma'] = self._pack(w0[:, :, self.static_idx, :], h, wd_, 1)
     for i in range(n):
       wi = np.asarray(weights['ctrl_cnn_w_%d' % i], np.float32)
       if i > 0:
-        w['ccnn_w%d' % i] = self._dev(wi)
+        w['ccnn_w%d' % i] = self._pack(wi, h, wd_, self.ctrl_pool[i])
+      h, wd_ = h // self.ctrl_pool[i], wd_ // self.ctrl_pool[i]
       sc, sh = _fold_bn(weights, 'ctrl_cnn', i, T, np.asarray(weights['ctrl_cnn_b_%d' % i], np.float32))
       w['ccnn_scale%d' % i] = self._dev(sc)
       w['ccnn_shift%d' % i] = self._dev(sh)
@@ -128,6 +130,18 @@ class _ModelBase(object):
       raise _lib.RecAttendError('glimpse_mlp_w_1 maps to {} positions, the feature map has {}'.format(
           w['glimpse_mlp_w_1'].shape[1], self.P))
     return w
+
+  def _pack(self, w_hwio, Hout, Wout, pool):
+    """Pre-pack a conv-form HWIO filter into the tcgen05 kernel's shared-memory image for a layer
+    whose (un-pooled) output is Hout x Wout."""
+    w_hwio = np.asarray(w_hwio, np.float32)
+    KC, NP, _ = ops.umma_plan(w_hwio.shape[2], w_hwio.shape[3], Hout, Wout, pool)
+    return (self._dev(ops.pack_umma_weights(w_hwio, KC, NP)), int(w_hwio.shape[3]))
+
+  def _conv(self, x, wp, scale, shift, pool, relu=True, x2=None, upsample=1, out=None):
+    """One conv block on the tensor cores (csrc/conv_umma.cu)."""
+    return ops.conv3x3_block_umma(x, wp[0], wp[1], scale, shift, pool=pool, relu=relu, x2=x2, upsample=upsample,
+                                  out=out)
 
   def _weight_decay_term(self, weights):
     """nnlib.py:59-61: sum over conv/mlp/lstm weight matrices of wd * ||w||^2 / 2 (a constant
@@ -198,21 +212,20 @@ class _ModelBase(object):
     w = self.w
     _lib.TAG = 'prepare'
     ops.concat_channels(x, d_in, y_in, out=bufs['xs'])
-    ops.conv3x3_block(bufs['xs'], w['ccnn_w0_static'], w['one_c0'], w['zero_c0'], pool=1, relu=False,
-                      out=bufs['static_pre'])
+    self._conv(bufs['xs'], w['ccnn_w0_static_umma'], w['one_c0'], w['zero_c0'], 1, relu=False,
+               out=bufs['static_pre'])
     bufs['canvas'].zero_()  # full_model.py:239
 
   def _controller(self, bufs, t):
     """full_model.py:663-725: controller CNN (BN copy t) + glimpse LSTM + head -> box params."""
     w = self.w
     B, H, W = bufs['canvas'].shape
-    cv = bufs['canvas'].view(B, H, W, 1)
     _lib.TAG = 'ctrl_cnn'
-    ops.conv3x3_block(cv, w['ccnn_w0_canvas'], w['ccnn_scale0'][t], w['ccnn_shift0'][t], pool=self.ctrl_pool[0],
-                      relu=True, add_to=bufs['static_pre'], out=bufs['ccnn'][0])
+    ops.canvas_conv(bufs['static_pre'], bufs['canvas'], w['ccnn_w0_canvas'], w['ccnn_scale0'][t],
+                    w['ccnn_shift0'][t], pool=self.ctrl_pool[0], relu=True, out=bufs['ccnn'][0])
     for i in range(1, len(self.ctrl_pool)):
-      ops.conv3x3_block(bufs['ccnn'][i - 1], w['ccnn_w%d' % i], w['ccnn_scale%d' % i][t], w['ccnn_shift%d' % i][t],
-                        pool=self.ctrl_pool[i], relu=True, out=bufs['ccnn'][i])
+      self._conv(bufs['ccnn'][i - 1], w['ccnn_w%d' % i], w['ccnn_scale%d' % i][t], w['ccnn_shift%d' % i][t],
+                 self.ctrl_pool[i], out=bufs['ccnn'][i])
     feat = bufs['ccnn'][-1].view(B, self.P, -1)
     _lib.TAG = 'controller'
     ops.controller_step(feat, w['lstm_wx'], w['lstm_wh'], w['lstm_b'], w['glimpse_mlp_w_0'], w['glimpse_mlp_b_0'],
@@ -266,12 +279,16 @@ class FullModel(_ModelBase):
     T = self.T
     self._raw_weights = {k: np.asarray(v, np.float32) for k, v in weights.items()}
     w = self._load_controller(weights)
+    sz = self.F
     for i in range(len(self.attn_pool)):
-      w['acnn_w%d' % i] = self._dev(weights['attn_cnn_w_%d' % i])
+      w['acnn_w%d' % i] = self._pack(weights['attn_cnn_w_%d' % i], sz, sz, self.attn_pool[i])
+      sz //= self.attn_pool[i]
       sc, sh = _fold_bn(weights, 'attn_cnn', i, T, np.asarray(weights['attn_cnn_b_%d' % i], np.float32))
       w['acnn_scale%d' % i], w['acnn_shift%d' % i] = self._dev(sc), self._dev(sh)
     for i in range(len(self.dcnn_pool)):
-      w['adcnn_w%d' % i] = self._dev(_deconv_to_conv(np.asarray(weights['attn_dcnn_w_%d' % i], np.float32)))
+      sz *= self.dcnn_pool[i]
+      w['adcnn_w%d' % i] = self._pack(_deconv_to_conv(np.asarray(weights['attn_dcnn_w_%d' % i], np.float32)), sz, sz,
+                                      1)
       sc, sh = _fold_bn(weights, 'attn_dcnn', i, T, np.asarray(weights['attn_dcnn_b_%d' % i], np.float32))
       w['adcnn_scale%d' % i], w['adcnn_shift%d' % i] = self._dev(sc), self._dev(sh)
     self.w = w
@@ -313,8 +330,8 @@ class FullModel(_ModelBase):
       prev = x_patch
       _lib.TAG = 'attn_cnn'
       for i, pl in enumerate(self.attn_pool):  # full_model.py:792
-        ops.conv3x3_block(prev, w['acnn_w%d' % i], w['acnn_scale%d' % i][t], w['acnn_shift%d' % i][t], pool=pl,
-                          relu=True, out=bufs['acnn'][i])
+        self._conv(prev, w['acnn_w%d' % i], w['acnn_scale%d' % i][t], w['acnn_shift%d' % i][t], pl,
+                   out=bufs['acnn'][i])
         prev = bufs['acnn'][i]
       core = bufs['acnn'][-1]
       ops.score(bufs['h_all'][t], core, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
@@ -326,8 +343,8 @@ class FullModel(_ModelBase):
       for i, pl in enumerate(self.dcnn_pool):
         sk = skips[i] if (self.use_skip and self.skip_ch[i] > 0) else None
         dst = bufs['y_patch_all'][t] if i == n_d - 1 else bufs['adcnn'][i]
-        ops.conv3x3_block(prev, w['adcnn_w%d' % i], w['adcnn_scale%d' % i][t], w['adcnn_shift%d' % i][t], pool=1,
-                          relu=True, x2=sk, upsample=pl, out=dst)
+        self._conv(prev, w['adcnn_w%d' % i], w['adcnn_scale%d' % i][t], w['adcnn_shift%d' % i][t], 1, x2=sk,
+                   upsample=pl, out=dst)
         prev = dst
       _lib.TAG = 'paste_back'
       ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],

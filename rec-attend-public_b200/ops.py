@@ -90,6 +90,54 @@ def conv3x3_block(x, w, scale, shift, pool=1, relu=True, x2=None, upsample=1, ad
   return out
 
 
+def canvas_conv(pre, canvas, w, scale, shift, pool=1, relu=True, out=None):
+  """Per-step half of the first controller layer: pool(relu((pre + conv(canvas)) * scale + shift))."""
+  _chk(pre, canvas, w, scale, shift, out)
+  B, H, W, C0 = pre.shape
+  if out is None:
+    out = torch.empty((B, H // pool, W // pool, C0), device=pre.device, dtype=torch.float32)
+  _lib.call('ra_canvas_conv_f32', _p(pre), _p(canvas), _p(w), _p(scale), _p(shift), B, H, W, C0, pool,
+            1 if relu else 0, _p(out), _stream())
+  return out
+
+
+def umma_plan(Cin, Cout, Hout, Wout, pool):
+  """(KC, NP, n_chunks) of the tcgen05 conv kernel for one layer shape."""
+  kc, npad, nch = _c.c_int(0), _c.c_int(0), _c.c_int(0)
+  _lib.call('ra_conv3x3_umma_plan', Cin, Cout, Hout, Wout, pool, _c.byref(kc), _c.byref(npad), _c.byref(nch))
+  return kc.value, npad.value, nch.value
+
+
+def pack_umma_weights(w_hwio, KC, NP):
+  """HWIO conv filter [3,3,Cin,Cout] (numpy) -> the kernel's shared-memory image
+  [n_chunks][9][2 (hi,lo)][KC/4][NP][4]: hi = w with the low 13 mantissa bits cleared, lo = w - hi."""
+  import numpy as np
+  w = np.asarray(w_hwio, np.float32)
+  _, _, Cin, Cout = w.shape
+  n_chunks = (Cin + KC - 1) // KC
+  wp = np.zeros((9, n_chunks * KC, NP), np.float32)
+  wp[:, :Cin, :Cout] = w.reshape(9, Cin, Cout)
+  hi = (wp.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+  lo = wp - hi
+  def lay(a):  # [9, chunks*KC, NP] -> [chunks, 9, KC/4, NP, 4]
+    return a.reshape(9, n_chunks, KC // 4, 4, NP).transpose(1, 0, 2, 4, 3)
+  return np.ascontiguousarray(np.stack([lay(hi), lay(lo)], axis=2))
+
+
+def conv3x3_block_umma(x, wpack, Cout, scale, shift, pool=1, relu=True, x2=None, upsample=1, out=None):
+  """conv3x3_block on the tensor cores (3xTF32); wpack from pack_umma_weights for this layer's plan."""
+  _chk(x, wpack, scale, shift, x2, out)
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  Ho, Wo = H * upsample // pool, W * upsample // pool
+  if out is None:
+    out = torch.empty((B, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+  assert tuple(out.shape) == (B, Ho, Wo, Cout)
+  _lib.call('ra_conv3x3_umma_f32', _p(x), C1, _p(x2), C2, _p(wpack), _p(scale), _p(shift), B, H, W, Cout, upsample,
+            pool, 1 if relu else 0, _p(out), _stream())
+  return out
+
+
 def concat_channels(a, b=None, c=None, out=None):
   _chk(a, b, c, out)
   B, H, W, Ca = a.shape

@@ -392,3 +392,78 @@ def test_box_gt_step(ops):
   y_sel = (g.view(B, T, 1, 1) * torch.from_numpy(y_gt)).sum(1)
   y_sel = y_sel - y_sel * torch.from_numpy(noise)
   assert rel_err(canvas.cpu().numpy(), torch.maximum(y_sel, torch.from_numpy(canvas0)).numpy()) < TOL
+
+
+# ----------------------------------------------------------------------------- tcgen05 conv
+UMMA_CASES = [
+    # B, H, W, C1, C2, Cout, up, pool, relu   (the KITTI/Cityscapes-arch layers + odd shapes)
+    (2, 128, 256, 16, 0, 16, 1, 2, 1),   # ctrl L1
+    (2, 64, 128, 16, 0, 32, 1, 1, 1),    # ctrl L2
+    (2, 64, 128, 32, 0, 32, 1, 2, 1),    # ctrl L3
+    (2, 32, 64, 32, 0, 64, 1, 1, 1),     # ctrl L4
+    (2, 32, 64, 64, 0, 64, 1, 2, 1),     # ctrl L5
+    (3, 16, 32, 64, 0, 64, 1, 1, 1),     # ctrl L6
+    (3, 16, 32, 64, 0, 64, 1, 2, 1),     # ctrl L7
+    (2, 48, 48, 13, 0, 16, 1, 1, 1),     # attn L0 (Cin not a multiple of 4)
+    (2, 48, 48, 16, 0, 32, 1, 2, 1),     # attn L1
+    (2, 24, 24, 32, 0, 64, 1, 2, 1),     # attn L3
+    (2, 12, 12, 64, 0, 96, 1, 2, 1),     # attn L5 (N = 96)
+    (2, 6, 6, 96, 0, 64, 2, 1, 1),       # dcnn L0 (stride-2 transposed)
+    (2, 12, 12, 64, 64, 64, 1, 1, 1),    # dcnn L1 (skip concat)
+    (2, 12, 12, 64, 64, 32, 2, 1, 1),    # dcnn L2
+    (2, 24, 24, 32, 32, 16, 2, 1, 1),    # dcnn L4
+    (2, 48, 48, 16, 13, 1, 1, 1, 1),     # dcnn L6 (Cout = 1, odd skip)
+    (1, 34, 70, 8, 0, 8, 1, 2, 0),       # ragged tiles, Cout = 8 (CVPPP-arch)
+    (1, 512, 1024, 16, 0, 16, 1, 2, 1),  # Cityscapes-size ctrl L1
+]
+
+
+@pytest.mark.parametrize('case', UMMA_CASES)
+def test_conv3x3_block_umma(ops, case):
+  B, H, W, C1, C2, Cout, up, pool, relu = case
+  rng = np.random.default_rng(hash(case) % 2**31)
+  x1 = rng.standard_normal((B, H, W, C1)).astype(np.float32)
+  x2 = rng.standard_normal((B, H, W, C2)).astype(np.float32) if C2 else None
+  Cin = C1 + C2
+  scale = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+  shift = rng.standard_normal(Cout).astype(np.float32)
+  xin = torch.from_numpy(x1 if x2 is None else np.concatenate([x1, x2], 3))
+  if up == 1:
+    w = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    ref = OM.conv2d_same(xin, torch.from_numpy(w), torch.zeros(Cout))
+  else:
+    from rec_attend_b200.full_model import _deconv_to_conv
+    wt = (rng.standard_normal((3, 3, Cout, Cin)) / np.sqrt(9 * Cin)).astype(np.float32)
+    ref = OM.conv2d_transpose_same(xin, torch.from_numpy(wt), torch.zeros(Cout), up)
+    w = _deconv_to_conv(wt)
+  ref = ref * torch.from_numpy(scale) + torch.from_numpy(shift)
+  if relu:
+    ref = torch.relu(ref)
+  if pool == 2:
+    ref = OM.max_pool_same(ref, 2)
+  KC, NP, nch = ops.umma_plan(Cin, Cout, H * up, W * up, pool)
+  wp = ops.pack_umma_weights(w, KC, NP)
+  assert wp.shape == (nch, 9, 2, KC // 4, NP, 4)
+  out = ops.conv3x3_block_umma(_g(x1), _g(wp), Cout, _g(scale), _g(shift), pool=pool, relu=bool(relu),
+                               x2=None if x2 is None else _g(x2), upsample=up)
+  torch.cuda.synchronize()
+  assert tuple(out.shape) == tuple(ref.shape)
+  # 3xTF32: ~2^-21 per product; 1e-5 of the tensor scale leaves margin
+  assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('C0,pool,H,W', [(16, 2, 32, 64), (8, 1, 24, 40), (16, 1, 16, 16), (8, 2, 64, 32)])
+def test_canvas_conv(ops, C0, pool, H, W):
+  rng = np.random.default_rng(C0 * 10 + pool)
+  B = 2
+  pre = rng.standard_normal((B, H, W, C0)).astype(np.float32)
+  canvas = rng.random((B, H, W)).astype(np.float32)
+  w = (rng.standard_normal((3, 3, 1, C0)) / 3).astype(np.float32)
+  scale = rng.uniform(0.5, 1.5, C0).astype(np.float32)
+  shift = rng.standard_normal(C0).astype(np.float32)
+  ref = OM.conv2d_same(torch.from_numpy(canvas).unsqueeze(3), torch.from_numpy(w), torch.zeros(C0))
+  ref = torch.relu((ref + torch.from_numpy(pre)) * torch.from_numpy(scale) + torch.from_numpy(shift))
+  if pool == 2:
+    ref = OM.max_pool_same(ref, 2)
+  out = ops.canvas_conv(_g(pre), _g(canvas), _g(w), _g(scale), _g(shift), pool=pool)
+  assert rel_err(out.cpu().numpy(), ref.numpy()) < TOL
