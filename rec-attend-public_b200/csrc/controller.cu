@@ -7,7 +7,12 @@
 // memory and re-read 5 times; thread j owns hidden unit j: its four gate pre-activations are
 // dot products over the 64+256 inputs with weight reads coalesced across j (weights live in
 // L2: 1.7 MB shared by every CTA).  The read-out and the softmax are warp/CTA reductions.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -20,6 +25,43 @@ struct CtrlParams {
   int P, Cf, Hd, n_iter;
   int inp_h, inp_w, filt_h, filt_w, flags;
 };
+
+// Controller head -> box record (RA_BOX_* layout): full_model.py:691-725, modellib.py:752-856.
+__device__ void write_box(const CtrlParams &p, const float *out_s, float *bo) {
+  // full_model.py:691-725 and modellib.py:752-856
+  float cn[2] = {out_s[0], out_s[1]};
+  float ls[2] = {out_s[2], out_s[3]};
+  if (p.flags & RA_CTRL_SQUASH) {
+    for (int d = 0; d < 2; ++d) {
+      cn[d] = tanhf(cn[d]);
+      // -softplus(x) = -log(1 + exp(x)), computed the numerically safe way
+      const float x = ls[d];
+      ls[d] = -(fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))));
+    }
+  }
+  const float img[2] = {(float)p.inp_h, (float)p.inp_w};
+  const float filt[2] = {(float)p.filt_h, (float)p.filt_w};
+  for (int d = 0; d < 2; ++d) {
+    const float ctr = (cn[d] + 1.0f) * (img[d] / 2.0f);
+    const float size = expf(ls[d]) * img[d];
+    float lgv;
+    if (p.flags & RA_CTRL_FIXED_VAR)
+      lgv = 0.f;
+    else
+      lgv = logf(size) - logf(filt[d]);
+    if (p.flags & RA_CTRL_DYNAMIC_VAR) lgv = out_s[4 + d];
+    bo[RA_BOX_CTR_Y + d] = ctr;
+    bo[RA_BOX_SIZE_Y + d] = size;
+    bo[RA_BOX_LGVAR_Y + d] = lgv;
+    bo[RA_BOX_TL_Y + d] = ctr - size / 2.0f;  // modellib.py:850-852
+    bo[RA_BOX_BR_Y + d] = ctr + size / 2.0f;
+  }
+  const bool fg = (p.flags & RA_CTRL_FIXED_GAMMA) != 0;
+  bo[RA_BOX_GAMMA_ATTN] = fg ? 1.0f : expf(out_s[6]);
+  bo[RA_BOX_GAMMA_BOX] = expf(out_s[7]);
+  bo[RA_BOX_GAMMA_Y] = fg ? expf(2.0f) : expf(out_s[8]);
+  bo[13] = bo[14] = bo[15] = 0.f;
+}
 
 __global__ void __launch_bounds__(256) controller_kernel(CtrlParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -172,43 +214,199 @@ __global__ void __launch_bounds__(256) controller_kernel(CtrlParams p) {
   }
 
   if (tid < 9) p.ctrl_out[(size_t)b * 9 + tid] = out_s[tid];
-  if (tid == 0) {
-    // full_model.py:691-725 and modellib.py:752-856
-    float cn[2] = {out_s[0], out_s[1]};
-    float ls[2] = {out_s[2], out_s[3]};
-    if (p.flags & RA_CTRL_SQUASH) {
-      for (int d = 0; d < 2; ++d) {
-        cn[d] = tanhf(cn[d]);
-        // -softplus(x) = -log(1 + exp(x)), computed the numerically safe way
-        const float x = ls[d];
-        ls[d] = -(fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))));
+  if (tid == 0) write_box(p, out_s, p.box_out + (size_t)b * RA_BOX_STRIDE);
+}
+
+// ------------------------------------------------------------------------------------------
+// Cluster version: 8 CTAs (one thread-block cluster) serve 8 examples.  CTA r keeps the LSTM
+// gate weights of hidden units [32r, 32r+32) (160 KB) and its 32 columns of the first glimpse-MLP
+// layer (32 KB) in shared memory for the whole step, so the 1.7 MB of controller weights are
+// read from L2 once per cluster instead of once per example and glimpse iteration; hidden
+// state, MLP activations and logits are exchanged through distributed shared memory.
+// CTA r also owns example r for the per-example work (read-out, softmax, head).
+// ------------------------------------------------------------------------------------------
+constexpr int kCl = 8;
+constexpr int kHd2 = 256;
+constexpr int kCf2 = 64;
+constexpr int kUnits = kHd2 / kCl;     // 32 hidden units per CTA
+constexpr int kKin = kCf2 + kHd2;      // 320 LSTM inputs
+
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cluster_kernel(CtrlParams p, int B) {
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int r = (int)cluster.block_rank();
+  const int e_glob = (blockIdx.x / kCl) * kCl + r;  // the example this CTA owns
+  const bool own = e_glob < B;
+  const int P = p.P;
+  const int PS = (P + kCl - 1) / kCl;  // glimpse-map positions per CTA
+  const int tid = threadIdx.x;
+
+  float *wg_s = smem;                          // [320][128]  (k, q*32+u)
+  float *w0_s = wg_s + kKin * 4 * kUnits;      // [256][32]
+  float *x_s = w0_s + kHd2 * kUnits;           // [64][8]
+  float *h_s = x_s + kCf2 * kCl;               // [2][256][8]
+  float *t_s = h_s + 2 * kHd2 * kCl;           // [256][8]  (also the gate partial-sum buffer)
+  float *lg_s = t_s + kHd2 * kCl;              // [PS*8] logits / glimpse map of my example
+  float *bg_s = lg_s + PS * kCl;               // [128]
+  float *b0_s = bg_s + 4 * kUnits;             // [32]
+  float *part_s = b0_s + kUnits;               // [256]
+  float *red_s = part_s + 256;                 // [32]
+  float *out_s = red_s + 32;                   // [16]
+
+  // ---- one-time loads: my slice of the weights
+  for (int i = tid; i < kKin * 4 * kUnits; i += 256) {
+    const int col = i % (4 * kUnits), k = i / (4 * kUnits);
+    const int q = col / kUnits, u = col % kUnits;
+    const int j = r * kUnits + u;
+    wg_s[i] = (k < kCf2) ? __ldg(p.wx + ((size_t)q * kCf2 + k) * kHd2 + j)
+                         : __ldg(p.wh + ((size_t)q * kHd2 + (k - kCf2)) * kHd2 + j);
+  }
+  for (int i = tid; i < kHd2 * kUnits; i += 256) {
+    const int u = i % kUnits, k = i / kUnits;
+    w0_s[i] = __ldg(p.gw0 + (size_t)k * kHd2 + r * kUnits + u);
+  }
+  if (tid < 4 * kUnits) bg_s[tid] = __ldg(p.bg + (tid / kUnits) * kHd2 + r * kUnits + (tid % kUnits));
+  if (tid < kUnits) b0_s[tid] = __ldg(p.gb0 + r * kUnits + tid);
+  for (int i = tid; i < 2 * kHd2 * kCl; i += 256) h_s[i] = 0.f;  // full_model.py:674
+  for (int i = tid; i < PS * kCl; i += 256) lg_s[i] = 1.0f / (float)P;  // full_model.py:676-677
+  float c_state = 0.f;  // cell state of (unit tid%32, example tid/32)
+  cluster.sync();
+
+  const float *feat = p.feat + (size_t)(own ? e_glob : 0) * P * kCf2;
+  for (int it = 0; it < p.n_iter; ++it) {
+    const float *h_cur = h_s + (it & 1) * kHd2 * kCl;
+    float *h_nxt_local = h_s + ((it + 1) & 1) * kHd2 * kCl;
+
+    // ---- step 1 (owner): glimpse map out, read-out x = sum_p feat[p][:] * map[p]; broadcast x
+    if (own)
+      for (int i = tid; i < P; i += 256) p.gmap_out[((size_t)e_glob * p.n_iter + it) * P + i] = lg_s[i];
+    {
+      const int c = tid % kCf2, sl = tid / kCf2;  // 4 slices over p
+      float a = 0.f;
+      if (own)
+        for (int q = sl; q < P; q += 4) a = fmaf(__ldg(feat + (size_t)q * kCf2 + c), lg_s[q], a);
+      part_s[tid] = a;
+      __syncthreads();
+      if (tid < kCf2) {
+        const float x = (part_s[tid] + part_s[tid + 64]) + (part_s[tid + 128] + part_s[tid + 192]);
+#pragma unroll
+        for (int d = 0; d < kCl; ++d) cluster.map_shared_rank(x_s, d)[tid * kCl + r] = x;
       }
     }
-    const float img[2] = {(float)p.inp_h, (float)p.inp_w};
-    const float filt[2] = {(float)p.filt_h, (float)p.filt_w};
-    float *bo = p.box_out + (size_t)b * RA_BOX_STRIDE;
-    for (int d = 0; d < 2; ++d) {
-      const float ctr = (cn[d] + 1.0f) * (img[d] / 2.0f);
-      const float size = expf(ls[d]) * img[d];
-      float lgv;
-      if (p.flags & RA_CTRL_FIXED_VAR)
-        lgv = 0.f;
-      else
-        lgv = logf(size) - logf(filt[d]);
-      if (p.flags & RA_CTRL_DYNAMIC_VAR) lgv = out_s[4 + d];
-      bo[RA_BOX_CTR_Y + d] = ctr;
-      bo[RA_BOX_SIZE_Y + d] = size;
-      bo[RA_BOX_LGVAR_Y + d] = lgv;
-      bo[RA_BOX_TL_Y + d] = ctr - size / 2.0f;  // modellib.py:850-852
-      bo[RA_BOX_BR_Y + d] = ctr + size / 2.0f;
+    cluster.sync();
+
+    // ---- step 2: LSTM gates of my 32 units for the 8 examples (nnlib.py:641-647)
+    {
+      const int col = tid % (4 * kUnits), kh = tid / (4 * kUnits);  // 2 halves of the 320 inputs
+      float acc[kCl];
+#pragma unroll
+      for (int e = 0; e < kCl; ++e) acc[e] = 0.f;
+      const int k0 = kh * (kKin / 2);
+      for (int k = k0; k < k0 + kKin / 2; ++k) {
+        const float w = wg_s[k * (4 * kUnits) + col];
+        const float *v = (k < kCf2) ? (x_s + k * kCl) : (h_cur + (k - kCf2) * kCl);
+        const float4 v0 = *reinterpret_cast<const float4 *>(v);
+        const float4 v1 = *reinterpret_cast<const float4 *>(v + 4);
+        acc[0] = fmaf(w, v0.x, acc[0]);
+        acc[1] = fmaf(w, v0.y, acc[1]);
+        acc[2] = fmaf(w, v0.z, acc[2]);
+        acc[3] = fmaf(w, v0.w, acc[3]);
+        acc[4] = fmaf(w, v1.x, acc[4]);
+        acc[5] = fmaf(w, v1.y, acc[5]);
+        acc[6] = fmaf(w, v1.z, acc[6]);
+        acc[7] = fmaf(w, v1.w, acc[7]);
+      }
+      float *gp = t_s + (size_t)kh * (4 * kUnits) * kCl + col * kCl;  // [kh][col][e]
+#pragma unroll
+      for (int e = 0; e < kCl; ++e) gp[e] = acc[e];
+      __syncthreads();
+      const int u = tid % kUnits, e = tid / kUnits;
+      float g[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cq = q * kUnits + u;
+        g[q] = (t_s[cq * kCl + e] + t_s[(4 * kUnits + cq) * kCl + e]) + bg_s[cq];
+      }
+      const float gi = ra::sigmoidf_acc(g[0]);
+      const float gf = ra::sigmoidf_acc(g[1]);
+      const float go = ra::sigmoidf_acc(g[2]);
+      const float uu = tanhf(g[3]);
+      c_state = gf * c_state + gi * uu;
+      const float hn = go * tanhf(c_state);
+      const int off = (int)(h_nxt_local - smem) + (r * kUnits + u) * kCl + e;
+#pragma unroll
+      for (int d = 0; d < kCl; ++d) cluster.map_shared_rank(smem, d)[off] = hn;
     }
-    const bool fg = (p.flags & RA_CTRL_FIXED_GAMMA) != 0;
-    bo[RA_BOX_GAMMA_ATTN] = fg ? 1.0f : expf(out_s[6]);
-    bo[RA_BOX_GAMMA_BOX] = expf(out_s[7]);
-    bo[RA_BOX_GAMMA_Y] = fg ? expf(2.0f) : expf(out_s[8]);
-    bo[13] = bo[14] = bo[15] = 0.f;
+    cluster.sync();
+    if (it == p.n_iter - 1) break;  // the last glimpse map is dead compute (full_model.py:686-688)
+    const float *h_new = h_nxt_local;
+
+    // ---- step 3: glimpse MLP layer 0, my 32 columns x 8 examples: relu(h W0 + b0)
+    {
+      const int u = tid % kUnits, e = tid / kUnits;
+      float a0 = 0.f, a1 = 0.f;
+      for (int k = 0; k < kHd2; k += 2) {
+        a0 = fmaf(h_new[k * kCl + e], w0_s[k * kUnits + u], a0);
+        a1 = fmaf(h_new[(k + 1) * kCl + e], w0_s[(k + 1) * kUnits + u], a1);
+      }
+      const float tv = fmaxf((a0 + a1) + b0_s[u], 0.f);
+      const int off = (int)(t_s - smem) + (r * kUnits + u) * kCl + e;
+#pragma unroll
+      for (int d = 0; d < kCl; ++d) cluster.map_shared_rank(smem, d)[off] = tv;
+    }
+    cluster.sync();
+
+    // ---- step 4: glimpse MLP layer 1 logits for my PS positions x 8 examples -> owner CTAs
+    for (int o = tid; o < PS * kCl; o += 256) {
+      const int pos = o % PS, e = o / PS;
+      const int gp = r * PS + pos;
+      if (gp < P) {
+        float a0 = 0.f, a1 = 0.f;
+        const float *wq = p.gw1 + gp;
+        for (int k = 0; k < kHd2; k += 2) {
+          a0 = fmaf(t_s[k * kCl + e], __ldg(wq + (size_t)k * P), a0);
+          a1 = fmaf(t_s[(k + 1) * kCl + e], __ldg(wq + (size_t)(k + 1) * P), a1);
+        }
+        cluster.map_shared_rank(lg_s, e)[gp] = (a0 + a1) + __ldg(p.gb1 + gp);
+      }
+    }
+    cluster.sync();
+
+    // ---- step 5 (owner): softmax over the P positions (full_model.py:350-352)
+    {
+      float lmax = -INFINITY;
+      for (int q = tid; q < P; q += 256) lmax = fmaxf(lmax, lg_s[q]);
+      lmax = ra::block_max(lmax, red_s);
+      float lsum = 0.f;
+      for (int q = tid; q < P; q += 256) {
+        const float ev = expf(lg_s[q] - lmax);
+        lg_s[q] = ev;
+        lsum += ev;
+      }
+      lsum = ra::block_sum(lsum, red_s);
+      for (int q = tid; q < P; q += 256) lg_s[q] = lg_s[q] / lsum;
+      __syncthreads();
+    }
   }
+
+  // ---- head (owner): ctrl_out = h Wc + bc, box parameters
+  const float *h_fin = h_s + (p.n_iter & 1) * kHd2 * kCl;
+  if (own) {
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int o = wid; o < 9; o += 8) {
+      float a = 0.f;
+      for (int k = lane; k < kHd2; k += 32) a = fmaf(h_fin[k * kCl + r], __ldg(p.cw + (size_t)k * 9 + o), a);
+      a = ra::warp_sum(a);
+      if (lane == 0) out_s[o] = a + __ldg(p.cb + o);
+    }
+    p.h_out[(size_t)e_glob * kHd2 + tid] = h_fin[tid * kCl + r];
+  }
+  __syncthreads();
+  if (own && tid < 9) p.ctrl_out[(size_t)e_glob * 9 + tid] = out_s[tid];
+  if (own && tid == 0) write_box(p, out_s, p.box_out + (size_t)e_glob * RA_BOX_STRIDE);
+  cluster.sync();  // no CTA may exit while its shared memory can still be written remotely
 }
+
 
 }  // namespace
 
@@ -247,6 +445,26 @@ extern "C" int ra_controller_step_f32(const float *feat, int B, int P, int Cf, i
   p.filt_h = filter_height;
   p.filt_w = filter_width;
   p.flags = flags;
+  if (Cf == kCf2 && Hd == kHd2 && getenv("RA_CTRL_NO_CLUSTER") == nullptr) {
+    const int PS = (P + kCl - 1) / kCl;
+    const size_t smem2 = ((size_t)kKin * 4 * kUnits + kHd2 * kUnits + kCf2 * kCl + 3 * kHd2 * kCl + PS * kCl +
+                          4 * kUnits + kUnits + 256 + 32 + 16) * sizeof(float);
+    if (smem2 <= 227 * 1024) {
+      static bool attr2 = false;
+      if (!attr2) {
+        cudaError_t e = cudaFuncSetAttribute(controller_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             227 * 1024);
+        if (e != cudaSuccess) {
+          ra::set_last_error("cudaFuncSetAttribute(controller_cluster_kernel)", e);
+          return RA_ERR_CUDA;
+        }
+        attr2 = true;
+      }
+      const int clusters = (B + kCl - 1) / kCl;
+      controller_cluster_kernel<<<clusters * kCl, 256, smem2, ra::as_stream(stream)>>>(p, B);
+      return ra::finish_launch("controller_cluster_kernel");
+    }
+  }
   const size_t smem = ((size_t)P * Cf + P + Cf + 2 * Hd + 4 * Cf + 32 + 16) * sizeof(float);
   if (smem > 200 * 1024) return RA_ERR_UNSUPPORTED;
   static bool attr_set = false;

@@ -15,9 +15,15 @@ MODEL_TOL = 1e-3
 
 FP_KEYS = ['y_out', 's_out', 'attn_box', 'x_patch', 'y_out_patch', 'attn_ctr', 'attn_size', 'attn_top_left',
            'attn_bot_right', 'ctrl_out', 'ctrl_rnn_glimpse_map', 'attn_top_left_gt', 'attn_bot_right_gt',
-           'iou_soft_pairwise', 'iou_soft_box_pairwise', 'iou_hard_pairwise', 'canvas']
-SCALAR_KEYS = ['loss', 'box_loss', 'segm_loss', 'conf_loss', 'iou_soft', 'iou_hard', 'wt_cov_soft', 'unwt_cov_soft',
-               'wt_cov_hard', 'unwt_cov_hard', 'dice', 'count_acc', 'dic', 'dic_abs']
+           'iou_soft_pairwise', 'iou_soft_box_pairwise', 'canvas']
+# statistics of the THRESHOLDED masks (full_model.py:1063-1081) are discontinuous in y_out: one pixel
+# within fp32 noise of 0.5 moves them by 1/|mask|.  They are checked through the number of flipped
+# pixels (must be a vanishing fraction) and a correspondingly looser tolerance.
+HARD_KEYS = ['iou_hard_pairwise']
+HARD_SCALARS = ['iou_hard', 'wt_cov_hard', 'unwt_cov_hard', 'dice']
+HARD_TOL = 5e-3
+SCALAR_KEYS = ['loss', 'box_loss', 'segm_loss', 'conf_loss', 'iou_soft', 'wt_cov_soft', 'unwt_cov_soft', 'count_acc',
+               'dic', 'dic_abs']
 
 CASES = [
     # name, arch, H, W, T, B   (first row = BASELINE.json configs[0])
@@ -56,6 +62,13 @@ def test_full_model_parity(cuda, case):
   for k in SCALAR_KEYS:
     a, b = float(out[k]), float(ref[k])
     assert abs(a - b) <= MODEL_TOL * max(1.0, abs(b)), (k, a, b)
+  flips = int(((out['y_out'].cpu().numpy() > 0.5) != (ref['y_out'].numpy() > 0.5)).sum())
+  assert flips <= 2 + 1e-5 * ref['y_out'].numel(), 'thresholded masks differ in {} pixels'.format(flips)
+  for k in HARD_KEYS:
+    assert rel_err(out[k].cpu().numpy(), ref[k].numpy()) <= HARD_TOL, k
+  for k in HARD_SCALARS:
+    a, b = float(out[k]), float(ref[k])
+    assert abs(a - b) <= HARD_TOL * max(1.0, abs(b)), (k, a, b)
   assert (out['attn_box_gt'].cpu().numpy() == ref['attn_box_gt'].numpy()).all()
   # matchings: bit-exact (the synthetic inputs are margin-checked: re-matching the oracle's
   # IoU perturbed by the observed fp32 difference must not change the oracle's answer)
