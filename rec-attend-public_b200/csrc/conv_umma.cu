@@ -75,7 +75,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// hi part of the 3xTF32 split: v rounded to NEAREST tf32 (not truncated), so |lo| <= 2^-12 |v| and the
+// tensor core's own truncation of lo costs 2^-23 instead of 2^-22.
+__device__ __forceinline__ float tf32_hi(float v) {
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+}
 
 constexpr int kThreads = 256;
 constexpr int kStageUnroll = 4;

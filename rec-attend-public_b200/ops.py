@@ -110,14 +110,14 @@ def umma_plan(Cin, Cout, Hout, Wout, pool):
 
 def pack_umma_weights(w_hwio, KC, NP):
   """HWIO conv filter [3,3,Cin,Cout] (numpy) -> the kernel's shared-memory image
-  [n_chunks][9][2 (hi,lo)][KC/4][NP][4]: hi = w with the low 13 mantissa bits cleared, lo = w - hi."""
+  [n_chunks][9][2 (hi,lo)][KC/4][NP][4]: hi = w rounded to the nearest tf32, lo = w - hi (exact)."""
   import numpy as np
   w = np.asarray(w_hwio, np.float32)
   _, _, Cin, Cout = w.shape
   n_chunks = (Cin + KC - 1) // KC
   wp = np.zeros((9, n_chunks * KC, NP), np.float32)
   wp[:, :Cin, :Cout] = w.reshape(9, Cin, Cout)
-  hi = (wp.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+  hi = ((wp.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)  # round to nearest tf32
   lo = wp - hi
   def lay(a):  # [9, chunks*KC, NP] -> [chunks, 9, KC/4, NP, 4]
     return a.reshape(9, n_chunks, KC // 4, 4, NP).transpose(1, 0, 2, 4, 3)

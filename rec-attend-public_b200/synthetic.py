@@ -112,7 +112,7 @@ def make_weights(opt, seed=4321, model='full'):
   w['ctrl_mlp_w_%d' % last][:, 0:2] *= 1.5  # spread the box centres
   w['ctrl_mlp_w_%d' % last][:, 2:4] *= 2.0
   #            ctr_y ctr_x lg_sy lg_sx lg_vy lg_vx  lg_g_attn lg_g_box lg_g_y
-  w['ctrl_mlp_b_%d' % last][:] = [0.0, 0.0, -1.3, -1.3, 1.0, 1.0, 0.0, 5.0, 3.5]
+  w['ctrl_mlp_b_%d' % last][:] = [0.0, 0.0, -1.3, -1.3, 1.0, 1.0, 0.0, 3.0, 3.5]
 
   if model == 'box':
     w['score_mlp_w_0'] = _normal(rng, (hid, 1), hid)
