@@ -1,0 +1,89 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and exports every
+symbol that include/rec_attend_b200.h declares; host-side logic (configs, weight packing, plans)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+  hdr = open(os.path.join(ROOT, 'include', 'rec_attend_b200.h')).read()
+  hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+  return sorted(set(re.findall(r'\b(ra_[a-z0-9_]+)\s*\(', hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+  from rec_attend_b200 import _lib
+  lib = _lib.lib()
+  names = _declared()
+  assert len(names) >= 18
+  for n in names:
+    assert hasattr(lib, n), 'librecattend_b200.so does not export ' + n
+  assert sorted(_lib.EXPORTED) == names, 'ctypes table and header disagree'
+  assert lib.ra_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('GPU present')
+  import rec_attend_b200 as ra
+  from rec_attend_b200 import _lib
+  from rec_attend_b200.full_model import FullModel
+  assert _lib.lib().ra_device_count() == 0
+  with pytest.raises(_lib.RecAttendError):
+    FullModel(ra.config.baseline_opt(0))
+
+
+def test_baseline_configs_and_input_depths():
+  import rec_attend_b200 as ra
+  names = [c['name'] for c in ra.config.BASELINE_CONFIGS]
+  assert names[2] == 'kitti_256x512_T20_B32'
+  assert ra.config.input_depths(ra.config.baseline_opt(1))[0] == 4
+  assert ra.config.input_depths(ra.config.baseline_opt(2))[0] == 13
+  assert ra.config.input_depths(ra.config.baseline_opt(3))[0] == 21
+  opt = ra.config.baseline_opt(2)
+  assert opt['disable_overwrite'] is False and opt['dynamic_var'] and not opt['fixed_gamma']  # run_kitti.sh:68-111
+  assert ra.synthetic.dcnn_skip_channels(opt) == [0, 64, 64, 32, 32, 16, 13]
+  assert ra.synthetic.dcnn_skip_channels(ra.config.baseline_opt(1)) == [0] * 7
+
+
+def test_synthetic_batch_contract():
+  import rec_attend_b200 as ra
+  opt = ra.config.full_model_opt('kitti', 32, 64, 6)
+  b = ra.synthetic.make_batch(opt, 3)
+  assert b['x'].shape == (3, 32, 64, 3) and b['d_in'].shape == (3, 32, 64, 8) and b['y_in'].shape == (3, 32, 64, 1)
+  area = b['y_gt'].sum((2, 3))
+  assert (np.diff(area, axis=1) <= 0).all(), 'masks sorted by area, descending (ins_seg_dataset.py:169-172)'
+  assert ((area > 0) == (b['s_gt'] > 0)).all()
+  assert b['y_gt'].sum(1).max() <= 1.0, 'instances are disjoint'
+
+
+def test_umma_plan_and_weight_packing():
+  from rec_attend_b200 import ops
+  KC, NP, nch = ops.umma_plan(64, 96, 12, 12, 2)
+  assert KC in (8, 16) and NP == 96 and nch == 64 // KC
+  rng = np.random.default_rng(0)
+  w = rng.standard_normal((3, 3, 13, 10)).astype(np.float32)
+  KC, NP, nch = ops.umma_plan(13, 10, 48, 48, 1)
+  wp = ops.pack_umma_weights(w, KC, NP)
+  assert wp.shape == (nch, 9, 2, KC // 4, NP, 4)
+  # hi + lo reproduces w exactly; hi has at most 11 significant mantissa bits
+  rec = (wp[:, :, 0] + wp[:, :, 1]).transpose(1, 0, 2, 4, 3).reshape(9, nch * KC, NP)
+  assert (rec[:, :13, :10] == w.reshape(9, 13, 10)).all() and (rec[:, 13:] == 0).all() and (rec[:, :, 10:] == 0).all()
+  assert (wp[:, :, 0].view(np.uint32) & np.uint32(0x1FFF) == 0).all()
+
+
+def test_fold_bn_and_deconv_filter_transform():
+  from rec_attend_b200.full_model import _deconv_to_conv, _fold_bn
+  w = {'n_0_0_gamma': np.array([2.0], np.float32), 'n_0_0_beta': np.array([0.5], np.float32),
+       'n_0_0_ema_mean': np.array([1.0], np.float32), 'n_0_0_ema_var': np.array([3.0], np.float32)}
+  sc, sh = _fold_bn(w, 'n', 0, 1, np.array([0.25], np.float32))
+  inv = 2.0 / np.sqrt(3.0 + 1e-3)
+  assert abs(sc[0, 0] - inv) < 1e-6 and abs(sh[0, 0] - (0.5 - 1.0 * inv + 0.25 * inv)) < 1e-6
+  wt = np.arange(3 * 3 * 2 * 5, dtype=np.float32).reshape(3, 3, 2, 5)
+  wc = _deconv_to_conv(wt)
+  assert wc.shape == (3, 3, 5, 2) and wc[0, 2, 4, 1] == wt[2, 0, 1, 4]

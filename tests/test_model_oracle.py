@@ -1,0 +1,170 @@
+"""CPU semantic tests of the model oracle (oracle/model.py).  The model graph is PARITY UNPINNED
+(no TensorFlow 0.12 here, no golden outputs in the reference), so every TF-specific semantic the
+restatement relies on is checked against an independent numpy formulation."""
+import numpy as np
+import torch
+
+from oracle import model as OM
+
+
+def _conv_same_numpy(x, w):
+  B, H, W, Ci = x.shape
+  Co = w.shape[3]
+  xp = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0)))
+  y = np.zeros((B, H, W, Co), np.float64)
+  for ky in range(3):
+    for kx in range(3):
+      y += np.einsum('bhwc,cd->bhwd', xp[:, ky:ky + H, kx:kx + W, :], w[ky, kx])
+  return y
+
+
+def test_conv_same_padding_is_symmetric_one():
+  rng = np.random.default_rng(0)
+  x = rng.standard_normal((2, 6, 8, 3)).astype(np.float32)
+  w = rng.standard_normal((3, 3, 3, 5)).astype(np.float32)
+  y = OM.conv2d_same(torch.from_numpy(x), torch.from_numpy(w), torch.zeros(5)).numpy()
+  assert np.abs(y - _conv_same_numpy(x, w)).max() < 1e-4
+
+
+def _conv_transpose_numpy(x, w, stride):
+  """Gradient of a SAME stride-s 3x3 conv w.r.t. its input == tf.nn.conv2d_transpose (nnlib.py:372-376).
+  Forward SAME padding for k=3: s=1 -> 1 before; s=2 (even input) -> 0 before, 1 after."""
+  B, M, N, Ci = x.shape
+  Co = w.shape[2]
+  H, W = M * stride, N * stride
+  pad_before = 1 if stride == 1 else 0
+  y = np.zeros((B, H, W, Co), np.float64)
+  for iy in range(M):
+    for ix in range(N):
+      for ky in range(3):
+        for kx in range(3):
+          oy, ox = iy * stride + ky - pad_before, ix * stride + kx - pad_before
+          if 0 <= oy < H and 0 <= ox < W:
+            y[:, oy, ox, :] += x[:, iy, ix, :] @ w[ky, kx].T  # w [kh,kw,Cout,Cin]
+  return y
+
+
+def test_conv2d_transpose_crops_at_the_end():
+  rng = np.random.default_rng(1)
+  for stride in (1, 2):
+    x = rng.standard_normal((2, 4, 5, 3)).astype(np.float32)
+    w = rng.standard_normal((3, 3, 4, 3)).astype(np.float32)
+    y = OM.conv2d_transpose_same(torch.from_numpy(x), torch.from_numpy(w), torch.zeros(4), stride).numpy()
+    assert y.shape == (2, 4 * stride, 5 * stride, 4)
+    assert np.abs(y - _conv_transpose_numpy(x, w, stride)).max() < 1e-4
+
+
+def test_deconv_as_conv_over_zero_inserted_input():
+  """The identity the CUDA path relies on: conv2d_transpose(stride s) == SAME-style conv with the
+  flipped/swapped filter over the zero-inserted input, window starting s before the output pixel."""
+  rng = np.random.default_rng(2)
+  for s in (1, 2):
+    x = rng.standard_normal((1, 3, 4, 2)).astype(np.float32)
+    wt = rng.standard_normal((3, 3, 5, 2)).astype(np.float32)
+    ref = _conv_transpose_numpy(x, wt, s)
+    wc = wt[::-1, ::-1].transpose(0, 1, 3, 2)  # [k,k,Cin,Cout]
+    H, W = 3 * s, 4 * s
+    v = np.zeros((1, H, W, 2))
+    v[:, ::s, ::s] = x
+    vp = np.pad(v, ((0, 0), (s, 2), (s, 2), (0, 0)))
+    y = np.zeros((1, H, W, 5))
+    for ky in range(3):
+      for kx in range(3):
+        y += np.einsum('bhwc,cd->bhwd', vp[:, ky:ky + H, kx:kx + W], wc[ky, kx])
+    assert np.abs(y - ref).max() < 1e-5
+
+
+def test_batch_norm_eval_uses_ema_and_eps_1e3():
+  x = torch.tensor([[[[2.0, -1.0]]]])
+  p = {'gamma': torch.tensor([2.0, 0.5]), 'beta': torch.tensor([0.1, -0.2]), 'ema_mean': torch.tensor([1.0, 0.0]),
+       'ema_var': torch.tensor([4.0, 1.0])}
+  y = OM.batch_norm_eval(x, p).numpy().ravel()
+  ref = (np.array([2.0, -1.0]) - [1.0, 0.0]) / np.sqrt(np.array([4.0, 1.0]) + 1e-3) * [2.0, 0.5] + [0.1, -0.2]
+  assert np.abs(y - ref).max() < 1e-6
+
+
+def test_gaussian_filter_formula():  # SURVEY §10, modellib.py:581-612
+  f = OM.get_gaussian_filter(torch.tensor([10.0]), torch.tensor([23.0]), torch.tensor([0.5]), 32, 48).numpy()[0]
+  mu = 10.0 + 24.0 / 48 * (np.arange(48) - 23.5)
+  var = np.exp(0.5)
+  ref = np.exp(-0.5 * (np.arange(32)[:, None] - mu[None])**2 / var) / np.sqrt(var) / np.sqrt(2 * np.pi)
+  assert f.shape == (32, 48) and np.abs(f - ref).max() < 1e-6
+
+
+def test_extract_patch_is_FyT_X_Fx():
+  rng = np.random.default_rng(3)
+  x = rng.random((2, 7, 9, 3)).astype(np.float32)
+  fy = rng.random((2, 7, 4)).astype(np.float32)
+  fx = rng.random((2, 9, 5)).astype(np.float32)
+  p = OM.extract_patch(torch.from_numpy(x), torch.from_numpy(fy), torch.from_numpy(fx), 3).numpy()
+  ref = np.einsum('byi,byxd,bxj->bijd', fy, x, fx)
+  assert np.abs(p - ref).max() < 1e-4
+
+
+def test_union_eps_is_per_pixel():
+  a = torch.zeros(1, 1, 4, 5)
+  b = torch.zeros(1, 1, 4, 5)
+  assert abs(float(OM.f_union(a, b)) - 20 * 1e-5) < 1e-9
+  iou = OM.f_iou_pairwise(torch.ones(1, 2, 4, 5), torch.ones(1, 3, 4, 5))
+  assert iou.shape == (1, 2, 3) and abs(float(iou[0, 0, 0]) - 20 / (20 + 20e-5)) < 1e-6
+
+
+def test_gt_box_padding_and_empty_mask():  # modellib.py:663-701
+  y = torch.zeros(1, 2, 40, 50)
+  y[0, 0, 10:21, 5:31] = 1  # rows 10..20, cols 5..30
+  tl, br, box = OM.get_gt_box(y, padding_ratio=0.2, min_padding=4.0)
+  # size = (10, 25); pad = max(0.2*size, 4) = (4, 5)
+  assert tl[0, 0].tolist() == [6.0, 0.0] and br[0, 0].tolist() == [24.0, 35.0]
+  assert float(box[0, 0].sum()) == (24 - 6 + 1) * (35 - 0 + 1)
+  assert tl[0, 1].tolist() == [0.0, 0.0] and br[0, 1].tolist() == [8.0, 8.0]  # empty mask -> (0,0)-(2*min_pad)
+  assert float(box[0, 1].sum()) == 0.0  # the filled box is drawn BEFORE the fix-up
+
+
+def test_segm_match_rounding_and_masking():  # modellib.py:395-415, SURVEY §9.14
+  iou = torch.tensor([[[0.4999995, 0.2], [0.1, 0.3]]])
+  s_gt = torch.tensor([[1.0, 0.0]])
+  w = OM.segm_match_weights(iou, s_gt).numpy()
+  assert abs(w[0, 0, 0] - (0.5 + 1e-5)) < 1e-7  # floor(x*1e6 + 0.5): half-up
+  assert np.allclose(w[0, :, 1], 1e-5) and np.allclose(w[0, 1, :], 1e-5)
+  m = OM.f_segm_match(iou, s_gt).numpy()
+  assert m.sum() == 1 and m[0, 0, 0] == 1
+
+
+def test_conf_loss_cummin_cummax():  # modellib.py:316-339
+  s = torch.tensor([[0.9, 0.2, 0.6]])
+  match = torch.zeros(1, 3, 3)
+  match[0, 0, 1] = 1
+  ref = -(np.log(0.9 + 1e-5)) - np.log(1 - 0.6 + 1e-5) - np.log(1 - 0.6 + 1e-5)
+  assert abs(float(OM.f_conf_loss(s, match)) - ref / 3) < 1e-6
+
+
+def test_full_forward_shapes_and_skip_wiring():
+  import rec_attend_b200 as ra
+  for arch, nsc in (('kitti', 1), ('cityscapes', 9), ('cvppp', 1)):
+    opt = ra.config.full_model_opt(arch, 32, 64, 3)
+    batch = ra.synthetic.make_batch(opt, 2)
+    w = ra.synthetic.make_weights(opt)
+    D = 4 if arch == 'cvppp' else 12 + nsc
+    assert w['attn_cnn_w_0'].shape[2] == D
+    if arch != 'cvppp':  # every deconv layer >= 1 has a skip
+      assert w['attn_dcnn_w_6'].shape == (3, 3, 1, 16 + D)
+      assert w['attn_dcnn_w_1'].shape == (3, 3, 64, 64 + 64)
+    else:
+      assert w['attn_dcnn_w_6'].shape == (3, 3, 1, 8)
+    m = OM.full_model_forward(opt, w, batch)
+    assert m['y_out'].shape == (2, 3, 32, 64) and m['x_patch'].shape == (2, 3, 48, 48, D)
+    assert m['ctrl_rnn_glimpse_map'].shape == (2, 3, 5, 1, 2)
+    assert torch.isfinite(m['loss'])
+    # masks can only rise from sigmoid(-5) and the canvas is their running max
+    assert float(m['y_out'].min()) >= 0.0066
+    assert torch.allclose(m['canvas'][..., 0], m['y_out'].max(dim=1)[0])
+
+
+def test_box_model_forward_shapes():
+  import rec_attend_b200 as ra
+  opt = ra.config.box_model_opt(32, 64, 3)
+  batch = ra.synthetic.make_batch(opt, 2)
+  w = ra.synthetic.make_weights(opt, model='box')
+  m = OM.box_model_forward(opt, w, batch)
+  assert m['attn_box'].shape == (2, 3, 32, 64) and m['s_out'].shape == (2, 3)
+  assert m['match_box'].shape == (2, 3, 3) and torch.isfinite(m['loss'])
