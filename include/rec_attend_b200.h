@@ -97,15 +97,21 @@ int ra_canvas_conv_f32(const float *pre, const float *canvas, const float *w, co
 
 /* --------------------------------------------------------------------------------------
  * The same convolution block on the tcgen05 tensor cores (kind::tf32, accumulators in TMEM)
- * with the 3xTF32 split (hi*hi + hi*lo + lo*hi, ~2^-21 relative) that the 1e-3 parity bar
- * needs.  Arguments as ra_conv3x3_f32 except: no add_to, and the filter is pre-packed by the
- * caller into the kernel's shared-memory image
- *   wpack [n_chunks][9 taps][2 (hi, lo)][KC/4][NP][4]
- * (element [ch][tap][h][c4][n][j] = hi/lo part of w[tap][ch*KC + 4*c4 + j][n], zero padded),
- * with KC, NP, n_chunks given by ra_conv3x3_umma_plan for the layer's (Cin, Cout, output size,
- * pool).  Supported: Cout <= 256, output width >= 8 and even.
+ * with the 3xTF32 split (hi*hi + hi*lo + lo*hi, ~2^-22 relative) that the 1e-3 parity bar
+ * needs; persistent warp-specialised pipeline (csrc/conv_umma.cu).  Arguments as
+ * ra_conv3x3_f32 except: no add_to, and the filter is pre-packed by the caller into the
+ * kernel's shared-memory image
+ *   wpack [n_split][n_chunks][9 taps][KC/4][2*NPc][4]
+ * element [s][ch][tap][c4][r][j] = part(w[tap][ch*KC + 4*c4 + j][s*NPc + (r mod NPc)]), part = hi
+ * (w rounded to the nearest tf32) for r < NPc and lo = w - hi for r >= NPc, zero padded,
+ * with KC, NPc, n_split, n_chunks given by ra_conv3x3_umma_plan for the layer's (Cin, Cout,
+ * un-pooled output size, pool, batch).  Supported: Cout <= 256, even output width.
  * -------------------------------------------------------------------------------------- */
-int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int *KC, int *NP, int *n_chunks);
+int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc, int *n_split,
+                         int *n_chunks);
+/* Diagnostics: info[16] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
+ * acc_cols, stage_bytes, w_res_bytes, slots_alloc of the tile plan. */
+int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info);
 int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int C2, const float *wpack, const float *scale,
                         const float *shift, int B, int Hin, int Win, int Cout, int upsample, int pool, int relu,
                         float *y, void *stream);

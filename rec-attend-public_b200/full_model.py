@@ -132,16 +132,20 @@ class _ModelBase(object):
     return w
 
   def _pack(self, w_hwio, Hout, Wout, pool):
-    """Pre-pack a conv-form HWIO filter into the tcgen05 kernel's shared-memory image for a layer
-    whose (un-pooled) output is Hout x Wout."""
-    w_hwio = np.asarray(w_hwio, np.float32)
-    KC, NP, _ = ops.umma_plan(w_hwio.shape[2], w_hwio.shape[3], Hout, Wout, pool)
-    return (self._dev(ops.pack_umma_weights(w_hwio, KC, NP)), int(w_hwio.shape[3]))
+    """Register a conv-form HWIO filter for the tcgen05 kernel; the shared-memory image depends on the
+    tile plan (hence on the batch size) and is packed on first use per batch size."""
+    return {'w': np.ascontiguousarray(w_hwio, dtype=np.float32), 'Hout': Hout, 'Wout': Wout, 'pool': pool,
+            'packed': {}}
 
   def _conv(self, x, wp, scale, shift, pool, relu=True, x2=None, upsample=1, out=None):
     """One conv block on the tensor cores (csrc/conv_umma.cu)."""
-    return ops.conv3x3_block_umma(x, wp[0], wp[1], scale, shift, pool=pool, relu=relu, x2=x2, upsample=upsample,
-                                  out=out)
+    B = x.shape[0]
+    if B not in wp['packed']:
+      w = wp['w']
+      KC, NPc, nsp, _ = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], wp['pool'], B)
+      wp['packed'][B] = self._dev(ops.pack_umma_weights(w, KC, NPc, nsp))
+    return ops.conv3x3_block_umma(x, wp['packed'][B], wp['w'].shape[3], scale, shift, pool=pool, relu=relu, x2=x2,
+                                  upsample=upsample, out=out)
 
   def _weight_decay_term(self, weights):
     """nnlib.py:59-61: sum over conv/mlp/lstm weight matrices of wd * ||w||^2 / 2 (a constant
@@ -161,9 +165,12 @@ class _ModelBase(object):
   # ------------------------------------------------------------------ shared pieces
   def _inputs(self, batch):
     def dev(v):
+      # host arrays stay on the host here: forward() copies them straight into its static device buffers
       if isinstance(v, np.ndarray):
         v = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
-      return v.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+      if v.dtype != torch.float32:
+        v = v.float()
+      return v.contiguous()
 
     x = dev(batch['x'])
     B = x.shape[0]
@@ -372,9 +379,30 @@ class FullModel(_ModelBase):
     if box_gt is not None:
       out['attn_box_gt'] = box_gt
 
-  def forward(self, batch, outputs=None, phase_train=False, with_loss=True):
+  def _run(self, bufs, B, with_loss, want_all):
+    """Enqueue one full forward on the current stream; returns the dict of (static) output tensors."""
+    st = bufs['static_in']
+    self._prepare(bufs, st['x'], st.get('d_in'), st.get('y_in'))
+    self._decode(bufs, B)
+    out = {}
+    self._controller_outputs(bufs, out)
+    out['y_out'] = bufs['y_out']
+    if want_all:
+      out['x_patch'] = bufs['x_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
+      out['y_out_patch'] = bufs['y_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
+    if with_loss:
+      self._loss(bufs, st['y_gt'], st['s_gt'], out, want_gt_box=want_all)
+      scal = out['loss_scalars']
+      for i, k in enumerate(LOSS_KEYS):
+        out[k] = scal[i]
+    return out
+
+  def forward(self, batch, outputs=None, phase_train=False, with_loss=True, use_graph=True):
     """``sess.run([model[k] for k in outputs], feed_dict)`` of runner.py:98-105.
-    Returns a dict of CUDA tensors (all keys when ``outputs`` is None)."""
+    Returns a dict of CUDA tensors (all keys when ``outputs`` is None).  The inputs are copied into
+    static device buffers; with ``use_graph`` the ~750 kernel launches of the T-step decode + loss block are
+    captured once per (batch size, output set) in a CUDA graph and replayed (the returned tensors are the
+    graph's static outputs: they are overwritten by the next forward of the same batch size)."""
     if phase_train:
       raise _lib.RecAttendError('training-mode forward (batch-stat BN, knob) is a later row of the scope table')
     if self.w is None:
@@ -382,21 +410,36 @@ class FullModel(_ModelBase):
     x, d_in, y_in, y_gt, s_gt = self._inputs(batch)
     B = x.shape[0]
     bufs = self._buffers(B)
-    self._prepare(bufs, x, d_in, y_in)
-    self._decode(bufs, B)
-    out = {}
-    self._controller_outputs(bufs, out)
-    out['y_out'] = bufs['y_out']
+    with_loss = bool(with_loss and y_gt is not None)
+    if 'static_in' not in bufs:
+      bufs['static_in'] = {}
+    st = bufs['static_in']
+    for k, v in (('x', x), ('d_in', d_in), ('y_in', y_in), ('y_gt', y_gt), ('s_gt', s_gt)):
+      if v is None:
+        continue
+      if k not in st:
+        st[k] = torch.empty(v.shape, device=self.device, dtype=torch.float32)
+      st[k].copy_(v, non_blocking=True)
     want = None if outputs is None else set(outputs)
-    if want is None or 'x_patch' in want:
-      out['x_patch'] = bufs['x_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
-    if want is None or 'y_out_patch' in want:
-      out['y_out_patch'] = bufs['y_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
-    if with_loss and y_gt is not None:
-      self._loss(bufs, y_gt, s_gt, out, want_gt_box=(want is None or 'attn_box_gt' in want))
-      scal = out['loss_scalars']
-      for i, k in enumerate(LOSS_KEYS):
-        out[k] = scal[i]
+    want_all = want is None or bool(want & {'x_patch', 'y_out_patch', 'attn_box_gt'})
+    key = (with_loss, want_all)
+    if not use_graph:
+      out = self._run(bufs, B, with_loss, want_all)
+    else:
+      graphs = bufs.setdefault('graphs', {})
+      if key not in graphs:
+        # warm-up on a side stream (lazy weight packing, cudaFuncSetAttribute, allocator), then capture
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+          self._run(bufs, B, with_loss, want_all)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          static_out = self._run(bufs, B, with_loss, want_all)
+        graphs[key] = (g, static_out)
+      g, out = graphs[key]
+      g.replay()
     if want is not None:
       out = {k: out[k] for k in outputs}
     return out

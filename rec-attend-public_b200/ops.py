@@ -101,27 +101,41 @@ def canvas_conv(pre, canvas, w, scale, shift, pool=1, relu=True, out=None):
   return out
 
 
-def umma_plan(Cin, Cout, Hout, Wout, pool):
-  """(KC, NP, n_chunks) of the tcgen05 conv kernel for one layer shape."""
-  kc, npad, nch = _c.c_int(0), _c.c_int(0), _c.c_int(0)
-  _lib.call('ra_conv3x3_umma_plan', Cin, Cout, Hout, Wout, pool, _c.byref(kc), _c.byref(npad), _c.byref(nch))
-  return kc.value, npad.value, nch.value
+def umma_plan(Cin, Cout, Hout, Wout, pool, B):
+  """(KC, NPc, n_split, n_chunks) of the tcgen05 conv kernel for one layer shape and batch size."""
+  kc, npc, nsp, nch = _c.c_int(0), _c.c_int(0), _c.c_int(0), _c.c_int(0)
+  _lib.call('ra_conv3x3_umma_plan', Cin, Cout, Hout, Wout, pool, B, _c.byref(kc), _c.byref(npc), _c.byref(nsp),
+            _c.byref(nch))
+  return kc.value, npc.value, nsp.value, nch.value
 
 
-def pack_umma_weights(w_hwio, KC, NP):
+def umma_plan_info(Cin, Cout, Hout, Wout, pool, B):
+  """The full tile plan of the tcgen05 conv kernel as a dict (diagnostics)."""
+  info = (_c.c_int * 16)()
+  _lib.call('ra_conv3x3_umma_plan_info', Cin, Cout, Hout, Wout, pool, B, info)
+  keys = ['KC', 'NPc', 'n_split', 'n_chunks', 'TH', 'TW', 'n_mt', 'stages', 'merged', 'w_resident', 'grid',
+          'smem_bytes', 'acc_cols', 'stage_bytes', 'w_res_bytes', 'slots_alloc']
+  return dict(zip(keys, list(info)))
+
+
+def pack_umma_weights(w_hwio, KC, NPc, n_split):
   """HWIO conv filter [3,3,Cin,Cout] (numpy) -> the kernel's shared-memory image
-  [n_chunks][9][2 (hi,lo)][KC/4][NP][4]: hi = w rounded to the nearest tf32, lo = w - hi (exact)."""
+  [n_split][n_chunks][9][KC/4][2*NPc][4]: rows 0..NPc-1 = hi (w rounded to the nearest tf32),
+  rows NPc..2NPc-1 = lo = w - hi (exact)."""
   import numpy as np
   w = np.asarray(w_hwio, np.float32)
   _, _, Cin, Cout = w.shape
   n_chunks = (Cin + KC - 1) // KC
+  NP = NPc * n_split
   wp = np.zeros((9, n_chunks * KC, NP), np.float32)
   wp[:, :Cin, :Cout] = w.reshape(9, Cin, Cout)
   hi = ((wp.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)  # round to nearest tf32
   lo = wp - hi
-  def lay(a):  # [9, chunks*KC, NP] -> [chunks, 9, KC/4, NP, 4]
-    return a.reshape(9, n_chunks, KC // 4, 4, NP).transpose(1, 0, 2, 4, 3)
-  return np.ascontiguousarray(np.stack([lay(hi), lay(lo)], axis=2))
+
+  def lay(a):  # [9, chunks*KC, NP] -> [n_split, chunks, 9, KC/4, NPc, 4]
+    return a.reshape(9, n_chunks, KC // 4, 4, n_split, NPc).transpose(4, 1, 0, 2, 5, 3)
+
+  return np.ascontiguousarray(np.concatenate([lay(hi), lay(lo)], axis=4))
 
 
 def conv3x3_block_umma(x, wpack, Cout, scale, shift, pool=1, relu=True, x2=None, upsample=1, out=None):

@@ -64,17 +64,22 @@ def test_synthetic_batch_contract():
 
 def test_umma_plan_and_weight_packing():
   from rec_attend_b200 import ops
-  KC, NP, nch = ops.umma_plan(64, 96, 12, 12, 2)
-  assert KC in (8, 16) and NP == 96 and nch == 64 // KC
+  KC, NPc, nsp, nch = ops.umma_plan(64, 96, 12, 12, 2, 32)
+  assert KC in (8, 16, 32) and NPc * nsp == 96 and nch == 64 // KC
   rng = np.random.default_rng(0)
-  w = rng.standard_normal((3, 3, 13, 10)).astype(np.float32)
-  KC, NP, nch = ops.umma_plan(13, 10, 48, 48, 1)
-  wp = ops.pack_umma_weights(w, KC, NP)
-  assert wp.shape == (nch, 9, 2, KC // 4, NP, 4)
-  # hi + lo reproduces w exactly; hi has at most 11 significant mantissa bits
-  rec = (wp[:, :, 0] + wp[:, :, 1]).transpose(1, 0, 2, 4, 3).reshape(9, nch * KC, NP)
-  assert (rec[:, :13, :10] == w.reshape(9, 13, 10)).all() and (rec[:, 13:] == 0).all() and (rec[:, :, 10:] == 0).all()
-  assert (wp[:, :, 0].view(np.uint32) & np.uint32(0x1FFF) == 0).all()
+  w = rng.standard_normal((3, 3, 13, 40)).astype(np.float32)
+  for B in (1, 32):
+    KC, NPc, nsp, nch = ops.umma_plan(13, 40, 48, 48, 1, B)
+    assert NPc * nsp == 48 and NPc % 16 == 0
+    wp = ops.pack_umma_weights(w, KC, NPc, nsp)
+    assert wp.shape == (nsp, nch, 9, KC // 4, 2 * NPc, 4)
+    hi, lo = wp[:, :, :, :, :NPc], wp[:, :, :, :, NPc:]
+    # hi + lo reproduces w exactly; hi has at most 11 significant mantissa bits
+    rec = (hi + lo).transpose(2, 1, 3, 5, 0, 4).reshape(9, nch * KC, nsp * NPc)
+    assert (rec[:, :13, :40] == w.reshape(9, 13, 40)).all() and (rec[:, 13:] == 0).all() and (rec[:, :, 40:] == 0).all()
+    assert (np.ascontiguousarray(hi).view(np.uint32) & np.uint32(0x1FFF) == 0).all()
+  with pytest.raises(Exception):
+    ops.umma_plan(8, 8, 7, 7, 1, 1)  # odd output width is not supported
 
 
 def test_fold_bn_and_deconv_filter_transform():

@@ -415,6 +415,10 @@ UMMA_CASES = [
     (2, 48, 48, 16, 13, 1, 1, 1, 1),     # dcnn L6 (Cout = 1, odd skip)
     (1, 34, 70, 8, 0, 8, 1, 2, 0),       # ragged tiles, Cout = 8 (CVPPP-arch)
     (1, 512, 1024, 16, 0, 16, 1, 2, 1),  # Cityscapes-size ctrl L1
+    (32, 16, 32, 64, 0, 64, 1, 2, 1),    # ctrl L7 at the bench batch (N split over CTAs)
+    (32, 12, 12, 64, 64, 64, 1, 1, 1),   # dcnn L1 at the bench batch
+    (7, 12, 12, 64, 0, 96, 1, 2, 1),     # odd batch, N = 96
+    (5, 64, 128, 32, 0, 32, 1, 2, 1),    # several tiles per CTA (persistent loop, TMEM double buffering)
 ]
 
 
@@ -441,9 +445,9 @@ def test_conv3x3_block_umma(ops, case):
     ref = torch.relu(ref)
   if pool == 2:
     ref = OM.max_pool_same(ref, 2)
-  KC, NP, nch = ops.umma_plan(Cin, Cout, H * up, W * up, pool)
-  wp = ops.pack_umma_weights(w, KC, NP)
-  assert wp.shape == (nch, 9, 2, KC // 4, NP, 4)
+  KC, NPc, nsp, nch = ops.umma_plan(Cin, Cout, H * up, W * up, pool, B)
+  wp = ops.pack_umma_weights(w, KC, NPc, nsp)
+  assert wp.shape == (nsp, nch, 9, KC // 4, 2 * NPc, 4)
   out = ops.conv3x3_block_umma(_g(x1), _g(wp), Cout, _g(scale), _g(shift), pool=pool, relu=bool(relu),
                                x2=None if x2 is None else _g(x2), upsample=up)
   torch.cuda.synchronize()
