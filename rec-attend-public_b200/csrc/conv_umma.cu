@@ -15,11 +15,11 @@
 // M = 128 consecutive output slots per MMA (2 of every TWP are halo garbage and are dropped in
 // the epilogue), N = the CTA's share of Cout (padded to 16), K = 8 channels per instruction.
 //
-// Persistent, warp-specialised pipeline (one CTA per SM, 384 threads):
-//   warps 5-11  producers: stage the input chunk (with the hi/lo split) and the pre-packed filter
+// Persistent, warp-specialised pipeline (one CTA per SM, 512 threads):
+//   warps 8-15  producers: stage the input chunk (with the hi/lo split) and the pre-packed filter
 //               slice of (tile, channel-chunk) items into a ring of shared-memory stages;
 //               fence.proxy.async + mbarrier arrive (full[s]).
-//   warp 4      one thread issues n_mt x 9 taps x (2|3) tcgen05.mma per item, tcgen05.commit ->
+//   warps 4-7   one lane each issues its share of the n_mt x 9 taps x (2|3) tcgen05.mma per item, tcgen05.commit ->
 //               empty[s]; after a tile's last chunk tcgen05.commit -> tmem_full[buf].
 //   warps 0-3   epilogue: tcgen05.ld (thread = TMEM lane = slot), folded BN scale/shift, ReLU,
 //               2x2 max-pool (horizontal by shuffle, vertical through a small shared tile),
@@ -35,9 +35,10 @@
 namespace {
 
 constexpr int kEpiThreads = 128;   // warps 0-3
-constexpr int kMmaWarp = 4;        // warp 4
-constexpr int kProdThreads = 224;  // warps 5-11
-constexpr int kThreads = kEpiThreads + 32 + kProdThreads;
+constexpr int kMmaWarp0 = 4;       // warps 4-7: one issuing lane each, m-tiles dealt round-robin
+constexpr int kMmaWarps = 4;
+constexpr int kProdThreads = 256;  // warps 8-15
+constexpr int kThreads = kEpiThreads + 32 * kMmaWarps + kProdThreads;
 constexpr int kMaxStages = 4;
 constexpr int kStageUnroll = 4;
 constexpr int kPoolLd = 20;  // floats per staged half-row of a 16-column chunk (16 + 4 padding)
@@ -165,10 +166,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), kProdThreads);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), kMmaWarps);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tfull[s]), kMmaWarps);
       mbar_init(smem_u32(&bar_tempty[s]), kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
   const uint32_t tmem_base = tmem_base_s;
   const int slots_in = (p.TH + 2) * p.TWP + 2;  // slots that carry real (or zero-padding) data
 
-  if (warp > kMmaWarp) {
+  if (warp >= kMmaWarp0 + kMmaWarps) {
     // =============================== producers ===============================
-    const int ptid = tid - (kEpiThreads + 32);
+    const int ptid = tid - (kEpiThreads + 32 * kMmaWarps);
     int g = 0;  // running (tile, chunk) counter
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       const Item it = decode_tile(p, tile);
@@ -299,11 +300,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
         mbar_arrive(smem_u32(&bar_full[s]));
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp >= kMmaWarp0) {
     // =============================== MMA issuer ===============================
-    // One lane issues (measured: letting the whole warp run the loops with only the tcgen05 instructions
-    // predicated is slower — 31 lanes spin on the barriers and every MMA still pays the R2UR moves).
+    // The issue of one tcgen05.mma costs ~130 cycles of scalar work in the issuing thread (descriptor
+    // arithmetic + R2UR moves, see profiles/), 2-3x the tensor core's own 45-64 cycles per M=128 x K=8
+    // instruction, so kMmaWarps threads issue in parallel, each for its own m-tiles (= its own TMEM
+    // accumulators; no two threads ever accumulate into the same columns).
     if (lane == 0) {
+      const int mw = warp - kMmaWarp0;
       const int cols_mt = p.merged ? 2 * p.NPc : p.NPc;
       const uint32_t idesc_n =
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NPc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -340,18 +344,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
               const uint32_t acc_flag = (ch == 0 && tap == 0 && k8 == 0) ? 0u : 1u;
               if (p.merged) {
                 // D[:, 0:N] += A_hi B_hi and D[:, N:2N] += A_hi B_lo in ONE instruction ...
-                for (int mt = 0; mt < p.n_mt; ++mt)
+                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
                   umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_hi + (uint64_t)(mt * 128), db_hi, idesc_2n, acc_flag);
                 // ... then D[:, 0:N] += A_lo B_hi
-                for (int mt = 0; mt < p.n_mt; ++mt)
+                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
                   umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_lo + (uint64_t)(mt * 128), db_hi, idesc_n, 1u);
               } else {
                 const uint64_t db_lo = db_hi + (uint64_t)p.NPc;  // rows NPc..2NPc-1 of the plane
-                for (int mt = 0; mt < p.n_mt; ++mt)
+                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
                   umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_hi + (uint64_t)(mt * 128), db_hi, idesc_n, acc_flag);
-                for (int mt = 0; mt < p.n_mt; ++mt)
+                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
                   umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_hi + (uint64_t)(mt * 128), db_lo, idesc_n, 1u);
-                for (int mt = 0; mt < p.n_mt; ++mt)
+                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
                   umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_lo + (uint64_t)(mt * 128), db_hi, idesc_n, 1u);
               }
             }
@@ -494,12 +498,16 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
   for (int n_split = 1; n_split <= 8; n_split *= 2) {
     if (NP % (16 * n_split) != 0) break;
     const int NPc = NP / n_split;
-    const int merged = (NPc <= 64) ? 1 : 0;  // [B_hi; B_lo] stacked along N: one MMA (N' <= 128) reads A_hi once
+   for (int merged = 1; merged >= 0; --merged) {
+    // merged: [B_hi; B_lo] stacked along N, one MMA (N' = 2 NPc <= 256) reads A_hi once; 2 instead of 3 MMAs
+    if (merged && 2 * NPc > 256) continue;
     const int cols_mt = merged ? 2 * NPc : NPc;
     const int mt_max = 256 / cols_mt;  // two accumulator buffers in 512 TMEM columns
     if (mt_max < 1) continue;
-    const double mma_cycles = merged ? (2.0 * NPc / 2 > 64 ? 2.0 * NPc / 2 : 64.0) + 64.0
-                                     : 3.0 * (NPc / 2 > 64 ? NPc / 2 : 64.0);
+    // tensor-core time of one M=128 x K=8 instruction: max(~48, N/2) cycles (tools/umma_rate.cu)
+    const double hw_n = NPc / 2 > 48 ? NPc / 2 : 48.0, hw_2n = NPc > 48 ? (double)NPc : 48.0;
+    const double hw_cycles = merged ? hw_2n + hw_n : 3.0 * hw_n;
+    const double issue_cycles = (merged ? 2.0 : 3.0) * 130.0;  // scalar cost of issuing, per issuing thread
     for (int KC = 8; KC <= 32; KC *= 2) {
       if (KC > 8 && KC / 2 >= Cin) continue;
       const int planes = KC / 4;
@@ -526,7 +534,10 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
             if (fixed + 2 * stage_bytes > smem_cap) continue;
             int st = (int)((smem_cap - fixed) / stage_bytes);
             if (st > kMaxStages) st = kMaxStages;
-            const double mma_item = (double)n_mt * 9 * (KC / 8) * n_chunks * mma_cycles;
+            const double per_tap = (double)9 * (KC / 8) * n_chunks;
+            const double mma_hw = n_mt * per_tap * hw_cycles;
+            const double mma_issue = ((n_mt + kMmaWarps - 1) / kMmaWarps) * per_tap * issue_cycles;
+            const double mma_item = mma_hw > mma_issue ? mma_hw : mma_issue;
             const double prod_item = (double)n_chunks * stage_bytes / kProdBytesPerCycle;
             const double epi_item = 400.0 + 60.0 * n_mt * (NPc / 16);
             double item = mma_item > prod_item ? mma_item : prod_item;
@@ -561,6 +572,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
         }
       }
     }
+   }
   }
   if (!found) return RA_ERR_UNSUPPORTED;
   *pl = bp;
