@@ -253,17 +253,48 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
   float *red_s = part_s + 256;                 // [32]
   float *out_s = red_s + 32;                   // [16]
 
-  // ---- one-time loads: my slice of the weights
-  for (int i = tid; i < kKin * 4 * kUnits; i += 256) {
-    const int col = i % (4 * kUnits), k = i / (4 * kUnits);
-    const int q = col / kUnits, u = col % kUnits;
-    const int j = r * kUnits + u;
-    wg_s[i] = (k < kCf2) ? __ldg(p.wx + ((size_t)q * kCf2 + k) * kHd2 + j)
-                         : __ldg(p.wh + ((size_t)q * kHd2 + (k - kCf2)) * kHd2 + j);
-  }
-  for (int i = tid; i < kHd2 * kUnits; i += 256) {
-    const int u = i % kUnits, k = i / kUnits;
-    w0_s[i] = __ldg(p.gw0 + (size_t)k * kHd2 + r * kUnits + u);
+  // ---- one-time loads: my slice of the weights (float4 along the hidden-unit index, 8 loads in flight)
+  {
+    constexpr int kU = 8;
+    const int n4 = kKin * 4 * kUnits / 4;  // float4 items of wg_s
+    for (int base = tid; base < n4; base += 256 * kU) {
+      float4 v[kU];
+#pragma unroll
+      for (int u8 = 0; u8 < kU; ++u8) {
+        const int i4 = base + u8 * 256;
+        v[u8] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < n4) {
+          const int col = (i4 * 4) % (4 * kUnits), k = (i4 * 4) / (4 * kUnits);
+          const int q = col / kUnits, u = col % kUnits;
+          const int j = r * kUnits + u;
+          v[u8] = (k < kCf2) ? __ldg(reinterpret_cast<const float4 *>(p.wx + ((size_t)q * kCf2 + k) * kHd2 + j))
+                             : __ldg(reinterpret_cast<const float4 *>(p.wh + ((size_t)q * kHd2 + (k - kCf2)) * kHd2 + j));
+        }
+      }
+#pragma unroll
+      for (int u8 = 0; u8 < kU; ++u8) {
+        const int i4 = base + u8 * 256;
+        if (i4 < n4) *reinterpret_cast<float4 *>(wg_s + i4 * 4) = v[u8];
+      }
+    }
+    const int m4 = kHd2 * kUnits / 4;  // float4 items of w0_s
+    for (int base = tid; base < m4; base += 256 * kU) {
+      float4 v[kU];
+#pragma unroll
+      for (int u8 = 0; u8 < kU; ++u8) {
+        const int i4 = base + u8 * 256;
+        v[u8] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < m4) {
+          const int u = (i4 * 4) % kUnits, k = (i4 * 4) / kUnits;
+          v[u8] = __ldg(reinterpret_cast<const float4 *>(p.gw0 + (size_t)k * kHd2 + r * kUnits + u));
+        }
+      }
+#pragma unroll
+      for (int u8 = 0; u8 < kU; ++u8) {
+        const int i4 = base + u8 * 256;
+        if (i4 < m4) *reinterpret_cast<float4 *>(w0_s + i4 * 4) = v[u8];
+      }
+    }
   }
   if (tid < 4 * kUnits) bg_s[tid] = __ldg(p.bg + (tid / kUnits) * kHd2 + r * kUnits + (tid % kUnits));
   if (tid < kUnits) b0_s[tid] = __ldg(p.gb0 + r * kUnits + tid);

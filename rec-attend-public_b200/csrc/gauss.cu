@@ -18,13 +18,16 @@ namespace {
 
 constexpr float kCut = 30.0f;  // drop filter entries below exp(-30) ~ 9e-14 of the tap's peak
 constexpr int kMaxF = 64;
+constexpr int kTapsPerCta = 8;
 
 // ------------------------------------------------------------------ filter construction
 __global__ void build_filters_kernel(const float *__restrict__ box, int H, int W, int F, float *__restrict__ fy,
                                      float *__restrict__ fx, int *__restrict__ band) {
   const int b = blockIdx.x;
   const float *bo = box + (size_t)b * RA_BOX_STRIDE;
-  for (int axis = 0; axis < 2; ++axis) {
+  {
+    const int axis = blockIdx.y;  // one CTA per (example, axis, group of kTapsPerCta taps)
+    const int t0 = blockIdx.z * kTapsPerCta, t1 = min(F, t0 + kTapsPerCta);
     const int L = axis == 0 ? H : W;
     float *f = axis == 0 ? fy + (size_t)b * F * H : fx + (size_t)b * F * W;
     const float ctr = bo[RA_BOX_CTR_Y + axis];
@@ -33,7 +36,7 @@ __global__ void build_filters_kernel(const float *__restrict__ box, int H, int W
     // modellib.py:610: 1 / sqrt(exp(lg_var)) / sqrt(2*pi)
     const float norm = 1.0f / sqrtf(var) / sqrtf(2.0f * 3.14159265358979323846f);
     const float step = (size + 1.0f) / (float)F;  // modellib.py:599
-    for (int idx = threadIdx.x; idx < F * L; idx += blockDim.x) {
+    for (int idx = t0 * L + threadIdx.x; idx < t1 * L; idx += blockDim.x) {
       const int t = idx / L, l = idx - t * L;
       const float mu = ctr + step * ((float)t - (float)(F - 1) / 2.0f);
       const float d = (float)l - mu;
@@ -41,7 +44,7 @@ __global__ void build_filters_kernel(const float *__restrict__ box, int H, int W
       f[idx] = (e >= -kCut) ? norm * expf(e) : 0.f;
     }
     // support band of every tap (a superset of the non-zero entries; empty if hi < lo)
-    for (int t = threadIdx.x; t < F; t += blockDim.x) {
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
       const float mu = ctr + step * ((float)t - (float)(F - 1) / 2.0f);
       const float R = sqrtf(2.0f * var * kCut) + 1.0f;
       float lo = ceilf(mu - R), hi = floorf(mu + R);
@@ -271,7 +274,8 @@ extern "C" int ra_gaussian_filters_f32(const float *box, int B, int H, int W, in
   if (!box || !fy || !fx || !band || B < 0 || H < 1 || W < 1 || F < 1) return RA_ERR_INVALID_ARG;
   if (F > kMaxF) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
-  build_filters_kernel<<<B, 256, 0, ra::as_stream(stream)>>>(box, H, W, F, fy, fx, band);
+  build_filters_kernel<<<dim3(B, 2, (F + kTapsPerCta - 1) / kTapsPerCta), 256, 0, ra::as_stream(stream)>>>(box, H, W, F, fy, fx,
+                                                                                                  band);
   return ra::finish_launch("build_filters_kernel");
 }
 

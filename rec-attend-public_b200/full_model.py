@@ -364,10 +364,13 @@ class FullModel(_ModelBase):
     _lib.TAG = 'loss'
     tl, br, box_gt, rect, area = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'],
                                                 min_padding=self.min_padding, want_box=want_gt_box)
-    iou_box = ops.f_iou(bufs['attn_box'], None, b_rect=rect)
-    match_box = ops.f_segm_match(iou_box, s_gt)
-    iou_soft = ops.f_iou(bufs['y_out'], y_gt)
-    match = ops.f_segm_match(iou_soft, s_gt)
+    # both matchings (boxes, masks) in ONE launch of 2B warps: they are independent and latency-bound
+    B, T = s_gt.shape
+    iou_both = torch.empty((2 * B, T, T), device=s_gt.device, dtype=torch.float32)
+    iou_box = ops.f_iou(bufs['attn_box'], None, b_rect=rect, out=iou_both[:B])
+    iou_soft = ops.f_iou(bufs['y_out'], y_gt, out=iou_both[B:])
+    match_both = ops.f_segm_match(iou_both, torch.cat([s_gt, s_gt], 0))
+    match_box, match = match_both[:B], match_both[B:]
     iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
     scal = ops.loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice, bufs['s_out'], s_gt, area,
                           o['loss_mix_ratio'], self.wd_term)

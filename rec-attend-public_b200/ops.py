@@ -260,7 +260,7 @@ def get_gt_box(y_gt, padding_ratio=0.0, min_padding=10.0, want_box=True):
   return tl, br, box, rect, area
 
 
-def f_iou(a, b=None, pairwise=True, b_rect=None, hard_threshold=0.0, want_dice=False, H=None, W=None):
+def f_iou(a, b=None, pairwise=True, b_rect=None, hard_threshold=0.0, want_dice=False, H=None, W=None, out=None):
   """modellib.f_iou(a, b, timespan, pairwise=True) (modellib.py:138-153): a [B,N,H,W],
   b [B,M,H,W] (or b_rect [B,M,4] rectangles) -> iou [B,N,M] (and f_dice, :81-97)."""
   assert pairwise, 'only the pairwise form is on the hot path'
@@ -272,7 +272,8 @@ def f_iou(a, b=None, pairwise=True, b_rect=None, hard_threshold=0.0, want_dice=F
   if n_ws == 0:
     raise _lib.RecAttendError('ra_pairwise_iou: unsupported N/M')
   ws = torch.empty((n_ws,), device=dev, dtype=torch.float32)
-  iou = torch.empty((B, N, M), device=dev, dtype=torch.float32)
+  iou = torch.empty((B, N, M), device=dev, dtype=torch.float32) if out is None else out
+  assert tuple(iou.shape) == (B, N, M) and iou.is_contiguous()
   dice = torch.empty((B, N, M), device=dev, dtype=torch.float32) if want_dice else None
   _lib.call('ra_pairwise_iou_f32', _p(a), _p(b), _p(b_rect), B, N, M, H, W, float(hard_threshold), _p(ws), _p(iou),
             _p(dice), _stream())
