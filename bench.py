@@ -247,9 +247,23 @@ def run_ours(args):
   def step_device():
     return model.forward(dev_batch, outputs=fetch)
 
+  # two pinned host copies of the step's inputs, used alternately (a real loader hands over a new batch each step)
+  pinned2 = {k: v.clone().pin_memory() for k, v in pinned.items()}
+  host_batches = [pinned, pinned2]
+  e2e_state = {'i': 0}
+
   def step_e2e():
-    # public API call with HOST buffers: H2D of every input, forward, D2H of the step's results
-    out = model.forward(pinned, outputs=fetch)
+    # public API call with HOST buffers: H2D of every input, forward, D2H of the step's results.  The H2D of
+    # step i+1 is issued (model.prefetch) before step i computes, i.e. the copies are double buffered; every
+    # step still copies all of its inputs from pinned host memory inside the timed region.
+    i = e2e_state['i']
+    cur, nxt = host_batches[i % 2], host_batches[(i + 1) % 2]
+    e2e_state['i'] = i + 1
+    if i == 0:
+      model.prefetch(cur)
+    out_prev = None
+    out = model.forward(cur, outputs=fetch)
+    model.prefetch(nxt)
     for k, v in out.items():
       if k not in host_out:
         host_out[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
@@ -361,7 +375,8 @@ def run_ours(args):
                    'l2': 'inputs {:.0f} MB + per-step working set exceed the 126 MB L2'.format(h2d / 1e6),
                    'step': 'eval forward (T-step decode) + matching loss block'},
         'e2e': {'value': e2e_value, 'unit': 'masks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': ms_e2e / args.steps, 'fetch': fetch},
+                'ms_per_step': ms_e2e / args.steps, 'fetch': fetch,
+                'pipeline': 'H2D of step i+1 overlaps the compute of step i (double-buffered static inputs)'},
         'gpu_launches': launches_per_step * args.steps,
         'gpu_launches_note': '{} kernels of librecattend_b200.so per step (counted in one eager step); the timed '
                              'steps replay exactly these launches from one CUDA graph per step'.format(launches_per_step),

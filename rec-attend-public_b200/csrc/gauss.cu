@@ -160,19 +160,23 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
   for (int idx = threadIdx.x; idx < F * D; idx += blockDim.x) {
     const int j = idx / D, d = idx - j * D;
     const int lo = bd[j * 2], hi = bd[j * 2 + 1];
-    float a0 = 0.f, a1 = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float *fj = fxb + (size_t)j * W;
     int x = lo;
-    for (; x + 1 <= hi; x += 2) {
-      a0 = fmaf(slab[x * D + d], fxb[(size_t)j * W + x], a0);
-      a1 = fmaf(slab[(x + 1) * D + d], fxb[(size_t)j * W + x + 1], a1);
+    for (; x + 3 <= hi; x += 4) {
+      const float f0 = __ldg(fj + x), f1 = __ldg(fj + x + 1), f2 = __ldg(fj + x + 2), f3 = __ldg(fj + x + 3);
+      a0 = fmaf(slab[x * D + d], f0, a0);
+      a1 = fmaf(slab[(x + 1) * D + d], f1, a1);
+      a2 = fmaf(slab[(x + 2) * D + d], f2, a2);
+      a3 = fmaf(slab[(x + 3) * D + d], f3, a3);
     }
-    if (x <= hi) a0 = fmaf(slab[x * D + d], fxb[(size_t)j * W + x], a0);
-    patch[(((size_t)b * F + i) * F + j) * D + d] = gamma * (a0 + a1);  // full_model.py:788
+    for (; x <= hi; ++x) a0 = fmaf(slab[x * D + d], __ldg(fj + x), a0);
+    patch[(((size_t)b * F + i) * F + j) * D + d] = gamma * ((a0 + a1) + (a2 + a3));  // full_model.py:788
   }
 }
 
 // ------------------------------------------------------------------ paste-back
-constexpr int kPbTY = 8;
+constexpr int kPbTY = 8;  // rows per CTA (32 measured slower: fewer CTAs in flight to hide the prologue loads)
 constexpr int kPbTX = 128;
 
 __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict__ patch,
@@ -214,7 +218,8 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
   }
   __syncthreads();
 
-  const int col = tid % kPbTX, rh = tid / kPbTX;  // 2 row-halves of 4 rows
+  constexpr int kRows = kPbTY / 2;
+  const int col = tid % kPbTX, rh = tid / kPbTX;  // 2 row-halves of kRows rows
   const int x = x0 + col;
   // taps whose band can reach column x (analytic superset; entries outside a band are 0)
   int jlo = 0, jhi = F - 1;
@@ -235,7 +240,9 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
     jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
     jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
   }
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
   float sx = 0.f;
   if (x < W) {
     const float *fxp = fx + (size_t)b * F * W + x;
@@ -244,17 +251,17 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
       sx += wx;
       if (has_patch) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r] = fmaf(t2_s[rh * 4 + r][j], wx, acc[r]);
+        for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t2_s[rh * kRows + r][j], wx, acc[r]);
       }
     }
     const float g_box = bo[RA_BOX_GAMMA_BOX], g_y = bo[RA_BOX_GAMMA_Y];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int y = y0 + rh * 4 + r;
+    for (int r = 0; r < kRows; ++r) {
+      const int y = y0 + rh * kRows + r;
       if (y >= H) continue;
       const size_t pix = (size_t)y * W + x;
       if (attn_box != nullptr)  // full_model.py:738-741
-        attn_box[(size_t)b * out_bstride + pix] = ra::sigmoidf_acc(g_box * (sy_s[rh * 4 + r] * sx) - 5.0f);
+        attn_box[(size_t)b * out_bstride + pix] = ra::sigmoidf_acc(g_box * (sy_s[rh * kRows + r] * sx) - 5.0f);
       if (has_patch) {  // full_model.py:810-818, 845
         const size_t cpix = (size_t)b * H * W + pix;
         const float cv = canvas[cpix];
