@@ -243,12 +243,12 @@ int ra_pairwise_iou_f32(const float *a, const float *b, const float *b_rect, int
 #define RA_LOSS_COUNT_ACC 10
 #define RA_LOSS_DIC 11
 #define RA_LOSS_DIC_ABS 12
-#define RA_LOSS_TOTAL 13 /* box + segm + mix*conf + weight_decay_term */
+#define RA_LOSS_TOTAL 13 /* box + segm_coeff*segm + mix*conf + weight_decay_term (segm_coeff = 0: box_model.py:558-629) */
 #define RA_LOSS_COUNT 16
 int ra_loss_block_f32(const float *iou_box, const float *match_box, const float *iou_soft, const float *match,
                       const float *iou_hard, const float *dice_hard, const float *s_out, const float *s_gt,
                       const float *gt_area, int B, int T, float loss_mix_ratio, float weight_decay_term,
-                      float *out, void *stream);
+                      float segm_coeff, float *out, void *stream);
 
 /* Greedy GT interaction of box_model.py:484-504 for one decode step: iou_t[b,m] =
  * f_inter(attn_box_t, box_gt_m)/f_union (rectangle form of box_gt), grd = one-hot of the row

@@ -47,7 +47,7 @@ _SIGNATURES = {
     'ra_score_f32': [_P, _I, _P, _I, _P, _P, _I, _P, _I, _P],
     'ra_gt_box_f32': [_P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     'ra_pairwise_iou_f32': [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P],
-    'ra_loss_block_f32': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P],
+    'ra_loss_block_f32': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P],
     'ra_box_gt_step_f32': [_P, _Z, _P, _P, _P, _Z, _I, _I, _I, _I, _P, _I, _P, _P, _P],
     'ra_concat_channels_f32': [_P, _I, _P, _I, _P, _I, _Z, _P, _P],
 }

@@ -1,0 +1,103 @@
+"""Host side of the controller-only model — the drop-in for ``box_model.get_model`` (box_model.py:11)
+in eval mode: the same controller CNN + glimpse LSTM + box head as the full model, no patch CNN / mask
+head; the canvas is driven by the greedily matched ground-truth masks in eval too (box_model.py:484-504).
+BASELINE config 5.  Same conventions as full_model.py (opt dict, named inputs/outputs, weight keys of
+box_model_read.py:31-52); every FLOP runs in librecattend_b200.so.
+"""
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .full_model import _ModelBase
+
+
+class BoxModel(_ModelBase):
+
+  def __init__(self, opt, device=None):
+    super(BoxModel, self).__init__(opt, device)
+    if self.opt.get('num_semantic_classes', 1) != 1 and not self.add_d:
+      raise _lib.RecAttendError('multi-class score head is not used by the shipped box configs')
+    if self.opt.get('use_iou_box', False):
+      raise _lib.RecAttendError('use_iou_box is not used by the shipped box configs (run_kitti.sh:44-60)')
+    if self.opt['box_loss_fn'] != 'iou':
+      raise _lib.RecAttendError("only box_loss_fn='iou' works in the reference (SURVEY §9.13)")
+    self.min_padding = 10.0  # modellib.get_gt_box default (box_model.py:386-387)
+
+  def _fixed_var(self):
+    return bool(self.opt.get('fixed_var', True))  # box_model.py:58-61
+
+  def _fixed_gamma(self):
+    return True  # the box model has no attention / mask gains
+
+  def load_weights(self, weights):
+    self._raw_weights = {k: np.asarray(v, np.float32) for k, v in weights.items()}
+    self.w = self._load_controller(weights)
+    if self.w['score_mlp_w_0'].numel() != self.Hd:
+      raise _lib.RecAttendError('box model score MLP takes the controller state only (box_model.py:359-363)')
+    self.wd_term = self._weight_decay_term(weights)
+    return self
+
+  def _alloc(self, B):
+    bufs = {}
+    self._alloc_controller(B, bufs)
+    dev, T = self.device, self.T
+    bufs['iou_box'] = torch.empty((B, T, T), device=dev, dtype=torch.float32)
+    bufs['grd'] = torch.empty((B, T), device=dev, dtype=torch.float32)
+    return bufs
+
+  def _run(self, bufs, B, noise):
+    w, o = self.w, self.opt
+    T, H, W = self.T, self.H, self.W
+    st = bufs['static_in']
+    y_gt, s_gt = st['y_gt'], st['s_gt']
+    self._prepare(bufs, st['x'], st.get('d_in'), st.get('y_in'))
+    _lib.TAG = 'loss'
+    tl, br, box_gt, rect, area = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'],
+                                                min_padding=self.min_padding, want_box=False)
+    thw = T * H * W
+    for t in range(T):
+      self._controller(bufs, t)
+      _lib.TAG = 'paste_back'
+      ops.paste_back(None, bufs['box_all'][t], bufs['fy'], bufs['fx'], None, attn_box=bufs['attn_box'][:, t],
+                     y_out=None, out_bstride=thw)
+      _lib.TAG = 'box_gt'
+      ops.box_gt_step(bufs['attn_box'][:, t], thw, rect, y_gt, None if noise is None else noise[:, t], thw,
+                      bufs['iou_box'][:, t], T * T, bufs['grd'], bufs['canvas'])
+      ops.score(bufs['h_all'][t], None, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
+    out = {}
+    self._controller_outputs(bufs, out)
+    _lib.TAG = 'loss'
+    match_box = ops.f_segm_match(bufs['iou_box'], s_gt)
+    scal = ops.loss_block(bufs['iou_box'], match_box, bufs['iou_box'], match_box, None, None, bufs['s_out'], s_gt,
+                          area, 1.0, self.wd_term, segm_coeff=0.0)
+    out.update({'iou_soft_box_pairwise': bufs['iou_box'], 'match_box': match_box, 'attn_top_left_gt': tl,
+                'attn_bot_right_gt': br, 'box_loss': scal[0], 'conf_loss': scal[2], 'loss': scal[13]})
+    return out
+
+  def forward(self, batch, outputs=None, phase_train=False):
+    """``sess.run`` replacement for the box model (eval mode).  batch: x, y_gt, s_gt[, d_in, y_in] and the
+    optional explicit random draw ``canvas_noise`` [B,T,H,W] of box_model.py:501-502 (zeros when absent)."""
+    if phase_train:
+      raise _lib.RecAttendError('training-mode forward is a later row of the scope table')
+    if self.w is None:
+      raise _lib.RecAttendError('load_weights() first')
+    x, d_in, y_in, y_gt, s_gt = self._inputs(batch)
+    if y_gt is None or s_gt is None:
+      raise _lib.RecAttendError('the box model needs y_gt / s_gt: its canvas is driven by the ground truth')
+    B = x.shape[0]
+    bufs = self._buffers(B)
+    cur = torch.cuda.current_stream()
+    st = self._stage_inputs(bufs, 0, {'x': x, 'd_in': d_in, 'y_in': y_in, 'y_gt': y_gt, 's_gt': s_gt}, cur)
+    bufs['static_in'] = st
+    noise = None
+    if batch.get('canvas_noise') is not None:
+      noise = torch.as_tensor(batch['canvas_noise'], dtype=torch.float32).to(self.device).contiguous()
+    out = self._run(bufs, B, noise)
+    if outputs is not None:
+      out = {k: out[k] for k in outputs}
+    return out
+
+
+def get_model(opt, device=None):
+  """Same call as the reference's ``box_model.get_model(opt)``."""
+  return BoxModel(opt, device=device)

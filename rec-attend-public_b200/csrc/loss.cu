@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(256) loss_block_kernel(const float *__restrict
                                                          const float *__restrict__ s_out,
                                                          const float *__restrict__ s_gt,
                                                          const float *__restrict__ gt_area, int B, int T,
-                                                         float mix, float wd_term, float *__restrict__ out) {
+                                                         float mix, float wd_term, float segm_coeff,
+                                                         float *__restrict__ out) {
   __shared__ float red[32];
   float v[RA_LOSS_COUNT];
 #pragma unroll
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(256) loss_block_kernel(const float *__restrict
     out[RA_LOSS_COUNT_ACC] = v[RA_LOSS_COUNT_ACC] / fB;
     out[RA_LOSS_DIC] = v[RA_LOSS_DIC] / fB;
     out[RA_LOSS_DIC_ABS] = v[RA_LOSS_DIC_ABS] / fB;
-    out[RA_LOSS_TOTAL] = out[RA_LOSS_BOX] + out[RA_LOSS_SEGM] + mix * out[RA_LOSS_CONF] + wd_term;
+    out[RA_LOSS_TOTAL] = out[RA_LOSS_BOX] + segm_coeff * out[RA_LOSS_SEGM] + mix * out[RA_LOSS_CONF] + wd_term;
     out[14] = 0.f;
     out[15] = 0.f;
   }
@@ -494,12 +495,13 @@ extern "C" int ra_pairwise_iou_f32(const float *a, const float *b, const float *
 extern "C" int ra_loss_block_f32(const float *iou_box, const float *match_box, const float *iou_soft,
                                  const float *match, const float *iou_hard, const float *dice_hard,
                                  const float *s_out, const float *s_gt, const float *gt_area, int B, int T,
-                                 float loss_mix_ratio, float weight_decay_term, float *out, void *stream) {
+                                 float loss_mix_ratio, float weight_decay_term, float segm_coeff, float *out,
+                                 void *stream) {
   if (!iou_box || !match_box || !iou_soft || !match || !s_out || !s_gt || !gt_area || !out || B < 1 || T < 1)
     return RA_ERR_INVALID_ARG;
   loss_block_kernel<<<1, 256, 0, ra::as_stream(stream)>>>(iou_box, match_box, iou_soft, match, iou_hard, dice_hard,
                                                           s_out, s_gt, gt_area, B, T, loss_mix_ratio,
-                                                          weight_decay_term, out);
+                                                          weight_decay_term, segm_coeff, out);
   return ra::finish_launch("loss_block_kernel");
 }
 

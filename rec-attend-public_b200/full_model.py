@@ -185,6 +185,19 @@ class _ModelBase(object):
     s_gt = dev(batch['s_gt']) if 's_gt' in batch else None
     return x, d_in, y_in, y_gt, s_gt
 
+  def _stage_inputs(self, bufs, slot, tensors, stream):
+    """Copy the step's inputs into static input set `slot` on `stream` (H2D for host tensors)."""
+    sets = bufs.setdefault('static_in_sets', [{}, {}])
+    st = sets[slot]
+    with torch.cuda.stream(stream):
+      for k, v in tensors.items():
+        if v is None:
+          continue
+        if k not in st:
+          st[k] = torch.empty(v.shape, device=self.device, dtype=torch.float32)
+        st[k].copy_(v, non_blocking=True)
+    return st
+
   def _buffers(self, B):
     if B not in self._bufs:
       self._bufs[B] = self._alloc(B)
@@ -399,19 +412,6 @@ class FullModel(_ModelBase):
       for i, k in enumerate(LOSS_KEYS):
         out[k] = scal[i]
     return out
-
-  def _stage_inputs(self, bufs, slot, tensors, stream):
-    """Copy the step's inputs into static input set `slot` on `stream` (H2D for host tensors)."""
-    sets = bufs.setdefault('static_in_sets', [{}, {}])
-    st = sets[slot]
-    with torch.cuda.stream(stream):
-      for k, v in tensors.items():
-        if v is None:
-          continue
-        if k not in st:
-          st[k] = torch.empty(v.shape, device=self.device, dtype=torch.float32)
-        st[k].copy_(v, non_blocking=True)
-    return st
 
   def prefetch(self, batch):
     """Start copying the NEXT step's inputs (pinned host memory -> the idle static input set) on a copy

@@ -283,14 +283,14 @@ def f_iou(a, b=None, pairwise=True, b_rect=None, hard_threshold=0.0, want_dice=F
 
 
 def loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice_hard, s_out, s_gt, gt_area, loss_mix_ratio,
-               weight_decay_term):
+               weight_decay_term, segm_coeff=1.0):
   """full_model.py:942-1081 scalars -> dict keyed like the reference's model dict."""
   _chk(iou_box, match_box, iou_soft, match, iou_hard, dice_hard, s_out, s_gt, gt_area)
   B, T = s_out.shape
   out = torch.empty((_lib.LOSS_COUNT,), device=s_out.device, dtype=torch.float32)
   _lib.call('ra_loss_block_f32', _p(iou_box), _p(match_box), _p(iou_soft), _p(match), _p(iou_hard), _p(dice_hard),
-            _p(s_out), _p(s_gt), _p(gt_area), B, T, float(loss_mix_ratio), float(weight_decay_term), _p(out),
-            _stream())
+            _p(s_out), _p(s_gt), _p(gt_area), B, T, float(loss_mix_ratio), float(weight_decay_term),
+            float(segm_coeff), _p(out), _stream())
   return out
 
 

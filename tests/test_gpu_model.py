@@ -112,3 +112,28 @@ def test_outputs_subset_and_errors(cuda):
     model.forward(ra.synthetic.make_batch(opt, 1), phase_train=True)
   w = model.export_weights()
   assert 'ctrl_cnn_w_0' in w and w['ctrl_cnn_w_0'].shape == (3, 3, 4, 8)
+
+
+@pytest.mark.parametrize('H,W,T,B,noise', [(64, 128, 5, 2, False), (64, 128, 4, 3, True)])
+def test_box_model_parity(cuda, H, W, T, B, noise):
+  """box_model.get_model (BASELINE config 5 architecture, reduced size) against the oracle."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.box_model import BoxModel
+  opt = ra.config.box_model_opt(H, W, T)
+  batch = ra.synthetic.make_batch(opt, B, seed=99)
+  weights = ra.synthetic.make_weights(opt, seed=4321, model='box')
+  cn = None
+  if noise:
+    cn = (np.random.default_rng(5).random((B, T, H, W)) * 0.3).astype(np.float32)
+    batch['canvas_noise'] = cn
+  ref = OM.box_model_forward(opt, weights, batch, canvas_noise=cn)
+  out = BoxModel(opt).load_weights(weights).forward(batch)
+  torch.cuda.synchronize()
+  for k in ('attn_box', 's_out', 'attn_ctr', 'attn_size', 'attn_top_left', 'attn_bot_right', 'ctrl_out',
+            'iou_soft_box_pairwise', 'canvas', 'attn_top_left_gt', 'attn_bot_right_gt'):
+    a, b = out[k].float().cpu().numpy(), ref[k].numpy()
+    assert a.shape == b.shape, (k, a.shape, b.shape)
+    assert rel_err(a, b) <= MODEL_TOL, (k, rel_err(a, b))
+  assert (out['match_box'].cpu().numpy() == ref['match_box'].numpy()).all()
+  for k in ('box_loss', 'conf_loss', 'loss'):
+    assert abs(float(out[k]) - float(ref[k])) <= MODEL_TOL * max(1.0, abs(float(ref[k]))), k
