@@ -214,18 +214,15 @@ def run_reference(args):
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
   import torch
-  import torch.distributed as dist
   from rec_attend_b200 import _lib, config, synthetic
   from rec_attend_b200.full_model import FullModel
 
-  world = int(os.environ.get('WORLD_SIZE', '1'))
-  rank = int(os.environ.get('RANK', '0'))
-  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  from rec_attend_b200 import dist_util
+  rank, local_rank, world = dist_util.env_world()
   if not torch.cuda.is_available():
     raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
   torch.cuda.set_device(local_rank)
-  if world > 1:
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  dist_util.init('nccl', torch.device('cuda', local_rank))
 
   cfg = config.BASELINE_CONFIGS[args.config]
   if cfg['model'] != 'full':
@@ -233,7 +230,7 @@ def run_ours(args):
   opt = config.baseline_opt(args.config)
   B = args.batch or cfg['B']
   T = cfg['T']
-  batch_np = synthetic.make_batch(opt, B, seed=1234 + args.config + 1000 * rank)
+  batch_np = synthetic.make_batch(opt, B, seed=dist_util.rank_seed(1234, args.config, rank))
   weights = synthetic.make_weights(opt)
   model = FullModel(opt).load_weights(weights)
   lib = _lib.lib()
@@ -271,8 +268,7 @@ def run_ours(args):
     return out
 
   def barrier():
-    if world > 1:
-      dist.barrier()
+    dist_util.barrier()
     torch.cuda.synchronize()
 
   def timed(fn, steps):
@@ -287,10 +283,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.ra_launch_count() - n0
-    if world > 1:
-      t = torch.tensor([ms], device='cuda')
-      dist.all_reduce(t, op=dist.ReduceOp.MAX)
-      ms = float(t.item())
+    ms = dist_util.max_over_ranks(ms, device='cuda')
     return ms, launches
 
   for _ in range(max(3, args.warmup)):
@@ -304,9 +297,8 @@ def run_ours(args):
     step_e2e()
   ms_e2e, _ = timed(step_e2e, args.steps)
 
-  masks_per_step = world * B * T
-  value = masks_per_step / (ms / args.steps / 1e3)
-  e2e_value = masks_per_step / (ms_e2e / args.steps / 1e3)
+  value = dist_util.aggregate_masks_per_sec(world, B, T, ms / args.steps)
+  e2e_value = dist_util.aggregate_masks_per_sec(world, B, T, ms_e2e / args.steps)
   h2d = sum(v.numel() * v.element_size() for v in pinned.values())
   d2h = sum(v.numel() * v.element_size() for v in host_out.values())
 
@@ -387,9 +379,7 @@ def run_ours(args):
         'cpu_baseline': cpu_baseline,
     }
     print(json.dumps(line))
-  if world > 1:
-    dist.barrier()
-    dist.destroy_process_group()
+  dist_util.finalize()
   return 0
 
 
