@@ -207,7 +207,7 @@ def run_reference(args):
                            B_sample, cfg['T'], cfg['H'], cfg['W'])},
       'e2e': {'value': val, 'unit': 'masks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
-  print(json.dumps(line))
+  emit(line)
   return 0
 
 
@@ -378,12 +378,32 @@ def run_ours(args):
         'conv_layers': layers,
         'cpu_baseline': cpu_baseline,
     }
-    print(json.dumps(line))
+    emit(line)
   dist_util.finalize()
   return 0
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+  """Everything that libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the single JSON
+  line is written to the real stdout by emit()."""
+  global _REAL_STDOUT
+  if _REAL_STDOUT is None:
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+  out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+  out.write(json.dumps(line) + '\n')
+  out.flush()
+
+
 def main():
+  _quiet_stdout()
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=5)

@@ -112,6 +112,9 @@ int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B,
 /* Diagnostics: info[16] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
  * acc_cols, stage_bytes, w_res_bytes, slots_alloc of the tile plan. */
 int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info);
+/* Diagnostics: device buffer of 8 int64 per CTA (148 CTAs max) receiving clock64() stamps of the pipeline
+ * phases of the next ra_conv3x3_umma_f32 launches; NULL switches it off. */
+int ra_debug_conv_timeline(long long *device_buf);
 int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int C2, const float *wpack, const float *scale,
                         const float *shift, int B, int Hin, int Win, int Cout, int upsample, int pool, int relu,
                         float *y, void *stream);

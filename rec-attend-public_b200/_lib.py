@@ -38,6 +38,7 @@ _SIGNATURES = {
     'ra_canvas_conv_f32': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     'ra_conv3x3_umma_plan': [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     'ra_conv3x3_umma_plan_info': [_I, _I, _I, _I, _I, _I, _P],
+    'ra_debug_conv_timeline': [_P],
     'ra_conv3x3_umma_f32': [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'ra_controller_step_f32': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P,
                                _P, _P, _P, _P],

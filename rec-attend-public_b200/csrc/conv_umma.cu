@@ -63,6 +63,7 @@ struct UmmaConvParams {
   int acc_cols;     // TMEM columns of one accumulator buffer (n_mt * cols_per_mt)
   int stage_bytes;  // bytes of one shared-memory stage (input hi + lo + filter slice)
   int vec4;         // both sources have channel counts divisible by 4
+  long long *dbg;   // optional per-CTA timeline (ra_debug_conv_timeline), 8 slots per CTA
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,7 +148,13 @@ __device__ __forceinline__ Item decode_tile(const UmmaConvParams &p, int t) {
   return it;
 }
 
+#define RA_DBG(slot)                                                                                   \
+  do {                                                                                                 \
+    if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64();                          \
+  } while (0)
+
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParams p) {
+  if (threadIdx.x == 0) RA_DBG(0);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2];
@@ -205,9 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
   const int slots_in = (p.TH + 2) * p.TWP + 2;  // slots that carry real (or zero-padding) data
+  if (threadIdx.x == 0) RA_DBG(1);  // setup done (barriers, TMEM, resident filters)
 
   if (warp >= kMmaWarp0 + kMmaWarps) {
     // =============================== producers ===============================
+    // (Splitting the producers into groups that stage different chunks concurrently was measured: it does not
+    // help — the first stage takes twice as long — and needs stages % groups == 0 for the parity waits.)
     const int ptid = tid - (kEpiThreads + 32 * kMmaWarps);
     int g = 0;  // running (tile, chunk) counter
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
@@ -298,8 +308,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (tensor core)
         mbar_arrive(smem_u32(&bar_full[s]));
+        if (g == 0 && ptid == 0) RA_DBG(2);  // first stage staged
       }
     }
+    if (ptid == 0) RA_DBG(3);  // producers done
   } else if (warp >= kMmaWarp0) {
     // =============================== MMA issuer ===============================
     // The issue of one tcgen05.mma costs ~130 cycles of scalar work in the issuing thread (descriptor
@@ -326,6 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
           const int s = g % p.stages;
           mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((g / p.stages) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (g == 0 && mw == 0) RA_DBG(4);  // first MMA can issue
           // Descriptors differ only in the start-address field (bits 0-13, 16-byte units), so the loops
           // below only add small constants.  The m-tile loop is INNERMOST: consecutive MMAs then target
           // different TMEM accumulators and pipeline, instead of forming one chain of dependent accumulations.
@@ -364,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
         }
         umma_commit(smem_u32(&bar_tfull[buf]));  // accumulators of this tile are complete
       }
+      if (mw == 0) RA_DBG(5);  // all MMAs issued
     }
   } else {
     // =============================== epilogue (warps 0-3) ===============================
@@ -376,6 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
       const int buf = t & 1;
       mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)((t >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (t == 0 && tid == 0) RA_DBG(6);  // first accumulator complete
       const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols) + lane_sel;
       const int co_base = ns * p.NPc;
       for (int cb = 0; cb < p.NPc; cb += 16) {
@@ -467,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) RA_DBG(7);  // all roles done
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
@@ -624,7 +640,16 @@ int make_plan_forced(int Cin, int Cout, int Hout, int Wout, int pool, int B, Pla
   return RA_OK;
 }
 
+long long *g_conv_dbg = nullptr;
+
 }  // namespace
+
+// Diagnostics: when set, every conv3x3_umma CTA writes 8 clock64() stamps (start, setup done, first stage
+// staged, producers done, first MMA issuable, MMAs issued, first accumulator complete, all done).
+extern "C" int ra_debug_conv_timeline(long long *device_buf) {
+  g_conv_dbg = device_buf;
+  return RA_OK;
+}
 
 // Plan query for the host-side weight packer.
 extern "C" int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc,
@@ -704,6 +729,7 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   if (items > 0x7fffffffLL) return RA_ERR_UNSUPPORTED;
   p.n_items = (int)items;
   p.vec4 = ((C1 & 3) == 0 && (C2 & 3) == 0) ? 1 : 0;
+  p.dbg = g_conv_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
