@@ -109,8 +109,8 @@ int ra_canvas_conv_f32(const float *pre, const float *canvas, const float *w, co
  * -------------------------------------------------------------------------------------- */
 int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc, int *n_split,
                          int *n_chunks);
-/* Diagnostics: info[16] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
- * acc_cols, stage_bytes, w_res_bytes, slots_alloc of the tile plan. */
+/* Diagnostics: info[18] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
+ * acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf of the tile plan. */
 int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info);
 /* Diagnostics: device buffer of 8 int64 per CTA (148 CTAs max) receiving clock64() stamps of the pipeline
  * phases of the next ra_conv3x3_umma_f32 launches; NULL switches it off. */
@@ -177,12 +177,14 @@ int ra_gaussian_filters_f32(const float *box, int B, int H, int W, int F, float 
  * (full_model.py:645-660): xs [B,H,W,Cs] step-invariant channels and canvas [B,H,W]
  * (either may be absent: Cs = 0 / canvas = NULL).  chan_map [Cs+1] int32 gives, for every
  * source channel (xs 0..Cs-1, then the canvas), its channel position in the reference's
- * concat order.  x_patch [B,F,F,Cs+1].  tmp: caller workspace of B*F*W*(Cs+1) floats.
+ * concat order.  x_patch [B,F,F,patch_cstride] with patch_cstride >= Cs+1: channels Cs+1..
+ * patch_cstride-1 are written as zeros (padding the patch to a multiple of 4 channels lets
+ * ra_conv3x3_umma_f32 read it with TMA).  tmp: caller workspace of B*F*W*(Cs+1) floats.
  * W must be a multiple of 4.
  * -------------------------------------------------------------------------------------- */
 int ra_gaussian_extract_f32(const float *xs, int Cs, const float *canvas, const int32_t *chan_map,
                             const float *box, const float *fy, const float *fx, const int32_t *band, int B, int H,
-                            int W, int F, float *tmp, float *x_patch, void *stream);
+                            int W, int F, float *tmp, float *x_patch, int patch_cstride, void *stream);
 
 /* --------------------------------------------------------------------------------------
  * Paste-back — extract_patch(., Fy^T, Fx^T, 1) as used for the attention box

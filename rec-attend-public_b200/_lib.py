@@ -43,7 +43,7 @@ _SIGNATURES = {
     'ra_controller_step_f32': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P,
                                _P, _P, _P, _P],
     'ra_gaussian_filters_f32': [_P, _I, _I, _I, _I, _P, _P, _P, _P],
-    'ra_gaussian_extract_f32': [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    'ra_gaussian_extract_f32': [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
     'ra_paste_back_f32': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P, _P],
     'ra_score_f32': [_P, _I, _P, _I, _P, _P, _I, _P, _I, _P],
     'ra_gt_box_f32': [_P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],

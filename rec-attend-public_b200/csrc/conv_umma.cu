@@ -15,10 +15,16 @@
 // M = 128 consecutive output slots per MMA (2 of every TWP are halo garbage and are dropped in
 // the epilogue), N = the CTA's share of Cout (padded to 16), K = 8 channels per instruction.
 //
-// Persistent, warp-specialised pipeline (one CTA per SM, 512 threads):
-//   warps 8-15  producers: stage the input chunk (with the hi/lo split) and the pre-packed filter
-//               slice of (tile, channel-chunk) items into a ring of shared-memory stages;
-//               fence.proxy.async + mbarrier arrive (full[s]).
+// Persistent, warp-specialised pipeline (one CTA per SM, 544 threads):
+//   warp 16     TMA: one lane issues, per (tile, channel-chunk) item, one cp.async.bulk.tensor (4-D
+//               tiled map over the NHWC activation, box = [4 channels][TW+2][TH+2][1]) per channel
+//               plane - the box lands in shared memory already in the plane layout, image borders
+//               are the TMA's out-of-bounds zero fill - plus one cp.async.bulk for the filter slice;
+//               completion is counted on raw[s] (mbarrier complete_tx).
+//   warps 8-15  converters: split the landed fp32 values IN PLACE into hi (tf32, nearest) and lo planes
+//               (for the transposed convolutions: scatter the low-resolution box into the zero-inserted
+//               tile); fence.proxy.async + mbarrier arrive (full[s]).  Layers whose channel counts are
+//               not multiples of 4 (no legal tensor map) are gathered by these warps with plain loads.
 //   warps 4-7   one lane each issues its share of the n_mt x 9 taps x (2|3) tcgen05.mma per item, tcgen05.commit ->
 //               empty[s]; after a tile's last chunk tcgen05.commit -> tmem_full[buf].
 //   warps 0-3   epilogue: tcgen05.ld (thread = TMEM lane = slot), folded BN scale/shift, ReLU,
@@ -28,7 +34,13 @@
 // Narrow layers (N <= 32) are bound by the tensor core's shared-memory reads of A, so there the
 // two filter parts are stacked along N ([B_hi; B_lo], one MMA with N' = 2N reads A_hi once) and
 // summed in the epilogue; small feature maps split N over CTAs to fill the 148 SMs.
+#include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched with cudaGetDriverEntryPoint
+#include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -38,7 +50,8 @@ constexpr int kEpiThreads = 128;   // warps 0-3
 constexpr int kMmaWarp0 = 4;       // warps 4-7: one issuing lane each, m-tiles dealt round-robin
 constexpr int kMmaWarps = 4;
 constexpr int kProdThreads = 256;  // warps 8-15
-constexpr int kThreads = kEpiThreads + 32 * kMmaWarps + kProdThreads;
+constexpr int kTmaWarp = (kEpiThreads + 32 * kMmaWarps + kProdThreads) / 32;  // warp 16
+constexpr int kThreads = kEpiThreads + 32 * kMmaWarps + kProdThreads + 32;
 constexpr int kMaxStages = 4;
 constexpr int kStageUnroll = 4;
 constexpr int kPoolLd = 20;  // floats per staged half-row of a 16-column chunk (16 + 4 padding)
@@ -60,9 +73,15 @@ struct UmmaConvParams {
   int stages;
   int w_resident;   // the CTA's whole filter image stays in shared memory for all of its tiles
   int w_res_bytes;  // bytes of that resident image (0 when streaming)
-  int acc_cols;     // TMEM columns of one accumulator buffer (n_mt * cols_per_mt)
+  int acc_cols;     // TMEM columns of one accumulator buffer (n_mt * ksplit * cols_per_mt)
+  int ksplit;       // independent accumulators per m-tile: (tap, k8) step q goes to accumulator q % ksplit
+  int nbuf;         // accumulator buffers in TMEM (2: the epilogue of tile i overlaps the MMAs of tile i+1)
   int stage_bytes;  // bytes of one shared-memory stage (input hi + lo + filter slice)
   int vec4;         // both sources have channel counts divisible by 4
+  int tma;          // inputs (and streamed filters) arrive by TMA; the producer warps only convert
+  int RW, RH;       // TMA box: columns x rows of input pixels (low resolution when up == 2)
+  int raw_plane_bytes;  // up == 2 only: bytes per channel plane of the landed low-resolution box
+  int raw_off;      // up == 2 only: offset of that landing zone inside a stage
   long long *dbg;   // optional per-CTA timeline (ra_debug_conv_timeline), 8 slots per CTA
 };
 
@@ -89,6 +108,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
+// One lane of a converged warp (always the same one for a full mask).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
@@ -99,6 +129,26 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+
+// One box of a 4-D tiled tensor map -> shared memory; completion (bytes) is counted on mbar.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3,
+                                            uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// Contiguous global -> shared bulk copy (filter slices).
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
@@ -132,6 +182,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// Asynchronous TMEM load of 16 columns (no wait): pair with tmem_wait16 before the values are used.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// tcgen05.wait::ld; the registers are in/out operands so that no use of them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_wait16(uint32_t *r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 struct Item {
   int b, y0, x0;
 };
@@ -148,18 +216,92 @@ __device__ __forceinline__ Item decode_tile(const UmmaConvParams &p, int t) {
   return it;
 }
 
+// Operands of one chunk's MMAs, all warp-uniform (see the MMA issuer warps).
+struct IssueCtx {
+  uint64_t a0_hi, a1_hi, a0_lo, a1_lo, b;  // A descriptors of the warp's two m-tiles (hi / lo parts), filter desc
+  uint32_t d0, d1;                         // TMEM columns of the two m-tiles' first accumulator
+  uint32_t idesc_n, idesc_2n;
+  uint32_t TWP, a_k8, b_k8, b_tap, b_lo, cols_mt, wrap, init_steps;
+};
+
+// The 9 taps x K8N k8-steps of one channel chunk, fully unrolled.  Step q accumulates into partial accumulator
+// q % ksplit (kept incrementally as a column offset jc that wraps at ksplit * cols_mt).  TWO: the warp owns a
+// second m-tile.  Everything outside the `if (leader)` is uniform-datapath arithmetic.
+template <int K8N, bool MERGED, bool TWO>
+__device__ __forceinline__ void issue_chunk(const IssueCtx c, const bool leader) {
+  uint32_t jc = 0;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+      for (int k8 = 0; k8 < K8N; ++k8) {
+        const int q = (ky * 3 + kx) * K8N + k8;
+        const uint64_t a_off = (uint64_t)((uint32_t)ky * c.TWP + (uint32_t)kx + (uint32_t)k8 * c.a_k8);
+        const uint64_t b_hi = c.b + (uint64_t)((uint32_t)(ky * 3 + kx) * c.b_tap + (uint32_t)k8 * c.b_k8);
+        const uint32_t flag = (uint32_t)q < c.init_steps ? 0u : 1u;
+        const uint32_t d0 = c.d0 + jc, d1 = c.d1 + jc;
+        const uint64_t a0h = c.a0_hi + a_off, a1h = c.a1_hi + a_off, a0l = c.a0_lo + a_off, a1l = c.a1_lo + a_off;
+        if (MERGED) {
+          // D[:, 0:N] += A_hi B_hi and D[:, N:2N] += A_hi B_lo in ONE instruction, then D[:, 0:N] += A_lo B_hi
+          if (leader) {
+            umma_tf32(d0, a0h, b_hi, c.idesc_2n, flag);
+            if (TWO) umma_tf32(d1, a1h, b_hi, c.idesc_2n, flag);
+            umma_tf32(d0, a0l, b_hi, c.idesc_n, 1u);
+            if (TWO) umma_tf32(d1, a1l, b_hi, c.idesc_n, 1u);
+          }
+        } else {
+          const uint64_t b_lo = b_hi + (uint64_t)c.b_lo;
+          if (leader) {
+            umma_tf32(d0, a0h, b_hi, c.idesc_n, flag);
+            if (TWO) umma_tf32(d1, a1h, b_hi, c.idesc_n, flag);
+            umma_tf32(d0, a0h, b_lo, c.idesc_n, 1u);
+            if (TWO) umma_tf32(d1, a1h, b_lo, c.idesc_n, 1u);
+            umma_tf32(d0, a0l, b_hi, c.idesc_n, 1u);
+            if (TWO) umma_tf32(d1, a1l, b_hi, c.idesc_n, 1u);
+          }
+        }
+        jc += c.cols_mt;
+        if (jc == c.wrap) jc = 0;
+      }
+    }
+  }
+}
+
+template <int K8N>
+__device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool leader, bool merged, bool two) {
+  if (merged) {
+    if (two)
+      issue_chunk<K8N, true, true>(c, leader);
+    else
+      issue_chunk<K8N, true, false>(c, leader);
+  } else {
+    if (two)
+      issue_chunk<K8N, false, true>(c, leader);
+    else
+      issue_chunk<K8N, false, false>(c, leader);
+  }
+}
+
 #define RA_DBG(slot)                                                                                   \
   do {                                                                                                 \
     if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64();                          \
   } while (0)
 
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+    conv3x3_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant__ CUtensorMap tm1,
+                        const __grid_constant__ CUtensorMap tm2) {
   if (threadIdx.x == 0) RA_DBG(0);
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2];
+  __shared__ __align__(16) float sc_s[256], sh_s[256];  // folded-BN scale / shift of this CTA's channels
+  __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_raw[kMaxStages], bar_tfull[2],
+      bar_tempty[2];
+  // TMA destinations want 128-byte alignment: round the dynamic window up (the launcher adds the slack)
+  unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler, too
   const int planes = p.KC / 4;
   const uint32_t plane_bytes = (uint32_t)p.slots_alloc * 16u;
   const int in_floats = planes * p.slots_alloc * 4;  // one of hi / lo
@@ -174,6 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), kProdThreads);
       mbar_init(smem_u32(&bar_empty[s]), kMmaWarps);
+      mbar_init(smem_u32(&bar_raw[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), kMmaWarps);
@@ -185,6 +328,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp == kTmaWarp && p.tma && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm1)) : "memory");
+    if (p.C2 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm2)) : "memory");
   }
   if (p.w_resident) {
     // the whole filter image of this CTA's channel split: loaded once, reused by every tile
@@ -210,14 +357,103 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);  // uniform register
   const int slots_in = (p.TH + 2) * p.TWP + 2;  // slots that carry real (or zero-padding) data
   if (threadIdx.x == 0) RA_DBG(1);  // setup done (barriers, TMEM, resident filters)
 
-  if (warp >= kMmaWarp0 + kMmaWarps) {
-    // =============================== producers ===============================
-    // (Splitting the producers into groups that stage different chunks concurrently was measured: it does not
-    // help — the first stage takes twice as long — and needs stages % groups == 0 for the parity waits.)
+  if (warp == kTmaWarp) {
+    // =============================== TMA issuer ===============================
+    // (warp-uniform control flow, one elected lane issues: TMA operands live in uniform registers, see the MMA warps)
+    if (p.tma) {
+      const bool leader = elect_one();
+      const uint32_t w_bytes = p.w_resident ? 0u : (uint32_t)w_chunk_floats * 4u;
+      const uint32_t tx_bytes = (uint32_t)planes * (uint32_t)(p.RW * p.RH) * 16u + w_bytes;
+      const uint32_t dst_plane = p.up == 2 ? (uint32_t)p.raw_plane_bytes : plane_bytes;
+      int g = 0;
+      for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+        const Item it = decode_tile(p, tile);
+        // first input pixel of the box (negative / past-the-end coordinates are zero-filled = SAME padding)
+        const int cx = p.up == 2 ? (it.x0 >> 1) - 1 : it.x0 - 1;
+        const int cy = p.up == 2 ? ((it.y0 - 1) >> 1) : it.y0 - 1;
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
+          const int s = g % p.stages;
+          mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((g / p.stages) & 1) ^ 1));
+          const uint32_t st = smem_u32(stage_base + (size_t)s * p.stage_bytes);
+          const uint32_t bar = smem_u32(&bar_raw[s]);
+          if (leader) mbar_arrive_expect_tx(bar, tx_bytes);
+          const uint32_t dst0 = p.up == 2 ? st + (uint32_t)p.raw_off : st;
+          for (int pl = 0; pl < planes; ++pl) {
+            const int cc = ch * p.KC + 4 * pl;
+            const uint32_t dst = dst0 + (uint32_t)pl * dst_plane;
+            // channels past Cin (padding planes) fall outside the map and come back as zeros
+            if (cc < p.C1 || p.C2 == 0) {
+              if (leader) tma_load_4d(dst, &tm1, cc, cx, cy, it.b, bar);
+            } else {
+              if (leader) tma_load_4d(dst, &tm2, cc - p.C1, cx, cy, it.b, bar);
+            }
+          }
+          if (!p.w_resident) {
+            const float *wsrc = p.wpack + ((size_t)ns * p.n_chunks + ch) * w_chunk_floats;
+            if (leader) bulk_load(st + 2u * (uint32_t)in_floats * 4u, wsrc, w_bytes, bar);
+          }
+          __syncwarp();
+          if (g == 0 && leader) RA_DBG(2);  // first stage requested
+        }
+      }
+    }
+  } else if (warp >= kMmaWarp0 + kMmaWarps && p.tma) {
+    // =============================== converters (TMA mode) ===============================
+    const int ptid = tid - (kEpiThreads + 32 * kMmaWarps);
+    const int box_slots = (p.TH + 2) * p.TWP;  // slots the taps of real output pixels can touch
+    const int n_conv = planes * box_slots;
+    int g = 0;
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+      const Item it = decode_tile(p, tile);
+      const int cx = (it.x0 >> 1) - 1, cy = (it.y0 - 1) >> 1;  // up == 2: origin of the landed box
+      for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
+        const int s = g % p.stages;
+        mbar_wait(smem_u32(&bar_raw[s]), (uint32_t)((g / p.stages) & 1));
+        unsigned char *st = stage_base + (size_t)s * p.stage_bytes;
+        float4 *hi4 = reinterpret_cast<float4 *>(st);
+        float4 *lo4 = hi4 + in_floats / 4;
+        const float4 *raw4 = reinterpret_cast<const float4 *>(st + p.raw_off);
+        const int raw_plane4 = p.raw_plane_bytes >> 4;
+        for (int base = ptid; base < n_conv; base += kProdThreads * kStageUnroll) {
+          float4 v[kStageUnroll];
+          int dst[kStageUnroll];
+#pragma unroll
+          for (int u = 0; u < kStageUnroll; ++u) {
+            const int idx = base + u * kProdThreads;
+            dst[u] = -1;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < n_conv) {
+              const int c4 = idx / box_slots, slot = idx - c4 * box_slots;  // slot fastest: conflict-free
+              dst[u] = c4 * p.slots_alloc + slot;
+              if (p.up == 1) {
+                v[u] = hi4[dst[u]];  // the box landed in place
+              } else {
+                const int r = slot / p.TWP, col = slot - r * p.TWP;
+                const int vy = it.y0 - 2 + r, vx = it.x0 - 2 + col;  // zero-inserted (virtual) pixel
+                if (((vy | vx) & 1) == 0) v[u] = raw4[c4 * raw_plane4 + ((vy >> 1) - cy) * p.RW + ((vx >> 1) - cx)];
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kStageUnroll; ++u) {
+            if (dst[u] < 0) continue;
+            const float4 h = make_float4(tf32_hi(v[u].x), tf32_hi(v[u].y), tf32_hi(v[u].z), tf32_hi(v[u].w));
+            const float4 l = make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w);
+            hi4[dst[u]] = h;
+            lo4[dst[u]] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (tensor core)
+        mbar_arrive(smem_u32(&bar_full[s]));
+      }
+    }
+    if (ptid == 0) RA_DBG(3);  // converters done
+  } else if (warp >= kMmaWarp0 + kMmaWarps) {
+    // =============================== producers (plain-load mode) ===============================
     const int ptid = tid - (kEpiThreads + 32 * kMmaWarps);
     int g = 0;  // running (tile, chunk) counter
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
@@ -313,111 +549,150 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
     }
     if (ptid == 0) RA_DBG(3);  // producers done
   } else if (warp >= kMmaWarp0) {
-    // =============================== MMA issuer ===============================
-    // The issue of one tcgen05.mma costs ~130 cycles of scalar work in the issuing thread (descriptor
-    // arithmetic + R2UR moves, see profiles/), 2-3x the tensor core's own 45-64 cycles per M=128 x K=8
-    // instruction, so kMmaWarps threads issue in parallel, each for its own m-tiles (= its own TMEM
-    // accumulators; no two threads ever accumulate into the same columns).
-    if (lane == 0) {
+    // =============================== MMA issuers ===============================
+    // tcgen05.mma takes its operands from UNIFORM registers, and uniform-datapath instructions cost ~5 cycles each
+    // when they depend on one another (tools/umma_rate.cu): issued from an `if (lane == 0)` region every MMA sits in
+    // an ELECT / R2UR.BROADCAST loop (~185 cycles), and even warp-uniform generic loops spend ~450 cycles per
+    // (tap, k8) step on loop control.  So: the whole warp runs warp-uniform code (warp index / TMEM base through
+    // shuffles, everything else from kernel parameters), only the instruction sits behind the elected lane, and
+    // the 9 x K8N steps of a chunk are straight-line code (issue_chunk<>).  Warp mw owns m-tiles mw and mw + 4.
+    {
+      const bool leader = elect_one();
       const int mw = warp - kMmaWarp0;
       const int cols_mt = p.merged ? 2 * p.NPc : p.NPc;
-      const uint32_t idesc_n =
-          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NPc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc_2n =
+      IssueCtx c;
+      c.idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NPc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      c.idesc_2n =
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * p.NPc) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t w_plane = (uint32_t)(2 * p.NPc) * 16u;  // bytes between channel planes of the filter image
-      const uint32_t plane16 = plane_bytes >> 4, wplane16 = w_plane >> 4;
+      c.TWP = (uint32_t)p.TWP;
+      c.a_k8 = 2u * (plane_bytes >> 4);                 // A start-address step of one k8 (two channel planes)
+      c.b_k8 = 2u * (w_plane >> 4);                     // same for the filter image
+      c.b_tap = (uint32_t)planes * (w_plane >> 4);      // filter image step of one tap
+      c.b_lo = (uint32_t)p.NPc;                         // rows NPc..2NPc-1 of a plane hold the lo part
+      c.cols_mt = (uint32_t)cols_mt;
+      c.wrap = (uint32_t)(p.ksplit * cols_mt);          // TMEM columns of one m-tile (all its partial accumulators)
+      const bool has0 = mw < p.n_mt, has1 = mw + kMmaWarps < p.n_mt;
+      const bool merged = p.merged != 0;
+      const uint32_t a_mt0 = (uint32_t)(mw * 128), a_mt1 = (uint32_t)((mw + kMmaWarps) * 128);
       const int k8n = p.KC / 8;
       int g = 0, t = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
-        const int buf = t & 1;
-        mbar_wait(smem_u32(&bar_tempty[buf]), (uint32_t)(((t >> 1) & 1) ^ 1));
+        const int buf = p.nbuf == 2 ? (t & 1) : 0;
+        const uint32_t use = p.nbuf == 2 ? (uint32_t)(t >> 1) : (uint32_t)t;
+        mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
+        c.d0 = acc + (uint32_t)mw * c.wrap;
+        c.d1 = acc + (uint32_t)(mw + kMmaWarps) * c.wrap;
         for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
           const int s = g % p.stages;
           mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((g / p.stages) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (g == 0 && mw == 0) RA_DBG(4);  // first MMA can issue
-          // Descriptors differ only in the start-address field (bits 0-13, 16-byte units), so the loops
-          // below only add small constants.  The m-tile loop is INNERMOST: consecutive MMAs then target
-          // different TMEM accumulators and pipeline, instead of forming one chain of dependent accumulations.
+          if (g == 0 && mw == 0 && leader) RA_DBG(4);  // first MMA can issue
+          // Descriptors differ only in the start-address field (bits 0-13, 16-byte units): a tap, a k8 step, an
+          // m-tile are small additive constants.
           const uint32_t a_hi = smem_u32(stage_base + (size_t)s * p.stage_bytes);
-          const uint64_t dA_hi = make_desc(a_hi, plane_bytes, 128);
-          const uint64_t dA_lo = dA_hi + (uint64_t)(((uint32_t)in_floats * 4u) >> 4);
+          const uint64_t dA = make_desc(a_hi, plane_bytes, 128);
+          const uint64_t lo_off = (uint64_t)(((uint32_t)in_floats * 4u) >> 4);
+          c.a0_hi = dA + (uint64_t)a_mt0;
+          c.a1_hi = dA + (uint64_t)a_mt1;
+          c.a0_lo = c.a0_hi + lo_off;
+          c.a1_lo = c.a1_hi + lo_off;
           const uint32_t w_addr = p.w_resident ? smem_u32(smem_raw) + (uint32_t)ch * (uint32_t)w_chunk_floats * 4u
                                                : a_hi + 2u * (uint32_t)in_floats * 4u;
-          const uint64_t dB = make_desc(w_addr, w_plane, 128);
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a_t = (uint32_t)((tap / 3) * p.TWP + (tap % 3));
-            for (int k8 = 0; k8 < k8n; ++k8) {
-              const uint64_t ao_hi = dA_hi + (uint64_t)(a_t + (uint32_t)(2 * k8) * plane16);
-              const uint64_t ao_lo = dA_lo + (uint64_t)(a_t + (uint32_t)(2 * k8) * plane16);
-              const uint64_t db_hi = dB + (uint64_t)((uint32_t)(tap * planes + 2 * k8) * wplane16);
-              const uint32_t acc_flag = (ch == 0 && tap == 0 && k8 == 0) ? 0u : 1u;
-              if (p.merged) {
-                // D[:, 0:N] += A_hi B_hi and D[:, N:2N] += A_hi B_lo in ONE instruction ...
-                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
-                  umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_hi + (uint64_t)(mt * 128), db_hi, idesc_2n, acc_flag);
-                // ... then D[:, 0:N] += A_lo B_hi
-                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
-                  umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_lo + (uint64_t)(mt * 128), db_hi, idesc_n, 1u);
-              } else {
-                const uint64_t db_lo = db_hi + (uint64_t)p.NPc;  // rows NPc..2NPc-1 of the plane
-                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
-                  umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_hi + (uint64_t)(mt * 128), db_hi, idesc_n, acc_flag);
-                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
-                  umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_hi + (uint64_t)(mt * 128), db_lo, idesc_n, 1u);
-                for (int mt = mw; mt < p.n_mt; mt += kMmaWarps)
-                  umma_tf32(acc + (uint32_t)(mt * cols_mt), ao_lo + (uint64_t)(mt * 128), db_hi, idesc_n, 1u);
-              }
-            }
+          c.b = make_desc(w_addr, w_plane, 128);
+          c.init_steps = ch == 0 ? (uint32_t)p.ksplit : 0u;  // the first MMA into each accumulator overwrites
+          if (has0) {
+            if (k8n == 1)
+              issue_chunk_k8<1>(c, leader, merged, has1);
+            else if (k8n == 2)
+              issue_chunk_k8<2>(c, leader, merged, has1);
+            else
+              issue_chunk_k8<4>(c, leader, merged, has1);
           }
-          umma_commit(smem_u32(&bar_empty[s]));  // the stage may be refilled once these MMAs have read it
+          if (leader) umma_commit(smem_u32(&bar_empty[s]));  // the stage may be refilled once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(smem_u32(&bar_tfull[buf]));  // accumulators of this tile are complete
+        if (leader) umma_commit(smem_u32(&bar_tfull[buf]));  // accumulators of this tile are complete
+        __syncwarp();
       }
-      if (mw == 0) RA_DBG(5);  // all MMAs issued
+      if (mw == 0 && leader) RA_DBG(5);  // all MMAs issued
     }
   } else {
     // =============================== epilogue (warps 0-3) ===============================
     const int cols_mt = p.merged ? 2 * p.NPc : p.NPc;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;  // warp w may touch TMEM lanes [32w, 32w+32)
     const int slots_out = p.TH * p.TWP;
+    const int chain_cols = p.ksplit * cols_mt;  // TMEM columns of one m-tile
+    const int co_base = ns * p.NPc;
+    // folded-BN scale / shift of this CTA's channels: once into shared memory (padded channels: 0)
+    for (int i = tid; i < p.NPc; i += kEpiThreads) {
+      const int co = co_base + i;
+      sc_s[i] = co < p.Cout ? __ldg(p.scale + co) : 0.f;
+      sh_s[i] = co < p.Cout ? __ldg(p.shift + co) : 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+
+    // v[16] <- columns cb..cb+15 of m-tile mt: sum of the merged halves and of the K-split partial accumulators;
+    // the loads of one (hi half, lo half) pair are in flight together.  Then BN scale/shift (+ ReLU).
+    auto load16 = [&](uint32_t acc, int mt, int cb, float *v) {
+      uint32_t r0[16], r1[16];
+      const uint32_t base = acc + (uint32_t)(mt * chain_cols + cb);
+      tmem_ld16_issue(base, r0);
+      if (p.merged) tmem_ld16_issue(base + (uint32_t)p.NPc, r1);
+      tmem_wait16(r0);
+      if (p.merged) {
+        tmem_wait16(r1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
+      }
+      for (int ks = 1; ks < p.ksplit; ++ks) {  // partial accumulators of the K split
+        tmem_ld16_issue(base + (uint32_t)(ks * cols_mt), r0);
+        if (p.merged) tmem_ld16_issue(base + (uint32_t)(ks * cols_mt + p.NPc), r1);
+        tmem_wait16(r0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r0[j]);
+        if (p.merged) {
+          tmem_wait16(r1);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 sc = *reinterpret_cast<const float4 *>(sc_s + cb + j);
+        const float4 sh = *reinterpret_cast<const float4 *>(sh_s + cb + j);
+        v[j] = fmaf(v[j], sc.x, sh.x);
+        v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+        v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+        v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+    };
+
     int t = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
       const Item it = decode_tile(p, tile);
-      const int buf = t & 1;
-      mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)((t >> 1) & 1));
+      const int buf = p.nbuf == 2 ? (t & 1) : 0;
+      const uint32_t use = p.nbuf == 2 ? (uint32_t)(t >> 1) : (uint32_t)t;
+      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (t == 0 && tid == 0) RA_DBG(6);  // first accumulator complete
       const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols) + lane_sel;
-      const int co_base = ns * p.NPc;
-      for (int cb = 0; cb < p.NPc; cb += 16) {
-        if (co_base + cb >= p.Cout) break;  // padded channel chunks
-        float sc[16], sh[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = co_base + cb + j;
-          sc[j] = co < p.Cout ? __ldg(p.scale + co) : 0.f;
-          sh[j] = co < p.Cout ? __ldg(p.shift + co) : 0.f;
-        }
-        for (int mt = 0; mt < p.n_mt; ++mt) {
-          const int s = mt * 128 + tid;
-          float v[16];
-          tmem_ld16(acc + (uint32_t)(mt * cols_mt + cb), v);
-          if (p.merged) {
-            float v2[16];
-            tmem_ld16(acc + (uint32_t)(mt * cols_mt + p.NPc + cb), v2);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += v2[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v[j] = fmaf(v[j], sc[j], sh[j]);
-            if (p.relu) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.pool == 2) {
+      const int cb_end = (p.Cout - co_base) < p.NPc ? (p.Cout - co_base) : p.NPc;  // real channels of this split
+      if (p.pool == 2) {
+        for (int cb = 0; cb < cb_end; cb += 16) {
+          for (int mt = 0; mt < p.n_mt; ++mt) {
+            const int s = mt * 128 + tid;
+            float v[16];
+            load16(acc, mt, cb, v);
             // horizontal max with the next slot (same image row: TW, x0 are even so pairs do not straddle)
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_down_sync(0xffffffffu, v[j], 1));
@@ -427,25 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-          } else {
-            const int oy_l = s / p.TWP, ox_l = s - oy_l * p.TWP;
-            const int oy = it.y0 + oy_l, ox = it.x0 + ox_l;
-            if (s < slots_out && ox_l < p.TW && oy < p.Hout && ox < p.Wout) {
-              float *dst = p.y + (((size_t)it.b * p.Hout + oy) * p.Wout + ox) * p.Cout + co_base + cb;
-              if ((p.Cout & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                  if (co_base + cb + j < p.Cout)
-                    *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (co_base + cb + j < p.Cout) dst[j] = v[j];
-              }
-            }
           }
-        }
-        if (p.pool == 2) {
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
           // vertical max + store of this 16-channel chunk: pooled pixel (py, px) <- staged half-rows of
           // slots (2py)*TWP+2px and +TWP
@@ -454,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
           for (int idx = tid; idx < ph * pw * 4; idx += kEpiThreads) {
             const int c4 = idx & 3;
             const int pix = idx >> 2;
-            const int px = pix % pw, py = pix / pw;
+            const int py = pix / pw, px = pix - py * pw;
             const int gy = (it.y0 >> 1) + py, gx = (it.x0 >> 1) + px;
             const int co = co_base + cb + c4 * 4;
             if (gy >= Ho || gx >= Wo || co >= p.Cout) continue;
@@ -473,6 +730,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_kernel(UmmaConvParam
             }
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        }
+      } else {
+        for (int mt = 0; mt < p.n_mt; ++mt) {
+          const int s = mt * 128 + tid;
+          const int oy_l = s / p.TWP, ox_l = s - oy_l * p.TWP;
+          const int oy = it.y0 + oy_l, ox = it.x0 + ox_l;
+          const bool valid = s < slots_out && ox_l < p.TW && oy < p.Hout && ox < p.Wout;
+          float *dst_px = p.y + (((size_t)it.b * p.Hout + oy) * p.Wout + ox) * p.Cout + co_base;
+          for (int cb = 0; cb < cb_end; cb += 16) {
+            float v[16];
+            load16(acc, mt, cb, v);  // (warp-collective: every lane takes part, valid or not)
+            if (!valid) continue;
+            float *dst = dst_px + cb;
+            if ((p.Cout & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                if (co_base + cb + j < p.Cout)
+                  *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (co_base + cb + j < p.Cout) dst[j] = v[j];
+            }
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -493,13 +774,14 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // Tile plan shared by the launcher and the weight packer (through ra_conv3x3_umma_plan).
 struct Plan {
   int KC, NP, NPc, n_split, merged, TH, TW, TWP, n_mt, slots_alloc, n_chunks, stages, acc_cols, stage_bytes;
+  int ksplit, nbuf;
   int w_resident, w_res_bytes, grid;
   size_t smem_bytes;
 };
 
-// Cost model (cycles per CTA), calibrated with tools/umma_rate.cu and the ncu captures under profiles/:
-// a tcgen05.mma with M=128, K=8 costs max(64, N/2) cycles whatever N is (the A operand streams from shared
-// memory at 64 B/cycle), and the 224 producer threads stage about 20 B/cycle (latency-bound L2 loads).
+// Cost model (cycles per CTA), calibrated with tools/umma_rate.cu, tools/conv_timeline.py and the ncu captures
+// under profiles/: a tcgen05.mma with M=128, K=8 occupies the tensor core for max(48, N/2) cycles (the A operand
+// streams from shared memory) and one issuing warp sustains an instruction every 50-75 cycles.
 int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) {
   const int NP = round_up(Cout, 16);
   if (NP > 256) return RA_ERR_UNSUPPORTED;
@@ -507,7 +789,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
   if (pool == 2 && (Hout & 1)) return RA_ERR_UNSUPPORTED;
   if (B < 1) B = 1;
   const size_t smem_cap = 200 * 1024;
-  const double kProdBytesPerCycle = 20.0;
+  const double kProdBytesPerCycle = 40.0;  // TMA + in-place hi/lo split by the converter warps
   double best = 1e30;
   Plan bp{};
   bool found = false;
@@ -518,12 +800,12 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
     // merged: [B_hi; B_lo] stacked along N, one MMA (N' = 2 NPc <= 256) reads A_hi once; 2 instead of 3 MMAs
     if (merged && 2 * NPc > 256) continue;
     const int cols_mt = merged ? 2 * NPc : NPc;
-    const int mt_max = 256 / cols_mt;  // two accumulator buffers in 512 TMEM columns
+    const int mt_max = 512 / cols_mt;  // all 512 TMEM columns, single accumulator buffer
     if (mt_max < 1) continue;
+    const double n_mma = merged ? 2.0 : 3.0;  // instructions per (tap, k8) step and m-tile, one dependent chain
     // tensor-core time of one M=128 x K=8 instruction: max(~48, N/2) cycles (tools/umma_rate.cu)
     const double hw_n = NPc / 2 > 48 ? NPc / 2 : 48.0, hw_2n = NPc > 48 ? (double)NPc : 48.0;
     const double hw_cycles = merged ? hw_2n + hw_n : 3.0 * hw_n;
-    const double issue_cycles = (merged ? 2.0 : 3.0) * 130.0;  // scalar cost of issuing, per issuing thread
     for (int KC = 8; KC <= 32; KC *= 2) {
       if (KC > 8 && KC / 2 >= Cin) continue;
       const int planes = KC / 4;
@@ -535,8 +817,8 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
         const int TWP = TW + 2;
         for (int TH = (pool == 2 ? 2 : 1); TH <= Hout; TH += (pool == 2 ? 2 : 1)) {
           const int n_mt = (TH * TWP + 127) / 128;
-          if (n_mt > mt_max) break;
-          const int slots_alloc = n_mt * 128 + 2 * TWP + 2;
+          if (n_mt > mt_max || n_mt > 2 * kMmaWarps) break;  // each MMA warp owns at most two m-tiles
+          const int slots_alloc = round_up(n_mt * 128 + 2 * TWP + 2, 8);  // planes stay 128-byte aligned (TMA)
           const size_t in_bytes = (size_t)2 * planes * slots_alloc * 16;
           const size_t pool_bytes = pool == 2 ? (size_t)(n_mt * 64) * kPoolLd * 4 : 0;
           const int tiles = ((Wout + TW - 1) / TW) * ((Hout + TH - 1) / TH) * B;
@@ -544,20 +826,32 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
           if (grid_t > tiles) grid_t = tiles;
           if (grid_t < 1) continue;
           const int tiles_per_cta = (tiles + grid_t - 1) / grid_t;
+          for (int nbuf = 2; nbuf >= 1; --nbuf) {
+          if (n_mt * cols_mt * nbuf > 512) continue;
+          // K split (partial accumulators per m-tile, summed by the epilogue): measured useless - back-to-back MMAs
+          // into one accumulator already pipeline at the tensor core's rate - so the planner keeps 1; the kernel
+          // path stays (RA_UMMA_KSPLIT with a forced plan) as the experiment that shows it.
+          const int ksplit = 1;
           for (int resident = 1; resident >= 0; --resident) {
             const size_t stage_bytes = in_bytes + (resident ? 0 : w_chunk_bytes);
             const size_t fixed = pool_bytes + (resident ? w_total : 0);
             if (fixed + 2 * stage_bytes > smem_cap) continue;
             int st = (int)((smem_cap - fixed) / stage_bytes);
             if (st > kMaxStages) st = kMaxStages;
-            const double per_tap = (double)9 * (KC / 8) * n_chunks;
-            const double mma_hw = n_mt * per_tap * hw_cycles;
-            const double mma_issue = ((n_mt + kMmaWarps - 1) / kMmaWarps) * per_tap * issue_cycles;
-            const double mma_item = mma_hw > mma_issue ? mma_hw : mma_issue;
+            const double per_tap = (double)9 * (KC / 8) * n_chunks;  // (tap, k8) steps per tile
+            const double step_tc = n_mt * hw_cycles;  // tensor-core occupancy of one step
+            // issue: ~75 cycles per instruction for a warp that owns one m-tile, ~50 with two (tools/conv_timeline.py)
+            const int mt_warp = (n_mt + kMmaWarps - 1) / kMmaWarps;
+            const double step_issue = (mt_warp == 1 ? 75.0 : 100.0) * n_mma;
+            const double step = step_tc > step_issue ? step_tc : step_issue;
+            const double mma_item = per_tap * step;
             const double prod_item = (double)n_chunks * stage_bytes / kProdBytesPerCycle;
-            const double epi_item = 400.0 + 60.0 * n_mt * (NPc / 16);
+            const double epi_item = 500.0 + n_mt * (NPc / 16) * (merged ? 550.0 : 450.0);  // measured: slow (TMEM latency)
             double item = mma_item > prod_item ? mma_item : prod_item;
-            if (epi_item > item) item = epi_item;
+            if (nbuf == 1)
+              item += epi_item;  // single accumulator buffer: the next tile's MMAs wait for the epilogue
+            else if (epi_item > item)
+              item = epi_item;
             item += 500.0 * n_chunks + 1500.0;  // barrier round trips per chunk / per tile
             // pipeline fill: the first stage of every CTA and the last epilogue are exposed
             const double cost = tiles_per_cta * item + prod_item / n_chunks + epi_item +
@@ -576,7 +870,9 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
               bp.n_mt = n_mt;
               bp.slots_alloc = slots_alloc;
               bp.n_chunks = n_chunks;
-              bp.acc_cols = n_mt * cols_mt;
+              bp.acc_cols = n_mt * ksplit * cols_mt;
+              bp.ksplit = ksplit;
+              bp.nbuf = nbuf;
               bp.stage_bytes = (int)stage_bytes;
               bp.stages = st;
               bp.w_resident = resident;
@@ -584,6 +880,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
               bp.grid = grid_t * n_split;
               bp.smem_bytes = fixed + (size_t)st * stage_bytes;
             }
+          }
           }
         }
       }
@@ -614,10 +911,14 @@ int make_plan_forced(int Cin, int Cout, int Hout, int Wout, int pool, int B, Pla
   bp.TW = TW;
   bp.TWP = TW + 2;
   bp.n_mt = (TH * bp.TWP + 127) / 128;
-  if (bp.n_mt * cols_mt > 256) return RA_ERR_UNSUPPORTED;
-  bp.slots_alloc = bp.n_mt * 128 + 2 * bp.TWP + 2;
+  if (bp.n_mt * cols_mt > 512 || bp.n_mt > 2 * kMmaWarps) return RA_ERR_UNSUPPORTED;
+  bp.nbuf = bp.n_mt * cols_mt * 2 <= 512 ? 2 : 1;
+  bp.ksplit = 512 / (bp.nbuf * bp.n_mt * cols_mt);
+  if (bp.ksplit > (8 + bp.n_mt - 1) / bp.n_mt) bp.ksplit = (8 + bp.n_mt - 1) / bp.n_mt;
+  if (const char *ks = getenv("RA_UMMA_KSPLIT")) bp.ksplit = atoi(ks) < 1 ? 1 : (atoi(ks) < bp.ksplit ? atoi(ks) : bp.ksplit);
+  bp.slots_alloc = round_up(bp.n_mt * 128 + 2 * bp.TWP + 2, 8);
   bp.n_chunks = (Cin + KC - 1) / KC;
-  bp.acc_cols = bp.n_mt * cols_mt;
+  bp.acc_cols = bp.n_mt * bp.ksplit * cols_mt;
   const int planes = KC / 4;
   const size_t in_bytes = (size_t)2 * planes * bp.slots_alloc * 16;
   const size_t w_chunk = (size_t)9 * planes * 2 * bp.NPc * 16;
@@ -642,6 +943,71 @@ int make_plan_forced(int Cin, int Cout, int Hout, int Wout, int pool, int B, Pla
 
 long long *g_conv_dbg = nullptr;
 
+// ---- tensor maps -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void *ptr;
+  int C, W, H, B, RW, RH;
+  bool operator==(const MapKey &o) const {
+    return ptr == o.ptr && C == o.C && W == o.W && H == o.H && B == o.B && RW == o.RW && RH == o.RH;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey &k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr);
+    const int v[6] = {k.C, k.W, k.H, k.B, k.RW, k.RH};
+    for (int i = 0; i < 6; ++i) h = h * 0x9E3779B97F4A7C15ull + (uint64_t)v[i];
+    return (size_t)h;
+  }
+};
+
+// 4-D tiled map over an NHWC fp32 activation: dims (C, W, H, B) innermost first, box = 4 channels x RW x RH x 1
+// pixel block = one channel plane of the shared-memory tile.  No swizzle, zero fill out of bounds.
+bool activation_map(const float *x, int C, int W, int H, int B, int RW, int RH, CUtensorMap *out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{x, C, W, H, B, RW, RH};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (enc == nullptr) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  const cuuint32_t box[4] = {4, (cuuint32_t)RW, (cuuint32_t)RH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, tm);
+  *out = tm;
+  return true;
+}
+
 }  // namespace
 
 // Diagnostics: when set, every conv3x3_umma CTA writes 8 clock64() stamps (start, setup done, first stage
@@ -664,17 +1030,17 @@ extern "C" int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int p
   return RA_OK;
 }
 
-// Full plan dump (diagnostics / DESIGN.md tables): info[16] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages,
-// merged, w_resident, grid, smem_bytes, acc_cols, stage_bytes, w_res_bytes, slots_alloc.
+// Full plan dump (diagnostics / DESIGN.md tables): info[18] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages,
+// merged, w_resident, grid, smem_bytes, acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf.
 extern "C" int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info) {
   Plan pl;
   const int rc = make_plan_forced(Cin, Cout, Hout, Wout, pool, B, &pl);
   if (rc != RA_OK) return rc;
   if (!info) return RA_ERR_INVALID_ARG;
-  const int v[16] = {pl.KC, pl.NPc, pl.n_split, pl.n_chunks, pl.TH, pl.TW, pl.n_mt, pl.stages, pl.merged,
+  const int v[18] = {pl.KC, pl.NPc, pl.n_split, pl.n_chunks, pl.TH, pl.TW, pl.n_mt, pl.stages, pl.merged,
                      pl.w_resident, pl.grid, (int)pl.smem_bytes, pl.acc_cols, pl.stage_bytes, pl.w_res_bytes,
-                     pl.slots_alloc};
-  for (int i = 0; i < 16; ++i) info[i] = v[i];
+                     pl.slots_alloc, pl.ksplit, pl.nbuf};
+  for (int i = 0; i < 18; ++i) info[i] = v[i];
   return RA_OK;
 }
 
@@ -722,6 +1088,8 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   p.w_resident = pl.w_resident;
   p.w_res_bytes = pl.w_res_bytes;
   p.acc_cols = pl.acc_cols;
+  p.ksplit = pl.ksplit;
+  p.nbuf = pl.nbuf;
   p.stage_bytes = pl.stage_bytes;
   p.tiles_x = (p.Wout + p.TW - 1) / p.TW;
   p.tiles_y = (p.Hout + p.TH - 1) / p.TH;
@@ -730,15 +1098,55 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   p.n_items = (int)items;
   p.vec4 = ((C1 & 3) == 0 && (C2 & 3) == 0) ? 1 : 0;
   p.dbg = g_conv_dbg;
+  // ---- TMA feed: needs channel counts that are multiples of 4 (16-byte global strides) and boxes <= 256
+  const bool no_tma = getenv("RA_CONV_NO_TMA") != nullptr;  // diagnostics: plain-load producers everywhere
+  constexpr size_t kSmemMax = 224 * 1024;  // + ~2.3 KB static shared memory <= 227 KB
+  p.tma = 0;
+  p.RW = upsample == 2 ? p.TW / 2 + 1 : p.TWP;
+  p.RH = upsample == 2 ? p.TH / 2 + 2 : p.TH + 2;
+  p.raw_plane_bytes = 0;
+  p.raw_off = 0;
+  size_t smem_bytes = pl.smem_bytes;
+  CUtensorMap tm1, tm2;
+  memset(&tm1, 0, sizeof(tm1));
+  memset(&tm2, 0, sizeof(tm2));
+  if (!no_tma && p.vec4 && p.RW <= 256 && p.RH <= 256 && (reinterpret_cast<uintptr_t>(x1) & 15) == 0 &&
+      (C2 == 0 || (reinterpret_cast<uintptr_t>(x2) & 15) == 0) && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0) {
+    bool ok = true;
+    int stages = pl.stages, stage_bytes = pl.stage_bytes;
+    if (upsample == 2) {
+      // landing zone of the low-resolution box, appended to every stage; drop stages if it does not fit
+      p.raw_plane_bytes = round_up(p.RW * p.RH * 16, 128);
+      p.raw_off = pl.stage_bytes;
+      stage_bytes = pl.stage_bytes + (p.KC / 4) * p.raw_plane_bytes;
+      const size_t fixed = pl.smem_bytes - (size_t)pl.stages * pl.stage_bytes;
+      while (stages > 2 && fixed + (size_t)stages * stage_bytes > kSmemMax - 128) --stages;
+      ok = fixed + (size_t)stages * stage_bytes <= kSmemMax - 128;
+      if (ok) smem_bytes = fixed + (size_t)stages * stage_bytes;
+    }
+    ok = ok && activation_map(x1, C1, Win, Hin, B, p.RW, p.RH, &tm1);
+    ok = ok && (C2 == 0 || activation_map(x2, C2, Win, Hin, B, p.RW, p.RH, &tm2));
+    if (ok) {
+      p.tma = 1;
+      p.stages = stages;
+      p.stage_bytes = stage_bytes;
+    } else {
+      p.raw_plane_bytes = 0;
+      p.raw_off = 0;
+      smem_bytes = pl.smem_bytes;
+    }
+  }
+  smem_bytes += 128;  // alignment slack (the kernel rounds its window up to 128 bytes)
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    cudaError_t e =
+        cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
     if (e != cudaSuccess) {
       ra::set_last_error("cudaFuncSetAttribute(conv3x3_umma_kernel)", e);
       return RA_ERR_CUDA;
     }
     attr_set = true;
   }
-  conv3x3_umma_kernel<<<pl.grid, kThreads, pl.smem_bytes, ra::as_stream(stream)>>>(p);
+  conv3x3_umma_kernel<<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
   return ra::finish_launch("conv3x3_umma_kernel");
 }

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
                                                            const float *__restrict__ tmp_c,
                                                            const int *__restrict__ chan_map,
                                                            const float *__restrict__ fx, const int *__restrict__ band,
-                                                           const float *__restrict__ box, int W, int F,
+                                                           const float *__restrict__ box, int W, int F, int Dp,
                                                            float *__restrict__ patch) {
   extern __shared__ float slab[];  // [W][D]
   const int i = blockIdx.x, b = blockIdx.y;
@@ -157,8 +157,14 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
   const float gamma = box[(size_t)b * RA_BOX_STRIDE + RA_BOX_GAMMA_ATTN];
   const int *bd = band + ((size_t)b * 2 + 1) * F * 2;
   const float *fxb = fx + (size_t)b * F * W;
-  for (int idx = threadIdx.x; idx < F * D; idx += blockDim.x) {
-    const int j = idx / D, d = idx - j * D;
+  // Dp >= D is the channel stride of the patch; channels D..Dp-1 are written as zeros (padding to a multiple of
+  // 4 channels lets the tensor-core convolutions read the patch with TMA)
+  for (int idx = threadIdx.x; idx < F * Dp; idx += blockDim.x) {
+    const int j = idx / Dp, d = idx - j * Dp;
+    if (d >= D) {
+      patch[(((size_t)b * F + i) * F + j) * Dp + d] = 0.f;
+      continue;
+    }
     const int lo = bd[j * 2], hi = bd[j * 2 + 1];
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     const float *fj = fxb + (size_t)j * W;
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
       a3 = fmaf(slab[(x + 3) * D + d], f3, a3);
     }
     for (; x <= hi; ++x) a0 = fmaf(slab[x * D + d], __ldg(fj + x), a0);
-    patch[(((size_t)b * F + i) * F + j) * D + d] = gamma * ((a0 + a1) + (a2 + a3));  // full_model.py:788
+    patch[(((size_t)b * F + i) * F + j) * Dp + d] = gamma * ((a0 + a1) + (a2 + a3));  // full_model.py:788
   }
 }
 
@@ -288,9 +294,10 @@ extern "C" int ra_gaussian_filters_f32(const float *box, int B, int H, int W, in
 
 extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *canvas, const int32_t *chan_map,
                                        const float *box, const float *fy, const float *fx, const int32_t *band, int B,
-                                       int H, int W, int F, float *tmp, float *x_patch, void *stream) {
+                                       int H, int W, int F, float *tmp, float *x_patch, int patch_cstride,
+                                       void *stream) {
   if (!chan_map || !box || !fy || !fx || !band || !tmp || !x_patch || B < 0 || Cs < 0 || (Cs > 0 && !xs) ||
-      (Cs == 0 && !canvas))
+      (Cs == 0 && !canvas) || patch_cstride < Cs + (canvas != nullptr ? 1 : 0))
     return RA_ERR_INVALID_ARG;
   if (F > kMaxF || (W % 4) != 0) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
@@ -327,7 +334,7 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
   }
   extract_cols_kernel<<<dim3(F, B), 256, smem_cols, s>>>(Cs > 0 ? tmp_s : nullptr, Cs,
                                                          canvas != nullptr ? tmp_c : nullptr, chan_map, fx, band, box,
-                                                         W, F, x_patch);
+                                                         W, F, patch_cstride, x_patch);
   return ra::finish_launch("extract_cols_kernel");
 }
 

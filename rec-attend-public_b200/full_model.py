@@ -41,6 +41,15 @@ def _deconv_to_conv(w):
   return np.ascontiguousarray(w[::-1, ::-1].transpose(0, 1, 3, 2)).astype(np.float32)
 
 
+def _pad_cin(w_hwio, cin):
+  """Zero rows for padded input channels (appended after the real ones)."""
+  if w_hwio.shape[2] == cin:
+    return w_hwio
+  out = np.zeros(w_hwio.shape[:2] + (cin, w_hwio.shape[3]), np.float32)
+  out[:, :, :w_hwio.shape[2]] = w_hwio
+  return out
+
+
 class _ModelBase(object):
 
   def __init__(self, opt, device=None):
@@ -294,6 +303,9 @@ class FullModel(_ModelBase):
     self.use_skip = bool(o.get('add_skip_conn', True))
     self.disable_overwrite = bool(o.get('disable_overwrite', True))  # full_model.py:117-120
     self.min_padding = float(o['padding'] + 4)  # full_model.py:567
+    # the glimpse is stored with its channel count padded to a multiple of 4 (zero channels, zero filter rows):
+    # 16-byte pixel strides are what a TMA tensor map over it needs (csrc/conv_umma.cu)
+    self.Dp = (self.D + 3) // 4 * 4
 
   def load_weights(self, weights):
     T = self.T
@@ -301,14 +313,19 @@ class FullModel(_ModelBase):
     w = self._load_controller(weights)
     sz = self.F
     for i in range(len(self.attn_pool)):
-      w['acnn_w%d' % i] = self._pack(weights['attn_cnn_w_%d' % i], sz, sz, self.attn_pool[i])
+      wi = np.asarray(weights['attn_cnn_w_%d' % i], np.float32)
+      if i == 0:
+        wi = _pad_cin(wi, self.Dp)
+      w['acnn_w%d' % i] = self._pack(wi, sz, sz, self.attn_pool[i])
       sz //= self.attn_pool[i]
       sc, sh = _fold_bn(weights, 'attn_cnn', i, T, np.asarray(weights['attn_cnn_b_%d' % i], np.float32))
       w['acnn_scale%d' % i], w['acnn_shift%d' % i] = self._dev(sc), self._dev(sh)
     for i in range(len(self.dcnn_pool)):
       sz *= self.dcnn_pool[i]
-      w['adcnn_w%d' % i] = self._pack(_deconv_to_conv(np.asarray(weights['attn_dcnn_w_%d' % i], np.float32)), sz, sz,
-                                      1)
+      wi = _deconv_to_conv(np.asarray(weights['attn_dcnn_w_%d' % i], np.float32))
+      if i == len(self.attn_pool) and self.use_skip and self.skip_ch[i] > 0:
+        wi = _pad_cin(wi, wi.shape[2] - self.D + self.Dp)  # its skip input is the padded glimpse
+      w['adcnn_w%d' % i] = self._pack(wi, sz, sz, 1)
       sc, sh = _fold_bn(weights, 'attn_dcnn', i, T, np.asarray(weights['attn_dcnn_b_%d' % i], np.float32))
       w['adcnn_scale%d' % i], w['adcnn_shift%d' % i] = self._dev(sc), self._dev(sh)
     self.w = w
@@ -321,7 +338,7 @@ class FullModel(_ModelBase):
     bufs = {}
     self._alloc_controller(B, bufs)
     bufs['extract_tmp'] = torch.empty((B * F * W * self.D,), device=dev, dtype=f32)
-    bufs['x_patch_all'] = torch.empty((T, B, F, F, self.D), device=dev, dtype=f32)
+    bufs['x_patch_all'] = torch.empty((T, B, F, F, self.Dp), device=dev, dtype=f32)
     bufs['y_patch_all'] = torch.empty((T, B, F, F, 1), device=dev, dtype=f32)
     s = F
     bufs['acnn'] = []
@@ -404,7 +421,7 @@ class FullModel(_ModelBase):
     self._controller_outputs(bufs, out)
     out['y_out'] = bufs['y_out']
     if want_all:
-      out['x_patch'] = bufs['x_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
+      out['x_patch'] = bufs['x_patch_all'][..., :self.D].permute(1, 0, 2, 3, 4).contiguous()
       out['y_out_patch'] = bufs['y_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
     if with_loss:
       self._loss(bufs, st['y_gt'], st['s_gt'], out, want_gt_box=want_all)

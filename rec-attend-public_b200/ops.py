@@ -111,10 +111,10 @@ def umma_plan(Cin, Cout, Hout, Wout, pool, B):
 
 def umma_plan_info(Cin, Cout, Hout, Wout, pool, B):
   """The full tile plan of the tcgen05 conv kernel as a dict (diagnostics)."""
-  info = (_c.c_int * 16)()
+  info = (_c.c_int * 18)()
   _lib.call('ra_conv3x3_umma_plan_info', Cin, Cout, Hout, Wout, pool, B, info)
   keys = ['KC', 'NPc', 'n_split', 'n_chunks', 'TH', 'TW', 'n_mt', 'stages', 'merged', 'w_resident', 'grid',
-          'smem_bytes', 'acc_cols', 'stage_bytes', 'w_res_bytes', 'slots_alloc']
+          'smem_bytes', 'acc_cols', 'stage_bytes', 'w_res_bytes', 'slots_alloc', 'ksplit', 'nbuf']
   return dict(zip(keys, list(info)))
 
 
@@ -206,7 +206,8 @@ def get_gaussian_filter(box, H, W, F, fy=None, fx=None, band=None):
 
 def extract_patch(xs, canvas, chan_map, box, fy, fx, band, tmp=None, out=None):
   """modellib.extract_patch (modellib.py:615-641) with the attention gain of
-  full_model.py:788: xs [B,H,W,Cs] + canvas [B,H,W] -> x_patch [B,F,F,Cs+1]."""
+  full_model.py:788: xs [B,H,W,Cs] + canvas [B,H,W] -> x_patch [B,F,F,Cs+1].  `out` may have a wider last
+  dimension (channel stride); the extra channels are zero-filled."""
   _chk(xs, canvas, chan_map, box, fy, fx, band, tmp, out)
   B, F, H = fy.shape
   W = fx.shape[2]
@@ -217,9 +218,10 @@ def extract_patch(xs, canvas, chan_map, box, fy, fx, band, tmp=None, out=None):
     tmp = torch.empty((B * F * W * D,), device=dev, dtype=torch.float32)
   if out is None:
     out = torch.empty((B, F, F, D), device=dev, dtype=torch.float32)
-  assert tmp.numel() >= B * F * W * D and tuple(out.shape) == (B, F, F, D)
+  assert tmp.numel() >= B * F * W * D and tuple(out.shape[:3]) == (B, F, F) and out.shape[3] >= D
+  assert out.is_contiguous()
   _lib.call('ra_gaussian_extract_f32', _p(xs), Cs, _p(canvas), _p(chan_map), _p(box), _p(fy), _p(fx), _p(band), B,
-            H, W, F, _p(tmp), _p(out), _stream())
+            H, W, F, _p(tmp), _p(out), out.shape[3], _stream())
   return out
 
 

@@ -419,7 +419,19 @@ UMMA_CASES = [
     (32, 12, 12, 64, 64, 64, 1, 1, 1),   # dcnn L1 at the bench batch
     (7, 12, 12, 64, 0, 96, 1, 2, 1),     # odd batch, N = 96
     (5, 64, 128, 32, 0, 32, 1, 2, 1),    # several tiles per CTA (persistent loop, TMEM double buffering)
+    (2, 48, 48, 16, 0, 16, 1, 1, 1),     # attn L0 on the glimpse padded to 16 channels (TMA feed)
+    (2, 48, 48, 16, 16, 1, 1, 1, 1),     # dcnn L6 with the padded glimpse as skip input
+    (32, 24, 24, 32, 32, 16, 2, 1, 1),   # dcnn L4 at the bench batch (TMA box of the low-resolution input)
+    (1, 17, 22, 8, 4, 8, 2, 1, 0),       # transposed, odd height, ragged tiles
+    (3, 10, 6, 4, 0, 20, 1, 1, 1),       # tile wider than the image (TMA box larger than the tensor)
 ]
+
+
+@pytest.mark.parametrize('case', [UMMA_CASES[i] for i in (0, 4, 12, 13, 14, 21)])
+def test_conv3x3_block_umma_plain_loads(ops, case, monkeypatch):
+  """The same layers with the TMA feed switched off (the path layers with odd channel counts take)."""
+  monkeypatch.setenv('RA_CONV_NO_TMA', '1')
+  test_conv3x3_block_umma(ops, case)
 
 
 @pytest.mark.parametrize('case', UMMA_CASES)

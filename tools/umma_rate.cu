@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128) rate_kernel(int N, int n_acc, int n_mma, 
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u));
 }
-int main() {
+int main_rate() {
   long long *d, h[2];
   cudaMalloc(&d, 16);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -106,4 +106,98 @@ int main() {
           printf("%3d %d %d %d : %7.1f %7.1f\n", N, n_acc, shift, swz, (double)h[0] / n_mma, (double)h[1] / n_mma);
         }
   return 0;
+}
+
+// Pattern of the conv kernel: n_acc independent accumulators (m-tiles), per step either one instruction shape
+// (mode 0: N) or the merged pair (mode 1: for acc: MMA(2N, A_hi); for acc: MMA(N, A_lo); mode 2: per acc both
+// back to back).  The whole warp runs the loop (uniform operands), as in conv_umma.cu.
+__global__ void __launch_bounds__(128) pattern_kernel(int N, int n_acc, int n_steps, int mode, int shift_rows, long long *out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint32_t tmem_s;
+  __shared__ __align__(8) uint64_t mbar;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<float *>(smem)[i] = 1.0f;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_s)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = __shfl_sync(0xffffffffu, tmem_s, 0);
+  if (warp == 0) {
+    const bool leader = elect_one();
+    const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // A: 2 planes of 2048 slots x 16 B (plane stride 32 KB) = 64 KB; B: 2 planes of 2N rows at 128 KB
+    const uint64_t da = make_desc(smem_u32(smem), 32768, 128);
+    const uint64_t db = make_desc(smem_u32(smem) + 131072, (uint32_t)(2 * N) * 16, 128);
+    const int cols = mode == 0 ? N : 2 * N;
+    long long t0 = clock64();
+    for (int i = 0; i < n_steps; ++i) {
+      const uint64_t a_i = da + (uint64_t)((i % 9) * shift_rows);  // tap-like start offsets
+      if (mode == 0) {
+        for (int a = 0; a < n_acc; ++a)
+          if (leader) umma(tm + a * cols, a_i + (uint64_t)(a * 128), db, idesc_n, 1u);
+      } else if (mode == 1) {
+        for (int a = 0; a < n_acc; ++a)
+          if (leader) umma(tm + a * cols, a_i + (uint64_t)(a * 128), db, idesc_2n, 1u);
+        for (int a = 0; a < n_acc; ++a)
+          if (leader) umma(tm + a * cols, a_i + (uint64_t)(a * 128 + 1024), db, idesc_n, 1u);
+      } else {
+        for (int a = 0; a < n_acc; ++a) {
+          if (leader) umma(tm + a * cols, a_i + (uint64_t)(a * 128), db, idesc_2n, 1u);
+          if (leader) umma(tm + a * cols, a_i + (uint64_t)(a * 128 + 1024), db, idesc_n, 1u);
+        }
+      }
+    }
+    __syncwarp();
+    long long t1 = clock64();
+    if (leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+    }
+    long long t2 = clock64();
+    if (tid == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u));
+}
+int main(int argc, char **argv) {
+  long long *d, h[2];
+  cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  printf("conv pattern: N n_acc mode shift grid : issue_cyc/mma  total_cyc/mma\n");
+  int Ns[] = {16, 32, 64, 128};
+  for (int grid = 1; grid <= 148; grid += 147)
+    for (int ni = 0; ni < 4; ++ni)
+      for (int mode = 0; mode < 3; ++mode)
+        for (int n_acc = 1; n_acc <= 8; ++n_acc)
+          for (int shift = 0; shift <= 1; ++shift) {
+            const int N = Ns[ni];
+            const int cols = mode == 0 ? N : 2 * N;
+            if (n_acc * cols > 512 || (mode > 0 && 2 * N > 256)) continue;
+            if (grid > 1 && (shift == 0 || (n_acc != 1 && n_acc != 3 && n_acc != 7))) continue;
+            const int n_steps = 300;
+            const int n_mma = n_steps * n_acc * (mode == 0 ? 1 : 2);
+            pattern_kernel<<<grid, 128, 200 * 1024>>>(N, n_acc, n_steps, mode, shift, d);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+            cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+            printf("%3d %d %d %d %3d : %7.1f %7.1f\n", N, n_acc, mode, shift, grid, (double)h[0] / n_mma, (double)h[1] / n_mma);
+          }
+  if (argc > 1) return 0;
+  return main_rate();
 }
