@@ -224,42 +224,40 @@ struct IssueCtx {
   uint32_t TWP, a_k8, b_k8, b_tap, b_lo, cols_mt, wrap, init_steps;
 };
 
-// The 9 taps x K8N k8-steps of one channel chunk, fully unrolled.  Step q accumulates into partial accumulator
-// q % ksplit (kept incrementally as a column offset jc that wraps at ksplit * cols_mt).  TWO: the warp owns a
-// second m-tile.  Everything outside the `if (leader)` is uniform-datapath arithmetic.
+// The 9 taps x K8N k8-steps of one channel chunk, run by the ELECTED lane only (the caller branches on it): the
+// compiler then knows a single thread is active and feeds the MMA's uniform-register operands with plain R2UR
+// moves from ordinary integer arithmetic.  Taps are a rolled loop - fully unrolled variants made the kernel 335 KB
+// of code and every launch paid the instruction-cache misses; the k8 steps and the warp's one or two m-tiles (TWO)
+// are unrolled.  Step q accumulates into partial accumulator q % ksplit (column offset jc, wraps at wrap).
 template <int K8N, bool MERGED, bool TWO>
-__device__ __forceinline__ void issue_chunk(const IssueCtx c, const bool leader) {
-  uint32_t jc = 0;
+__device__ __forceinline__ void issue_chunk(const IssueCtx &c) {
+  uint32_t jc = 0, a_row = 0, b_tap = 0;
+  int q = 0;
+#pragma unroll 1
+  for (int ky = 0; ky < 3; ++ky, a_row += c.TWP) {
+#pragma unroll 1
+    for (int kx = 0; kx < 3; ++kx, b_tap += c.b_tap) {
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-      for (int k8 = 0; k8 < K8N; ++k8) {
-        const int q = (ky * 3 + kx) * K8N + k8;
-        const uint64_t a_off = (uint64_t)((uint32_t)ky * c.TWP + (uint32_t)kx + (uint32_t)k8 * c.a_k8);
-        const uint64_t b_hi = c.b + (uint64_t)((uint32_t)(ky * 3 + kx) * c.b_tap + (uint32_t)k8 * c.b_k8);
+      for (int k8 = 0; k8 < K8N; ++k8, ++q) {
+        const uint64_t a_off = (uint64_t)(a_row + (uint32_t)kx + (uint32_t)k8 * c.a_k8);
+        const uint64_t b_hi = c.b + (uint64_t)(b_tap + (uint32_t)k8 * c.b_k8);
         const uint32_t flag = (uint32_t)q < c.init_steps ? 0u : 1u;
         const uint32_t d0 = c.d0 + jc, d1 = c.d1 + jc;
         const uint64_t a0h = c.a0_hi + a_off, a1h = c.a1_hi + a_off, a0l = c.a0_lo + a_off, a1l = c.a1_lo + a_off;
         if (MERGED) {
           // D[:, 0:N] += A_hi B_hi and D[:, N:2N] += A_hi B_lo in ONE instruction, then D[:, 0:N] += A_lo B_hi
-          if (leader) {
-            umma_tf32(d0, a0h, b_hi, c.idesc_2n, flag);
-            if (TWO) umma_tf32(d1, a1h, b_hi, c.idesc_2n, flag);
-            umma_tf32(d0, a0l, b_hi, c.idesc_n, 1u);
-            if (TWO) umma_tf32(d1, a1l, b_hi, c.idesc_n, 1u);
-          }
+          umma_tf32(d0, a0h, b_hi, c.idesc_2n, flag);
+          if (TWO) umma_tf32(d1, a1h, b_hi, c.idesc_2n, flag);
+          umma_tf32(d0, a0l, b_hi, c.idesc_n, 1u);
+          if (TWO) umma_tf32(d1, a1l, b_hi, c.idesc_n, 1u);
         } else {
           const uint64_t b_lo = b_hi + (uint64_t)c.b_lo;
-          if (leader) {
-            umma_tf32(d0, a0h, b_hi, c.idesc_n, flag);
-            if (TWO) umma_tf32(d1, a1h, b_hi, c.idesc_n, flag);
-            umma_tf32(d0, a0h, b_lo, c.idesc_n, 1u);
-            if (TWO) umma_tf32(d1, a1h, b_lo, c.idesc_n, 1u);
-            umma_tf32(d0, a0l, b_hi, c.idesc_n, 1u);
-            if (TWO) umma_tf32(d1, a1l, b_hi, c.idesc_n, 1u);
-          }
+          umma_tf32(d0, a0h, b_hi, c.idesc_n, flag);
+          if (TWO) umma_tf32(d1, a1h, b_hi, c.idesc_n, flag);
+          umma_tf32(d0, a0h, b_lo, c.idesc_n, 1u);
+          if (TWO) umma_tf32(d1, a1h, b_lo, c.idesc_n, 1u);
+          umma_tf32(d0, a0l, b_hi, c.idesc_n, 1u);
+          if (TWO) umma_tf32(d1, a1l, b_hi, c.idesc_n, 1u);
         }
         jc += c.cols_mt;
         if (jc == c.wrap) jc = 0;
@@ -269,17 +267,17 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx c, const bool leader)
 }
 
 template <int K8N>
-__device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool leader, bool merged, bool two) {
+__device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, bool two) {
   if (merged) {
     if (two)
-      issue_chunk<K8N, true, true>(c, leader);
+      issue_chunk<K8N, true, true>(c);
     else
-      issue_chunk<K8N, true, false>(c, leader);
+      issue_chunk<K8N, true, false>(c);
   } else {
     if (two)
-      issue_chunk<K8N, false, true>(c, leader);
+      issue_chunk<K8N, false, true>(c);
     else
-      issue_chunk<K8N, false, false>(c, leader);
+      issue_chunk<K8N, false, false>(c);
   }
 }
 
@@ -550,12 +548,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (ptid == 0) RA_DBG(3);  // producers done
   } else if (warp >= kMmaWarp0) {
     // =============================== MMA issuers ===============================
-    // tcgen05.mma takes its operands from UNIFORM registers, and uniform-datapath instructions cost ~5 cycles each
-    // when they depend on one another (tools/umma_rate.cu): issued from an `if (lane == 0)` region every MMA sits in
-    // an ELECT / R2UR.BROADCAST loop (~185 cycles), and even warp-uniform generic loops spend ~450 cycles per
-    // (tap, k8) step on loop control.  So: the whole warp runs warp-uniform code (warp index / TMEM base through
-    // shuffles, everything else from kernel parameters), only the instruction sits behind the elected lane, and
-    // the 9 x K8N steps of a chunk are straight-line code (issue_chunk<>).  Warp mw owns m-tiles mw and mw + 4.
+    // tcgen05.mma takes its operands from UNIFORM registers.  Issued from an `if (lane == 0)` region the compiler
+    // cannot prove them warp-uniform and wraps every MMA in an ELECT / R2UR.BROADCAST loop (~185 cycles per
+    // instruction); generic warp-uniform loops are no better (dependent uniform-datapath instructions cost ~5 cycles
+    // each, ~450 cycles of loop control per step).  What works: branch on elect.sync - the compiler then knows ONE
+    // thread is active and uses plain R2UR moves (~50-75 cycles per instruction, measured) - and let kMmaWarps warps
+    // issue in parallel.  Warp mw owns m-tiles mw and mw + 4 (their own TMEM accumulator columns).
     {
       const bool leader = elect_one();
       const int mw = warp - kMmaWarp0;
@@ -603,14 +601,15 @@ __global__ void __launch_bounds__(kThreads, 1)
                                                : a_hi + 2u * (uint32_t)in_floats * 4u;
           c.b = make_desc(w_addr, w_plane, 128);
           c.init_steps = ch == 0 ? (uint32_t)p.ksplit : 0u;  // the first MMA into each accumulator overwrites
-          if (has0) {
+          if (has0 && leader) {
             if (k8n == 1)
-              issue_chunk_k8<1>(c, leader, merged, has1);
+              issue_chunk_k8<1>(c, merged, has1);
             else if (k8n == 2)
-              issue_chunk_k8<2>(c, leader, merged, has1);
+              issue_chunk_k8<2>(c, merged, has1);
             else
-              issue_chunk_k8<4>(c, leader, merged, has1);
+              issue_chunk_k8<4>(c, merged, has1);
           }
+          __syncwarp();
           if (leader) umma_commit(smem_u32(&bar_empty[s]));  // the stage may be refilled once these MMAs have read it
           __syncwarp();
         }
