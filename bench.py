@@ -88,9 +88,11 @@ class ClockSampler(object):
 
 
 # --------------------------------------------------------------------------- roofline model
-def kernel_algorithmic_work(opt, B):
+def kernel_algorithmic_work(opt, B, Bc=None):
   """Algorithmic bytes / flops PER LAUNCH of the HBM-/tensor-bound kernels.
-  Keys are the C-ABI entry points (one decode step of B images per launch unless noted)."""
+  Keys are the C-ABI entry points.  Decode-loop kernels process one step of Bc images per launch (Bc = B / chains,
+  FullModel._chains); the loss-side kernels see the whole batch B."""
+  Bc = B if Bc is None else Bc
   H, W, T, F = opt['inp_height'], opt['inp_width'], opt['timespan'], opt['filter_height']
   from rec_attend_b200.config import input_depths
   D = input_depths(opt)[0]
@@ -98,9 +100,9 @@ def kernel_algorithmic_work(opt, B):
   p0 = opt['ctrl_cnn_pool'][0]
   work = {
       # (H*W*D + F^2*D)*4 per image-step
-      'ra_gaussian_extract_f32': {'bytes': B * (H * W * D + F * F * D) * 4.0},
+      'ra_gaussian_extract_f32': {'bytes': Bc * (H * W * D + F * F * D) * 4.0},
       # (F^2 + 3*H*W)*4 (read patch + read canvas + write y_out + write canvas) + H*W*4 (attn_box write)
-      'ra_paste_back_f32': {'bytes': B * (F * F + 4 * H * W) * 4.0},
+      'ra_paste_back_f32': {'bytes': Bc * (F * F + 4 * H * W) * 4.0},
       # pairwise IoU: 2*B*T*H*W*4 per call
       'ra_pairwise_iou_f32': {'bytes': 2.0 * B * T * H * W * 4, 'flops': 2.0 * B * T * T * H * W},
       'ra_gt_box_f32': {'bytes': 1.0 * B * T * H * W * 4},
@@ -111,8 +113,9 @@ def kernel_algorithmic_work(opt, B):
   for i, pl in enumerate(opt['ctrl_cnn_pool']):
     fl += 2.0 * h * w * ch[i + 1] * 9 * ch[i]
     h, w = h // pl, w // pl
-  work['ctrl_cnn_step'] = {'flops': B * fl,
-                           'bytes': B * (H * W * (c0 + 1) + (H // p0) * (W // p0) * c0) * 4.0}
+  work['ctrl_cnn_step'] = {'flops': B * fl}  # all chains together: one decode step of the whole batch
+  # first controller layer, per-step half: read static_pre + canvas at full resolution, write the pooled output
+  work['ra_canvas_conv_f32'] = {'bytes': Bc * (H * W * (c0 + 1) + (H // p0) * (W // p0) * c0) * 4.0}
   return work
 
 
@@ -311,7 +314,8 @@ def run_ours(args):
       model.forward(dev_batch, outputs=fetch, use_graph=False)  # eager: one C-ABI call per kernel group
     agg = ot.summary()
     launches_per_step = int(lib.ra_launch_count() - n0)
-    work = kernel_algorithmic_work(opt, B)
+    chains = model._chains(B)
+    work = kernel_algorithmic_work(opt, B, chains[0][1] - chains[0][0])
     total_ms = sum(d['ms'] for d in agg.values())
     groups = {}
     for key, d in agg.items():
@@ -365,7 +369,9 @@ def run_ours(args):
         'config': {'workload': cfg['name'], 'arch': cfg['arch'], 'batch_per_gpu': B, 'timespan': T,
                    'height': cfg['H'], 'width': cfg['W'], 'parallelism': 'dp{}'.format(world),
                    'l2': 'inputs {:.0f} MB + per-step working set exceed the 126 MB L2'.format(h2d / 1e6),
-                   'step': 'eval forward (T-step decode) + matching loss block'},
+                   'step': 'eval forward (T-step decode) + matching loss block',
+                   'chains': '{} sub-batch chains of the decode loop run as parallel CUDA-graph branches'.format(
+                       len(chains))},
         'e2e': {'value': e2e_value, 'unit': 'masks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps, 'fetch': fetch,
                 'pipeline': 'H2D of step i+1 overlaps the compute of step i (double-buffered static inputs)'},

@@ -195,11 +195,13 @@ int ra_gaussian_extract_f32(const float *xs, int Cs, const float *canvas, const 
  * patch [B,F,F] (may be NULL: attention box only, box_model.py:484-487); attn_box may be
  * NULL (mask only).  attn_box / y_out are written at [b*out_bstride + y*W + x]
  * (out_bstride = T*H*W lets the caller write step t of a [B,T,H,W] stack in place);
- * canvas [B,H,W] is updated in place.
+ * canvas [B,H,W] is updated in place.  band [B,2,F,2] (from ra_gaussian_filters_f32; may be
+ * NULL) lets tiles outside every tap's support skip the filter arithmetic: the result is the
+ * same (entries outside a band are exact zeros), only faster.
  * -------------------------------------------------------------------------------------- */
-int ra_paste_back_f32(const float *patch, const float *box, const float *fy, const float *fx, int B, int H, int W,
-                      int F, int disable_overwrite, float *attn_box, float *y_out, size_t out_bstride, float *canvas,
-                      void *stream);
+int ra_paste_back_f32(const float *patch, const float *box, const float *fy, const float *fx, const int32_t *band,
+                      int B, int H, int W, int F, int disable_overwrite, float *attn_box, float *y_out,
+                      size_t out_bstride, float *canvas, void *stream);
 
 /* Score head, full_model.py:821-822: s = sigmoid(w . concat(h, core) + b); h [B,Hd],
  * core [B,Cd] (may be NULL with Cd = 0: box_model.py:508-511), w [Hd+Cd], s_out at
@@ -268,6 +270,27 @@ int ra_box_gt_step_f32(const float *attn_box, size_t box_bstride, const float *g
  * step-invariant part of the input stack of full_model.py:640-661 (Cb, Cc may be 0). */
 int ra_concat_channels_f32(const float *a, int Ca, const float *b, int Cb, const float *c, int Cc, size_t npix,
                            float *out, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Instance-label post-processing — utils/postprocess.py as chained by
+ * full_model_eval.py:112-125: apply_confidence (postprocess.py:17-31),
+ * apply_one_label (:34-55), apply_threshold (:6-14), mask_foreground (:146-155),
+ * remove_tiny (:106-143).  y_out [B,T,H,W], s_out [B,T], fg [B,H,W] (may be NULL):
+ *   v[t]     = y_out[b,t,p] * s_out[b,t]                       (fp32)
+ *   k        = first arg max_t v[t]                             (np.argmax)
+ *   on       = (double)v[k] > thresh                            (Python-float threshold)
+ *   label[p] = k + 1 if on (and fg[p] != 0) else 0              int32 [B,H,W]
+ *   area[b,t] = sum_p on * fg[p] over pixels with k == t        (remove_tiny's y.sum)
+ *   remove_tiny > 0: instances with area <= remove_tiny are erased from the label map
+ *   conf[b,t] = (s_out > 0.5) * (area > remove_tiny or remove_tiny == 0)
+ *   y_hard (may be NULL) [B,T,H,W] = the reference's dense float masks (label == t+1) * fg.
+ * workspace: ra_postprocess_workspace(B, T) bytes of device memory.  cv2-based steps
+ * (upsample + bilateral filter, morph) are outside this entry point.
+ * -------------------------------------------------------------------------------------- */
+size_t ra_postprocess_workspace(int B, int T);
+int ra_postprocess_f32(const float *y_out, const float *s_out, const float *fg, int B, int T, int H, int W,
+                       double thresh, float remove_tiny, void *workspace, int32_t *label, float *y_hard, float *conf,
+                       float *area, void *stream);
 
 #ifdef __cplusplus
 }

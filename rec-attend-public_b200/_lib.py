@@ -44,16 +44,17 @@ _SIGNATURES = {
                                _P, _P, _P, _P],
     'ra_gaussian_filters_f32': [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     'ra_gaussian_extract_f32': [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
-    'ra_paste_back_f32': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P, _P],
+    'ra_paste_back_f32': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P, _P],
     'ra_score_f32': [_P, _I, _P, _I, _P, _P, _I, _P, _I, _P],
     'ra_gt_box_f32': [_P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P],
     'ra_pairwise_iou_f32': [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P],
     'ra_loss_block_f32': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P],
     'ra_box_gt_step_f32': [_P, _Z, _P, _P, _P, _Z, _I, _I, _I, _I, _P, _I, _P, _P, _P],
     'ra_concat_channels_f32': [_P, _I, _P, _I, _P, _I, _Z, _P, _P],
+    'ra_postprocess_f32': [_P, _P, _P, _I, _I, _I, _I, ctypes.c_double, _F, _P, _P, _P, _P, _P, _P],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last_error', 'ra_launch_count',
-                                         'ra_pairwise_iou_workspace'])
+                                         'ra_pairwise_iou_workspace', 'ra_postprocess_workspace'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -81,6 +82,8 @@ def lib():
     l.ra_launch_count.restype = ctypes.c_ulonglong
     l.ra_pairwise_iou_workspace.argtypes = [_I, _I, _I, _I]
     l.ra_pairwise_iou_workspace.restype = _Z
+    l.ra_postprocess_workspace.argtypes = [_I, _I]
+    l.ra_postprocess_workspace.restype = _Z
     _lib = l
   return _lib
 

@@ -59,7 +59,7 @@ class BoxModel(_ModelBase):
       self._controller(bufs, t)
       _lib.TAG = 'paste_back'
       ops.paste_back(None, bufs['box_all'][t], bufs['fy'], bufs['fx'], None, attn_box=bufs['attn_box'][:, t],
-                     y_out=None, out_bstride=thw)
+                     y_out=None, out_bstride=thw, band=bufs['band'])
       _lib.TAG = 'box_gt'
       ops.box_gt_step(bufs['attn_box'][:, t], thw, rect, y_gt, None if noise is None else noise[:, t], thw,
                       bufs['iou_box'][:, t], T * T, bufs['grd'], bufs['canvas'])

@@ -192,77 +192,93 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvParams p) {
 // linear in its input channels and only the canvas changes between decode steps, so the
 // step-invariant channels are convolved once per forward (pre [B,H,W,C0]) and every step adds
 // the 1-channel canvas convolution: y = pool(relu((pre + conv(canvas)) * scale + shift)).
-// HBM-bound: one read of pre, one of the canvas, one write of the pooled map.  A thread owns
-// one pooled pixel x 4 channels: a 4x4 canvas patch (L1), 4 float4 of pre, 9x4 weights in
-// registers.
+// HBM-bound: one read of pre, one of the canvas, one write of the pooled map.  A CTA owns one pooled output
+// row segment of one example (grid = segments x pooled rows x B: no 64-bit index arithmetic); the (POOL+2)-row
+// canvas strip is staged once in shared memory (zero padded = SAME), a thread owns one pooled pixel x 4
+// channels: POOL^2 float4 of pre (streamed, all loads issued up front), 9x4 weights in registers.
+constexpr int kCcThreads = 256;
+constexpr int kCcMaxCols = kCcThreads / 2 * 2 + 2;  // widest strip: C0 = 8 -> 128 pooled pixels x POOL 2, + halo
+
 template <int POOL>
-__global__ void __launch_bounds__(256) canvas_conv_kernel(const float *__restrict__ pre,
-                                                          const float *__restrict__ canvas,
-                                                          const float *__restrict__ w, const float *__restrict__ scale,
-                                                          const float *__restrict__ shift, int B, int H, int W, int C0,
-                                                          int relu, float *__restrict__ y) {
+__global__ void __launch_bounds__(kCcThreads) canvas_conv_kernel(const float *__restrict__ pre,
+                                                                 const float *__restrict__ canvas,
+                                                                 const float *__restrict__ w,
+                                                                 const float *__restrict__ scale,
+                                                                 const float *__restrict__ shift, int B, int H, int W,
+                                                                 int C0, int relu, float *__restrict__ y) {
+  __shared__ float cv_s[POOL + 2][kCcMaxCols];
   const int cg_n = C0 >> 2;
+  const int PX = kCcThreads / cg_n;  // pooled pixels per CTA
   const int Ho = H / POOL, Wo = W / POOL;
-  const size_t total = (size_t)B * Ho * Wo * cg_n;
-  const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int cg = (int)(gid % cg_n);
-  size_t pix = gid / cg_n;
-  const int ox = (int)(pix % Wo);
-  pix /= Wo;
-  const int oy = (int)(pix % Ho);
-  const int b = (int)(pix / Ho);
+  const int b = blockIdx.z, oy = blockIdx.y;
+  const int ox0 = blockIdx.x * PX;
+  const int tid = threadIdx.x;
+  const int cg = tid % cg_n, oxl = tid / cg_n;
+  const int ox = ox0 + oxl;
   const int c = cg * 4;
 
+  // canvas strip: rows oy*POOL-1 .. oy*POOL+POOL, columns ox0*POOL-1 .. (ox0+PX)*POOL
+  const int ncol = PX * POOL + 2;
+  const float *cb = canvas + (size_t)b * H * W;
+  for (int idx = tid; idx < (POOL + 2) * ncol; idx += kCcThreads) {
+    const int r = idx / ncol, q = idx - r * ncol;
+    const int yy = oy * POOL - 1 + r, xx = ox0 * POOL - 1 + q;
+    cv_s[r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(cb + (size_t)yy * W + xx) : 0.f;
+  }
+  const bool live = ox < Wo;
+  float4 a[POOL][POOL];
+  if (live) {
+#pragma unroll
+    for (int py = 0; py < POOL; ++py)
+#pragma unroll
+      for (int px = 0; px < POOL; ++px)
+        a[py][px] = __ldcs(reinterpret_cast<const float4 *>(
+            pre + (((size_t)b * H + oy * POOL + py) * W + ox * POOL + px) * C0 + c));
+  }
   float4 wk[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) wk[k] = __ldg(reinterpret_cast<const float4 *>(w + k * C0 + c));
   const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c));
   const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
+  __syncthreads();
+  if (!live) return;
 
-  // canvas patch (POOL+2)^2 around the POOL x POOL window, zero padded (SAME)
   float cv[POOL + 2][POOL + 2];
-  const float *cb = canvas + (size_t)b * H * W;
-  const int y0 = oy * POOL - 1, x0 = ox * POOL - 1;
 #pragma unroll
   for (int r = 0; r < POOL + 2; ++r)
 #pragma unroll
-    for (int q = 0; q < POOL + 2; ++q) {
-      const int yy = y0 + r, xx = x0 + q;
-      cv[r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(cb + (size_t)yy * W + xx) : 0.f;
-    }
+    for (int q = 0; q < POOL + 2; ++q) cv[r][q] = cv_s[r][oxl * POOL + q];
   float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
   for (int py = 0; py < POOL; ++py)
 #pragma unroll
     for (int px = 0; px < POOL; ++px) {
-      const int yy = oy * POOL + py, xx = ox * POOL + px;
-      float4 a = __ldcs(reinterpret_cast<const float4 *>(pre + (((size_t)b * H + yy) * W + xx) * C0 + c));
+      float4 v4 = a[py][px];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const float v = cv[py + ky][px + kx];
           const float4 ww = wk[ky * 3 + kx];
-          a.x = fmaf(v, ww.x, a.x);
-          a.y = fmaf(v, ww.y, a.y);
-          a.z = fmaf(v, ww.z, a.z);
-          a.w = fmaf(v, ww.w, a.w);
+          v4.x = fmaf(v, ww.x, v4.x);
+          v4.y = fmaf(v, ww.y, v4.y);
+          v4.z = fmaf(v, ww.z, v4.z);
+          v4.w = fmaf(v, ww.w, v4.w);
         }
-      a.x = fmaf(a.x, sc.x, sh.x);
-      a.y = fmaf(a.y, sc.y, sh.y);
-      a.z = fmaf(a.z, sc.z, sh.z);
-      a.w = fmaf(a.w, sc.w, sh.w);
+      v4.x = fmaf(v4.x, sc.x, sh.x);
+      v4.y = fmaf(v4.y, sc.y, sh.y);
+      v4.z = fmaf(v4.z, sc.z, sh.z);
+      v4.w = fmaf(v4.w, sc.w, sh.w);
       if (relu) {
-        a.x = fmaxf(a.x, 0.f);
-        a.y = fmaxf(a.y, 0.f);
-        a.z = fmaxf(a.z, 0.f);
-        a.w = fmaxf(a.w, 0.f);
+        v4.x = fmaxf(v4.x, 0.f);
+        v4.y = fmaxf(v4.y, 0.f);
+        v4.z = fmaxf(v4.z, 0.f);
+        v4.w = fmaxf(v4.w, 0.f);
       }
-      best.x = fmaxf(best.x, a.x);
-      best.y = fmaxf(best.y, a.y);
-      best.z = fmaxf(best.z, a.z);
-      best.w = fmaxf(best.w, a.w);
+      best.x = fmaxf(best.x, v4.x);
+      best.y = fmaxf(best.y, v4.y);
+      best.z = fmaxf(best.z, v4.z);
+      best.w = fmaxf(best.w, v4.w);
     }
   *reinterpret_cast<float4 *>(y + (((size_t)b * Ho + oy) * Wo + ox) * C0 + c) = best;
 }
@@ -371,13 +387,18 @@ extern "C" int ra_canvas_conv_f32(const float *pre, const float *canvas, const f
   if ((C0 & 3) != 0 || (pool != 1 && pool != 2)) return RA_ERR_UNSUPPORTED;
   if (pool == 2 && ((H | W) & 1)) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
-  const size_t total = (size_t)B * (H / pool) * (W / pool) * (C0 / 4);
-  const size_t blocks = (total + 255) / 256;
-  if (blocks > 0x7fffffffULL) return RA_ERR_UNSUPPORTED;
+  // a CTA serves kCcThreads / (C0/4) pooled pixels of one pooled row; C0/4 must divide the CTA and the strip
+  // must fit the static shared tile (C0 >= 8)
+  const int cg_n = C0 / 4;
+  if (C0 < 8 || (kCcThreads % cg_n) != 0 || cg_n > kCcThreads) return RA_ERR_UNSUPPORTED;
+  const int PX = kCcThreads / cg_n;
+  const int Ho = H / pool, Wo = W / pool;
+  if (Ho > 65535 || B > 65535) return RA_ERR_UNSUPPORTED;
+  dim3 grid((Wo + PX - 1) / PX, Ho, B);
   cudaStream_t s = ra::as_stream(stream);
   if (pool == 2)
-    canvas_conv_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
+    canvas_conv_kernel<2><<<grid, kCcThreads, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
   else
-    canvas_conv_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
+    canvas_conv_kernel<1><<<grid, kCcThreads, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
   return ra::finish_launch("canvas_conv_kernel");
 }

@@ -1144,6 +1144,11 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
       ra::set_last_error("cudaFuncSetAttribute(conv3x3_umma_kernel)", e);
       return RA_ERR_CUDA;
     }
+    // diagnostics: pin the SM shared-memory carve-out to its maximum for every launch of this kernel, so that
+    // consecutive layers with different dynamic sizes never trigger a carve-out reconfiguration
+    if (getenv("RA_CONV_CARVEOUT") != nullptr)
+      (void)cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   conv3x3_umma_kernel<<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);

@@ -63,16 +63,51 @@ __global__ void build_filters_kernel(const float *__restrict__ box, int H, int W
 }
 
 // ------------------------------------------------------------------ glimpse: row pass
-// src viewed as [B][H][rowlen] (rowlen = W*D, any D); tmp [B][F][rowlen].
+// Union over the F taps of one axis' support bands -> r[0..1] (shared); empty union: r[0] > r[1].
+// Filter entries outside a tap's band are exact zeros, so consumers may skip everything outside the union.
+__device__ __forceinline__ void band_union(const int *__restrict__ bd, int F, int L, int *r) {
+  if (threadIdx.x == 0) {
+    r[0] = L;
+    r[1] = -1;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < F; t += blockDim.x) {
+    const int lo = bd[t * 2], hi = bd[t * 2 + 1];
+    if (hi >= lo) {
+      atomicMin(&r[0], lo);
+      atomicMax(&r[1], hi);
+    }
+  }
+  __syncthreads();
+}
+
+// One launch for both sources: CTAs [0, nx_s) of grid.x serve the static stack xs viewed as [B][H][W*Cs],
+// the rest the canvas [B][H][W]; tmp_s [B][F][W*Cs], tmp_c [B][F][W].  Only the columns inside the union of
+// the x-bands are produced (the column pass reads nothing else) and only the rows of the taps' y-bands are read.
 // grid (chunks of 4*blockDim floats, F/IB tap groups, B).
 template <int IB>
-__global__ void __launch_bounds__(128) extract_rows_kernel(const float *__restrict__ src, int H, int rowlen,
+__global__ void __launch_bounds__(128) extract_rows_kernel(const float *__restrict__ xs, int Cs,
+                                                           const float *__restrict__ canvas, int H, int W,
                                                            const float *__restrict__ fy, const int *__restrict__ band,
-                                                           int F, float *__restrict__ tmp) {
+                                                           int F, float *__restrict__ tmp_s, float *__restrict__ tmp_c,
+                                                           int nx_s) {
   extern __shared__ float wsm[];  // [IB][H]
+  __shared__ int xr[2];
   const int b = blockIdx.z;
   const int i0 = blockIdx.y * IB;
-  const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const bool is_c = (int)blockIdx.x >= nx_s;
+  const float *src = is_c ? canvas : xs;
+  float *tmp = is_c ? tmp_c : tmp_s;
+  const int C = is_c ? 1 : Cs;
+  const int rowlen = W * C;
+  const int bx = is_c ? (int)blockIdx.x - nx_s : (int)blockIdx.x;
+  const int e0 = (bx * (int)blockDim.x + (int)threadIdx.x) * 4;
+  band_union(band + ((size_t)b * 2 + 1) * F * 2, F, W, xr);
+  const int elo = xr[0] * C, ehi = (xr[1] + 1) * C;  // floats [elo, ehi) of a row are needed
+  {
+    const int c0 = bx * (int)blockDim.x * 4, c1 = c0 + (int)blockDim.x * 4;
+    if (c1 <= elo || c0 >= ehi) return;  // whole CTA outside the box columns (uniform)
+  }
   const int *bd = band + ((size_t)b * 2 + 0) * F * 2;
   int ylo = H, yhi = -1;
 #pragma unroll
@@ -91,7 +126,7 @@ __global__ void __launch_bounds__(128) extract_rows_kernel(const float *__restri
     wsm[k * H + yy] = (i0 + k < F) ? fy[((size_t)b * F + i0 + k) * H + ylo + yy] : 0.f;
   }
   __syncthreads();
-  if (e0 >= rowlen) return;
+  if (e0 >= rowlen || e0 + 4 <= elo || e0 >= ehi) return;
 
   float4 acc[IB];
 #pragma unroll
@@ -139,11 +174,15 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
                                                            const float *__restrict__ box, int W, int F, int Dp,
                                                            float *__restrict__ patch) {
   extern __shared__ float slab[];  // [W][D]
+  __shared__ int xr[2];
   const int i = blockIdx.x, b = blockIdx.y;
   const int D = Cs + (tmp_c != nullptr ? 1 : 0);
+  // only columns inside the union of the x-bands were produced by the row pass and are read below
+  band_union(band + ((size_t)b * 2 + 1) * F * 2, F, W, xr);
+  const int xlo = xr[0], xhi = xr[1];
   if (Cs > 0) {
     const float *ts = tmp_s + ((size_t)b * F + i) * (size_t)W * Cs;
-    for (int idx = threadIdx.x; idx < W * Cs; idx += blockDim.x) {
+    for (int idx = xlo * Cs + threadIdx.x; idx < (xhi + 1) * Cs; idx += blockDim.x) {
       const int x = idx / Cs, c = idx - x * Cs;
       slab[x * D + chan_map[c]] = ts[idx];
     }
@@ -151,7 +190,7 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
   if (tmp_c != nullptr) {
     const float *tc = tmp_c + ((size_t)b * F + i) * W;
     const int cc = chan_map[Cs];
-    for (int x = threadIdx.x; x < W; x += blockDim.x) slab[x * D + cc] = tc[x];
+    for (int x = xlo + threadIdx.x; x <= xhi; x += blockDim.x) slab[x * D + cc] = tc[x];
   }
   __syncthreads();
   const float gamma = box[(size_t)b * RA_BOX_STRIDE + RA_BOX_GAMMA_ATTN];
@@ -187,6 +226,7 @@ constexpr int kPbTX = 128;
 
 __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict__ patch,
                                                          const float *__restrict__ fy, const float *__restrict__ fx,
+                                                         const int *__restrict__ band,
                                                          const float *__restrict__ box, int H, int W, int F,
                                                          int disable_overwrite, float *__restrict__ attn_box,
                                                          float *__restrict__ y_out, size_t out_bstride,
@@ -195,11 +235,55 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
   __shared__ float wy_s[kPbTY][kMaxF];       // fy[i][y] for the tile rows
   __shared__ float t2_s[kPbTY][kMaxF + 1];   // sum_i fy[i][y] P[i][j]
   __shared__ float sy_s[kPbTY];              // sum_i fy[i][y]
+  __shared__ int yr[2], xr[2];
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * kPbTY, x0 = blockIdx.x * kPbTX;
   const int tid = threadIdx.x;
   const float *bo = box + (size_t)b * RA_BOX_STRIDE;
   const bool has_patch = patch != nullptr;
+
+  // Tiles that no tap's support band reaches (most of the image for a small box): every filter entry is an exact
+  // zero there, so attn_box = y_out = sigmoid(-5) - write the constants (float4) and update the canvas.
+  if (band != nullptr) {
+    band_union(band + ((size_t)b * 2 + 0) * F * 2, F, H, yr);
+    band_union(band + ((size_t)b * 2 + 1) * F * 2, F, W, xr);
+  }
+  if (band != nullptr && (y0 > yr[1] || y0 + kPbTY - 1 < yr[0] || x0 > xr[1] || x0 + kPbTX - 1 < xr[0])) {
+    const float c5 = ra::sigmoidf_acc(-5.0f);
+    if ((W & 3) == 0) {
+      const float4 c4 = make_float4(c5, c5, c5, c5);
+      for (int idx = tid; idx < kPbTY * (kPbTX / 4); idx += blockDim.x) {
+        const int ty = idx / (kPbTX / 4), x = x0 + (idx - ty * (kPbTX / 4)) * 4, y = y0 + ty;
+        if (y >= H || x >= W) continue;
+        const size_t pix = (size_t)y * W + x;
+        if (attn_box != nullptr) *reinterpret_cast<float4 *>(attn_box + (size_t)b * out_bstride + pix) = c4;
+        if (has_patch) {
+          float4 *cp = reinterpret_cast<float4 *>(canvas + (size_t)b * H * W + pix);
+          const float4 cv = *cp;
+          float4 v = c4;
+          if (disable_overwrite) v = make_float4(c5 * (1.0f - cv.x), c5 * (1.0f - cv.y), c5 * (1.0f - cv.z), c5 * (1.0f - cv.w));
+          *reinterpret_cast<float4 *>(y_out + (size_t)b * out_bstride + pix) = v;
+          *cp = make_float4(fmaxf(cv.x, v.x), fmaxf(cv.y, v.y), fmaxf(cv.z, v.z), fmaxf(cv.w, v.w));
+        }
+      }
+    } else {
+      for (int idx = tid; idx < kPbTY * kPbTX; idx += blockDim.x) {
+        const int ty = idx / kPbTX, x = x0 + (idx - ty * kPbTX), y = y0 + ty;
+        if (y >= H || x >= W) continue;
+        const size_t pix = (size_t)y * W + x;
+        if (attn_box != nullptr) attn_box[(size_t)b * out_bstride + pix] = c5;
+        if (has_patch) {
+          const size_t cpix = (size_t)b * H * W + pix;
+          const float cv = canvas[cpix];
+          float v = c5;
+          if (disable_overwrite) v *= (1.0f - cv);
+          y_out[(size_t)b * out_bstride + pix] = v;
+          canvas[cpix] = fmaxf(cv, v);
+        }
+      }
+    }
+    return;
+  }
 
   if (has_patch)
     for (int idx = tid; idx < F * F; idx += blockDim.x) P_s[idx] = patch[(size_t)b * F * F + idx];
@@ -307,16 +391,12 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
   float *tmp_s = tmp;
   float *tmp_c = tmp + (size_t)B * F * W * Cs;
   const size_t smem_rows = (size_t)IB * H * sizeof(float);
-  if (Cs > 0) {
-    const int rowlen = W * Cs;
-    dim3 grid((rowlen / 4 + 127) / 128, groups, B);
-    extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(xs, H, rowlen, fy, band, F, tmp_s);
-    const int rc = ra::finish_launch("extract_rows_kernel");
-    if (rc != RA_OK) return rc;
-  }
-  if (canvas != nullptr) {
-    dim3 grid((W / 4 + 127) / 128, groups, B);
-    extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(canvas, H, W, fy, band, F, tmp_c);
+  {
+    // one launch for both sources (the static stack and the canvas)
+    const int nx_s = Cs > 0 ? (W * Cs / 4 + 127) / 128 : 0;
+    const int nx_c = canvas != nullptr ? (W / 4 + 127) / 128 : 0;
+    dim3 grid(nx_s + nx_c, groups, B);
+    extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(xs, Cs, canvas, H, W, fy, band, F, tmp_s, tmp_c, nx_s);
     const int rc = ra::finish_launch("extract_rows_kernel");
     if (rc != RA_OK) return rc;
   }
@@ -338,16 +418,16 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
   return ra::finish_launch("extract_cols_kernel");
 }
 
-extern "C" int ra_paste_back_f32(const float *patch, const float *box, const float *fy, const float *fx, int B, int H,
-                                 int W, int F, int disable_overwrite, float *attn_box, float *y_out,
-                                 size_t out_bstride, float *canvas, void *stream) {
+extern "C" int ra_paste_back_f32(const float *patch, const float *box, const float *fy, const float *fx,
+                                 const int32_t *band, int B, int H, int W, int F, int disable_overwrite,
+                                 float *attn_box, float *y_out, size_t out_bstride, float *canvas, void *stream) {
   if (!box || !fy || !fx || B < 0 || H < 1 || W < 1) return RA_ERR_INVALID_ARG;
   if (patch != nullptr && (!y_out || !canvas)) return RA_ERR_INVALID_ARG;
   if (patch == nullptr && attn_box == nullptr) return RA_ERR_INVALID_ARG;
   if (F > kMaxF) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
   dim3 grid((W + kPbTX - 1) / kPbTX, (H + kPbTY - 1) / kPbTY, B);
-  paste_back_kernel<<<grid, 256, 0, ra::as_stream(stream)>>>(patch, fy, fx, box, H, W, F, disable_overwrite, attn_box,
-                                                             y_out, out_bstride, canvas);
+  paste_back_kernel<<<grid, 256, 0, ra::as_stream(stream)>>>(patch, fy, fx, band, box, H, W, F, disable_overwrite,
+                                                             attn_box, y_out, out_bstride, canvas);
   return ra::finish_launch("paste_back_kernel");
 }

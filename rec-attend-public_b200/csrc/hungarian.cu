@@ -30,70 +30,155 @@ struct WarpScratch {
   float cx[kMaxN];
   float cy[kMaxN];
   mask_t eq[kMaxN];
-  mask_t claimed[kMaxN];
   int match_y[kMaxN];
   int match_x[kMaxN];
   int level_x[kMaxN];
   int level_y[kMaxN];
   int parent_y[kMaxN];
-  int n_matched;
-  int first_free;
 };
 
-// One ranked breadth-first search + augmentation (lane 0 only). Returns true if augmented.
-__device__ bool augment_ranked(WarpScratch &s, int nx) {
-  int n_lx = 0;
-  mask_t seen_y = 0;
-  for (int x = 0; x < nx; ++x)
-    if (s.match_y[x] < 0) s.level_x[n_lx++] = x;
+__device__ __forceinline__ mask_t shfl_down64(mask_t v, int o) {
+  return (mask_t)__shfl_down_sync(0xffffffffu, (unsigned long long)v, o);
+}
+__device__ __forceinline__ mask_t shfl64(mask_t v, int src) {
+  return (mask_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src);
+}
 
-  while (n_lx > 0) {
-    // the highest-ranked pusher wins: claim columns from the back of the level
-    mask_t level_claim = 0;
-    for (int r = n_lx - 1; r >= 0; --r) {
-      const int x = s.level_x[r];
-      mask_t adj = s.eq[x];
-      const int my = s.match_y[x];
+// Inclusive suffix OR over the lanes (lane l gets OR of lanes l..31).
+__device__ __forceinline__ mask_t suffix_or(mask_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const mask_t t = shfl_down64(v, o);
+    if (lane + o < 32) v |= t;
+  }
+  return v;
+}
+// Exclusive prefix sum over the lanes; *total = sum over the warp.
+__device__ __forceinline__ int prefix_sum_excl(int v, int lane, int *total) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+
+// One ranked breadth-first search + augmentation, run by the whole warp: rank r of a level lives in lane r
+// (and lane r - 32 for r >= 32).  "The highest-ranked pusher wins" is an exclusive suffix OR over the ranks,
+// "next level in (parent rank, column index) order" an exclusive prefix sum of the claim counts.  free_x /
+// free_y (unmatched rows / columns) are replicated in every lane.  Returns true if the matching grew.
+__device__ bool augment_ranked(WarpScratch &s, int lane, mask_t &free_x, mask_t &free_y) {
+  if (!free_x) return false;
+  // level 1: the unmatched rows in index order
+  {
+    const int x0 = lane, x1 = lane + 32;
+    if ((free_x >> x0) & 1ull) s.level_x[__popcll(free_x & ((1ull << x0) - 1ull))] = x0;
+    if ((free_x >> x1) & 1ull) s.level_x[__popcll(free_x & ((1ull << x1) - 1ull))] = x1;
+  }
+  int n_lx = __popcll(free_x);
+  mask_t seen_y = 0;
+  __syncwarp();
+
+  for (;;) {
+    const bool two = n_lx > 32;  // warp-uniform
+    // ---- claims: c[r] = A[r] & ~(OR of A[r'] for r' > r), A[r] = residual neighbours of rank r not seen yet
+    mask_t A0 = 0, A1 = 0;
+    int px0 = -1, px1 = -1;
+    if (lane < n_lx) {
+      px0 = s.level_x[lane];
+      mask_t adj = s.eq[px0];
+      const int my = s.match_y[px0];
       if (my >= 0) adj &= ~(1ull << my);  // a saturated edge has no residual capacity
-      const mask_t c = adj & ~seen_y & ~level_claim;
-      s.claimed[r] = c;
-      level_claim |= c;
+      A0 = adj & ~seen_y;
     }
+    mask_t excl1 = 0, total1 = 0;
+    if (two) {
+      if (lane + 32 < n_lx) {
+        px1 = s.level_x[lane + 32];
+        mask_t adj = s.eq[px1];
+        const int my = s.match_y[px1];
+        if (my >= 0) adj &= ~(1ull << my);
+        A1 = adj & ~seen_y;
+      }
+      const mask_t S1 = suffix_or(A1, lane);
+      excl1 = shfl_down64(S1, 1);
+      if (lane == 31) excl1 = 0;
+      total1 = shfl64(S1, 0);
+    }
+    const mask_t S0 = suffix_or(A0, lane);
+    mask_t excl0 = shfl_down64(S0, 1);
+    if (lane == 31) excl0 = 0;
+    excl0 |= total1;
+    const mask_t level_claim = shfl64(S0, 0) | total1;
     if (!level_claim) return false;
     seen_y |= level_claim;
+    const mask_t c0 = A0 & ~excl0, c1 = A1 & ~excl1;
 
-    // next level in (parent rank, column index) order; remember the last free column
-    int n_ly = 0;
-    int last_free_y = -1;
-    for (int r = 0; r < n_lx; ++r) {
-      mask_t c = s.claimed[r];
-      const int px = s.level_x[r];
-      while (c) {
+    // ---- next level in (parent rank, column index) order
+    int tot0 = 0, tot1 = 0;
+    int pos0 = prefix_sum_excl(__popcll(c0), lane, &tot0);
+    for (mask_t c = c0; c; c &= c - 1) {
+      const int y = __ffsll((long long)c) - 1;
+      s.parent_y[y] = px0;
+      s.level_y[pos0++] = y;
+    }
+    if (two) {
+      int pos1 = tot0 + prefix_sum_excl(__popcll(c1), lane, &tot1);
+      for (mask_t c = c1; c; c &= c - 1) {
         const int y = __ffsll((long long)c) - 1;
-        c &= c - 1;
-        s.parent_y[y] = px;
-        s.level_y[n_ly++] = y;
-        if (s.match_x[y] < 0) last_free_y = y;
+        s.parent_y[y] = px1;
+        s.level_y[pos1++] = y;
       }
     }
+    const int n_ly = tot0 + tot1;
+    __syncwarp();
 
-    if (last_free_y >= 0) {  // the sink is reached from the highest-ranked free column
-      int y = last_free_y;
-      for (;;) {
-        const int x = s.parent_y[y];
-        const int prev = s.match_y[x];
-        s.match_y[x] = y;
-        s.match_x[y] = x;
-        if (prev < 0) break;
-        y = prev;
+    // ---- the sink is reached from the highest-ranked free column: highest rank, then highest index
+    int last_free_y = -1;
+    {
+      const mask_t f0 = c0 & free_y, f1 = c1 & free_y;
+      const unsigned b1 = two ? __ballot_sync(0xffffffffu, f1 != 0) : 0u;
+      if (b1) {
+        const int src = 31 - __clz((int)b1);
+        last_free_y = 63 - __clzll((long long)shfl64(f1, src));
+      } else {
+        const unsigned b0 = __ballot_sync(0xffffffffu, f0 != 0);
+        if (b0) {
+          const int src = 31 - __clz((int)b0);
+          last_free_y = 63 - __clzll((long long)shfl64(f0, src));
+        }
       }
+    }
+    if (last_free_y >= 0) {
+      int x_start = 0;
+      if (lane == 0) {
+        int y = last_free_y;
+        for (;;) {
+          const int x = s.parent_y[y];
+          const int prev = s.match_y[x];
+          s.match_y[x] = y;
+          s.match_x[y] = x;
+          if (prev < 0) {
+            x_start = x;
+            break;
+          }
+          y = prev;
+        }
+      }
+      x_start = __shfl_sync(0xffffffffu, x_start, 0);
+      free_x &= ~(1ull << x_start);
+      free_y &= ~(1ull << last_free_y);
+      __syncwarp();
       return true;
     }
-    // all columns of the level are matched: follow the matched edges back into X
-    n_lx = 0;
-    for (int r = 0; r < n_ly; ++r) s.level_x[n_lx++] = s.match_x[s.level_y[r]];
+    // ---- all columns of the level are matched: follow the matched edges back into X
+    if (lane < n_ly) s.level_x[lane] = s.match_x[s.level_y[lane]];
+    if (lane + 32 < n_ly) s.level_x[lane + 32] = s.match_x[s.level_y[lane + 32]];
+    n_lx = n_ly;
+    __syncwarp();
   }
-  return false;
 }
 
 // iou/s_gt == nullptr: plain op (W given).  Otherwise f_segm_match: W is built from iou and
@@ -142,7 +227,10 @@ __global__ void __launch_bounds__(32) hungarian_kernel(const float *__restrict__
 
   mask_t S = 0, T = 0;
   bool next_match = true;
+  bool eq_stale = true;  // the equality graph is a function of (covers, w): rebuild it only after a cover update
   int status = 0;
+  const mask_t all_x = nx == 64 ? ~0ull : ((1ull << nx) - 1ull);
+  const mask_t all_y = ny == 64 ? ~0ull : ((1ull << ny) - 1ull);
 
   for (int round = 0;; ++round) {
     if (round == kMaxRounds) {  // hungarian.cc:362-377: give back the unfinished matching
@@ -151,7 +239,7 @@ __global__ void __launch_bounds__(32) hungarian_kernel(const float *__restrict__
     }
     // ---- equality graph (hungarian.cc:309-325).  `<= 1e-6` on the double literal is the same
     // set of floats as `<= 1e-6f` (the float below 1e-6; tests/test_hungarian_oracle.py).
-    {
+    if (eq_stale) {
       const float cy0 = s.cy[y0], cy1 = s.cy[y1];
       for (int x = 0; x < nx; ++x) {
         const float c = s.cx[x];
@@ -160,37 +248,33 @@ __global__ void __launch_bounds__(32) hungarian_kernel(const float *__restrict__
           const float d = __fsub_rn(__fadd_rn(c, cy0), w[x * ny + y0]);
           p0 = (fabsf(d) <= 1e-6f) && (c > 0.f || cy0 > 0.f);
         }
-        if (has1) {
-          const float d = __fsub_rn(__fadd_rn(c, cy1), w[x * ny + y1]);
-          p1 = (fabsf(d) <= 1e-6f) && (c > 0.f || cy1 > 0.f);
-        }
         const unsigned m0 = __ballot_sync(0xffffffffu, p0);
-        const unsigned m1 = __ballot_sync(0xffffffffu, p1);
+        unsigned m1 = 0u;
+        if (ny > 32) {  // warp-uniform
+          if (has1) {
+            const float d = __fsub_rn(__fadd_rn(c, cy1), w[x * ny + y1]);
+            p1 = (fabsf(d) <= 1e-6f) && (c > 0.f || cy1 > 0.f);
+          }
+          m1 = __ballot_sync(0xffffffffu, p1);
+        }
         if (lane == 0) s.eq[x] = (mask_t)m0 | ((mask_t)m1 << 32);
       }
+      eq_stale = false;
+      __syncwarp();
     }
-    __syncwarp();
 
     if (next_match) {
-      if (lane == 0) {
-        for (int x = 0; x < nx; ++x) s.match_y[x] = -1;
-        for (int y = 0; y < ny; ++y) s.match_x[y] = -1;
-        while (augment_ranked(s, nx)) {
-        }
-        int n_matched = 0, first_free = -1;
-        for (int x = 0; x < nx; ++x) {
-          if (s.match_y[x] >= 0)
-            ++n_matched;
-          else if (first_free < 0)
-            first_free = x;
-        }
-        s.n_matched = n_matched;
-        s.first_free = first_free;
-      }
+      s.match_y[y0] = -1;
+      s.match_y[y1] = -1;
+      s.match_x[y0] = -1;
+      s.match_x[y1] = -1;
       __syncwarp();
+      mask_t free_x = all_x, free_y = all_y;
+      while (augment_ranked(s, lane, free_x, free_y)) {
+      }
       // hungarian.cc:219-248: the smaller side must be fully matched
-      if (s.n_matched == (nx >= ny ? ny : nx)) break;
-      S = 1ull << s.first_free;
+      if (nx - __popcll(free_x) == (nx >= ny ? ny : nx)) break;
+      S = 1ull << (__ffsll((long long)free_x) - 1);  // first unmatched row, hungarian.cc:394-403
       T = 0;
     }
 
@@ -218,6 +302,7 @@ __global__ void __launch_bounds__(32) hungarian_kernel(const float *__restrict__
       if (y1 < nx && ((S >> y1) & 1ull)) s.cx[y1] = __fsub_rn(s.cx[y1], a);
       if (has0 && ((T >> y0) & 1ull)) s.cy[y0] = __fadd_rn(s.cy[y0], a);
       if (has1 && ((T >> y1) & 1ull)) s.cy[y1] = __fadd_rn(s.cy[y1], a);
+      eq_stale = true;
       __syncwarp();
     } else {
       // hungarian.cc:446-482: pull matched columns of N(S) into T, their rows into S

@@ -88,12 +88,60 @@ struct IouParams {
   float hard_thr;
 };
 
+__device__ __forceinline__ void cp_async16(float *dst_smem, const float *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+
+// Stage chunk k0 of both operands into (A_s, B_s): rows of real masks by cp.async (16 B, L2 only: the data is read
+// once), the ones row / zero padding rows / rectangle indicators / ragged tail by plain stores.
+__device__ __forceinline__ void iou_stage(const IouParams &p, int b, int k0, int NP, int MP, float *A_s, float *B_s) {
+  const int HW = p.H * p.W, ld = kKC + kPad, tid = threadIdx.x;
+  for (int idx = tid; idx < NP * (kKC / 4); idx += blockDim.x) {
+    const int r = idx / (kKC / 4), q = (idx - r * (kKC / 4)) * 4;
+    const int k = k0 + q;
+    float *dst = A_s + r * ld + q;
+    if (r < p.N && k < HW) {
+      cp_async16(dst, p.a + ((size_t)b * p.N + r) * HW + k);
+    } else {
+      const float o = (r == p.N && k < HW) ? 1.f : 0.f;
+      *reinterpret_cast<float4 *>(dst) = make_float4(o, o, o, o);
+    }
+  }
+  for (int idx = tid; idx < MP * (kKC / 4); idx += blockDim.x) {
+    const int r = idx / (kKC / 4), q = (idx - r * (kKC / 4)) * 4;
+    const int k = k0 + q;
+    float *dst = B_s + r * ld + q;
+    if (r < p.M && k < HW && p.b_rect == nullptr) {
+      cp_async16(dst, p.b + ((size_t)b * p.M + r) * HW + k);
+    } else {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < HW) {
+        if (r < p.M) {
+          const float *rc = p.b_rect + ((size_t)b * p.M + r) * 4;
+          const float ty = rc[0], tx = rc[1], by = rc[2], bx = rc[3];
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float fy = (float)((k + e) / p.W), fx = (float)((k + e) % p.W);
+            o[e] = (fy >= ty && fx >= tx && fy <= by && fx <= bx) ? 1.f : 0.f;
+          }
+          v = make_float4(o[0], o[1], o[2], o[3]);
+        } else if (r == p.M) {
+          v = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      }
+      *reinterpret_cast<float4 *>(dst) = v;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256) pairwise_iou_kernel(IouParams p) {
   extern __shared__ __align__(16) float smem[];
   const int NP = p.NB * kR, MP = p.MB * kR;
   const int ld = kKC + kPad;
-  float *A_s = smem;            // [NP][ld]
-  float *B_s = smem + NP * ld;  // [MP][ld]
+  const int buf_floats = (NP + MP) * ld;  // one stage: A rows [NP][ld] then B rows [MP][ld]; two stages
   const int b = blockIdx.y;
   const int HW = p.H * p.W;
   const int tid = threadIdx.x;
@@ -101,6 +149,7 @@ __global__ void __launch_bounds__(256) pairwise_iou_kernel(IouParams p) {
   const int blk = tid / p.KS;
   const int nb = blk / p.MB, mb = blk % p.MB;
   const bool active = blk < p.NB * p.MB;
+  const bool hard = p.hard_thr > 0.f;
 
   float acc[kR][kR];
 #pragma unroll
@@ -109,54 +158,19 @@ __global__ void __launch_bounds__(256) pairwise_iou_kernel(IouParams p) {
     for (int j = 0; j < kR; ++j) acc[i][j] = 0.f;
 
   const int chunk0 = blockIdx.x * p.chunks_per_cta;
-  for (int ch = 0; ch < p.chunks_per_cta; ++ch) {
-    const int k0 = (chunk0 + ch) * kKC;
-    if (k0 >= HW) break;
-    __syncthreads();
-    // stage A rows (N real rows, the ones row, zero padding)
-    for (int idx = tid; idx < NP * (kKC / 4); idx += blockDim.x) {
-      const int r = idx / (kKC / 4), q = (idx - r * (kKC / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int k = k0 + q;
-      if (k < HW) {
-        if (r < p.N) {
-          v = __ldcs(reinterpret_cast<const float4 *>(p.a + ((size_t)b * p.N + r) * HW + k));
-          if (p.hard_thr > 0.f) {
-            v.x = v.x > p.hard_thr ? 1.f : 0.f;
-            v.y = v.y > p.hard_thr ? 1.f : 0.f;
-            v.z = v.z > p.hard_thr ? 1.f : 0.f;
-            v.w = v.w > p.hard_thr ? 1.f : 0.f;
-          }
-        } else if (r == p.N) {
-          v = make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-      }
-      *reinterpret_cast<float4 *>(A_s + r * ld + q) = v;
-    }
-    for (int idx = tid; idx < MP * (kKC / 4); idx += blockDim.x) {
-      const int r = idx / (kKC / 4), q = (idx - r * (kKC / 4)) * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int k = k0 + q;
-      if (k < HW) {
-        if (r < p.M) {
-          if (p.b_rect != nullptr) {
-            const float *rc = p.b_rect + ((size_t)b * p.M + r) * 4;
-            const float ty = rc[0], tx = rc[1], by = rc[2], bx = rc[3];
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float fy = (float)((k + e) / p.W), fx = (float)((k + e) % p.W);
-              o[e] = (fy >= ty && fx >= tx && fy <= by && fx <= bx) ? 1.f : 0.f;
-            }
-            v = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-            v = __ldcs(reinterpret_cast<const float4 *>(p.b + ((size_t)b * p.M + r) * HW + k));
-          }
-        } else if (r == p.M) {
-          v = make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-      }
-      *reinterpret_cast<float4 *>(B_s + r * ld + q) = v;
+  int n_ch = 0;
+  for (int ch = 0; ch < p.chunks_per_cta; ++ch)
+    if ((chunk0 + ch) * kKC < HW) n_ch = ch + 1;
+  if (n_ch > 0) iou_stage(p, b, chunk0 * kKC, NP, MP, smem, smem + NP * ld);
+  for (int ch = 0; ch < n_ch; ++ch) {
+    float *A_s = smem + (ch & 1) * buf_floats;
+    float *B_s = A_s + NP * ld;
+    if (ch + 1 < n_ch) {  // prefetch the next chunk into the other stage while this one is consumed
+      float *A_n = smem + ((ch + 1) & 1) * buf_floats;
+      iou_stage(p, b, (chunk0 + ch + 1) * kKC, NP, MP, A_n, A_n + NP * ld);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (active) {
@@ -166,6 +180,15 @@ __global__ void __launch_bounds__(256) pairwise_iou_kernel(IouParams p) {
         for (int i = 0; i < kR; ++i) av[i] = *reinterpret_cast<const float4 *>(A_s + (nb * kR + i) * ld + q);
 #pragma unroll
         for (int j = 0; j < kR; ++j) bv[j] = *reinterpret_cast<const float4 *>(B_s + (mb * kR + j) * ld + q);
+        if (hard) {  // thresholded masks (the ones row stays 1, padding stays 0: thr is in (0, 1))
+#pragma unroll
+          for (int i = 0; i < kR; ++i) {
+            av[i].x = av[i].x > p.hard_thr ? 1.f : 0.f;
+            av[i].y = av[i].y > p.hard_thr ? 1.f : 0.f;
+            av[i].z = av[i].z > p.hard_thr ? 1.f : 0.f;
+            av[i].w = av[i].w > p.hard_thr ? 1.f : 0.f;
+          }
+        }
 #pragma unroll
         for (int i = 0; i < kR; ++i)
 #pragma unroll
@@ -177,6 +200,7 @@ __global__ void __launch_bounds__(256) pairwise_iou_kernel(IouParams p) {
           }
       }
     }
+    __syncthreads();  // the stage is refilled by the next iteration's prefetch
   }
   // reduce the KS k-slices of every (nb, mb) block through shared memory, fixed order
   __syncthreads();
@@ -455,7 +479,9 @@ extern "C" int ra_pairwise_iou_f32(const float *a, const float *b, const float *
                                    int W, float hard_threshold, float *partial, float *iou, float *dice, void *stream) {
   if (!a || (!b && !b_rect) || !partial || !iou || B < 0 || N < 1 || M < 1 || H < 1 || W < 1)
     return RA_ERR_INVALID_ARG;
-  if (((size_t)H * W) % 4 != 0) return RA_ERR_UNSUPPORTED;
+  if (((size_t)H * W) % 4 != 0 || hard_threshold >= 1.0f) return RA_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(a) & 15) != 0 || (b != nullptr && (reinterpret_cast<uintptr_t>(b) & 15) != 0))
+    return RA_ERR_INVALID_ARG;  // 16-byte cp.async
   IouParams p;
   int rc = iou_plan(N, M, H * W, &p);
   if (rc != RA_OK) return rc;
@@ -470,12 +496,12 @@ extern "C" int ra_pairwise_iou_f32(const float *a, const float *b, const float *
   p.W = W;
   p.hard_thr = hard_threshold;
   const int NP = p.NB * kR, MP = p.MB * kR;
-  size_t smem = (size_t)(NP + MP) * (kKC + kPad) * sizeof(float);
+  size_t smem = (size_t)2 * (NP + MP) * (kKC + kPad) * sizeof(float);  // two stages
   const size_t red_bytes = (size_t)256 * kR * kR * sizeof(float);
   if (smem < red_bytes) smem = red_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pairwise_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(pairwise_iou_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
       ra::set_last_error("cudaFuncSetAttribute(pairwise_iou_kernel)", e);
       return RA_ERR_CUDA;

@@ -9,6 +9,8 @@ full_model.py:853-910,941-1081), weights imported by the flat ``weights.h5`` key
 librecattend_b200.so through the C ABI (ops.py); torch provides device memory, streams and
 (optionally) CUDA-graph capture of the whole T-step decode.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -95,6 +97,7 @@ class _ModelBase(object):
     self.w = None
     self.wd_term = 0.0
     self._bufs = {}
+    self.n_chains = int(os.environ.get('RA_CHAINS', '1'))  # sub-batch chains of the decode loop (see _chains)
 
   def _fixed_var(self):
     return bool(self.opt.get('fixed_var', False))
@@ -386,14 +389,75 @@ class FullModel(_ModelBase):
       _lib.TAG = 'paste_back'
       ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],
                      attn_box=bufs['attn_box'][:, t], y_out=bufs['y_out'][:, t], out_bstride=thw,
-                     disable_overwrite=self.disable_overwrite)
+                     disable_overwrite=self.disable_overwrite, band=bufs['band'])
 
-  def _loss(self, bufs, y_gt, s_gt, out, want_gt_box):
+  def _side_stream(self, bufs, i):
+    """Side streams become parallel branches of the captured CUDA graph; eager runs stay on one stream (the
+    caching allocator would need record_stream bookkeeping for cross-stream temporaries)."""
+    if not torch.cuda.is_current_stream_capturing():
+      return None
+    ss = bufs.setdefault('_side_streams', [])
+    while len(ss) <= i:
+      ss.append(torch.cuda.Stream())
+    ss[i].wait_stream(torch.cuda.current_stream())
+    return ss[i]
+
+  def _chains(self, B):
+    """The decode loop is a strictly serial chain of ~30 mostly latency-bound launches per step, but examples are
+    independent (eval mode): the batch can be cut into `n_chains` contiguous sub-batches whose chains run as
+    parallel branches of the CUDA graph.  MEASURED SLOWER on B200 at the bench config (18.1 ms -> 24.7 ms with 2
+    chains, 28.3 ms with 4; profiles/r01d_*): the per-launch cost of the persistent conv kernels does not overlap
+    across branches, so doubling the launches costs more than the concurrency gains.  Default 1; RA_CHAINS=n or
+    `model.n_chains` enables it (kept because it is the natural way to use a second GPU-side queue later)."""
+    n = max(1, int(self.n_chains))
+    while n > 1 and (B % n != 0):
+      n -= 1
+    step = B // n
+    return [(i * step, (i + 1) * step) for i in range(n)]
+
+  def _chain_views(self, bufs, st, b0, b1):
+    """Views of the per-batch buffers for examples [b0, b1) (batch-major buffers are sliced on dim 0, the
+    time-major per-step records on dim 1; a step's slice stays contiguous)."""
+    cb = {}
+    for k in ('xs', 'static_pre', 'canvas', 'fy', 'fx', 'band', 'attn_box', 's_out', 'y_out'):
+      cb[k] = bufs[k][b0:b1]
+    for k in ('ccnn', 'acnn', 'adcnn'):
+      cb[k] = [t[b0:b1] for t in bufs[k]]
+    for k in ('h_all', 'ctrl_out_all', 'gmap_all', 'box_all', 'x_patch_all', 'y_patch_all'):
+      cb[k] = bufs[k][:, b0:b1]
+    per_ex = bufs['extract_tmp'].numel() // bufs['canvas'].shape[0]
+    cb['extract_tmp'] = bufs['extract_tmp'][b0 * per_ex:b1 * per_ex]
+    cb['static_in'] = {k: v[b0:b1] for k, v in st.items() if k in ('x', 'd_in', 'y_in')}
+    return cb
+
+  def _gt_boxes(self, bufs, y_gt, want_gt_box):
+    """get_gt_attn (full_model.py:561-567) depends on y_gt only: it runs beside the decode loop."""
+    o = self.opt
+    side = self._side_stream(bufs, 0)
+    _lib.TAG = 'loss'
+    if side is None:
+      return ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'], min_padding=self.min_padding,
+                            want_box=want_gt_box), None
+    with torch.cuda.stream(side):
+      res = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'], min_padding=self.min_padding,
+                           want_box=want_gt_box)
+    return res, side
+
+  def _loss(self, bufs, y_gt, s_gt, out, gt):
     """full_model.py:916-1081 (matching on soft IoU, 'iou' losses, hard statistics)."""
     o = self.opt
     _lib.TAG = 'loss'
-    tl, br, box_gt, rect, area = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'],
-                                                min_padding=self.min_padding, want_box=want_gt_box)
+    cur = torch.cuda.current_stream()
+    (tl, br, box_gt, rect, area), gt_side = gt
+    # the hard-IoU statistics (full_model.py:1063-1081) do not feed the matching: a parallel branch
+    side = self._side_stream(bufs, 1)  # the chains have joined: their streams are free again
+    if side is None:
+      iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
+    else:
+      with torch.cuda.stream(side):
+        iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
+    if gt_side is not None:
+      cur.wait_stream(gt_side)
     # both matchings (boxes, masks) in ONE launch of 2B warps: they are independent and latency-bound
     B, T = s_gt.shape
     iou_both = torch.empty((2 * B, T, T), device=s_gt.device, dtype=torch.float32)
@@ -401,7 +465,8 @@ class FullModel(_ModelBase):
     iou_soft = ops.f_iou(bufs['y_out'], y_gt, out=iou_both[B:])
     match_both = ops.f_segm_match(iou_both, torch.cat([s_gt, s_gt], 0))
     match_box, match = match_both[:B], match_both[B:]
-    iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
+    if side is not None:
+      cur.wait_stream(side)
     scal = ops.loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice, bufs['s_out'], s_gt, area,
                           o['loss_mix_ratio'], self.wd_term)
     out.update({
@@ -415,8 +480,28 @@ class FullModel(_ModelBase):
   def _run(self, bufs, B, with_loss, want_all):
     """Enqueue one full forward on the current stream; returns the dict of (static) output tensors."""
     st = bufs['static_in']
-    self._prepare(bufs, st['x'], st.get('d_in'), st.get('y_in'))
-    self._decode(bufs, B)
+    gt = self._gt_boxes(bufs, st['y_gt'], want_all) if with_loss else None
+    chains = self._chains(B)
+    if len(chains) == 1:
+      self._prepare(bufs, st['x'], st.get('d_in'), st.get('y_in'))
+      self._decode(bufs, B)
+    else:
+      cur = torch.cuda.current_stream()
+      forked = []
+      for i, (b0, b1) in enumerate(chains):
+        cb = self._chain_views(bufs, st, b0, b1)
+        cst = cb['static_in']
+        side = self._side_stream(bufs, 1 + i) if i > 0 else None  # chain 0 stays on the capturing stream
+        if side is None:
+          self._prepare(cb, cst['x'], cst.get('d_in'), cst.get('y_in'))
+          self._decode(cb, b1 - b0)
+        else:
+          with torch.cuda.stream(side):
+            self._prepare(cb, cst['x'], cst.get('d_in'), cst.get('y_in'))
+            self._decode(cb, b1 - b0)
+          forked.append(side)
+      for side in forked:
+        cur.wait_stream(side)
     out = {}
     self._controller_outputs(bufs, out)
     out['y_out'] = bufs['y_out']
@@ -424,7 +509,7 @@ class FullModel(_ModelBase):
       out['x_patch'] = bufs['x_patch_all'][..., :self.D].permute(1, 0, 2, 3, 4).contiguous()
       out['y_out_patch'] = bufs['y_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
     if with_loss:
-      self._loss(bufs, st['y_gt'], st['s_gt'], out, want_gt_box=want_all)
+      self._loss(bufs, st['y_gt'], st['s_gt'], out, gt)
       scal = out['loss_scalars']
       for i, k in enumerate(LOSS_KEYS):
         out[k] = scal[i]

@@ -225,15 +225,17 @@ def extract_patch(xs, canvas, chan_map, box, fy, fx, band, tmp=None, out=None):
   return out
 
 
-def paste_back(patch, box, fy, fx, canvas, attn_box=None, y_out=None, out_bstride=None, disable_overwrite=False):
+def paste_back(patch, box, fy, fx, canvas, attn_box=None, y_out=None, out_bstride=None, disable_overwrite=False,
+               band=None):
   """full_model.py:738-741 (attention box), :810-818 (mask) and :845 (canvas = max) fused.
-  attn_box / y_out may be views of step t of a [B,T,H,W] stack (pass out_bstride = T*H*W)."""
+  attn_box / y_out may be views of step t of a [B,T,H,W] stack (pass out_bstride = T*H*W).
+  `band` (from get_gaussian_filter) enables the constant fast path for tiles outside the box."""
   B, F, H = fy.shape
   W = fx.shape[2]
   if out_bstride is None:
     out_bstride = H * W
-  _chk(patch, box, fy, fx, canvas)
-  _lib.call('ra_paste_back_f32', _p(patch), _p(box), _p(fy), _p(fx), B, H, W, F, 1 if disable_overwrite else 0,
+  _chk(patch, box, fy, fx, canvas, band)
+  _lib.call('ra_paste_back_f32', _p(patch), _p(box), _p(fy), _p(fx), _p(band), B, H, W, F, 1 if disable_overwrite else 0,
             _p(attn_box), _p(y_out), out_bstride, _p(canvas), _stream())
 
 

@@ -137,3 +137,30 @@ def test_box_model_parity(cuda, H, W, T, B, noise):
   assert (out['match_box'].cpu().numpy() == ref['match_box'].numpy()).all()
   for k in ('box_loss', 'conf_loss', 'loss'):
     assert abs(float(out[k]) - float(ref[k])) <= MODEL_TOL * max(1.0, abs(float(ref[k]))), k
+
+
+@pytest.mark.parametrize('use_graph', [True, False])
+def test_sub_batch_chains_agree(cuda, use_graph):
+  """FullModel._chains: the decode loop cut into 1, 2 or 4 parallel sub-batch chains (CUDA-graph branches) gives
+  the same outputs - examples are independent in eval mode.  (Tile plans depend on the sub-batch size, so the
+  comparison is to fp32 round-off, not bit-exact; matchings must be identical.)"""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt('kitti', 64, 128, 5)
+  batch = ra.synthetic.make_batch(opt, 4, seed=77)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  outs = []
+  for n in (1, 2, 4):
+    model = FullModel(opt).load_weights(weights)
+    model.n_chains = n
+    assert len(model._chains(4)) == n and len(model._chains(3)) in (1, 3)
+    out = model.forward(batch, use_graph=use_graph)
+    if use_graph:
+      out = model.forward(batch, use_graph=True)  # replay of the captured graph (parallel branches)
+    torch.cuda.synchronize()
+    outs.append({k: out[k].detach().cpu().numpy().copy() for k in ('y_out', 's_out', 'attn_box', 'x_patch', 'match',
+                                                                    'match_box', 'loss', 'canvas')})
+  for o in outs[1:]:
+    for k in ('y_out', 's_out', 'attn_box', 'x_patch', 'loss', 'canvas'):
+      assert rel_err(o[k], outs[0][k]) < 1e-4, k
+    assert (o['match'] == outs[0]['match']).all() and (o['match_box'] == outs[0]['match_box']).all()

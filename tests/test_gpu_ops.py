@@ -233,13 +233,13 @@ def test_controller_step(ops, arch, H, W):
 
 
 # ----------------------------------------------------------------------------- attention
-def _boxes(rng, B, H, W, dense=False):
+def _boxes(rng, B, H, W, dense=False, small=False):
   from rec_attend_b200 import _lib
   box = np.zeros((B, _lib.BOX_STRIDE), np.float32)
   box[:, 0] = rng.uniform(-0.1 * H, 1.1 * H, B)
   box[:, 1] = rng.uniform(-0.1 * W, 1.1 * W, B)
-  box[:, 2] = rng.uniform(0.05 * H, 1.3 * H, B)
-  box[:, 3] = rng.uniform(0.05 * W, 1.3 * W, B)
+  box[:, 2] = rng.uniform(0.05 * H, (0.3 if small else 1.3) * H, B)
+  box[:, 3] = rng.uniform(0.05 * W, (0.3 if small else 1.3) * W, B)
   box[:, 4:6] = rng.uniform(-1.0, 2.5, (B, 2)) if not dense else rng.uniform(5.0, 7.0, (B, 2))
   box[:, 6] = rng.uniform(0.5, 2.0, B)
   box[:, 7] = rng.uniform(20, 200, B)
@@ -248,12 +248,15 @@ def _boxes(rng, B, H, W, dense=False):
 
 
 @pytest.mark.parametrize('H,W,Cs,dense', [(64, 128, 12, False), (128, 128, 3, False), (32, 64, 12, True),
-                                          (64, 64, 20, False)])
+                                          (64, 64, 20, False), (128, 512, 12, 'small'), (96, 384, 3, 'small')])
 def test_gaussian_filters_extract_paste(ops, H, W, Cs, dense):
   rng = np.random.default_rng(H * 1000 + W + Cs)
   B, F = 3, 48
   D = Cs + 1
-  box = _boxes(rng, B, H, W, dense)
+  # 'small': boxes that leave most 8x128 paste-back tiles / extract column chunks outside every tap's band
+  box = _boxes(rng, B, H, W, dense is True, small=(dense == 'small'))
+  if dense == 'small':
+    box[0, 0:2] = [-0.4 * H, 0.5 * W]  # one box (almost) entirely off the image
   bt = torch.from_numpy(box)
   fy, fx, band = ops.get_gaussian_filter(_g(box), H, W, F)
   fy_o = OM.get_gaussian_filter(bt[:, 0], bt[:, 2], bt[:, 4], H, F)  # [B,H,F]
@@ -273,13 +276,13 @@ def test_gaussian_filters_extract_paste(ops, H, W, Cs, dense):
   assert rel_err(patch.cpu().numpy(), ref.numpy()) < TOL
   # paste-back + canvas update, both overwrite modes
   P = np.maximum(rng.standard_normal((B, F, F)), 0).astype(np.float32)
-  for dis in (False, True):
+  for dis, bnd in ((False, band), (True, band), (False, None), (True, None)):
     cv = _g(canvas.copy())
     T = 2
     attn_box = torch.zeros((B, T, H, W), device='cuda')
     y_out = torch.zeros((B, T, H, W), device='cuda')
     ops.paste_back(_g(P), _g(box), fy, fx, cv, attn_box=attn_box[:, 1], y_out=y_out[:, 1], out_bstride=T * H * W,
-                   disable_overwrite=dis)
+                   disable_overwrite=dis, band=bnd)
     y_ref = OM.extract_patch(torch.from_numpy(P).unsqueeze(3), fy_o.transpose(1, 2), fx_o.transpose(1, 2), 1)[..., 0]
     y_ref = torch.sigmoid(bt[:, 8].view(-1, 1, 1) * y_ref - 5.0)
     if dis:
@@ -293,8 +296,10 @@ def test_gaussian_filters_extract_paste(ops, H, W, Cs, dense):
     assert rel_err(cv.cpu().numpy(), torch.maximum(torch.from_numpy(canvas), y_ref).numpy()) < TOL
   # attention box only (box model)
   only = torch.zeros((B, 1, H, W), device='cuda')
-  ops.paste_back(None, _g(box), fy, fx, None, attn_box=only[:, 0], y_out=None, out_bstride=H * W)
-  assert rel_err(only[:, 0].cpu().numpy(), b_ref.numpy()) < TOL
+  for bnd in (None, band):
+    only.zero_()
+    ops.paste_back(None, _g(box), fy, fx, None, attn_box=only[:, 0], y_out=None, out_bstride=H * W, band=bnd)
+    assert rel_err(only[:, 0].cpu().numpy(), b_ref.numpy()) < TOL
 
 
 def test_score(ops):
@@ -483,3 +488,87 @@ def test_canvas_conv(ops, C0, pool, H, W):
     ref = OM.max_pool_same(ref, 2)
   out = ops.canvas_conv(_g(pre), _g(canvas), _g(w), _g(scale), _g(shift), pool=pool)
   assert rel_err(out.cpu().numpy(), ref.numpy()) < TOL
+
+
+# ----------------------------------------------------------------------------- post-processing
+def _pp_golden():
+  import os
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'postprocess_golden.npz'))
+  for i in range(int(g['n_cases'])):
+    p = 'c%d_' % i
+    yield (g[p + 'y_out'], g[p + 's_out'], g[p + 'fg'] if p + 'fg' in g.files else None, float(g[p + 'thresh']),
+           int(g[p + 'tiny']), g[p + 'dense'], g[p + 'conf'], g[p + 'area'])
+
+
+def test_postprocess_reference_golden(ops):
+  """ra_postprocess_f32 against outputs of the reference's own utils/postprocess.py (tests/golden)."""
+  from rec_attend_b200 import postprocess as PP
+  from oracle import postprocess as OP
+  for y, s, fg, thresh, tiny, dense, conf, area in _pp_golden():
+    out = PP.postprocess(_g(y), _g(s), thresh, fg=None if fg is None else _g(fg), remove_tiny=tiny, want_dense=True)
+    assert (out['y_out_thresh'].cpu().numpy() == dense).all()
+    assert (out['conf'].cpu().numpy() == conf).all()
+    assert rel_err(out['area'].cpu().numpy(), area) < 1e-6
+    binary_fg = fg is None or set(np.unique(fg)) <= {0.0, 1.0}
+    if binary_fg:
+      assert (out['area'].cpu().numpy() == area).all()
+    assert (out['label'].cpu().numpy() == OP.label_map(dense)).all()
+
+
+@pytest.mark.parametrize('B,T,H,W,tiny', [(3, 20, 64, 96, 0), (2, 32, 48, 64, 30), (4, 7, 30, 44, 15), (1, 64, 16, 16, 0)])
+def test_postprocess_vs_oracle(ops, B, T, H, W, tiny):
+  from rec_attend_b200 import postprocess as PP
+  from oracle import postprocess as OP
+  rng = np.random.default_rng(B * 100 + T)
+  y = rng.random((B, T, H, W)).astype(np.float32)**3
+  y[:, T // 2] = y[:, 0]  # exact ties: the first maximum must win
+  s = rng.uniform(0.3, 1.0, (B, T)).astype(np.float32)
+  s[:, T // 2] = s[:, 0]
+  fg = (rng.random((B, H, W)) > 0.2).astype(np.float32)
+  for use_fg in (False, True):
+    dense, conf, area = OP.eval_chain(y, s, 0.3, fg if use_fg else None, tiny)
+    out = PP.postprocess(_g(y), _g(s), 0.3, fg=_g(fg) if use_fg else None, remove_tiny=tiny, want_dense=True)
+    assert (out['label'].cpu().numpy() == OP.label_map(dense)).all()
+    assert (out['y_out_thresh'].cpu().numpy() == dense).all()
+    assert (out['conf'].cpu().numpy() == conf).all() and (out['area'].cpu().numpy() == area).all()
+    lab_only = PP.postprocess(_g(y), _g(s), 0.3, fg=_g(fg) if use_fg else None, remove_tiny=tiny)
+    assert (lab_only['label'].cpu().numpy() == OP.label_map(dense)).all()
+
+
+def test_postprocess_full_size_properties(ops):
+  """BASELINE config-3 size (T=20, 256x512): size-independent properties instead of the (slow) numpy oracle."""
+  from rec_attend_b200 import postprocess as PP
+  B, T, H, W = 4, 20, 256, 512
+  gen = torch.Generator(device='cuda').manual_seed(5)
+  y = torch.rand((B, T, H, W), device='cuda', generator=gen)
+  s = torch.rand((B, T), device='cuda', generator=gen) * 0.6 + 0.4
+  out = PP.postprocess(y, s, 0.3, remove_tiny=0, want_dense=True)
+  lab, dense, area = out['label'], out['y_out_thresh'], out['area']
+  v = y * s.view(B, T, 1, 1)
+  ref_lab = torch.where(v.max(dim=1).values.double() > 0.3, v.argmax(dim=1) + 1, torch.zeros_like(lab, dtype=torch.int64))
+  # torch.argmax does not promise the first maximum on ties; random floats make ties vanishingly rare
+  assert float((lab.long() == ref_lab).float().mean()) > 0.99999
+  assert (dense.sum(dim=1) <= 1).all()                                         # one label per pixel
+  assert (dense.sum(dim=(2, 3)) == area).all()                                  # areas are the dense sums
+  assert int((lab > 0).sum()) == int(area.sum())                                # checksum of checksums
+  onehot = torch.stack([(lab == t + 1) for t in range(T)], 1).float()
+  assert (onehot == dense).all()
+  # idempotence: the dense masks are a fixed point (confidence 1, same threshold)
+  again = PP.postprocess(dense, torch.ones_like(s), 0.3, want_dense=True)
+  assert (again['label'] == lab).all() and (again['y_out_thresh'] == dense).all()
+  # removing everything below a huge threshold empties the map and zeroes the confidences
+  none = PP.postprocess(y, s, 0.3, remove_tiny=H * W)
+  assert int(none['label'].abs().sum()) == 0 and float(none['conf'].abs().sum()) == 0.0
+
+
+def test_postprocess_errors(ops):
+  from rec_attend_b200 import _lib, postprocess as PP
+  y = torch.zeros((1, 65, 8, 8), device='cuda')
+  with pytest.raises(_lib.RecAttendError):
+    PP.postprocess(y, torch.zeros((1, 65), device='cuda'))          # T > 64
+  with pytest.raises(_lib.RecAttendError):
+    PP.postprocess(torch.zeros((1, 2, 3, 3), device='cuda'), torch.zeros((1, 2), device='cuda'))  # H*W % 4
+  with pytest.raises(_lib.RecAttendError):
+    PP.postprocess(torch.zeros((1, 2, 4, 4), device='cuda'), torch.zeros((1, 3), device='cuda'))
+  out = PP.postprocess(torch.zeros((0, 2, 4, 4), device='cuda'), torch.zeros((0, 2), device='cuda'))
+  assert tuple(out['label'].shape) == (0, 4, 4)
