@@ -314,8 +314,22 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
     {
       const int c = tid % kCf2, sl = tid / kCf2;  // 4 slices over p
       float a = 0.f;
-      if (own)
-        for (int q = sl; q < P; q += 4) a = fmaf(__ldg(feat + (size_t)q * kCf2 + c), lg_s[q], a);
+      if (own) {
+        // 8 independent loads in flight (the first iteration of a launch reads feat from L2, not L1)
+        float a4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a4[j] = 0.f;
+        int q = sl;
+        for (; q + 28 < P; q += 32) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __ldg(feat + (size_t)(q + 4 * j) * kCf2 + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a4[j] = fmaf(f[j], lg_s[q + 4 * j], a4[j]);
+        }
+        for (; q < P; q += 4) a4[0] = fmaf(__ldg(feat + (size_t)q * kCf2 + c), lg_s[q], a4[0]);
+        a = ((a4[0] + a4[1]) + (a4[2] + a4[3])) + ((a4[4] + a4[5]) + (a4[6] + a4[7]));
+      }
       part_s[tid] = a;
       __syncthreads();
       if (tid < kCf2) {
@@ -333,6 +347,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
 #pragma unroll
       for (int e = 0; e < kCl; ++e) acc[e] = 0.f;
       const int k0 = kh * (kKin / 2);
+#pragma unroll 4
       for (int k = k0; k < k0 + kKin / 2; ++k) {
         const float w = wg_s[k * (4 * kUnits) + col];
         const float *v = (k < kCf2) ? (x_s + k * kCl) : (h_cur + (k - kCf2) * kCl);
@@ -376,6 +391,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
     {
       const int u = tid % kUnits, e = tid / kUnits;
       float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
       for (int k = 0; k < kHd2; k += 2) {
         a0 = fmaf(h_new[k * kCl + e], w0_s[k * kUnits + u], a0);
         a1 = fmaf(h_new[(k + 1) * kCl + e], w0_s[(k + 1) * kUnits + u], a1);
@@ -388,17 +404,51 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
     cluster.sync();
 
     // ---- step 4: glimpse MLP layer 1 logits for my PS positions x 8 examples -> owner CTAs
-    for (int o = tid; o < PS * kCl; o += 256) {
+    // The weights come straight from global memory (no shared memory left for them): 8 independent loads are kept
+    // in flight, and when the CTA has at most 128 outputs the 256 inputs are split over two thread halves.
+    if (PS * kCl <= 128) {
+      const int o = tid & 127, kh = tid >> 7;
       const int pos = o % PS, e = o / PS;
       const int gp = r * PS + pos;
-      if (gp < P) {
-        float a0 = 0.f, a1 = 0.f;
+      const bool live = o < PS * kCl && gp < P;
+      float a = 0.f;
+      if (live) {
         const float *wq = p.gw1 + gp;
-        for (int k = 0; k < kHd2; k += 2) {
-          a0 = fmaf(t_s[k * kCl + e], __ldg(wq + (size_t)k * P), a0);
-          a1 = fmaf(t_s[(k + 1) * kCl + e], __ldg(wq + (size_t)(k + 1) * P), a1);
+        float a8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] = 0.f;
+        const int k0 = kh * (kHd2 / 2);
+        for (int k = k0; k < k0 + kHd2 / 2; k += 8) {
+          float wv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wv[j] = __ldg(wq + (size_t)(k + j) * P);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a8[j] = fmaf(t_s[(k + j) * kCl + e], wv[j], a8[j]);
         }
-        cluster.map_shared_rank(lg_s, e)[gp] = (a0 + a1) + __ldg(p.gb1 + gp);
+        a = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+      }
+      part_s[tid] = a;
+      __syncthreads();
+      if (live && kh == 0) cluster.map_shared_rank(lg_s, e)[gp] = (part_s[o] + part_s[o + 128]) + __ldg(p.gb1 + gp);
+    } else {
+      for (int o = tid; o < PS * kCl; o += 256) {
+        const int pos = o % PS, e = o / PS;
+        const int gp = r * PS + pos;
+        if (gp < P) {
+          const float *wq = p.gw1 + gp;
+          float a8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a8[j] = 0.f;
+          for (int k = 0; k < kHd2; k += 8) {
+            float wv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wv[j] = __ldg(wq + (size_t)(k + j) * P);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a8[j] = fmaf(t_s[(k + j) * kCl + e], wv[j], a8[j]);
+          }
+          cluster.map_shared_rank(lg_s, e)[gp] =
+              (((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]))) + __ldg(p.gb1 + gp);
+        }
       }
     }
     cluster.sync();

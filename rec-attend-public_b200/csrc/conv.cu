@@ -200,13 +200,14 @@ constexpr int kCcThreads = 256;
 constexpr int kCcMaxCols = kCcThreads / 2 * 2 + 2;  // widest strip: C0 = 8 -> 128 pooled pixels x POOL 2, + halo
 
 template <int POOL>
-__global__ void __launch_bounds__(kCcThreads) canvas_conv_kernel(const float *__restrict__ pre,
-                                                                 const float *__restrict__ canvas,
-                                                                 const float *__restrict__ w,
-                                                                 const float *__restrict__ scale,
-                                                                 const float *__restrict__ shift, int B, int H, int W,
-                                                                 int C0, int relu, float *__restrict__ y) {
+__global__ void __launch_bounds__(kCcThreads, 4) canvas_conv_kernel(const float *__restrict__ pre,
+                                                                    const float *__restrict__ canvas,
+                                                                    const float *__restrict__ w,
+                                                                    const float *__restrict__ scale,
+                                                                    const float *__restrict__ shift, int B, int H,
+                                                                    int W, int C0, int relu, float *__restrict__ y) {
   __shared__ float cv_s[POOL + 2][kCcMaxCols];
+  __shared__ __align__(16) float w_s[9 * 64];  // [tap][C0] (C0 <= 64)
   const int cg_n = C0 >> 2;
   const int PX = kCcThreads / cg_n;  // pooled pixels per CTA
   const int Ho = H / POOL, Wo = W / POOL;
@@ -216,16 +217,9 @@ __global__ void __launch_bounds__(kCcThreads) canvas_conv_kernel(const float *__
   const int cg = tid % cg_n, oxl = tid / cg_n;
   const int ox = ox0 + oxl;
   const int c = cg * 4;
-
-  // canvas strip: rows oy*POOL-1 .. oy*POOL+POOL, columns ox0*POOL-1 .. (ox0+PX)*POOL
-  const int ncol = PX * POOL + 2;
-  const float *cb = canvas + (size_t)b * H * W;
-  for (int idx = tid; idx < (POOL + 2) * ncol; idx += kCcThreads) {
-    const int r = idx / ncol, q = idx - r * ncol;
-    const int yy = oy * POOL - 1 + r, xx = ox0 * POOL - 1 + q;
-    cv_s[r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(cb + (size_t)yy * W + xx) : 0.f;
-  }
   const bool live = ox < Wo;
+
+  // the POOL^2 streamed float4 of pre first: they are the long-latency loads
   float4 a[POOL][POOL];
   if (live) {
 #pragma unroll
@@ -235,11 +229,18 @@ __global__ void __launch_bounds__(kCcThreads) canvas_conv_kernel(const float *__
         a[py][px] = __ldcs(reinterpret_cast<const float4 *>(
             pre + (((size_t)b * H + oy * POOL + py) * W + ox * POOL + px) * C0 + c));
   }
-  float4 wk[9];
+  // canvas strip: rows oy*POOL-1 .. oy*POOL+POOL, columns ox0*POOL-1 .. (ox0+PX)*POOL
+  const int ncol = PX * POOL + 2;
+  const float *cb = canvas + (size_t)b * H * W;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) wk[k] = __ldg(reinterpret_cast<const float4 *>(w + k * C0 + c));
-  const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c));
-  const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
+  for (int r = 0; r < POOL + 2; ++r) {
+    const int yy = oy * POOL - 1 + r;
+    for (int q = tid; q < ncol; q += kCcThreads) {
+      const int xx = ox0 * POOL - 1 + q;
+      cv_s[r][q] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(cb + (size_t)yy * W + xx) : 0.f;
+    }
+  }
+  for (int i = tid; i < 9 * C0; i += kCcThreads) w_s[i] = __ldg(w + i);
   __syncthreads();
   if (!live) return;
 
@@ -248,23 +249,31 @@ __global__ void __launch_bounds__(kCcThreads) canvas_conv_kernel(const float *__
   for (int r = 0; r < POOL + 2; ++r)
 #pragma unroll
     for (int q = 0; q < POOL + 2; ++q) cv[r][q] = cv_s[r][oxl * POOL + q];
+  // tap-outer accumulation: one 16-byte weight read serves the POOL^2 positions (few live registers -> 4 CTAs / SM)
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const float4 ww = *reinterpret_cast<const float4 *>(w_s + (ky * 3 + kx) * C0 + c);
+#pragma unroll
+      for (int py = 0; py < POOL; ++py)
+#pragma unroll
+        for (int px = 0; px < POOL; ++px) {
+          const float v = cv[py + ky][px + kx];
+          a[py][px].x = fmaf(v, ww.x, a[py][px].x);
+          a[py][px].y = fmaf(v, ww.y, a[py][px].y);
+          a[py][px].z = fmaf(v, ww.z, a[py][px].z);
+          a[py][px].w = fmaf(v, ww.w, a[py][px].w);
+        }
+    }
+  const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
   float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
   for (int py = 0; py < POOL; ++py)
 #pragma unroll
     for (int px = 0; px < POOL; ++px) {
       float4 v4 = a[py][px];
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float v = cv[py + ky][px + kx];
-          const float4 ww = wk[ky * 3 + kx];
-          v4.x = fmaf(v, ww.x, v4.x);
-          v4.y = fmaf(v, ww.y, v4.y);
-          v4.z = fmaf(v, ww.z, v4.z);
-          v4.w = fmaf(v, ww.w, v4.w);
-        }
       v4.x = fmaf(v4.x, sc.x, sh.x);
       v4.y = fmaf(v4.y, sc.y, sh.y);
       v4.z = fmaf(v4.z, sc.z, sh.z);
@@ -390,7 +399,7 @@ extern "C" int ra_canvas_conv_f32(const float *pre, const float *canvas, const f
   // a CTA serves kCcThreads / (C0/4) pooled pixels of one pooled row; C0/4 must divide the CTA and the strip
   // must fit the static shared tile (C0 >= 8)
   const int cg_n = C0 / 4;
-  if (C0 < 8 || (kCcThreads % cg_n) != 0 || cg_n > kCcThreads) return RA_ERR_UNSUPPORTED;
+  if (C0 < 8 || C0 > 64 || (kCcThreads % cg_n) != 0) return RA_ERR_UNSUPPORTED;
   const int PX = kCcThreads / cg_n;
   const int Ho = H / pool, Wo = W / pool;
   if (Ho > 65535 || B > 65535) return RA_ERR_UNSUPPORTED;

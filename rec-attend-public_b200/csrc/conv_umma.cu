@@ -82,6 +82,7 @@ struct UmmaConvParams {
   int RW, RH;       // TMA box: columns x rows of input pixels (low resolution when up == 2)
   int raw_plane_bytes;  // up == 2 only: bytes per channel plane of the landed low-resolution box
   int raw_off;      // up == 2 only: offset of that landing zone inside a stage
+  int pdl;          // launched with programmatic stream serialization: griddepcontrol.wait before touching activations
   long long *dbg;   // optional per-CTA timeline (ra_debug_conv_timeline), 8 slots per CTA
 };
 
@@ -310,26 +311,69 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int tile0 = blockIdx.x / p.n_split, tile_step = gridDim.x / p.n_split;
   const int n_tiles = p.n_items / p.n_split;
 
-  if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), kProdThreads);
-      mbar_init(smem_u32(&bar_empty[s]), kMmaWarps);
-      mbar_init(smem_u32(&bar_raw[s]), 1);
+  // Barriers are initialised by the TMA warp, which (TMA mode) fires the first `stages` loads right away - before
+  // the block-wide setup barrier - so the activation fetch overlaps TMEM allocation and the filter load.
+  int tma_prologue = 0;  // (tile, chunk) items already requested by the early issue (TMA warp only)
+  if (warp == kTmaWarp) {
+    const bool leader = elect_one();
+    if (leader) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(smem_u32(&bar_full[s]), kProdThreads);
+        mbar_init(smem_u32(&bar_empty[s]), kMmaWarps);
+        mbar_init(smem_u32(&bar_raw[s]), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(smem_u32(&bar_tfull[s]), kMmaWarps);
+        mbar_init(smem_u32(&bar_tempty[s]), kEpiThreads);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bar_tfull[s]), kMmaWarps);
-      mbar_init(smem_u32(&bar_tempty[s]), kEpiThreads);
+    __syncwarp();
+    if (p.tma) {
+      if (leader) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm1)) : "memory");
+        if (p.C2 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm2)) : "memory");
+      }
+      // the activations are the previous kernel's output: wait for it (programmatic dependent launch) here, and
+      // only here - every other access to dependent memory is ordered after these loads
+      if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+      const uint32_t w_bytes = p.w_resident ? 0u : (uint32_t)w_chunk_floats * 4u;
+      const uint32_t tx_bytes = (uint32_t)planes * (uint32_t)(p.RW * p.RH) * 16u + w_bytes;
+      const uint32_t dst_plane = p.up == 2 ? (uint32_t)p.raw_plane_bytes : plane_bytes;
+      int g = 0;
+      for (int tile = tile0; tile < n_tiles && g < p.stages; tile += tile_step) {
+        const Item it = decode_tile(p, tile);
+        const int cx = p.up == 2 ? (it.x0 >> 1) - 1 : it.x0 - 1;
+        const int cy = p.up == 2 ? ((it.y0 - 1) >> 1) : it.y0 - 1;
+        for (int ch = 0; ch < p.n_chunks && g < p.stages; ++ch, ++g) {
+          const uint32_t st = smem_u32(stage_base + (size_t)g * p.stage_bytes);  // first pass: stage g, all empty
+          const uint32_t bar = smem_u32(&bar_raw[g]);
+          if (leader) mbar_arrive_expect_tx(bar, tx_bytes);
+          const uint32_t dst0 = p.up == 2 ? st + (uint32_t)p.raw_off : st;
+          for (int pl = 0; pl < planes; ++pl) {
+            const int cc = ch * p.KC + 4 * pl;
+            const uint32_t dst = dst0 + (uint32_t)pl * dst_plane;
+            if (cc < p.C1 || p.C2 == 0) {
+              if (leader) tma_load_4d(dst, &tm1, cc, cx, cy, it.b, bar);
+            } else {
+              if (leader) tma_load_4d(dst, &tm2, cc - p.C1, cx, cy, it.b, bar);
+            }
+          }
+          if (!p.w_resident) {
+            const float *wsrc = p.wpack + ((size_t)ns * p.n_chunks + ch) * w_chunk_floats;
+            if (leader) bulk_load(st + 2u * (uint32_t)in_floats * 4u, wsrc, w_bytes, bar);
+          }
+          __syncwarp();
+          if (g == 0 && leader) RA_DBG(2);  // first stage requested
+        }
+      }
+      tma_prologue = g;
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  if (warp == kTmaWarp && p.tma && elect_one()) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm1)) : "memory");
-    if (p.C2 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm2)) : "memory");
   }
   if (p.w_resident) {
     // the whole filter image of this CTA's channel split: loaded once, reused by every tile
@@ -358,6 +402,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);  // uniform register
   const int slots_in = (p.TH + 2) * p.TWP + 2;  // slots that carry real (or zero-padding) data
   if (threadIdx.x == 0) RA_DBG(1);  // setup done (barriers, TMEM, resident filters)
+  // programmatic dependent launch: the next kernel of the stream may start its own setup on SMs this grid has
+  // left; it still waits (griddepcontrol.wait) for this grid to complete before it reads our output
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == kTmaWarp) {
     // =============================== TMA issuer ===============================
@@ -374,6 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int cx = p.up == 2 ? (it.x0 >> 1) - 1 : it.x0 - 1;
         const int cy = p.up == 2 ? ((it.y0 - 1) >> 1) : it.y0 - 1;
         for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
+          if (g < tma_prologue) continue;  // requested before the setup barrier
           const int s = g % p.stages;
           mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((g / p.stages) & 1) ^ 1));
           const uint32_t st = smem_u32(stage_base + (size_t)s * p.stage_bytes);
@@ -395,7 +443,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (leader) bulk_load(st + 2u * (uint32_t)in_floats * 4u, wsrc, w_bytes, bar);
           }
           __syncwarp();
-          if (g == 0 && leader) RA_DBG(2);  // first stage requested
         }
       }
     }
@@ -453,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp >= kMmaWarp0 + kMmaWarps) {
     // =============================== producers (plain-load mode) ===============================
     const int ptid = tid - (kEpiThreads + 32 * kMmaWarps);
+    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous kernel's output
     int g = 0;  // running (tile, chunk) counter
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       const Item it = decode_tile(p, tile);
@@ -1151,6 +1199,30 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
                                  (int)cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
-  conv3x3_umma_kernel<<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
+  static const bool use_pdl = []() {
+    const char *e = getenv("RA_CONV_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  p.pdl = use_pdl ? 1 : 0;
+  if (use_pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = ra::as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel, p, tm1, tm2);
+    if (e != cudaSuccess) {
+      ra::set_last_error("cudaLaunchKernelEx(conv3x3_umma_kernel)", e);
+      return RA_ERR_CUDA;
+    }
+  } else {
+    conv3x3_umma_kernel<<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
+  }
   return ra::finish_launch("conv3x3_umma_kernel");
 }

@@ -63,22 +63,29 @@ __global__ void build_filters_kernel(const float *__restrict__ box, int H, int W
 }
 
 // ------------------------------------------------------------------ glimpse: row pass
-// Union over the F taps of one axis' support bands -> r[0..1] (shared); empty union: r[0] > r[1].
-// Filter entries outside a tap's band are exact zeros, so consumers may skip everything outside the union.
-__device__ __forceinline__ void band_union(const int *__restrict__ bd, int F, int L, int *r) {
-  if (threadIdx.x == 0) {
-    r[0] = L;
-    r[1] = -1;
+// Superset of the union of the F taps' support bands along one axis, recomputed from the box (no memory traffic,
+// no synchronisation): taps are monotone in t, so the union is [lo(tap 0), hi(tap F-1)]; one extra pixel on each
+// side absorbs any last-bit difference to build_filters_kernel's arithmetic.  Filter entries outside a tap's band
+// are exact zeros, so consumers may skip everything outside [lo, hi] (empty: lo > hi).
+__device__ __forceinline__ void band_union(const float *__restrict__ bo, int axis, int F, int L, int *lo_out,
+                                           int *hi_out) {
+  const float ctr = bo[RA_BOX_CTR_Y + axis];
+  const float size = bo[RA_BOX_SIZE_Y + axis];
+  const float var = expf(bo[RA_BOX_LGVAR_Y + axis]);
+  const float step = (size + 1.0f) / (float)F;
+  const float half = (float)(F - 1) / 2.0f;
+  const float R = sqrtf(2.0f * var * kCut) + 1.0f;
+  const float m0 = ctr - step * half, m1 = ctr + step * half;
+  float lo = floorf(fminf(m0, m1) - R) - 1.0f, hi = ceilf(fmaxf(m0, m1) + R) + 1.0f;
+  int ilo = 0, ihi = L - 1;
+  if (lo == lo && hi == hi) {  // not NaN (NaN boxes keep the full range, like the per-tap bands)
+    lo = fminf(fmaxf(lo, 0.f), (float)L);
+    hi = fmaxf(fminf(hi, (float)(L - 1)), -1.f);
+    ilo = (int)lo;
+    ihi = (int)hi;
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < F; t += blockDim.x) {
-    const int lo = bd[t * 2], hi = bd[t * 2 + 1];
-    if (hi >= lo) {
-      atomicMin(&r[0], lo);
-      atomicMax(&r[1], hi);
-    }
-  }
-  __syncthreads();
+  *lo_out = ilo;
+  *hi_out = ihi;
 }
 
 // One launch for both sources: CTAs [0, nx_s) of grid.x serve the static stack xs viewed as [B][H][W*Cs],
@@ -89,10 +96,11 @@ template <int IB>
 __global__ void __launch_bounds__(128) extract_rows_kernel(const float *__restrict__ xs, int Cs,
                                                            const float *__restrict__ canvas, int H, int W,
                                                            const float *__restrict__ fy, const int *__restrict__ band,
-                                                           int F, float *__restrict__ tmp_s, float *__restrict__ tmp_c,
+                                                           const float *__restrict__ box, int F,
+                                                           float *__restrict__ tmp_s, float *__restrict__ tmp_c,
                                                            int nx_s) {
   extern __shared__ float wsm[];  // [IB][H]
-  __shared__ int xr[2];
+  int xr[2];
   const int b = blockIdx.z;
   const int i0 = blockIdx.y * IB;
   const bool is_c = (int)blockIdx.x >= nx_s;
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(128) extract_rows_kernel(const float *__restri
   const int rowlen = W * C;
   const int bx = is_c ? (int)blockIdx.x - nx_s : (int)blockIdx.x;
   const int e0 = (bx * (int)blockDim.x + (int)threadIdx.x) * 4;
-  band_union(band + ((size_t)b * 2 + 1) * F * 2, F, W, xr);
+  band_union(box + (size_t)b * RA_BOX_STRIDE, 1, F, W, &xr[0], &xr[1]);
   const int elo = xr[0] * C, ehi = (xr[1] + 1) * C;  // floats [elo, ehi) of a row are needed
   {
     const int c0 = bx * (int)blockDim.x * 4, c1 = c0 + (int)blockDim.x * 4;
@@ -174,12 +182,11 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
                                                            const float *__restrict__ box, int W, int F, int Dp,
                                                            float *__restrict__ patch) {
   extern __shared__ float slab[];  // [W][D]
-  __shared__ int xr[2];
   const int i = blockIdx.x, b = blockIdx.y;
   const int D = Cs + (tmp_c != nullptr ? 1 : 0);
   // only columns inside the union of the x-bands were produced by the row pass and are read below
-  band_union(band + ((size_t)b * 2 + 1) * F * 2, F, W, xr);
-  const int xlo = xr[0], xhi = xr[1];
+  int xlo, xhi;
+  band_union(box + (size_t)b * RA_BOX_STRIDE, 1, F, W, &xlo, &xhi);
   if (Cs > 0) {
     const float *ts = tmp_s + ((size_t)b * F + i) * (size_t)W * Cs;
     for (int idx = xlo * Cs + threadIdx.x; idx < (xhi + 1) * Cs; idx += blockDim.x) {
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
   __shared__ float wy_s[kPbTY][kMaxF];       // fy[i][y] for the tile rows
   __shared__ float t2_s[kPbTY][kMaxF + 1];   // sum_i fy[i][y] P[i][j]
   __shared__ float sy_s[kPbTY];              // sum_i fy[i][y]
-  __shared__ int yr[2], xr[2];
+  int yr[2] = {0, H - 1}, xr[2] = {0, W - 1};
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * kPbTY, x0 = blockIdx.x * kPbTX;
   const int tid = threadIdx.x;
@@ -244,9 +251,10 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
 
   // Tiles that no tap's support band reaches (most of the image for a small box): every filter entry is an exact
   // zero there, so attn_box = y_out = sigmoid(-5) - write the constants (float4) and update the canvas.
+  // (band != NULL says the filters come from build_filters_kernel, i.e. are exact zeros outside the bands)
   if (band != nullptr) {
-    band_union(band + ((size_t)b * 2 + 0) * F * 2, F, H, yr);
-    band_union(band + ((size_t)b * 2 + 1) * F * 2, F, W, xr);
+    band_union(bo, 0, F, H, &yr[0], &yr[1]);
+    band_union(bo, 1, F, W, &xr[0], &xr[1]);
   }
   if (band != nullptr && (y0 > yr[1] || y0 + kPbTY - 1 < yr[0] || x0 > xr[1] || x0 + kPbTX - 1 < xr[0])) {
     const float c5 = ra::sigmoidf_acc(-5.0f);
@@ -336,12 +344,19 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
   float sx = 0.f;
   if (x < W) {
     const float *fxp = fx + (size_t)b * F * W + x;
-    for (int j = jlo; j <= jhi; ++j) {
-      const float wx = __ldg(fxp + (size_t)j * W);
-      sx += wx;
-      if (has_patch) {
+    // four filter loads in flight per round (same summation order as the plain loop)
+    for (int j = jlo; j <= jhi; j += 4) {
+      float wx[4];
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t2_s[rh * kRows + r][j], wx, acc[r]);
+      for (int u = 0; u < 4; ++u) wx[u] = (j + u <= jhi) ? __ldg(fxp + (size_t)(j + u) * W) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j + u > jhi) break;
+        sx += wx[u];
+        if (has_patch) {
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t2_s[rh * kRows + r][j + u], wx[u], acc[r]);
+        }
       }
     }
     const float g_box = bo[RA_BOX_GAMMA_BOX], g_y = bo[RA_BOX_GAMMA_Y];
@@ -396,7 +411,7 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
     const int nx_s = Cs > 0 ? (W * Cs / 4 + 127) / 128 : 0;
     const int nx_c = canvas != nullptr ? (W / 4 + 127) / 128 : 0;
     dim3 grid(nx_s + nx_c, groups, B);
-    extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(xs, Cs, canvas, H, W, fy, band, F, tmp_s, tmp_c, nx_s);
+    extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(xs, Cs, canvas, H, W, fy, band, box, F, tmp_s, tmp_c, nx_s);
     const int rc = ra::finish_launch("extract_rows_kernel");
     if (rc != RA_OK) return rc;
   }

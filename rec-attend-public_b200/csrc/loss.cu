@@ -121,10 +121,21 @@ __device__ __forceinline__ void iou_stage(const IouParams &p, int b, int k0, int
           const float *rc = p.b_rect + ((size_t)b * p.M + r) * 4;
           const float ty = rc[0], tx = rc[1], by = rc[2], bx = rc[3];
           float o[4];
+          if ((p.W & 3) == 0) {  // the four pixels share a row: one division
+            const int yy = k / p.W, xx = k - yy * p.W;
+            const float fy = (float)yy;
+            const bool row_in = fy >= ty && fy <= by;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float fy = (float)((k + e) / p.W), fx = (float)((k + e) % p.W);
-            o[e] = (fy >= ty && fx >= tx && fy <= by && fx <= bx) ? 1.f : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              const float fx = (float)(xx + e);
+              o[e] = (row_in && fx >= tx && fx <= bx) ? 1.f : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float fy = (float)((k + e) / p.W), fx = (float)((k + e) % p.W);
+              o[e] = (fy >= ty && fx >= tx && fy <= by && fx <= bx) ? 1.f : 0.f;
+            }
           }
           v = make_float4(o[0], o[1], o[2], o[3]);
         } else if (r == p.M) {

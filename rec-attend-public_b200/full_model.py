@@ -360,6 +360,7 @@ class FullModel(_ModelBase):
     w = self.w
     T, H, W, F = self.T, self.H, self.W, self.F
     thw = T * H * W
+    fork_score = int(self.n_chains) <= 1  # with sub-batch chains the side streams belong to the chains
     for t in range(T):
       self._controller(bufs, t)
       box_t = bufs['box_all'][t]
@@ -374,7 +375,13 @@ class FullModel(_ModelBase):
                    out=bufs['acnn'][i])
         prev = bufs['acnn'][i]
       core = bufs['acnn'][-1]
-      ops.score(bufs['h_all'][t], core, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
+      # the score head (full_model.py:821-822) feeds only the loss: a parallel graph branch beside the mask head
+      score_side = self._side_stream(bufs, 2) if fork_score else None
+      if score_side is None:
+        ops.score(bufs['h_all'][t], core, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
+      else:
+        with torch.cuda.stream(score_side):
+          ops.score(bufs['h_all'][t], core, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
       # full_model.py:797-807: skip list [None, h_acnn[4..0], x_patch]
       skips = [None] + (bufs['acnn'][::-1][1:] + [x_patch])
       prev = core
@@ -390,6 +397,8 @@ class FullModel(_ModelBase):
       ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],
                      attn_box=bufs['attn_box'][:, t], y_out=bufs['y_out'][:, t], out_bstride=thw,
                      disable_overwrite=self.disable_overwrite, band=bufs['band'])
+      if score_side is not None:
+        torch.cuda.current_stream().wait_stream(score_side)  # before the next step overwrites `core`
 
   def _side_stream(self, bufs, i):
     """Side streams become parallel branches of the captured CUDA graph; eager runs stay on one stream (the
