@@ -34,6 +34,34 @@ def load_peaks():
   return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'source': 'fallback'}
 
 
+# C-ABI entry point -> the CUDA kernels it launches (names as ncu prints them), for `traffic`
+ENTRY_KERNELS = {
+    'ra_gaussian_extract_f32': ['extract_rows_kernel<4>', 'extract_cols_kernel'],
+    'ra_paste_back_f32': ['paste_back_kernel'],
+    'ra_pairwise_iou_f32': ['pairwise_iou_kernel'],
+    'ra_gt_box_f32': ['gt_box_kernel'],
+    'ra_canvas_conv_f32': ['canvas_conv_bulk_kernel<2>'],
+    'ra_conv3x3_umma_f32': ['conv3x3_umma_kernel'],
+}
+
+
+def load_traffic():
+  """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu --set full
+  captures, profiles/ncu_traffic.json written by tools/ncu_traffic.py).  {} if the file is absent."""
+  p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+  try:
+    return json.load(open(p))
+  except (OSError, ValueError):
+    return {}
+
+
+def entry_traffic(traffic, entry):
+  ks = ENTRY_KERNELS.get(entry.split(':')[0])
+  if not ks or any(k not in traffic for k in ks):
+    return None
+  return float(sum(traffic[k]['dram_bytes_per_launch'] for k in ks))
+
+
 class ClockSampler(object):
   """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
   Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -326,8 +354,12 @@ def run_ours(args):
       gg['ms'] += d['ms']
       gg['n'] += d['n']
     kernels = {}
+    traffic = load_traffic()
     for g, d in sorted(groups.items(), key=lambda kv: -kv[1]['ms']):
       ent = {'ms_per_step': round(d['ms'], 4), 'launches': d['n'], 'share': round(d['ms'] / total_ms, 4)}
+      tr = entry_traffic(traffic, g)
+      if tr is not None:
+        ent['traffic'] = tr
       if g in work and 'bytes' in work[g]:
         gbs = work[g]['bytes'] / (d['ms'] / d['n'] / 1e3) / 1e9
         ent['achieved_gbs'] = round(gbs, 1)
@@ -343,14 +375,14 @@ def run_ours(args):
           'kernel': 'conv3x3_umma_kernel (controller CNN layers, tcgen05 kind::tf32 x3 split; group = ' + dom + ')',
           'bound': 'tensor',
           'achieved': round(conv_tflops, 3), 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-          'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': None,
+          'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': entry_traffic(traffic, dom),
           'peak_source': peaks['source'] + ' (cuBLAS bf16 burst)',
           'note': 'flops = the reference\'s 8 conv layers per decode step (the linear split of layer 0 does fewer)'
       }
     else:
       k = kernels[dom]
       roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': k.get('achieved_gbs'), 'peak': peaks['hbm_gbs'],
-                  'unit': 'GB/s', 'frac': k.get('hbm_frac'), 'traffic': None, 'peak_source': peaks['source']}
+                  'unit': 'GB/s', 'frac': k.get('hbm_frac'), 'traffic': k.get('traffic'), 'peak_source': peaks['source']}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -11,6 +11,8 @@
 // shared-memory broadcasts and the input reads are conflict-free float2's from a
 // channel-planar tile [CK][TH+2][TW+4].  Per input channel a thread issues 8 LDS.64 + 18
 // LDS.128 for 288 FMAs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -312,6 +314,202 @@ __global__ void concat_channels_kernel(const float *__restrict__ a, int Ca, cons
   }
 }
 
+
+// ---- the same layer as a bulk-copy (TMA) pipeline -------------------------------------------------------------
+// Persistent CTAs; warp 8 streams the `pre` rows of successive (example, pooled row, segment) items into a 4-stage
+// shared-memory ring with cp.async.bulk (each row segment is one contiguous run of NHWC memory) and mbarrier
+// transaction counts; warps 0-7 consume: canvas strip (prefetched one item ahead with 4-byte cp.async), 9 taps,
+// folded BN, ReLU, max-pool, one float4 store per thread.  64 KB of loads in flight per CTA instead of 16 KB.
+constexpr int kCbStages = 4;
+constexpr int kCbThreads = kCcThreads + 32;
+
+__device__ __forceinline__ uint32_t cb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cb_mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void cb_mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void cb_mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cb_mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cb_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(kCbThreads) canvas_conv_bulk_kernel(const float *__restrict__ pre,
+                                                                      const float *__restrict__ canvas,
+                                                                      const float *__restrict__ w,
+                                                                      const float *__restrict__ scale,
+                                                                      const float *__restrict__ shift, int B, int H,
+                                                                      int W, int C0, int relu, float *__restrict__ y,
+                                                                      int nseg, int n_items) {
+  extern __shared__ __align__(128) unsigned char cb_smem[];
+  __shared__ float cv_s[2][POOL + 2][kCcMaxCols];
+  __shared__ __align__(16) float w_s[9 * 64];
+  __shared__ __align__(8) uint64_t bar_full[kCbStages], bar_empty[kCbStages];
+  const int cg_n = C0 >> 2;
+  const int PX = kCcThreads / cg_n;  // pooled pixels per item
+  const int PXI = PX * POOL;         // input pixels per item row
+  const int Ho = H / POOL, Wo = W / POOL;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t row_bytes = (uint32_t)PXI * (uint32_t)C0 * 4u;  // one full row segment in a stage
+  const uint32_t stage_bytes = row_bytes * POOL;
+  float *stage0 = reinterpret_cast<float *>(cb_smem + ((128u - (cb_smem_u32(cb_smem) & 127u)) & 127u));
+
+  if (tid == 0) {
+    for (int s = 0; s < kCbStages; ++s) {
+      cb_mbar_init(cb_smem_u32(&bar_full[s]), 1);
+      cb_mbar_init(cb_smem_u32(&bar_empty[s]), kCcThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 9 * C0; i += kCbThreads) w_s[i] = __ldg(w + i);
+  __syncthreads();
+
+  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == kCcThreads / 32) {
+    // =============================== producer warp ===============================
+    if (lane == 0) {
+      for (int k = 0; k < my_items; ++k) {
+        const int s = k % kCbStages;
+        if (k >= kCbStages) cb_mbar_wait(cb_smem_u32(&bar_empty[s]), (uint32_t)(((k / kCbStages) - 1) & 1));
+        int it = (int)blockIdx.x + k * (int)gridDim.x;
+        const int seg = it % nseg;
+        it /= nseg;
+        const int oy = it % Ho, b = it / Ho;
+        const int x0 = seg * PXI;
+        const int npx = min(PXI, W - x0);
+        const uint32_t bytes = (uint32_t)npx * (uint32_t)C0 * 4u;
+        const uint32_t bar = cb_smem_u32(&bar_full[s]);
+        cb_mbar_expect_tx(bar, bytes * POOL);
+        const uint32_t dst = cb_smem_u32(stage0) + (uint32_t)s * stage_bytes;
+#pragma unroll
+        for (int py = 0; py < POOL; ++py)
+          cb_bulk_load(dst + (uint32_t)py * row_bytes, pre + (((size_t)b * H + oy * POOL + py) * W + x0) * C0, bytes, bar);
+      }
+    }
+    return;
+  }
+
+  // =============================== consumers (warps 0-7) ===============================
+  const int cg = tid % cg_n, oxl = tid / cg_n;
+  const int c = cg * 4;
+  const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
+  const int ncol = PXI + 2;
+
+  // canvas strip of item k -> cv_s[k & 1] (4-byte cp.async inside the image, zeros outside = SAME padding)
+  auto strip_prefetch = [&](int k) {
+    if (k < my_items) {
+      int it = (int)blockIdx.x + k * (int)gridDim.x;
+      const int seg = it % nseg;
+      it /= nseg;
+      const int oy = it % Ho, b = it / Ho;
+      const float *cb = canvas + (size_t)b * H * W;
+#pragma unroll
+      for (int r = 0; r < POOL + 2; ++r) {
+        const int yy = oy * POOL - 1 + r;
+        for (int q = tid; q < ncol; q += kCcThreads) {
+          const int xx = seg * PXI - 1 + q;
+          float *dst = &cv_s[k & 1][r][q];
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cb_smem_u32(dst)), "l"(cb + (size_t)yy * W + xx)
+                         : "memory");
+          } else {
+            *dst = 0.f;
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  strip_prefetch(0);
+  for (int k = 0; k < my_items; ++k) {
+    const int s = k % kCbStages;
+    int it = (int)blockIdx.x + k * (int)gridDim.x;
+    const int seg = it % nseg;
+    it /= nseg;
+    const int oy = it % Ho, b = it / Ho;
+    const int ox = seg * PX + oxl;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");          // strip k has landed (this thread's part)
+    asm volatile("bar.sync 1, %0;" ::"n"(kCcThreads) : "memory");  // ... and everybody else's; item k-1 is fully read
+    strip_prefetch(k + 1);  // into the buffer item k-1 used: overlaps this item's arithmetic
+    cb_mbar_wait(cb_smem_u32(&bar_full[s]), (uint32_t)((k / kCbStages) & 1));
+    const float *st = stage0 + (size_t)s * (stage_bytes / 4);
+    if (ox < Wo) {
+      float4 a[POOL][POOL];
+#pragma unroll
+      for (int py = 0; py < POOL; ++py)
+#pragma unroll
+        for (int px = 0; px < POOL; ++px)
+          a[py][px] = *reinterpret_cast<const float4 *>(st + ((size_t)py * PXI + oxl * POOL + px) * C0 + c);
+      float cv[POOL + 2][POOL + 2];
+#pragma unroll
+      for (int r = 0; r < POOL + 2; ++r)
+#pragma unroll
+        for (int q = 0; q < POOL + 2; ++q) cv[r][q] = cv_s[k & 1][r][oxl * POOL + q];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 ww = *reinterpret_cast<const float4 *>(w_s + (ky * 3 + kx) * C0 + c);
+#pragma unroll
+          for (int py = 0; py < POOL; ++py)
+#pragma unroll
+            for (int px = 0; px < POOL; ++px) {
+              const float v = cv[py + ky][px + kx];
+              a[py][px].x = fmaf(v, ww.x, a[py][px].x);
+              a[py][px].y = fmaf(v, ww.y, a[py][px].y);
+              a[py][px].z = fmaf(v, ww.z, a[py][px].z);
+              a[py][px].w = fmaf(v, ww.w, a[py][px].w);
+            }
+        }
+      float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+      for (int py = 0; py < POOL; ++py)
+#pragma unroll
+        for (int px = 0; px < POOL; ++px) {
+          float4 v4 = a[py][px];
+          v4.x = fmaf(v4.x, sc.x, sh.x);
+          v4.y = fmaf(v4.y, sc.y, sh.y);
+          v4.z = fmaf(v4.z, sc.z, sh.z);
+          v4.w = fmaf(v4.w, sc.w, sh.w);
+          if (relu) {
+            v4.x = fmaxf(v4.x, 0.f);
+            v4.y = fmaxf(v4.y, 0.f);
+            v4.z = fmaxf(v4.z, 0.f);
+            v4.w = fmaxf(v4.w, 0.f);
+          }
+          best.x = fmaxf(best.x, v4.x);
+          best.y = fmaxf(best.y, v4.y);
+          best.z = fmaxf(best.z, v4.z);
+          best.w = fmaxf(best.w, v4.w);
+        }
+      *reinterpret_cast<float4 *>(y + (((size_t)b * Ho + oy) * Wo + ox) * C0 + c) = best;
+    }
+    __syncwarp();
+    if (lane == 0) cb_mbar_arrive(cb_smem_u32(&bar_empty[s]));  // this warp has read stage s
+  }
+}
+
 }  // namespace
 
 extern "C" int ra_conv3x3_f32(const float *x1, int C1, const float *x2, int C2, const float *w, const float *scale,
@@ -405,6 +603,32 @@ extern "C" int ra_canvas_conv_f32(const float *pre, const float *canvas, const f
   if (Ho > 65535 || B > 65535) return RA_ERR_UNSUPPORTED;
   dim3 grid((Wo + PX - 1) / PX, Ho, B);
   cudaStream_t s = ra::as_stream(stream);
+  // bulk-copy pipeline: needs 16-byte aligned row segments (C0 % 4 == 0 gives the size; the base must be aligned)
+  const bool no_bulk = getenv("RA_CANVAS_NO_BULK") != nullptr;  // diagnostics / tests: the plain-load kernel
+  const long long n_items = (long long)grid.x * Ho * B;
+  if (!no_bulk && (reinterpret_cast<uintptr_t>(pre) & 15) == 0 && n_items <= 0x7fffffffLL) {
+    const size_t stage_bytes = (size_t)pool * (PX * pool) * C0 * 4;
+    const size_t smem = kCbStages * stage_bytes + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e1 = cudaFuncSetAttribute(canvas_conv_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaError_t e2 = cudaFuncSetAttribute(canvas_conv_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        ra::set_last_error("cudaFuncSetAttribute(canvas_conv_bulk_kernel)", e1 != cudaSuccess ? e1 : e2);
+        return RA_ERR_CUDA;
+      }
+      attr_set = true;
+    }
+    int ctas = ra::kNumSMs * 2;  // 2 x 4 stages x 16 KB in flight per SM
+    if ((long long)ctas > n_items) ctas = (int)n_items;
+    if (pool == 2)
+      canvas_conv_bulk_kernel<2><<<ctas, kCbThreads, smem, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y,
+                                                                (int)grid.x, (int)n_items);
+    else
+      canvas_conv_bulk_kernel<1><<<ctas, kCbThreads, smem, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y,
+                                                                (int)grid.x, (int)n_items);
+    return ra::finish_launch("canvas_conv_bulk_kernel");
+  }
   if (pool == 2)
     canvas_conv_kernel<2><<<grid, kCcThreads, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
   else

@@ -228,8 +228,11 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
 }
 
 // ------------------------------------------------------------------ paste-back
-constexpr int kPbTY = 8;  // rows per CTA (32 measured slower: fewer CTAs in flight to hide the prologue loads)
-constexpr int kPbTX = 128;
+constexpr int kPbTY = 8;      // rows per tile
+constexpr int kPbTX = 128;    // columns per tile
+constexpr int kPbTilesY = 1;  // consecutive row tiles served by one CTA.  MEASURED: 4 tiles per CTA (fewer, fatter CTAs,
+                              // patch loaded once) is slower - 54 us vs 37 us per launch at 256x512, B=32 - because
+                              // the tiles inside the box serialise within a CTA; 1 keeps them spread over the SMs.
 
 __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict__ patch,
                                                          const float *__restrict__ fy, const float *__restrict__ fx,
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
   __shared__ float sy_s[kPbTY];              // sum_i fy[i][y]
   int yr[2] = {0, H - 1}, xr[2] = {0, W - 1};
   const int b = blockIdx.z;
-  const int y0 = blockIdx.y * kPbTY, x0 = blockIdx.x * kPbTX;
+  const int x0 = blockIdx.x * kPbTX;
   const int tid = threadIdx.x;
   const float *bo = box + (size_t)b * RA_BOX_STRIDE;
   const bool has_patch = patch != nullptr;
@@ -256,65 +259,8 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
     band_union(bo, 0, F, H, &yr[0], &yr[1]);
     band_union(bo, 1, F, W, &xr[0], &xr[1]);
   }
-  if (band != nullptr && (y0 > yr[1] || y0 + kPbTY - 1 < yr[0] || x0 > xr[1] || x0 + kPbTX - 1 < xr[0])) {
-    const float c5 = ra::sigmoidf_acc(-5.0f);
-    if ((W & 3) == 0) {
-      const float4 c4 = make_float4(c5, c5, c5, c5);
-      for (int idx = tid; idx < kPbTY * (kPbTX / 4); idx += blockDim.x) {
-        const int ty = idx / (kPbTX / 4), x = x0 + (idx - ty * (kPbTX / 4)) * 4, y = y0 + ty;
-        if (y >= H || x >= W) continue;
-        const size_t pix = (size_t)y * W + x;
-        if (attn_box != nullptr) *reinterpret_cast<float4 *>(attn_box + (size_t)b * out_bstride + pix) = c4;
-        if (has_patch) {
-          float4 *cp = reinterpret_cast<float4 *>(canvas + (size_t)b * H * W + pix);
-          const float4 cv = *cp;
-          float4 v = c4;
-          if (disable_overwrite) v = make_float4(c5 * (1.0f - cv.x), c5 * (1.0f - cv.y), c5 * (1.0f - cv.z), c5 * (1.0f - cv.w));
-          *reinterpret_cast<float4 *>(y_out + (size_t)b * out_bstride + pix) = v;
-          *cp = make_float4(fmaxf(cv.x, v.x), fmaxf(cv.y, v.y), fmaxf(cv.z, v.z), fmaxf(cv.w, v.w));
-        }
-      }
-    } else {
-      for (int idx = tid; idx < kPbTY * kPbTX; idx += blockDim.x) {
-        const int ty = idx / kPbTX, x = x0 + (idx - ty * kPbTX), y = y0 + ty;
-        if (y >= H || x >= W) continue;
-        const size_t pix = (size_t)y * W + x;
-        if (attn_box != nullptr) attn_box[(size_t)b * out_bstride + pix] = c5;
-        if (has_patch) {
-          const size_t cpix = (size_t)b * H * W + pix;
-          const float cv = canvas[cpix];
-          float v = c5;
-          if (disable_overwrite) v *= (1.0f - cv);
-          y_out[(size_t)b * out_bstride + pix] = v;
-          canvas[cpix] = fmaxf(cv, v);
-        }
-      }
-    }
-    return;
-  }
-
-  if (has_patch)
-    for (int idx = tid; idx < F * F; idx += blockDim.x) P_s[idx] = patch[(size_t)b * F * F + idx];
-  for (int idx = tid; idx < kPbTY * F; idx += blockDim.x) {
-    const int ty = idx / F, i = idx - ty * F;
-    const int y = y0 + ty;
-    wy_s[ty][i] = (y < H) ? fy[((size_t)b * F + i) * H + y] : 0.f;
-  }
-  __syncthreads();
-  if (has_patch) {
-    for (int idx = tid; idx < kPbTY * F; idx += blockDim.x) {
-      const int ty = idx / F, j = idx - ty * F;
-      float a = 0.f;
-      for (int i = 0; i < F; ++i) a = fmaf(wy_s[ty][i], P_s[i * F + j], a);
-      t2_s[ty][j] = a;
-    }
-  }
-  if (tid < kPbTY) {
-    float a = 0.f;
-    for (int i = 0; i < F; ++i) a += wy_s[tid][i];
-    sy_s[tid] = a;
-  }
-  __syncthreads();
+  const bool x_outside = band != nullptr && (x0 > xr[1] || x0 + kPbTX - 1 < xr[0]);
+  const float c5 = ra::sigmoidf_acc(-5.0f);
 
   constexpr int kRows = kPbTY / 2;
   const int col = tid % kPbTX, rh = tid / kPbTX;  // 2 row-halves of kRows rows
@@ -338,42 +284,113 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
     jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
     jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
   }
-  float acc[kRows];
-#pragma unroll
-  for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
-  float sx = 0.f;
-  if (x < W) {
-    const float *fxp = fx + (size_t)b * F * W + x;
-    // four filter loads in flight per round (same summation order as the plain loop)
-    for (int j = jlo; j <= jhi; j += 4) {
-      float wx[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) wx[u] = (j + u <= jhi) ? __ldg(fxp + (size_t)(j + u) * W) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (j + u > jhi) break;
-        sx += wx[u];
-        if (has_patch) {
-#pragma unroll
-          for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t2_s[rh * kRows + r][j + u], wx[u], acc[r]);
+  const float g_box = bo[RA_BOX_GAMMA_BOX], g_y = bo[RA_BOX_GAMMA_Y];
+  bool p_loaded = false;
+
+  for (int tyi = 0; tyi < kPbTilesY; ++tyi) {
+    const int y0 = (blockIdx.y * kPbTilesY + tyi) * kPbTY;
+    if (y0 >= H) break;
+    if (x_outside || (band != nullptr && (y0 > yr[1] || y0 + kPbTY - 1 < yr[0]))) {
+      // ---------------- constant tile
+      if ((W & 3) == 0) {
+        const float4 c4 = make_float4(c5, c5, c5, c5);
+        for (int idx = tid; idx < kPbTY * (kPbTX / 4); idx += blockDim.x) {
+          const int ty = idx / (kPbTX / 4), xx = x0 + (idx - ty * (kPbTX / 4)) * 4, y = y0 + ty;
+          if (y >= H || xx >= W) continue;
+          const size_t pix = (size_t)y * W + xx;
+          if (attn_box != nullptr) *reinterpret_cast<float4 *>(attn_box + (size_t)b * out_bstride + pix) = c4;
+          if (has_patch) {
+            float4 *cp = reinterpret_cast<float4 *>(canvas + (size_t)b * H * W + pix);
+            const float4 cv = *cp;
+            float4 v = c4;
+            if (disable_overwrite)
+              v = make_float4(c5 * (1.0f - cv.x), c5 * (1.0f - cv.y), c5 * (1.0f - cv.z), c5 * (1.0f - cv.w));
+            *reinterpret_cast<float4 *>(y_out + (size_t)b * out_bstride + pix) = v;
+            *cp = make_float4(fmaxf(cv.x, v.x), fmaxf(cv.y, v.y), fmaxf(cv.z, v.z), fmaxf(cv.w, v.w));
+          }
+        }
+      } else {
+        for (int idx = tid; idx < kPbTY * kPbTX; idx += blockDim.x) {
+          const int ty = idx / kPbTX, xx = x0 + (idx - ty * kPbTX), y = y0 + ty;
+          if (y >= H || xx >= W) continue;
+          const size_t pix = (size_t)y * W + xx;
+          if (attn_box != nullptr) attn_box[(size_t)b * out_bstride + pix] = c5;
+          if (has_patch) {
+            const size_t cpix = (size_t)b * H * W + pix;
+            const float cv = canvas[cpix];
+            float v = c5;
+            if (disable_overwrite) v *= (1.0f - cv);
+            y_out[(size_t)b * out_bstride + pix] = v;
+            canvas[cpix] = fmaxf(cv, v);
+          }
         }
       }
+      continue;
     }
-    const float g_box = bo[RA_BOX_GAMMA_BOX], g_y = bo[RA_BOX_GAMMA_Y];
+
+    // ---------------- tile inside the box: Fy^T P for its rows, then the band of Fx per column
+    __syncthreads();  // the previous tile's readers of wy_s / t2_s / sy_s are done
+    if (has_patch && !p_loaded) {
+      for (int idx = tid; idx < F * F; idx += blockDim.x) P_s[idx] = patch[(size_t)b * F * F + idx];
+      p_loaded = true;
+    }
+    for (int idx = tid; idx < kPbTY * F; idx += blockDim.x) {
+      const int ty = idx / F, i = idx - ty * F;
+      const int y = y0 + ty;
+      wy_s[ty][i] = (y < H) ? fy[((size_t)b * F + i) * H + y] : 0.f;
+    }
+    __syncthreads();
+    if (has_patch) {
+      for (int idx = tid; idx < kPbTY * F; idx += blockDim.x) {
+        const int ty = idx / F, j = idx - ty * F;
+        float a = 0.f;
+        for (int i = 0; i < F; ++i) a = fmaf(wy_s[ty][i], P_s[i * F + j], a);
+        t2_s[ty][j] = a;
+      }
+    }
+    if (tid < kPbTY) {
+      float a = 0.f;
+      for (int i = 0; i < F; ++i) a += wy_s[tid][i];
+      sy_s[tid] = a;
+    }
+    __syncthreads();
+
+    float acc[kRows];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int y = y0 + rh * kRows + r;
-      if (y >= H) continue;
-      const size_t pix = (size_t)y * W + x;
-      if (attn_box != nullptr)  // full_model.py:738-741
-        attn_box[(size_t)b * out_bstride + pix] = ra::sigmoidf_acc(g_box * (sy_s[rh * kRows + r] * sx) - 5.0f);
-      if (has_patch) {  // full_model.py:810-818, 845
-        const size_t cpix = (size_t)b * H * W + pix;
-        const float cv = canvas[cpix];
-        float v = ra::sigmoidf_acc(g_y * acc[r] - 5.0f);
-        if (disable_overwrite) v *= (1.0f - cv);
-        y_out[(size_t)b * out_bstride + pix] = v;
-        canvas[cpix] = fmaxf(cv, v);
+    for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+    float sx = 0.f;
+    if (x < W) {
+      const float *fxp = fx + (size_t)b * F * W + x;
+      // four filter loads in flight per round (same summation order as the plain loop)
+      for (int j = jlo; j <= jhi; j += 4) {
+        float wx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wx[u] = (j + u <= jhi) ? __ldg(fxp + (size_t)(j + u) * W) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j + u > jhi) break;
+          sx += wx[u];
+          if (has_patch) {
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) acc[r] = fmaf(t2_s[rh * kRows + r][j + u], wx[u], acc[r]);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const int y = y0 + rh * kRows + r;
+        if (y >= H) continue;
+        const size_t pix = (size_t)y * W + x;
+        if (attn_box != nullptr)  // full_model.py:738-741
+          attn_box[(size_t)b * out_bstride + pix] = ra::sigmoidf_acc(g_box * (sy_s[rh * kRows + r] * sx) - 5.0f);
+        if (has_patch) {  // full_model.py:810-818, 845
+          const size_t cpix = (size_t)b * H * W + pix;
+          const float cv = canvas[cpix];
+          float v = ra::sigmoidf_acc(g_y * acc[r] - 5.0f);
+          if (disable_overwrite) v *= (1.0f - cv);
+          y_out[(size_t)b * out_bstride + pix] = v;
+          canvas[cpix] = fmaxf(cv, v);
+        }
       }
     }
   }
@@ -441,7 +458,7 @@ extern "C" int ra_paste_back_f32(const float *patch, const float *box, const flo
   if (patch == nullptr && attn_box == nullptr) return RA_ERR_INVALID_ARG;
   if (F > kMaxF) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
-  dim3 grid((W + kPbTX - 1) / kPbTX, (H + kPbTY - 1) / kPbTY, B);
+  dim3 grid((W + kPbTX - 1) / kPbTX, ((H + kPbTY - 1) / kPbTY + kPbTilesY - 1) / kPbTilesY, B);
   paste_back_kernel<<<grid, 256, 0, ra::as_stream(stream)>>>(patch, fy, fx, band, box, H, W, F, disable_overwrite,
                                                              attn_box, y_out, out_bstride, canvas);
   return ra::finish_launch("paste_back_kernel");

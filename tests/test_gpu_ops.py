@@ -473,10 +473,17 @@ def test_conv3x3_block_umma(ops, case):
   assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5
 
 
-@pytest.mark.parametrize('C0,pool,H,W', [(16, 2, 32, 64), (8, 1, 24, 40), (16, 1, 16, 16), (8, 2, 64, 32)])
-def test_canvas_conv(ops, C0, pool, H, W):
+@pytest.mark.parametrize('bulk', [True, False])
+@pytest.mark.parametrize('C0,pool,H,W,B', [(16, 2, 32, 64, 2), (8, 1, 24, 40, 2), (16, 1, 16, 16, 2), (8, 2, 64, 32, 2),
+                                           (16, 2, 16, 320, 2),    # 3 segments per row, ragged last one
+                                           (8, 2, 8, 520, 1),      # C0 = 8: 128 pooled pixels per item, 4-pixel tail
+                                           (16, 1, 8, 300, 2),     # no pooling, 5 segments
+                                           (16, 2, 256, 512, 3)])  # > 4 items per persistent CTA: the ring wraps
+def test_canvas_conv(ops, C0, pool, H, W, B, bulk, monkeypatch):
+  """Both kernels of ra_canvas_conv_f32: the cp.async.bulk pipeline (default) and the plain-load one."""
+  if not bulk:
+    monkeypatch.setenv('RA_CANVAS_NO_BULK', '1')
   rng = np.random.default_rng(C0 * 10 + pool)
-  B = 2
   pre = rng.standard_normal((B, H, W, C0)).astype(np.float32)
   canvas = rng.random((B, H, W)).astype(np.float32)
   w = (rng.standard_normal((3, 3, 1, C0)) / 3).astype(np.float32)
