@@ -316,12 +316,14 @@ __global__ void concat_channels_kernel(const float *__restrict__ a, int Ca, cons
 
 
 // ---- the same layer as a bulk-copy (TMA) pipeline -------------------------------------------------------------
-// Persistent CTAs; warp 8 streams the `pre` rows of successive (example, pooled row, segment) items into a 4-stage
+// Persistent CTAs; warp 4 streams the `pre` rows of successive (example, pooled row, segment) items into a 3-stage
 // shared-memory ring with cp.async.bulk (each row segment is one contiguous run of NHWC memory) and mbarrier
-// transaction counts; warps 0-7 consume: canvas strip (prefetched one item ahead with 4-byte cp.async), 9 taps,
-// folded BN, ReLU, max-pool, one float4 store per thread.  64 KB of loads in flight per CTA instead of 16 KB.
-constexpr int kCbStages = 4;
-constexpr int kCbThreads = kCcThreads + 32;
+// transaction counts; warps 0-3 consume: canvas strip (prefetched one item ahead with cp.async), 9 taps, folded BN,
+// max-pool, ReLU, two float4 stores per thread.
+constexpr int kCbStages = 3;  // x 3 CTAs/SM x 16 KB = 144 KB of loads in flight per SM
+constexpr int kCbConsumers = 128;              // consumer threads (warps 0-3); warp 4 is the producer
+constexpr int kCbThreads = kCbConsumers + 32;
+constexpr int kCbStripW = 4 + 256 + 4;         // strip row: 3 pad + left halo | up to 256 interior columns | right halo + pad
 
 __device__ __forceinline__ uint32_t cb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cb_mbar_init(uint32_t mbar, uint32_t count) {
@@ -359,13 +361,20 @@ __global__ void __launch_bounds__(kCbThreads) canvas_conv_bulk_kernel(const floa
                                                                       const float *__restrict__ shift, int B, int H,
                                                                       int W, int C0, int relu, float *__restrict__ y,
                                                                       int nseg, int n_items) {
+  // ncu (profiles/r01j_*): the first version of this kernel was ISSUE-bound (57 % issue-active at 37 % of the DRAM
+  // peak, ~540 instructions per thread and item for 144 FMAs).  Hence: two pooled pixels per thread (the canvas
+  // patch, the weight reads, the item bookkeeping and the barriers are shared by twice the arithmetic), the strip
+  // fetched with 16-byte cp.async, ReLU after the max.
+  constexpr int NP = 2;                    // pooled pixels per thread (horizontally adjacent)
+  constexpr int PW = NP * POOL;            // input columns per thread
   extern __shared__ __align__(128) unsigned char cb_smem[];
-  __shared__ float cv_s[2][POOL + 2][kCcMaxCols];
+  __shared__ __align__(16) float cv_s[2][POOL + 2][kCbStripW];  // [buffer][row][3 pad | left halo | interior | right halo]
   __shared__ __align__(16) float w_s[9 * 64];
   __shared__ __align__(8) uint64_t bar_full[kCbStages], bar_empty[kCbStages];
   const int cg_n = C0 >> 2;
-  const int PX = kCcThreads / cg_n;  // pooled pixels per item
-  const int PXI = PX * POOL;         // input pixels per item row
+  const int PXT = kCbConsumers / cg_n;  // thread columns per item
+  const int PX = PXT * NP;              // pooled pixels per item
+  const int PXI = PX * POOL;            // input pixels per item row
   const int Ho = H / POOL, Wo = W / POOL;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t row_bytes = (uint32_t)PXI * (uint32_t)C0 * 4u;  // one full row segment in a stage
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(kCbThreads) canvas_conv_bulk_kernel(const floa
   if (tid == 0) {
     for (int s = 0; s < kCbStages; ++s) {
       cb_mbar_init(cb_smem_u32(&bar_full[s]), 1);
-      cb_mbar_init(cb_smem_u32(&bar_empty[s]), kCcThreads / 32);
+      cb_mbar_init(cb_smem_u32(&bar_empty[s]), kCbConsumers / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -384,7 +393,7 @@ __global__ void __launch_bounds__(kCbThreads) canvas_conv_bulk_kernel(const floa
 
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == kCcThreads / 32) {
+  if (warp == kCbConsumers / 32) {
     // =============================== producer warp ===============================
     if (lane == 0) {
       for (int k = 0; k < my_items; ++k) {
@@ -408,64 +417,83 @@ __global__ void __launch_bounds__(kCbThreads) canvas_conv_bulk_kernel(const floa
     return;
   }
 
-  // =============================== consumers (warps 0-7) ===============================
-  const int cg = tid % cg_n, oxl = tid / cg_n;
+  // =============================== consumers ===============================
+  const int cg = tid % cg_n, oxp = tid / cg_n;
   const int c = cg * 4;
   const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c));
   const float4 sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
-  const int ncol = PXI + 2;
+  const int n16 = PXI / 4;  // 16-byte pieces of a strip row's interior
 
-  // canvas strip of item k -> cv_s[k & 1] (4-byte cp.async inside the image, zeros outside = SAME padding)
-  auto strip_prefetch = [&](int k) {
-    if (k < my_items) {
-      int it = (int)blockIdx.x + k * (int)gridDim.x;
-      const int seg = it % nseg;
-      it /= nseg;
-      const int oy = it % Ho, b = it / Ho;
+  // canvas strip of the item (seg, oy, b) -> cv_s[buf]: interior columns by 16-byte cp.async (W % 4 == 0, so a piece
+  // is entirely inside or outside the image), the two halo columns by 4-byte cp.async, zeros outside (SAME padding)
+  auto strip_prefetch = [&](int buf, int seg, int oy, int b, bool valid) {
+    if (valid) {
       const float *cb = canvas + (size_t)b * H * W;
-#pragma unroll
-      for (int r = 0; r < POOL + 2; ++r) {
-        const int yy = oy * POOL - 1 + r;
-        for (int q = tid; q < ncol; q += kCcThreads) {
-          const int xx = seg * PXI - 1 + q;
-          float *dst = &cv_s[k & 1][r][q];
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cb_smem_u32(dst)), "l"(cb + (size_t)yy * W + xx)
-                         : "memory");
-          } else {
-            *dst = 0.f;
-          }
+      const int x0 = seg * PXI;
+      for (int idx = tid; idx < (POOL + 2) * n16; idx += kCbConsumers) {
+        const int r = idx / n16, i4 = idx - r * n16;
+        const int yy = oy * POOL - 1 + r, xx = x0 + i4 * 4;
+        float *dst = &cv_s[buf][r][4 + i4 * 4];
+        if (yy >= 0 && yy < H && xx < W) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cb_smem_u32(dst)), "l"(cb + (size_t)yy * W + xx)
+                       : "memory");
+        } else {
+          *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (tid < (POOL + 2) * 2) {
+        const int r = tid >> 1, right = tid & 1;
+        const int yy = oy * POOL - 1 + r, xx = right ? x0 + PXI : x0 - 1;
+        float *dst = &cv_s[buf][r][right ? 4 + PXI : 3];
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cb_smem_u32(dst)), "l"(cb + (size_t)yy * W + xx)
+                       : "memory");
+        } else {
+          *dst = 0.f;
         }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  strip_prefetch(0);
+  // item k of this CTA -> (seg, oy, b); decoded once, one item ahead
+  int seg_n, oy_n, b_n;
+  {
+    int it = (int)blockIdx.x;
+    seg_n = it % nseg;
+    it /= nseg;
+    oy_n = it % Ho;
+    b_n = it / Ho;
+  }
+  strip_prefetch(0, seg_n, oy_n, b_n, my_items > 0);
   for (int k = 0; k < my_items; ++k) {
     const int s = k % kCbStages;
-    int it = (int)blockIdx.x + k * (int)gridDim.x;
-    const int seg = it % nseg;
-    it /= nseg;
-    const int oy = it % Ho, b = it / Ho;
-    const int ox = seg * PX + oxl;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");          // strip k has landed (this thread's part)
-    asm volatile("bar.sync 1, %0;" ::"n"(kCcThreads) : "memory");  // ... and everybody else's; item k-1 is fully read
-    strip_prefetch(k + 1);  // into the buffer item k-1 used: overlaps this item's arithmetic
+    const int seg = seg_n, oy = oy_n, b = b_n;
+    {
+      int it = (int)blockIdx.x + (k + 1) * (int)gridDim.x;
+      seg_n = it % nseg;
+      it /= nseg;
+      oy_n = it % Ho;
+      b_n = it / Ho;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");            // strip k has landed (this thread's part)
+    asm volatile("bar.sync 1, %0;" ::"n"(kCbConsumers) : "memory");  // ... and everybody else's; item k-1 is fully read
+    strip_prefetch((k + 1) & 1, seg_n, oy_n, b_n, k + 1 < my_items);  // overlaps this item's arithmetic
     cb_mbar_wait(cb_smem_u32(&bar_full[s]), (uint32_t)((k / kCbStages) & 1));
     const float *st = stage0 + (size_t)s * (stage_bytes / 4);
-    if (ox < Wo) {
-      float4 a[POOL][POOL];
+    const int ox = seg * PX + oxp * NP;  // first of this thread's pooled pixels
+    if (ox < Wo) {                       // (Wo is even whenever PX is, so both pixels are in or out together)
+      float4 a[POOL][PW];
 #pragma unroll
       for (int py = 0; py < POOL; ++py)
 #pragma unroll
-        for (int px = 0; px < POOL; ++px)
-          a[py][px] = *reinterpret_cast<const float4 *>(st + ((size_t)py * PXI + oxl * POOL + px) * C0 + c);
-      float cv[POOL + 2][POOL + 2];
+        for (int px = 0; px < PW; ++px)
+          a[py][px] = *reinterpret_cast<const float4 *>(st + ((size_t)py * PXI + oxp * PW + px) * C0 + c);
+      float cv[POOL + 2][PW + 2];
 #pragma unroll
       for (int r = 0; r < POOL + 2; ++r)
 #pragma unroll
-        for (int q = 0; q < POOL + 2; ++q) cv[r][q] = cv_s[k & 1][r][oxl * POOL + q];
+        for (int q = 0; q < PW + 2; ++q) cv[r][q] = cv_s[k & 1][r][3 + oxp * PW + q];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -474,7 +502,7 @@ __global__ void __launch_bounds__(kCbThreads) canvas_conv_bulk_kernel(const floa
 #pragma unroll
           for (int py = 0; py < POOL; ++py)
 #pragma unroll
-            for (int px = 0; px < POOL; ++px) {
+            for (int px = 0; px < PW; ++px) {
               const float v = cv[py + ky][px + kx];
               a[py][px].x = fmaf(v, ww.x, a[py][px].x);
               a[py][px].y = fmaf(v, ww.y, a[py][px].y);
@@ -482,28 +510,28 @@ __global__ void __launch_bounds__(kCbThreads) canvas_conv_bulk_kernel(const floa
               a[py][px].w = fmaf(v, ww.w, a[py][px].w);
             }
         }
-      float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-      for (int py = 0; py < POOL; ++py)
+      for (int np = 0; np < NP; ++np) {
+        if (ox + np >= Wo) break;
+        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-        for (int px = 0; px < POOL; ++px) {
-          float4 v4 = a[py][px];
-          v4.x = fmaf(v4.x, sc.x, sh.x);
-          v4.y = fmaf(v4.y, sc.y, sh.y);
-          v4.z = fmaf(v4.z, sc.z, sh.z);
-          v4.w = fmaf(v4.w, sc.w, sh.w);
-          if (relu) {
-            v4.x = fmaxf(v4.x, 0.f);
-            v4.y = fmaxf(v4.y, 0.f);
-            v4.z = fmaxf(v4.z, 0.f);
-            v4.w = fmaxf(v4.w, 0.f);
+        for (int py = 0; py < POOL; ++py)
+#pragma unroll
+          for (int px = 0; px < POOL; ++px) {
+            const float4 v4 = a[py][np * POOL + px];
+            best.x = fmaxf(best.x, fmaf(v4.x, sc.x, sh.x));
+            best.y = fmaxf(best.y, fmaf(v4.y, sc.y, sh.y));
+            best.z = fmaxf(best.z, fmaf(v4.z, sc.z, sh.z));
+            best.w = fmaxf(best.w, fmaf(v4.w, sc.w, sh.w));
           }
-          best.x = fmaxf(best.x, v4.x);
-          best.y = fmaxf(best.y, v4.y);
-          best.z = fmaxf(best.z, v4.z);
-          best.w = fmaxf(best.w, v4.w);
+        if (relu) {  // max(relu(.)) == relu(max(.))
+          best.x = fmaxf(best.x, 0.f);
+          best.y = fmaxf(best.y, 0.f);
+          best.z = fmaxf(best.z, 0.f);
+          best.w = fmaxf(best.w, 0.f);
         }
-      *reinterpret_cast<float4 *>(y + (((size_t)b * Ho + oy) * Wo + ox) * C0 + c) = best;
+        *reinterpret_cast<float4 *>(y + (((size_t)b * Ho + oy) * Wo + ox + np) * C0 + c) = best;
+      }
     }
     __syncwarp();
     if (lane == 0) cb_mbar_arrive(cb_smem_u32(&bar_empty[s]));  // this warp has read stage s
@@ -603,11 +631,15 @@ extern "C" int ra_canvas_conv_f32(const float *pre, const float *canvas, const f
   if (Ho > 65535 || B > 65535) return RA_ERR_UNSUPPORTED;
   dim3 grid((Wo + PX - 1) / PX, Ho, B);
   cudaStream_t s = ra::as_stream(stream);
-  // bulk-copy pipeline: needs 16-byte aligned row segments (C0 % 4 == 0 gives the size; the base must be aligned)
+  // bulk-copy pipeline: needs 16-byte aligned row segments and strip pieces (C0 % 4 == 0 and W % 4 == 0 give the
+  // sizes; the bases must be aligned)
   const bool no_bulk = getenv("RA_CANVAS_NO_BULK") != nullptr;  // diagnostics / tests: the plain-load kernel
-  const long long n_items = (long long)grid.x * Ho * B;
-  if (!no_bulk && (reinterpret_cast<uintptr_t>(pre) & 15) == 0 && n_items <= 0x7fffffffLL) {
-    const size_t stage_bytes = (size_t)pool * (PX * pool) * C0 * 4;
+  const int PXb = (kCbConsumers / cg_n) * 2;                    // pooled pixels per item of the bulk kernel
+  const int nseg = (Wo + PXb - 1) / PXb;
+  const long long n_items = (long long)nseg * Ho * B;
+  if (!no_bulk && (W & 3) == 0 && PXb * pool <= 256 && (reinterpret_cast<uintptr_t>(pre) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(canvas) & 15) == 0 && n_items <= 0x7fffffffLL) {
+    const size_t stage_bytes = (size_t)pool * (PXb * pool) * C0 * 4;
     const size_t smem = kCbStages * stage_bytes + 128;
     static bool attr_set = false;
     if (!attr_set) {
@@ -619,14 +651,14 @@ extern "C" int ra_canvas_conv_f32(const float *pre, const float *canvas, const f
       }
       attr_set = true;
     }
-    int ctas = ra::kNumSMs * 2;  // 2 x 4 stages x 16 KB in flight per SM
+    int ctas = ra::kNumSMs * 3;  // 61 KB of shared memory each: three per SM
     if ((long long)ctas > n_items) ctas = (int)n_items;
     if (pool == 2)
       canvas_conv_bulk_kernel<2><<<ctas, kCbThreads, smem, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y,
-                                                                (int)grid.x, (int)n_items);
+                                                                nseg, (int)n_items);
     else
       canvas_conv_bulk_kernel<1><<<ctas, kCbThreads, smem, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y,
-                                                                (int)grid.x, (int)n_items);
+                                                                nseg, (int)n_items);
     return ra::finish_launch("canvas_conv_bulk_kernel");
   }
   if (pool == 2)

@@ -64,19 +64,20 @@ __global__ void build_filters_kernel(const float *__restrict__ box, int H, int W
 
 // ------------------------------------------------------------------ glimpse: row pass
 // Superset of the union of the F taps' support bands along one axis, recomputed from the box (no memory traffic,
-// no synchronisation): taps are monotone in t, so the union is [lo(tap 0), hi(tap F-1)]; one extra pixel on each
-// side absorbs any last-bit difference to build_filters_kernel's arithmetic.  Filter entries outside a tap's band
+// no synchronisation): taps are monotone in t, so the union is [lo(tap 0), hi(tap F-1)].  Every thread of every
+// consumer CTA runs this, so it uses the fast exp / sqrt intrinsics; two extra pixels on each side absorb their
+// error and any last-bit difference to build_filters_kernel's arithmetic.  Filter entries outside a tap's band
 // are exact zeros, so consumers may skip everything outside [lo, hi] (empty: lo > hi).
 __device__ __forceinline__ void band_union(const float *__restrict__ bo, int axis, int F, int L, int *lo_out,
                                            int *hi_out) {
   const float ctr = bo[RA_BOX_CTR_Y + axis];
   const float size = bo[RA_BOX_SIZE_Y + axis];
-  const float var = expf(bo[RA_BOX_LGVAR_Y + axis]);
+  const float var = __expf(bo[RA_BOX_LGVAR_Y + axis]);
   const float step = (size + 1.0f) / (float)F;
   const float half = (float)(F - 1) / 2.0f;
-  const float R = sqrtf(2.0f * var * kCut) + 1.0f;
+  const float R = __fsqrt_rn(2.0f * var * kCut) * 1.0001f + 1.0f;
   const float m0 = ctr - step * half, m1 = ctr + step * half;
-  float lo = floorf(fminf(m0, m1) - R) - 1.0f, hi = ceilf(fmaxf(m0, m1) + R) + 1.0f;
+  float lo = floorf(fminf(m0, m1) - R) - 2.0f, hi = ceilf(fmaxf(m0, m1) + R) + 2.0f;
   int ilo = 0, ihi = L - 1;
   if (lo == lo && hi == hi) {  // not NaN (NaN boxes keep the full range, like the per-tap bands)
     lo = fminf(fmaxf(lo, 0.f), (float)L);
@@ -260,31 +261,10 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
     band_union(bo, 1, F, W, &xr[0], &xr[1]);
   }
   const bool x_outside = band != nullptr && (x0 > xr[1] || x0 + kPbTX - 1 < xr[0]);
-  const float c5 = ra::sigmoidf_acc(-5.0f);
 
   constexpr int kRows = kPbTY / 2;
   const int col = tid % kPbTX, rh = tid / kPbTX;  // 2 row-halves of kRows rows
   const int x = x0 + col;
-  // taps whose band can reach column x (analytic superset; entries outside a band are 0)
-  int jlo = 0, jhi = F - 1;
-  {
-    const float ctr = bo[RA_BOX_CTR_X], size = bo[RA_BOX_SIZE_X];
-    const float var = expf(bo[RA_BOX_LGVAR_X]);
-    const float step = (size + 1.0f) / (float)F;
-    const float R = sqrtf(2.0f * var * kCut) + 1.0f;
-    const float half = (float)(F - 1) / 2.0f;
-    const float a = ((float)x - R - ctr) / step + half, c = ((float)x + R - ctr) / step + half;
-    if (a == a && c == c && fabsf(a) < 1e9f && fabsf(c) < 1e9f) {
-      jlo = max(0, (int)floorf(a));
-      jhi = min(F - 1, (int)ceilf(c));
-    }
-  }
-  // warp-uniform tap range so that t2_s reads are broadcasts
-  for (int o = 16; o > 0; o >>= 1) {
-    jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
-    jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
-  }
-  const float g_box = bo[RA_BOX_GAMMA_BOX], g_y = bo[RA_BOX_GAMMA_Y];
   bool p_loaded = false;
 
   for (int tyi = 0; tyi < kPbTilesY; ++tyi) {
@@ -292,6 +272,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
     if (y0 >= H) break;
     if (x_outside || (band != nullptr && (y0 > yr[1] || y0 + kPbTY - 1 < yr[0]))) {
       // ---------------- constant tile
+      const float c5 = ra::sigmoidf_acc(-5.0f);
       if ((W & 3) == 0) {
         const float4 c4 = make_float4(c5, c5, c5, c5);
         for (int idx = tid; idx < kPbTY * (kPbTX / 4); idx += blockDim.x) {
@@ -329,6 +310,26 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
     }
 
     // ---------------- tile inside the box: Fy^T P for its rows, then the band of Fx per column
+    // taps whose band can reach column x (analytic superset; entries outside a band are 0)
+    int jlo = 0, jhi = F - 1;
+    {
+      const float ctr = bo[RA_BOX_CTR_X], size = bo[RA_BOX_SIZE_X];
+      const float var = expf(bo[RA_BOX_LGVAR_X]);
+      const float step = (size + 1.0f) / (float)F;
+      const float R = sqrtf(2.0f * var * kCut) + 1.0f;
+      const float half = (float)(F - 1) / 2.0f;
+      const float a = ((float)x - R - ctr) / step + half, c = ((float)x + R - ctr) / step + half;
+      if (a == a && c == c && fabsf(a) < 1e9f && fabsf(c) < 1e9f) {
+        jlo = max(0, (int)floorf(a));
+        jhi = min(F - 1, (int)ceilf(c));
+      }
+    }
+    // warp-uniform tap range so that t2_s reads are broadcasts
+    for (int o = 16; o > 0; o >>= 1) {
+      jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+      jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+    }
+    const float g_box = bo[RA_BOX_GAMMA_BOX], g_y = bo[RA_BOX_GAMMA_Y];
     __syncthreads();  // the previous tile's readers of wy_s / t2_s / sy_s are done
     if (has_patch && !p_loaded) {
       for (int idx = tid; idx < F * F; idx += blockDim.x) P_s[idx] = patch[(size_t)b * F * F + idx];

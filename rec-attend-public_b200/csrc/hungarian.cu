@@ -37,18 +37,38 @@ struct WarpScratch {
   int parent_y[kMaxN];
 };
 
-__device__ __forceinline__ mask_t shfl_down64(mask_t v, int o) {
-  return (mask_t)__shfl_down_sync(0xffffffffu, (unsigned long long)v, o);
-}
-__device__ __forceinline__ mask_t shfl64(mask_t v, int src) {
-  return (mask_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src);
-}
+// Mask arithmetic for the two widths of the search: 32-bit masks when nx, ny <= 32 (every shuffle and bit operation is
+// one instruction instead of two - the kernel is a single latency-bound warp, so instruction count is time), 64-bit
+// otherwise.
+template <typename M>
+struct MaskOps;
+template <>
+struct MaskOps<uint32_t> {
+  static __device__ __forceinline__ int popc(uint32_t m) { return __popc(m); }
+  static __device__ __forceinline__ int lowest(uint32_t m) { return __ffs((int)m) - 1; }
+  static __device__ __forceinline__ int highest(uint32_t m) { return 31 - __clz((int)m); }
+  static __device__ __forceinline__ uint32_t shfl_down(uint32_t v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+  static __device__ __forceinline__ uint32_t shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+};
+template <>
+struct MaskOps<mask_t> {
+  static __device__ __forceinline__ int popc(mask_t m) { return __popcll(m); }
+  static __device__ __forceinline__ int lowest(mask_t m) { return __ffsll((long long)m) - 1; }
+  static __device__ __forceinline__ int highest(mask_t m) { return 63 - __clzll((long long)m); }
+  static __device__ __forceinline__ mask_t shfl_down(mask_t v, int o) {
+    return (mask_t)__shfl_down_sync(0xffffffffu, (unsigned long long)v, o);
+  }
+  static __device__ __forceinline__ mask_t shfl(mask_t v, int src) {
+    return (mask_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src);
+  }
+};
 
 // Inclusive suffix OR over the lanes (lane l gets OR of lanes l..31).
-__device__ __forceinline__ mask_t suffix_or(mask_t v, int lane) {
+template <typename M>
+__device__ __forceinline__ M suffix_or(M v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const mask_t t = shfl_down64(v, o);
+    const M t = MaskOps<M>::shfl_down(v, o);
     if (lane + o < 32) v |= t;
   }
   return v;
@@ -69,65 +89,73 @@ __device__ __forceinline__ int prefix_sum_excl(int v, int lane, int *total) {
 // (and lane r - 32 for r >= 32).  "The highest-ranked pusher wins" is an exclusive suffix OR over the ranks,
 // "next level in (parent rank, column index) order" an exclusive prefix sum of the claim counts.  free_x /
 // free_y (unmatched rows / columns) are replicated in every lane.  Returns true if the matching grew.
-__device__ bool augment_ranked(WarpScratch &s, int lane, mask_t &free_x, mask_t &free_y) {
+// M = uint32_t requires nx, ny <= 32 (then a level never has more than 32 ranks).
+template <typename M>
+__device__ bool augment_ranked(WarpScratch &s, int lane, M &free_x, M &free_y) {
+  typedef MaskOps<M> O;
+  constexpr bool kWide = sizeof(M) == 8;
+  const M one = 1;
   if (!free_x) return false;
   // level 1: the unmatched rows in index order
   {
-    const int x0 = lane, x1 = lane + 32;
-    if ((free_x >> x0) & 1ull) s.level_x[__popcll(free_x & ((1ull << x0) - 1ull))] = x0;
-    if ((free_x >> x1) & 1ull) s.level_x[__popcll(free_x & ((1ull << x1) - 1ull))] = x1;
+    const int x0 = lane;
+    if ((free_x >> x0) & one) s.level_x[O::popc(free_x & ((one << x0) - one))] = x0;
+    if (kWide) {
+      const int x1 = lane + 32;
+      if ((free_x >> x1) & one) s.level_x[O::popc(free_x & ((one << x1) - one))] = x1;
+    }
   }
-  int n_lx = __popcll(free_x);
-  mask_t seen_y = 0;
+  int n_lx = O::popc(free_x);
+  M seen_y = 0;
   __syncwarp();
 
   for (;;) {
-    const bool two = n_lx > 32;  // warp-uniform
+    const bool two = kWide && n_lx > 32;  // warp-uniform
     // ---- claims: c[r] = A[r] & ~(OR of A[r'] for r' > r), A[r] = residual neighbours of rank r not seen yet
-    mask_t A0 = 0, A1 = 0;
+    M A0 = 0, A1 = 0;
     int px0 = -1, px1 = -1;
     if (lane < n_lx) {
       px0 = s.level_x[lane];
-      mask_t adj = s.eq[px0];
+      M adj = (M)s.eq[px0];
       const int my = s.match_y[px0];
-      if (my >= 0) adj &= ~(1ull << my);  // a saturated edge has no residual capacity
+      if (my >= 0) adj &= ~(one << my);  // a saturated edge has no residual capacity
       A0 = adj & ~seen_y;
     }
-    mask_t excl1 = 0, total1 = 0;
+    M excl1 = 0, total1 = 0;
     if (two) {
       if (lane + 32 < n_lx) {
         px1 = s.level_x[lane + 32];
-        mask_t adj = s.eq[px1];
+        M adj = (M)s.eq[px1];
         const int my = s.match_y[px1];
-        if (my >= 0) adj &= ~(1ull << my);
+        if (my >= 0) adj &= ~(one << my);
         A1 = adj & ~seen_y;
       }
-      const mask_t S1 = suffix_or(A1, lane);
-      excl1 = shfl_down64(S1, 1);
+      const M S1 = suffix_or<M>(A1, lane);
+      excl1 = O::shfl_down(S1, 1);
       if (lane == 31) excl1 = 0;
-      total1 = shfl64(S1, 0);
+      total1 = O::shfl(S1, 0);
     }
-    const mask_t S0 = suffix_or(A0, lane);
-    mask_t excl0 = shfl_down64(S0, 1);
+    const M S0 = suffix_or<M>(A0, lane);
+    M excl0 = O::shfl_down(S0, 1);
     if (lane == 31) excl0 = 0;
     excl0 |= total1;
-    const mask_t level_claim = shfl64(S0, 0) | total1;
+    const M level_claim = O::shfl(S0, 0) | total1;
     if (!level_claim) return false;
     seen_y |= level_claim;
-    const mask_t c0 = A0 & ~excl0, c1 = A1 & ~excl1;
+    const M c0 = A0 & ~excl0, c1 = A1 & ~excl1;
 
     // ---- next level in (parent rank, column index) order
     int tot0 = 0, tot1 = 0;
-    int pos0 = prefix_sum_excl(__popcll(c0), lane, &tot0);
-    for (mask_t c = c0; c; c &= c - 1) {
-      const int y = __ffsll((long long)c) - 1;
+    int pos0 = prefix_sum_excl(O::popc(c0), lane, &tot0);
+    for (M c = c0; c; c &= c - one) {
+      const int y = O::lowest(c);
       s.parent_y[y] = px0;
       s.level_y[pos0++] = y;
     }
     if (two) {
-      int pos1 = tot0 + prefix_sum_excl(__popcll(c1), lane, &tot1);
-      for (mask_t c = c1; c; c &= c - 1) {
-        const int y = __ffsll((long long)c) - 1;
+      int pos1 = tot0 + prefix_sum_excl(O::popc(c1), lane, &tot1);
+      for (M c = c1; c; c &= c - one) {
+        const int y = O::lowest(c);
         s.parent_y[y] = px1;
         s.level_y[pos1++] = y;
       }
@@ -138,16 +166,16 @@ __device__ bool augment_ranked(WarpScratch &s, int lane, mask_t &free_x, mask_t 
     // ---- the sink is reached from the highest-ranked free column: highest rank, then highest index
     int last_free_y = -1;
     {
-      const mask_t f0 = c0 & free_y, f1 = c1 & free_y;
+      const M f0 = c0 & free_y, f1 = c1 & free_y;
       const unsigned b1 = two ? __ballot_sync(0xffffffffu, f1 != 0) : 0u;
       if (b1) {
         const int src = 31 - __clz((int)b1);
-        last_free_y = 63 - __clzll((long long)shfl64(f1, src));
+        last_free_y = O::highest(O::shfl(f1, src));
       } else {
         const unsigned b0 = __ballot_sync(0xffffffffu, f0 != 0);
         if (b0) {
           const int src = 31 - __clz((int)b0);
-          last_free_y = 63 - __clzll((long long)shfl64(f0, src));
+          last_free_y = O::highest(O::shfl(f0, src));
         }
       }
     }
@@ -168,14 +196,14 @@ __device__ bool augment_ranked(WarpScratch &s, int lane, mask_t &free_x, mask_t 
         }
       }
       x_start = __shfl_sync(0xffffffffu, x_start, 0);
-      free_x &= ~(1ull << x_start);
-      free_y &= ~(1ull << last_free_y);
+      free_x &= ~(one << x_start);
+      free_y &= ~(one << last_free_y);
       __syncwarp();
       return true;
     }
     // ---- all columns of the level are matched: follow the matched edges back into X
     if (lane < n_ly) s.level_x[lane] = s.match_x[s.level_y[lane]];
-    if (lane + 32 < n_ly) s.level_x[lane + 32] = s.match_x[s.level_y[lane + 32]];
+    if (kWide && lane + 32 < n_ly) s.level_x[lane + 32] = s.match_x[s.level_y[lane + 32]];
     n_lx = n_ly;
     __syncwarp();
   }
@@ -183,6 +211,7 @@ __device__ bool augment_ranked(WarpScratch &s, int lane, mask_t &free_x, mask_t 
 
 // iou/s_gt == nullptr: plain op (W given).  Otherwise f_segm_match: W is built from iou and
 // s_gt when it is loaded, and the matching is masked on the way out.
+template <typename M>
 __global__ void __launch_bounds__(32) hungarian_kernel(const float *__restrict__ W_in, const float *__restrict__ s_gt,
                                                        int nx, int ny, float *__restrict__ M_out,
                                                        float *__restrict__ cx_out, float *__restrict__ cy_out,
@@ -269,12 +298,12 @@ __global__ void __launch_bounds__(32) hungarian_kernel(const float *__restrict__
       s.match_x[y0] = -1;
       s.match_x[y1] = -1;
       __syncwarp();
-      mask_t free_x = all_x, free_y = all_y;
-      while (augment_ranked(s, lane, free_x, free_y)) {
+      M free_x = (M)all_x, free_y = (M)all_y;
+      while (augment_ranked<M>(s, lane, free_x, free_y)) {
       }
       // hungarian.cc:219-248: the smaller side must be fully matched
-      if (nx - __popcll(free_x) == (nx >= ny ? ny : nx)) break;
-      S = 1ull << (__ffsll((long long)free_x) - 1);  // first unmatched row, hungarian.cc:394-403
+      if (nx - MaskOps<M>::popc(free_x) == (nx >= ny ? ny : nx)) break;
+      S = 1ull << MaskOps<M>::lowest(free_x);  // first unmatched row, hungarian.cc:394-403
       T = 0;
     }
 
@@ -356,7 +385,10 @@ int launch(const float *W, const float *s_gt, int B, int nx, int ny, float *M, f
   if (B == 0) return RA_OK;  // empty batch: nothing to read or write
   if (W == nullptr || M == nullptr) return RA_ERR_INVALID_ARG;
   const size_t smem = sizeof(WarpScratch) + (size_t)nx * ny * sizeof(float);
-  hungarian_kernel<<<B, 32, smem, stream>>>(W, s_gt, nx, ny, M, cx, cy, w_out, status);
+  if (nx <= 32 && ny <= 32)
+    hungarian_kernel<uint32_t><<<B, 32, smem, stream>>>(W, s_gt, nx, ny, M, cx, cy, w_out, status);
+  else
+    hungarian_kernel<mask_t><<<B, 32, smem, stream>>>(W, s_gt, nx, ny, M, cx, cy, w_out, status);
   return ra::finish_launch("hungarian_kernel");
 }
 

@@ -21,15 +21,39 @@ __global__ void __launch_bounds__(256) gt_box_kernel(const float *__restrict__ y
   const float *g = y_gt + m * (size_t)H * W;
   const float hw = (float)(H * W);
   float mny = INFINITY, mnx = INFINITY, mxy = -INFINITY, mxx = -INFINITY, sum = 0.f;
-  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
-    const float v = g[i];
-    const float fy = (float)(i / W), fx = (float)(i % W);
+  auto visit = [&](float v, float fy, float fx) {
     const float off = (1.0f - v) * hw;  // modellib.py:682-683
     mny = fminf(mny, fy + off);
     mnx = fminf(mnx, fx + off);
     mxy = fmaxf(mxy, fy * v);
     mxx = fmaxf(mxx, fx * v);
     sum += v;
+  };
+  if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    // streamed float4 loads, four in flight per thread, one row/column split per 16 bytes
+    const int W4 = W >> 2, n4 = H * W4;
+    for (int base = threadIdx.x; base < n4; base += blockDim.x * 4) {
+      float4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i4 = base + u * blockDim.x;
+        q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i4 < n4) q[u] = ra::ldg_stream4(g + (size_t)i4 * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i4 = base + u * blockDim.x;
+        if (i4 >= n4) break;
+        const int yy = i4 / W4, xx = (i4 - yy * W4) * 4;
+        const float fy = (float)yy, fx = (float)xx;
+        visit(q[u].x, fy, fx);
+        visit(q[u].y, fy, fx + 1.0f);
+        visit(q[u].z, fy, fx + 2.0f);
+        visit(q[u].w, fy, fx + 3.0f);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) visit(g[i], (float)(i / W), (float)(i % W));
   }
   mny = ra::block_min(mny, red);
   mnx = ra::block_min(mnx, red);

@@ -323,9 +323,10 @@ def _masks(rng, B, T, H, W):
   return b['y_gt'], b['s_gt']
 
 
-def test_gt_box(ops):
+@pytest.mark.parametrize('W', [96, 90])  # float4 path / scalar path
+def test_gt_box(ops, W):
   rng = np.random.default_rng(3)
-  B, T, H, W = 3, 6, 64, 96
+  B, T, H = 3, 6, 64
   y_gt, _ = _masks(rng, B, T, H, W)
   y_gt[0, 2] = 0  # an empty mask in the middle (modellib.py:696-699)
   tl, br, box, rect, area = ops.get_gt_box(_g(y_gt), padding_ratio=0.2, min_padding=20.0)
