@@ -292,6 +292,21 @@ int ra_postprocess_f32(const float *y_out, const float *s_out, const float *fg, 
                        double thresh, float remove_tiny, void *workspace, int32_t *label, float *y_hard, float *conf,
                        float *area, void *stream);
 
+/* --------------------------------------------------------------------------------------
+ * Optimiser block — full_model.py:1039-1057 / box_model.py:635-652 on one flat fp32 bucket of
+ * n trainable elements (the buffer the gradient all-reduce of SURVEY §8e runs on):
+ *   g  = grad * grad_scale (1/world after a SUM all-reduce) + wd[i] * param   (wd may be NULL;
+ *        wd[i] = weight_decay on conv/mlp/lstm weight matrices, 0 elsewhere, nnlib.py:59-61)
+ *   g  = clip(g, -clip, clip)                  (tf.clip_by_value per element; clip <= 0: off)
+ *   m += (g - m)(1-beta1);  v += (g*g - v)(1-beta2)
+ *   param -= lr_t * m / (sqrt(v) + eps),  lr_t = lr * sqrt(1-beta2^t) / (1-beta1^t), t = step_t >= 1
+ * (TensorFlow-0.12 AdamOptimizer; the reference uses eps = 1e-7).  lr is the already decayed
+ * learning rate base * decay^floor(step / steps_per_decay) (tf.train.exponential_decay, staircase).
+ * -------------------------------------------------------------------------------------- */
+int ra_adam_step_f32(float *param, const float *grad, float *m, float *v, const float *wd, size_t n,
+                     float grad_scale, float lr, float beta1, float beta2, float eps, float clip, int step_t,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,7 @@ _SIGNATURES = {
     'ra_loss_block_f32': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P],
     'ra_box_gt_step_f32': [_P, _Z, _P, _P, _P, _Z, _I, _I, _I, _I, _P, _I, _P, _P, _P],
     'ra_concat_channels_f32': [_P, _I, _P, _I, _P, _I, _Z, _P, _P],
+    'ra_adam_step_f32': [_P, _P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _P],
     'ra_postprocess_f32': [_P, _P, _P, _I, _I, _I, _I, ctypes.c_double, _F, _P, _P, _P, _P, _P, _P],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last_error', 'ra_launch_count',
