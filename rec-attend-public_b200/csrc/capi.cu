@@ -1,4 +1,5 @@
 // Library-level entry points and error plumbing of librecattend_b200.so.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -10,6 +11,14 @@ static unsigned long long g_launches = 0;  // kernels launched by this library (
 
 void set_last_error(const char *what, cudaError_t e) {
   snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+}
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char *e = getenv("RA_PDL");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  return on;
 }
 
 int finish_launch(const char *what) {

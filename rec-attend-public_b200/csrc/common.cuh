@@ -68,6 +68,33 @@ __device__ __forceinline__ float block_min(float v, float *scratch) {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// The decode loop is a serial chain of ~30 launches per step.  Kernels launched through launch_pdl carry
+// cudaLaunchAttributeProgrammaticStreamSerialization: once every CTA of the PREVIOUS kernel of the stream has called
+// pdl_trigger (or exited), the next grid is scheduled and waits in pdl_wait until the previous grid has completed and
+// its memory is visible.  Every PDL kernel starts with pdl_wait(); pdl_trigger(); so the only thing that overlaps is
+// the launch / CTA scheduling latency - never a data access.  (Both are no-ops for a kernel launched normally.)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // RA_PDL=0 switches the attribute off (capi.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // streaming (read-once) loads: keep them out of L1
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
   return __ldcs(reinterpret_cast<const float4 *>(p));

@@ -232,6 +232,8 @@ constexpr int kUnits = kHd2 / kCl;     // 32 hidden units per CTA
 constexpr int kKin = kCf2 + kHd2;      // 320 LSTM inputs
 
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cluster_kernel(CtrlParams p, int B) {
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int r = (int)cluster.block_rank();
@@ -542,7 +544,12 @@ extern "C" int ra_controller_step_f32(const float *feat, int B, int P, int Cf, i
         attr2 = true;
       }
       const int clusters = (B + kCl - 1) / kCl;
-      controller_cluster_kernel<<<clusters * kCl, 256, smem2, ra::as_stream(stream)>>>(p, B);
+      const cudaError_t le = ra::launch_pdl(controller_cluster_kernel, dim3(clusters * kCl), dim3(256), (size_t)smem2,
+                                            ra::as_stream(stream), p, B);
+      if (le != cudaSuccess) {
+        ra::set_last_error("cudaLaunchKernelEx(controller_cluster_kernel)", le);
+        return RA_ERR_CUDA;
+      }
       return ra::finish_launch("controller_cluster_kernel");
     }
   }

@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(kCcThreads, 4) canvas_conv_kernel(const float 
                                                                     const float *__restrict__ scale,
                                                                     const float *__restrict__ shift, int B, int H,
                                                                     int W, int C0, int relu, float *__restrict__ y) {
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
   __shared__ float cv_s[POOL + 2][kCcMaxCols];
   __shared__ __align__(16) float w_s[9 * 64];  // [tap][C0] (C0 <= 64)
   const int cg_n = C0 >> 2;
@@ -361,6 +363,8 @@ __global__ void __launch_bounds__(kCbThreads) canvas_conv_bulk_kernel(const floa
                                                                       const float *__restrict__ shift, int B, int H,
                                                                       int W, int C0, int relu, float *__restrict__ y,
                                                                       int nseg, int n_items) {
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
   // ncu (profiles/r01j_*): the first version of this kernel was ISSUE-bound (57 % issue-active at 37 % of the DRAM
   // peak, ~540 instructions per thread and item for 144 FMAs).  Hence: two pooled pixels per thread (the canvas
   // patch, the weight reads, the item bookkeeping and the barriers are shared by twice the arithmetic), the strip
@@ -653,17 +657,25 @@ extern "C" int ra_canvas_conv_f32(const float *pre, const float *canvas, const f
     }
     int ctas = ra::kNumSMs * 3;  // 61 KB of shared memory each: three per SM
     if ((long long)ctas > n_items) ctas = (int)n_items;
-    if (pool == 2)
-      canvas_conv_bulk_kernel<2><<<ctas, kCbThreads, smem, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y,
-                                                                nseg, (int)n_items);
-    else
-      canvas_conv_bulk_kernel<1><<<ctas, kCbThreads, smem, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y,
-                                                                nseg, (int)n_items);
+    const cudaError_t le =
+        pool == 2 ? ra::launch_pdl(canvas_conv_bulk_kernel<2>, dim3(ctas), dim3(kCbThreads), smem, s, pre, canvas, w, scale,
+                                   shift, B, H, W, C0, relu, y, nseg, (int)n_items)
+                  : ra::launch_pdl(canvas_conv_bulk_kernel<1>, dim3(ctas), dim3(kCbThreads), smem, s, pre, canvas, w, scale,
+                                   shift, B, H, W, C0, relu, y, nseg, (int)n_items);
+    if (le != cudaSuccess) {
+      ra::set_last_error("cudaLaunchKernelEx(canvas_conv_bulk_kernel)", le);
+      return RA_ERR_CUDA;
+    }
     return ra::finish_launch("canvas_conv_bulk_kernel");
   }
-  if (pool == 2)
-    canvas_conv_kernel<2><<<grid, kCcThreads, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
-  else
-    canvas_conv_kernel<1><<<grid, kCcThreads, 0, s>>>(pre, canvas, w, scale, shift, B, H, W, C0, relu, y);
+  const cudaError_t le =
+      pool == 2 ? ra::launch_pdl(canvas_conv_kernel<2>, grid, dim3(kCcThreads), (size_t)0, s, pre, canvas, w, scale, shift, B,
+                                 H, W, C0, relu, y)
+                : ra::launch_pdl(canvas_conv_kernel<1>, grid, dim3(kCcThreads), (size_t)0, s, pre, canvas, w, scale, shift, B,
+                                 H, W, C0, relu, y);
+  if (le != cudaSuccess) {
+    ra::set_last_error("cudaLaunchKernelEx(canvas_conv_kernel)", le);
+    return RA_ERR_CUDA;
+  }
   return ra::finish_launch("canvas_conv_kernel");
 }

@@ -23,6 +23,8 @@ constexpr int kTapsPerCta = 8;
 // ------------------------------------------------------------------ filter construction
 __global__ void build_filters_kernel(const float *__restrict__ box, int H, int W, int F, float *__restrict__ fy,
                                      float *__restrict__ fx, int *__restrict__ band) {
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
   const int b = blockIdx.x;
   const float *bo = box + (size_t)b * RA_BOX_STRIDE;
   {
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(128) extract_rows_kernel(const float *__restri
                                                            const float *__restrict__ box, int F,
                                                            float *__restrict__ tmp_s, float *__restrict__ tmp_c,
                                                            int nx_s) {
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
   extern __shared__ float wsm[];  // [IB][H]
   int xr[2];
   const int b = blockIdx.z;
@@ -182,6 +186,8 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
                                                            const float *__restrict__ fx, const int *__restrict__ band,
                                                            const float *__restrict__ box, int W, int F, int Dp,
                                                            float *__restrict__ patch) {
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
   extern __shared__ float slab[];  // [W][D]
   const int i = blockIdx.x, b = blockIdx.y;
   const int D = Cs + (tmp_c != nullptr ? 1 : 0);
@@ -242,6 +248,8 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
                                                          int disable_overwrite, float *__restrict__ attn_box,
                                                          float *__restrict__ y_out, size_t out_bstride,
                                                          float *__restrict__ canvas) {
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
   __shared__ float P_s[kMaxF * kMaxF];       // patch [F][F]
   __shared__ float wy_s[kPbTY][kMaxF];       // fy[i][y] for the tile rows
   __shared__ float t2_s[kPbTY][kMaxF + 1];   // sum_i fy[i][y] P[i][j]
@@ -362,7 +370,9 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
     float sx = 0.f;
     if (x < W) {
       const float *fxp = fx + (size_t)b * F * W + x;
-      // four filter loads in flight per round (same summation order as the plain loop)
+      // four filter loads in flight per round (same summation order as the plain loop).  MEASURED: staging these Fx
+      // rows in shared memory (24 KB per CTA, coalesced loads) is slower - 45 us vs 34 us per launch - the lost
+      // occupancy costs more than the dependent L2 round trips.
       for (int j = jlo; j <= jhi; j += 4) {
         float wx[4];
 #pragma unroll
@@ -404,8 +414,12 @@ extern "C" int ra_gaussian_filters_f32(const float *box, int B, int H, int W, in
   if (!box || !fy || !fx || !band || B < 0 || H < 1 || W < 1 || F < 1) return RA_ERR_INVALID_ARG;
   if (F > kMaxF) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
-  build_filters_kernel<<<dim3(B, 2, (F + kTapsPerCta - 1) / kTapsPerCta), 256, 0, ra::as_stream(stream)>>>(box, H, W, F, fy, fx,
-                                                                                                  band);
+  const cudaError_t le = ra::launch_pdl(build_filters_kernel, dim3(B, 2, (F + kTapsPerCta - 1) / kTapsPerCta), dim3(256),
+                                        (size_t)0, ra::as_stream(stream), box, H, W, F, fy, fx, band);
+  if (le != cudaSuccess) {
+    ra::set_last_error("cudaLaunchKernelEx(build_filters_kernel)", le);
+    return RA_ERR_CUDA;
+  }
   return ra::finish_launch("build_filters_kernel");
 }
 
@@ -429,7 +443,12 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
     const int nx_s = Cs > 0 ? (W * Cs / 4 + 127) / 128 : 0;
     const int nx_c = canvas != nullptr ? (W / 4 + 127) / 128 : 0;
     dim3 grid(nx_s + nx_c, groups, B);
-    extract_rows_kernel<IB><<<grid, 128, smem_rows, s>>>(xs, Cs, canvas, H, W, fy, band, box, F, tmp_s, tmp_c, nx_s);
+    const cudaError_t le = ra::launch_pdl(extract_rows_kernel<IB>, grid, dim3(128), smem_rows, s, xs, Cs, canvas, H, W, fy,
+                                          band, box, F, tmp_s, tmp_c, nx_s);
+    if (le != cudaSuccess) {
+      ra::set_last_error("cudaLaunchKernelEx(extract_rows_kernel)", le);
+      return RA_ERR_CUDA;
+    }
     const int rc = ra::finish_launch("extract_rows_kernel");
     if (rc != RA_OK) return rc;
   }
@@ -445,9 +464,15 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
     }
     attr_bytes = 200 * 1024;
   }
-  extract_cols_kernel<<<dim3(F, B), 256, smem_cols, s>>>(Cs > 0 ? tmp_s : nullptr, Cs,
-                                                         canvas != nullptr ? tmp_c : nullptr, chan_map, fx, band, box,
-                                                         W, F, patch_cstride, x_patch);
+  {
+    const float *ts_arg = Cs > 0 ? tmp_s : nullptr, *tc_arg = canvas != nullptr ? tmp_c : nullptr;
+    const cudaError_t le = ra::launch_pdl(extract_cols_kernel, dim3(F, B), dim3(256), smem_cols, s, ts_arg, Cs, tc_arg,
+                                          chan_map, fx, band, box, W, F, patch_cstride, x_patch);
+    if (le != cudaSuccess) {
+      ra::set_last_error("cudaLaunchKernelEx(extract_cols_kernel)", le);
+      return RA_ERR_CUDA;
+    }
+  }
   return ra::finish_launch("extract_cols_kernel");
 }
 
@@ -460,7 +485,11 @@ extern "C" int ra_paste_back_f32(const float *patch, const float *box, const flo
   if (F > kMaxF) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
   dim3 grid((W + kPbTX - 1) / kPbTX, ((H + kPbTY - 1) / kPbTY + kPbTilesY - 1) / kPbTilesY, B);
-  paste_back_kernel<<<grid, 256, 0, ra::as_stream(stream)>>>(patch, fy, fx, band, box, H, W, F, disable_overwrite,
-                                                             attn_box, y_out, out_bstride, canvas);
+  const cudaError_t le = ra::launch_pdl(paste_back_kernel, grid, dim3(256), (size_t)0, ra::as_stream(stream), patch, fy, fx,
+                                        band, box, H, W, F, disable_overwrite, attn_box, y_out, out_bstride, canvas);
+  if (le != cudaSuccess) {
+    ra::set_last_error("cudaLaunchKernelEx(paste_back_kernel)", le);
+    return RA_ERR_CUDA;
+  }
   return ra::finish_launch("paste_back_kernel");
 }

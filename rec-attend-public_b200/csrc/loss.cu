@@ -387,6 +387,8 @@ __global__ void __launch_bounds__(256) loss_block_kernel(const float *__restrict
 __global__ void score_kernel(const float *__restrict__ h, int Hd, const float *__restrict__ core, int Cd,
                              const float *__restrict__ w, const float *__restrict__ bias, float *__restrict__ s_out,
                              int s_stride) {
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
   __shared__ float red[32];
   const int b = blockIdx.x;
   float a = 0.f;
@@ -570,7 +572,12 @@ extern "C" int ra_score_f32(const float *h, int Hd, const float *core, int Cd, c
                             int B, float *s_out, int s_stride, void *stream) {
   if (!h || !w || !bias || !s_out || Hd < 1 || Cd < 0 || (Cd > 0 && !core) || B < 0) return RA_ERR_INVALID_ARG;
   if (B == 0) return RA_OK;
-  score_kernel<<<B, 256, 0, ra::as_stream(stream)>>>(h, Hd, core, Cd, w, bias, s_out, s_stride);
+  const cudaError_t le = ra::launch_pdl(score_kernel, dim3(B), dim3(256), (size_t)0, ra::as_stream(stream), h, Hd, core, Cd,
+                                        w, bias, s_out, s_stride);
+  if (le != cudaSuccess) {
+    ra::set_last_error("cudaLaunchKernelEx(score_kernel)", le);
+    return RA_ERR_CUDA;
+  }
   return ra::finish_launch("score_kernel");
 }
 
