@@ -293,6 +293,30 @@ int ra_postprocess_f32(const float *y_out, const float *s_out, const float *fg, 
                        float *area, void *stream);
 
 /* --------------------------------------------------------------------------------------
+ * In-graph augmentation — image_ops.random_transformation (image_ops.py:9-113) with the
+ * random draws as arguments: dst = transpose?(flip?(crop(pad(src, padding), off_y, off_x))).
+ * src / dst [N,H,W,C] (NHWC images: N = B; mask stacks [B,T,H,W]: N = B*T, C = 1); off_* in
+ * [0, 2*padding] (tf.random_uniform(maxval = 2*padding)); transpose needs H == W.
+ * phase_train = False is off_y = off_x = padding with no flips (the identity).
+ * -------------------------------------------------------------------------------------- */
+int ra_random_transformation_f32(const float *src, size_t N, int H, int W, int C, int padding, int off_y, int off_x,
+                                 int vflip, int hflip, int transpose, float *dst, void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Training-mode batch normalisation of one conv block — nnlib.batch_norm with
+ * phase_train = True (nnlib.py:65-128) + ReLU + max-pool (nnlib.py:229-253):
+ *   mean, var = moments of x over (B,H,W) (biased);  ema -= (1-decay)*(ema - batch)  (decay 0.9)
+ *   y = pool(relu(x*inv + (beta - mean*inv))),  inv = gamma * rsqrt(var + eps)       (eps 1e-3)
+ * x [B,H,W,C] = raw convolution output incl. bias (e.g. ra_conv3x3_umma_f32 with scale 1,
+ * shift = bias, relu 0, pool 1); C % 4 == 0, C <= 256; ema_* updated in place
+ * (may be NULL), batch_* [C] out (may be NULL); workspace: ra_bn_train_workspace() floats.
+ * -------------------------------------------------------------------------------------- */
+size_t ra_bn_train_workspace(int B, int H, int W, int C);
+int ra_bn_train_block_f32(const float *x, int B, int H, int W, int C, const float *gamma, const float *beta, float eps,
+                          float decay, int pool, int relu, float *workspace, float *ema_mean, float *ema_var,
+                          float *batch_mean, float *batch_var, float *y, void *stream);
+
+/* --------------------------------------------------------------------------------------
  * Optimiser block — full_model.py:1039-1057 / box_model.py:635-652 on one flat fp32 bucket of
  * n trainable elements (the buffer the gradient all-reduce of SURVEY §8e runs on):
  *   g  = grad * grad_scale (1/world after a SUM all-reduce) + wd[i] * param   (wd may be NULL;

@@ -44,6 +44,52 @@ def batch_norm_eval(x, p):
   return x * inv + (p['beta'] - p['ema_mean'] * inv)
 
 
+def random_transformation(x, padding, offset, vflip=False, hflip=False, transpose=False, y=None, d=None, c=None):
+  """image_ops.random_transformation (image_ops.py:9-113) with phase_train=True and the random draws supplied
+  (offset = the tf.random_uniform([2], maxval=2*padding) draw; flips / transpose = the thresholded uniform draws)."""
+  def crop_nhwc(t):
+    tp = F.pad(t, (0, 0, padding, padding, padding, padding))
+    return tp[:, offset[0]:offset[0] + t.shape[1], offset[1]:offset[1] + t.shape[2], :]
+
+  res = {}
+  xr = crop_nhwc(x)
+  yr = None
+  if y is not None:
+    yp = F.pad(y, (padding, padding, padding, padding))
+    yr = yp[:, :, offset[0]:offset[0] + y.shape[2], offset[1]:offset[1] + y.shape[3]]
+  if d is None:
+    if vflip:
+      xr = torch.flip(xr, [1])
+      yr = torch.flip(yr, [2]) if yr is not None else None
+    if hflip:
+      xr = torch.flip(xr, [2])
+      yr = torch.flip(yr, [3]) if yr is not None else None
+    if transpose:
+      xr = xr.permute(0, 2, 1, 3)
+      yr = yr.permute(0, 1, 3, 2) if yr is not None else None
+  res['x'] = xr.contiguous()
+  if yr is not None:
+    res['y'] = yr.contiguous()
+  if d is not None:
+    res['d'] = crop_nhwc(d).contiguous()
+  if c is not None:
+    res['c'] = crop_nhwc(c).contiguous()
+  return res
+
+
+def batch_norm_train(x, p, decay=0.9):
+  """nnlib.py:65-128 with phase_train=True: batch moments over (B,H,W) (tf.nn.moments, biased variance), the EMA
+  shadows move by (1-decay) toward them (tf.train.ExponentialMovingAverage, decay = 1 - 0.1, :101-108), and the
+  batch statistics normalise.  Returns (normed, batch_mean, batch_var, new_ema_mean, new_ema_var)."""
+  mean = x.mean(dim=(0, 1, 2))
+  var = ((x - mean)**2).mean(dim=(0, 1, 2))
+  inv = torch.rsqrt(var + BN_EPS) * p['gamma']
+  normed = x * inv + (p['beta'] - mean * inv)
+  new_mean = p['ema_mean'] - (1.0 - decay) * (p['ema_mean'] - mean)
+  new_var = p['ema_var'] - (1.0 - decay) * (p['ema_var'] - var)
+  return normed, mean, var, new_mean, new_var
+
+
 def conv2d_transpose_same(x, w, b, stride):
   """nnlib.py:372-376.  w is [3,3,Cout,Cin] (TF layout for conv2d_transpose), output
   spatial = in*stride, padding SAME.  For stride 2 this is the full transposed conv

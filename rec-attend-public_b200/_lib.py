@@ -51,11 +51,14 @@ _SIGNATURES = {
     'ra_loss_block_f32': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P],
     'ra_box_gt_step_f32': [_P, _Z, _P, _P, _P, _Z, _I, _I, _I, _I, _P, _I, _P, _P, _P],
     'ra_concat_channels_f32': [_P, _I, _P, _I, _P, _I, _Z, _P, _P],
+    'ra_bn_train_block_f32': [_P, _I, _I, _I, _I, _P, _P, _F, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    'ra_random_transformation_f32': [_P, _Z, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'ra_adam_step_f32': [_P, _P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _P],
     'ra_postprocess_f32': [_P, _P, _P, _I, _I, _I, _I, ctypes.c_double, _F, _P, _P, _P, _P, _P, _P],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last_error', 'ra_launch_count',
-                                         'ra_pairwise_iou_workspace', 'ra_postprocess_workspace'])
+                                         'ra_pairwise_iou_workspace', 'ra_postprocess_workspace',
+                                         'ra_bn_train_workspace'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -85,6 +88,8 @@ def lib():
     l.ra_pairwise_iou_workspace.restype = _Z
     l.ra_postprocess_workspace.argtypes = [_I, _I]
     l.ra_postprocess_workspace.restype = _Z
+    l.ra_bn_train_workspace.argtypes = [_I, _I, _I, _I]
+    l.ra_bn_train_workspace.restype = _Z
     _lib = l
   return _lib
 

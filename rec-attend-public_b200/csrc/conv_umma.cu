@@ -82,9 +82,13 @@ struct UmmaConvParams {
   int RW, RH;       // TMA box: columns x rows of input pixels (low resolution when up == 2)
   int raw_plane_bytes;  // up == 2 only: bytes per channel plane of the landed low-resolution box
   int raw_off;      // up == 2 only: offset of that landing zone inside a stage
+  int split_corr;   // merged mode: accumulate A_lo B_hi in the second accumulator half (RA_UMMA_JOINT_CORR=1: first)
+  int four_term;    // merged mode: the A_lo instruction also spans [B_hi; B_lo] (adds the lo x lo partial product)
   int pdl;          // launched with programmatic stream serialization: griddepcontrol.wait before touching activations
   long long *dbg;   // optional per-CTA timeline (ra_debug_conv_timeline), 8 slots per CTA
 };
+
+__device__ __forceinline__ bool getenv_split_corr(const UmmaConvParams &p) { return p.split_corr != 0; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -221,8 +225,8 @@ __device__ __forceinline__ Item decode_tile(const UmmaConvParams &p, int t) {
 struct IssueCtx {
   uint64_t a0_hi, a1_hi, a0_lo, a1_lo, b;  // A descriptors of the warp's two m-tiles (hi / lo parts), filter desc
   uint32_t d0, d1;                         // TMEM columns of the two m-tiles' first accumulator
-  uint32_t idesc_n, idesc_2n;
-  uint32_t TWP, a_k8, b_k8, b_tap, b_lo, cols_mt, wrap, init_steps;
+  uint32_t idesc_n, idesc_2n, idesc_lo;  // idesc_lo: the A_lo instruction of the merged mode (N or 2N wide)
+  uint32_t TWP, a_k8, b_k8, b_tap, b_lo, cols_mt, wrap, init_steps, lo_col;
 };
 
 // The 9 taps x K8N k8-steps of one channel chunk, run by the ELECTED lane only (the caller branches on it): the
@@ -246,11 +250,18 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx &c) {
         const uint32_t d0 = c.d0 + jc, d1 = c.d1 + jc;
         const uint64_t a0h = c.a0_hi + a_off, a1h = c.a1_hi + a_off, a0l = c.a0_lo + a_off, a1l = c.a1_lo + a_off;
         if (MERGED) {
-          // D[:, 0:N] += A_hi B_hi and D[:, N:2N] += A_hi B_lo in ONE instruction, then D[:, 0:N] += A_lo B_hi
+          // D[:, 0:N] += A_hi B_hi and D[:, N:2N] += A_hi B_lo in ONE instruction, then D[:, 0:N] += A_lo B_hi.
+          // RA_UMMA_4TERM=1 widens the A_lo instruction to [B_hi; B_lo] as well (adds lo x lo, 2^-22 of a product):
+          // MEASURED to change nothing in the end-to-end error (tools/dbg_parity.py: ctrl_out 5e-6 either way) and
+          // to cost 0.2 ms per forward, so the three-term form is the default.
+          // The A_lo B_hi correction goes to the SECOND half of the accumulator (c.lo_col = N), next to A_hi B_lo:
+          // the tensor core truncates every fp32 accumulation, a bias proportional to the accumulator's magnitude,
+          // so the full-magnitude half D[:, 0:N] should see one add per step, not two (tools/dbg_parity.py:
+          // controller output error vs the fp32 oracle with both corrections in one half / split).
           umma_tf32(d0, a0h, b_hi, c.idesc_2n, flag);
           if (TWO) umma_tf32(d1, a1h, b_hi, c.idesc_2n, flag);
-          umma_tf32(d0, a0l, b_hi, c.idesc_n, 1u);
-          if (TWO) umma_tf32(d1, a1l, b_hi, c.idesc_n, 1u);
+          umma_tf32(d0 + c.lo_col, a0l, b_hi, c.idesc_lo, 1u);
+          if (TWO) umma_tf32(d1 + c.lo_col, a1l, b_hi, c.idesc_lo, 1u);
         } else {
           const uint64_t b_lo = b_hi + (uint64_t)c.b_lo;
           umma_tf32(d0, a0h, b_hi, c.idesc_n, flag);
@@ -610,6 +621,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       c.idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NPc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       c.idesc_2n =
           (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * p.NPc) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      c.idesc_lo = p.four_term ? c.idesc_2n : c.idesc_n;
+      // column offset of the A_lo B_hi correction inside an m-tile's accumulator (0: same half as the main sum)
+      c.lo_col = (p.merged && !p.four_term && getenv_split_corr(p)) ? (uint32_t)p.NPc : 0u;
       const uint32_t w_plane = (uint32_t)(2 * p.NPc) * 16u;  // bytes between channel planes of the filter image
       c.TWP = (uint32_t)p.TWP;
       c.a_k8 = 2u * (plane_bytes >> 4);                 // A start-address step of one k8 (two channel planes)
@@ -1204,6 +1218,8 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
     return e == nullptr || atoi(e) != 0;
   }();
   p.pdl = use_pdl ? 1 : 0;
+  p.four_term = getenv("RA_UMMA_4TERM") != nullptr ? 1 : 0;
+  p.split_corr = getenv("RA_UMMA_JOINT_CORR") == nullptr ? 1 : 0;
   if (use_pdl) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

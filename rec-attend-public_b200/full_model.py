@@ -150,7 +150,12 @@ class _ModelBase(object):
             'packed': {}}
 
   def _conv(self, x, wp, scale, shift, pool, relu=True, x2=None, upsample=1, out=None):
-    """One conv block on the tensor cores (csrc/conv_umma.cu)."""
+    """One conv block on the tensor cores (csrc/conv_umma.cu).  RA_CONV_FP32=1 (diagnostics) runs the same block
+    on the CUDA cores in plain fp32 FMA arithmetic (csrc/conv.cu) - the precision reference for the 3xTF32 path."""
+    if os.environ.get('RA_CONV_FP32'):
+      if 'w_dev' not in wp:
+        wp['w_dev'] = self._dev(wp['w'])
+      return ops.conv3x3_block(x, wp['w_dev'], scale, shift, pool=pool, relu=relu, x2=x2, upsample=upsample, out=out)
     B = x.shape[0]
     if B not in wp['packed']:
       w = wp['w']

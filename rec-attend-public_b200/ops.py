@@ -303,3 +303,60 @@ def box_gt_step(attn_box_t, box_bstride, gt_rect, y_gt, noise_t, noise_bstride, 
   B, T, H, W = y_gt.shape
   _lib.call('ra_box_gt_step_f32', _p(attn_box_t), box_bstride, _p(gt_rect), _p(y_gt), _p(noise_t), noise_bstride, B,
             T, H, W, _p(iou_t), iou_bstride, _p(grd_ws), _p(canvas), _stream())
+
+
+# ----------------------------------------------------------------------------- training-mode conv block
+def batch_norm_train_block(x_raw, gamma, beta, ema_mean=None, ema_var=None, pool=1, relu=True, eps=1e-3, decay=0.9,
+                           out=None):
+  """nnlib.batch_norm with phase_train=True (nnlib.py:65-128) + activation + max-pool (nnlib.py:229-253) on the raw
+  convolution output x_raw [B,H,W,C] (bias included): batch moments, EMA shadows updated IN PLACE
+  (shadow -= (1-decay)(shadow - batch)), y = pool(relu(bn(x))).  Returns (y, batch_mean, batch_var)."""
+  _chk(x_raw, gamma, beta, ema_mean, ema_var, out)
+  B, H, W, C = x_raw.shape
+  dev = x_raw.device
+  n_ws = _lib.lib().ra_bn_train_workspace(B, H, W, C) if B > 0 else 1
+  if n_ws == 0:
+    raise _lib.RecAttendError('ra_bn_train_block: unsupported channel count {}'.format(C))
+  ws = torch.empty((n_ws,), device=dev, dtype=torch.float32)
+  if out is None:
+    out = torch.empty((B, H // pool, W // pool, C), device=dev, dtype=torch.float32)
+  bm = torch.empty((C,), device=dev, dtype=torch.float32)
+  bv = torch.empty((C,), device=dev, dtype=torch.float32)
+  _lib.call('ra_bn_train_block_f32', _p(x_raw), B, H, W, C, _p(gamma), _p(beta), float(eps), float(decay), pool,
+            1 if relu else 0, _p(ws), _p(ema_mean), _p(ema_var), _p(bm), _p(bv), _p(out), _stream())
+  return out, bm, bv
+
+
+def conv3x3_block_train(x, wpack, bias, gamma, beta, ema_mean=None, ema_var=None, pool=1, relu=True, x2=None,
+                        upsample=1):
+  """One nn.cnn / nn.dcnn layer in TRAINING mode (nnlib.py:229-253, :372-400): tensor-core convolution + bias, then
+  batch-statistics BN + ReLU + max-pool.  wpack from pack_umma_weights for this layer's plan."""
+  Cout = bias.shape[0]
+  ones = torch.ones_like(bias)
+  raw = conv3x3_block_umma(x, wpack, Cout, ones, bias, pool=1, relu=False, x2=x2, upsample=upsample)
+  return batch_norm_train_block(raw, gamma, beta, ema_mean, ema_var, pool=pool, relu=relu)
+
+
+# ----------------------------------------------------------------------------- augmentation
+def random_transformation(x, padding, offset, vflip=False, hflip=False, transpose=False, y=None, d=None, c=None):
+  """image_ops.random_transformation (image_ops.py:9-113) in training mode with the random draws supplied:
+  offset = (off_y, off_x) in [0, 2*padding], flips / transpose as booleans (the reference draws them only when no
+  orientation input `d` is given, :46-49).  x [B,H,W,3], y [B,T,H,W], d [B,H,W,8], c [B,H,W,C'].  Returns a dict with
+  the keys of the reference ('x', 'y', 'd', 'c').  phase_train=False == offset (padding, padding), no flips."""
+  if d is not None and (vflip or hflip or transpose):
+    raise _lib.RecAttendError('orientation mode is on: no random flips / transpose (image_ops.py:46-49)')
+  out = {}
+  for key, t, is_stack in (('x', x, False), ('y', y, True), ('d', d, False), ('c', c, False)):
+    if t is None:
+      continue
+    _chk(t)
+    if is_stack:
+      B, T, H, W = t.shape
+      N, C = B * T, 1
+    else:
+      N, H, W, C = t.shape
+    dst = torch.empty_like(t)
+    _lib.call('ra_random_transformation_f32', _p(t), N, H, W, C, int(padding), int(offset[0]), int(offset[1]),
+              1 if vflip else 0, 1 if hflip else 0, 1 if transpose else 0, _p(dst), _stream())
+    out[key] = dst
+  return out

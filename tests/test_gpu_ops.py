@@ -580,3 +580,88 @@ def test_postprocess_errors(ops):
     PP.postprocess(torch.zeros((1, 2, 4, 4), device='cuda'), torch.zeros((1, 3), device='cuda'))
   out = PP.postprocess(torch.zeros((0, 2, 4, 4), device='cuda'), torch.zeros((0, 2), device='cuda'))
   assert tuple(out['label'].shape) == (0, 4, 4)
+
+
+# ----------------------------------------------------------------------------- training-mode BN block
+@pytest.mark.parametrize('B,H,W,C,pool', [(3, 16, 24, 16, 2), (2, 12, 12, 96, 2), (4, 48, 48, 16, 1), (1, 6, 10, 64, 1),
+                                          (8, 128, 256, 16, 2)])
+def test_batch_norm_train_block(ops, B, H, W, C, pool):
+  """nnlib.batch_norm(phase_train=True) + ReLU + max-pool against the oracle (batch moments, EMA update)."""
+  rng = np.random.default_rng(B * 100 + C)
+  x = (rng.standard_normal((B, H, W, C)) * rng.uniform(0.5, 3.0, C) + rng.uniform(-4, 4, C)).astype(np.float32)
+  p = {'gamma': rng.uniform(0.5, 1.5, C).astype(np.float32), 'beta': rng.standard_normal(C).astype(np.float32),
+       'ema_mean': rng.standard_normal(C).astype(np.float32), 'ema_var': rng.uniform(0.5, 1.5, C).astype(np.float32)}
+  pt = {k: torch.from_numpy(v) for k, v in p.items()}
+  normed, mean, var, new_mean, new_var = OM.batch_norm_train(torch.from_numpy(x), pt)
+  ref = torch.relu(normed)
+  if pool == 2:
+    ref = OM.max_pool_same(ref, 2)
+  em, ev = _g(p['ema_mean'].copy()), _g(p['ema_var'].copy())
+  y, bm, bv = ops.batch_norm_train_block(_g(x), _g(p['gamma']), _g(p['beta']), em, ev, pool=pool)
+  assert rel_err(bm.cpu().numpy(), mean.numpy()) < 1e-5 and rel_err(bv.cpu().numpy(), var.numpy()) < 1e-4
+  assert rel_err(em.cpu().numpy(), new_mean.numpy()) < 1e-5 and rel_err(ev.cpu().numpy(), new_var.numpy()) < 1e-4
+  assert rel_err(y.cpu().numpy(), ref.numpy()) < 1e-4
+  # without EMA buffers / without ReLU
+  y2, _, _ = ops.batch_norm_train_block(_g(x), _g(p['gamma']), _g(p['beta']), None, None, pool=pool, relu=False)
+  ref2 = OM.max_pool_same(normed, 2) if pool == 2 else normed
+  assert rel_err(y2.cpu().numpy(), ref2.numpy()) < 1e-4
+
+
+def test_conv_block_train_mode(ops):
+  """A whole training-mode layer: tcgen05 conv + bias, batch-stat BN, ReLU, pool (nnlib.py:229-253)."""
+  rng = np.random.default_rng(11)
+  B, H, W, Cin, Cout, pool = 4, 32, 48, 16, 32, 2
+  x = rng.standard_normal((B, H, W, Cin)).astype(np.float32)
+  w = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+  b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+  p = {'gamma': rng.uniform(0.5, 1.5, Cout).astype(np.float32), 'beta': rng.standard_normal(Cout).astype(np.float32),
+       'ema_mean': np.zeros(Cout, np.float32), 'ema_var': np.ones(Cout, np.float32)}
+  KC, NPc, nsp, _ = ops.umma_plan(Cin, Cout, H, W, 1, B)
+  wp = _g(ops.pack_umma_weights(w, KC, NPc, nsp))
+  y, bm, bv = ops.conv3x3_block_train(_g(x), wp, _g(b), _g(p['gamma']), _g(p['beta']), pool=pool)
+  raw = OM.conv2d_same(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b))
+  normed, mean, var, _, _ = OM.batch_norm_train(raw, {k: torch.from_numpy(v) for k, v in p.items()})
+  ref = OM.max_pool_same(torch.relu(normed), 2)
+  assert rel_err(bm.cpu().numpy(), mean.numpy()) < 1e-5 and rel_err(y.cpu().numpy(), ref.numpy()) < 1e-4
+
+
+def test_batch_norm_train_errors(ops):
+  from rec_attend_b200 import _lib
+  with pytest.raises(_lib.RecAttendError):
+    ops.batch_norm_train_block(torch.zeros((1, 4, 4, 6), device='cuda'), torch.ones(6, device='cuda'),
+                               torch.zeros(6, device='cuda'))  # C % 4
+
+
+# ----------------------------------------------------------------------------- augmentation
+@pytest.mark.parametrize('H,W,pad,off,vf,hf,tr,with_d', [(16, 16, 4, (4, 4), False, False, False, False),
+                                                         (16, 16, 4, (0, 7), True, False, True, False),
+                                                         (12, 20, 3, (6, 1), True, True, False, False),
+                                                         (24, 24, 8, (16, 0), False, True, True, False),
+                                                         (12, 20, 5, (2, 9), False, False, False, True)])
+def test_random_transformation(ops, H, W, pad, off, vf, hf, tr, with_d):
+  rng = np.random.default_rng(H + W + pad)
+  B, T = 2, 3
+  x = rng.random((B, H, W, 3)).astype(np.float32)
+  y = (rng.random((B, T, H, W)) > 0.5).astype(np.float32)
+  d = rng.random((B, H, W, 8)).astype(np.float32) if with_d else None
+  c = rng.random((B, H, W, 2)).astype(np.float32) if with_d else None
+  ref = OM.random_transformation(torch.from_numpy(x), pad, off, vf, hf, tr, y=torch.from_numpy(y),
+                                 d=None if d is None else torch.from_numpy(d), c=None if c is None else torch.from_numpy(c))
+  out = ops.random_transformation(_g(x), pad, off, vf, hf, tr, y=_g(y), d=None if d is None else _g(d),
+                                  c=None if c is None else _g(c))
+  assert sorted(out) == sorted(ref)
+  for k in ref:
+    assert (out[k].cpu().numpy() == ref[k].numpy()).all(), k
+  if off == (pad, pad) and not (vf or hf or tr):
+    assert (out['x'].cpu().numpy() == x).all()  # the eval-mode identity (image_ops.py:70-80,106-112)
+
+
+def test_random_transformation_errors(ops):
+  from rec_attend_b200 import _lib
+  x = torch.zeros((1, 8, 12, 3), device='cuda')
+  with pytest.raises(_lib.RecAttendError):
+    ops.random_transformation(x, 2, (1, 1), transpose=True)            # H != W
+  with pytest.raises(_lib.RecAttendError):
+    ops.random_transformation(x, 2, (5, 0))                            # offset > 2*padding
+  with pytest.raises(_lib.RecAttendError):
+    ops.random_transformation(x, 2, (1, 1), hflip=True, d=torch.zeros((1, 8, 12, 8), device='cuda'))

@@ -168,3 +168,35 @@ def test_box_model_forward_shapes():
   m = OM.box_model_forward(opt, w, batch)
   assert m['attn_box'].shape == (2, 3, 32, 64) and m['s_out'].shape == (2, 3)
   assert m['match_box'].shape == (2, 3, 3) and torch.isfinite(m['loss'])
+
+
+def test_batch_norm_train_matches_torch_and_ema_rule():
+  """oracle.batch_norm_train (nnlib.py:65-128, phase_train=True): biased batch moments, eps 1e-3, EMA decay 0.9."""
+  import torch.nn.functional as F
+  g = torch.Generator().manual_seed(0)
+  x = torch.randn((3, 5, 7, 8), generator=g) * 2 + 1
+  p = {'gamma': torch.rand(8, generator=g) + 0.5, 'beta': torch.randn(8, generator=g),
+       'ema_mean': torch.randn(8, generator=g), 'ema_var': torch.rand(8, generator=g) + 0.5}
+  normed, mean, var, nm, nv = OM.batch_norm_train(x, p)
+  ref = F.batch_norm(x.permute(0, 3, 1, 2), None, None, p['gamma'], p['beta'], training=True, eps=1e-3).permute(0, 2, 3, 1)
+  assert torch.allclose(normed, ref, atol=1e-5)
+  assert torch.allclose(mean, x.reshape(-1, 8).mean(0), atol=1e-6)
+  assert torch.allclose(var, x.reshape(-1, 8).var(0, unbiased=False), atol=1e-5)
+  assert torch.allclose(nm, 0.9 * p['ema_mean'] + 0.1 * mean, atol=1e-6)
+  assert torch.allclose(nv, 0.9 * p['ema_var'] + 0.1 * var, atol=1e-6)
+
+
+def test_random_transformation_oracle_semantics():
+  """image_ops.py:9-113: offset == padding without flips is the identity (the eval path); flips and transpose
+  compose in the reference's order (crop, vflip, hflip, transpose)."""
+  g = torch.Generator().manual_seed(1)
+  x = torch.rand((2, 6, 6, 3), generator=g)
+  y = torch.rand((2, 4, 6, 6), generator=g)
+  r = OM.random_transformation(x, 2, (2, 2), y=y)
+  assert torch.equal(r['x'], x) and torch.equal(r['y'], y)
+  r = OM.random_transformation(x, 2, (0, 4), y=y)           # shifted crop: zeros come in from the padding
+  assert torch.equal(r['x'][:, 2:, :4], x[:, :4, 2:]) and float(r['x'][:, :2].abs().sum()) == 0.0
+  assert float(r['x'][:, :, 4:].abs().sum()) == 0.0
+  r = OM.random_transformation(x, 2, (2, 2), vflip=True, hflip=True, transpose=True, y=y)
+  assert torch.equal(r['x'], torch.flip(x, [1, 2]).permute(0, 2, 1, 3))
+  assert torch.equal(r['y'], torch.flip(y, [2, 3]).permute(0, 1, 3, 2))

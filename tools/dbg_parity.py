@@ -1,13 +1,25 @@
-import sys; sys.path.insert(0,'.')
+"""Where does the full-resolution parity error come from?  Per decode step: max |cuda - oracle| of the controller
+output, the box parameters, attn_box and y_out (KITTI arch 256x512, T=20).  python tools/dbg_parity.py [arch H W T B]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import rec_attend_b200 as ra
 from rec_attend_b200.full_model import FullModel
 from oracle import model as OM
-opt=ra.config.full_model_opt('cvppp',128,128,8); b=ra.synthetic.make_batch(opt,1); w=ra.synthetic.make_weights(opt)
-ref=OM.full_model_forward(opt,w,b)
-out=FullModel(opt).load_weights(w).forward(b)
-for k in ['ctrl_out','attn_ctr','attn_size','attn_lg_var','attn_box','y_out','x_patch','y_out_patch','s_out','canvas','h_ctrl']:
-    a=out[k].cpu().numpy(); r=ref[k].numpy()
-    err=np.abs(a-r); 
-    print(k, 'max rel %.2e'%(err.max()/np.abs(r).max()), 'per-step', ['%.1e'%(np.abs(a[:,t]-r[:,t]).max()/np.abs(r).max()) for t in range(8)] if a.ndim>1 and a.shape[1]==8 else '')
-print('ctr', ref['attn_ctr'][0].numpy().T, 'box gamma', np.exp(ref['ctrl_out'][0,:,7].numpy()))
+
+arch, H, W, T, B = (sys.argv[1:] + ['kitti', 256, 512, 20, 2])[:5] if len(sys.argv) > 1 else ('kitti', 256, 512, 20, 2)
+H, W, T, B = int(H), int(W), int(T), int(B)
+opt = ra.config.full_model_opt(arch, H, W, T)
+batch = ra.synthetic.make_batch(opt, B, seed=1234)
+w = ra.synthetic.make_weights(opt, seed=4321)
+with torch.no_grad():
+  ref = OM.full_model_forward(opt, w, batch)
+out = FullModel(opt).load_weights(w).forward(batch)
+torch.cuda.synchronize()
+print('mode', 'fp32 CUDA-core convs' if os.environ.get('RA_CONV_FP32') else 'tcgen05 3xTF32 convs', arch, H, W, T, B)
+for k in ('ctrl_out', 'attn_ctr', 'attn_size', 'attn_lg_var', 'x_patch', 'y_out_patch', 'attn_box', 'y_out', 's_out'):
+  if k not in ref or k not in out:
+    continue
+  a, b = out[k].float().cpu().numpy(), ref[k].numpy()
+  per_t = [float(np.abs(a[:, t] - b[:, t]).max()) for t in range(T)]
+  print('{:12s} scale {:9.3g}  max|d| per step: {}'.format(k, float(np.abs(b).max()), ' '.join('%.1e' % v for v in per_t)))
