@@ -405,8 +405,8 @@ def run_ours(args):
                    'height': cfg['H'], 'width': cfg['W'], 'parallelism': 'dp{}'.format(world),
                    'l2': 'inputs {:.0f} MB + per-step working set exceed the 126 MB L2'.format(h2d / 1e6),
                    'step': 'eval forward (T-step decode) + matching loss block',
-                   'chains': '{} sub-batch chains of the decode loop run as parallel CUDA-graph branches'.format(
-                       len(chains))},
+                   'graph': 'one CUDA graph per forward ({} sub-batch chain{}); gt-box, hard-IoU and score-head '
+                            'kernels on parallel branches'.format(len(chains), '' if len(chains) == 1 else 's')},
         'e2e': {'value': e2e_value, 'unit': 'masks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps, 'fetch': fetch,
                 'pipeline': 'H2D of step i+1 overlaps the compute of step i (double-buffered static inputs)'},
