@@ -106,13 +106,26 @@ def conv2d_transpose_same(x, w, b, stride):
   return y.permute(0, 2, 3, 1) + b
 
 
-def run_cnn(x, weights, scope, nlayers, pool, copy):
+def _batch_norm(y, weights, scope, layer, copy, ema_out):
+  """Eval mode (ema_out is None): EMA statistics.  Training mode: batch statistics; the moved EMA shadows are
+  recorded in ema_out under the weight-dict keys (nnlib.py:101-127)."""
+  p = _bn(weights, scope, layer, copy)
+  if ema_out is None:
+    return batch_norm_eval(y, p)
+  normed, _, _, new_mean, new_var = batch_norm_train(y, p)
+  k = '{}_{}_{}_'.format(scope, layer, copy)
+  ema_out[k + 'ema_mean'] = new_mean
+  ema_out[k + 'ema_var'] = new_var
+  return normed
+
+
+def run_cnn(x, weights, scope, nlayers, pool, copy, ema_out=None):
   """nnlib.py:214-255.  conv+b -> BN(copy) -> relu -> maxpool; returns every layer."""
   h = []
   for ii in range(nlayers):
     inp = x if ii == 0 else h[-1]
     y = conv2d_same(inp, weights['{}_w_{}'.format(scope, ii)], weights['{}_b_{}'.format(scope, ii)])
-    y = batch_norm_eval(y, _bn(weights, scope, ii, copy))
+    y = _batch_norm(y, weights, scope, ii, copy, ema_out)
     y = torch.relu(y)
     if pool[ii] > 1:
       y = max_pool_same(y, pool[ii])
@@ -120,7 +133,7 @@ def run_cnn(x, weights, scope, nlayers, pool, copy):
   return h
 
 
-def run_dcnn(x, weights, scope, nlayers, unpool, copy, skip=None):
+def run_dcnn(x, weights, scope, nlayers, unpool, copy, skip=None, ema_out=None):
   """nnlib.py:339-402.  concat(prev, skip) -> conv2d_transpose+b -> BN(copy) -> relu
   (relu also on the last layer, full_model.py:487)."""
   h = []
@@ -130,7 +143,7 @@ def run_dcnn(x, weights, scope, nlayers, unpool, copy, skip=None):
       inp = torch.cat([inp, skip[ii]], 3)
     y = conv2d_transpose_same(inp, weights['{}_w_{}'.format(scope, ii)], weights['{}_b_{}'.format(scope, ii)],
                               unpool[ii])
-    y = batch_norm_eval(y, _bn(weights, scope, ii, copy))
+    y = _batch_norm(y, weights, scope, ii, copy, ema_out)
     y = torch.relu(y)
     h.append(y)
   return h
@@ -353,7 +366,7 @@ def _t(a):
   return torch.as_tensor(np.asarray(a), dtype=torch.float32)
 
 
-def controller_step(opt, weights, ccnn_inp, tt):
+def controller_step(opt, weights, ccnn_inp, tt, ema_out=None):
   """full_model.py:663-725 == box_model.py:413-470: ctrl CNN, 5 glimpse iterations of the
   LSTM, controller head and the box-parameter maths.  Returns a dict of per-step tensors."""
   H, W = opt['inp_height'], opt['inp_width']
@@ -362,7 +375,7 @@ def controller_step(opt, weights, ccnn_inp, tt):
   n_iter = opt['num_ctrl_rnn_iter']
   B = ccnn_inp.shape[0]
   nl = len(opt['ctrl_cnn_filter_size'])
-  h_ccnn = run_cnn(ccnn_inp, weights, 'ctrl_cnn', nl, opt['ctrl_cnn_pool'], tt)
+  h_ccnn = run_cnn(ccnn_inp, weights, 'ctrl_cnn', nl, opt['ctrl_cnn_pool'], tt, ema_out=ema_out)
   feat = h_ccnn[-1]
   gdim = feat.shape[1] * feat.shape[2]
   crnn_inp = feat.reshape(B, gdim, feat.shape[3])  # p = y*w' + x
@@ -422,9 +435,11 @@ def attn_box_from(opt, ctr, size, lg_var, box_lg_gamma):
   return box.reshape(B, 1, H, W), f_y, f_x
 
 
-def full_model_forward(opt, weights, batch, with_loss=True):
+def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False):
   """full_model.get_model in eval mode (phase_train=False, random_transformation is the
-  identity, image_ops.py:70-112; the knob terms vanish because phase_train_f = 0).
+  identity, image_ops.py:70-112; the knob terms vanish because phase_train_f = 0), or - phase_train=True - the
+  training-mode forward with use_knob=False and the identity draw of the augmentation: every BN layer normalises with
+  the batch statistics and moves its EMA shadows (nnlib.py:96-119); the result then carries 'ema_updates'.
 
   batch: dict of numpy/torch fp32: x [B,H,W,3], y_gt [B,T,H,W], s_gt [B,T], optional
   d_in [B,H,W,8], y_in [B,H,W,C].  weights: dict keyed like full_model_read.py:32-70.
@@ -448,6 +463,7 @@ def full_model_forward(opt, weights, batch, with_loss=True):
   d_in = _t(batch['d_in']) if add_d_out else None
   y_in = _t(batch['y_in']) if add_d_out else None
 
+  ema_out = {} if phase_train else None
   canvas = torch.zeros(B, H, W, 1)
   n_acnn = len(opt['attn_cnn_filter_size'])
   n_adcnn = len(opt['attn_dcnn_filter_size'])
@@ -467,21 +483,22 @@ def full_model_forward(opt, weights, batch, with_loss=True):
     acnn_inp = torch.cat(acnn_list, 3)
     ccnn_inp = torch.cat(ccnn_list, 3)
 
-    c = controller_step(opt, weights, ccnn_inp, tt)
+    c = controller_step(opt, weights, ccnn_inp, tt, ema_out=ema_out)
     ctr, size = c['ctr'], c['size']
     box, f_y, f_x = attn_box_from(opt, ctr, size, c['lg_var'], c['box_lg_gamma'])
     top_left, bot_right = ctr - size / 2.0, ctr + size / 2.0
 
     # full_model.py:788-807
     x_patch = torch.exp(c['lg_gamma']).view(-1, 1, 1, 1) * extract_patch(acnn_inp, f_y, f_x, acnn_inp.shape[3])
-    h_acnn = run_cnn(x_patch, weights, 'attn_cnn', n_acnn, opt['attn_cnn_pool'], tt)
+    h_acnn = run_cnn(x_patch, weights, 'attn_cnn', n_acnn, opt['attn_cnn_pool'], tt, ema_out=ema_out)
     h_core = h_acnn[-1].reshape(B, -1)  # (h, w, c) flatten order, full_model.py:794
     if add_skip:
       # full_model.py:497-499,799-803: every layer >= 1 gets a skip
       skip = [None] + (h_acnn[::-1][1:] + [x_patch])[:n_adcnn - 1]
     else:
       skip = None
-    h_adcnn = run_dcnn(h_acnn[-1], weights, 'attn_dcnn', n_adcnn, opt['attn_dcnn_pool'], tt, skip=skip)
+    h_adcnn = run_dcnn(h_acnn[-1], weights, 'attn_dcnn', n_adcnn, opt['attn_dcnn_pool'], tt, skip=skip,
+                       ema_out=ema_out)
 
     # full_model.py:810-822
     y = extract_patch(h_adcnn[-1], f_y.transpose(1, 2), f_x.transpose(1, 2), 1)
@@ -511,6 +528,8 @@ def full_model_forward(opt, weights, batch, with_loss=True):
   sub = int(np.prod(opt['ctrl_cnn_pool']))
   model['ctrl_rnn_glimpse_map'] = gm.reshape(B, T, gm.shape[2], H // sub, W // sub)
   model['canvas'] = canvas
+  if ema_out is not None:
+    model['ema_updates'] = ema_out
   if not with_loss:
     return model
 

@@ -37,6 +37,14 @@ def _fold_bn(weights, scope, layer, T, bias):
   return scale, shift
 
 
+def _bn_params(weights, scope, layer, T, bias):
+  """Per-(layer, step) BN parameters and EMA shadows as [T, C] arrays + the conv bias (training-mode forward)."""
+  out = {'bias': np.asarray(bias, np.float32)}
+  for n in ('gamma', 'beta', 'ema_mean', 'ema_var'):
+    out[n] = np.stack([np.asarray(weights['{}_{}_{}_{}'.format(scope, layer, t, n)], np.float32) for t in range(T)])
+  return out
+
+
 def _deconv_to_conv(w):
   """conv2d_transpose filter [kh,kw,Cout,Cin] (nnlib.py:320-325,372-376) -> the HWIO filter of
   the equivalent stride-1 convolution over the (zero-inserted) input: spatial flip + swap."""
@@ -97,6 +105,8 @@ class _ModelBase(object):
     self.w = None
     self.wd_term = 0.0
     self._bufs = {}
+    self._bn_layers = []   # (device-key prefix, weight-dict scope, layer) of every BN layer
+    self._bn_dirty = False  # a training-mode forward has moved the EMA shadows: refold before the next eval forward
     self.n_chains = int(os.environ.get('RA_CHAINS', '1'))  # sub-batch chains of the decode loop (see _chains)
 
   def _fixed_var(self):
@@ -130,6 +140,7 @@ class _ModelBase(object):
       sc, sh = _fold_bn(weights, 'ctrl_cnn', i, T, np.asarray(weights['ctrl_cnn_b_%d' % i], np.float32))
       w['ccnn_scale%d' % i] = self._dev(sc)
       w['ccnn_shift%d' % i] = self._dev(sh)
+      self._load_bn(w, 'ccnn', 'ctrl_cnn', i, weights)
     gates = 'ifou'  # kernel gate order i, f, o, u
     w['lstm_wx'] = self._dev(np.stack([weights['ctrl_lstm_w_x' + g] for g in gates]))
     w['lstm_wh'] = self._dev(np.stack([weights['ctrl_lstm_w_h' + g] for g in gates]))
@@ -142,6 +153,14 @@ class _ModelBase(object):
       raise _lib.RecAttendError('glimpse_mlp_w_1 maps to {} positions, the feature map has {}'.format(
           w['glimpse_mlp_w_1'].shape[1], self.P))
     return w
+
+  def _load_bn(self, w, prefix, scope, i, weights):
+    """Unfolded BN parameters of layer i for the training-mode forward (batch statistics, EMA update in place)."""
+    bp = _bn_params(weights, scope, i, self.T, weights['{}_b_{}'.format(scope, i)])
+    for n, a in bp.items():
+      w['{}_{}{}'.format(prefix, n, i)] = self._dev(a)
+    w['{}_one{}'.format(prefix, i)] = torch.ones(bp['bias'].shape[0], device=self.device)
+    self._bn_layers.append((prefix, scope, i))
 
   def _pack(self, w_hwio, Hout, Wout, pool):
     """Register a conv-form HWIO filter for the tcgen05 kernel; the shared-memory image depends on the
@@ -157,12 +176,37 @@ class _ModelBase(object):
         wp['w_dev'] = self._dev(wp['w'])
       return ops.conv3x3_block(x, wp['w_dev'], scale, shift, pool=pool, relu=relu, x2=x2, upsample=upsample, out=out)
     B = x.shape[0]
-    if B not in wp['packed']:
+    key = (B, pool)  # the tile plan (hence the packed image) depends on the batch size and on the pooling
+    if key not in wp['packed']:
       w = wp['w']
-      KC, NPc, nsp, _ = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], wp['pool'], B)
-      wp['packed'][B] = self._dev(ops.pack_umma_weights(w, KC, NPc, nsp))
-    return ops.conv3x3_block_umma(x, wp['packed'][B], wp['w'].shape[3], scale, shift, pool=pool, relu=relu, x2=x2,
+      KC, NPc, nsp, _ = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], pool, B)
+      wp['packed'][key] = self._dev(ops.pack_umma_weights(w, KC, NPc, nsp))
+    return ops.conv3x3_block_umma(x, wp['packed'][key], wp['w'].shape[3], scale, shift, pool=pool, relu=relu, x2=x2,
                                   upsample=upsample, out=out)
+
+  def _block(self, train, x, wp, prefix, i, t, pool, relu=True, x2=None, upsample=1, out=None):
+    """One nn.cnn / nn.dcnn layer.  Eval: conv with the folded EMA batch norm in its epilogue.  Training
+    (nnlib.py:96-119): raw conv + bias, then batch-statistics BN + ReLU + pool, EMA shadows of copy t moved in place."""
+    w = self.w
+    if not train:
+      return self._conv(x, wp, w['%s_scale%d' % (prefix, i)][t], w['%s_shift%d' % (prefix, i)][t], pool, relu=relu,
+                        x2=x2, upsample=upsample, out=out)
+    raw = self._conv(x, wp, w['%s_one%d' % (prefix, i)], w['%s_bias%d' % (prefix, i)], 1, relu=False, x2=x2,
+                     upsample=upsample)
+    y, _, _ = ops.batch_norm_train_block(raw, w['%s_gamma%d' % (prefix, i)][t], w['%s_beta%d' % (prefix, i)][t],
+                                         w['%s_ema_mean%d' % (prefix, i)][t], w['%s_ema_var%d' % (prefix, i)][t],
+                                         pool=pool, relu=relu, eps=BN_EPS, out=out)
+    return y
+
+  def _refold_bn(self):
+    """After training-mode forwards: fold the moved EMA shadows back into the eval-mode scale / shift rows."""
+    w = self.w
+    for prefix, _, i in self._bn_layers:
+      inv = w['%s_gamma%d' % (prefix, i)] * torch.rsqrt(w['%s_ema_var%d' % (prefix, i)] + BN_EPS)
+      w['%s_scale%d' % (prefix, i)].copy_(inv)
+      w['%s_shift%d' % (prefix, i)].copy_(w['%s_beta%d' % (prefix, i)] - w['%s_ema_mean%d' % (prefix, i)] * inv +
+                                           w['%s_bias%d' % (prefix, i)] * inv)
+    self._bn_dirty = False
 
   def _weight_decay_term(self, weights):
     """nnlib.py:59-61: sum over conv/mlp/lstm weight matrices of wd * ||w||^2 / 2 (a constant
@@ -176,8 +220,16 @@ class _ModelBase(object):
     return tot
 
   def export_weights(self):
-    """The weights as loaded (reference key schema, TF layouts)."""
-    return {k: np.array(v) for k, v in self._raw_weights.items()}
+    """The weights in the reference key schema (TF layouts); the BN EMA shadows reflect every training-mode forward
+    run since load_weights."""
+    out = {k: np.array(v) for k, v in self._raw_weights.items()}
+    if self.w is not None:
+      for prefix, scope, i in self._bn_layers:
+        for n in ('ema_mean', 'ema_var'):
+          a = self.w['%s_%s%d' % (prefix, n, i)].cpu().numpy()
+          for t in range(self.T):
+            out['{}_{}_{}_{}'.format(scope, i, t, n)] = a[t].copy()
+    return out
 
   # ------------------------------------------------------------------ shared pieces
   def _inputs(self, batch):
@@ -253,16 +305,23 @@ class _ModelBase(object):
                out=bufs['static_pre'])
     bufs['canvas'].zero_()  # full_model.py:239
 
-  def _controller(self, bufs, t):
+  def _controller(self, bufs, t, train=False):
     """full_model.py:663-725: controller CNN (BN copy t) + glimpse LSTM + head -> box params."""
     w = self.w
     B, H, W = bufs['canvas'].shape
     _lib.TAG = 'ctrl_cnn'
-    ops.canvas_conv(bufs['static_pre'], bufs['canvas'], w['ccnn_w0_canvas'], w['ccnn_scale0'][t],
-                    w['ccnn_shift0'][t], pool=self.ctrl_pool[0], relu=True, out=bufs['ccnn'][0])
+    if not train:
+      ops.canvas_conv(bufs['static_pre'], bufs['canvas'], w['ccnn_w0_canvas'], w['ccnn_scale0'][t],
+                      w['ccnn_shift0'][t], pool=self.ctrl_pool[0], relu=True, out=bufs['ccnn'][0])
+    else:
+      # raw layer-0 output = static part + canvas part + bias at full resolution, then batch-statistics BN
+      raw0 = ops.canvas_conv(bufs['static_pre'], bufs['canvas'], w['ccnn_w0_canvas'], w['ccnn_one0'], w['ccnn_bias0'],
+                             pool=1, relu=False)
+      ops.batch_norm_train_block(raw0, w['ccnn_gamma0'][t], w['ccnn_beta0'][t], w['ccnn_ema_mean0'][t],
+                                 w['ccnn_ema_var0'][t], pool=self.ctrl_pool[0], relu=True, eps=BN_EPS,
+                                 out=bufs['ccnn'][0])
     for i in range(1, len(self.ctrl_pool)):
-      self._conv(bufs['ccnn'][i - 1], w['ccnn_w%d' % i], w['ccnn_scale%d' % i][t], w['ccnn_shift%d' % i][t],
-                 self.ctrl_pool[i], out=bufs['ccnn'][i])
+      self._block(train, bufs['ccnn'][i - 1], w['ccnn_w%d' % i], 'ccnn', i, t, self.ctrl_pool[i], out=bufs['ccnn'][i])
     feat = bufs['ccnn'][-1].view(B, self.P, -1)
     _lib.TAG = 'controller'
     ops.controller_step(feat, w['lstm_wx'], w['lstm_wh'], w['lstm_b'], w['glimpse_mlp_w_0'], w['glimpse_mlp_b_0'],
@@ -318,6 +377,8 @@ class FullModel(_ModelBase):
   def load_weights(self, weights):
     T = self.T
     self._raw_weights = {k: np.asarray(v, np.float32) for k, v in weights.items()}
+    self._bn_layers = []
+    self._bn_dirty = False
     w = self._load_controller(weights)
     sz = self.F
     for i in range(len(self.attn_pool)):
@@ -328,6 +389,7 @@ class FullModel(_ModelBase):
       sz //= self.attn_pool[i]
       sc, sh = _fold_bn(weights, 'attn_cnn', i, T, np.asarray(weights['attn_cnn_b_%d' % i], np.float32))
       w['acnn_scale%d' % i], w['acnn_shift%d' % i] = self._dev(sc), self._dev(sh)
+      self._load_bn(w, 'acnn', 'attn_cnn', i, weights)
     for i in range(len(self.dcnn_pool)):
       sz *= self.dcnn_pool[i]
       wi = _deconv_to_conv(np.asarray(weights['attn_dcnn_w_%d' % i], np.float32))
@@ -336,6 +398,7 @@ class FullModel(_ModelBase):
       w['adcnn_w%d' % i] = self._pack(wi, sz, sz, 1)
       sc, sh = _fold_bn(weights, 'attn_dcnn', i, T, np.asarray(weights['attn_dcnn_b_%d' % i], np.float32))
       w['adcnn_scale%d' % i], w['adcnn_shift%d' % i] = self._dev(sc), self._dev(sh)
+      self._load_bn(w, 'adcnn', 'attn_dcnn', i, weights)
     self.w = w
     self.wd_term = self._weight_decay_term(weights)
     return self
@@ -360,14 +423,14 @@ class FullModel(_ModelBase):
     bufs['y_out'] = torch.empty((B, T, H, W), device=dev, dtype=f32)
     return bufs
 
-  def _decode(self, bufs, B):
-    """The T-step decode loop, full_model.py:638-848 (eval mode)."""
+  def _decode(self, bufs, B, train=False):
+    """The T-step decode loop, full_model.py:638-848 (eval mode; train=True: batch-statistics BN, use_knob=False)."""
     w = self.w
     T, H, W, F = self.T, self.H, self.W, self.F
     thw = T * H * W
     fork_score = int(self.n_chains) <= 1  # with sub-batch chains the side streams belong to the chains
     for t in range(T):
-      self._controller(bufs, t)
+      self._controller(bufs, t, train)
       box_t = bufs['box_all'][t]
       x_patch = bufs['x_patch_all'][t]
       _lib.TAG = 'extract'
@@ -376,8 +439,7 @@ class FullModel(_ModelBase):
       prev = x_patch
       _lib.TAG = 'attn_cnn'
       for i, pl in enumerate(self.attn_pool):  # full_model.py:792
-        self._conv(prev, w['acnn_w%d' % i], w['acnn_scale%d' % i][t], w['acnn_shift%d' % i][t], pl,
-                   out=bufs['acnn'][i])
+        self._block(train, prev, w['acnn_w%d' % i], 'acnn', i, t, pl, out=bufs['acnn'][i])
         prev = bufs['acnn'][i]
       core = bufs['acnn'][-1]
       # the score head (full_model.py:821-822) feeds only the loss: a parallel graph branch beside the mask head
@@ -395,8 +457,7 @@ class FullModel(_ModelBase):
       for i, pl in enumerate(self.dcnn_pool):
         sk = skips[i] if (self.use_skip and self.skip_ch[i] > 0) else None
         dst = bufs['y_patch_all'][t] if i == n_d - 1 else bufs['adcnn'][i]
-        self._conv(prev, w['adcnn_w%d' % i], w['adcnn_scale%d' % i][t], w['adcnn_shift%d' % i][t], 1, x2=sk,
-                   upsample=pl, out=dst)
+        self._block(train, prev, w['adcnn_w%d' % i], 'adcnn', i, t, 1, x2=sk, upsample=pl, out=dst)
         prev = dst
       _lib.TAG = 'paste_back'
       ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],
@@ -491,14 +552,14 @@ class FullModel(_ModelBase):
     if box_gt is not None:
       out['attn_box_gt'] = box_gt
 
-  def _run(self, bufs, B, with_loss, want_all):
+  def _run(self, bufs, B, with_loss, want_all, train=False):
     """Enqueue one full forward on the current stream; returns the dict of (static) output tensors."""
     st = bufs['static_in']
     gt = self._gt_boxes(bufs, st['y_gt'], want_all) if with_loss else None
     chains = self._chains(B)
-    if len(chains) == 1:
+    if len(chains) == 1 or train:  # batch statistics couple the examples: training mode never splits the batch
       self._prepare(bufs, st['x'], st.get('d_in'), st.get('y_in'))
-      self._decode(bufs, B)
+      self._decode(bufs, B, train)
     else:
       cur = torch.cuda.current_stream()
       forked = []
@@ -555,10 +616,19 @@ class FullModel(_ModelBase):
     static device buffers; with ``use_graph`` the ~750 kernel launches of the T-step decode + loss block are
     captured once per (batch size, output set, input set) in a CUDA graph and replayed (the returned tensors
     are the graph's static outputs: they are overwritten by the next forward of the same batch size)."""
-    if phase_train:
-      raise _lib.RecAttendError('training-mode forward (batch-stat BN, knob) is a later row of the scope table')
     if self.w is None:
       raise _lib.RecAttendError('load_weights() first')
+    if phase_train:
+      # Training-mode forward (SURVEY §8a-a2): every BN layer normalises with the statistics of THIS batch and moves
+      # the EMA shadows of its (layer, step) copy in place (nnlib.py:96-119).  use_knob=False and the identity draw of
+      # random_transformation (apply ops.random_transformation to the batch beforehand for other draws); eager
+      # launches, no CUDA graph (the raw conv outputs are temporaries).
+      if self.opt.get('use_knob', False):
+        raise _lib.RecAttendError('the scheduled-sampling knob (full_model.py:589-625) is not built; use_knob=False')
+      use_graph = False
+      self._bn_dirty = True
+    elif self._bn_dirty:
+      self._refold_bn()
     cur = torch.cuda.current_stream()
     pf = None
     for bb in self._bufs.values():
@@ -584,7 +654,7 @@ class FullModel(_ModelBase):
     want_all = want is None or bool(want & {'x_patch', 'y_out_patch', 'attn_box_gt'})
     key = (with_loss, want_all, slot)
     if not use_graph:
-      out = self._run(bufs, B, with_loss, want_all)
+      out = self._run(bufs, B, with_loss, want_all, train=bool(phase_train))
     else:
       graphs = bufs.setdefault('graphs', {})
       if key not in graphs:

@@ -130,8 +130,9 @@ def test_outputs_subset_and_errors(cuda):
   model.load_weights(ra.synthetic.make_weights(opt))
   out = model.forward(ra.synthetic.make_batch(opt, 2), outputs=['y_out', 's_out'])
   assert sorted(out) == ['s_out', 'y_out'] and tuple(out['y_out'].shape) == (2, 3, 64, 64)
+  knob = get_model(dict(opt, use_knob=True)).load_weights(ra.synthetic.make_weights(opt))
   with pytest.raises(_lib.RecAttendError):
-    model.forward(ra.synthetic.make_batch(opt, 1), phase_train=True)
+    knob.forward(ra.synthetic.make_batch(opt, 1), phase_train=True)  # scheduled sampling is not built
   w = model.export_weights()
   assert 'ctrl_cnn_w_0' in w and w['ctrl_cnn_w_0'].shape == (3, 3, 4, 8)
 
@@ -187,3 +188,32 @@ def test_sub_batch_chains_agree(cuda, use_graph):
     for k in ('y_out', 's_out', 'attn_box', 'x_patch', 'loss', 'canvas'):
       assert rel_err(o[k], outs[0][k]) < 1e-4, k
     assert (o['match'] == outs[0]['match']).all() and (o['match_box'] == outs[0]['match_box']).all()
+
+
+def test_training_mode_forward_batch_stat_bn(cuda):
+  """phase_train=True, use_knob=False: batch-statistics BN in every conv block, EMA shadows moved in place
+  (nnlib.py:96-119) — against the oracle's training-mode forward; then the eval forward uses the moved shadows."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt('kitti', 64, 128, 4, use_knob=False)
+  batch = ra.synthetic.make_batch(opt, 4, seed=5)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  ref = OM.full_model_forward(opt, weights, batch, phase_train=True)
+  model = FullModel(opt).load_weights(weights)
+  out = model.forward(batch, phase_train=True)
+  torch.cuda.synchronize()
+  for k in ('y_out', 's_out', 'attn_box', 'x_patch', 'ctrl_out', 'iou_soft_pairwise'):
+    assert rel_err(out[k].float().cpu().numpy(), ref[k].numpy()) <= MODEL_TOL, k
+  assert abs(float(out['loss']) - float(ref['loss'])) <= MODEL_TOL * max(1.0, abs(float(ref['loss'])))
+  assert (out['match'].cpu().numpy() == ref['match'].numpy()).all()
+  new_w = model.export_weights()
+  assert len(ref['ema_updates']) == (8 + 6 + 7) * 4 * 2
+  worst = max(rel_err(new_w[k], v.numpy()) for k, v in ref['ema_updates'].items())
+  assert worst <= 1e-4, worst
+  assert rel_err(new_w['ctrl_cnn_3_2_ema_var'], weights['ctrl_cnn_3_2_ema_var']) > 1e-3  # the shadows did move
+  # eval forward after training: uses the moved shadows (refolded), like the oracle fed with the exported weights
+  ref_eval = OM.full_model_forward(opt, new_w, batch)
+  out_eval = model.forward(batch)
+  torch.cuda.synchronize()
+  for k in ('y_out', 's_out', 'attn_box'):
+    assert rel_err(out_eval[k].float().cpu().numpy(), ref_eval[k].numpy()) <= MODEL_TOL, k
