@@ -308,7 +308,7 @@ int ra_random_transformation_f32(const float *src, size_t N, int H, int W, int C
  *   mean, var = moments of x over (B,H,W) (biased);  ema -= (1-decay)*(ema - batch)  (decay 0.9)
  *   y = pool(relu(x*inv + (beta - mean*inv))),  inv = gamma * rsqrt(var + eps)       (eps 1e-3)
  * x [B,H,W,C] = raw convolution output incl. bias (e.g. ra_conv3x3_umma_f32 with scale 1,
- * shift = bias, relu 0, pool 1); C % 4 == 0, C <= 256; ema_* updated in place
+ * shift = bias, relu 0, pool 1); C <= 256 (float4 path when C % 4 == 0); ema_* updated in place
  * (may be NULL), batch_* [C] out (may be NULL); workspace: ra_bn_train_workspace() floats.
  * -------------------------------------------------------------------------------------- */
 size_t ra_bn_train_workspace(int B, int H, int W, int C);

@@ -2,7 +2,7 @@
 //   batch_mean, batch_var = tf.nn.moments(x, [0, 1, 2])            (biased variance, two passes like TF)
 //   ema_x -= (1 - decay) * (ema_x - batch_x)                        (ExponentialMovingAverage, decay 0.9, :103-108)
 //   y = pool(relu(x * inv + (beta - mean * inv))),  inv = gamma * rsqrt(var + 1e-3)   (tf.nn.batch_normalization, :119)
-// x [B,H,W,C] is the raw convolution output (bias included), NHWC, C % 4 == 0.  Three launches: per-CTA channel sums,
+// x [B,H,W,C] is the raw convolution output (bias included), NHWC (float4 path when C % 4 == 0).  Three launches: per-CTA channel sums,
 // per-CTA centred squared sums (every CTA first reduces the partial sums to the mean, in double), then the fused
 // normalise + ReLU + max-pool pass whose CTA 0 also publishes the statistics and updates the EMA shadows.
 // HBM-bound: x is read three times (the second and third pass hit L2 for the patch-network layers).
@@ -14,14 +14,15 @@ constexpr int kBnThreads = 256;
 constexpr int kBnMaxC = 256;
 
 // partial[cta][C] <- sum over this CTA's pixels of (x - center[c])^pow, pow in {1, 2}
-template <int POW>
+// V = 4: float4 path (C % 4 == 0); V = 1: any channel count (the 1-channel mask layer of the deconv head)
+template <int POW, int V>
 __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float *__restrict__ x, size_t npix, int C,
                                                                 const float *__restrict__ prev_partial, int prev_ctas,
                                                                 float *__restrict__ partial) {
   __shared__ float center_s[kBnMaxC];
   __shared__ float red_s[kBnThreads * 4];
   const int tid = threadIdx.x;
-  const int cg_n = C >> 2;
+  const int cg_n = C / V;
   for (int c = tid; c < C; c += kBnThreads) {
     float m = 0.f;
     if (POW == 2) {  // the mean, from the first pass's partial sums (fixed order, double)
@@ -34,34 +35,45 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float *__r
   __syncthreads();
   // thread -> channel group cg = tid % cg_n, pixel lane pl = tid / cg_n; threads beyond lanes * cg_n idle (C = 96)
   const int cg = tid % cg_n, lanes = kBnThreads / cg_n, pl = tid / cg_n;
-  const float4 ctr = *reinterpret_cast<const float4 *>(center_s + cg * 4);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float ctr[V], acc[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    ctr[e] = center_s[cg * V + e];
+    acc[e] = 0.f;
+  }
   for (size_t p = (size_t)blockIdx.x * lanes + pl; pl < lanes && p < npix; p += (size_t)gridDim.x * lanes) {
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(x + p * C + cg * 4));
-    if (POW == 1) {
-      acc.x += v.x;
-      acc.y += v.y;
-      acc.z += v.z;
-      acc.w += v.w;
+    float v[V];
+    if (V == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4 *>(x + p * C + cg * 4));
+      v[0] = q.x;
+      v[V > 1 ? 1 : 0] = q.y;
+      v[V > 2 ? 2 : 0] = q.z;
+      v[V > 3 ? 3 : 0] = q.w;
     } else {
-      const float dx = v.x - ctr.x, dy = v.y - ctr.y, dz = v.z - ctr.z, dw = v.w - ctr.w;
-      acc.x = fmaf(dx, dx, acc.x);
-      acc.y = fmaf(dy, dy, acc.y);
-      acc.z = fmaf(dz, dz, acc.z);
-      acc.w = fmaf(dw, dw, acc.w);
+      v[0] = __ldg(x + p * C + cg);
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      if (POW == 1) {
+        acc[e] += v[e];
+      } else {
+        const float d = v[e] - ctr[e];
+        acc[e] = fmaf(d, d, acc[e]);
+      }
     }
   }
-  *reinterpret_cast<float4 *>(red_s + tid * 4) = acc;
+#pragma unroll
+  for (int e = 0; e < V; ++e) red_s[tid * V + e] = acc[e];
   __syncthreads();
   for (int c = tid; c < C; c += kBnThreads) {
-    const int g = c >> 2, e = c & 3;
+    const int g = c / V, e = c % V;
     float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += red_s[(l * cg_n + g) * 4 + e];
+    for (int l = 0; l < lanes; ++l) s += red_s[(l * cg_n + g) * V + e];
     partial[(size_t)blockIdx.x * C + c] = s;
   }
 }
 
-template <int POOL>
+template <int POOL, int V>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__restrict__ x, int B, int H, int W, int C,
                                                               const float *__restrict__ sum_partial,
                                                               const float *__restrict__ sq_partial, int ctas,
@@ -92,7 +104,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
     }
   }
   __syncthreads();
-  const int cg_n = C >> 2;
+  const int cg_n = C / V;
   const int Ho = H / POOL, Wo = W / POOL;
   const size_t total = (size_t)B * Ho * Wo * cg_n;
   for (size_t idx = (size_t)blockIdx.x * kBnThreads + tid; idx < total; idx += (size_t)gridDim.x * kBnThreads) {
@@ -102,32 +114,35 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
     pix /= Wo;
     const int oy = (int)(pix % Ho);
     const int b = (int)(pix / Ho);
-    const float4 inv = *reinterpret_cast<const float4 *>(inv_s + cg * 4);
-    const float4 sh = *reinterpret_cast<const float4 *>(sh_s + cg * 4);
-    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    float best[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) best[e] = -INFINITY;
 #pragma unroll
     for (int py = 0; py < POOL; ++py)
 #pragma unroll
       for (int px = 0; px < POOL; ++px) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(
-            x + (((size_t)b * H + oy * POOL + py) * W + ox * POOL + px) * C + cg * 4));
-        best.x = fmaxf(best.x, fmaf(v.x, inv.x, sh.x));
-        best.y = fmaxf(best.y, fmaf(v.y, inv.y, sh.y));
-        best.z = fmaxf(best.z, fmaf(v.z, inv.z, sh.z));
-        best.w = fmaxf(best.w, fmaf(v.w, inv.w, sh.w));
+        const float *src = x + (((size_t)b * H + oy * POOL + py) * W + ox * POOL + px) * C + cg * V;
+        float v[V];
+        if (V == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4 *>(src));
+          v[0] = q.x;
+          v[V > 1 ? 1 : 0] = q.y;
+          v[V > 2 ? 2 : 0] = q.z;
+          v[V > 3 ? 3 : 0] = q.w;
+        } else {
+          v[0] = __ldg(src);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) best[e] = fmaxf(best[e], fmaf(v[e], inv_s[cg * V + e], sh_s[cg * V + e]));
       }
-    if (relu) {  // max(relu(.)) == relu(max(.))
-      best.x = fmaxf(best.x, 0.f);
-      best.y = fmaxf(best.y, 0.f);
-      best.z = fmaxf(best.z, 0.f);
-      best.w = fmaxf(best.w, 0.f);
-    }
-    *reinterpret_cast<float4 *>(y + (((size_t)b * Ho + oy) * Wo + ox) * C + cg * 4) = best;
+    float *dst = y + (((size_t)b * Ho + oy) * Wo + ox) * C + cg * V;
+#pragma unroll
+    for (int e = 0; e < V; ++e) dst[e] = relu ? fmaxf(best[e], 0.f) : best[e];  // max(relu(.)) == relu(max(.))
   }
 }
 
 int bn_ctas(size_t npix, int C) {
-  const int lanes = kBnThreads / (C / 4);
+  const int lanes = kBnThreads / ((C & 3) ? C : C / 4);
   size_t want = (npix + lanes - 1) / lanes;
   const size_t cap = (size_t)ra::kNumSMs * 4;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
@@ -136,7 +151,7 @@ int bn_ctas(size_t npix, int C) {
 }  // namespace
 
 extern "C" size_t ra_bn_train_workspace(int B, int H, int W, int C) {
-  if (B < 1 || H < 1 || W < 1 || C < 4 || (C & 3) || C > kBnMaxC) return 0;
+  if (B < 1 || H < 1 || W < 1 || C < 1 || C > kBnMaxC) return 0;
   return (size_t)2 * bn_ctas((size_t)B * H * W, C) * C;  // floats: per-CTA sums, then per-CTA centred squared sums
 }
 
@@ -144,7 +159,7 @@ extern "C" int ra_bn_train_block_f32(const float *x, int B, int H, int W, int C,
                                      float eps, float decay, int pool, int relu, float *workspace, float *ema_mean,
                                      float *ema_var, float *batch_mean, float *batch_var, float *y, void *stream) {
   if (B < 0 || H < 1 || W < 1 || C < 1) return RA_ERR_INVALID_ARG;
-  if ((C & 3) || C > kBnMaxC || (pool != 1 && pool != 2)) return RA_ERR_UNSUPPORTED;
+  if (C > kBnMaxC || (pool != 1 && pool != 2)) return RA_ERR_UNSUPPORTED;
   if (pool == 2 && ((H | W) & 1)) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
   if (!x || !gamma || !beta || !workspace || !y) return RA_ERR_INVALID_ARG;
@@ -152,20 +167,30 @@ extern "C" int ra_bn_train_block_f32(const float *x, int B, int H, int W, int C,
   const size_t npix = (size_t)B * H * W;
   const int ctas = bn_ctas(npix, C);
   float *sum_p = workspace, *sq_p = workspace + (size_t)ctas * C;
-  bn_partial_kernel<1><<<ctas, kBnThreads, 0, s>>>(x, npix, C, nullptr, 0, sum_p);
+  const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (vec)
+    bn_partial_kernel<1, 4><<<ctas, kBnThreads, 0, s>>>(x, npix, C, nullptr, 0, sum_p);
+  else
+    bn_partial_kernel<1, 1><<<ctas, kBnThreads, 0, s>>>(x, npix, C, nullptr, 0, sum_p);
   int rc = ra::finish_launch("bn_partial_kernel<1>");
   if (rc != RA_OK) return rc;
-  bn_partial_kernel<2><<<ctas, kBnThreads, 0, s>>>(x, npix, C, sum_p, ctas, sq_p);
+  if (vec)
+    bn_partial_kernel<2, 4><<<ctas, kBnThreads, 0, s>>>(x, npix, C, sum_p, ctas, sq_p);
+  else
+    bn_partial_kernel<2, 1><<<ctas, kBnThreads, 0, s>>>(x, npix, C, sum_p, ctas, sq_p);
   rc = ra::finish_launch("bn_partial_kernel<2>");
   if (rc != RA_OK) return rc;
-  const size_t total = (size_t)B * (H / pool) * (W / pool) * (C / 4);
+  const size_t total = (size_t)B * (H / pool) * (W / pool) * (vec ? C / 4 : C);
   size_t blocks = (total + kBnThreads - 1) / kBnThreads;
   if (blocks > (size_t)ra::kNumSMs * 8) blocks = (size_t)ra::kNumSMs * 8;
-  if (pool == 2)
-    bn_apply_kernel<2><<<(unsigned)blocks, kBnThreads, 0, s>>>(x, B, H, W, C, sum_p, sq_p, ctas, gamma, beta, eps, decay, relu,
-                                                               ema_mean, ema_var, batch_mean, batch_var, y);
-  else
-    bn_apply_kernel<1><<<(unsigned)blocks, kBnThreads, 0, s>>>(x, B, H, W, C, sum_p, sq_p, ctas, gamma, beta, eps, decay, relu,
-                                                               ema_mean, ema_var, batch_mean, batch_var, y);
+#define RA_BN_APPLY(P, V)                                                                                            \
+  bn_apply_kernel<P, V><<<(unsigned)blocks, kBnThreads, 0, s>>>(x, B, H, W, C, sum_p, sq_p, ctas, gamma, beta, eps, decay, \
+                                                                relu, ema_mean, ema_var, batch_mean, batch_var, y)
+  if (pool == 2) {
+    if (vec) RA_BN_APPLY(2, 4); else RA_BN_APPLY(2, 1);
+  } else {
+    if (vec) RA_BN_APPLY(1, 4); else RA_BN_APPLY(1, 1);
+  }
+#undef RA_BN_APPLY
   return ra::finish_launch("bn_apply_kernel");
 }

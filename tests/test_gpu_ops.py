@@ -584,7 +584,7 @@ def test_postprocess_errors(ops):
 
 # ----------------------------------------------------------------------------- training-mode BN block
 @pytest.mark.parametrize('B,H,W,C,pool', [(3, 16, 24, 16, 2), (2, 12, 12, 96, 2), (4, 48, 48, 16, 1), (1, 6, 10, 64, 1),
-                                          (8, 128, 256, 16, 2)])
+                                          (8, 128, 256, 16, 2), (3, 48, 48, 1, 1), (2, 10, 14, 6, 2)])
 def test_batch_norm_train_block(ops, B, H, W, C, pool):
   """nnlib.batch_norm(phase_train=True) + ReLU + max-pool against the oracle (batch moments, EMA update)."""
   rng = np.random.default_rng(B * 100 + C)
@@ -628,8 +628,8 @@ def test_conv_block_train_mode(ops):
 def test_batch_norm_train_errors(ops):
   from rec_attend_b200 import _lib
   with pytest.raises(_lib.RecAttendError):
-    ops.batch_norm_train_block(torch.zeros((1, 4, 4, 6), device='cuda'), torch.ones(6, device='cuda'),
-                               torch.zeros(6, device='cuda'))  # C % 4
+    ops.batch_norm_train_block(torch.zeros((1, 4, 4, 300), device='cuda'), torch.ones(300, device='cuda'),
+                               torch.zeros(300, device='cuda'))  # C > 256
 
 
 # ----------------------------------------------------------------------------- augmentation

@@ -12,11 +12,18 @@ H, W, T, B = int(H), int(W), int(T), int(B)
 opt = ra.config.full_model_opt(arch, H, W, T)
 batch = ra.synthetic.make_batch(opt, B, seed=1234)
 w = ra.synthetic.make_weights(opt, seed=4321)
+train = bool(os.environ.get('RA_DBG_TRAIN'))  # training-mode forward (batch-statistics BN)
 with torch.no_grad():
-  ref = OM.full_model_forward(opt, w, batch)
-out = FullModel(opt).load_weights(w).forward(batch)
+  ref = OM.full_model_forward(opt, w, batch, phase_train=train)
+model = FullModel(opt).load_weights(w)
+out = model.forward(batch, phase_train=train)
 torch.cuda.synchronize()
-print('mode', 'fp32 CUDA-core convs' if os.environ.get('RA_CONV_FP32') else 'tcgen05 3xTF32 convs', arch, H, W, T, B)
+if train:
+  new_w = model.export_weights()
+  errs = sorted(((float(np.abs(new_w[k] - v.numpy()).max() / max(1e-12, np.abs(v.numpy()).max())), k)
+                 for k, v in ref['ema_updates'].items()), reverse=True)
+  print('worst EMA updates:', errs[:6])
+print('train' if train else 'eval', 'mode', 'fp32 CUDA-core convs' if os.environ.get('RA_CONV_FP32') else 'tcgen05 3xTF32 convs', arch, H, W, T, B)
 for k in ('ctrl_out', 'attn_ctr', 'attn_size', 'attn_lg_var', 'x_patch', 'y_out_patch', 'attn_box', 'y_out', 's_out'):
   if k not in ref or k not in out:
     continue
