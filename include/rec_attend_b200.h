@@ -266,6 +266,28 @@ int ra_box_gt_step_f32(const float *attn_box, size_t box_bstride, const float *g
                        const float *noise, size_t noise_bstride, int B, int T, int H, int W, float *iou_t,
                        int iou_bstride, float *grd_ws, float *canvas, void *stream);
 
+/* --------------------------------------------------------------------------------------
+ * Scheduled sampling ("knob", training mode only) — full_model.py:561-625,744-785,826-845, with
+ * the random draws as inputs:
+ *  ra_gt_attn_noise_f32: noisy GT attention boxes (modellib.get_gt_attn with per-object padding
+ *    ratio pad [B,T] and centre shift [B,T,2]) from the raw mask extrema rect_raw [B,T,4]
+ *    (ra_gt_box_f32 with zero padding) and area [B,T] -> ctr, size [B,T,2].
+ *  ra_knob_greedy_box_f32: iou_t[b,m] = f_inter(attn_box_t, box_gt_m) / f_union (rectangle form)
+ *    and grd = f_greedy_match(iou_t, 0) (modellib.py:366-379), :756-759.
+ *  ra_knob_mix_box_f32: box record (RA_BOX_*) of step t <- knob ? matched noisy GT box : itself, :760-776.
+ *  ra_knob_canvas_f32: canvas = max(canvas, knob ? (sum_m grd*y_gt)*(1-noise) : y_out_t), :826-845.
+ * knob points at the [B] switches of this step (element b at knob[b*knob_stride]).
+ * -------------------------------------------------------------------------------------- */
+int ra_gt_attn_noise_f32(const float *rect_raw, const float *area, const float *pad, const float *shift,
+                         float min_padding, int B, int T, float *ctr, float *size, void *stream);
+int ra_knob_greedy_box_f32(const float *attn_box, size_t box_bstride, const float *gt_rect, int B, int T, int H, int W,
+                           float *iou_t, int iou_bstride, float *grd, void *stream);
+int ra_knob_mix_box_f32(float *box, const float *grd, const float *ctr_gt, const float *size_gt, const float *knob,
+                        int knob_stride, int B, int T, void *stream);
+int ra_knob_canvas_f32(const float *grd, const float *y_gt, const float *noise, size_t noise_bstride, const float *knob,
+                       int knob_stride, const float *y_out, size_t out_bstride, int B, int T, int H, int W,
+                       float *canvas, void *stream);
+
 /* out[b,h,w,:] = concat(a[..,:Ca], b[..,:Cb], c[..,:Cc]) over npix = B*H*W pixels — the
  * step-invariant part of the input stack of full_model.py:640-661 (Cb, Cc may be 0). */
 int ra_concat_channels_f32(const float *a, int Ca, const float *b, int Cb, const float *c, int Cc, size_t npix,

@@ -422,6 +422,14 @@ def controller_step(opt, weights, ccnn_inp, tt, ema_out=None):
   }
 
 
+def top_left_pred(ctr, size):
+  return ctr - size / 2.0
+
+
+def bot_right_pred(ctr, size):
+  return ctr + size / 2.0
+
+
 def attn_box_from(opt, ctr, size, lg_var, box_lg_gamma):
   """full_model.py:728-741 / box_model.py:473-487."""
   H, W = opt['inp_height'], opt['inp_width']
@@ -435,11 +443,28 @@ def attn_box_from(opt, ctr, size, lg_var, box_lg_gamma):
   return box.reshape(B, 1, H, W), f_y, f_x
 
 
-def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False):
+def knob_probability(opt, global_step, offset_key):
+  """full_model.py:598-625: min(1, knob_base * knob_decay^(max(0, step - offset) / steps_per_knob_decay) * time scale),
+  time scale = 1 + log(1 + 3t) when knob_use_timescale.  Returns [T] probabilities (fp32 like the graph)."""
+  T = opt['timespan']
+  step = max(0.0, float(global_step) - float(opt[offset_key]))
+  p = np.float32(opt['knob_base']) * np.power(np.float32(opt['knob_decay']),
+                                               np.float32(step / float(opt['steps_per_knob_decay'])))
+  scale = (1.0 + np.log(1.0 + np.arange(T, dtype=np.float32) * 3.0)) if opt.get('knob_use_timescale', True) \
+      else np.ones(T, np.float32)
+  return np.minimum(np.float32(1.0), p * scale.astype(np.float32)).astype(np.float32)
+
+
+def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False, draws=None):
   """full_model.get_model in eval mode (phase_train=False, random_transformation is the
   identity, image_ops.py:70-112; the knob terms vanish because phase_train_f = 0), or - phase_train=True - the
-  training-mode forward with use_knob=False and the identity draw of the augmentation: every BN layer normalises with
-  the batch statistics and moves its EMA shadows (nnlib.py:96-119); the result then carries 'ema_updates'.
+  training-mode forward with the identity draw of the augmentation: every BN layer normalises with the batch
+  statistics and moves its EMA shadows (nnlib.py:96-119); the result then carries 'ema_updates'.
+
+  Scheduled sampling (opt['use_knob'] with phase_train, full_model.py:589-625,744-785,826-843): TensorFlow's random
+  streams cannot be reproduced, so the draws are inputs - draws = {'gt_knob_box' [B,T] in {0,1},
+  'gt_knob_segm' [B,T] in {0,1}, 'gt_box_pad' [B,T,1] (padding ratio of the noisy GT box), 'gt_box_ctr_shift' [B,T,2],
+  'gt_segm_noise' [B,T,H,W] in [0, opt['gt_segm_noise'])}.
 
   batch: dict of numpy/torch fp32: x [B,H,W,3], y_gt [B,T,H,W], s_gt [B,T], optional
   d_in [B,H,W,8], y_in [B,H,W,C].  weights: dict keyed like full_model_read.py:32-70.
@@ -464,6 +489,21 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False):
   y_in = _t(batch['y_in']) if add_d_out else None
 
   ema_out = {} if phase_train else None
+  use_knob = bool(phase_train and _opt(opt, 'use_knob', False))
+  if use_knob:
+    if draws is None:
+      raise ValueError('use_knob needs the random draws as inputs')
+    y_gt_k = _t(batch['y_gt'])
+    minpad = opt['padding'] + 4
+    # full_model.py:561-580: the clean GT boxes (for the greedy match) and the noisy ones (mixed into the controller)
+    tl_gt_k, br_gt_k, box_gt_k = get_gt_box(y_gt_k, padding_ratio=opt['attn_box_padding_ratio'],
+                                            center_shift_ratio=0.0, min_padding=minpad)
+    tl_n, br_n, _ = get_gt_box(y_gt_k, padding_ratio=_t(draws['gt_box_pad']),
+                               center_shift_ratio=_t(draws['gt_box_ctr_shift']), min_padding=minpad)
+    ctr_gt_noise, size_gt_noise = (tl_n + br_n) / 2.0, br_n - tl_n
+    knob_box, knob_segm = _t(draws['gt_knob_box']), _t(draws['gt_knob_segm'])
+    segm_noise = _t(draws['gt_segm_noise'])
+    iou_box_steps = []
   canvas = torch.zeros(B, H, W, 1)
   n_acnn = len(opt['attn_cnn_filter_size'])
   n_adcnn = len(opt['attn_dcnn_filter_size'])
@@ -486,6 +526,20 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False):
     c = controller_step(opt, weights, ccnn_inp, tt, ema_out=ema_out)
     ctr, size = c['ctr'], c['size']
     box, f_y, f_x = attn_box_from(opt, ctr, size, c['lg_var'], c['box_lg_gamma'])
+    if use_knob:
+      # full_model.py:744-785: greedy-match the predicted box to a GT box (grd_match_cum stays zero),
+      # mix the matched noisy GT box into centre / size where the Bernoulli draw says so, rebuild the filters
+      if _opt(opt, 'use_iou_box', False):
+        iou_t = f_iou_box(top_left_pred(ctr, size).unsqueeze(1), bot_right_pred(ctr, size).unsqueeze(1), tl_gt_k, br_gt_k)
+      else:
+        iou_t = f_inter(box, box_gt_k) / f_union(box, box_gt_k)
+      iou_box_steps.append(iou_t.unsqueeze(1))
+      grd = f_greedy_match(iou_t, torch.zeros(B, T))
+      kb = knob_box[:, tt:tt + 1]
+      ctr = kb * (grd.unsqueeze(2) * ctr_gt_noise).sum(1) + (1.0 - kb) * ctr
+      size = kb * (grd.unsqueeze(2) * size_gt_noise).sum(1) + (1.0 - kb) * size
+      f_y = get_gaussian_filter(ctr[:, 0], size[:, 0], c['lg_var'][:, 0], H, Fh)
+      f_x = get_gaussian_filter(ctr[:, 1], size[:, 1], c['lg_var'][:, 1], W, Fw)
     top_left, bot_right = ctr - size / 2.0, ctr + size / 2.0
 
     # full_model.py:788-807
@@ -507,7 +561,14 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False):
     if disable_overwrite:
       y = (1 - canvas).reshape(B, 1, H, W) * y
     s = run_mlp(torch.cat([c['h'], h_core], 1), weights, 'score_mlp', ['sigmoid'])[-1]
-    canvas = torch.maximum(y.reshape(B, H, W, 1), canvas)  # full_model.py:843-845
+    y_canvas = y.reshape(B, H, W, 1)
+    if use_knob:
+      # full_model.py:826-843: the canvas may be written from the greedily matched GT mask (x (1 - noise)) instead
+      y_gtm = (grd.view(B, T, 1, 1) * y_gt_k).sum(1)
+      y_gtm = (y_gtm - y_gtm * segm_noise[:, tt]).reshape(B, H, W, 1)
+      ks = knob_segm[:, tt].view(B, 1, 1, 1)
+      y_canvas = ks * y_gtm + (1.0 - ks) * y_canvas
+    canvas = torch.maximum(y_canvas, canvas)  # full_model.py:843-845
 
     out['y_out'].append(y)
     out['s_out'].append(s)
@@ -528,6 +589,8 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False):
   sub = int(np.prod(opt['ctrl_cnn_pool']))
   model['ctrl_rnn_glimpse_map'] = gm.reshape(B, T, gm.shape[2], H // sub, W // sub)
   model['canvas'] = canvas
+  if use_knob:
+    model['iou_soft_box_steps'] = torch.cat(iou_box_steps, 1)  # [B,T(step),T(gt)], full_model.py:926-929
   if ema_out is not None:
     model['ema_updates'] = ema_out
   if not with_loss:
@@ -560,7 +623,10 @@ def full_model_loss(opt, weights, model, y_gt, s_gt):
   r['attn_top_left_gt'], r['attn_bot_right_gt'], r['attn_box_gt'] = tl_gt, br_gt, box_gt
   r['attn_ctr_gt'], r['attn_size_gt'] = (tl_gt + br_gt) / 2.0, br_gt - tl_gt
 
-  iou_box = f_iou_pairwise(model['attn_box'], box_gt)  # :931
+  if 'iou_soft_box_steps' in model:
+    iou_box = model['iou_soft_box_steps']  # use_knob: the per-step IoUs of the decode loop, full_model.py:926-929
+  else:
+    iou_box = f_iou_pairwise(model['attn_box'], box_gt)  # :931
   match_box = f_segm_match(iou_box, s_gt)  # :939
   r['iou_soft_box_pairwise'] = iou_box
   r['match_box'] = match_box

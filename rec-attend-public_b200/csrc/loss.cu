@@ -480,6 +480,83 @@ __global__ void box_gt_canvas_kernel(const float *__restrict__ grd, const float 
   }
 }
 
+// ------------------------------------------------------------------ scheduled-sampling knob (training mode)
+// Noisy GT attention boxes, full_model.py:568-580 = modellib.get_gt_attn / get_gt_box (modellib.py:644-701) with a
+// per-(example, object) padding ratio and centre shift: from the raw extrema of the mask (rect_raw = get_gt_box with
+// zero padding) to centre and size.  One thread per (b, t).
+__global__ void gt_attn_noise_kernel(const float *__restrict__ rect_raw, const float *__restrict__ area,
+                                     const float *__restrict__ pad, const float *__restrict__ shift, float min_padding,
+                                     int n, float *__restrict__ ctr, float *__restrict__ size) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float nz = area[i] > 0.f ? 1.f : 0.f;
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    float tl = rect_raw[i * 4 + d], br = rect_raw[i * 4 + 2 + d];
+    const float sz = br - tl;                                 // modellib.py:689
+    tl += shift[i * 2 + d] * sz;                              // :690
+    tl -= fmaxf(pad[i] * sz, min_padding);                    // :691
+    br += shift[i * 2 + d] * sz;                              // :692
+    br += fmaxf(pad[i] * sz, min_padding);                    // :693
+    tl *= nz;                                                 // :697-699 (empty mask -> top-left corner box)
+    br = nz * br + (1.f - nz) * (2.f * min_padding);
+    ctr[i * 2 + d] = (tl + br) / 2.0f;                        // get_box_ctr_size
+    size[i * 2 + d] = br - tl;
+  }
+}
+
+// full_model.py:760-773: where the Bernoulli switch of this step is on, centre and size of the attention box become
+// those of the greedily matched noisy GT box (grd = one-hot / tie-shared weights); top-left / bottom-right follow.
+__global__ void knob_mix_box_kernel(float *__restrict__ box, const float *__restrict__ grd,
+                                    const float *__restrict__ ctr_gt, const float *__restrict__ size_gt,
+                                    const float *__restrict__ knob, int knob_stride, int B, int T) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float *bo = box + (size_t)b * RA_BOX_STRIDE;
+  const float kb = knob[(size_t)b * knob_stride];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    float c = 0.f, s = 0.f;
+    for (int m = 0; m < T; ++m) {
+      const float g = grd[(size_t)b * T + m];
+      c += g * ctr_gt[((size_t)b * T + m) * 2 + d];
+      s += g * size_gt[((size_t)b * T + m) * 2 + d];
+    }
+    const float cn = kb * c + (1.f - kb) * bo[RA_BOX_CTR_Y + d];
+    const float sn = kb * s + (1.f - kb) * bo[RA_BOX_SIZE_Y + d];
+    bo[RA_BOX_CTR_Y + d] = cn;
+    bo[RA_BOX_SIZE_Y + d] = sn;
+    bo[RA_BOX_TL_Y + d] = cn - sn / 2.0f;  // modellib.get_box_coord
+    bo[RA_BOX_BR_Y + d] = cn + sn / 2.0f;
+  }
+}
+
+// full_model.py:826-845: canvas = max(canvas, knob ? (sum_m grd*y_gt) * (1 - noise) : y_out)
+__global__ void knob_canvas_kernel(const float *__restrict__ grd, const float *__restrict__ y_gt,
+                                   const float *__restrict__ noise, size_t noise_bstride,
+                                   const float *__restrict__ knob, int knob_stride, const float *__restrict__ y_out,
+                                   size_t out_bstride, int T, int HW, float *__restrict__ canvas) {
+  const int b = blockIdx.y;
+  __shared__ float g_s[64];
+  for (int m = threadIdx.x; m < T; m += blockDim.x) g_s[m] = grd[(size_t)b * T + m];
+  __syncthreads();
+  const float ks = knob[(size_t)b * knob_stride];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (ks != 0.f) {
+      for (int m = 0; m < T; ++m) {
+        const float g = g_s[m];
+        if (g != 0.f) v += g * y_gt[((size_t)b * T + m) * HW + i];
+      }
+      v = v - v * noise[(size_t)b * noise_bstride + i];
+    }
+    const float yo = y_out[(size_t)b * out_bstride + i];
+    const float w = ks * v + (1.f - ks) * yo;
+    const size_t ci = (size_t)b * HW + i;
+    canvas[ci] = fmaxf(canvas[ci], w);
+  }
+}
+
 int iou_plan(int N, int M, int HW, IouParams *p) {
   const int rows = (N > M ? N : M) + 1;
   const int nb = (rows + kR - 1) / kR;
@@ -597,4 +674,48 @@ extern "C" int ra_box_gt_step_f32(const float *attn_box, size_t box_bstride, con
   if (bx > 64) bx = 64;
   box_gt_canvas_kernel<<<dim3(bx, B), 256, 0, s>>>(grd_ws, y_gt, noise, noise_bstride, T, HW, canvas);
   return ra::finish_launch("box_gt_canvas_kernel");
+}
+
+extern "C" int ra_gt_attn_noise_f32(const float *rect_raw, const float *area, const float *pad, const float *shift,
+                                    float min_padding, int B, int T, float *ctr, float *size, void *stream) {
+  if (B < 0 || T < 1) return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  if (!rect_raw || !area || !pad || !shift || !ctr || !size) return RA_ERR_INVALID_ARG;
+  const int n = B * T;
+  gt_attn_noise_kernel<<<(n + 127) / 128, 128, 0, ra::as_stream(stream)>>>(rect_raw, area, pad, shift, min_padding, n, ctr,
+                                                                           size);
+  return ra::finish_launch("gt_attn_noise_kernel");
+}
+
+extern "C" int ra_knob_greedy_box_f32(const float *attn_box, size_t box_bstride, const float *gt_rect, int B, int T, int H,
+                                      int W, float *iou_t, int iou_bstride, float *grd, void *stream) {
+  if (B < 0 || T < 1 || T > 64 || H < 1 || W < 1) return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  if (!attn_box || !gt_rect || !iou_t || !grd) return RA_ERR_INVALID_ARG;
+  box_gt_iou_kernel<<<B, 256, (size_t)(6 * T) * sizeof(float), ra::as_stream(stream)>>>(attn_box, box_bstride, gt_rect, T, H,
+                                                                                        W, iou_t, iou_bstride, grd);
+  return ra::finish_launch("box_gt_iou_kernel");
+}
+
+extern "C" int ra_knob_mix_box_f32(float *box, const float *grd, const float *ctr_gt, const float *size_gt,
+                                   const float *knob, int knob_stride, int B, int T, void *stream) {
+  if (B < 0 || T < 1 || knob_stride < 1) return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  if (!box || !grd || !ctr_gt || !size_gt || !knob) return RA_ERR_INVALID_ARG;
+  knob_mix_box_kernel<<<(B + 63) / 64, 64, 0, ra::as_stream(stream)>>>(box, grd, ctr_gt, size_gt, knob, knob_stride, B, T);
+  return ra::finish_launch("knob_mix_box_kernel");
+}
+
+extern "C" int ra_knob_canvas_f32(const float *grd, const float *y_gt, const float *noise, size_t noise_bstride,
+                                  const float *knob, int knob_stride, const float *y_out, size_t out_bstride, int B, int T,
+                                  int H, int W, float *canvas, void *stream) {
+  if (B < 0 || T < 1 || T > 64 || H < 1 || W < 1 || knob_stride < 1) return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  if (!grd || !y_gt || !noise || !knob || !y_out || !canvas) return RA_ERR_INVALID_ARG;
+  const int HW = H * W;
+  int bx = (HW + 255) / 256;
+  if (bx > 64) bx = 64;
+  knob_canvas_kernel<<<dim3(bx, B), 256, 0, ra::as_stream(stream)>>>(grd, y_gt, noise, noise_bstride, knob, knob_stride, y_out,
+                                                                     out_bstride, T, HW, canvas);
+  return ra::finish_launch("knob_canvas_kernel");
 }

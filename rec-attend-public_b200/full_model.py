@@ -423,8 +423,29 @@ class FullModel(_ModelBase):
     bufs['y_out'] = torch.empty((B, T, H, W), device=dev, dtype=f32)
     return bufs
 
-  def _decode(self, bufs, B, train=False):
-    """The T-step decode loop, full_model.py:638-848 (eval mode; train=True: batch-statistics BN, use_knob=False)."""
+  def _knob_setup(self, bufs, y_gt, draws):
+    """Scheduled sampling, once per forward (full_model.py:561-625): clean GT rectangles for the greedy match, noisy
+    GT boxes to mix in, the draws on the device."""
+    o = self.opt
+    dev = lambda a: a if isinstance(a, torch.Tensor) and a.is_cuda else self._dev(np.asarray(a, np.float32))
+    B, T = y_gt.shape[0], self.T
+    _, _, _, rect_clean, area = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'],
+                                               min_padding=self.min_padding, want_box=False)
+    _, _, _, rect_raw, _ = ops.get_gt_box(y_gt, padding_ratio=0.0, min_padding=0.0, want_box=False)
+    ctr_n, size_n = ops.gt_attn_noise(rect_raw, area, dev(draws['gt_box_pad']).reshape(B, T).contiguous(),
+                                      dev(draws['gt_box_ctr_shift']).contiguous(), self.min_padding)
+    return {
+        'rect': rect_clean, 'ctr': ctr_n, 'size': size_n, 'y_gt': y_gt,
+        'knob_box': dev(draws['gt_knob_box']).contiguous(), 'knob_segm': dev(draws['gt_knob_segm']).contiguous(),
+        'noise': dev(draws['gt_segm_noise']).contiguous(),
+        'iou_steps': torch.empty((B, T, T), device=self.device, dtype=torch.float32),
+        'grd': torch.empty((B, T), device=self.device, dtype=torch.float32),
+        'canvas_tmp': torch.empty_like(bufs['canvas']),
+    }
+
+  def _decode(self, bufs, B, train=False, knob=None):
+    """The T-step decode loop, full_model.py:638-848 (eval mode; train=True: batch-statistics BN; knob: the
+    scheduled-sampling state of _knob_setup, training only)."""
     w = self.w
     T, H, W, F = self.T, self.H, self.W, self.F
     thw = T * H * W
@@ -432,6 +453,15 @@ class FullModel(_ModelBase):
     for t in range(T):
       self._controller(bufs, t, train)
       box_t = bufs['box_all'][t]
+      if knob is not None:
+        # full_model.py:738-785: the attention-box OUTPUT comes from the controller's own box; then the matched noisy
+        # GT box may replace centre / size, and the filters are rebuilt from the mixed box
+        ops.paste_back(None, box_t, bufs['fy'], bufs['fx'], None, attn_box=bufs['attn_box'][:, t], y_out=None,
+                       out_bstride=thw, band=bufs['band'])
+        ops.knob_greedy_box(bufs['attn_box'][:, t], thw, knob['rect'], H, W, knob['iou_steps'][:, t], T * T,
+                            knob['grd'])
+        ops.knob_mix_box(box_t, knob['grd'], knob['ctr'], knob['size'], knob['knob_box'][:, t], T)
+        ops.get_gaussian_filter(box_t, H, W, F, fy=bufs['fy'], fx=bufs['fx'], band=bufs['band'])
       x_patch = bufs['x_patch_all'][t]
       _lib.TAG = 'extract'
       ops.extract_patch(bufs['xs'], bufs['canvas'], self.chan_map, box_t, bufs['fy'], bufs['fx'], bufs['band'],
@@ -460,9 +490,19 @@ class FullModel(_ModelBase):
         self._block(train, prev, w['adcnn_w%d' % i], 'adcnn', i, t, 1, x2=sk, upsample=pl, out=dst)
         prev = dst
       _lib.TAG = 'paste_back'
-      ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],
-                     attn_box=bufs['attn_box'][:, t], y_out=bufs['y_out'][:, t], out_bstride=thw,
-                     disable_overwrite=self.disable_overwrite, band=bufs['band'])
+      if knob is None:
+        ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],
+                       attn_box=bufs['attn_box'][:, t], y_out=bufs['y_out'][:, t], out_bstride=thw,
+                       disable_overwrite=self.disable_overwrite, band=bufs['band'])
+      else:
+        # the mask goes through the MIXED filters; the canvas write is decided per example by the mask switch, so
+        # the fused canvas update runs on a scratch copy and knob_canvas writes the real one (full_model.py:826-845)
+        knob['canvas_tmp'].copy_(bufs['canvas'])
+        ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], knob['canvas_tmp'],
+                       attn_box=None, y_out=bufs['y_out'][:, t], out_bstride=thw,
+                       disable_overwrite=self.disable_overwrite, band=bufs['band'])
+        ops.knob_canvas(knob['grd'], knob['y_gt'], knob['noise'][:, t], T * H * W, knob['knob_segm'][:, t], T,
+                        bufs['y_out'][:, t], thw, bufs['canvas'])
       if score_side is not None:
         torch.cuda.current_stream().wait_stream(score_side)  # before the next step overwrites `core`
 
@@ -518,7 +558,7 @@ class FullModel(_ModelBase):
                            want_box=want_gt_box)
     return res, side
 
-  def _loss(self, bufs, y_gt, s_gt, out, gt):
+  def _loss(self, bufs, y_gt, s_gt, out, gt, iou_box_steps=None):
     """full_model.py:916-1081 (matching on soft IoU, 'iou' losses, hard statistics)."""
     o = self.opt
     _lib.TAG = 'loss'
@@ -536,7 +576,11 @@ class FullModel(_ModelBase):
     # both matchings (boxes, masks) in ONE launch of 2B warps: they are independent and latency-bound
     B, T = s_gt.shape
     iou_both = torch.empty((2 * B, T, T), device=s_gt.device, dtype=torch.float32)
-    iou_box = ops.f_iou(bufs['attn_box'], None, b_rect=rect, out=iou_both[:B])
+    if iou_box_steps is None:
+      iou_box = ops.f_iou(bufs['attn_box'], None, b_rect=rect, out=iou_both[:B])
+    else:  # use_knob: the per-step IoUs of the decode loop (full_model.py:926-929)
+      iou_both[:B].copy_(iou_box_steps)
+      iou_box = iou_both[:B]
     iou_soft = ops.f_iou(bufs['y_out'], y_gt, out=iou_both[B:])
     match_both = ops.f_segm_match(iou_both, torch.cat([s_gt, s_gt], 0))
     match_box, match = match_both[:B], match_both[B:]
@@ -552,14 +596,17 @@ class FullModel(_ModelBase):
     if box_gt is not None:
       out['attn_box_gt'] = box_gt
 
-  def _run(self, bufs, B, with_loss, want_all, train=False):
+  def _run(self, bufs, B, with_loss, want_all, train=False, draws=None):
     """Enqueue one full forward on the current stream; returns the dict of (static) output tensors."""
     st = bufs['static_in']
     gt = self._gt_boxes(bufs, st['y_gt'], want_all) if with_loss else None
     chains = self._chains(B)
+    knob = None
     if len(chains) == 1 or train:  # batch statistics couple the examples: training mode never splits the batch
       self._prepare(bufs, st['x'], st.get('d_in'), st.get('y_in'))
-      self._decode(bufs, B, train)
+      if train and draws is not None:
+        knob = self._knob_setup(bufs, st['y_gt'], draws)
+      self._decode(bufs, B, train, knob)
     else:
       cur = torch.cuda.current_stream()
       forked = []
@@ -584,7 +631,7 @@ class FullModel(_ModelBase):
       out['x_patch'] = bufs['x_patch_all'][..., :self.D].permute(1, 0, 2, 3, 4).contiguous()
       out['y_out_patch'] = bufs['y_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
     if with_loss:
-      self._loss(bufs, st['y_gt'], st['s_gt'], out, gt)
+      self._loss(bufs, st['y_gt'], st['s_gt'], out, gt, None if knob is None else knob['iou_steps'])
       scal = out['loss_scalars']
       for i, k in enumerate(LOSS_KEYS):
         out[k] = scal[i]
@@ -610,7 +657,7 @@ class FullModel(_ModelBase):
     done.record(cs)
     bufs['prefetched'] = (id(batch), slot, done, y_gt is not None)
 
-  def forward(self, batch, outputs=None, phase_train=False, with_loss=True, use_graph=True):
+  def forward(self, batch, outputs=None, phase_train=False, with_loss=True, use_graph=True, draws=None):
     """``sess.run([model[k] for k in outputs], feed_dict)`` of runner.py:98-105.
     Returns a dict of CUDA tensors (all keys when ``outputs`` is None).  The inputs are copied into
     static device buffers; with ``use_graph`` the ~750 kernel launches of the T-step decode + loss block are
@@ -623,8 +670,17 @@ class FullModel(_ModelBase):
       # the EMA shadows of its (layer, step) copy in place (nnlib.py:96-119).  use_knob=False and the identity draw of
       # random_transformation (apply ops.random_transformation to the batch beforehand for other draws); eager
       # launches, no CUDA graph (the raw conv outputs are temporaries).
+      # opt['use_knob'] (scheduled sampling, full_model.py:589-625,744-785,826-845) needs its random draws as inputs
+      # (synthetic.make_knob_draws): Bernoulli switches, noisy-GT-box parameters and the canvas noise.
       if self.opt.get('use_knob', False):
-        raise _lib.RecAttendError('the scheduled-sampling knob (full_model.py:589-625) is not built; use_knob=False')
+        if draws is None:
+          raise _lib.RecAttendError('use_knob=True: pass the random draws (synthetic.make_knob_draws) as `draws`')
+        if self.opt.get('use_iou_box', False):
+          raise _lib.RecAttendError('use_iou_box (coordinate IoU for the knob match, full_model.py:750-754) is not built')
+        if 'y_gt' not in batch:
+          raise _lib.RecAttendError('use_knob=True needs y_gt')
+      else:
+        draws = None
       use_graph = False
       self._bn_dirty = True
     elif self._bn_dirty:
@@ -654,7 +710,7 @@ class FullModel(_ModelBase):
     want_all = want is None or bool(want & {'x_patch', 'y_out_patch', 'attn_box_gt'})
     key = (with_loss, want_all, slot)
     if not use_graph:
-      out = self._run(bufs, B, with_loss, want_all, train=bool(phase_train))
+      out = self._run(bufs, B, with_loss, want_all, train=bool(phase_train), draws=draws if phase_train else None)
     else:
       graphs = bufs.setdefault('graphs', {})
       if key not in graphs:

@@ -360,3 +360,37 @@ def random_transformation(x, padding, offset, vflip=False, hflip=False, transpos
               1 if vflip else 0, 1 if hflip else 0, 1 if transpose else 0, _p(dst), _stream())
     out[key] = dst
   return out
+
+
+# ----------------------------------------------------------------------------- scheduled sampling (training mode)
+def gt_attn_noise(rect_raw, area, pad, shift, min_padding):
+  """Noisy GT attention boxes (full_model.py:568-580): rect_raw [B,T,4] raw mask extrema, area [B,T], pad [B,T(,1)],
+  shift [B,T,2] -> (ctr [B,T,2], size [B,T,2])."""
+  _chk(rect_raw, area, pad, shift)
+  B, T = area.shape
+  ctr = torch.empty((B, T, 2), device=area.device, dtype=torch.float32)
+  size = torch.empty((B, T, 2), device=area.device, dtype=torch.float32)
+  _lib.call('ra_gt_attn_noise_f32', _p(rect_raw), _p(area), _p(pad), _p(shift), float(min_padding), B, T, _p(ctr),
+            _p(size), _stream())
+  return ctr, size
+
+
+def knob_greedy_box(attn_box_t, box_bstride, gt_rect, H, W, iou_t, iou_bstride, grd):
+  """full_model.py:756-759: IoU of this step's attention box with every GT box + greedy match."""
+  B, T = grd.shape
+  _lib.call('ra_knob_greedy_box_f32', _p(attn_box_t), box_bstride, _p(gt_rect), B, T, H, W, _p(iou_t), iou_bstride,
+            _p(grd), _stream())
+
+
+def knob_mix_box(box_t, grd, ctr_gt, size_gt, knob_t, knob_stride):
+  """full_model.py:760-776: mix the matched noisy GT box into the box record of this step (in place)."""
+  B, T = grd.shape
+  _lib.call('ra_knob_mix_box_f32', _p(box_t), _p(grd), _p(ctr_gt), _p(size_gt), _p(knob_t), knob_stride, B, T,
+            _stream())
+
+
+def knob_canvas(grd, y_gt, noise_t, noise_bstride, knob_t, knob_stride, y_out_t, out_bstride, canvas):
+  """full_model.py:826-845: canvas = max(canvas, knob ? matched GT mask * (1 - noise) : y_out_t)."""
+  B, T, H, W = y_gt.shape
+  _lib.call('ra_knob_canvas_f32', _p(grd), _p(y_gt), _p(noise_t), noise_bstride, _p(knob_t), knob_stride, _p(y_out_t),
+            out_bstride, B, T, H, W, _p(canvas), _stream())

@@ -158,3 +158,33 @@ def dcnn_skip_channels(opt):
   ach = [d_attn] + list(opt['attn_cnn_depth'])
   rev = ach[::-1][1:] + [d_attn]
   return ([0] + rev)[:n]
+
+
+def knob_probability(opt, global_step, offset_key):
+  """full_model.py:598-625: min(1, knob_base * knob_decay^(max(0, step - offset) / steps_per_knob_decay) * (1 + log(1 + 3t)))
+  per decode step t (time scale only with knob_use_timescale)."""
+  T = opt['timespan']
+  step = max(0.0, float(global_step) - float(opt[offset_key]))
+  p = np.float32(opt['knob_base']) * np.power(np.float32(opt['knob_decay']),
+                                               np.float32(step / float(opt['steps_per_knob_decay'])))
+  scale = (1.0 + np.log(1.0 + np.arange(T, dtype=np.float32) * 3.0)) if opt.get('knob_use_timescale', True) \
+      else np.ones(T, np.float32)
+  return np.minimum(np.float32(1.0), p * scale.astype(np.float32)).astype(np.float32)
+
+
+def make_knob_draws(opt, batch_size, global_step=0, seed=99):
+  """The random draws of one training step of the scheduled-sampling knob as explicit arrays (TensorFlow's streams
+  cannot be reproduced): Bernoulli box / mask switches (full_model.py:608-610,622-624), the padding
+  ratio and centre shift of the noisy GT boxes (:573-579) and the per-step canvas noise (:836-837)."""
+  rng = np.random.default_rng(seed)
+  B, T, H, W = batch_size, opt['timespan'], opt['inp_height'], opt['inp_width']
+  pb = knob_probability(opt, global_step, 'knob_box_offset').reshape(1, T)
+  ps = knob_probability(opt, global_step, 'knob_segm_offset').reshape(1, T)
+  r = opt['attn_box_padding_ratio']
+  return {
+      'gt_knob_box': (rng.random((B, T)) <= pb).astype(np.float32),
+      'gt_knob_segm': (rng.random((B, T)) <= ps).astype(np.float32),
+      'gt_box_pad': rng.uniform(r - opt['gt_box_pad_noise'], r + opt['gt_box_pad_noise'], (B, T, 1)).astype(np.float32),
+      'gt_box_ctr_shift': rng.uniform(-opt['gt_box_ctr_noise'], opt['gt_box_ctr_noise'], (B, T, 2)).astype(np.float32),
+      'gt_segm_noise': rng.uniform(0.0, opt['gt_segm_noise'], (B, T, H, W)).astype(np.float32),
+  }

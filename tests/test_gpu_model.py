@@ -132,7 +132,7 @@ def test_outputs_subset_and_errors(cuda):
   assert sorted(out) == ['s_out', 'y_out'] and tuple(out['y_out'].shape) == (2, 3, 64, 64)
   knob = get_model(dict(opt, use_knob=True)).load_weights(ra.synthetic.make_weights(opt))
   with pytest.raises(_lib.RecAttendError):
-    knob.forward(ra.synthetic.make_batch(opt, 1), phase_train=True)  # scheduled sampling is not built
+    knob.forward(ra.synthetic.make_batch(opt, 1), phase_train=True)  # scheduled sampling needs its draws
   w = model.export_weights()
   assert 'ctrl_cnn_w_0' in w and w['ctrl_cnn_w_0'].shape == (3, 3, 4, 8)
 
@@ -250,3 +250,36 @@ def test_training_mode_forward_batch_stat_bn(cuda):
   torch.cuda.synchronize()
   for k in ('y_out', 's_out', 'attn_box'):
     assert rel_err(out_eval[k].float().cpu().numpy(), ref_eval[k].numpy()) <= MODEL_TOL, k
+
+
+@pytest.mark.parametrize('step', [0, 9000])
+def test_training_mode_knob(cuda, step):
+  """Scheduled sampling (full_model.py:589-625,744-785,826-845) with explicit draws against the oracle: greedy GT-box
+  match per step, noisy GT box mixed into centre / size, canvas written from the matched GT mask where the mask
+  switch is on.  T = 2 keeps the round-off amplification of the training-mode loop small (see the BN test)."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.full_model import FullModel
+  T, B = 2, 4
+  opt = ra.config.full_model_opt('kitti', 64, 128, T, use_knob=True)
+  batch = ra.synthetic.make_batch(opt, B, seed=8)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  draws = ra.synthetic.make_knob_draws(opt, B, global_step=step, seed=2)
+  if step > 0:  # make sure both branches of both switches occur
+    draws['gt_knob_box'][:, 0] = [1, 0, 1, 0]
+    draws['gt_knob_segm'][:, 0] = [0, 1, 1, 0]
+    draws['gt_knob_box'][:, 1] = [0, 1, 1, 0]
+  ref = OM.full_model_forward(opt, weights, batch, phase_train=True, draws=draws)
+  model = FullModel(opt).load_weights(weights)
+  out = model.forward(batch, phase_train=True, draws=draws)
+  torch.cuda.synchronize()
+  tol = {0: MODEL_TOL, 1: 5e-3}  # step 1 sits behind one pass of the ill-conditioned training loop
+  for k in ('attn_ctr', 'attn_size', 'attn_box', 'x_patch', 'y_out', 's_out'):
+    for t in range(T):
+      assert rel_err(out[k][:, t].float().cpu().numpy(), ref[k][:, t].numpy()) <= tol[t], (k, t)
+  assert rel_err(out['iou_soft_box_pairwise'].cpu().numpy(), ref['iou_soft_box_pairwise'].numpy()) <= 5e-3
+  assert rel_err(out['canvas'].float().cpu().numpy(), ref['canvas'].numpy()) <= 5e-3
+  # where the box switch is on at step 0 the centre is the matched noisy GT centre, not the controller's
+  plain = OM.full_model_forward(dict(opt, use_knob=False), weights, batch, phase_train=True)
+  on = draws['gt_knob_box'][:, 0] > 0
+  moved = (out['attn_ctr'][:, 0].cpu() - plain['attn_ctr'][:, 0]).abs().sum(1).numpy()
+  assert (moved[on] > 1e-2).all() and (moved[~on] < 1e-2).all()

@@ -2,6 +2,7 @@
 (no TensorFlow 0.12 here, no golden outputs in the reference), so every TF-specific semantic the
 restatement relies on is checked against an independent numpy formulation."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import model as OM
@@ -200,3 +201,42 @@ def test_random_transformation_oracle_semantics():
   r = OM.random_transformation(x, 2, (2, 2), vflip=True, hflip=True, transpose=True, y=y)
   assert torch.equal(r['x'], torch.flip(x, [1, 2]).permute(0, 2, 1, 3))
   assert torch.equal(r['y'], torch.flip(y, [2, 3]).permute(0, 1, 3, 2))
+
+
+def test_knob_oracle_semantics():
+  """Scheduled sampling (full_model.py:589-625,744-785,826-843) in the oracle: switches off == plain training
+  forward; box switch on == the matched noisy GT box drives the glimpse; mask switch on == the canvas is written
+  from the matched GT mask."""
+  import rec_attend_b200 as ra
+  opt = ra.config.full_model_opt('kitti', 32, 64, 3, use_knob=True)
+  B, T = 3, 3
+  batch = ra.synthetic.make_batch(opt, B, seed=3)
+  w = ra.synthetic.make_weights(opt)
+  draws = ra.synthetic.make_knob_draws(opt, B, global_step=0, seed=1)
+  assert (draws['gt_knob_box'] == 1).all(), 'at step 0 the box knob probability is 1 (knob_base = 1)'
+  p = ra.synthetic.knob_probability(opt, 8000 + 1500, 'knob_segm_offset')
+  assert p[0] == pytest.approx(0.5) and p[1] == pytest.approx(min(1.0, 0.5 * (1 + np.log(4.0))))
+  off = dict(draws, gt_knob_box=np.zeros((B, T), np.float32), gt_knob_segm=np.zeros((B, T), np.float32))
+  with torch.no_grad():
+    plain = OM.full_model_forward(dict(opt, use_knob=False), w, batch, phase_train=True)
+    r_off = OM.full_model_forward(opt, w, batch, phase_train=True, draws=off)
+    r_on = OM.full_model_forward(opt, w, batch, phase_train=True, draws=draws)
+  for k in ('y_out', 'attn_box', 'attn_ctr', 's_out'):
+    assert torch.equal(plain[k], r_off[k]), k
+  assert torch.allclose(plain['iou_soft_box_pairwise'], r_off['iou_soft_box_pairwise'], atol=1e-6)
+  assert float(plain['loss']) == pytest.approx(float(r_off['loss']), abs=1e-5)
+  # box switch on: centre / size of step 0 are those of a (noisy) GT box, not the controller's
+  tl_n, br_n, _ = OM.get_gt_box(torch.from_numpy(batch['y_gt']), padding_ratio=torch.from_numpy(draws['gt_box_pad']),
+                                center_shift_ratio=torch.from_numpy(draws['gt_box_ctr_shift']),
+                                min_padding=opt['padding'] + 4)
+  ctr_n = (tl_n + br_n) / 2.0
+  d = (r_on['attn_ctr'][:, 0].unsqueeze(1) - ctr_n).abs().sum(2).min(1)[0]
+  assert float(d.max()) < 1e-4
+  assert not torch.equal(r_on['attn_ctr'], plain['attn_ctr'])
+  # the attention box OUTPUT of step 0 is still the controller's own box (computed before the mix, :738-741)
+  assert torch.equal(r_on['attn_box'][:, 0], plain['attn_box'][:, 0])
+  # mask switch: with noise 0 and the switch on, the final canvas contains every matched GT mask
+  seg = dict(draws, gt_knob_segm=np.ones((B, T), np.float32), gt_segm_noise=np.zeros_like(draws['gt_segm_noise']))
+  with torch.no_grad():
+    r_seg = OM.full_model_forward(opt, w, batch, phase_train=True, draws=seg)
+  assert float(r_seg['canvas'].max()) == 1.0
