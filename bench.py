@@ -328,6 +328,28 @@ def run_ours(args):
     step_e2e()
   ms_e2e, _ = timed(step_e2e, args.steps)
 
+  # secondary: the TRAINING-mode forward (batch-statistics BN, EMA update, scheduled sampling with explicit draws) -
+  # forward only, the backward pass is not built; 1-GPU runs only, a few steps
+  train_forward = None
+  if world == 1 and not args.no_train_forward:
+    opt_t = dict(opt, use_knob=True)
+    model_t = FullModel(opt_t).load_weights(weights)
+    draws = synthetic.make_knob_draws(opt_t, B, global_step=0, seed=7)
+
+    def step_train():
+      return model_t.forward(dev_batch, outputs=fetch, phase_train=True, draws=draws)
+
+    for _ in range(2):
+      step_train()
+    n_t = max(2, min(args.steps, 5))
+    ms_t, launches_t = timed(step_train, n_t)
+    train_forward = {'value': B * T / (ms_t / n_t / 1e3), 'unit': 'masks/s', 'ms_per_step': ms_t / n_t,
+                     'gpu_launches_per_step': int(launches_t // n_t),
+                     'note': 'training-mode FORWARD only (batch-statistics BN + EMA update + scheduled-sampling knob), '
+                             'one CUDA graph per step; no backward pass yet'}
+    del model_t
+    torch.cuda.empty_cache()
+
   value = dist_util.aggregate_masks_per_sec(world, B, T, ms / args.steps)
   e2e_value = dist_util.aggregate_masks_per_sec(world, B, T, ms_e2e / args.steps)
   h2d = sum(v.numel() * v.element_size() for v in pinned.values())
@@ -418,6 +440,7 @@ def run_ours(args):
         'kernels': kernels,
         'conv_layers': layers,
         'cpu_baseline': cpu_baseline,
+        'train_forward': train_forward,
     }
     emit(line)
   dist_util.finalize()
@@ -454,6 +477,7 @@ def main():
   ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch size')
   ap.add_argument('--ref-batch', type=int, default=4, help='batch size of the bounded CPU-baseline sample')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-train-forward', action='store_true', help='skip the secondary training-mode forward timing')
   args = ap.parse_args()
   if args.impl == 'reference':
     return run_reference(args)

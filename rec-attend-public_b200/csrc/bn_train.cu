@@ -13,6 +13,26 @@ namespace {
 constexpr int kBnThreads = 256;
 constexpr int kBnMaxC = 256;
 
+// Sum the per-CTA partials of every channel with the whole CTA (fixed order, double): thread t takes channel t % C and
+// every (kBnThreads / C)-th partial, a second step adds the groups.  out_s[c] = sum / npix.  Needs C <= kBnThreads.
+__device__ __forceinline__ void reduce_partials(const float *__restrict__ partial, int ctas, int C, double inv_npix,
+                                                float *out_s, double *scratch /* [kBnThreads] */) {
+  const int tid = threadIdx.x;
+  const int groups = kBnThreads / C;
+  const int c = tid % C, j = tid / C;
+  double s = 0.0;
+  if (j < groups)
+    for (int k = j; k < ctas; k += groups) s += (double)partial[(size_t)k * C + c];
+  scratch[tid] = s;
+  __syncthreads();
+  if (tid < C) {
+    double t = 0.0;
+    for (int g = 0; g < groups; ++g) t += scratch[g * C + tid];
+    out_s[tid] = (float)(t * inv_npix);
+  }
+  __syncthreads();
+}
+
 // partial[cta][C] <- sum over this CTA's pixels of (x - center[c])^pow, pow in {1, 2}
 // V = 4: float4 path (C % 4 == 0); V = 1: any channel count (the 1-channel mask layer of the deconv head)
 template <int POW, int V>
@@ -21,18 +41,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float *__r
                                                                 float *__restrict__ partial) {
   __shared__ float center_s[kBnMaxC];
   __shared__ float red_s[kBnThreads * 4];
+  __shared__ double dbl_s[kBnThreads];
   const int tid = threadIdx.x;
   const int cg_n = C / V;
-  for (int c = tid; c < C; c += kBnThreads) {
-    float m = 0.f;
-    if (POW == 2) {  // the mean, from the first pass's partial sums (fixed order, double)
-      double s = 0.0;
-      for (int k = 0; k < prev_ctas; ++k) s += (double)prev_partial[(size_t)k * C + c];
-      m = (float)(s / (double)npix);
-    }
-    center_s[c] = m;
+  if (POW == 2) {  // the mean, from the first pass's partial sums
+    reduce_partials(prev_partial, prev_ctas, C, 1.0 / (double)npix, center_s, dbl_s);
+  } else {
+    for (int c = tid; c < C; c += kBnThreads) center_s[c] = 0.f;
+    __syncthreads();
   }
-  __syncthreads();
   // thread -> channel group cg = tid % cg_n, pixel lane pl = tid / cg_n; threads beyond lanes * cg_n idle (C = 96)
   const int cg = tid % cg_n, lanes = kBnThreads / cg_n, pl = tid / cg_n;
   float ctr[V], acc[V];
@@ -41,26 +58,39 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float *__r
     ctr[e] = center_s[cg * V + e];
     acc[e] = 0.f;
   }
-  for (size_t p = (size_t)blockIdx.x * lanes + pl; pl < lanes && p < npix; p += (size_t)gridDim.x * lanes) {
-    float v[V];
-    if (V == 4) {
-      const float4 q = __ldg(reinterpret_cast<const float4 *>(x + p * C + cg * 4));
-      v[0] = q.x;
-      v[V > 1 ? 1 : 0] = q.y;
-      v[V > 2 ? 2 : 0] = q.z;
-      v[V > 3 ? 3 : 0] = q.w;
-    } else {
-      v[0] = __ldg(x + p * C + cg);
-    }
+  // four independent loads in flight per thread (the big first-layer tensors are streamed from HBM)
+  constexpr int U = 4;
+  const size_t stride = (size_t)gridDim.x * lanes;
+  for (size_t p0 = (size_t)blockIdx.x * lanes + pl; pl < lanes && p0 < npix; p0 += U * stride) {
+    float v[U][V];
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      if (POW == 1) {
-        acc[e] += v[e];
-      } else {
-        const float d = v[e] - ctr[e];
-        acc[e] = fmaf(d, d, acc[e]);
+    for (int u = 0; u < U; ++u) {
+      const size_t p = p0 + u * stride;
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[u][e] = (POW == 1) ? 0.f : ctr[e];  // neutral element for pixels past the end
+      if (p < npix) {
+        if (V == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4 *>(x + p * C + cg * 4));
+          v[u][0] = q.x;
+          v[u][V > 1 ? 1 : 0] = q.y;
+          v[u][V > 2 ? 2 : 0] = q.z;
+          v[u][V > 3 ? 3 : 0] = q.w;
+        } else {
+          v[u][0] = __ldg(x + p * C + cg);
+        }
       }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        if (POW == 1) {
+          acc[e] += v[u][e];
+        } else {
+          const float d = v[u][e] - ctr[e];
+          acc[e] = fmaf(d, d, acc[e]);
+        }
+      }
   }
 #pragma unroll
   for (int e = 0; e < V; ++e) red_s[tid * V + e] = acc[e];
@@ -82,16 +112,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
                                                               int relu, float *__restrict__ ema_mean,
                                                               float *__restrict__ ema_var, float *__restrict__ batch_mean,
                                                               float *__restrict__ batch_var, float *__restrict__ y) {
-  __shared__ float inv_s[kBnMaxC], sh_s[kBnMaxC];
+  __shared__ float inv_s[kBnMaxC], sh_s[kBnMaxC], mean_s[kBnMaxC], var_s[kBnMaxC];
+  __shared__ double dbl_s[kBnThreads];
   const int tid = threadIdx.x;
   const size_t npix = (size_t)B * H * W;
+  reduce_partials(sum_partial, ctas, C, 1.0 / (double)npix, mean_s, dbl_s);
+  reduce_partials(sq_partial, ctas, C, 1.0 / (double)npix, var_s, dbl_s);
   for (int c = tid; c < C; c += kBnThreads) {
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < ctas; ++k) {
-      s += (double)sum_partial[(size_t)k * C + c];
-      q += (double)sq_partial[(size_t)k * C + c];
-    }
-    const float mean = (float)(s / (double)npix), var = (float)(q / (double)npix);
+    const float mean = mean_s[c], var = var_s[c];
     const float inv = gamma[c] * rsqrtf(var + eps);
     inv_s[c] = inv;
     sh_s[c] = beta[c] - mean * inv;
@@ -106,14 +134,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
   __syncthreads();
   const int cg_n = C / V;
   const int Ho = H / POOL, Wo = W / POOL;
-  const size_t total = (size_t)B * Ho * Wo * cg_n;
-  for (size_t idx = (size_t)blockIdx.x * kBnThreads + tid; idx < total; idx += (size_t)gridDim.x * kBnThreads) {
-    const int cg = (int)(idx % cg_n);
-    size_t pix = idx / cg_n;
-    const int ox = (int)(pix % Wo);
-    pix /= Wo;
-    const int oy = (int)(pix % Ho);
-    const int b = (int)(pix / Ho);
+  const unsigned total = (unsigned)((size_t)B * Ho * Wo * cg_n);  // < 2^32, checked by the launcher: 32-bit index math
+  for (unsigned idx = blockIdx.x * kBnThreads + tid; idx < total; idx += gridDim.x * kBnThreads) {
+    const int cg = (int)(idx % (unsigned)cg_n);
+    unsigned pix = idx / (unsigned)cg_n;
+    const int ox = (int)(pix % (unsigned)Wo);
+    pix /= (unsigned)Wo;
+    const int oy = (int)(pix % (unsigned)Ho);
+    const int b = (int)(pix / (unsigned)Ho);
     float best[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) best[e] = -INFINITY;
@@ -144,7 +172,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
 int bn_ctas(size_t npix, int C) {
   const int lanes = kBnThreads / ((C & 3) ? C : C / 4);
   size_t want = (npix + lanes - 1) / lanes;
-  const size_t cap = (size_t)ra::kNumSMs * 4;
+  const size_t cap = (size_t)ra::kNumSMs;  // one CTA per SM at most: every CTA of the next pass re-reduces these partials
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
@@ -181,6 +209,7 @@ extern "C" int ra_bn_train_block_f32(const float *x, int B, int H, int W, int C,
   rc = ra::finish_launch("bn_partial_kernel<2>");
   if (rc != RA_OK) return rc;
   const size_t total = (size_t)B * (H / pool) * (W / pool) * (vec ? C / 4 : C);
+  if (total >= 0xffffffffULL) return RA_ERR_UNSUPPORTED;
   size_t blocks = (total + kBnThreads - 1) / kBnThreads;
   if (blocks > (size_t)ra::kNumSMs * 8) blocks = (size_t)ra::kNumSMs * 8;
 #define RA_BN_APPLY(P, V)                                                                                            \

@@ -399,29 +399,35 @@ __global__ void score_kernel(const float *__restrict__ h, int Hd, const float *_
 }
 
 // ------------------------------------------------------------------ box model GT interaction
-// Phase 1: per example, soft IoU of this step's attention box against every GT rectangle.
-__global__ void __launch_bounds__(256) box_gt_iou_kernel(const float *__restrict__ attn_box, size_t box_bstride,
-                                                         const float *__restrict__ gt_rect, int T, int H, int W,
-                                                         float *__restrict__ iou_t, int iou_bstride,
-                                                         float *__restrict__ grd) {
-  extern __shared__ float sm[];  // [T] inter, [T] rect area, then scratch
+// Phase 1: per example, soft IoU of this step's attention box against every GT rectangle, then the greedy match.
+// Two launches: (row chunks x examples) CTAs accumulate, per GT rectangle, the sum of the box inside it (and the total),
+// one small CTA per example finishes - the rectangle areas are analytic.  (The first version used ONE CTA per example
+// for all H*W pixels: 1.27 ms per launch at 256x512, B = 32.)
+constexpr int kBgChunks = 16;  // row chunks per example
+
+__global__ void __launch_bounds__(256) box_gt_partial_kernel(const float *__restrict__ attn_box, size_t box_bstride,
+                                                             const float *__restrict__ gt_rect, int T, int H, int W,
+                                                             float *__restrict__ partial /* [B][kBgChunks][T+1] */) {
+  extern __shared__ float sm[];  // rc_s [T][4]
   __shared__ float red[32];
-  const int b = blockIdx.x;
-  float *inter_s = sm, *area_s = sm + T, *rc_s = sm + 2 * T;  // rc_s [T][4]
+  const int b = blockIdx.y, ch = blockIdx.x;
+  float *rc_s = sm;
   for (int i = threadIdx.x; i < T * 4; i += blockDim.x) rc_s[i] = gt_rect[(size_t)b * T * 4 + i];
-  for (int i = threadIdx.x; i < 2 * T; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
-  const float *bx = attn_box + (size_t)b * box_bstride;
+  const int rows = (H + kBgChunks - 1) / kBgChunks;
+  const int y0 = ch * rows, y1 = min(H, y0 + rows);
+  const int n = max(0, y1 - y0) * W;
+  const float *bx = attn_box + (size_t)b * box_bstride + (size_t)y0 * W;
+  float *out = partial + ((size_t)b * kBgChunks + ch) * (T + 1);
   float tot = 0.f;
-  // thread-private accumulation over a strided set of pixels, one GT at a time is too slow;
-  // instead each thread walks its pixels and adds to per-GT shared accumulators at the end
   for (int m0 = 0; m0 < T; m0 += 8) {
-    float in8[8], ar8[8];
+    float in8[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) in8[e] = ar8[e] = 0.f;
-    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    for (int e = 0; e < 8; ++e) in8[e] = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const float v = bx[i];
-      const float fy = (float)(i / W), fx = (float)(i % W);
+      const int yy = i / W;
+      const float fy = (float)(y0 + yy), fx = (float)(i - yy * W);
       if (m0 == 0) tot += v;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -429,35 +435,57 @@ __global__ void __launch_bounds__(256) box_gt_iou_kernel(const float *__restrict
           const float *rc = rc_s + (m0 + e) * 4;
           const bool in = fy >= rc[0] && fx >= rc[1] && fy <= rc[2] && fx <= rc[3];
           in8[e] += in ? v : 0.f;
-          ar8[e] += in ? 1.f : 0.f;
         }
       }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float s1 = ra::block_sum(in8[e], red);
-      const float s2 = ra::block_sum(ar8[e], red);
-      if (threadIdx.x == 0 && m0 + e < T) {
-        inter_s[m0 + e] = s1;
-        area_s[m0 + e] = s2;
-      }
+      if (threadIdx.x == 0 && m0 + e < T) out[m0 + e] = s1;
     }
   }
   tot = ra::block_sum(tot, red);
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) out[T] = tot;
+}
+
+__global__ void box_gt_finalize_kernel(const float *__restrict__ partial, const float *__restrict__ gt_rect, int T, int H,
+                                       int W, float *__restrict__ iou_t, int iou_bstride, float *__restrict__ grd) {
+  __shared__ float iou_s[64];
+  const int b = blockIdx.x, m = threadIdx.x;
+  const float *pp = partial + (size_t)b * kBgChunks * (T + 1);
+  float tot = 0.f;
+  for (int c = 0; c < kBgChunks; ++c) tot += pp[c * (T + 1) + T];
+  if (m < T) {
+    float inter = 0.f;
+    for (int c = 0; c < kBgChunks; ++c) inter += pp[c * (T + 1) + m];
+    // number of pixels (y, x) with ty <= y <= by, tx <= x <= bx inside the image
+    const float *rc = gt_rect + ((size_t)b * T + m) * 4;
+    const float ylo = fmaxf(0.f, ceilf(rc[0])), yhi = fminf((float)(H - 1), floorf(rc[2]));
+    const float xlo = fmaxf(0.f, ceilf(rc[1])), xhi = fminf((float)(W - 1), floorf(rc[3]));
+    const float area = fmaxf(0.f, yhi - ylo + 1.f) * fmaxf(0.f, xhi - xlo + 1.f);
     const float hw_eps = (float)(H * W) * 1e-5f;
-    float mx = -INFINITY;
-    for (int m = 0; m < T; ++m) {
-      const float v = inter_s[m] / (tot + area_s[m] - inter_s[m] + hw_eps);  // box_model.py:494-495
-      iou_t[(size_t)b * iou_bstride + m] = v;
-      inter_s[m] = v;
-      mx = fmaxf(mx, v);
-    }
-    float cnt = 0.f;  // modellib.py:366-379 with matched == 0
-    for (int m = 0; m < T; ++m) cnt += (inter_s[m] == mx) ? 1.f : 0.f;
-    for (int m = 0; m < T; ++m) grd[(size_t)b * T + m] = (inter_s[m] == mx) ? 1.f / cnt : 0.f;
+    const float v = inter / (tot + area - inter + hw_eps);  // box_model.py:494-495, full_model.py:756-758
+    iou_t[(size_t)b * iou_bstride + m] = v;
+    iou_s[m] = v;
   }
+  __syncthreads();
+  if (m < T) {  // modellib.py:366-379 with matched == 0: one-hot of the row max, ties share 1/k
+    float mx = -INFINITY, cnt = 0.f;
+    for (int k = 0; k < T; ++k) mx = fmaxf(mx, iou_s[k]);
+    for (int k = 0; k < T; ++k) cnt += (iou_s[k] == mx) ? 1.f : 0.f;
+    grd[(size_t)b * T + m] = (iou_s[m] == mx) ? 1.f / cnt : 0.f;
+  }
+}
+
+// grd_ws doubles as the workspace of the partial sums: it must hold B * max(T, kBgChunks * (T + 1)) floats
+int box_gt_iou_launch(const float *attn_box, size_t box_bstride, const float *gt_rect, int B, int T, int H, int W,
+                      float *iou_t, int iou_bstride, float *grd, float *partial, cudaStream_t s) {
+  box_gt_partial_kernel<<<dim3(kBgChunks, B), 256, (size_t)(4 * T) * sizeof(float), s>>>(attn_box, box_bstride, gt_rect, T,
+                                                                                       H, W, partial);
+  int rc = ra::finish_launch("box_gt_partial_kernel");
+  if (rc != RA_OK) return rc;
+  box_gt_finalize_kernel<<<B, 64, 0, s>>>(partial, gt_rect, T, H, W, iou_t, iou_bstride, grd);
+  return ra::finish_launch("box_gt_finalize_kernel");
 }
 
 // Phase 2: canvas = max(canvas, sum_m grd[m] * y_gt[m] * (1 - noise))   (box_model.py:497-503)
@@ -574,6 +602,23 @@ int iou_plan(int N, int M, int HW, IouParams *p) {
 
 }  // namespace
 
+// Device scratch of the box/GT IoU partial sums, grown on demand and kept (a few KB; one per process and device).
+// Allocation happens outside stream capture in practice: the first (eager warm-up) call sizes it.
+static float *box_gt_workspace(size_t floats) {
+  static float *buf = nullptr;
+  static size_t cap = 0;
+  if (floats > cap) {
+    float *nb = nullptr;
+    if (cudaMalloc(&nb, floats * sizeof(float)) != cudaSuccess) {
+      ra::set_last_error("cudaMalloc(box_gt workspace)", cudaGetLastError());
+      return nullptr;
+    }
+    buf = nb;  // the old, smaller buffer is leaked on purpose: an in-flight kernel or a captured graph may still use it
+    cap = floats;
+  }
+  return buf;
+}
+
 extern "C" int ra_gt_box_f32(const float *y_gt, int B, int T, int H, int W, float padding_ratio, float min_padding,
                              float *top_left, float *bot_right, float *rect, float *box, float *area, void *stream) {
   if (!y_gt || !top_left || !bot_right || B < 0 || T < 1 || H < 1 || W < 1) return RA_ERR_INVALID_ARG;
@@ -665,9 +710,9 @@ extern "C" int ra_box_gt_step_f32(const float *attn_box, size_t box_bstride, con
     return RA_ERR_INVALID_ARG;
   if (B == 0) return RA_OK;
   cudaStream_t s = ra::as_stream(stream);
-  box_gt_iou_kernel<<<B, 256, (size_t)(6 * T) * sizeof(float), s>>>(attn_box, box_bstride, gt_rect, T, H, W, iou_t,
-                                                                    iou_bstride, grd_ws);
-  int rc = ra::finish_launch("box_gt_iou_kernel");
+  float *partial = box_gt_workspace((size_t)B * kBgChunks * (T + 1));
+  if (partial == nullptr) return RA_ERR_CUDA;
+  int rc = box_gt_iou_launch(attn_box, box_bstride, gt_rect, B, T, H, W, iou_t, iou_bstride, grd_ws, partial, s);
   if (rc != RA_OK) return rc;
   const int HW = H * W;
   int bx = (HW + 255) / 256;
@@ -692,9 +737,10 @@ extern "C" int ra_knob_greedy_box_f32(const float *attn_box, size_t box_bstride,
   if (B < 0 || T < 1 || T > 64 || H < 1 || W < 1) return RA_ERR_INVALID_ARG;
   if (B == 0) return RA_OK;
   if (!attn_box || !gt_rect || !iou_t || !grd) return RA_ERR_INVALID_ARG;
-  box_gt_iou_kernel<<<B, 256, (size_t)(6 * T) * sizeof(float), ra::as_stream(stream)>>>(attn_box, box_bstride, gt_rect, T, H,
-                                                                                        W, iou_t, iou_bstride, grd);
-  return ra::finish_launch("box_gt_iou_kernel");
+  float *partial = box_gt_workspace((size_t)B * kBgChunks * (T + 1));
+  if (partial == nullptr) return RA_ERR_CUDA;
+  return box_gt_iou_launch(attn_box, box_bstride, gt_rect, B, T, H, W, iou_t, iou_bstride, grd, partial,
+                           ra::as_stream(stream));
 }
 
 extern "C" int ra_knob_mix_box_f32(float *box, const float *grd, const float *ctr_gt, const float *size_gt,

@@ -423,6 +423,17 @@ class FullModel(_ModelBase):
     bufs['y_out'] = torch.empty((B, T, H, W), device=dev, dtype=f32)
     return bufs
 
+  def _stage_draws(self, bufs, draws):
+    """Copy the scheduled-sampling draws into static device buffers (one set per batch size)."""
+    st = bufs.setdefault('static_draws', {})
+    for k in ('gt_knob_box', 'gt_knob_segm', 'gt_box_pad', 'gt_box_ctr_shift', 'gt_segm_noise'):
+      v = draws[k]
+      v = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+      if k not in st:
+        st[k] = torch.empty(v.shape, device=self.device, dtype=torch.float32)
+      st[k].copy_(v, non_blocking=True)
+    return st
+
   def _knob_setup(self, bufs, y_gt, draws):
     """Scheduled sampling, once per forward (full_model.py:561-625): clean GT rectangles for the greedy match, noisy
     GT boxes to mix in, the draws on the device."""
@@ -667,9 +678,8 @@ class FullModel(_ModelBase):
       raise _lib.RecAttendError('load_weights() first')
     if phase_train:
       # Training-mode forward: every BN layer normalises with the statistics of THIS batch and moves
-      # the EMA shadows of its (layer, step) copy in place (nnlib.py:96-119).  use_knob=False and the identity draw of
-      # random_transformation (apply ops.random_transformation to the batch beforehand for other draws); eager
-      # launches, no CUDA graph (the raw conv outputs are temporaries).
+      # the EMA shadows of its (layer, step) copy in place (nnlib.py:96-119).  The identity draw of
+      # random_transformation is assumed (apply ops.random_transformation to the batch beforehand for other draws).
       # opt['use_knob'] (scheduled sampling, full_model.py:589-625,744-785,826-845) needs its random draws as inputs
       # (synthetic.make_knob_draws): Bernoulli switches, noisy-GT-box parameters and the canvas noise.
       if self.opt.get('use_knob', False):
@@ -681,7 +691,6 @@ class FullModel(_ModelBase):
           raise _lib.RecAttendError('use_knob=True needs y_gt')
       else:
         draws = None
-      use_graph = False
       self._bn_dirty = True
     elif self._bn_dirty:
       self._refold_bn()
@@ -708,7 +717,9 @@ class FullModel(_ModelBase):
     with_loss = bool(with_loss and has_gt)
     want = None if outputs is None else set(outputs)
     want_all = want is None or bool(want & {'x_patch', 'y_out_patch', 'attn_box_gt'})
-    key = (with_loss, want_all, slot)
+    key = (with_loss, want_all, slot, bool(phase_train), draws is not None)
+    if phase_train and draws is not None:
+      draws = self._stage_draws(bufs, draws)  # static device copies: the captured graph reads the same buffers
     if not use_graph:
       out = self._run(bufs, B, with_loss, want_all, train=bool(phase_train), draws=draws if phase_train else None)
     else:
@@ -717,12 +728,19 @@ class FullModel(_ModelBase):
         # warm-up on a side stream (lazy weight packing, cudaFuncSetAttribute, allocator), then capture
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        train = bool(phase_train)
+        ema_keep = None
+        if train:  # the warm-up and the capture run must not move the EMA shadows: only replays count
+          ema_keep = {k: v.clone() for k, v in self.w.items() if '_ema_' in k}
         with torch.cuda.stream(side):
-          self._run(bufs, B, with_loss, want_all)
+          self._run(bufs, B, with_loss, want_all, train=train, draws=draws if train else None)
         cur.wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-          static_out = self._run(bufs, B, with_loss, want_all)
+          static_out = self._run(bufs, B, with_loss, want_all, train=train, draws=draws if train else None)
+        if ema_keep is not None:
+          for k, v in ema_keep.items():
+            self.w[k].copy_(v)
         graphs[key] = (g, static_out)
       g, out = graphs[key]
       g.replay()
