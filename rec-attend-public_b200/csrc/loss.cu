@@ -3,6 +3,8 @@
 // modellib.py:71-155 (f_dice/f_inter/f_union/f_iou), :268-339 (coverage, conf loss),
 // :366-379 (greedy match), :482-511 (count metrics), :663-749 (GT boxes);
 // full_model.py:821-822 (score), :916-1081 (loss block); box_model.py:484-504.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -605,8 +607,10 @@ int iou_plan(int N, int M, int HW, IouParams *p) {
 // Device scratch of the box/GT IoU partial sums, grown on demand and kept (a few KB; one per process and device).
 // Allocation happens outside stream capture in practice: the first (eager warm-up) call sizes it.
 static float *box_gt_workspace(size_t floats) {
+  static std::mutex mu;
   static float *buf = nullptr;
   static size_t cap = 0;
+  std::lock_guard<std::mutex> lock(mu);
   if (floats > cap) {
     float *nb = nullptr;
     if (cudaMalloc(&nb, floats * sizeof(float)) != cudaSuccess) {
