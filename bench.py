@@ -323,10 +323,10 @@ def run_ours(args):
   if rank == 0:
     sampler.start()
   ms, launches = timed(step_device, args.steps)
-  clocks = sampler.stop() if rank == 0 else None
   for _ in range(2):
     step_e2e()
   ms_e2e, _ = timed(step_e2e, args.steps)
+  clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end-to-end)
 
   # secondary: the TRAINING-mode forward (batch-statistics BN, EMA update, scheduled sampling with explicit draws) -
   # forward only, the backward pass is not built; 1-GPU runs only, a few steps
