@@ -257,7 +257,7 @@ def run_ours(args):
 
   cfg = config.BASELINE_CONFIGS[args.config]
   if cfg['model'] != 'full':
-    raise SystemExit('bench.py times the full model; the box model (config 4) is a parity-test case')
+    return run_box(args, cfg, rank, local_rank, world)
   opt = config.baseline_opt(args.config)
   B = args.batch or cfg['B']
   T = cfg['T']
@@ -443,6 +443,53 @@ def run_ours(args):
         'train_forward': train_forward,
     }
     emit(line)
+  dist_util.finalize()
+  return 0
+
+
+def run_box(args, cfg, rank, local_rank, world):
+  """BASELINE configs[4]: the controller-only model (box_model.py) - a microbench of the controller CNN + glimpse
+  LSTM + attention-box path without the mask head.  Metric: box-steps/sec = B*T / forward time."""
+  import torch
+  from rec_attend_b200 import config, dist_util, synthetic
+  from rec_attend_b200.box_model import BoxModel
+  from rec_attend_b200 import _lib
+  opt = config.baseline_opt(args.config)
+  B, T = args.batch or cfg['B'], cfg['T']
+  batch_np = synthetic.make_batch(opt, B, seed=dist_util.rank_seed(1234, args.config, rank))
+  model = BoxModel(opt).load_weights(synthetic.make_weights(opt, model='box'))
+  dev_batch = {k: torch.from_numpy(v).cuda() for k, v in batch_np.items()}
+  fetch = ['loss', 'box_loss', 'conf_loss', 's_out', 'match_box']
+  lib = _lib.lib()
+  for _ in range(max(3, args.warmup)):
+    model.forward(dev_batch, outputs=fetch)
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  dist_util.barrier()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(args.steps):
+    model.forward(dev_batch, outputs=fetch)
+  e1.record()
+  dist_util.barrier()
+  torch.cuda.synchronize()
+  ms = dist_util.max_over_ranks(e0.elapsed_time(e1), device='cuda')
+  clocks = sampler.stop() if rank == 0 else None
+  n0 = lib.ra_launch_count()
+  model.forward(dev_batch, outputs=fetch, use_graph=False)
+  torch.cuda.synchronize()
+  launches = int(lib.ra_launch_count() - n0)
+  if rank == 0:
+    emit({'metric': 'box-steps/sec', 'value': world * B * T / (ms / args.steps / 1e3), 'unit': 'box-steps/s',
+          'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps,
+          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+          'config': {'workload': cfg['name'], 'arch': cfg['arch'], 'batch_per_gpu': B, 'timespan': T,
+                     'height': cfg['H'], 'width': cfg['W'], 'parallelism': 'dp{}'.format(world),
+                     'step': 'eval forward of the controller-only model (T-step loop with GT-driven canvas) + box / '
+                             'confidence loss'},
+          'gpu_launches': launches * args.steps, 'clocks': clocks})
   dist_util.finalize()
   return 0
 

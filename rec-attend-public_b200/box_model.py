@@ -74,9 +74,11 @@ class BoxModel(_ModelBase):
                 'attn_bot_right_gt': br, 'box_loss': scal[0], 'conf_loss': scal[2], 'loss': scal[13]})
     return out
 
-  def forward(self, batch, outputs=None, phase_train=False):
+  def forward(self, batch, outputs=None, phase_train=False, use_graph=True):
     """``sess.run`` replacement for the box model (eval mode).  batch: x, y_gt, s_gt[, d_in, y_in] and the
-    optional explicit random draw ``canvas_noise`` [B,T,H,W] of box_model.py:501-502 (zeros when absent)."""
+    optional explicit random draw ``canvas_noise`` [B,T,H,W] of box_model.py:501-502 (zeros when absent).
+    With ``use_graph`` the launches of the T-step loop are captured once per (batch size, noise present) in a CUDA
+    graph and replayed; the returned tensors are then the graph's static outputs."""
     if phase_train:
       raise _lib.RecAttendError('training-mode forward is a later row of the scope table')
     if self.w is None:
@@ -91,8 +93,29 @@ class BoxModel(_ModelBase):
     bufs['static_in'] = st
     noise = None
     if batch.get('canvas_noise') is not None:
-      noise = torch.as_tensor(batch['canvas_noise'], dtype=torch.float32).to(self.device).contiguous()
-    out = self._run(bufs, B, noise)
+      src = torch.as_tensor(batch['canvas_noise'], dtype=torch.float32)
+      if 'static_noise' not in bufs:
+        bufs['static_noise'] = torch.empty(tuple(src.shape), device=self.device, dtype=torch.float32)
+      bufs['static_noise'].copy_(src, non_blocking=True)
+      noise = bufs['static_noise']
+    if not use_graph:
+      out = self._run(bufs, B, noise)
+    else:
+      graphs = bufs.setdefault('graphs', {})
+      key = noise is not None
+      if key not in graphs:
+        # warm-up on a side stream (lazy weight packing, attribute calls, workspace allocation), then capture
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+          self._run(bufs, B, noise)
+        cur.wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          static_out = self._run(bufs, B, noise)
+        graphs[key] = (g, static_out)
+      g, out = graphs[key]
+      g.replay()
     if outputs is not None:
       out = {k: out[k] for k in outputs}
     return out
