@@ -17,8 +17,6 @@ class BoxModel(_ModelBase):
     super(BoxModel, self).__init__(opt, device)
     if self.opt.get('num_semantic_classes', 1) != 1 and not self.add_d:
       raise _lib.RecAttendError('multi-class score head is not used by the shipped box configs')
-    if self.opt.get('use_iou_box', False):
-      raise _lib.RecAttendError('use_iou_box is not used by the shipped box configs (run_kitti.sh:44-60)')
     if self.opt['box_loss_fn'] != 'iou':
       raise _lib.RecAttendError("only box_loss_fn='iou' works in the reference (SURVEY §9.13)")
     self.min_padding = 10.0  # modellib.get_gt_box default (box_model.py:386-387)
@@ -61,8 +59,13 @@ class BoxModel(_ModelBase):
       ops.paste_back(None, bufs['box_all'][t], bufs['fy'], bufs['fx'], None, attn_box=bufs['attn_box'][:, t],
                      y_out=None, out_bstride=thw, band=bufs['band'])
       _lib.TAG = 'box_gt'
-      ops.box_gt_step(bufs['attn_box'][:, t], thw, rect, y_gt, None if noise is None else noise[:, t], thw,
-                      bufs['iou_box'][:, t], T * T, bufs['grd'], bufs['canvas'])
+      noise_t = None if noise is None else noise[:, t]
+      if o.get('use_iou_box', False):  # box_model.py:487-491: coordinate IoU instead of the soft box IoU
+        ops.greedy_iou_box(bufs['box_all'][t], rect, bufs['iou_box'][:, t], T * T, bufs['grd'])
+        ops.box_gt_canvas(bufs['grd'], y_gt, noise_t, thw, bufs['canvas'])
+      else:
+        ops.box_gt_step(bufs['attn_box'][:, t], thw, rect, y_gt, noise_t, thw, bufs['iou_box'][:, t], T * T,
+                        bufs['grd'], bufs['canvas'])
       ops.score(bufs['h_all'][t], None, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
     out = {}
     self._controller_outputs(bufs, out)

@@ -490,6 +490,39 @@ int box_gt_iou_launch(const float *attn_box, size_t box_bstride, const float *gt
   return ra::finish_launch("box_gt_finalize_kernel");
 }
 
+// use_iou_box (full_model.py:750-754, box_model.py:487-491): the knob / box-model greedy match on the coordinate IoU
+// of modellib.f_iou_box (modellib.py:206-238; no eps, strict overlap test) between this step's box and every (clean)
+// GT box, instead of the soft IoU of the pasted attention box.  One CTA per example, thread m = GT box m.
+__global__ void greedy_iou_box_kernel(const float *__restrict__ box, const float *__restrict__ gt_rect, int T,
+                                      float *__restrict__ iou_t, int iou_bstride, float *__restrict__ grd) {
+  __shared__ float iou_s[64];
+  const int b = blockIdx.x, m = threadIdx.x;
+  const float *bo = box + (size_t)b * RA_BOX_STRIDE;
+  if (m < T) {
+    const float y1a = bo[RA_BOX_TL_Y], x1a = bo[RA_BOX_TL_X], y2a = bo[RA_BOX_BR_Y], x2a = bo[RA_BOX_BR_X];
+    const float *rc = gt_rect + ((size_t)b * T + m) * 4;
+    const float y1b = rc[0], x1b = rc[1], y2b = rc[2], x2b = rc[3];
+    const float x1 = fmaxf(x1a, x1b), y1 = fmaxf(y1a, y1b), x2 = fminf(x2a, x2b), y2 = fminf(y2a, y2b);
+    const float flag = ((x1 < x2) ? 1.f : 0.f) * ((y1 < y2) ? 1.f : 0.f);
+    const float inter = __fmul_rn(__fmul_rn(flag, x2 - x1), y2 - y1);
+    const float area_a = __fmul_rn(x2a - x1a, y2a - y1a), area_b = __fmul_rn(x2b - x1b, y2b - y1b);
+    const float v = __fdiv_rn(inter, __fadd_rn(area_a, area_b) - inter);
+    iou_t[(size_t)b * iou_bstride + m] = v;
+    iou_s[m] = v;
+  }
+  __syncthreads();
+  if (m < T) {  // modellib.py:366-379 with matched == 0; a NaN score (0/0) poisons the row like a NaN-propagating max
+    float mx = -INFINITY, cnt = 0.f;
+    bool nan = false;
+    for (int k = 0; k < T; ++k) {
+      nan |= (iou_s[k] != iou_s[k]);
+      mx = fmaxf(mx, iou_s[k]);
+    }
+    for (int k = 0; k < T; ++k) cnt += (iou_s[k] == mx) ? 1.f : 0.f;
+    grd[(size_t)b * T + m] = nan ? __int_as_float(0x7fc00000) : ((iou_s[m] == mx) ? 1.f / cnt : 0.f);
+  }
+}
+
 // Phase 2: canvas = max(canvas, sum_m grd[m] * y_gt[m] * (1 - noise))   (box_model.py:497-503)
 __global__ void box_gt_canvas_kernel(const float *__restrict__ grd, const float *__restrict__ y_gt,
                                      const float *__restrict__ noise, size_t noise_bstride, int T, int HW,
@@ -745,6 +778,27 @@ extern "C" int ra_knob_greedy_box_f32(const float *attn_box, size_t box_bstride,
   if (partial == nullptr) return RA_ERR_CUDA;
   return box_gt_iou_launch(attn_box, box_bstride, gt_rect, B, T, H, W, iou_t, iou_bstride, grd, partial,
                            ra::as_stream(stream));
+}
+
+extern "C" int ra_greedy_iou_box_f32(const float *box, const float *gt_rect, int B, int T, float *iou_t, int iou_bstride,
+                                     float *grd, void *stream) {
+  if (B < 0 || T < 1 || T > 64 || iou_bstride < T) return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  if (!box || !gt_rect || !iou_t || !grd) return RA_ERR_INVALID_ARG;
+  greedy_iou_box_kernel<<<B, 64, 0, ra::as_stream(stream)>>>(box, gt_rect, T, iou_t, iou_bstride, grd);
+  return ra::finish_launch("greedy_iou_box_kernel");
+}
+
+extern "C" int ra_box_gt_canvas_f32(const float *grd, const float *y_gt, const float *noise, size_t noise_bstride, int B,
+                                    int T, int H, int W, float *canvas, void *stream) {
+  if (B < 0 || T < 1 || T > 64 || H < 1 || W < 1) return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  if (!grd || !y_gt || !canvas) return RA_ERR_INVALID_ARG;
+  const int HW = H * W;
+  int bx = (HW + 255) / 256;
+  if (bx > 64) bx = 64;
+  box_gt_canvas_kernel<<<dim3(bx, B), 256, 0, ra::as_stream(stream)>>>(grd, y_gt, noise, noise_bstride, T, HW, canvas);
+  return ra::finish_launch("box_gt_canvas_kernel");
 }
 
 extern "C" int ra_knob_mix_box_f32(float *box, const float *grd, const float *ctr_gt, const float *size_gt,

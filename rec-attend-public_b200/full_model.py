@@ -469,8 +469,11 @@ class FullModel(_ModelBase):
         # GT box may replace centre / size, and the filters are rebuilt from the mixed box
         ops.paste_back(None, box_t, bufs['fy'], bufs['fx'], None, attn_box=bufs['attn_box'][:, t], y_out=None,
                        out_bstride=thw, band=bufs['band'])
-        ops.knob_greedy_box(bufs['attn_box'][:, t], thw, knob['rect'], H, W, knob['iou_steps'][:, t], T * T,
-                            knob['grd'])
+        if self.opt.get('use_iou_box', False):  # coordinate IoU of the (pre-mix) box, full_model.py:750-754
+          ops.greedy_iou_box(box_t, knob['rect'], knob['iou_steps'][:, t], T * T, knob['grd'])
+        else:
+          ops.knob_greedy_box(bufs['attn_box'][:, t], thw, knob['rect'], H, W, knob['iou_steps'][:, t], T * T,
+                              knob['grd'])
         ops.knob_mix_box(box_t, knob['grd'], knob['ctr'], knob['size'], knob['knob_box'][:, t], T)
         ops.get_gaussian_filter(box_t, H, W, F, fy=bufs['fy'], fx=bufs['fx'], band=bufs['band'])
       x_patch = bufs['x_patch_all'][t]
@@ -685,8 +688,6 @@ class FullModel(_ModelBase):
       if self.opt.get('use_knob', False):
         if draws is None:
           raise _lib.RecAttendError('use_knob=True: pass the random draws (synthetic.make_knob_draws) as `draws`')
-        if self.opt.get('use_iou_box', False):
-          raise _lib.RecAttendError('use_iou_box (coordinate IoU for the knob match, full_model.py:750-754) is not built')
         if 'y_gt' not in batch:
           raise _lib.RecAttendError('use_knob=True needs y_gt')
       else:

@@ -382,6 +382,19 @@ def knob_greedy_box(attn_box_t, box_bstride, gt_rect, H, W, iou_t, iou_bstride, 
             _p(grd), _stream())
 
 
+def greedy_iou_box(box_t, gt_rect, iou_t, iou_bstride, grd):
+  """opt['use_iou_box'] (full_model.py:750-754, box_model.py:487-491): modellib.f_iou_box of this step's box record
+  against every GT box (gt_rect [B,T,4]) + f_greedy_match."""
+  B, T = grd.shape
+  _lib.call('ra_greedy_iou_box_f32', _p(box_t), _p(gt_rect), B, T, _p(iou_t), iou_bstride, _p(grd), _stream())
+
+
+def box_gt_canvas(grd, y_gt, noise_t, noise_bstride, canvas):
+  """box_model.py:497-503: canvas = max(canvas, sum_m grd*y_gt_m*(1-noise)) (noise_t may be None)."""
+  B, T, H, W = y_gt.shape
+  _lib.call('ra_box_gt_canvas_f32', _p(grd), _p(y_gt), _p(noise_t), noise_bstride, B, T, H, W, _p(canvas), _stream())
+
+
 def knob_mix_box(box_t, grd, ctr_gt, size_gt, knob_t, knob_stride):
   """full_model.py:760-776: mix the matched noisy GT box into the box record of this step (in place)."""
   B, T = grd.shape

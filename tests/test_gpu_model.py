@@ -137,13 +137,15 @@ def test_outputs_subset_and_errors(cuda):
   assert 'ctrl_cnn_w_0' in w and w['ctrl_cnn_w_0'].shape == (3, 3, 4, 8)
 
 
-@pytest.mark.parametrize('H,W,T,B,noise', [(64, 128, 5, 2, False), (64, 128, 4, 3, True),
-                                          (256, 512, 20, 2, True)])  # BASELINE configs[4] at full size, B = 2
-def test_box_model_parity(cuda, H, W, T, B, noise):
+@pytest.mark.parametrize('H,W,T,B,noise,iou_box', [
+    (64, 128, 5, 2, False, False), (64, 128, 4, 3, True, False),
+    (256, 512, 20, 2, True, False),  # BASELINE configs[4] at full size, B = 2
+    (64, 128, 5, 3, True, True)])    # --use_iou_box: coordinate IoU in the greedy match (box_model.py:487-491)
+def test_box_model_parity(cuda, H, W, T, B, noise, iou_box):
   """box_model.get_model (BASELINE config 5 architecture, reduced size) against the oracle."""
   import rec_attend_b200 as ra
   from rec_attend_b200.box_model import BoxModel
-  opt = ra.config.box_model_opt(H, W, T)
+  opt = ra.config.box_model_opt(H, W, T, use_iou_box=iou_box)
   batch = ra.synthetic.make_batch(opt, B, seed=99)
   weights = ra.synthetic.make_weights(opt, seed=4321, model='box')
   cn = None
@@ -252,15 +254,16 @@ def test_training_mode_forward_batch_stat_bn(cuda):
     assert rel_err(out_eval[k].float().cpu().numpy(), ref_eval[k].numpy()) <= MODEL_TOL, k
 
 
-@pytest.mark.parametrize('step', [0, 9000])
-def test_training_mode_knob(cuda, step):
+@pytest.mark.parametrize('step,arch', [(0, 'kitti'), (9000, 'kitti'), (9000, 'cityscapes')])
+def test_training_mode_knob(cuda, step, arch):
   """Scheduled sampling (full_model.py:589-625,744-785,826-845) with explicit draws against the oracle: greedy GT-box
   match per step, noisy GT box mixed into centre / size, canvas written from the matched GT mask where the mask
   switch is on.  T = 2 keeps the round-off amplification of the training-mode loop small (see the BN test)."""
   import rec_attend_b200 as ra
   from rec_attend_b200.full_model import FullModel
   T, B = 2, 4
-  opt = ra.config.full_model_opt('kitti', 64, 128, T, use_knob=True)
+  opt = ra.config.full_model_opt(arch, 64, 128, T, use_knob=True)
+  assert bool(opt.get('use_iou_box', False)) == (arch == 'cityscapes')  # run_cityscapes.sh passes --use_iou_box
   batch = ra.synthetic.make_batch(opt, B, seed=8)
   weights = ra.synthetic.make_weights(opt, seed=4321)
   draws = ra.synthetic.make_knob_draws(opt, B, global_step=step, seed=2)

@@ -400,6 +400,49 @@ def test_box_gt_step(ops):
   assert rel_err(canvas.cpu().numpy(), torch.maximum(y_sel, torch.from_numpy(canvas0)).numpy()) < TOL
 
 
+def test_greedy_iou_box(ops):
+  """opt['use_iou_box'] (full_model.py:750-754): modellib.f_iou_box + f_greedy_match on the box record, against the
+  oracle's restatement; covers disjoint boxes (all-zero row -> every GT shares 1/T), exact ties and the canvas half."""
+  import rec_attend_b200 as ra
+  rng = np.random.default_rng(21)
+  B, T, H, W = 6, 7, 32, 64
+  stride = 16  # RA_BOX_STRIDE
+  tl_gt = rng.uniform(0, 20, (B, T, 2)).astype(np.float32)
+  br_gt = tl_gt + rng.uniform(2, 30, (B, T, 2)).astype(np.float32)
+  ctr = rng.uniform(8, 28, (B, 2)).astype(np.float32)
+  size = rng.uniform(4, 24, (B, 2)).astype(np.float32)
+  ctr[0] = [500.0, 500.0]  # example 0: no overlap with any GT box
+  tl_gt[1, 3], br_gt[1, 3] = tl_gt[1, 2], br_gt[1, 2]  # example 1: two identical GT boxes (a tie if they win)
+  tl, br = ctr - size / 2.0, ctr + size / 2.0
+  tl_gt[2, 4], br_gt[2, 4] = tl[2], br[2]  # example 2: GT box 4 equals the predicted box (IoU exactly 1)
+  box = np.zeros((B, stride), np.float32)
+  box[:, 0:2], box[:, 2:4], box[:, 9:11], box[:, 11:13] = ctr, size, tl, br
+  rect = np.concatenate([tl_gt, br_gt], 2)
+  iou_t = torch.full((B, 2, T), -1.0, device='cuda')
+  grd = torch.zeros((B, T), device='cuda')
+  ops.greedy_iou_box(_g(box), _g(rect), iou_t[:, 1], 2 * T, grd)
+  ref_iou = OM.f_iou_box(torch.from_numpy(tl).unsqueeze(1), torch.from_numpy(br).unsqueeze(1), torch.from_numpy(tl_gt),
+                         torch.from_numpy(br_gt))
+  ref_grd = OM.f_greedy_match(ref_iou, torch.zeros(B, T))
+  assert np.array_equal(iou_t[:, 1].cpu().numpy(), ref_iou.numpy())  # same fp32 operations in the same order
+  assert (iou_t[:, 0] == -1.0).all()  # the batch stride is honoured
+  assert np.array_equal(grd.cpu().numpy(), ref_grd.numpy())
+  assert np.allclose(grd[0].cpu().numpy(), 1.0 / T) and float(iou_t[2, 1, 4]) == 1.0
+  # canvas half alone (box_model.py:497-503), with and without noise
+  y_gt, _ = _masks(rng, B, T, H, W)
+  noise = (rng.random((B, H, W)) * 0.3).astype(np.float32)
+  canvas0 = (rng.random((B, H, W)) * 0.2).astype(np.float32)
+  for nz in (noise, None):
+    canvas = _g(canvas0.copy())
+    ops.box_gt_canvas(grd, _g(y_gt), None if nz is None else _g(nz), H * W, canvas)
+    y_sel = (ref_grd.view(B, T, 1, 1) * torch.from_numpy(y_gt)).sum(1)
+    if nz is not None:
+      y_sel = y_sel - y_sel * torch.from_numpy(nz)
+    assert rel_err(canvas.cpu().numpy(), torch.maximum(y_sel, torch.from_numpy(canvas0)).numpy()) < TOL
+  with pytest.raises(ra._lib.RecAttendError):
+    ops.greedy_iou_box(_g(box), _g(rect), iou_t[:, 1], T - 1, grd)  # batch stride shorter than a row
+
+
 # ----------------------------------------------------------------------------- tcgen05 conv
 UMMA_CASES = [
     # B, H, W, C1, C2, Cout, up, pool, relu   (the KITTI/Cityscapes-arch layers + odd shapes)

@@ -240,3 +240,50 @@ def test_knob_oracle_semantics():
   with torch.no_grad():
     r_seg = OM.full_model_forward(opt, w, batch, phase_train=True, draws=seg)
   assert float(r_seg['canvas'].max()) == 1.0
+
+
+def test_iou_box_coordinate_form():
+  """modellib.f_iou_box (modellib.py:206-238): strict overlap test, no eps; used by the knob / box-model greedy match
+  when opt['use_iou_box'] (full_model.py:750-754, box_model.py:487-491)."""
+  import rec_attend_b200 as ra
+  tl_a = torch.tensor([[[0.0, 0.0]]])
+  br_a = torch.tensor([[[4.0, 6.0]]])  # 4 x 6 box
+  tl_b = torch.tensor([[[2.0, 3.0], [4.0, 0.0], [0.0, 0.0], [10.0, 10.0]]])
+  br_b = torch.tensor([[[6.0, 9.0], [8.0, 6.0], [4.0, 6.0], [12.0, 12.0]]])
+  iou = OM.f_iou_box(tl_a, br_a, tl_b, br_b)
+  # overlap 2x3 = 6 of 24 + 24 - 6; touching edge (y1 == y2) is NOT an overlap; identical boxes; disjoint
+  assert torch.allclose(iou, torch.tensor([[6.0 / 42.0, 0.0, 1.0, 0.0]]))
+  # the flag switches both model oracles onto it
+  opt = ra.config.full_model_opt('cityscapes', 32, 64, 2, use_knob=True)
+  assert opt['use_iou_box']
+  B = 2
+  batch = ra.synthetic.make_batch(opt, B, seed=3)
+  w = ra.synthetic.make_weights(opt)
+  draws = ra.synthetic.make_knob_draws(opt, B, global_step=0, seed=1)
+  with torch.no_grad():
+    r_box = OM.full_model_forward(opt, w, batch, phase_train=True, draws=draws)
+    r_soft = OM.full_model_forward(dict(opt, use_iou_box=False), w, batch, phase_train=True, draws=draws)
+  tl_gt, br_gt, _ = OM.get_gt_box(torch.from_numpy(batch['y_gt']), padding_ratio=opt['attn_box_padding_ratio'],
+                                  center_shift_ratio=0.0, min_padding=opt['padding'] + 4)
+  # step 0's box is the controller's own in both runs; the per-step IoU rows are the coordinate form in one, soft in the other
+  tl0, br0 = _pre_mix_box(opt, w, batch)
+  want = OM.f_iou_box(tl0.unsqueeze(1), br0.unsqueeze(1), tl_gt, br_gt)
+  assert torch.allclose(r_box['iou_soft_box_pairwise'][:, 0], want, atol=1e-6)
+  assert not torch.allclose(r_box['iou_soft_box_pairwise'][:, 0], r_soft['iou_soft_box_pairwise'][:, 0], atol=1e-4)
+  bopt = ra.config.box_model_opt(32, 64, 2, use_iou_box=True)
+  bb = ra.synthetic.make_batch(bopt, B, seed=3)
+  bw = ra.synthetic.make_weights(bopt, model='box')
+  with torch.no_grad():
+    rb = OM.box_model_forward(bopt, bw, bb)
+  tl_g, br_g, _ = OM.get_gt_box(torch.from_numpy(bb['y_gt']), padding_ratio=bopt['attn_box_padding_ratio'],
+                                center_shift_ratio=0.0)
+  want = OM.f_iou_box(rb['attn_top_left'][:, 0].unsqueeze(1), rb['attn_bot_right'][:, 0].unsqueeze(1), tl_g, br_g)
+  assert torch.allclose(rb['iou_soft_box_pairwise'][:, 0], want, atol=1e-6)
+
+
+def _pre_mix_box(opt, w, batch):
+  """Step-0 box of the controller before the knob mixes a GT box in = the plain training-mode forward's step-0 box."""
+  with torch.no_grad():
+    plain = OM.full_model_forward(dict(opt, use_knob=False), w, batch, phase_train=True)
+  return plain['attn_top_left'][:, 0], plain['attn_bot_right'][:, 0]
+
