@@ -23,9 +23,11 @@ ADAM_EPS = 1e-7  # full_model.py:1046
 ADAM_BETA1, ADAM_BETA2 = 0.9, 0.999  # tf.train.AdamOptimizer defaults
 
 
-def trainable_keys(weights):
-  """Sorted names of the trainable tensors (everything but the BN EMA shadows)."""
-  return sorted(k for k in weights if not k.endswith(('_ema_mean', '_ema_var')))
+def trainable_keys(weights, frozen=()):
+  """Sorted names of the trainable tensors: everything but the BN EMA shadows and the tensors the freeze_* flags of
+  the pretrained hand-off exclude (`checkpoint.apply_pretrained`; tf.Variable(trainable=False), nnlib.py:185,455,527)."""
+  frozen = set(frozen)
+  return sorted(k for k in weights if not k.endswith(('_ema_mean', '_ema_var')) and k not in frozen)
 
 
 def has_weight_decay(key):
@@ -36,8 +38,8 @@ def has_weight_decay(key):
 class FlatParams(object):
   """Layout of the trainable tensors in one flat buffer: key -> (offset, shape)."""
 
-  def __init__(self, weights):
-    self.keys = trainable_keys(weights)
+  def __init__(self, weights, frozen=()):
+    self.keys = trainable_keys(weights, frozen)
     self.layout = {}
     off = 0
     for k in self.keys:
@@ -90,13 +92,13 @@ def all_reduce_sum_(flat):
 class AdamOptimizer(object):
   """The reference's train_step on the flat bucket.  State (params, m, v, wd vector) lives on the GPU."""
 
-  def __init__(self, opt, weights, device=None):
+  def __init__(self, opt, weights, device=None, frozen=()):
     if not torch.cuda.is_available():
       raise _lib.RecAttendError('rec_attend_b200.optim needs a CUDA device (there is no CPU fallback)')
     _lib.lib()
     self.opt = dict(opt)
     self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
-    self.flat = FlatParams(weights)
+    self.flat = FlatParams(weights, frozen)
     self.params = torch.from_numpy(self.flat.flatten(weights)).to(self.device)
     self.m = torch.zeros_like(self.params)
     self.v = torch.zeros_like(self.params)
@@ -119,6 +121,20 @@ class AdamOptimizer(object):
               ops._p(self.wd), self.params.numel(), 1.0 / world, lr, ADAM_BETA1, ADAM_BETA2, ADAM_EPS, self.clip,
               self.global_step, ops._stream())
     return lr
+
+  def state(self):
+    """(m, v, global_step) as host arrays, for `checkpoint.pack_state`."""
+    return self.m.cpu().numpy(), self.v.cpu().numpy(), self.global_step
+
+  def load_state(self, m, v, global_step):
+    """Resume from a checkpoint written with `state()` (same weight schema and frozen set)."""
+    for name, src in (('m', m), ('v', v)):
+      src = np.asarray(src, np.float32).reshape(-1)
+      if src.size != self.params.numel():
+        raise _lib.RecAttendError('Adam slot {} has {} elements, expected {}'.format(name, src.size,
+                                                                                   self.params.numel()))
+      getattr(self, name).copy_(torch.from_numpy(src))
+    self.global_step = int(global_step)
 
   def export_weights(self, weights):
     """The updated trainable tensors merged back into a weight dict (reference key schema)."""

@@ -130,3 +130,33 @@ def test_adam_step_errors(cuda):
   o = optim.AdamOptimizer(opt, w)
   with pytest.raises(_lib.RecAttendError):
     o.step(torch.zeros(3, device='cuda'))
+
+
+@pytest.mark.gpu
+def test_adam_frozen_set_and_resume(cuda):
+  """Pretrained hand-off (checkpoint.apply_pretrained): frozen tensors stay out of the bucket and keep their values;
+  a run resumed from (weights, m, v, step) continues bit-identically to the uninterrupted one."""
+  from rec_attend_b200 import checkpoint as ck, optim
+  opt, w = _weights()
+  _, frozen = ck.apply_pretrained(dict(opt, freeze_ctrl_cnn=True, freeze_ctrl_rnn=True), w)
+  a = optim.AdamOptimizer(opt, w, frozen=frozen)
+  assert a.params.numel() == sum(np.asarray(w[k]).size for k in optim.trainable_keys(w, frozen))
+  rng = np.random.default_rng(1)
+  grads = [torch.from_numpy(rng.standard_normal(a.params.numel()).astype(np.float32)).cuda() for _ in range(4)]
+  for g in grads[:2]:
+    a.step(g.clone())
+  w_mid = a.export_weights(w)
+  for k in frozen:
+    assert np.array_equal(w_mid[k], np.asarray(w[k], np.float32)), k
+  assert not np.array_equal(w_mid['ctrl_cnn_0_0_gamma'], w['ctrl_cnn_0_0_gamma'])  # BN stays trainable (SURVEY §9.4)
+  m, v, step = a.state()
+  st = ck.pack_state(w_mid, m, v, step)
+  w2, m2, v2, step2 = ck.unpack_state(st)
+  b = optim.AdamOptimizer(opt, w2, frozen=frozen)
+  b.load_state(m2, v2, step2)
+  for g in grads[2:]:
+    a.step(g.clone())
+    b.step(g.clone())
+  assert torch.equal(a.params, b.params) and torch.equal(a.v, b.v) and a.global_step == b.global_step == 4
+  with pytest.raises(Exception):
+    b.load_state(m2[:-1], v2, 0)
