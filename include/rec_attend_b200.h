@@ -305,6 +305,30 @@ int ra_concat_channels_f32(const float *a, int Ca, const float *b, int Cb, const
                            float *out, void *stream);
 
 /* --------------------------------------------------------------------------------------
+ * Foreground / orientation FCN head + loss block — fg_model.py:174-236 (the
+ * FCN's conv stack runs on ra_conv3x3_umma_f32 / ra_conv3x3_f32).  logits [npix, nsc+nori] = last
+ * DCNN layer (no BN, no activation, fg_model.py:121,148):
+ *   y_out [npix,nsc] = sigmoid (nsc == 1) or softmax over the nsc semantic channels (:183-188);
+ *   d_out [npix,nori] = softmax over the orientation channels (:176-181; nori may be 0);
+ *   y_hard [npix,nsc] (may be NULL) = y_out > 0.5, or the one-hot of the per-pixel maximum (:201-204).
+ * With y_gt [npix,nsc] (and d_gt [npix,nori] when nori > 0) also out[RA_FG_*]: f_iou_all soft / hard
+ * (modellib.py:171-181; over channels 1.. when nsc > 1), the per-pixel mean of f_bce / f_ce
+ * (modellib.py:418-427), foreground_loss = that mean if loss_is_bce else -iou_soft (:223-226), the
+ * masked orientation cross-entropy and accuracy (:229-239) and loss = foreground_loss + orientation_ce.
+ * ws: device scratch of ra_fg_head_workspace() bytes (needed with y_gt).  y_gt == NULL: inference only.
+ * -------------------------------------------------------------------------------------- */
+#define RA_FG_IOU_SOFT 0
+#define RA_FG_IOU_HARD 1
+#define RA_FG_SEGLOSS 2
+#define RA_FG_FOREGROUND_LOSS 3
+#define RA_FG_ORIENTATION_CE 4
+#define RA_FG_ORIENTATION_ACC 5
+#define RA_FG_LOSS 6
+size_t ra_fg_head_workspace(void);
+int ra_fg_head_f32(const float *logits, size_t npix, int nsc, int nori, const float *y_gt, const float *d_gt,
+                   int loss_is_bce, float *y_out, float *d_out, float *y_hard, float *out, void *ws, void *stream);
+
+/* --------------------------------------------------------------------------------------
  * Instance-label post-processing — utils/postprocess.py as chained by
  * full_model_eval.py:112-125: apply_confidence (postprocess.py:17-31),
  * apply_one_label (:34-55), apply_threshold (:6-14), mask_foreground (:146-155),

@@ -728,3 +728,98 @@ def box_model_forward(opt, weights, batch, canvas_noise=None):
   model['conf_loss'] = f_conf_loss(model['s_out'], match_box)
   model['loss'] = model['box_loss'] + model['conf_loss'] + weight_decay_loss(opt, weights)
   return model
+
+
+# ----------------------------------------------------------------------------- fg_model.py
+def f_iou_all(a, b):
+  """modellib.py:171-181: one IoU over every element, eps on the union only."""
+  inter = (a * b).sum()
+  return inter / (a.sum() + b.sum() - inter + 1e-5)
+
+
+def f_ce(y_out, y_gt):
+  """modellib.py:418-421."""
+  return -y_gt * torch.log(y_out + 1e-5)
+
+
+def f_bce(y_out, y_gt):
+  """modellib.py:424-427."""
+  return -y_gt * torch.log(y_out + 1e-5) - (1 - y_gt) * torch.log(1 - y_out + 1e-5)
+
+
+def fg_skip_lists(opt, x, h_cnn):
+  """fg_model.py:122-146: the CNN-side mask picks activations from [x] + h_cnn[:-1] in order, the DCNN-side mask
+  hands them out from the last one backwards; DCNN layer 0 has no skip."""
+  if not _opt(opt, 'add_skip_conn', False):
+    return None
+  n = len(opt['cnn_depth'])
+  cnn_mask = opt['cnn_skip_mask'] if 'cnn_skip_mask' in opt else opt.get('cnn_skip', [True] * n)
+  dcnn_mask = opt['dcnn_skip_mask'] if 'dcnn_skip_mask' in opt else list(cnn_mask)[::-1]
+  layers = [h for sk, h in zip(cnn_mask, [x] + h_cnn[:-1]) if sk]
+  skip = [None]
+  counter = len(layers) - 1
+  for sk in dcnn_mask:
+    if sk:
+      skip.append(layers[counter])
+      counter -= 1
+    else:
+      skip.append(None)
+  return skip
+
+
+def fg_model_forward(opt, weights, batch):
+  """fg_model.get_model (fg_model.py:11-245) in eval mode (phase_train=False: random_transformation is the identity
+  crop, batch norm uses the EMA shadows): CNN -> DCNN with skip concatenation (last layer: no BN, no activation,
+  :121,148) -> sigmoid / softmax foreground head and softmax orientation head (:174-192) -> IoU / BCE / CE losses
+  (:194-236).  batch: x [B,H,W,3], y_gt [B,H,W,nsc][, d_gt [B,H,W,8]]."""
+  weights = {k: _t(v) for k, v in weights.items()}
+  x, y_gt = _t(batch['x']), _t(batch['y_gt'])
+  nsc = _opt(opt, 'num_semantic_classes', 1)
+  ori = bool(_opt(opt, 'add_orientation', False))
+  nori = opt['num_orientation_classes'] if ori else 0
+  n_c, n_d = len(opt['cnn_depth']), len(opt['dcnn_depth'])
+  if opt['dcnn_depth'][-1] != nsc + nori:
+    raise ValueError('Expecting last channel to be {}'.format(nsc + nori))  # fg_model.py:162-172
+  h_cnn = run_cnn(x, weights, 'cnn', n_c, opt['cnn_pool'], 0)
+  skip = fg_skip_lists(opt, x, h_cnn)
+  h = h_cnn[-1]
+  for ii in range(n_d):  # nnlib.py:339-402 with act = [relu]*(n-1) + [None], use_bn = [True]*(n-1) + [False]
+    inp = h
+    if skip is not None and skip[ii] is not None:
+      inp = torch.cat([inp, skip[ii]], 3)
+    h = conv2d_transpose_same(inp, weights['dcnn_w_%d' % ii], weights['dcnn_b_%d' % ii], opt['dcnn_pool'][ii])
+    if ii < n_d - 1:
+      h = torch.relu(batch_norm_eval(h, _bn(weights, 'dcnn', ii, 0)))
+  model = {'logits': h}
+  y_out = h[..., :nsc]
+  if ori:
+    d_out = torch.softmax(h[..., nsc:], dim=3)
+    model['d_out'] = d_out
+  y_out = torch.sigmoid(y_out) if nsc == 1 else torch.softmax(y_out, dim=3)
+  model['y_out'] = y_out
+  B, H, W = x.shape[0], x.shape[1], x.shape[2]
+  num_pixel = float(B * H * W)
+  y_gt_mask = y_gt[..., 1:nsc].max(dim=3, keepdim=True)[0] if nsc > 1 else y_gt
+  if nsc == 1:
+    y_hard = (y_out > 0.5).float()
+    model['iou_soft'] = f_iou_all(y_out, y_gt)
+    model['iou_hard'] = f_iou_all(y_hard, y_gt)
+    segloss = f_bce(y_out, y_gt).sum() / num_pixel
+  else:
+    y_hard = (y_out == y_out.max(dim=3, keepdim=True)[0]).float()
+    model['iou_soft'] = f_iou_all(y_out[..., 1:], y_gt[..., 1:])
+    model['iou_hard'] = f_iou_all(y_hard[..., 1:], y_gt[..., 1:])
+    segloss = f_ce(y_out, y_gt).sum() / num_pixel
+  model['y_out_hard'] = y_hard
+  fn = _opt(opt, 'segm_loss_fn', 'iou')
+  loss = -model['iou_soft'] if fn == 'iou' else segloss
+  model['foreground_loss'] = loss
+  if ori:
+    d_gt = _t(batch['d_gt'])
+    num_pixel_ori = y_gt_mask.sum()
+    model['orientation_ce'] = (f_ce(d_out, d_gt) * y_gt_mask).sum() / num_pixel_ori
+    loss = loss + model['orientation_ce']
+    correct = (d_out.argmax(dim=3) == d_gt.argmax(dim=3)).float()
+    model['orientation_acc'] = (correct * y_gt_mask[..., 0]).sum() / y_gt_mask.sum()
+  model['loss'] = loss
+  return model

@@ -147,6 +147,88 @@ def box_model_opt(inp_height, inp_width, timespan, **overrides):
   return opt
 
 
+_FG_ARCH = {
+    # fg_model_train.py:425-441 (parser defaults; skip connections only with --add_skip_conn)
+    'default': {
+        'cnn_depth': [8, 8, 16, 16, 32, 32, 64, 64, 128, 128],
+        'cnn_pool': [1, 2, 1, 2, 1, 2, 1, 2, 1, 2],
+        'cnn_skip_mask': [1, 0, 0, 0, 0, 0, 1, 0, 1, 0],
+        'dcnn_depth': [128, 128, 64, 64, 32, 32, 16, 16, 8, 8, 1],
+        'dcnn_pool': [2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 1],
+        'dcnn_skip_mask': [0, 1, 0, 1, 0, 0, 0, 0, 0, 1],
+        'add_skip_conn': False, 'add_orientation': False, 'num_semantic_classes': 1, 'segm_loss_fn': 'iou',
+    },
+    # run_kitti.sh:13-27 (`--cnn_skip` / `--dcnn_skip` are argparse prefixes of --cnn_skip_mask / --dcnn_skip_mask)
+    'kitti': {
+        'cnn_depth': [32, 64, 64, 96, 96, 128, 128, 128, 128, 128, 128, 128, 128, 256, 256, 256, 256, 512],
+        'cnn_pool': [1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1, 2],
+        'cnn_skip_mask': [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 1],
+        'dcnn_depth': [256, 256, 128, 128, 96, 96, 64, 64, 32, 32, 9],
+        'dcnn_pool': [2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 1],
+        'dcnn_skip_mask': [1, 0, 1, 0, 1, 0, 0, 0, 0, 1],
+        'add_skip_conn': True, 'add_orientation': True, 'num_semantic_classes': 1, 'segm_loss_fn': 'bce',
+    },
+    # run_cityscapes.sh:8-30
+    'cityscapes': {
+        'cnn_depth': [64, 96, 96, 128, 128, 192, 192, 256, 256, 256, 256, 256, 256, 256, 256, 512, 512, 512, 512, 512],
+        'cnn_pool': [1, 2, 1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1, 2],
+        'cnn_skip_mask': [1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0],
+        'dcnn_depth': [512, 512, 256, 256, 192, 192, 128, 128, 96, 96, 64, 64, 17],
+        'dcnn_pool': [2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 1],
+        'dcnn_skip_mask': [1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 0],
+        'add_skip_conn': True, 'add_orientation': True, 'num_semantic_classes': 9, 'segm_loss_fn': 'bce',
+    },
+}
+
+
+def fg_model_opt(arch, inp_height, inp_width, **overrides):
+  """opt dict for ``fg_model.get_model`` (fg_model_train.py:470-499), the FCN that produces d_in / y_in."""
+  a = copy.deepcopy(_FG_ARCH[arch])
+  opt = {
+      'inp_height': inp_height, 'inp_width': inp_width, 'inp_depth': 3, 'padding': 16,
+      'cnn_filter_size': [3] * len(a['cnn_depth']), 'dcnn_filter_size': [3] * len(a['dcnn_depth']),
+      'weight_decay': 5e-5, 'use_bn': True, 'rnd_hflip': False, 'rnd_vflip': False, 'rnd_transpose': False,
+      'rnd_colour': False, 'base_learn_rate': 1e-3, 'learn_rate_decay': 0.96, 'steps_per_learn_rate_decay': 5000,
+      'num_orientation_classes': 8, 'optimizer': 'adam', 'arch': 'fg_' + arch,
+  }
+  opt.update(a)
+  opt['cnn_skip_mask'] = [bool(v) for v in opt['cnn_skip_mask']]
+  opt['dcnn_skip_mask'] = [bool(v) for v in opt['dcnn_skip_mask']]
+  opt.update(overrides)
+  return opt
+
+
+def fg_skip_wiring(opt):
+  """fg_model.py:122-146: which activation feeds each DCNN layer as its skip input.  Returns a list, one entry
+  per DCNN layer: None or the index j into [x] + h_cnn[:-1] (j = 0 is the input image, j >= 1 is h_cnn[j-1]),
+  plus the list of skip channel counts.  The CNN-side mask picks layers in order, the DCNN-side mask consumes them
+  from the LAST one backwards; DCNN layer 0 never has a skip."""
+  n_d = len(opt['dcnn_depth'])
+  if not opt.get('add_skip_conn', False):
+    return [None] * n_d, [0] * n_d
+  cnn_channels = [opt['inp_depth']] + list(opt['cnn_depth'])
+  n_all = len(opt['cnn_depth'])  # len([x] + h_cnn[:-1])
+  cnn_mask = opt.get('cnn_skip_mask', opt.get('cnn_skip', [True] * n_all))
+  picked = [j for j, sk in zip(range(n_all), cnn_mask) if sk]
+  dcnn_mask = opt.get('dcnn_skip_mask', list(cnn_mask)[::-1])
+  src, ch = [None], [0]
+  counter = len(picked) - 1
+  for sk in dcnn_mask:
+    if sk:
+      if counter < 0:
+        raise ValueError('dcnn_skip_mask asks for more skips than cnn_skip_mask provides (IndexError in the reference)')
+      src.append(picked[counter])
+      ch.append(cnn_channels[picked[counter]])
+      counter -= 1
+    else:
+      src.append(None)
+      ch.append(0)
+  if len(src) < n_d:
+    raise ValueError('dcnn_skip_mask needs at least one entry per DCNN layer after the first ({} < {}; IndexError in '
+                     'nnlib.run_dcnn)'.format(len(src) - 1, n_d - 1))
+  return src[:n_d], ch[:n_d]  # nnlib.dcnn only reads the first nlayers entries (run_cityscapes.sh passes one extra)
+
+
 # BASELINE.json configs (index = position in BASELINE.json "configs")
 BASELINE_CONFIGS = [
     {'name': 'cvppp_128x128_T8_B1', 'model': 'full', 'arch': 'cvppp', 'H': 128, 'W': 128, 'T': 8, 'B': 1},

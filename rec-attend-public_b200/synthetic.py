@@ -188,3 +188,57 @@ def make_knob_draws(opt, batch_size, global_step=0, seed=99):
       'gt_box_ctr_shift': rng.uniform(-opt['gt_box_ctr_noise'], opt['gt_box_ctr_noise'], (B, T, 2)).astype(np.float32),
       'gt_segm_noise': rng.uniform(0.0, opt['gt_segm_noise'], (B, T, H, W)).astype(np.float32),
   }
+
+
+def make_fg_weights(opt, seed=4321):
+  """Random-init weights of the foreground / orientation FCN (fg_model.py) under the keys its graph registers
+  (nnlib scopes 'cnn' and 'dcnn', one BN copy: ``cnn_w_i``, ``cnn_b_i``, ``cnn_{i}_0_{beta,gamma,ema_mean,ema_var}``,
+  ``dcnn_w_i`` [3,3,Cout,Cin+skip] ...; the last DCNN layer has no BN, fg_model.py:148)."""
+  from .config import fg_skip_wiring
+  rng = np.random.default_rng(seed)
+  w = {}
+  ch = [opt['inp_depth']] + list(opt['cnn_depth'])
+  for i in range(len(ch) - 1):
+    w['cnn_w_%d' % i] = _normal(rng, (3, 3, ch[i], ch[i + 1]), 9 * ch[i]) * np.float32(1.4)
+    w['cnn_b_%d' % i] = (rng.standard_normal(ch[i + 1]) * 0.1).astype(np.float32)
+    _bn(rng, w, 'cnn', i, 0, ch[i + 1])
+  _, skip_ch = fg_skip_wiring(opt)
+  dch = [ch[-1]] + list(opt['dcnn_depth'])
+  n_d = len(dch) - 1
+  for i in range(n_d):
+    cin = dch[i] + skip_ch[i]
+    w['dcnn_w_%d' % i] = _normal(rng, (3, 3, dch[i + 1], cin), 9 * cin / float(opt['dcnn_pool'][i]**2)) * np.float32(1.4)
+    w['dcnn_b_%d' % i] = (rng.standard_normal(dch[i + 1]) * 0.1).astype(np.float32)
+    if i < n_d - 1:
+      _bn(rng, w, 'dcnn', i, 0, dch[i + 1])
+    else:
+      w['dcnn_w_%d' % i] *= np.float32(0.3)  # moderate logits: the heads are not saturated
+  return w
+
+
+def make_fg_batch(opt, batch_size, seed=1234):
+  """x [B,H,W,3]; y_gt [B,H,W,nsc] (one channel: foreground; several: one-hot classes, channel 0 = background);
+  d_gt [B,H,W,8] one-hot orientation inside the foreground when the model has the orientation head."""
+  rng = np.random.default_rng(seed)
+  H, W, B = opt['inp_height'], opt['inp_width'], batch_size
+  nsc = opt.get('num_semantic_classes', 1)
+  x = rng.random((B, H, W, 3), dtype=np.float32)
+  yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+  cls = np.zeros((B, H, W), np.int64)
+  for b in range(B):
+    for _ in range(4):
+      cy, cx = rng.uniform(0, H), rng.uniform(0, W)
+      ay, ax = rng.uniform(H / 8.0, H / 3.0), rng.uniform(W / 8.0, W / 3.0)
+      m = ((yy - cy) / ay)**2 + ((xx - cx) / ax)**2 <= 1.0
+      cls[b][m] = 1 if nsc == 1 else int(rng.integers(1, nsc))
+  if nsc == 1:
+    y_gt = (cls > 0).astype(np.float32)[..., None]
+  else:
+    y_gt = np.eye(nsc, dtype=np.float32)[cls]
+  batch = {'x': x, 'y_gt': y_gt}
+  if opt.get('add_orientation', False):
+    no = opt['num_orientation_classes']
+    ang = np.arctan2(yy - H / 2.0, xx - W / 2.0)
+    k = ((ang + np.pi) / (2 * np.pi) * no).astype(np.int64) % no
+    batch['d_gt'] = (np.eye(no, dtype=np.float32)[k][None] * (cls > 0)[..., None]).astype(np.float32)
+  return batch
