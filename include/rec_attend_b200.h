@@ -281,8 +281,10 @@ int ra_box_gt_canvas_f32(const float *grd, const float *y_gt, const float *noise
  *    and grd = f_greedy_match(iou_t, 0) (modellib.py:366-379), :756-759.
  *  ra_greedy_iou_box_f32: the opt['use_iou_box'] form of the same match (full_model.py:750-754,
  *    box_model.py:487-491): iou_t[b,m] = modellib.f_iou_box (modellib.py:206-238, coordinate IoU, strict overlap
- *    test, no eps) of the box record's top-left / bottom-right against gt_rect [B,T,4] = (tl_y, tl_x, br_y, br_x),
- *    then the greedy match.  A NaN score (0/0 for two zero-area boxes) makes the whole grd row NaN.
+ *    test, no eps) of the box record's top-left / bottom-right against tl_gt, br_gt [B,T,2] = the top_left /
+ *    bot_right OUTPUTS of ra_gt_box_f32 (after the empty-mask fix of modellib.py:697-699; not `rect`, which is the
+ *    rectangle of the filled box), then the greedy match.  A NaN score (0/0 for two zero-area boxes) makes the
+ *    whole grd row NaN.
  *  ra_knob_mix_box_f32: box record (RA_BOX_*) of step t <- knob ? matched noisy GT box : itself, :760-776.
  *  ra_knob_canvas_f32: canvas = max(canvas, knob ? (sum_m grd*y_gt)*(1-noise) : y_out_t), :826-845.
  * knob points at the [B] switches of this step (element b at knob[b*knob_stride]).
@@ -291,8 +293,8 @@ int ra_gt_attn_noise_f32(const float *rect_raw, const float *area, const float *
                          float min_padding, int B, int T, float *ctr, float *size, void *stream);
 int ra_knob_greedy_box_f32(const float *attn_box, size_t box_bstride, const float *gt_rect, int B, int T, int H, int W,
                            float *iou_t, int iou_bstride, float *grd, void *stream);
-int ra_greedy_iou_box_f32(const float *box, const float *gt_rect, int B, int T, float *iou_t, int iou_bstride,
-                          float *grd, void *stream);
+int ra_greedy_iou_box_f32(const float *box, const float *tl_gt, const float *br_gt, int B, int T, float *iou_t,
+                          int iou_bstride, float *grd, void *stream);
 int ra_knob_mix_box_f32(float *box, const float *grd, const float *ctr_gt, const float *size_gt, const float *knob,
                         int knob_stride, int B, int T, void *stream);
 int ra_knob_canvas_f32(const float *grd, const float *y_gt, const float *noise, size_t noise_bstride, const float *knob,

@@ -55,7 +55,7 @@ _SIGNATURES = {
     'ra_random_transformation_f32': [_P, _Z, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'ra_gt_attn_noise_f32': [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P],
     'ra_knob_greedy_box_f32': [_P, _Z, _P, _I, _I, _I, _I, _P, _I, _P, _P],
-    'ra_greedy_iou_box_f32': [_P, _P, _I, _I, _P, _I, _P, _P],
+    'ra_greedy_iou_box_f32': [_P, _P, _P, _I, _I, _P, _I, _P, _P],
     'ra_box_gt_canvas_f32': [_P, _P, _P, _Z, _I, _I, _I, _I, _P, _P],
     'ra_knob_mix_box_f32': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     'ra_knob_canvas_f32': [_P, _P, _P, _Z, _P, _I, _P, _Z, _I, _I, _I, _I, _P, _P],

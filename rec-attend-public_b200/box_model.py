@@ -61,7 +61,7 @@ class BoxModel(_ModelBase):
       _lib.TAG = 'box_gt'
       noise_t = None if noise is None else noise[:, t]
       if o.get('use_iou_box', False):  # box_model.py:487-491: coordinate IoU instead of the soft box IoU
-        ops.greedy_iou_box(bufs['box_all'][t], rect, bufs['iou_box'][:, t], T * T, bufs['grd'])
+        ops.greedy_iou_box(bufs['box_all'][t], tl, br, bufs['iou_box'][:, t], T * T, bufs['grd'])
         ops.box_gt_canvas(bufs['grd'], y_gt, noise_t, thw, bufs['canvas'])
       else:
         ops.box_gt_step(bufs['attn_box'][:, t], thw, rect, y_gt, noise_t, thw, bufs['iou_box'][:, t], T * T,

@@ -493,15 +493,18 @@ int box_gt_iou_launch(const float *attn_box, size_t box_bstride, const float *gt
 // use_iou_box (full_model.py:750-754, box_model.py:487-491): the knob / box-model greedy match on the coordinate IoU
 // of modellib.f_iou_box (modellib.py:206-238; no eps, strict overlap test) between this step's box and every (clean)
 // GT box, instead of the soft IoU of the pasted attention box.  One CTA per example, thread m = GT box m.
-__global__ void greedy_iou_box_kernel(const float *__restrict__ box, const float *__restrict__ gt_rect, int T,
-                                      float *__restrict__ iou_t, int iou_bstride, float *__restrict__ grd) {
+__global__ void greedy_iou_box_kernel(const float *__restrict__ box, const float *__restrict__ tl_gt,
+                                      const float *__restrict__ br_gt, int T, float *__restrict__ iou_t,
+                                      int iou_bstride, float *__restrict__ grd) {
   __shared__ float iou_s[64];
   const int b = blockIdx.x, m = threadIdx.x;
   const float *bo = box + (size_t)b * RA_BOX_STRIDE;
   if (m < T) {
     const float y1a = bo[RA_BOX_TL_Y], x1a = bo[RA_BOX_TL_X], y2a = bo[RA_BOX_BR_Y], x2a = bo[RA_BOX_BR_X];
-    const float *rc = gt_rect + ((size_t)b * T + m) * 4;
-    const float y1b = rc[0], x1b = rc[1], y2b = rc[2], x2b = rc[3];
+    // the GT corners are get_gt_box's RETURNED top_left / bot_right, i.e. after the empty-mask fix (an empty mask
+    // gives the box (0,0)-(2*min_padding), modellib.py:697-699) - not the rectangle of the filled box
+    const float *tg = tl_gt + ((size_t)b * T + m) * 2, *bg = br_gt + ((size_t)b * T + m) * 2;
+    const float y1b = tg[0], x1b = tg[1], y2b = bg[0], x2b = bg[1];
     const float x1 = fmaxf(x1a, x1b), y1 = fmaxf(y1a, y1b), x2 = fminf(x2a, x2b), y2 = fminf(y2a, y2b);
     const float flag = ((x1 < x2) ? 1.f : 0.f) * ((y1 < y2) ? 1.f : 0.f);
     const float inter = __fmul_rn(__fmul_rn(flag, x2 - x1), y2 - y1);
@@ -780,12 +783,12 @@ extern "C" int ra_knob_greedy_box_f32(const float *attn_box, size_t box_bstride,
                            ra::as_stream(stream));
 }
 
-extern "C" int ra_greedy_iou_box_f32(const float *box, const float *gt_rect, int B, int T, float *iou_t, int iou_bstride,
-                                     float *grd, void *stream) {
+extern "C" int ra_greedy_iou_box_f32(const float *box, const float *tl_gt, const float *br_gt, int B, int T, float *iou_t,
+                                     int iou_bstride, float *grd, void *stream) {
   if (B < 0 || T < 1 || T > 64 || iou_bstride < T) return RA_ERR_INVALID_ARG;
   if (B == 0) return RA_OK;
-  if (!box || !gt_rect || !iou_t || !grd) return RA_ERR_INVALID_ARG;
-  greedy_iou_box_kernel<<<B, 64, 0, ra::as_stream(stream)>>>(box, gt_rect, T, iou_t, iou_bstride, grd);
+  if (!box || !tl_gt || !br_gt || !iou_t || !grd) return RA_ERR_INVALID_ARG;
+  greedy_iou_box_kernel<<<B, 64, 0, ra::as_stream(stream)>>>(box, tl_gt, br_gt, T, iou_t, iou_bstride, grd);
   return ra::finish_launch("greedy_iou_box_kernel");
 }
 

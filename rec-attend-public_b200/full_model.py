@@ -440,13 +440,13 @@ class FullModel(_ModelBase):
     o = self.opt
     dev = lambda a: a if isinstance(a, torch.Tensor) and a.is_cuda else self._dev(np.asarray(a, np.float32))
     B, T = y_gt.shape[0], self.T
-    _, _, _, rect_clean, area = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'],
-                                               min_padding=self.min_padding, want_box=False)
+    tl_clean, br_clean, _, rect_clean, area = ops.get_gt_box(y_gt, padding_ratio=o['attn_box_padding_ratio'],
+                                                             min_padding=self.min_padding, want_box=False)
     _, _, _, rect_raw, _ = ops.get_gt_box(y_gt, padding_ratio=0.0, min_padding=0.0, want_box=False)
     ctr_n, size_n = ops.gt_attn_noise(rect_raw, area, dev(draws['gt_box_pad']).reshape(B, T).contiguous(),
                                       dev(draws['gt_box_ctr_shift']).contiguous(), self.min_padding)
     return {
-        'rect': rect_clean, 'ctr': ctr_n, 'size': size_n, 'y_gt': y_gt,
+        'rect': rect_clean, 'tl': tl_clean, 'br': br_clean, 'ctr': ctr_n, 'size': size_n, 'y_gt': y_gt,
         'knob_box': dev(draws['gt_knob_box']).contiguous(), 'knob_segm': dev(draws['gt_knob_segm']).contiguous(),
         'noise': dev(draws['gt_segm_noise']).contiguous(),
         'iou_steps': torch.empty((B, T, T), device=self.device, dtype=torch.float32),
@@ -470,7 +470,7 @@ class FullModel(_ModelBase):
         ops.paste_back(None, box_t, bufs['fy'], bufs['fx'], None, attn_box=bufs['attn_box'][:, t], y_out=None,
                        out_bstride=thw, band=bufs['band'])
         if self.opt.get('use_iou_box', False):  # coordinate IoU of the (pre-mix) box, full_model.py:750-754
-          ops.greedy_iou_box(box_t, knob['rect'], knob['iou_steps'][:, t], T * T, knob['grd'])
+          ops.greedy_iou_box(box_t, knob['tl'], knob['br'], knob['iou_steps'][:, t], T * T, knob['grd'])
         else:
           ops.knob_greedy_box(bufs['attn_box'][:, t], thw, knob['rect'], H, W, knob['iou_steps'][:, t], T * T,
                               knob['grd'])

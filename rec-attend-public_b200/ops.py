@@ -382,11 +382,13 @@ def knob_greedy_box(attn_box_t, box_bstride, gt_rect, H, W, iou_t, iou_bstride, 
             _p(grd), _stream())
 
 
-def greedy_iou_box(box_t, gt_rect, iou_t, iou_bstride, grd):
+def greedy_iou_box(box_t, tl_gt, br_gt, iou_t, iou_bstride, grd):
   """opt['use_iou_box'] (full_model.py:750-754, box_model.py:487-491): modellib.f_iou_box of this step's box record
-  against every GT box (gt_rect [B,T,4]) + f_greedy_match."""
+  against every GT box (tl_gt, br_gt [B,T,2] = get_gt_box's returned corners) + f_greedy_match."""
+  _chk(box_t, tl_gt, br_gt, grd)
   B, T = grd.shape
-  _lib.call('ra_greedy_iou_box_f32', _p(box_t), _p(gt_rect), B, T, _p(iou_t), iou_bstride, _p(grd), _stream())
+  _lib.call('ra_greedy_iou_box_f32', _p(box_t), _p(tl_gt), _p(br_gt), B, T, _p(iou_t), iou_bstride, _p(grd),
+            _stream())
 
 
 def box_gt_canvas(grd, y_gt, noise_t, noise_bstride, canvas):

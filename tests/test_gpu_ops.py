@@ -417,10 +417,9 @@ def test_greedy_iou_box(ops):
   tl_gt[2, 4], br_gt[2, 4] = tl[2], br[2]  # example 2: GT box 4 equals the predicted box (IoU exactly 1)
   box = np.zeros((B, stride), np.float32)
   box[:, 0:2], box[:, 2:4], box[:, 9:11], box[:, 11:13] = ctr, size, tl, br
-  rect = np.concatenate([tl_gt, br_gt], 2)
   iou_t = torch.full((B, 2, T), -1.0, device='cuda')
   grd = torch.zeros((B, T), device='cuda')
-  ops.greedy_iou_box(_g(box), _g(rect), iou_t[:, 1], 2 * T, grd)
+  ops.greedy_iou_box(_g(box), _g(tl_gt), _g(br_gt), iou_t[:, 1], 2 * T, grd)
   ref_iou = OM.f_iou_box(torch.from_numpy(tl).unsqueeze(1), torch.from_numpy(br).unsqueeze(1), torch.from_numpy(tl_gt),
                          torch.from_numpy(br_gt))
   ref_grd = OM.f_greedy_match(ref_iou, torch.zeros(B, T))
@@ -440,7 +439,7 @@ def test_greedy_iou_box(ops):
       y_sel = y_sel - y_sel * torch.from_numpy(nz)
     assert rel_err(canvas.cpu().numpy(), torch.maximum(y_sel, torch.from_numpy(canvas0)).numpy()) < TOL
   with pytest.raises(ra._lib.RecAttendError):
-    ops.greedy_iou_box(_g(box), _g(rect), iou_t[:, 1], T - 1, grd)  # batch stride shorter than a row
+    ops.greedy_iou_box(_g(box), _g(tl_gt), _g(br_gt), iou_t[:, 1], T - 1, grd)  # batch stride shorter than a row
 
 
 # ----------------------------------------------------------------------------- tcgen05 conv
