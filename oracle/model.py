@@ -253,7 +253,7 @@ def segm_match_weights(iou, s_gt):
 def f_segm_match(iou, s_gt):
   """modellib.py:382-415."""
   w = segm_match_weights(iou, s_gt)
-  m = torch.from_numpy(_hung.hungarian(w.numpy())[0])
+  m = torch.from_numpy(_hung.hungarian(w.detach().numpy())[0])  # ops.NoGradient("Hungarian"), modellib.py:11
   return m * s_gt.unsqueeze(1) * s_gt.unsqueeze(2)
 
 
@@ -363,6 +363,8 @@ def _opt(opt, key, default):
 
 
 def _t(a):
+  if isinstance(a, torch.Tensor):  # tensors pass through (oracle/grads.py hands in leaves that require grad)
+    return a if a.dtype == torch.float32 else a.to(torch.float32)
   return torch.as_tensor(np.asarray(a), dtype=torch.float32)
 
 
@@ -569,6 +571,8 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False, d
       ks = knob_segm[:, tt].view(B, 1, 1, 1)
       y_canvas = ks * y_gtm + (1.0 - ks) * y_canvas
     canvas = torch.maximum(y_canvas, canvas)  # full_model.py:843-845
+    if _opt(opt, 'stop_canvas_grad', True):
+      canvas = canvas.detach()  # tf.stop_gradient, full_model.py:846-848
 
     out['y_out'].append(y)
     out['s_out'].append(s)

@@ -192,17 +192,7 @@ def test_sub_batch_chains_agree(cuda, use_graph):
     assert (o['match'] == outs[0]['match']).all() and (o['match_box'] == outs[0]['match_box']).all()
 
 
-def _oracle_fp64():
-  """The model oracle re-typed to float64 (source rewrite: it hard-codes float32 in a few places).  Used as the
-  "truth" where fp32 implementations cannot agree with each other to 1e-3 because the computation itself amplifies
-  round-off (training-mode forward below)."""
-  import types
-  src = open(OM.__file__).read()
-  src = src.replace('torch.float32', 'torch.float64').replace('.float()', '.double()')
-  src = src.replace('from . import hungarian as _hung', 'from oracle import hungarian as _hung')
-  mod = types.ModuleType('oracle_model_fp64')
-  exec(compile(src, 'oracle_model_fp64', 'exec'), mod.__dict__)
-  return mod
+from conftest import oracle_fp64 as _oracle_fp64  # noqa: E402
 
 
 def test_training_mode_forward_batch_stat_bn(cuda):
