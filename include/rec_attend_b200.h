@@ -307,6 +307,34 @@ int ra_concat_channels_f32(const float *a, int Ca, const float *b, int Cb, const
                            float *out, void *stream);
 
 /* --------------------------------------------------------------------------------------
+ * Backward of one training-mode conv block  y = pool(relu(bn_batch(conv3x3(x [,x2]) + b)))  — the
+ * gradients TensorFlow's autodiff derives for nnlib.py:229-253 / :372-400 with phase_train = True
+ * (optimizer.compute_gradients, full_model.py:1049).  First building block of the backward pass; fp32
+ * CUDA-core kernels (csrc/conv_bwd.cu).
+ *  ra_bn_train_block_bwd_f32: raw [B,H,W,C] (conv output incl. bias, kept from the forward), the batch
+ *    statistics mean / var [C] (ra_bn_train_block_f32's batch_mean / batch_var), dy [B,H/pool,W/pool,C]
+ *    -> d_raw [B,H,W,C], dgamma [C], dbeta [C]; max-pool routes to the first maximum of the window, relu'(0) = 0,
+ *    the batch moments are differentiated (tf.nn.moments).  ws: ra_bn_train_block_bwd_workspace() bytes.
+ *  ra_conv3x3_bwd_weight_f32: dw [3,3,C1+C2,Cout] = gradient of the CONV-FORM filter ra_conv3x3_f32 consumes
+ *    (for upsample = 2 the input is zero-inserted, Z[2y,2x] = x[y,x], and a tap reads Z[Y+ky-2, X+kx-2] — the
+ *    forward kernel's convention, which makes it TensorFlow's SAME conv2d_transpose), db [Cout] (may be NULL) = column sums of
+ *    d_out [B,Hin*up,Win*up,Cout].  ws: ra_conv3x3_bwd_weight_workspace() bytes.
+ *  ra_filter_flip_transpose_f32: out[ky,kx,co,ci] = w[2-ky,2-kx,ci,co].  The data gradient of the block is
+ *    ra_conv3x3_f32(d_out, flip_transpose(w)) (then ra_subsample2_f32 with off = 1 for upsample = 2); the same map converts
+ *    between the conv-form filter of a transposed-conv layer and TensorFlow's [kh,kw,Cout,Cin] layout.
+ *  ra_subsample2_f32: dst [B,H,W,C] = src [B,2H,2W,C] at positions (2y+off, 2x+off), off in {0,1}.
+ * -------------------------------------------------------------------------------------- */
+size_t ra_bn_train_block_bwd_workspace(int B, int H, int W, int C, int pool);
+int ra_bn_train_block_bwd_f32(const float *raw, const float *dy, const float *gamma, const float *beta,
+                              const float *mean, const float *var, int B, int H, int W, int C, int pool, int relu,
+                              float eps, void *ws, float *d_raw, float *dgamma, float *dbeta, void *stream);
+size_t ra_conv3x3_bwd_weight_workspace(int B, int Hin, int Win, int Cin, int Cout, int upsample);
+int ra_conv3x3_bwd_weight_f32(const float *x1, int C1, const float *x2, int C2, const float *d_out, int B, int Hin,
+                              int Win, int Cout, int upsample, void *ws, float *dw, float *db, void *stream);
+int ra_filter_flip_transpose_f32(const float *w, int Ci, int Co, float *out, void *stream);
+int ra_subsample2_f32(const float *src, int B, int H, int W, int C, int off, float *dst, void *stream);
+
+/* --------------------------------------------------------------------------------------
  * Foreground / orientation FCN head + loss block — fg_model.py:174-236 (the
  * FCN's conv stack runs on ra_conv3x3_umma_f32 / ra_conv3x3_f32).  logits [npix, nsc+nori] = last
  * DCNN layer (no BN, no activation, fg_model.py:121,148):

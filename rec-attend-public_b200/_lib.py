@@ -59,13 +59,18 @@ _SIGNATURES = {
     'ra_box_gt_canvas_f32': [_P, _P, _P, _Z, _I, _I, _I, _I, _P, _P],
     'ra_knob_mix_box_f32': [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     'ra_knob_canvas_f32': [_P, _P, _P, _Z, _P, _I, _P, _Z, _I, _I, _I, _I, _P, _P],
+    'ra_bn_train_block_bwd_f32': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
+    'ra_conv3x3_bwd_weight_f32': [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    'ra_filter_flip_transpose_f32': [_P, _I, _I, _P, _P],
+    'ra_subsample2_f32': [_P, _I, _I, _I, _I, _I, _P, _P],
     'ra_fg_head_f32': [_P, _Z, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     'ra_adam_step_f32': [_P, _P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _P],
     'ra_postprocess_f32': [_P, _P, _P, _I, _I, _I, _I, ctypes.c_double, _F, _P, _P, _P, _P, _P, _P],
 }
 EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last_error', 'ra_launch_count',
                                          'ra_pairwise_iou_workspace', 'ra_postprocess_workspace',
-                                         'ra_bn_train_workspace', 'ra_fg_head_workspace'])
+                                         'ra_bn_train_workspace', 'ra_fg_head_workspace',
+                                         'ra_bn_train_block_bwd_workspace', 'ra_conv3x3_bwd_weight_workspace'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -99,6 +104,10 @@ def lib():
     l.ra_bn_train_workspace.restype = _Z
     l.ra_fg_head_workspace.argtypes = []
     l.ra_fg_head_workspace.restype = _Z
+    l.ra_bn_train_block_bwd_workspace.argtypes = [_I, _I, _I, _I, _I]
+    l.ra_bn_train_block_bwd_workspace.restype = _Z
+    l.ra_conv3x3_bwd_weight_workspace.argtypes = [_I, _I, _I, _I, _I, _I]
+    l.ra_conv3x3_bwd_weight_workspace.restype = _Z
     _lib = l
   return _lib
 

@@ -362,6 +362,86 @@ def random_transformation(x, padding, offset, vflip=False, hflip=False, transpos
   return out
 
 
+# ----------------------------------------------------------------------------- backward of a training-mode conv block
+def _ws(nbytes, device):
+  return torch.empty(max(int(nbytes), 8), device=device, dtype=torch.uint8)
+
+
+def batch_norm_train_block_bwd(raw, dy, gamma, beta, mean, var, pool=1, relu=True, eps=1e-3):
+  """Gradient of y = pool(relu(bn_batch(raw))) (ops.batch_norm_train_block): raw [B,H,W,C] = the conv output incl.
+  bias, mean / var [C] = the batch statistics the forward returned, dy [B,H/pool,W/pool,C].
+  Returns (d_raw [B,H,W,C], dgamma [C], dbeta [C])."""
+  _chk(raw, dy, gamma, beta, mean, var)
+  B, H, W, C = raw.shape
+  assert tuple(dy.shape) == (B, H // pool, W // pool, C), (tuple(dy.shape), tuple(raw.shape), pool)
+  dev = raw.device
+  d_raw = torch.empty_like(raw)
+  dgamma = torch.empty(C, device=dev, dtype=torch.float32)
+  dbeta = torch.empty(C, device=dev, dtype=torch.float32)
+  ws = _ws(_lib.lib().ra_bn_train_block_bwd_workspace(B, H, W, C, pool), dev)
+  _lib.call('ra_bn_train_block_bwd_f32', _p(raw), _p(dy), _p(gamma), _p(beta), _p(mean), _p(var), B, H, W, C, pool,
+            1 if relu else 0, float(eps), _p(ws), _p(d_raw), _p(dgamma), _p(dbeta), _stream())
+  return d_raw, dgamma, dbeta
+
+
+def conv3x3_bwd_weight(x, d_out, x2=None, upsample=1, want_db=True):
+  """Gradient of the conv-form filter w [3,3,C1+C2,Cout] of conv3x3_block(x [,x2], w, upsample=...) and of the bias,
+  given d_out [B,H*up,W*up,Cout] = gradient of the raw convolution output.  Returns (dw, db or None)."""
+  _chk(x, d_out, x2)
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  Cout = d_out.shape[3]
+  assert tuple(d_out.shape) == (B, H * upsample, W * upsample, Cout)
+  dev = x.device
+  dw = torch.empty((3, 3, C1 + C2, Cout), device=dev, dtype=torch.float32)
+  db = torch.empty(Cout, device=dev, dtype=torch.float32) if want_db else None
+  ws = _ws(_lib.lib().ra_conv3x3_bwd_weight_workspace(B, H, W, C1 + C2, Cout, upsample), dev)
+  _lib.call('ra_conv3x3_bwd_weight_f32', _p(x), C1, _p(x2), C2, _p(d_out), B, H, W, Cout, upsample, _p(ws), _p(dw),
+            _p(db), _stream())
+  return dw, db
+
+
+def filter_flip_transpose(w):
+  """out[ky,kx,co,ci] = w[2-ky,2-kx,ci,co] on the device (w [3,3,Ci,Co])."""
+  _chk(w)
+  _, _, Ci, Co = w.shape
+  out = torch.empty((3, 3, Co, Ci), device=w.device, dtype=torch.float32)
+  _lib.call('ra_filter_flip_transpose_f32', _p(w), Ci, Co, _p(out), _stream())
+  return out
+
+
+def conv3x3_bwd_data(d_out, w, upsample=1):
+  """Gradient of the input of conv3x3_block(x, w, upsample=...) (x = concat of x1, x2 along channels) given d_out:
+  a SAME convolution of d_out with the flipped, transposed filter; for the transposed-conv layer (upsample = 2) the
+  input gradient is that result at the odd positions.  w [3,3,Cin,Cout] conv-form -> dx [B,H,W,Cin]."""
+  _chk(d_out, w)
+  Cin = w.shape[2]
+  wb = filter_flip_transpose(w)
+  one = torch.ones(Cin, device=w.device, dtype=torch.float32)
+  zero = torch.zeros(Cin, device=w.device, dtype=torch.float32)
+  full = conv3x3_block(d_out, wb, one, zero, pool=1, relu=False)
+  if upsample == 1:
+    return full
+  B, H2, W2, _ = full.shape
+  dx = torch.empty((B, H2 // 2, W2 // 2, Cin), device=w.device, dtype=torch.float32)
+  _lib.call('ra_subsample2_f32', _p(full), B, H2 // 2, W2 // 2, Cin, 1, _p(dx), _stream())
+  return dx
+
+
+def conv3x3_block_train_bwd(x, w, raw, dy, gamma, beta, mean, var, pool=1, relu=True, x2=None, upsample=1, eps=1e-3,
+                            want_dx=True):
+  """Backward of one training-mode layer of nn.cnn / nn.dcnn (forward: raw = conv3x3_block(x [,x2], w, 1, bias,
+  relu=False, upsample=...); y = batch_norm_train_block(raw, ...)).  Returns a dict: dx (channels of x then x2),
+  dw (conv-form), db, dgamma, dbeta.  db is exactly the column sum of d_raw - analytically zero behind a
+  batch-statistics BN (the mean removes the bias), kept because TensorFlow computes it too."""
+  d_raw, dgamma, dbeta = batch_norm_train_block_bwd(raw, dy, gamma, beta, mean, var, pool=pool, relu=relu, eps=eps)
+  dw, db = conv3x3_bwd_weight(x, d_raw, x2=x2, upsample=upsample)
+  out = {'dw': dw, 'db': db, 'dgamma': dgamma, 'dbeta': dbeta, 'd_raw': d_raw}
+  if want_dx:
+    out['dx'] = conv3x3_bwd_data(d_raw, w, upsample=upsample)
+  return out
+
+
 # ----------------------------------------------------------------------------- scheduled sampling (training mode)
 def gt_attn_noise(rect_raw, area, pad, shift, min_padding):
   """Noisy GT attention boxes (full_model.py:568-580): rect_raw [B,T,4] raw mask extrema, area [B,T], pad [B,T(,1)],

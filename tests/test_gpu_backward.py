@@ -1,0 +1,105 @@
+"""GPU parity tests of the backward building blocks (csrc/conv_bwd.cu): the gradients of one training-mode conv block
+y = pool(relu(bn_batch(conv3x3(x [,x2]) + b))) against torch.autograd through the ORACLE's forward functions
+(oracle.model.conv2d_same / conv2d_transpose_same / batch_norm_train / max_pool_same) - i.e. what TensorFlow's autodiff
+derives for nnlib.py:229-253 / :372-400.  fp32 CUDA-core kernels: tolerance 1e-4 of the gradient's scale."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import model as OM
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-4
+
+
+def _g(a):
+  return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def _block_oracle(x, w_tf, b, gamma, beta, up, pool, relu):
+  """Forward of the block with autograd on; returns (y, raw, batch mean, batch var)."""
+  raw = OM.conv2d_same(x, w_tf, b) if up == 1 else OM.conv2d_transpose_same(x, w_tf, b, up)
+  p = {'gamma': gamma, 'beta': beta, 'ema_mean': torch.zeros_like(gamma), 'ema_var': torch.ones_like(gamma)}
+  y, mean, var, _, _ = OM.batch_norm_train(raw, p)
+  if relu:
+    y = torch.relu(y)
+  if pool == 2:
+    y = OM.max_pool_same(y, 2)
+  return y, raw, mean, var
+
+
+BWD_CASES = [
+    # B, H, W, C1, C2, Cout, up, pool, relu
+    (2, 16, 24, 13, 0, 16, 1, 2, 1),    # first attention-CNN layer shape (odd Cin)
+    (3, 12, 12, 64, 0, 96, 1, 2, 1),    # attn L5
+    (2, 6, 6, 96, 0, 64, 2, 1, 1),      # dcnn L0: transposed conv, stride 2
+    (2, 12, 12, 64, 64, 64, 1, 1, 1),   # dcnn L1: skip concat (two input pointers), 128 input channels
+    (2, 24, 24, 32, 32, 16, 2, 1, 1),   # dcnn L4: transposed conv + skip
+    (2, 48, 48, 16, 13, 1, 1, 1, 1),    # dcnn L6: one output channel
+    (4, 32, 64, 16, 0, 16, 1, 2, 1),    # controller L1 shape (reduced size)
+    (1, 10, 14, 140, 0, 100, 1, 1, 0),  # more than one channel block (Cin > 128, Cout > 96), no ReLU
+]
+
+
+@pytest.mark.parametrize('case', BWD_CASES)
+def test_conv_block_train_backward(cuda, case):
+  from rec_attend_b200 import ops
+  from rec_attend_b200.full_model import _deconv_to_conv
+  B, H, W, C1, C2, Cout, up, pool, relu = case
+  Cin = C1 + C2
+  rng = np.random.default_rng(abs(hash(case)) % 2**31)
+  x_np = rng.standard_normal((B, H, W, Cin)).astype(np.float32)
+  shape_tf = (3, 3, Cin, Cout) if up == 1 else (3, 3, Cout, Cin)
+  w_np = (rng.standard_normal(shape_tf) / np.sqrt(9 * Cin)).astype(np.float32)
+  b_np = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+  g_np = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+  be_np = (rng.standard_normal(Cout) * 0.5).astype(np.float32)
+  x, w, b, gamma, beta = [torch.from_numpy(a).requires_grad_(True) for a in (x_np, w_np, b_np, g_np, be_np)]
+  y, raw, mean, var = _block_oracle(x, w, b, gamma, beta, up, pool, bool(relu))
+  dy_np = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+  gx, gw, gb, gg, gbe = torch.autograd.grad(y, [x, w, b, gamma, beta], torch.from_numpy(dy_np))
+  w_conv = w_np if up == 1 else _deconv_to_conv(w_np)
+  gw_conv = gw.numpy() if up == 1 else _deconv_to_conv(gw.numpy())  # the same linear map carries the gradient
+
+  x1 = _g(x_np[..., :C1])
+  x2 = _g(x_np[..., C1:]) if C2 else None
+  out = ops.conv3x3_block_train_bwd(x1, _g(w_conv), _g(raw.detach().numpy()), _g(dy_np), _g(g_np), _g(be_np),
+                                    _g(mean.detach().numpy()), _g(var.detach().numpy()), pool=pool, relu=bool(relu),
+                                    x2=x2, upsample=up)
+  torch.cuda.synchronize()
+  assert rel_err(out['dgamma'].cpu().numpy(), gg.numpy()) < TOL
+  assert rel_err(out['dbeta'].cpu().numpy(), gbe.numpy()) < TOL
+  assert tuple(out['dw'].shape) == (3, 3, Cin, Cout)
+  assert rel_err(out['dw'].cpu().numpy(), gw_conv) < TOL
+  assert rel_err(out['dx'].cpu().numpy(), gx.numpy()) < TOL
+  # the bias sits in front of a batch-statistics BN: its gradient is zero up to round-off, in both implementations
+  scale = float(np.abs(out['d_raw'].cpu().numpy()).sum(axis=(0, 1, 2)).max())
+  assert float(out['db'].abs().max()) <= 1e-4 * max(scale, 1.0) and float(gb.abs().max()) <= 1e-4 * max(scale, 1.0)
+
+
+def test_bwd_weight_bias_and_filter_maps(cuda):
+  """Without a BN behind it (the raw-gradient path): db = column sums; flip_transpose / subsample index maps."""
+  from rec_attend_b200 import _lib, ops
+  rng = np.random.default_rng(5)
+  B, H, W, Cin, Cout = 2, 9, 11, 6, 5  # odd sizes: the kernels are per pixel
+  x = rng.standard_normal((B, H, W, Cin)).astype(np.float32)
+  g = rng.standard_normal((B, H, W, Cout)).astype(np.float32)
+  xt, wt = torch.from_numpy(x).requires_grad_(True), torch.randn(3, 3, Cin, Cout, requires_grad=True)
+  bt = torch.zeros(Cout, requires_grad=True)
+  y = OM.conv2d_same(xt, wt, bt)
+  gx, gw, gb = torch.autograd.grad(y, [xt, wt, bt], torch.from_numpy(g))
+  dw, db = ops.conv3x3_bwd_weight(_g(x), _g(g))
+  assert rel_err(dw.cpu().numpy(), gw.numpy()) < TOL and rel_err(db.cpu().numpy(), gb.numpy()) < TOL
+  dx = ops.conv3x3_bwd_data(_g(g), _g(wt.detach().numpy()))
+  assert rel_err(dx.cpu().numpy(), gx.numpy()) < TOL
+  dw2, none = ops.conv3x3_bwd_weight(_g(x), _g(g), want_db=False)
+  assert none is None and torch.equal(dw2, dw)  # fixed summation order: bit-identical from run to run
+  w = rng.standard_normal((3, 3, Cin, Cout)).astype(np.float32)
+  ft = ops.filter_flip_transpose(_g(w)).cpu().numpy()
+  assert np.array_equal(ft, np.ascontiguousarray(w[::-1, ::-1].transpose(0, 1, 3, 2)))
+  with pytest.raises(_lib.RecAttendError):
+    ops.batch_norm_train_block_bwd(_g(g), _g(g[:, :4, :5]), *[_g(np.ones(Cout)) for _ in range(4)], pool=2)  # odd H, W
+  empty = ops.conv3x3_bwd_weight(torch.zeros((0, 4, 4, 3), device='cuda'), torch.zeros((0, 4, 4, 2), device='cuda'))
+  assert tuple(empty[0].shape) == (3, 3, 3, 2)
