@@ -315,12 +315,16 @@ extern "C" size_t ra_conv3x3_bwd_weight_workspace(int B, int Hin, int Win, int C
 extern "C" int ra_conv3x3_bwd_weight_f32(const float *x1, int C1, const float *x2, int C2, const float *d_out, int B,
                                          int Hin, int Win, int Cout, int upsample, void *ws, float *dw, float *db,
                                          void *stream) {
-  if (!x1 || C1 < 1 || C2 < 0 || (C2 > 0 && !x2) || B < 0 || Hin < 1 || Win < 1 || Cout < 1) return RA_ERR_INVALID_ARG;
+  if (C1 < 1 || C2 < 0 || B < 0 || Hin < 1 || Win < 1 || Cout < 1 || !dw) return RA_ERR_INVALID_ARG;
   if (upsample != 1 && upsample != 2) return RA_ERR_UNSUPPORTED;
-  if (B == 0) return RA_OK;
-  if (!d_out || !ws || !dw) return RA_ERR_INVALID_ARG;
   cudaStream_t s = ra::as_stream(stream);
   const int Cin = C1 + C2;
+  if (B == 0) {  // an empty batch contributes nothing: zero gradients (empty tensors may carry null pointers)
+    cudaMemsetAsync(dw, 0, (size_t)9 * Cin * Cout * sizeof(float), s);
+    if (db) cudaMemsetAsync(db, 0, (size_t)Cout * sizeof(float), s);
+    return ra::finish_launch("cudaMemsetAsync(dw)");
+  }
+  if (!x1 || (C2 > 0 && !x2) || !d_out || !ws) return RA_ERR_INVALID_ARG;
   const size_t npix = (size_t)B * Hin * upsample * Win * upsample;
   const int chunks = wg_chunks(npix);
   const int n_ci_blk = (Cin + kWgCi - 1) / kWgCi, n_co_blk = (Cout + kWgCo - 1) / kWgCo;

@@ -102,4 +102,4 @@ def test_bwd_weight_bias_and_filter_maps(cuda):
   with pytest.raises(_lib.RecAttendError):
     ops.batch_norm_train_block_bwd(_g(g), _g(g[:, :4, :5]), *[_g(np.ones(Cout)) for _ in range(4)], pool=2)  # odd H, W
   empty = ops.conv3x3_bwd_weight(torch.zeros((0, 4, 4, 3), device='cuda'), torch.zeros((0, 4, 4, 2), device='cuda'))
-  assert tuple(empty[0].shape) == (3, 3, 3, 2)
+  assert tuple(empty[0].shape) == (3, 3, 3, 2) and float(empty[0].abs().sum()) == 0.0 and float(empty[1].abs().sum()) == 0.0
