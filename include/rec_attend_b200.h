@@ -335,6 +335,24 @@ int ra_filter_flip_transpose_f32(const float *w, int Ci, int Co, float *out, voi
 int ra_subsample2_f32(const float *src, int B, int H, int W, int C, int off, float *dst, void *stream);
 
 /* --------------------------------------------------------------------------------------
+ * Backward of the matching loss block (full_model.py:942-1034) to the model outputs — what TensorFlow's
+ * autodiff hands to y_out / attn_box / s_out; the matchings are constants (modellib.py:11).
+ *  ra_iou_loss_bwd_f32: da [B,N,H,W] (batch stride a_bstride, like a) = gradient of
+ *    -(scale/B) sum_b (1/max(1, sum match[b])) sum_nm match[b,n,m] * f_iou(a_n, g_m)  (modellib.py:104-155, eps per
+ *    pixel) with g = b_masks [B,M,H,W] (segmentation loss, :983-1012) or the filled rectangles b_rect [B,M,4]
+ *    (box loss, :931-973; ra_gt_box_f32's `rect`) — exactly one of the two non-NULL.  match [B,N,M].
+ *    ws: ra_iou_loss_bwd_workspace() bytes.
+ *  ra_conf_loss_bwd_f32: ds [B,T] = gradient of scale * f_conf_loss(s_out, match) (modellib.py:316-339 with the
+ *    cumulative min / max of :39-68): flows to the arg-min of every prefix and the arg-max of every suffix.
+ * -------------------------------------------------------------------------------------- */
+size_t ra_iou_loss_bwd_workspace(int B, int N, int M);
+int ra_iou_loss_bwd_f32(const float *a, size_t a_bstride, const float *b_masks, const float *b_rect,
+                        const float *match, int B, int N, int M, int H, int W, float scale, void *ws, float *da,
+                        void *stream);
+int ra_conf_loss_bwd_f32(const float *s_out, const float *match, int B, int T, int M, float scale, float *ds,
+                         void *stream);
+
+/* --------------------------------------------------------------------------------------
  * Foreground / orientation FCN head + loss block — fg_model.py:174-236 (the
  * FCN's conv stack runs on ra_conv3x3_umma_f32 / ra_conv3x3_f32).  logits [npix, nsc+nori] = last
  * DCNN layer (no BN, no activation, fg_model.py:121,148):

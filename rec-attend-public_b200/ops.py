@@ -442,6 +442,30 @@ def conv3x3_block_train_bwd(x, w, raw, dy, gamma, beta, mean, var, pool=1, relu=
   return out
 
 
+# ----------------------------------------------------------------------------- backward of the loss block
+def iou_loss_bwd(a, match, b_masks=None, b_rect=None, scale=1.0, out=None):
+  """Gradient wrt a [B,N,H,W] of -(scale/B) sum_b 1/cnt_b sum_nm match * f_iou(a_n, g_m) (full_model.py:942-1012):
+  g = b_masks [B,M,H,W] (segmentation loss) or b_rect [B,M,4] (box loss, get_gt_box's rect)."""
+  _chk(a, match, b_masks, b_rect, out)
+  B, N, H, W = a.shape
+  M = match.shape[2]
+  if out is None:
+    out = torch.empty_like(a)
+  ws = _ws(_lib.lib().ra_iou_loss_bwd_workspace(B, N, M), a.device)
+  _lib.call('ra_iou_loss_bwd_f32', _p(a), N * H * W, _p(b_masks), _p(b_rect), _p(match), B, N, M, H, W, float(scale),
+            _p(ws), _p(out), _stream())
+  return out
+
+
+def conf_loss_bwd(s_out, match, scale=1.0):
+  """Gradient wrt s_out [B,T] of scale * f_conf_loss(s_out, match) (modellib.py:316-339)."""
+  _chk(s_out, match)
+  B, T = s_out.shape
+  ds = torch.empty_like(s_out)
+  _lib.call('ra_conf_loss_bwd_f32', _p(s_out), _p(match), B, T, match.shape[2], float(scale), _p(ds), _stream())
+  return ds
+
+
 # ----------------------------------------------------------------------------- scheduled sampling (training mode)
 def gt_attn_noise(rect_raw, area, pad, shift, min_padding):
   """Noisy GT attention boxes (full_model.py:568-580): rect_raw [B,T,4] raw mask extrema, area [B,T], pad [B,T(,1)],

@@ -103,3 +103,46 @@ def test_bwd_weight_bias_and_filter_maps(cuda):
     ops.batch_norm_train_block_bwd(_g(g), _g(g[:, :4, :5]), *[_g(np.ones(Cout)) for _ in range(4)], pool=2)  # odd H, W
   empty = ops.conv3x3_bwd_weight(torch.zeros((0, 4, 4, 3), device='cuda'), torch.zeros((0, 4, 4, 2), device='cuda'))
   assert tuple(empty[0].shape) == (3, 3, 3, 2) and float(empty[0].abs().sum()) == 0.0 and float(empty[1].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('B,T,H,W', [(3, 5, 24, 40), (2, 20, 64, 128), (1, 8, 33, 47)])
+def test_loss_block_backward(cuda, B, T, H, W):
+  """Gradients of the matching loss (box + segm + mix * conf, full_model.py:942-1034) at the model outputs against
+  torch.autograd through oracle.model.full_model_loss; the matchings are the oracle's (constants of the gradient)."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200 import ops
+  opt = ra.config.full_model_opt('kitti', H, W, T)
+  rng = np.random.default_rng(B * 10 + T)
+  yy, xx = np.mgrid[0:H, 0:W]
+  y_gt = np.zeros((B, T, H, W), np.float32)
+  s_gt = np.zeros((B, T), np.float32)
+  for b in range(B):
+    k = T if b == 0 else max(1, T // 2)  # the other examples have empty ground-truth slots
+    for t in range(k):
+      cy, cx, r = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(3, H / 3)
+      y_gt[b, t] = ((yy - cy)**2 + (xx - cx)**2 <= r * r)
+      s_gt[b, t] = 1.0 if y_gt[b, t].sum() > 0 else 0.0
+  y_np = np.clip(0.6 * y_gt[:, rng.permutation(T)] + 0.4 * rng.random((B, T, H, W)), 0, 1).astype(np.float32)
+  box_np = rng.random((B, T, H, W)).astype(np.float32)
+  s_np = rng.uniform(0.05, 0.95, (B, T)).astype(np.float32)
+  y, box, s = [torch.from_numpy(a).requires_grad_(True) for a in (y_np, box_np, s_np)]
+  r = OM.full_model_loss(opt, {}, {'y_out': y, 'attn_box': box, 's_out': s}, torch.from_numpy(y_gt),
+                         torch.from_numpy(s_gt))
+  gy, gbox, gs = torch.autograd.grad(r['loss'], [y, box, s])
+  match, match_box = _g(r['match'].numpy()), _g(r['match_box'].numpy())
+  _, _, _, rect, _ = ops.get_gt_box(_g(y_gt), padding_ratio=opt['attn_box_padding_ratio'],
+                                    min_padding=opt['padding'] + 4, want_box=False)
+  dy = ops.iou_loss_bwd(_g(y_np), match, b_masks=_g(y_gt))
+  dbox = ops.iou_loss_bwd(_g(box_np), match_box, b_rect=rect)
+  ds = ops.conf_loss_bwd(_g(s_np), match, scale=opt['loss_mix_ratio'])
+  torch.cuda.synchronize()
+  assert float(gy.abs().max()) > 0 and float(gbox.abs().max()) > 0
+  assert rel_err(dy.cpu().numpy(), gy.numpy()) < TOL
+  assert rel_err(dbox.cpu().numpy(), gbox.numpy()) < TOL
+  assert rel_err(ds.cpu().numpy(), gs.numpy()) < TOL
+  # rows without a match get an exactly zero gradient
+  unmatched = (r['match'].sum(2) == 0).numpy()
+  assert float(dy.cpu().numpy()[unmatched].__abs__().sum()) == 0.0
+  from rec_attend_b200 import _lib
+  with pytest.raises(_lib.RecAttendError):
+    ops.iou_loss_bwd(_g(y_np), match)  # neither masks nor rectangles
