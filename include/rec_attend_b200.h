@@ -353,6 +353,26 @@ int ra_conf_loss_bwd_f32(const float *s_out, const float *match, int B, int T, i
                          void *stream);
 
 /* --------------------------------------------------------------------------------------
+ * Backward of the paste-back and of the Gaussian filters — TensorFlow's autodiff of
+ * out = sigmoid(gamma * (Fy P Fx^T) - 5) (full_model.py:738-741 with P = ones, :810-814 with the mask-head patch;
+ * modellib.py:615-641) and of modellib.get_gaussian_filter (modellib.py:581-612).
+ *  ra_paste_back_bwd_f32: d_out, out [B,H,W] (batch stride out_bstride), patch [B,F,F] or NULL (= ones),
+ *    fy [B,F,H], fx [B,F,W] tap-major, gamma at gamma[b*gamma_stride] (the exp'd gain of the box record)
+ *    -> d_patch [B,F,F] (NULL iff patch is NULL), d_fy [B,F,H], d_fx [B,F,W] (added to the existing contents when
+ *    accumulate != 0: the filters also feed the glimpse and the attention box), d_gamma [B] = dL/dgamma
+ *    (dL/d lg_gamma = d_gamma * gamma).  ws: ra_paste_back_bwd_workspace() bytes.  disable_overwrite is not handled.
+ *  ra_gaussian_filters_bwd_f32: d_fy, d_fx -> d_box [B,6] = (d_ctr_y, d_ctr_x, d_size_y, d_size_x, d_lg_var_y,
+ *    d_lg_var_x) for the box record `box` the filters were built from.
+ * -------------------------------------------------------------------------------------- */
+size_t ra_paste_back_bwd_workspace(int B, int H, int W, int F);
+int ra_paste_back_bwd_f32(const float *d_out, const float *out, size_t out_bstride, const float *patch, const float *fy,
+                          const float *fx, const float *gamma, int gamma_stride, int B, int H, int W, int F,
+                          int accumulate, void *ws, float *d_patch, float *d_fy, float *d_fx, float *d_gamma,
+                          void *stream);
+int ra_gaussian_filters_bwd_f32(const float *box, const float *fy, const float *fx, const float *d_fy, const float *d_fx,
+                                int B, int H, int W, int F, float *d_box, void *stream);
+
+/* --------------------------------------------------------------------------------------
  * Foreground / orientation FCN head + loss block — fg_model.py:174-236 (the
  * FCN's conv stack runs on ra_conv3x3_umma_f32 / ra_conv3x3_f32).  logits [npix, nsc+nori] = last
  * DCNN layer (no BN, no activation, fg_model.py:121,148):

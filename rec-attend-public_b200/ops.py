@@ -466,6 +466,41 @@ def conf_loss_bwd(s_out, match, scale=1.0):
   return ds
 
 
+# ----------------------------------------------------------------------------- backward of the attention write
+def paste_back_bwd(d_out, out, box, fy, fx, gamma_index, patch=None, d_fy=None, d_fx=None):
+  """Gradient of out = sigmoid(gamma * (Fy P Fx^T) - 5) (full_model.py:738-741, :810-814): d_out, out [B,H,W]
+  (contiguous), box [B,RA_BOX_STRIDE], fy [B,F,H], fx [B,F,W], gamma_index = _lib.BOX_GAMMA_Y or BOX_GAMMA_BOX,
+  patch [B,F,F] or None (= ones).  Passing d_fy / d_fx accumulates into them (the filters have several consumers).
+  Returns (d_patch or None, d_fy, d_fx, d_gamma [B])."""
+  _chk(d_out, out, box, fy, fx, patch, d_fy, d_fx)
+  B, H, W = d_out.shape
+  F = fy.shape[1]
+  dev = d_out.device
+  acc = 1 if d_fy is not None else 0
+  if d_fy is None:
+    d_fy = torch.empty_like(fy)
+    d_fx = torch.empty_like(fx)
+  d_patch = torch.empty((B, F, F), device=dev, dtype=torch.float32) if patch is not None else None
+  d_gamma = torch.empty(B, device=dev, dtype=torch.float32)
+  ws = _ws(_lib.lib().ra_paste_back_bwd_workspace(B, H, W, F), dev)
+  gamma = box.view(-1)[gamma_index:]
+  _lib.call('ra_paste_back_bwd_f32', _p(d_out), _p(out), H * W, _p(patch), _p(fy), _p(fx), _p(gamma), box.shape[1],
+            B, H, W, F, acc, _p(ws), _p(d_patch), _p(d_fy), _p(d_fx), _p(d_gamma), _stream())
+  return d_patch, d_fy, d_fx, d_gamma
+
+
+def gaussian_filters_bwd(box, fy, fx, d_fy, d_fx):
+  """Gradient of modellib.get_gaussian_filter (modellib.py:581-612) for both axes: -> d_box [B,6] =
+  (d_ctr_y, d_ctr_x, d_size_y, d_size_x, d_lg_var_y, d_lg_var_x)."""
+  _chk(box, fy, fx, d_fy, d_fx)
+  B, F, H = fy.shape
+  W = fx.shape[2]
+  d_box = torch.empty((B, 6), device=box.device, dtype=torch.float32)
+  _lib.call('ra_gaussian_filters_bwd_f32', _p(box), _p(fy), _p(fx), _p(d_fy), _p(d_fx), B, H, W, F, _p(d_box),
+            _stream())
+  return d_box
+
+
 # ----------------------------------------------------------------------------- scheduled sampling (training mode)
 def gt_attn_noise(rect_raw, area, pad, shift, min_padding):
   """Noisy GT attention boxes (full_model.py:568-580): rect_raw [B,T,4] raw mask extrema, area [B,T], pad [B,T(,1)],

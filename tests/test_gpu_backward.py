@@ -146,3 +146,55 @@ def test_loss_block_backward(cuda, B, T, H, W):
   from rec_attend_b200 import _lib
   with pytest.raises(_lib.RecAttendError):
     ops.iou_loss_bwd(_g(y_np), match)  # neither masks nor rectangles
+
+
+@pytest.mark.parametrize('B,H,W,F,with_patch', [(3, 64, 128, 48, True), (2, 40, 56, 12, True), (2, 64, 128, 48, False),
+                                               (1, 33, 47, 7, True)])
+def test_paste_back_and_filter_backward(cuda, B, H, W, F, with_patch):
+  """Gradients of out = sigmoid(gamma * (Fy P Fx^T) - 5) w.r.t. the patch, the gain and - through
+  modellib.get_gaussian_filter - the box centre, size and log-variance, against torch.autograd through the oracle's
+  get_gaussian_filter / extract_patch (full_model.py:728-741,810-814).  P = None is the attention-box form (ones)."""
+  from rec_attend_b200 import _lib, ops
+  rng = np.random.default_rng(B * 7 + F)
+  ctr_np = np.stack([rng.uniform(0.3 * H, 0.7 * H, B), rng.uniform(0.3 * W, 0.7 * W, B)], 1).astype(np.float32)
+  size_np = np.stack([rng.uniform(0.2 * H, 0.6 * H, B), rng.uniform(0.2 * W, 0.6 * W, B)], 1).astype(np.float32)
+  lgv_np = rng.uniform(-0.5, 1.5, (B, 2)).astype(np.float32)
+  lgg_np = rng.uniform(1.0, 3.0, B).astype(np.float32)
+  P_np = rng.random((B, F, F)).astype(np.float32) if with_patch else np.ones((B, F, F), np.float32)
+  ctr, size, lgv, lgg, P = [torch.from_numpy(a).requires_grad_(True) for a in (ctr_np, size_np, lgv_np, lgg_np, P_np)]
+  f_y = OM.get_gaussian_filter(ctr[:, 0], size[:, 0], lgv[:, 0], H, F)
+  f_x = OM.get_gaussian_filter(ctr[:, 1], size[:, 1], lgv[:, 1], W, F)
+  V = OM.extract_patch(P.unsqueeze(3), f_y.transpose(1, 2), f_x.transpose(1, 2), 1)[..., 0]
+  out = torch.sigmoid(torch.exp(lgg).view(-1, 1, 1) * V - 5.0)
+  d_out_np = rng.standard_normal((B, H, W)).astype(np.float32)
+  gP, gc, gs, gv, gg = torch.autograd.grad((out * torch.from_numpy(d_out_np)).sum(), [P, ctr, size, lgv, lgg])
+
+  box = np.zeros((B, _lib.BOX_STRIDE), np.float32)
+  box[:, 0:2], box[:, 2:4], box[:, 4:6] = ctr_np, size_np, lgv_np
+  box[:, _lib.BOX_GAMMA_ATTN] = 1.0
+  box[:, _lib.BOX_GAMMA_BOX] = np.exp(lgg_np)
+  box[:, _lib.BOX_GAMMA_Y] = np.exp(lgg_np)
+  box_d = _g(box)
+  fy, fx, _ = ops.get_gaussian_filter(box_d, H, W, F)
+  assert rel_err(fy.cpu().numpy(), f_y.detach().numpy().transpose(0, 2, 1)) < 1e-4  # tap-major forward filters
+  d_patch, d_fy, d_fx, d_gamma = ops.paste_back_bwd(_g(d_out_np), _g(out.detach().numpy()), box_d, fy, fx,
+                                                    _lib.BOX_GAMMA_Y if with_patch else _lib.BOX_GAMMA_BOX,
+                                                    patch=_g(P_np) if with_patch else None)
+  d_box = ops.gaussian_filters_bwd(box_d, fy, fx, d_fy, d_fx)
+  torch.cuda.synchronize()
+  tol = 1e-3
+  if with_patch:
+    assert rel_err(d_patch.cpu().numpy(), gP.numpy()) < tol
+  else:
+    assert d_patch is None
+  assert rel_err(d_gamma.cpu().numpy() * np.exp(lgg_np), gg.numpy()) < tol  # dL/d lg_gamma = dL/dgamma * gamma
+  db = d_box.cpu().numpy()
+  assert rel_err(db[:, 0:2], gc.numpy()) < tol and rel_err(db[:, 2:4], gs.numpy()) < tol
+  assert rel_err(db[:, 4:6], gv.numpy()) < tol
+  # accumulation: a second consumer of the same filters adds its share
+  d_fy2, d_fx2 = d_fy.clone(), d_fx.clone()
+  ops.paste_back_bwd(_g(d_out_np), _g(out.detach().numpy()), box_d, fy, fx,
+                     _lib.BOX_GAMMA_Y if with_patch else _lib.BOX_GAMMA_BOX, patch=_g(P_np) if with_patch else None,
+                     d_fy=d_fy2, d_fx=d_fx2)
+  torch.cuda.synchronize()
+  assert rel_err(d_fy2.cpu().numpy(), 2 * d_fy.cpu().numpy()) < 1e-6 and rel_err(d_fx2.cpu().numpy(), 2 * d_fx.cpu().numpy()) < 1e-6
