@@ -364,6 +364,16 @@ int ra_conf_loss_bwd_f32(const float *s_out, const float *match, int B, int T, i
  *  ra_gaussian_filters_bwd_f32: d_fy, d_fx -> d_box [B,6] = (d_ctr_y, d_ctr_x, d_size_y, d_size_x, d_lg_var_y,
  *    d_lg_var_x) for the box record `box` the filters were built from.
  * -------------------------------------------------------------------------------------- */
+ /* ra_gaussian_extract_bwd_f32: backward of the glimpse x_patch = gamma_attn * Fy^T X Fx (ra_gaussian_extract_f32,
+ *    full_model.py:788-789): d_patch, x_patch [B,F,F,patch_cstride] (patch channel order), X as xs / canvas /
+ *    chan_map like the forward -> d_fy, d_fx (accumulated when accumulate != 0), d_gamma [B] = dL/dgamma_attn.
+ *    No gradient goes to X (data; the canvas is behind tf.stop_gradient, full_model.py:846-848).
+ *    ws: ra_gaussian_extract_bwd_workspace(B, W, F, Cs + 1 or Cs) bytes. */
+size_t ra_gaussian_extract_bwd_workspace(int B, int W, int F, int D);
+int ra_gaussian_extract_bwd_f32(const float *xs, int Cs, const float *canvas, const int32_t *chan_map, const float *fy,
+                                const float *fx, const float *gamma, int gamma_stride, const float *d_patch,
+                                const float *x_patch, int patch_cstride, int B, int H, int W, int F, int accumulate,
+                                void *ws, float *d_fy, float *d_fx, float *d_gamma, void *stream);
 size_t ra_paste_back_bwd_workspace(int B, int H, int W, int F);
 int ra_paste_back_bwd_f32(const float *d_out, const float *out, size_t out_bstride, const float *patch, const float *fy,
                           const float *fx, const float *gamma, int gamma_stride, int B, int H, int W, int F,

@@ -66,6 +66,7 @@ _SIGNATURES = {
     'ra_iou_loss_bwd_f32': [_P, _Z, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P],
     'ra_conf_loss_bwd_f32': [_P, _P, _I, _I, _I, _F, _P, _P],
     'ra_paste_back_bwd_f32': [_P, _P, _Z, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    'ra_gaussian_extract_bwd_f32': [_P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     'ra_gaussian_filters_bwd_f32': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     'ra_fg_head_f32': [_P, _Z, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     'ra_adam_step_f32': [_P, _P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _P],
@@ -75,7 +76,8 @@ EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last
                                          'ra_pairwise_iou_workspace', 'ra_postprocess_workspace',
                                          'ra_bn_train_workspace', 'ra_fg_head_workspace',
                                          'ra_bn_train_block_bwd_workspace', 'ra_conv3x3_bwd_weight_workspace',
-                                         'ra_iou_loss_bwd_workspace', 'ra_paste_back_bwd_workspace'])
+                                         'ra_iou_loss_bwd_workspace', 'ra_paste_back_bwd_workspace',
+                                         'ra_gaussian_extract_bwd_workspace'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -117,6 +119,8 @@ def lib():
     l.ra_iou_loss_bwd_workspace.restype = _Z
     l.ra_paste_back_bwd_workspace.argtypes = [_I, _I, _I, _I]
     l.ra_paste_back_bwd_workspace.restype = _Z
+    l.ra_gaussian_extract_bwd_workspace.argtypes = [_I, _I, _I, _I]
+    l.ra_gaussian_extract_bwd_workspace.restype = _Z
     _lib = l
   return _lib
 

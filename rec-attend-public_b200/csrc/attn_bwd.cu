@@ -183,6 +183,147 @@ __global__ void __launch_bounds__(kT) filters_bwd_kernel(const float *__restrict
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- glimpse backward
+// forward (full_model.py:788-789, modellib.py:615-641): x_patch[i,j,d] = gamma * sum_{y,x} fy[i,y] X[y,x,d] fx[j,x],
+// X = the step's input stack given as xs [B,H,W,Cs] + canvas [B,H,W]; source channel c sits at patch channel
+// chan_map[c].  With G = d x_patch and T[i,x,c] = sum_y fy[i,y] X[y,x,c] (the forward's row pass, recomputed):
+//   d_fx[j,x] = gamma * sum_{i,c} G[i,j,c] T[i,x,c]
+//   d_fy[i,y] = sum_{x,c} S[i,x,c] X[y,x,c],   S[i,x,c] = gamma * sum_j G[i,j,c] fx[j,x]
+//   d_gamma   = sum G * x_patch / gamma
+// No gradient flows to X: the image is data and the canvas is behind tf.stop_gradient (full_model.py:846-848).
+__device__ __forceinline__ float x_value(const float *__restrict__ xs, int Cs, const float *__restrict__ canvas,
+                                         size_t pix, int c) {
+  return (c < Cs) ? xs[pix * Cs + c] : canvas[pix];
+}
+
+// thread per (x, c): T[b,i,x,c] for every tap i
+__global__ void __launch_bounds__(kT) ex_T_kernel(const float *__restrict__ xs, int Cs, const float *__restrict__ canvas,
+                                                  const float *__restrict__ fy, int H, int W, int F, int D,
+                                                  float *__restrict__ T) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * kT + threadIdx.x;
+  if (idx >= W * D) return;
+  const int x = idx / D, c = idx - x * D;
+  float acc[kMaxF];
+#pragma unroll
+  for (int i = 0; i < kMaxF; ++i) acc[i] = 0.f;
+  const float *fyb = fy + (size_t)b * F * H;
+  for (int y = 0; y < H; ++y) {
+    const float v = x_value(xs, Cs, canvas, ((size_t)b * H + y) * W + x, c);
+#pragma unroll
+    for (int i = 0; i < kMaxF; ++i)
+      if (i < F) acc[i] = fmaf(fyb[(size_t)i * H + y], v, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxF; ++i)
+    if (i < F) T[(((size_t)b * F + i) * W + x) * D + c] = acc[i];
+}
+
+// grid (x blocks, b): d_fx[b,:,x] (+)= gamma * sum_{i,c} G[b,i,:,ch(c)] T[b,i,x,c];  G rows staged per tap i
+__global__ void __launch_bounds__(kT) ex_dfx_kernel(const float *__restrict__ G, int cstride,
+                                                    const int *__restrict__ chan_map, const float *__restrict__ T,
+                                                    const float *__restrict__ gamma, int gamma_stride, int W, int F,
+                                                    int D, int accumulate, float *__restrict__ d_fx) {
+  extern __shared__ float G_s[];  // [F (j)][D] of the current tap i, source-channel order
+  const int b = blockIdx.y;
+  const int x = blockIdx.x * kT + threadIdx.x;
+  float acc[kMaxF];
+#pragma unroll
+  for (int j = 0; j < kMaxF; ++j) acc[j] = 0.f;
+  for (int i = 0; i < F; ++i) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < F * D; k += kT) {
+      const int j = k / D, c = k - j * D;
+      G_s[k] = G[(((size_t)b * F + i) * F + j) * cstride + chan_map[c]];
+    }
+    __syncthreads();
+    if (x < W) {
+      const float *Ti = T + (((size_t)b * F + i) * W + x) * D;
+      for (int c = 0; c < D; ++c) {
+        const float t = Ti[c];
+#pragma unroll
+        for (int j = 0; j < kMaxF; ++j)
+          if (j < F) acc[j] = fmaf(G_s[j * D + c], t, acc[j]);
+      }
+    }
+  }
+  if (x >= W) return;
+  const float g = gamma[(size_t)b * gamma_stride];
+#pragma unroll
+  for (int j = 0; j < kMaxF; ++j)
+    if (j < F) {
+      float *dst = d_fx + ((size_t)b * F + j) * W + x;
+      *dst = accumulate ? fmaf(g, acc[j], *dst) : g * acc[j];
+    }
+}
+
+// grid ((x,c) blocks, i, b): S[b,i,x,c] = gamma * sum_j G[b,i,j,ch(c)] fx[b,j,x]
+__global__ void __launch_bounds__(kT) ex_S_kernel(const float *__restrict__ G, int cstride,
+                                                  const int *__restrict__ chan_map, const float *__restrict__ fx,
+                                                  const float *__restrict__ gamma, int gamma_stride, int W, int F, int D,
+                                                  float *__restrict__ S) {
+  extern __shared__ float G_s[];  // [F (j)][D]
+  const int i = blockIdx.y, b = blockIdx.z;
+  for (int k = threadIdx.x; k < F * D; k += kT) {
+    const int j = k / D, c = k - j * D;
+    G_s[k] = G[(((size_t)b * F + i) * F + j) * cstride + chan_map[c]];
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * kT + threadIdx.x;
+  if (idx >= W * D) return;
+  const int x = idx / D, c = idx - x * D;
+  const float *fxb = fx + (size_t)b * F * W + x;
+  float s = 0.f;
+  for (int j = 0; j < F; ++j) s = fmaf(G_s[j * D + c], fxb[(size_t)j * W], s);
+  S[(((size_t)b * F + i) * W) * D + idx] = gamma[(size_t)b * gamma_stride] * s;
+}
+
+// grid (row tiles of kExRows, b): d_fy[b,i,y] (+)= sum_{x,c} S[b,i,x,c] X[b,y,x,c]
+constexpr int kExRows = 8;
+__global__ void __launch_bounds__(kT) ex_dfy_kernel(const float *__restrict__ xs, int Cs,
+                                                    const float *__restrict__ canvas, const float *__restrict__ S, int H,
+                                                    int W, int F, int D, int accumulate, float *__restrict__ d_fy) {
+  __shared__ float red[32];
+  const int y0 = blockIdx.x * kExRows, b = blockIdx.y;
+  const int n = W * D;
+  for (int i = 0; i < F; ++i) {
+    float acc[kExRows];
+#pragma unroll
+    for (int r = 0; r < kExRows; ++r) acc[r] = 0.f;
+    const float *Si = S + ((size_t)b * F + i) * n;
+    for (int idx = threadIdx.x; idx < n; idx += kT) {
+      const float s = Si[idx];
+      if (s == 0.f) continue;
+      const int x = idx / D, c = idx - x * D;
+#pragma unroll
+      for (int r = 0; r < kExRows; ++r)
+        if (y0 + r < H) acc[r] = fmaf(x_value(xs, Cs, canvas, ((size_t)b * H + y0 + r) * W + x, c), s, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kExRows; ++r) {
+      const float v = ra::block_sum(acc[r], red);
+      if (threadIdx.x == 0 && y0 + r < H) {
+        float *dst = d_fy + ((size_t)b * F + i) * H + y0 + r;
+        *dst = accumulate ? (*dst + v) : v;
+      }
+    }
+  }
+}
+
+// d_gamma[b] = sum G * x_patch / gamma over the D real channels
+__global__ void __launch_bounds__(kT) ex_dgamma_kernel(const float *__restrict__ G, const float *__restrict__ x_patch,
+                                                       int cstride, int D, int F, const float *__restrict__ gamma,
+                                                       int gamma_stride, float *__restrict__ d_gamma) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < F * F * cstride; k += kT)
+    if (k % cstride < D) s = fmaf(G[(size_t)b * F * F * cstride + k], x_patch[(size_t)b * F * F * cstride + k], s);
+  s = ra::block_sum(s, red);
+  if (threadIdx.x == 0) d_gamma[b] = s / gamma[(size_t)b * gamma_stride];
+}
+
 }  // namespace
 
 extern "C" size_t ra_paste_back_bwd_workspace(int B, int H, int W, int F) {
@@ -227,4 +368,42 @@ extern "C" int ra_gaussian_filters_bwd_f32(const float *box, const float *fy, co
   if (B > 65535) return RA_ERR_UNSUPPORTED;
   filters_bwd_kernel<<<dim3(2, B), kT, 0, ra::as_stream(stream)>>>(box, fy, fx, d_fy, d_fx, H, W, F, d_box);
   return ra::finish_launch("filters_bwd_kernel");
+}
+
+extern "C" size_t ra_gaussian_extract_bwd_workspace(int B, int W, int F, int D) {
+  if (B < 1 || W < 1 || F < 1 || D < 1) return 0;
+  return (size_t)2 * B * F * W * D * sizeof(float);  // T and S
+}
+
+extern "C" int ra_gaussian_extract_bwd_f32(const float *xs, int Cs, const float *canvas, const int32_t *chan_map,
+                                           const float *fy, const float *fx, const float *gamma, int gamma_stride,
+                                           const float *d_patch, const float *x_patch, int patch_cstride, int B, int H,
+                                           int W, int F, int accumulate, void *ws, float *d_fy, float *d_fx,
+                                           float *d_gamma, void *stream) {
+  const int D = Cs + (canvas ? 1 : 0);
+  if (B < 0 || H < 1 || W < 1 || F < 1 || F > kMaxF || Cs < 0 || D < 1 || patch_cstride < D || gamma_stride < 1)
+    return RA_ERR_INVALID_ARG;
+  if (B == 0) return RA_OK;
+  if ((Cs > 0 && !xs) || !chan_map || !fy || !fx || !gamma || !d_patch || !x_patch || !ws || !d_fy || !d_fx || !d_gamma)
+    return RA_ERR_INVALID_ARG;
+  if (B > 65535 || (size_t)F * D * sizeof(float) > 48 * 1024) return RA_ERR_UNSUPPORTED;
+  cudaStream_t s = ra::as_stream(stream);
+  float *T = reinterpret_cast<float *>(ws), *S = T + (size_t)B * F * W * D;
+  const int bxc = (W * D + kT - 1) / kT, bx = (W + kT - 1) / kT;
+  const size_t gsm = (size_t)F * D * sizeof(float);
+  ex_T_kernel<<<dim3(bxc, B), kT, 0, s>>>(xs, Cs, canvas, fy, H, W, F, D, T);
+  int rc = ra::finish_launch("ex_T_kernel");
+  if (rc != RA_OK) return rc;
+  ex_dfx_kernel<<<dim3(bx, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, T, gamma, gamma_stride, W, F, D, accumulate,
+                                             d_fx);
+  rc = ra::finish_launch("ex_dfx_kernel");
+  if (rc != RA_OK) return rc;
+  ex_S_kernel<<<dim3(bxc, F, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, fx, gamma, gamma_stride, W, F, D, S);
+  rc = ra::finish_launch("ex_S_kernel");
+  if (rc != RA_OK) return rc;
+  ex_dfy_kernel<<<dim3((H + kExRows - 1) / kExRows, B), kT, 0, s>>>(xs, Cs, canvas, S, H, W, F, D, accumulate, d_fy);
+  rc = ra::finish_launch("ex_dfy_kernel");
+  if (rc != RA_OK) return rc;
+  ex_dgamma_kernel<<<B, kT, 0, s>>>(d_patch, x_patch, patch_cstride, D, F, gamma, gamma_stride, d_gamma);
+  return ra::finish_launch("ex_dgamma_kernel");
 }

@@ -489,6 +489,29 @@ def paste_back_bwd(d_out, out, box, fy, fx, gamma_index, patch=None, d_fy=None, 
   return d_patch, d_fy, d_fx, d_gamma
 
 
+def extract_patch_bwd(d_patch, x_patch, xs, canvas, chan_map, box, fy, fx, d_fy=None, d_fx=None):
+  """Gradient of the glimpse x_patch = gamma_attn * Fy^T X Fx (ops.extract_patch; full_model.py:788-789) w.r.t. the
+  filters and the gain: d_patch, x_patch [B,F,F,cstride]; xs / canvas / chan_map as in the forward call.
+  Passing d_fy / d_fx accumulates into them.  Returns (d_fy, d_fx, d_gamma [B])."""
+  _chk(d_patch, x_patch, xs, canvas, chan_map, box, fy, fx, d_fy, d_fx)
+  B, F, H = fy.shape
+  W = fx.shape[2]
+  Cs = 0 if xs is None else xs.shape[3]
+  D = Cs + (1 if canvas is not None else 0)
+  dev = fy.device
+  acc = 1 if d_fy is not None else 0
+  if d_fy is None:
+    d_fy = torch.empty_like(fy)
+    d_fx = torch.empty_like(fx)
+  d_gamma = torch.empty(B, device=dev, dtype=torch.float32)
+  ws = _ws(_lib.lib().ra_gaussian_extract_bwd_workspace(B, W, F, D), dev)
+  gamma = box.view(-1)[_lib.BOX_GAMMA_ATTN:]
+  _lib.call('ra_gaussian_extract_bwd_f32', _p(xs), Cs, _p(canvas), _p(chan_map), _p(fy), _p(fx), _p(gamma),
+            box.shape[1], _p(d_patch), _p(x_patch), d_patch.shape[3], B, H, W, F, acc, _p(ws), _p(d_fy), _p(d_fx),
+            _p(d_gamma), _stream())
+  return d_fy, d_fx, d_gamma
+
+
 def gaussian_filters_bwd(box, fy, fx, d_fy, d_fx):
   """Gradient of modellib.get_gaussian_filter (modellib.py:581-612) for both axes: -> d_box [B,6] =
   (d_ctr_y, d_ctr_x, d_size_y, d_size_x, d_lg_var_y, d_lg_var_x)."""

@@ -198,3 +198,55 @@ def test_paste_back_and_filter_backward(cuda, B, H, W, F, with_patch):
                      d_fy=d_fy2, d_fx=d_fx2)
   torch.cuda.synchronize()
   assert rel_err(d_fy2.cpu().numpy(), 2 * d_fy.cpu().numpy()) < 1e-6 and rel_err(d_fx2.cpu().numpy(), 2 * d_fx.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize('B,H,W,F,D,cstride,with_canvas', [(2, 64, 128, 48, 13, 16, True), (3, 40, 56, 12, 4, 4, True),
+                                                          (2, 32, 48, 8, 3, 4, False)])
+def test_glimpse_extract_backward(cuda, B, H, W, F, D, cstride, with_canvas):
+  """Gradients of x_patch = gamma_attn * Fy^T X Fx (full_model.py:788-789) w.r.t. the gain and - through the filters -
+  the box centre / size / log-variance, against torch.autograd through the oracle's extract_patch.  X is split like
+  the forward kernel's inputs (step-invariant channels + canvas, chan_map = the reference's concat order)."""
+  from rec_attend_b200 import _lib, ops
+  rng = np.random.default_rng(B * 11 + D)
+  ctr_np = np.stack([rng.uniform(0.3 * H, 0.7 * H, B), rng.uniform(0.3 * W, 0.7 * W, B)], 1).astype(np.float32)
+  size_np = np.stack([rng.uniform(0.2 * H, 0.6 * H, B), rng.uniform(0.2 * W, 0.6 * W, B)], 1).astype(np.float32)
+  lgv_np = rng.uniform(-0.5, 1.5, (B, 2)).astype(np.float32)
+  lgg_np = rng.uniform(-0.5, 0.5, B).astype(np.float32)
+  X_np = rng.random((B, H, W, D)).astype(np.float32)
+  G_np = rng.standard_normal((B, F, F, D)).astype(np.float32)
+  ctr, size, lgv, lgg = [torch.from_numpy(a).requires_grad_(True) for a in (ctr_np, size_np, lgv_np, lgg_np)]
+  f_y = OM.get_gaussian_filter(ctr[:, 0], size[:, 0], lgv[:, 0], H, F)
+  f_x = OM.get_gaussian_filter(ctr[:, 1], size[:, 1], lgv[:, 1], W, F)
+  xp = torch.exp(lgg).view(-1, 1, 1, 1) * OM.extract_patch(torch.from_numpy(X_np), f_y, f_x, D)
+  gc, gs, gv, gg = torch.autograd.grad((xp * torch.from_numpy(G_np)).sum(), [ctr, size, lgv, lgg])
+
+  # device inputs: canvas = reference channel 3 (after x), the rest static, like FullModel.chan_map
+  if with_canvas:
+    static_idx = [c for c in range(D) if c != 3]
+    xs, canvas = _g(X_np[..., static_idx]), _g(X_np[..., 3])
+    chan_map = torch.tensor(static_idx + [3], dtype=torch.int32, device='cuda')
+  else:
+    xs, canvas = _g(X_np), None
+    chan_map = torch.arange(D + 1, dtype=torch.int32, device='cuda')  # [Cs+1] entries, the last one unused
+  box = np.zeros((B, _lib.BOX_STRIDE), np.float32)
+  box[:, 0:2], box[:, 2:4], box[:, 4:6] = ctr_np, size_np, lgv_np
+  box[:, _lib.BOX_GAMMA_ATTN] = np.exp(lgg_np)
+  box_d = _g(box)
+  fy, fx, band = ops.get_gaussian_filter(box_d, H, W, F)
+  pad = lambda a: np.concatenate([a, np.zeros(a.shape[:3] + (cstride - D,), np.float32)], 3)
+  x_patch = ops.extract_patch(xs, canvas, chan_map, box_d, fy, fx, band,
+                              out=torch.empty((B, F, F, cstride), device='cuda'))
+  assert rel_err(x_patch.cpu().numpy()[..., :D], xp.detach().numpy()) < 1e-3  # forward sanity (patch channel order)
+  d_fy, d_fx, d_gamma = ops.extract_patch_bwd(_g(pad(G_np)), x_patch, xs, canvas, chan_map, box_d, fy, fx)
+  d_box = ops.gaussian_filters_bwd(box_d, fy, fx, d_fy, d_fx)
+  torch.cuda.synchronize()
+  tol = 1e-3
+  assert rel_err(d_gamma.cpu().numpy() * np.exp(lgg_np), gg.numpy()) < tol
+  db = d_box.cpu().numpy()
+  assert rel_err(db[:, 0:2], gc.numpy()) < tol and rel_err(db[:, 2:4], gs.numpy()) < tol
+  assert rel_err(db[:, 4:6], gv.numpy()) < tol
+  # accumulate on top of an existing gradient
+  d_fy2, d_fx2 = d_fy.clone(), d_fx.clone()
+  ops.extract_patch_bwd(_g(pad(G_np)), x_patch, xs, canvas, chan_map, box_d, fy, fx, d_fy=d_fy2, d_fx=d_fx2)
+  torch.cuda.synchronize()
+  assert rel_err(d_fy2.cpu().numpy(), 2 * d_fy.cpu().numpy()) < 1e-6 and rel_err(d_fx2.cpu().numpy(), 2 * d_fx.cpu().numpy()) < 1e-6
