@@ -383,6 +383,35 @@ int ra_gaussian_filters_bwd_f32(const float *box, const float *fy, const float *
                                 int B, int H, int W, int F, float *d_box, void *stream);
 
 /* --------------------------------------------------------------------------------------
+ * Backward of the controller (full_model.py:668-725) — TensorFlow's autodiff of the soft read-out, the LSTM, the
+ * glimpse-MLP softmax (n_iter iterations), the linear head and the box-parameter maths.  Weight layouts as in
+ * ra_controller_step_f32 (gate order i, f, o, u).
+ *  ra_controller_tape_f32: re-runs the forward of one decode step and records per (example, iteration) the record
+ *    [map_k | glimpse_k | h_{k-1} | c_{k-1} | gates i,f,o,u | c_k | h_k | a1_k | map_{k+1}] (field offsets and record
+ *    size from ra_controller_tape_layout; ra_controller_tape_floats() floats per example); also h_out, ctrl_out.
+ *  ra_controller_head_bwd_f32: d_box [B,6] (ra_gaussian_filters_bwd_f32's layout, summed over the filters' consumers)
+ *    and d_gamma3 [B,3] = dL/dgamma (attn, box, y) -> d_ctrl_out [B,9], honouring the RA_CTRL_* flags.
+ *  ra_controller_bwd_f32: d_h [B,Hd] (may be NULL; the score head's share) and d_ctrl_out -> d_feat [B,P,Cf] and the
+ *    pre-activation deltas dG [B,n_iter,4,Hd], dA1 [B,n_iter,Hd], dLog [B,n_iter,P].
+ *  ra_outer_sum_f32: dW [n_in,n_out] = sum_r A[r*a_stride + :]^T D[r*d_stride + :], db [n_out] (may be NULL) = column
+ *    sums of D — every dense-layer weight gradient of the controller (rows = (example, iteration)).
+ * -------------------------------------------------------------------------------------- */
+size_t ra_controller_tape_floats(int P, int Cf, int Hd, int n_iter);
+int ra_controller_tape_layout(int P, int Cf, int Hd, int *offsets);
+int ra_controller_tape_f32(const float *feat, int B, int P, int Cf, int Hd, int n_iter, const float *lstm_wx,
+                           const float *lstm_wh, const float *lstm_b, const float *gmlp_w0, const float *gmlp_b0,
+                           const float *gmlp_w1, const float *gmlp_b1, const float *cmlp_w, const float *cmlp_b,
+                           float *tape, float *h_out, float *ctrl_out, void *stream);
+int ra_controller_head_bwd_f32(const float *ctrl_out, const float *box, const float *d_box, const float *d_gamma3, int B,
+                               int inp_height, int inp_width, int flags, float *d_ctrl_out, void *stream);
+int ra_controller_bwd_f32(const float *feat, int B, int P, int Cf, int Hd, int n_iter, const float *lstm_wx,
+                          const float *lstm_wh, const float *gmlp_w0, const float *gmlp_w1, const float *cmlp_w,
+                          const float *tape, const float *d_h, const float *d_ctrl_out, float *d_feat, float *dG,
+                          float *dA1, float *dLog, void *stream);
+int ra_outer_sum_f32(const float *A, size_t a_stride, int n_in, const float *D, size_t d_stride, int n_out, int R,
+                     float *dW, float *db, void *stream);
+
+/* --------------------------------------------------------------------------------------
  * Foreground / orientation FCN head + loss block — fg_model.py:174-236 (the
  * FCN's conv stack runs on ra_conv3x3_umma_f32 / ra_conv3x3_f32).  logits [npix, nsc+nori] = last
  * DCNN layer (no BN, no activation, fg_model.py:121,148):

@@ -68,6 +68,11 @@ _SIGNATURES = {
     'ra_paste_back_bwd_f32': [_P, _P, _Z, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     'ra_gaussian_extract_bwd_f32': [_P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     'ra_gaussian_filters_bwd_f32': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    'ra_controller_tape_f32': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'ra_controller_tape_layout': [_I, _I, _I, _P],
+    'ra_controller_head_bwd_f32': [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
+    'ra_controller_bwd_f32': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'ra_outer_sum_f32': [_P, _Z, _I, _P, _Z, _I, _I, _P, _P, _P],
     'ra_fg_head_f32': [_P, _Z, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     'ra_adam_step_f32': [_P, _P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _P],
     'ra_postprocess_f32': [_P, _P, _P, _I, _I, _I, _I, ctypes.c_double, _F, _P, _P, _P, _P, _P, _P],
@@ -77,7 +82,7 @@ EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last
                                          'ra_bn_train_workspace', 'ra_fg_head_workspace',
                                          'ra_bn_train_block_bwd_workspace', 'ra_conv3x3_bwd_weight_workspace',
                                          'ra_iou_loss_bwd_workspace', 'ra_paste_back_bwd_workspace',
-                                         'ra_gaussian_extract_bwd_workspace'])
+                                         'ra_gaussian_extract_bwd_workspace', 'ra_controller_tape_floats'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -121,6 +126,8 @@ def lib():
     l.ra_paste_back_bwd_workspace.restype = _Z
     l.ra_gaussian_extract_bwd_workspace.argtypes = [_I, _I, _I, _I]
     l.ra_gaussian_extract_bwd_workspace.restype = _Z
+    l.ra_controller_tape_floats.argtypes = [_I, _I, _I, _I]
+    l.ra_controller_tape_floats.restype = _Z
     _lib = l
   return _lib
 

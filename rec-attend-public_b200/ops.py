@@ -524,6 +524,76 @@ def gaussian_filters_bwd(box, fy, fx, d_fy, d_fx):
   return d_box
 
 
+# ----------------------------------------------------------------------------- backward of the controller
+TAPE_FIELDS = ('map', 'glimpse', 'h_prev', 'c_prev', 'gates', 'c', 'h', 'a1', 'map_next')
+
+
+def controller_tape(feat, lstm_wx, lstm_wh, lstm_b, gmlp_w0, gmlp_b0, gmlp_w1, gmlp_b1, cmlp_w, cmlp_b, n_iter=5):
+  """Forward of the controller for one decode step with everything the backward needs recorded
+  (ra_controller_tape_f32).  Returns (tape [B,n_iter,rec], offsets dict, h_out [B,Hd], ctrl_out [B,9])."""
+  _chk(feat, lstm_wx, lstm_wh, lstm_b, gmlp_w0, gmlp_b0, gmlp_w1, gmlp_b1, cmlp_w, cmlp_b)
+  B, P, Cf = feat.shape
+  Hd = lstm_wh.shape[-1]
+  off = (_c.c_int * 10)()
+  _lib.call('ra_controller_tape_layout', P, Cf, Hd, off)
+  offsets = dict(zip(TAPE_FIELDS + ('rec',), list(off)))
+  dev = feat.device
+  tape = torch.empty((B, n_iter, offsets['rec']), device=dev, dtype=torch.float32)
+  h_out = torch.empty((B, Hd), device=dev, dtype=torch.float32)
+  ctrl_out = torch.empty((B, 9), device=dev, dtype=torch.float32)
+  _lib.call('ra_controller_tape_f32', _p(feat), B, P, Cf, Hd, n_iter, _p(lstm_wx), _p(lstm_wh), _p(lstm_b),
+            _p(gmlp_w0), _p(gmlp_b0), _p(gmlp_w1), _p(gmlp_b1), _p(cmlp_w), _p(cmlp_b), _p(tape), _p(h_out),
+            _p(ctrl_out), _stream())
+  return tape, offsets, h_out, ctrl_out
+
+
+def outer_sum(A, a_stride, n_in, D, d_stride, n_out, R, want_bias=True):
+  """dW [n_in,n_out] = sum_r A_r^T D_r over R rows (A_r at A.data + r*a_stride floats), db = column sums of D."""
+  dev = D.device
+  dW = torch.empty((n_in, n_out), device=dev, dtype=torch.float32)
+  db = torch.empty(n_out, device=dev, dtype=torch.float32) if want_bias else None
+  _lib.call('ra_outer_sum_f32', _p(A), a_stride, n_in, _p(D), d_stride, n_out, R, _p(dW), _p(db), _stream())
+  return dW, db
+
+
+def controller_bwd(feat, box, lstm_wx, lstm_wh, lstm_b, gmlp_w0, gmlp_b0, gmlp_w1, gmlp_b1, cmlp_w, cmlp_b, inp_height,
+                   inp_width, flags, d_box, d_gamma3, d_h=None, n_iter=5):
+  """Backward of ops.controller_step for one decode step: d_box [B,6] = (d_ctr, d_size, d_lg_var) summed over the
+  consumers of the filters, d_gamma3 [B,3] = dL/dgamma (attn, box, y), d_h [B,Hd] = the score head's gradient.
+  Returns a dict: d_feat [B,P,Cf] and the weight gradients in the device layouts of the forward call
+  (lstm_wx [4,Cf,Hd], lstm_wh [4,Hd,Hd], lstm_b [4,Hd], gmlp_w0/b0, gmlp_w1/b1, cmlp_w/b)."""
+  _chk(feat, box, d_box, d_gamma3, d_h)
+  B, P, Cf = feat.shape
+  Hd = lstm_wh.shape[-1]
+  dev = feat.device
+  tape, off, h_out, ctrl_out = controller_tape(feat, lstm_wx, lstm_wh, lstm_b, gmlp_w0, gmlp_b0, gmlp_w1, gmlp_b1,
+                                               cmlp_w, cmlp_b, n_iter=n_iter)
+  d_ctrl = torch.empty((B, 9), device=dev, dtype=torch.float32)
+  _lib.call('ra_controller_head_bwd_f32', _p(ctrl_out), _p(box), _p(d_box), _p(d_gamma3), B, inp_height, inp_width,
+            flags, _p(d_ctrl), _stream())
+  d_feat = torch.empty_like(feat)
+  dG = torch.empty((B, n_iter, 4, Hd), device=dev, dtype=torch.float32)
+  dA1 = torch.empty((B, n_iter, Hd), device=dev, dtype=torch.float32)
+  dLog = torch.empty((B, n_iter, P), device=dev, dtype=torch.float32)
+  _lib.call('ra_controller_bwd_f32', _p(feat), B, P, Cf, Hd, n_iter, _p(lstm_wx), _p(lstm_wh), _p(gmlp_w0),
+            _p(gmlp_w1), _p(cmlp_w), _p(tape), _p(d_h), _p(d_ctrl), _p(d_feat), _p(dG), _p(dA1), _p(dLog), _stream())
+  R, rec = B * n_iter, off['rec']
+  flat = tape.view(-1)
+  out = {'d_feat': d_feat, 'd_ctrl_out': d_ctrl, 'h': h_out, 'ctrl_out': ctrl_out}
+  wx, wh, bg = [], [], []
+  for g in range(4):
+    Dg = dG.view(-1)[g * Hd:]
+    w_, b_ = outer_sum(flat[off['glimpse']:], rec, Cf, Dg, 4 * Hd, Hd, R)
+    wx.append(w_)
+    bg.append(b_)
+    wh.append(outer_sum(flat[off['h_prev']:], rec, Hd, Dg, 4 * Hd, Hd, R, want_bias=False)[0])
+  out['lstm_wx'], out['lstm_wh'], out['lstm_b'] = torch.stack(wx), torch.stack(wh), torch.stack(bg)
+  out['gmlp_w0'], out['gmlp_b0'] = outer_sum(flat[off['h']:], rec, Hd, dA1, Hd, Hd, R)
+  out['gmlp_w1'], out['gmlp_b1'] = outer_sum(flat[off['a1']:], rec, Hd, dLog, P, P, R)
+  out['cmlp_w'], out['cmlp_b'] = outer_sum(h_out, Hd, Hd, d_ctrl, 9, 9, B)
+  return out
+
+
 # ----------------------------------------------------------------------------- scheduled sampling (training mode)
 def gt_attn_noise(rect_raw, area, pad, shift, min_padding):
   """Noisy GT attention boxes (full_model.py:568-580): rect_raw [B,T,4] raw mask extrema, area [B,T], pad [B,T(,1)],

@@ -250,3 +250,65 @@ def test_glimpse_extract_backward(cuda, B, H, W, F, D, cstride, with_canvas):
   ops.extract_patch_bwd(_g(pad(G_np)), x_patch, xs, canvas, chan_map, box_d, fy, fx, d_fy=d_fy2, d_fx=d_fx2)
   torch.cuda.synchronize()
   assert rel_err(d_fy2.cpu().numpy(), 2 * d_fy.cpu().numpy()) < 1e-6 and rel_err(d_fx2.cpu().numpy(), 2 * d_fx.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize('arch,H,W,B', [('kitti', 64, 128, 3), ('cvppp', 64, 64, 2), ('cityscapes', 128, 128, 2)])
+def test_controller_backward(cuda, arch, H, W, B):
+  """BPTT through the controller (read-out, LSTM, glimpse-MLP softmax x5, head, box maths; full_model.py:668-725)
+  against torch.autograd through oracle.model.controller_step fed with the same feature map.  The tape kernel's
+  forward is also checked against the production controller kernel."""
+  from unittest import mock
+  import rec_attend_b200 as ra
+  from rec_attend_b200 import _lib, ops
+  opt = ra.config.full_model_opt(arch, H, W, 2)
+  w = ra.synthetic.make_weights(opt, seed=7)
+  gh, gw = H // 32, W // 32
+  P, Cf, Hd = gh * gw, opt['ctrl_cnn_depth'][-1], opt['ctrl_rnn_hid_dim']
+  rng = np.random.default_rng(B + P)
+  feat_np = np.abs(rng.standard_normal((B, P, Cf))).astype(np.float32)
+  keys = [k for k in w if k.startswith(('ctrl_lstm', 'glimpse_mlp', 'ctrl_mlp'))]
+  wt = {k: torch.from_numpy(np.asarray(v, np.float32)).requires_grad_(k in keys) for k, v in w.items()}
+  feat = torch.from_numpy(feat_np).requires_grad_(True)
+  with mock.patch.object(OM, 'run_cnn', lambda *a, **k: [feat.reshape(B, gh, gw, Cf)]):
+    c = OM.controller_step(opt, wt, torch.zeros(B, H, W, 4), 0)
+  r = {k: rng.standard_normal(tuple(c[k].shape)).astype(np.float32) for k in ('h', 'ctr', 'size', 'lg_var')}
+  rg = rng.standard_normal((B, 3)).astype(np.float32)
+  gam = torch.cat([torch.exp(c['lg_gamma']), torch.exp(c['box_lg_gamma']), torch.exp(c['y_lg_gamma'])], 1)
+  loss = sum((c[k] * torch.from_numpy(r[k])).sum() for k in r) + (gam * torch.from_numpy(rg)).sum()
+  grads = torch.autograd.grad(loss, [feat] + [wt[k] for k in keys], allow_unused=True)
+  ref = dict(zip(['feat'] + keys, [g.numpy() for g in grads]))
+
+  flags = 0
+  if opt.get('squash_ctrl_params', False):
+    flags |= _lib.CTRL_SQUASH
+  if opt.get('fixed_var', False):
+    flags |= _lib.CTRL_FIXED_VAR
+  if opt.get('dynamic_var', False):
+    flags |= _lib.CTRL_DYNAMIC_VAR
+  if opt.get('fixed_gamma', False):
+    flags |= _lib.CTRL_FIXED_GAMMA
+  gates = 'ifou'
+  dw = {'lstm_wx': _g(np.stack([w['ctrl_lstm_w_x' + g] for g in gates])),
+        'lstm_wh': _g(np.stack([w['ctrl_lstm_w_h' + g] for g in gates])),
+        'lstm_b': _g(np.stack([w['ctrl_lstm_b_' + g] for g in gates])),
+        'gmlp_w0': _g(w['glimpse_mlp_w_0']), 'gmlp_b0': _g(w['glimpse_mlp_b_0']), 'gmlp_w1': _g(w['glimpse_mlp_w_1']),
+        'gmlp_b1': _g(w['glimpse_mlp_b_1']), 'cmlp_w': _g(w['ctrl_mlp_w_0']), 'cmlp_b': _g(w['ctrl_mlp_b_0'])}
+  order = ('lstm_wx', 'lstm_wh', 'lstm_b', 'gmlp_w0', 'gmlp_b0', 'gmlp_w1', 'gmlp_b1', 'cmlp_w', 'cmlp_b')
+  h_fwd, ctrl_fwd, _, box = ops.controller_step(_g(feat_np), *[dw[k] for k in order], H, W, opt['filter_height'],
+                                                opt['filter_width'], flags)
+  d_box = _g(np.concatenate([r['ctr'], r['size'], r['lg_var']], 1))
+  out = ops.controller_bwd(_g(feat_np), box, *[dw[k] for k in order], H, W, flags, d_box, _g(rg), d_h=_g(r['h']))
+  torch.cuda.synchronize()
+  # the tape's forward = the oracle's = the production kernel's
+  assert rel_err(out['h'].cpu().numpy(), c['h'].detach().numpy()) < 1e-4
+  assert rel_err(out['h'].cpu().numpy(), h_fwd.cpu().numpy()) < 1e-4
+  assert rel_err(out['ctrl_out'].cpu().numpy(), ctrl_fwd.cpu().numpy()) < 1e-4
+  tol = 1e-3
+  assert rel_err(out['d_feat'].cpu().numpy(), ref['feat']) < tol
+  for gi, g in enumerate(gates):
+    assert rel_err(out['lstm_wx'][gi].cpu().numpy(), ref['ctrl_lstm_w_x' + g]) < tol, g
+    assert rel_err(out['lstm_wh'][gi].cpu().numpy(), ref['ctrl_lstm_w_h' + g]) < tol, g
+    assert rel_err(out['lstm_b'][gi].cpu().numpy(), ref['ctrl_lstm_b_' + g]) < tol, g
+  for ours, theirs in (('gmlp_w0', 'glimpse_mlp_w_0'), ('gmlp_b0', 'glimpse_mlp_b_0'), ('gmlp_w1', 'glimpse_mlp_w_1'),
+                       ('gmlp_b1', 'glimpse_mlp_b_1'), ('cmlp_w', 'ctrl_mlp_w_0'), ('cmlp_b', 'ctrl_mlp_b_0')):
+    assert rel_err(out[ours].cpu().numpy(), ref[theirs]) < tol, ours
