@@ -21,6 +21,11 @@ from . import hungarian as _hung
 
 BN_EPS = 1e-3  # nnlib.py:119
 
+# Optional recording of forward intermediates for oracle/backward_manual.py (the executable spec of the backward
+# assembly): when TAPE is a dict, conv layers record their input / skip / pre-BN output / batch statistics under
+# (scope, layer, copy) and full_model_forward records one dict per decode step under ('step', tt).
+TAPE = None
+
 
 # ----------------------------------------------------------------------------- nnlib.py
 def conv2d_same(x, w, b):
@@ -112,7 +117,9 @@ def _batch_norm(y, weights, scope, layer, copy, ema_out):
   p = _bn(weights, scope, layer, copy)
   if ema_out is None:
     return batch_norm_eval(y, p)
-  normed, _, _, new_mean, new_var = batch_norm_train(y, p)
+  normed, b_mean, b_var, new_mean, new_var = batch_norm_train(y, p)
+  if TAPE is not None:
+    TAPE.setdefault((scope, layer, copy), {}).update(raw=y.detach(), mean=b_mean.detach(), var=b_var.detach())
   k = '{}_{}_{}_'.format(scope, layer, copy)
   ema_out[k + 'ema_mean'] = new_mean
   ema_out[k + 'ema_var'] = new_var
@@ -124,6 +131,8 @@ def run_cnn(x, weights, scope, nlayers, pool, copy, ema_out=None):
   h = []
   for ii in range(nlayers):
     inp = x if ii == 0 else h[-1]
+    if TAPE is not None:
+      TAPE.setdefault((scope, ii, copy), {}).update(x=inp.detach(), skip=None)
     y = conv2d_same(inp, weights['{}_w_{}'.format(scope, ii)], weights['{}_b_{}'.format(scope, ii)])
     y = _batch_norm(y, weights, scope, ii, copy, ema_out)
     y = torch.relu(y)
@@ -139,6 +148,9 @@ def run_dcnn(x, weights, scope, nlayers, unpool, copy, skip=None, ema_out=None):
   h = []
   for ii in range(nlayers):
     inp = x if ii == 0 else h[-1]
+    if TAPE is not None:
+      has = skip is not None and skip[ii] is not None
+      TAPE.setdefault((scope, ii, copy), {}).update(x=inp.detach(), skip=skip[ii].detach() if has else None)
     if skip is not None and skip[ii] is not None:
       inp = torch.cat([inp, skip[ii]], 3)
     y = conv2d_transpose_same(inp, weights['{}_w_{}'.format(scope, ii)], weights['{}_b_{}'.format(scope, ii)],
@@ -570,6 +582,14 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False, d
       y_gtm = (y_gtm - y_gtm * segm_noise[:, tt]).reshape(B, H, W, 1)
       ks = knob_segm[:, tt].view(B, 1, 1, 1)
       y_canvas = ks * y_gtm + (1.0 - ks) * y_canvas
+    if TAPE is not None:
+      det = lambda v: v.detach() if isinstance(v, torch.Tensor) else v
+      TAPE[('step', tt)] = {k: det(v) for k, v in dict(
+          ccnn_inp=ccnn_inp, acnn_inp=acnn_inp, feat=c['h_ccnn'][-1], ctrl_out=c['ctrl_out'], h=c['h'],
+          ctr_ctrl=c['ctr'], size_ctrl=c['size'], lg_var=c['lg_var'], lg_gamma=c['lg_gamma'],
+          box_lg_gamma=c['box_lg_gamma'], y_lg_gamma=c['y_lg_gamma'], ctr=ctr, size=size, f_y=f_y, f_x=f_x,
+          kb=(knob_box[:, tt:tt + 1] if use_knob else None), x_patch=x_patch, h_core=h_core,
+          y_patch=h_adcnn[-1], y_out=y, attn_box=box, s_out=s).items()}
     canvas = torch.maximum(y_canvas, canvas)  # full_model.py:843-845
     if _opt(opt, 'stop_canvas_grad', True):
       canvas = canvas.detach()  # tf.stop_gradient, full_model.py:846-848
