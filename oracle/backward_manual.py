@@ -284,11 +284,11 @@ def full_model_backward(opt, weights, batch, draws=None, dtype=np.float32, model
   match, match_box = _np(out['match']).astype(dtype), _np(out['match_box']).astype(dtype)
   d_y = iou_loss_bwd(_np(out['y_out']).astype(dtype), y_gt, match)
   use_knob = 'iou_soft_box_steps' in out
-  if use_knob:
-    # box loss on the per-step IoUs of the decode loop (full_model.py:926-929): iou[b,t,m] = f_iou(attn_box_t, box_gt_m)
-    # - the same derivative with the CLEAN GT boxes of the knob; with use_iou_box it has no gradient path to attn_box
-    # (coordinates only; f_iou_box of (ctr, size) is differentiable in the reference but feeds a constant matching... )
-    raise NotImplementedError('manual backward: use_knob box loss path is specified in DESIGN.md, not assembled here')
+  if use_knob and opt.get('use_iou_box', False):
+    # the box loss then runs on modellib.f_iou_box of the controller's (ctr, size): a coordinate-only gradient path
+    raise NotImplementedError('manual backward: the use_iou_box form of the knob box loss is not assembled here')
+  # with use_knob the box loss uses the per-step IoUs of the decode loop (full_model.py:926-929): the same soft IoU of
+  # attn_box[t] against the same clean GT boxes (identical get_gt_box arguments, :561-567), so the same derivative
   box_gt = _np(out['attn_box_gt']).astype(dtype)
   d_box_out = iou_loss_bwd(_np(out['attn_box']).astype(dtype), box_gt, match_box)
   d_s = conf_loss_bwd(_np(out['s_out']).astype(dtype), match, scale=opt['loss_mix_ratio'])
@@ -302,9 +302,17 @@ def full_model_backward(opt, weights, batch, draws=None, dtype=np.float32, model
     g_attn, g_box, g_y = np.exp(st['lg_gamma'][:, 0]), np.exp(st['box_lg_gamma'][:, 0]), np.exp(st['y_lg_gamma'][:, 0])
     # mask write: y_out = sigmoid(g_y * Fy P Fx^T - 5)
     d_P, d_fy, d_fx, dg_y = paste_back_bwd(d_y[:, tt], st['y_out'][:, 0], st['y_patch'][..., 0], f_y, f_x, g_y)
-    # attention box (its filters are the same here: use_knob is off)
-    _, d_fy_b, d_fx_b, dg_box = paste_back_bwd(d_box_out[:, tt], st['attn_box'][:, 0], None, f_y, f_x, g_box)
-    d_fy, d_fx = d_fy + d_fy_b, d_fx + d_fx_b
+    # attention box: written from the controller's OWN box, before the scheduled-sampling mix (full_model.py:738-741)
+    if use_knob:
+      to_t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+      f_y0 = _np(model_module.get_gaussian_filter(to_t(st['ctr_ctrl'][:, 0]), to_t(st['size_ctrl'][:, 0]),
+                                                  to_t(st['lg_var'][:, 0]), H, opt['filter_height'])).astype(dtype)
+      f_x0 = _np(model_module.get_gaussian_filter(to_t(st['ctr_ctrl'][:, 1]), to_t(st['size_ctrl'][:, 1]),
+                                                  to_t(st['lg_var'][:, 1]), W, opt['filter_width'])).astype(dtype)
+      _, d_fy0, d_fx0, dg_box = paste_back_bwd(d_box_out[:, tt], st['attn_box'][:, 0], None, f_y0, f_x0, g_box)
+    else:
+      _, d_fy_b, d_fx_b, dg_box = paste_back_bwd(d_box_out[:, tt], st['attn_box'][:, 0], None, f_y, f_x, g_box)
+      d_fy, d_fx = d_fy + d_fy_b, d_fx + d_fx_b
     # deconv mask head, last layer first; skips hand their share back to the attention CNN / the glimpse
     d_skip = {}
     dcur = d_P[..., None]
@@ -362,6 +370,17 @@ def full_model_backward(opt, weights, batch, draws=None, dtype=np.float32, model
     for axis, (filt, dfilt) in enumerate(((f_y, d_fy), (f_x, d_fx))):
       dc_, ds_, dv_ = filters_bwd(st['ctr'][:, axis], st['size'][:, axis], st['lg_var'][:, axis], filt, dfilt)
       d_box6[:, 0 + axis], d_box6[:, 2 + axis], d_box6[:, 4 + axis] = dc_, ds_, dv_
+    if use_knob:
+      # ctr = kb * ctr_gt + (1 - kb) * ctr_ctrl (same for size; lg_var is not mixed, full_model.py:760-776): the mixed
+      # box passes (1 - kb) of its centre / size gradient on; the pre-mix filters of the attention box add theirs
+      keep = 1.0 - st['kb']  # [B,1]
+      d_box6[:, 0:2] *= keep
+      d_box6[:, 2:4] *= keep
+      for axis, (filt, dfilt) in enumerate(((f_y0, d_fy0), (f_x0, d_fx0))):
+        dc_, ds_, dv_ = filters_bwd(st['ctr_ctrl'][:, axis], st['size_ctrl'][:, axis], st['lg_var'][:, axis], filt, dfilt)
+        d_box6[:, 0 + axis] += dc_
+        d_box6[:, 2 + axis] += ds_
+        d_box6[:, 4 + axis] += dv_
     # controller
     feat4 = st['feat']
     feat = feat4.reshape(B, -1, feat4.shape[3])

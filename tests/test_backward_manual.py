@@ -12,19 +12,26 @@ from oracle import backward_manual as BM
 from oracle import grads as OG
 
 
-@pytest.mark.parametrize('arch,H,W', [('cvppp', 64, 64), ('kitti', 64, 64)])
-def test_manual_backward_equals_autograd(arch, H, W):
+@pytest.mark.parametrize('arch,H,W,knob', [('cvppp', 64, 64, False), ('kitti', 64, 64, False), ('kitti', 64, 64, True)])
+def test_manual_backward_equals_autograd(arch, H, W, knob):
   T, B = 2, 2
-  opt = ra.config.full_model_opt(arch, H, W, T, use_knob=False)
+  opt = ra.config.full_model_opt(arch, H, W, T, use_knob=knob)
   batch = ra.synthetic.make_batch(opt, B, seed=21)
   weights = ra.synthetic.make_weights(opt, seed=4321)
+  d64 = None
+  if knob:  # scheduled sampling with both branches of both switches present
+    draws = ra.synthetic.make_knob_draws(opt, B, global_step=9000, seed=3)
+    draws['gt_knob_box'][:, 0], draws['gt_knob_box'][:, 1] = [1, 0], [0, 1]
+    draws['gt_knob_segm'][:, 0] = [0, 1]
+    d64 = {k: np.asarray(v, np.float64) for k, v in draws.items()}
   O64 = oracle_fp64()
   w64 = {k: np.asarray(v, np.float64) for k, v in weights.items()}
   b64 = {k: np.asarray(v, np.float64) for k, v in batch.items()}
   torch.set_default_dtype(torch.float64)
   try:
-    ref, _ = OG.full_model_grads(opt, w64, b64, include_weight_decay=False, model_module=O64, dtype=torch.float64)
-    got, out = BM.full_model_backward(opt, w64, b64, dtype=np.float64, model_module=O64)
+    ref, _ = OG.full_model_grads(opt, w64, b64, draws=d64, include_weight_decay=False, model_module=O64,
+                                 dtype=torch.float64)
+    got, out = BM.full_model_backward(opt, w64, b64, draws=d64, dtype=np.float64, model_module=O64)
   finally:
     torch.set_default_dtype(torch.float32)
   assert set(got) == set(ref), sorted(set(ref) ^ set(got))[:8]
