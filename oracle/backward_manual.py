@@ -162,6 +162,33 @@ def filters_bwd(ctr, size, lg_var, filt, d_filt):
   return dmu.sum(axis=(1, 2)), (dmu * tap / F).sum(axis=(1, 2)), (t * (d * d / (2.0 * s2) - 0.5)).sum(axis=(1, 2))
 
 
+def iou_box_coord_bwd(ctr, size, tl_gt, br_gt, wgt):
+  """Gradient of sum_m wgt[b,m] * modellib.f_iou_box(box_b, gt_m) (modellib.py:206-238) w.r.t. the box centre and
+  size [B,2] (tl = ctr - size/2, br = ctr + size/2).  No CUDA twin yet: a [B,T] elementwise pass."""
+  tl, br = (ctr - size / 2.0)[:, None, :], (ctr + size / 2.0)[:, None, :]  # [B,1,2]
+  lo, hi = np.maximum(tl, tl_gt), np.minimum(br, br_gt)  # [B,M,2]
+  ext = hi - lo
+  flag = (ext[..., 0] > 0) & (ext[..., 1] > 0)
+  inter = np.where(flag, ext[..., 0] * ext[..., 1], 0.0)
+  area_a = (br - tl)[..., 0] * (br - tl)[..., 1]
+  area_b = (br_gt - tl_gt)[..., 0] * (br_gt - tl_gt)[..., 1]
+  union = area_a + area_b - inter
+  d_iou = wgt
+  d_inter = d_iou * (1.0 / union + inter / union**2)  # d(I/U)/dI with U = A + B - I
+  d_area_a = -d_iou * inter / union**2
+  d_tl, d_br = np.zeros(tl.shape[:1] + (2,), ctr.dtype), np.zeros(tl.shape[:1] + (2,), ctr.dtype)
+  for ax in range(2):
+    other = 1 - ax
+    d_ext = np.where(flag, d_inter * ext[..., other], 0.0)  # [B,M]
+    # hi = min(br, br_gt), lo = max(tl, tl_gt): the gradient goes to the box only where the box is the binding side
+    d_br[:, ax] += (d_ext * (br[..., ax] <= br_gt[..., ax])).sum(axis=1)
+    d_tl[:, ax] += (-d_ext * (tl[..., ax] >= tl_gt[..., ax])).sum(axis=1)
+    side = (br - tl)[..., other]  # [B,1]
+    d_br[:, ax] += (d_area_a * side).sum(axis=1)
+    d_tl[:, ax] += (-d_area_a * side).sum(axis=1)
+  return d_tl + d_br, (d_br - d_tl) / 2.0
+
+
 # ----------------------------------------------------------------------------- controller  (csrc/ctrl_bwd.cu)
 def _sig(x):
   return 1.0 / (1.0 + np.exp(-x))
@@ -284,13 +311,18 @@ def full_model_backward(opt, weights, batch, draws=None, dtype=np.float32, model
   match, match_box = _np(out['match']).astype(dtype), _np(out['match_box']).astype(dtype)
   d_y = iou_loss_bwd(_np(out['y_out']).astype(dtype), y_gt, match)
   use_knob = 'iou_soft_box_steps' in out
-  if use_knob and opt.get('use_iou_box', False):
-    # the box loss then runs on modellib.f_iou_box of the controller's (ctr, size): a coordinate-only gradient path
-    raise NotImplementedError('manual backward: the use_iou_box form of the knob box loss is not assembled here')
+  coord_box_loss = use_knob and bool(opt.get('use_iou_box', False))
   # with use_knob the box loss uses the per-step IoUs of the decode loop (full_model.py:926-929): the same soft IoU of
-  # attn_box[t] against the same clean GT boxes (identical get_gt_box arguments, :561-567), so the same derivative
+  # attn_box[t] against the same clean GT boxes (identical get_gt_box arguments, :561-567), so the same derivative -
+  # unless use_iou_box, where those IoUs are modellib.f_iou_box of the controller's (ctr, size): the attention box
+  # then gets no gradient and the box loss reaches the controller through the coordinates (iou_box_coord_bwd below)
   box_gt = _np(out['attn_box_gt']).astype(dtype)
-  d_box_out = iou_loss_bwd(_np(out['attn_box']).astype(dtype), box_gt, match_box)
+  if coord_box_loss:
+    d_box_out = np.zeros_like(_np(out['attn_box']).astype(dtype))
+    tl_gt, br_gt = _np(out['attn_top_left_gt']).astype(dtype), _np(out['attn_bot_right_gt']).astype(dtype)
+    cnt_box = np.maximum(match_box.sum(axis=(1, 2)), 1.0)
+  else:
+    d_box_out = iou_loss_bwd(_np(out['attn_box']).astype(dtype), box_gt, match_box)
   d_s = conf_loss_bwd(_np(out['s_out']).astype(dtype), match, scale=opt['loss_mix_ratio'])
   grads = {}
   n_c, n_a, n_d = len(opt['ctrl_cnn_filter_size']), len(opt['attn_cnn_filter_size']), len(opt['attn_dcnn_filter_size'])
@@ -381,6 +413,12 @@ def full_model_backward(opt, weights, batch, draws=None, dtype=np.float32, model
         d_box6[:, 0 + axis] += dc_
         d_box6[:, 2 + axis] += ds_
         d_box6[:, 4 + axis] += dv_
+      if coord_box_loss:
+        # box loss = -(1/B) sum_b 1/cnt_b sum_m match_box[b,t,m] * f_iou_box(box_t, gt_m): weights of this step's row
+        wgt = -match_box[:, tt, :] / (B * cnt_box[:, None])
+        dctr, dsize = iou_box_coord_bwd(st['ctr_ctrl'], st['size_ctrl'], tl_gt, br_gt, wgt)
+        d_box6[:, 0:2] += dctr
+        d_box6[:, 2:4] += dsize
     # controller
     feat4 = st['feat']
     feat = feat4.reshape(B, -1, feat4.shape[3])

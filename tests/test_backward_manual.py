@@ -12,7 +12,8 @@ from oracle import backward_manual as BM
 from oracle import grads as OG
 
 
-@pytest.mark.parametrize('arch,H,W,knob', [('cvppp', 64, 64, False), ('kitti', 64, 64, False), ('kitti', 64, 64, True)])
+@pytest.mark.parametrize('arch,H,W,knob', [('cvppp', 64, 64, False), ('kitti', 64, 64, False), ('kitti', 64, 64, True),
+                                          ('cityscapes', 64, 64, True)])  # Cityscapes: use_iou_box, fixed gamma
 def test_manual_backward_equals_autograd(arch, H, W, knob):
   T, B = 2, 2
   opt = ra.config.full_model_opt(arch, H, W, T, use_knob=knob)
@@ -70,3 +71,25 @@ def test_block_functions_match_autograd_in_isolation():
   Lc = OM.f_conf_loss(s, mt.float().double())
   gs, = torch.autograd.grad(Lc, [s])
   assert np.allclose(BM.conf_loss_bwd(s.detach().numpy(), match, 1.0), gs.numpy(), atol=1e-12)
+
+
+def test_iou_box_coordinate_gradient():
+  """modellib.f_iou_box (the use_iou_box box loss of the scheduled-sampling mode) differentiated by hand vs autograd,
+  on boxes that overlap their targets partially, fully and not at all."""
+  from oracle import model as OM
+  rng = np.random.default_rng(4)
+  B, M = 5, 6
+  ctr = torch.tensor(rng.uniform(20, 40, (B, 2)), requires_grad=True)
+  size = torch.tensor(rng.uniform(10, 30, (B, 2)), requires_grad=True)
+  tl_gt = rng.uniform(0, 40, (B, M, 2))
+  br_gt = tl_gt + rng.uniform(5, 40, (B, M, 2))
+  tl_gt[0, 0], br_gt[0, 0] = [0.0, 0.0], [100.0, 100.0]   # contains the box
+  tl_gt[1, 1], br_gt[1, 1] = [200.0, 200.0], [210.0, 210.0]  # disjoint
+  wgt = rng.standard_normal((B, M))
+  iou = OM.f_iou_box((ctr - size / 2).unsqueeze(1), (ctr + size / 2).unsqueeze(1), torch.from_numpy(tl_gt),
+                     torch.from_numpy(br_gt))
+  assert float((iou.detach() > 0).double().mean()) > 0.5 and float(iou.detach()[1, 1]) == 0.0
+  gc, gs = torch.autograd.grad((iou * torch.from_numpy(wgt)).sum(), [ctr, size])
+  dctr, dsize = BM.iou_box_coord_bwd(ctr.detach().numpy(), size.detach().numpy(), tl_gt, br_gt, wgt)
+  assert np.allclose(dctr, gc.numpy(), atol=1e-12) and np.allclose(dsize, gs.numpy(), atol=1e-12)
+  assert float(np.abs(gc.numpy()).max()) > 1e-4
