@@ -194,7 +194,7 @@ class OpTimer(object):
 
 
 # --------------------------------------------------------------------------- reference arm
-def cpu_reference_time(opt, B_sample, steps, warmup, seed=1234):
+def cpu_reference_time(opt, B_sample, steps, warmup, seed=1234, model='full'):
   """The reference's CPU implementation of the path = the structure-faithful oracle
   (PyTorch-CPU restatement + C restatement of hungarian.cc), all host threads."""
   import torch
@@ -204,12 +204,13 @@ def cpu_reference_time(opt, B_sample, steps, warmup, seed=1234):
   cores = os.cpu_count() or 1
   torch.set_num_threads(cores)
   batch = synthetic.make_batch(opt, B_sample, seed=seed)
-  weights = synthetic.make_weights(opt)
+  weights = synthetic.make_weights(opt, model=model)
+  fwd = OM.box_model_forward if model == 'box' else OM.full_model_forward  # BASELINE configs[4] is the box model
   times = []
   for i in range(warmup + steps):
     t0 = time.perf_counter()
     with torch.no_grad():
-      OM.full_model_forward(opt, weights, batch)
+      fwd(opt, weights, batch)
     dt = time.perf_counter() - t0
     if i >= warmup:
       times.append(dt)
@@ -224,19 +225,22 @@ def run_reference(args):
   cfg = config.BASELINE_CONFIGS[args.config]
   opt = config.baseline_opt(args.config)
   B_sample = args.ref_batch
-  sec, cores = cpu_reference_time(opt, B_sample, max(1, args.steps), max(0, args.warmup))
+  is_box = cfg.get('model', 'full') == 'box'
+  sec, cores = cpu_reference_time(opt, B_sample, max(1, args.steps), max(0, args.warmup),
+                                  model='box' if is_box else 'full')
   masks = B_sample * cfg['T']
   val = masks / sec
+  metric, unit = ('box-steps/sec', 'box-steps/s') if is_box else ('instance-masks/sec', 'masks/s')
   line = {
-      'impl': 'reference', 'metric': 'instance-masks/sec', 'value': val, 'unit': 'masks/s', 'n_gpus': args.gpus,
+      'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': args.gpus,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
       'config': {'workload': cfg['name'], 'sample': 'B={} of the workload batch, full T={} decode + loss block'.format(
           B_sample, cfg['T'])},
-      'cpu_baseline': {'value': val, 'unit': 'masks/s', 'cores': cores, 'kind': 'port',
+      'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
                        'sample': 'oracle (PyTorch-CPU restatement + C hungarian), B={} x T={} at {}x{}'.format(
                            B_sample, cfg['T'], cfg['H'], cfg['W'])},
-      'e2e': {'value': val, 'unit': 'masks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
   emit(line)
   return 0
