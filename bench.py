@@ -406,7 +406,9 @@ def run_ours(args):
           'achieved': round(conv_tflops, 3), 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
           'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': entry_traffic(traffic, dom),
           'peak_source': peaks['source'] + ' (cuBLAS bf16 burst)',
-          'note': 'flops = the reference\'s 8 conv layers per decode step (the linear split of layer 0 does fewer)'
+          'note': 'flops = the reference\'s 8 conv layers per decode step (the linear split of layer 0 does fewer); '
+                  'the kernel issues 3 TF32 MMAs per algorithmic MAC (fp32 parity, DESIGN 4.1) and the TF32 dense rate '
+                  'is half the bf16 rate, so frac = 1/6 would be a saturated tensor pipe for this formulation'
       }
     else:
       k = kernels[dom]
