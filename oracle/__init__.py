@@ -8,8 +8,11 @@ as the timed CPU baseline.
 Parity status:
   * ``oracle.hungarian``  — PINNED by the reference's own known-answer tests
     (/root/reference/hungarian_tf_tests.py, fixtures in tests/golden/hungarian_kat.json).
-  * ``oracle.model``      — PARITY UNPINNED: the reference model graph runs only on
+  * ``oracle.model``      — the graph as a whole is PARITY UNPINNED: it runs only on
     TensorFlow 0.12 / Python 2.7, neither of which exists here, and the reference
-    ships no golden outputs for it.  It is a structure-faithful restatement
-    validated by semantic unit tests (tests/test_model_oracle.py).
+    ships no golden outputs for it; it is a structure-faithful restatement validated by
+    semantic unit tests (tests/test_model_oracle.py).  Its math library (the functions
+    restating modellib.py) IS pinned: tests/golden/make_modellib_golden.py executes the
+    reference's own modellib.py, unmodified, over a numpy stand-in for the ~30 TF ops
+    it uses, and tests/test_modellib_golden.py holds the oracle to those vectors.
 """

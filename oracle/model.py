@@ -408,14 +408,25 @@ def controller_step(opt, weights, ccnn_inp, tt, ema_out=None):
   n_c = opt['num_ctrl_mlp_layers']
   ctrl_out = run_mlp(h, weights, 'ctrl_mlp', ['relu'] * (n_c - 1) + [None])[-1]
 
+  res = {'h_ccnn': h_ccnn, 'h': h, 'ctrl_out': ctrl_out, 'glimpse_map': torch.stack(gmaps, 1)}
+  res.update(box_params(opt, ctrl_out))
+  return res
+
+
+def box_params(opt, ctrl_out):
+  """full_model.py:691-725 with modellib.py:752-856: the nine controller outputs -> box centre / size / log-variance
+  and the three log-gains."""
+  H, W = opt['inp_height'], opt['inp_width']
+  Fh, Fw = opt['filter_height'], opt['filter_width']
+  B = ctrl_out.shape[0]
   ctr_norm = ctrl_out[:, 0:2]
   lg_size = ctrl_out[:, 2:4]
   if opt['squash_ctrl_params']:
     ctr_norm = torch.tanh(ctr_norm)
     lg_size = -F.softplus(lg_size)
   img_size = torch.tensor([H, W], dtype=torch.float32)
-  ctr = (ctr_norm + 1.0) * (img_size / 2.0)  # modellib.py:752-764
-  size = torch.exp(lg_size) * img_size  # modellib.py:812-825
+  ctr = (ctr_norm + 1.0) * (img_size / 2.0)  # modellib.get_unnormalized_center, modellib.py:752-764
+  size = torch.exp(lg_size) * img_size  # modellib.get_unnormalized_size, modellib.py:812-825
   if opt['fixed_var']:
     lg_var = torch.zeros(B, 2)
   else:
@@ -429,11 +440,8 @@ def controller_step(opt, weights, ccnn_inp, tt, ema_out=None):
     lg_gamma = ctrl_out[:, 6:7]
     y_lg_gamma = ctrl_out[:, 8:9]
   box_lg_gamma = ctrl_out[:, 7:8]
-  return {
-      'h_ccnn': h_ccnn, 'h': h, 'ctrl_out': ctrl_out, 'glimpse_map': torch.stack(gmaps, 1), 'ctr_norm': ctr_norm,
-      'lg_size': lg_size, 'ctr': ctr, 'size': size, 'lg_var': lg_var, 'lg_gamma': lg_gamma,
-      'box_lg_gamma': box_lg_gamma, 'y_lg_gamma': y_lg_gamma
-  }
+  return {'ctr_norm': ctr_norm, 'lg_size': lg_size, 'ctr': ctr, 'size': size, 'lg_var': lg_var, 'lg_gamma': lg_gamma,
+          'box_lg_gamma': box_lg_gamma, 'y_lg_gamma': y_lg_gamma}
 
 
 def top_left_pred(ctr, size):
