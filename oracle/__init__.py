@@ -8,11 +8,12 @@ as the timed CPU baseline.
 Parity status:
   * ``oracle.hungarian``  — PINNED by the reference's own known-answer tests
     (/root/reference/hungarian_tf_tests.py, fixtures in tests/golden/hungarian_kat.json).
-  * ``oracle.model``      — the graph as a whole is PARITY UNPINNED: it runs only on
-    TensorFlow 0.12 / Python 2.7, neither of which exists here, and the reference
-    ships no golden outputs for it; it is a structure-faithful restatement validated by
-    semantic unit tests (tests/test_model_oracle.py).  Its math library (the functions
-    restating modellib.py) IS pinned: tests/golden/make_modellib_golden.py executes the
-    reference's own modellib.py, unmodified, over a numpy stand-in for the ~30 TF ops
-    it uses, and tests/test_modellib_golden.py holds the oracle to those vectors.
+  * ``oracle.model``      — PINNED TO THE REFERENCE'S OWN PYTHON SOURCE for the full model:
+    TensorFlow 0.12 / Python 2.7 cannot run here, but full_model.py / nnlib.py /
+    modellib.py / image_ops.py parse as Python 3, so tests/golden/make_*_golden.py execute
+    them UNMODIFIED over a numpy stand-in for the TensorFlow-0.12 ops they use
+    (tests/golden/tf012_shim) and the oracle must reproduce the results
+    (full_model.get_model end to end to 1e-7 in float64; nnlib layer factories; modellib
+    function by function).  On trust: TensorFlow's own kernel semantics, one line each in
+    the shim.  box_model_forward / fg_model_forward: restated, not pinned this way yet.
 """

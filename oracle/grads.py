@@ -8,8 +8,8 @@ to the optimiser block and the resulting update (full_model.py:1039-1057; Traine
 The forward graph is oracle.model.full_model_forward(phase_train=True) — batch-statistics BN (differentiated through
 the moments like tf.nn.moments), scheduled sampling with the draws as inputs, tf.stop_gradient on the canvas
 (full_model.py:846-848), no gradient through the Hungarian op (modellib.py:11) — and torch.autograd stands in for
-TensorFlow's autodiff of the same graph.  PARITY UNPINNED like the rest of oracle.model (TensorFlow 0.12 cannot run
-here); the gradients are pinned to the forward oracle itself by central differences in float64
+TensorFlow's autodiff of the same graph.  The forward graph is pinned to the reference's own source (see oracle/model.py); TensorFlow's
+autodiff itself cannot run here, so the gradients are pinned to that forward by central differences in float64
 (tests/test_train_step_oracle.py).
 
 The CUDA backward pass does not exist yet; this module is the checker it will be built against, and

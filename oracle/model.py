@@ -1,15 +1,25 @@
 """CPU oracle of the recurrent-attention model graph — TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference graph (full_model.py / box_model.py / modellib.py /
-nnlib.py) runs only on TensorFlow 0.12 + Python 2.7, neither available here, and the
-reference ships no golden outputs for it.  This is a structure-faithful PyTorch-CPU fp32
-restatement: same T-step loop, same per-channel ``bmm`` pair in ``extract_patch``, same
-T-way pairwise-IoU loop, TF 'SAME' padding, TF ``conv2d_transpose`` cropping, per
-(layer, timestep) batch-norm copies, sequential Hungarian (oracle/hungarian_ref.c).
+A structure-faithful PyTorch-CPU fp32 restatement of the reference model graph (full_model.py / box_model.py /
+modellib.py / nnlib.py): same T-step loop, same per-channel ``bmm`` pair in ``extract_patch``, same T-way
+pairwise-IoU loop, TF 'SAME' padding, TF ``conv2d_transpose`` cropping, per (layer, timestep) batch-norm copies,
+sequential Hungarian (oracle/hungarian_ref.c).
+
+PARITY STATUS: TensorFlow 0.12 + Python 2.7 cannot run here and the reference ships no golden outputs for the graph,
+but its .py files parse as Python 3, so they are EXECUTED AS THEY ARE over a numpy stand-in for the TensorFlow-0.12 ops
+they use (tests/golden/tf012_shim) and this module is held to the results (tests/golden/make_*_golden.py ->
+tests/test_modellib_golden.py, test_nnlib_golden.py, test_full_model_golden.py):
+  * full_model_forward == the reference's own full_model.get_model(opt) to 1e-7 in float64 - three architectures,
+    training mode, with and without scheduled sampling (the graph's random draws replayed), incl. use_iou_box;
+  * the layer functions == the reference's nn.cnn / nn.dcnn / nn.mlp / nn.lstm / batch_norm (train and eval);
+  * the math library == the reference's modellib.py function by function.
+What remains on trust is TensorFlow's own kernel semantics (SAME padding, conv2d_transpose cropping, softmax ...): the
+shim states each in one line of numpy / torch.  box_model_forward and fg_model_forward are NOT pinned this way yet
+(box_model.py is the same graph minus the mask branch; fg_model.py imports a module the reference does not ship).
 
 Layouts follow the reference: images/features NHWC, mask stacks [B,T,H,W].
 Every function cites the reference lines it restates (paths relative to /root/reference).
-Only eval mode (``phase_train=False``) plus explicitly supplied random draws is covered.
+Eval mode (``phase_train=False``) and training mode with explicitly supplied random draws are covered.
 """
 import math
 

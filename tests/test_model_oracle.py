@@ -1,6 +1,7 @@
-"""CPU semantic tests of the model oracle (oracle/model.py).  The model graph is PARITY UNPINNED
-(no TensorFlow 0.12 here, no golden outputs in the reference), so every TF-specific semantic the
-restatement relies on is checked against an independent numpy formulation."""
+"""CPU semantic tests of the model oracle (oracle/model.py).  TensorFlow 0.12 cannot run here; the
+oracle is pinned to the reference's own source through the shim-executed golden vectors (tests/test_*_golden.py), and
+every TF-specific kernel semantic that pinning takes on trust is checked here against an independent
+numpy formulation."""
 import numpy as np
 import pytest
 import torch
