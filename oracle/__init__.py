@@ -15,5 +15,6 @@ Parity status:
     (tests/golden/tf012_shim) and the oracle must reproduce the results
     (full_model.get_model end to end to 1e-7 in float64; nnlib layer factories; modellib
     function by function).  On trust: TensorFlow's own kernel semantics, one line each in
-    the shim.  box_model_forward / fg_model_forward: restated, not pinned this way yet.
+    the shim.  box_model_forward is pinned the same way (the reference's box_model.get_model);
+    fg_model_forward is restated only (fg_model.py imports a module the reference lacks).
 """

@@ -14,8 +14,9 @@ tests/test_modellib_golden.py, test_nnlib_golden.py, test_full_model_golden.py):
   * the layer functions == the reference's nn.cnn / nn.dcnn / nn.mlp / nn.lstm / batch_norm (train and eval);
   * the math library == the reference's modellib.py function by function.
 What remains on trust is TensorFlow's own kernel semantics (SAME padding, conv2d_transpose cropping, softmax ...): the
-shim states each in one line of numpy / torch.  box_model_forward and fg_model_forward are NOT pinned this way yet
-(box_model.py is the same graph minus the mask branch; fg_model.py imports a module the reference does not ship).
+shim states each in one line of numpy / torch.  box_model_forward is pinned the same way (the reference's own
+box_model.get_model, training mode, with and without use_iou_box).  fg_model_forward is restated only: fg_model.py
+imports a module (image_ops_old) the reference does not ship, so it cannot be executed as it is.
 
 Layouts follow the reference: images/features NHWC, mask stacks [B,T,H,W].
 Every function cites the reference lines it restates (paths relative to /root/reference).
@@ -703,8 +704,9 @@ def full_model_loss(opt, weights, model, y_gt, s_gt):
   return r
 
 
-def box_model_forward(opt, weights, batch, canvas_noise=None):
-  """box_model.get_model (box_model.py:403-629) in eval mode.  The canvas is driven by the
+def box_model_forward(opt, weights, batch, canvas_noise=None, phase_train=False):
+  """box_model.get_model (box_model.py:403-629), eval mode or - phase_train=True - with batch-statistics BN.  The
+  canvas is driven by the
   greedily matched GT masks in eval too (:484-504); the per-step U[0,0.3) noise (:501-502)
   is an explicit input ``canvas_noise`` [B,T,H,W] (zeros when None)."""
   weights = {k: _t(v) for k, v in weights.items()}
@@ -725,6 +727,7 @@ def box_model_forward(opt, weights, batch, canvas_noise=None):
 
   tl_gt, br_gt, box_gt = get_gt_box(y_gt, padding_ratio=opt['attn_box_padding_ratio'], center_shift_ratio=0.0)
   canvas = torch.zeros(B, H, W, 1)
+  ema_out = {} if phase_train else None  # training mode: batch-statistics BN (nnlib.py:96-119)
   grd_match_cum = torch.zeros(B, T)  # never updated (box_model.py:398,496)
   out = {k: [] for k in ('s_out', 'attn_box', 'attn_ctr', 'attn_size', 'attn_top_left', 'attn_bot_right',
                          'iou_soft_box', 'glimpse_map', 'ctrl_out')}
@@ -733,7 +736,7 @@ def box_model_forward(opt, weights, batch, canvas_noise=None):
     if add_d_out:
       lst += [d_in, y_in]
     ccnn_inp = torch.cat(lst, 3)
-    c = controller_step(opt, weights, ccnn_inp, tt)
+    c = controller_step(opt, weights, ccnn_inp, tt, ema_out=ema_out)
     box, _, _ = attn_box_from(opt, c['ctr'], c['size'], c['lg_var'], c['box_lg_gamma'])
     if _opt(opt, 'use_iou_box', False):
       tl, br = c['ctr'] - c['size'] / 2.0, c['ctr'] + c['size'] / 2.0

@@ -71,3 +71,34 @@ def test_oracle_equals_the_reference_graph(name):
     assert rel(o[k].numpy(), ref(k)) < tol, (k, rel(o[k].numpy(), ref(k)))
   assert float(ref('learn_rate')) == pytest.approx(
       opt['base_learn_rate'] * opt['learn_rate_decay']**(meta['global_step'] // opt['steps_per_learn_rate_decay']), rel=1e-6)
+
+
+GB = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'box_model_golden.npz'))
+
+
+@pytest.mark.parametrize('name', sorted({k.split('/')[0] for k in GB.files}))
+def test_box_oracle_equals_the_reference_graph(name):
+  """oracle.model.box_model_forward against the reference's own box_model.get_model(opt) executed over the shim
+  (tests/golden/make_box_model_golden.py), float64, training mode, the graph's canvas noise replayed."""
+  meta = json.loads(str(GB[name + '/meta']))
+  opt = ra.config.box_model_opt(meta['H'], meta['W'], meta['T'], **meta['overrides'])
+  batch = {k: np.asarray(v, np.float64) for k, v in ra.synthetic.make_batch(opt, meta['B'], seed=meta['batch_seed']).items()}
+  w = {k: np.asarray(v, np.float64)
+       for k, v in ra.synthetic.make_weights(opt, seed=meta['weight_seed'], model='box').items()}
+  assert sum(float(np.abs(v).sum()) for v in w.values()) == pytest.approx(float(GB[name + '/weights_checksum']), rel=1e-12)
+  O64 = oracle_fp64()
+  torch.set_default_dtype(torch.float64)
+  try:
+    with torch.no_grad():
+      o = O64.box_model_forward(opt, w, batch, canvas_noise=GB[name + '/draw_canvas_noise'].astype(np.float64),
+                                phase_train=True)
+  finally:
+    torch.set_default_dtype(torch.float32)
+  assert np.array_equal(o['match_box'].numpy(), GB[name + '/match_box'])
+  for k in ('loss', 'box_loss', 'conf_loss'):
+    assert float(o[k]) == pytest.approx(float(GB['%s/%s' % (name, k)]), rel=1e-7, abs=1e-9), k
+  for k in ('attn_box', 's_out', 'attn_ctr', 'attn_size', 'attn_top_left', 'attn_bot_right', 'attn_top_left_gt',
+            'attn_bot_right_gt', 'ctrl_rnn_glimpse_map'):
+    ref = GB['%s/%s' % (name, k)]
+    tol = 1e-6 if ref.dtype == np.float32 else 1e-7
+    assert rel(o[k].numpy().reshape(ref.shape), ref) < tol, (k, rel(o[k].numpy().reshape(ref.shape), ref))
