@@ -15,6 +15,7 @@ Parity status:
     (tests/golden/tf012_shim) and the oracle must reproduce the results
     (full_model.get_model end to end to 1e-7 in float64; nnlib layer factories; modellib
     function by function).  On trust: TensorFlow's own kernel semantics, one line each in
-    the shim.  box_model_forward is pinned the same way (the reference's box_model.get_model);
-    fg_model_forward is restated only (fg_model.py imports a module the reference lacks).
+    the shim.  box_model_forward and fg_model_forward are pinned the same way (the reference's
+    box_model.get_model / fg_model.get_model; the latter needs its missing `image_ops_old`
+    import aliased to the reference's image_ops.py).
 """

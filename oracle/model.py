@@ -15,8 +15,9 @@ tests/test_modellib_golden.py, test_nnlib_golden.py, test_full_model_golden.py):
   * the math library == the reference's modellib.py function by function.
 What remains on trust is TensorFlow's own kernel semantics (SAME padding, conv2d_transpose cropping, softmax ...): the
 shim states each in one line of numpy / torch.  box_model_forward is pinned the same way (the reference's own
-box_model.get_model, training mode, with and without use_iou_box).  fg_model_forward is restated only: fg_model.py
-imports a module (image_ops_old) the reference does not ship, so it cannot be executed as it is.
+box_model.get_model, training mode, with and without use_iou_box), and so is fg_model_forward (the reference's
+fg_model.get_model for the three shipped FCN architectures at reduced width; fg_model.py imports `image_ops_old`,
+which the reference does not ship - the shim aliases it to the reference's image_ops.py, the only repair needed).
 
 Layouts follow the reference: images/features NHWC, mask stacks [B,T,H,W].
 Every function cites the reference lines it restates (paths relative to /root/reference).
@@ -812,9 +813,9 @@ def fg_skip_lists(opt, x, h_cnn):
   return skip
 
 
-def fg_model_forward(opt, weights, batch):
+def fg_model_forward(opt, weights, batch, phase_train=False):
   """fg_model.get_model (fg_model.py:11-245) in eval mode (phase_train=False: random_transformation is the identity
-  crop, batch norm uses the EMA shadows): CNN -> DCNN with skip concatenation (last layer: no BN, no activation,
+  crop, batch norm uses the EMA shadows) or, with phase_train=True, with batch-statistics BN and the identity crop: CNN -> DCNN with skip concatenation (last layer: no BN, no activation,
   :121,148) -> sigmoid / softmax foreground head and softmax orientation head (:174-192) -> IoU / BCE / CE losses
   (:194-236).  batch: x [B,H,W,3], y_gt [B,H,W,nsc][, d_gt [B,H,W,8]]."""
   weights = {k: _t(v) for k, v in weights.items()}
@@ -825,7 +826,8 @@ def fg_model_forward(opt, weights, batch):
   n_c, n_d = len(opt['cnn_depth']), len(opt['dcnn_depth'])
   if opt['dcnn_depth'][-1] != nsc + nori:
     raise ValueError('Expecting last channel to be {}'.format(nsc + nori))  # fg_model.py:162-172
-  h_cnn = run_cnn(x, weights, 'cnn', n_c, opt['cnn_pool'], 0)
+  ema_out = {} if phase_train else None  # training mode: batch-statistics BN
+  h_cnn = run_cnn(x, weights, 'cnn', n_c, opt['cnn_pool'], 0, ema_out=ema_out)
   skip = fg_skip_lists(opt, x, h_cnn)
   h = h_cnn[-1]
   for ii in range(n_d):  # nnlib.py:339-402 with act = [relu]*(n-1) + [None], use_bn = [True]*(n-1) + [False]
@@ -834,7 +836,7 @@ def fg_model_forward(opt, weights, batch):
       inp = torch.cat([inp, skip[ii]], 3)
     h = conv2d_transpose_same(inp, weights['dcnn_w_%d' % ii], weights['dcnn_b_%d' % ii], opt['dcnn_pool'][ii])
     if ii < n_d - 1:
-      h = torch.relu(batch_norm_eval(h, _bn(weights, 'dcnn', ii, 0)))
+      h = torch.relu(_batch_norm(h, weights, 'dcnn', ii, 0, ema_out))
   model = {'logits': h}
   y_out = h[..., :nsc]
   if ori:

@@ -211,7 +211,7 @@ def truncated_normal_initializer(stddev=1.0, seed=0):
     while bad.any():
       v[bad] = rng.standard_normal(int(bad.sum()))
       bad = np.abs(v) > 2
-    return (v * stddev).astype(F32)
+    return (v * stddev).astype(np.float32).astype(F32)  # float32-representable: fixtures store weights losslessly
 
   return init
 
@@ -464,6 +464,25 @@ class _AdamStub(object):
   def apply_gradients(self, gvs, global_step=None):
     return None
 
+  def minimize(self, loss, global_step=None):  # fg_model.py
+    return None
+
+
+class _MomentumStub(_AdamStub):
+
+  def __init__(self, learning_rate, momentum=0.9):
+    self.learning_rate = learning_rate
+
 
 _Train.exponential_decay = staticmethod(_exponential_decay)
 _Train.AdamOptimizer = _AdamStub
+_Train.MomentumOptimizer = _MomentumStub
+
+
+def argmax(x, dimension):
+  return np.argmax(np.asarray(x), axis=int(dimension))
+
+
+def squeeze(x, squeeze_dims=None):
+  return np.squeeze(np.asarray(x), axis=None if squeeze_dims is None else tuple(int(d) for d in squeeze_dims)).view(Tensor)
+

@@ -1,6 +1,7 @@
 """CPU tests of the foreground / orientation FCN restatement (oracle.model.fg_model_forward, fg_model.py:11-245) and
-of the host-side wiring tables (config.fg_model_opt / fg_skip_wiring).  PARITY UNPINNED like the rest of the model
-oracle (TensorFlow 0.12 is not runnable here; fg_model.py additionally imports a module the reference does not ship)."""
+of the host-side wiring tables (config.fg_model_opt / fg_skip_wiring).  The restatement is pinned to the
+reference's own fg_model.py executed over the TF-0.12 stand-in (last test; its missing `image_ops_old` import is
+aliased to the reference's image_ops.py)."""
 import numpy as np
 import pytest
 import torch
@@ -91,3 +92,43 @@ def test_last_layer_has_no_bn_and_no_relu():
     w2 = dict(w, dcnn_b_10=w['dcnn_b_10'] + np.float32(1.5))
     r2 = OM.fg_model_forward(opt, w2, b)
   assert torch.allclose(r2['logits'], r['logits'] + 1.5, atol=1e-5)  # the bias reaches the logits unscaled
+
+
+import json  # noqa: E402
+import os  # noqa: E402
+
+from conftest import oracle_fp64  # noqa: E402
+
+GF = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'fg_model_golden.npz'))
+
+
+@pytest.mark.parametrize('name', sorted({k.split('/')[0] for k in GF.files}))
+def test_fg_oracle_equals_the_reference_graph(name):
+  """oracle.model.fg_model_forward against the reference's OWN fg_model.get_model(opt), executed unmodified over the
+  numpy TF-0.12 stand-in (tests/golden/make_fg_model_golden.py; float64, training mode, the graph's own initial
+  weights).  Pins the FCN restatement - skip wiring incl. run_cityscapes.sh's over-long mask, last layer without BN /
+  activation, sigmoid / softmax heads, IoU / BCE / CE / orientation losses - to the reference's code."""
+  meta = json.loads(str(GF[name + '/meta']))
+  opt = ra.config.fg_model_opt(meta['arch'], meta['H'], meta['W'], **meta['overrides'])
+  opt['cnn_depth'], opt['dcnn_depth'] = meta['cnn_depth'], meta['dcnn_depth']
+  batch = {k: np.asarray(v, np.float64) for k, v in ra.synthetic.make_fg_batch(opt, meta['B'], seed=meta['batch_seed']).items()}
+  w = {k[len(name) + 3:]: GF[k].astype(np.float64) for k in GF.files if k.startswith(name + '/w/')}
+  for k in list(w):  # TensorFlow's EMA shadows of tensors start at zero (irrelevant in training mode)
+    if k.endswith('_gamma'):
+      w[k[:-5] + 'ema_mean'] = np.zeros_like(w[k])
+      w[k[:-5] + 'ema_var'] = np.zeros_like(w[k])
+  O64 = oracle_fp64()
+  torch.set_default_dtype(torch.float64)
+  try:
+    with torch.no_grad():
+      o = O64.fg_model_forward(opt, w, batch, phase_train=True)
+  finally:
+    torch.set_default_dtype(torch.float32)
+  for k in ('y_out', 'd_out', 'iou_soft', 'iou_hard', 'foreground_loss', 'orientation_ce', 'orientation_acc', 'loss'):
+    key = '%s/%s' % (name, k)
+    if key not in GF.files:
+      assert k in ('d_out', 'orientation_ce', 'orientation_acc') and not opt['add_orientation']
+      continue
+    a, b = np.asarray(o[k].numpy(), np.float64), GF[key].astype(np.float64)
+    tol = 1e-6 if GF[key].dtype == np.float32 else 1e-9
+    assert float(np.abs(a - b).max()) <= tol * max(float(np.abs(b).max()), 1e-9), (k, float(np.abs(a - b).max()))
