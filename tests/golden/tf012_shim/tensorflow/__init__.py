@@ -398,8 +398,15 @@ def placeholder(dtype, shape=None, name=None):
   return _t(value)
 
 
+RANDOM_OVERRIDES = []  # values handed out, in call order, before the generator is consulted
+
+
 def random_uniform(shape, minval=0, maxval=None, dtype='float32', seed=None, name=None):
   shp = tuple(int(s) for s in np.ravel(np.asarray(shape)))
+  if RANDOM_OVERRIDES:
+    v = np.broadcast_to(np.asarray(RANDOM_OVERRIDES.pop(0)), shp).astype(np.int32 if np.dtype(dtype).kind == 'i' else F32)
+    RANDOM_LOG.append({'shape': shp, 'min': minval, 'max': maxval, 'value': v.copy()})
+    return v.view(Tensor) if v.dtype.kind == 'f' else v
   if np.dtype(dtype).kind == 'i':
     # the only integer draw is the crop offset of image_ops.random_transformation: always the centre (identity crop)
     v = np.full(shp, int(maxval) // 2, np.int32)

@@ -94,3 +94,26 @@ def test_box_maths_filters_glimpse_and_paste_back():
         G['extract_patch'], tol=1e-5)
   close(OM.extract_patch(t('in_patch1'), t('get_gaussian_filter_y').transpose(1, 2),
                          t('get_gaussian_filter_x').transpose(1, 2), 1), G['paste_back'], tol=1e-5)
+
+
+GI = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'image_ops_golden.npz'))
+
+
+@pytest.mark.parametrize('name', sorted({k.split('/')[0] for k in GI.files}))
+def test_random_transformation_equals_the_reference(name):
+  """oracle.model.random_transformation against the reference's own image_ops.random_transformation executed over the
+  shim with chosen draws (tests/golden/make_image_ops_golden.py): crop offsets, flips, transpose, the orientation
+  mode (no flips) and the eval-mode identity (centre crop whatever the draws)."""
+  H, W, pad, oy, ox, hf, vf, tr, with_d, train = [int(v) for v in GI[name + '/params']]
+  g = lambda k: torch.from_numpy(GI['%s/%s' % (name, k)])
+  d = g('in_d') if with_d else None
+  c = g('in_c') if with_d else None
+  if train:
+    r = OM.random_transformation(g('in_x'), pad, (oy, ox), vflip=bool(vf), hflip=bool(hf), transpose=bool(tr),
+                                 y=g('in_y'), d=d, c=c)
+  else:  # phase_train = False: the centre slices, no flips (image_ops.py:70-80,106-112)
+    r = OM.random_transformation(g('in_x'), pad, (pad, pad), y=g('in_y'), d=d, c=c)
+  for k in ('x', 'y') + (('d', 'c') if with_d else ()):
+    ref = GI['%s/out_%s' % (name, k)]
+    assert tuple(r[k].shape) == ref.shape, (k, tuple(r[k].shape), ref.shape)
+    assert np.array_equal(r[k].numpy(), ref), k
