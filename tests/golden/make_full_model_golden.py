@@ -23,6 +23,9 @@ CASES = [
     ('cityscapes', 'cityscapes', 64, 64, 2, 2, {'use_knob': False}, 0),
     ('kitti_knob', 'kitti', 64, 64, 3, 3, {'use_knob': True}, 9500),
     ('cityscapes_knob_iou_box', 'cityscapes', 64, 64, 2, 3, {'use_knob': True}, 9500),
+    # phase_train = False: EMA statistics (TensorFlow's shadows of a fresh graph are ZERO, so every BN layer multiplies
+    # by gamma / sqrt(1e-3) - numerically wild but exactly defined in float64), centre crop, knob terms switched off
+    ('kitti_eval', 'kitti', 64, 64, 2, 2, {'use_knob': True, 'phase_train': False}, 9500),
 ]
 SMALL = {'ctrl_rnn_hid_dim': 32, 'ctrl_mlp_dim': 32}
 BIG = ('y_out', 'attn_box', 'y_out_patch', 'ctrl_rnn_glimpse_map')  # stored as float32 (compared at 1e-6)
@@ -47,6 +50,7 @@ def main():
   out = {}
   for name, arch, H, W, T, B, over, step in CASES:
     over = dict(SMALL, **over)
+    phase = bool(over.pop('phase_train', True))
     opt = ra.config.full_model_opt(arch, H, W, T, **over)
     batch = {k: np.asarray(v, np.float64) for k, v in ra.synthetic.make_batch(opt, B, seed=21).items()}
     w = {k: np.asarray(v, np.float64) for k, v in ra.synthetic.make_weights(opt, seed=4321).items()}
@@ -55,19 +59,20 @@ def main():
     feed = [('x', batch['x']), ('y_gt', batch['y_gt']), ('s_gt', batch['s_gt'])]
     if opt.get('add_d_out', False):
       feed += [('d_in', batch['d_in']), ('y_in', batch['y_in'])]
-    feed.append(('phase_train', True))
+    feed.append(('phase_train', phase))
     tf.reset(feed, seed=7)
     tf.VARIABLE_OVERRIDES['global_step'] = float(step)
     model = FM.get_model(ropt)
     assert not tf.FEED, 'unused placeholders'
     out[name + '/meta'] = np.array(json.dumps({'arch': arch, 'H': H, 'W': W, 'T': T, 'B': B, 'overrides': over,
-                                               'global_step': step, 'batch_seed': 21, 'weight_seed': 4321}))
+                                               'global_step': step, 'batch_seed': 21, 'weight_seed': 4321,
+                                               'phase_train': phase}))
     out[name + '/weights_checksum'] = np.float64(sum(float(np.abs(v).sum()) for v in w.values()))
     for k in KEEP:  # (the glimpse x_patch is left out to keep the fixture small: y_out_patch is computed from it)
       out['%s/%s' % (name, k)] = np.asarray(model[k], np.float32 if k in BIG else np.float64)
     # the random draws of the graph, in call order (image_ops first, then the scheduled-sampling draws)
     logs = [r for r in tf.RANDOM_LOG if np.asarray(r['value']).dtype.kind == 'f']
-    if over['use_knob']:
+    if over['use_knob'] and phase:
       by_shape = lambda shp: [r['value'] for r in logs if r['shape'] == shp]
       f32 = lambda a: np.asarray(a, np.float32)  # lossless: the shim draws in float32
       out[name + '/draw_box_pad'] = f32(by_shape((B, T, 1))[0])

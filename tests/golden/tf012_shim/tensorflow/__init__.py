@@ -259,7 +259,8 @@ def matmul(a, b):
 
 
 def sigmoid(x):
-  return _t(1.0 / (1.0 + np.exp(-_f(x))))
+  with np.errstate(over='ignore'):  # exp overflow -> inf -> sigmoid 0: the saturated value, as in TensorFlow
+    return _t(1.0 / (1.0 + np.exp(-_f(x))))
 
 
 def tanh(x):

@@ -38,8 +38,11 @@ def test_oracle_equals_the_reference_graph(name):
   w = {k: np.asarray(v, np.float64) for k, v in ra.synthetic.make_weights(opt, seed=meta['weight_seed']).items()}
   assert sum(float(np.abs(v).sum()) for v in w.values()) == pytest.approx(float(G[name + '/weights_checksum']), rel=1e-12), \
       'synthetic.make_weights changed: regenerate the fixture'
+  phase = meta.get('phase_train', True)
+  if not phase:  # eval mode: the EMA shadows of the reference's fresh graph are zero
+    w = {k: (np.zeros_like(v) if k.endswith(('_ema_mean', '_ema_var')) else v) for k, v in w.items()}
   draws = None
-  if opt['use_knob']:
+  if opt['use_knob'] and phase:
     step = meta['global_step']
     p_box = ra.synthetic.knob_probability(opt, step, 'knob_box_offset')
     p_segm = ra.synthetic.knob_probability(opt, step, 'knob_segm_offset')
@@ -54,7 +57,7 @@ def test_oracle_equals_the_reference_graph(name):
   torch.set_default_dtype(torch.float64)
   try:
     with torch.no_grad():
-      o = O64.full_model_forward(opt, w, batch, phase_train=True, draws=draws)
+      o = O64.full_model_forward(opt, w, batch, phase_train=phase, draws=draws)
   finally:
     torch.set_default_dtype(torch.float32)
   ref = lambda k: G['%s/%s' % (name, k)]
