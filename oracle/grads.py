@@ -9,8 +9,10 @@ The forward graph is oracle.model.full_model_forward(phase_train=True) — batch
 the moments like tf.nn.moments), scheduled sampling with the draws as inputs, tf.stop_gradient on the canvas
 (full_model.py:846-848), no gradient through the Hungarian op (modellib.py:11) — and torch.autograd stands in for
 TensorFlow's autodiff of the same graph.  The forward graph is pinned to the reference's own source (see oracle/model.py); TensorFlow's
-autodiff itself cannot run here, so the gradients are pinned to that forward by central differences in float64
-(tests/test_train_step_oracle.py).
+autodiff itself cannot run here, so the gradients are pinned (tests/test_train_step_oracle.py) by central differences
+in float64 - of the forward oracle, and of the REFERENCE GRAPH'S OWN LOSS (full_model.get_model executed over the
+TF-0.12 stand-in, tests/golden/make_reference_fd_golden.py).  What neither can see is where the reference stops
+gradients (two lines, full_model.py:846-848), restated by inspection.
 
 The CUDA backward pass does not exist yet; this module is the checker it will be built against, and
 `train_step` + oracle.optim.adam_step is the complete CPU restatement of one training step today.

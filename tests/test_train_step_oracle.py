@@ -132,3 +132,33 @@ def test_train_step_updates():
   keys_f = OG.trainable_keys(weights, fr)
   w3, m3, _, _ = OG.train_step(opt, weights, batch, {k: m[k] for k in keys_f}, {k: v[k] for k in keys_f}, 0, frozen=fr)
   assert np.array_equal(w3['ctrl_cnn_w_0'], weights['ctrl_cnn_w_0']) and 'ctrl_cnn_w_0' not in m3
+
+
+@pytest.mark.parametrize('name', ['cvppp', 'kitti'])
+def test_gradient_oracle_equals_derivatives_of_the_reference_graph(name):
+  """tests/golden/reference_fd_golden.npz holds central differences of the REFERENCE'S OWN loss (full_model.get_model
+  executed unmodified over the TF-0.12 stand-in, float64, canvas gradient not stopped).  torch.autograd through the
+  oracle, in the same setting, must give the same derivatives: the gradient oracle is then pinned to the reference's
+  code (up to where it stops gradients, full_model.py:846-848, restated by inspection)."""
+  import json
+  import os
+  G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_fd_golden.npz'))
+  meta = json.loads(str(G[name + '/meta']))
+  opt = ra.config.full_model_opt(meta['arch'], meta['H'], meta['W'], meta['T'], **meta['overrides'])
+  assert opt['stop_canvas_grad'] is False
+  batch = {k: np.asarray(v, np.float64) for k, v in ra.synthetic.make_batch(opt, meta['B'], seed=meta['batch_seed']).items()}
+  w64 = {k: np.asarray(v, np.float64) for k, v in ra.synthetic.make_weights(opt, seed=meta['weight_seed']).items()}
+  O64 = oracle_fp64()
+  torch.set_default_dtype(torch.float64)
+  try:
+    grads, _ = OG.full_model_grads(opt, w64, batch, include_weight_decay=True, model_module=O64, dtype=torch.float64)
+  finally:
+    torch.set_default_dtype(torch.float32)
+  checked = 0
+  for row in meta['rows']:
+    g = float(grads[row['key']][tuple(row['idx'])])
+    assert row['fd'] == pytest.approx(g, rel=2e-3, abs=2e-4), (row['key'], row['idx'], row['fd'], g)
+    checked += 1
+  assert checked == len(meta['rows']) >= 30
+  big = [abs(r['fd']) for r in meta['rows']]
+  assert max(big) > 1.0  # the probes are not all trivially small
