@@ -89,3 +89,40 @@ def hungarian_bitset(W, return_info=False):
   if return_info:
     return M, cx, cy, {'status': st}
   return M, cx, cy
+
+
+_REF = None
+REF_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'libhungarian_ref.so')
+
+
+def reference_available():
+  """True when oracle/_ref/libhungarian_ref.so (the reference's own hungarian.cc, see oracle/Makefile) is present."""
+  return os.path.exists(REF_PATH)
+
+
+def hungarian_reference(W):
+  """THE REFERENCE'S OWN HungarianOp (hungarian.cc compiled unmodified against oracle/ref_shim).  Returns
+  (matching, cover_x, cover_y, fatal) with the op's output shapes; fatal = text of the LOG(FATAL) the reference would
+  have aborted with (BFS / max-flow caps, hungarian.cc:124-127,186-188), else None."""
+  global _REF
+  if _REF is None:
+    lib = ctypes.CDLL(REF_PATH)
+    lib.ref_hungarian_f32.restype = ctypes.c_int
+    _REF = lib
+  W = np.ascontiguousarray(W, dtype=np.float32)
+  if W.ndim == 3:
+    B, nx, ny = W.shape
+  elif W.ndim == 2:
+    B, (nx, ny) = 0, W.shape
+  else:
+    raise ValueError('Must have dimension 3 or 2.')
+  nb = max(B, 1)
+  M = np.zeros((nb, nx, ny), np.float32)
+  cx = np.zeros((nb, nx, 1), np.float32)
+  cy = np.zeros((nb, 1, ny), np.float32)
+  msg = ctypes.create_string_buffer(512)
+  vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+  rc = _REF.ref_hungarian_f32(vp(W), B, nx, ny, vp(M), vp(cx), vp(cy), msg, 512)
+  if W.ndim == 2:
+    M, cx, cy = M[0], cx[0], cy[0]
+  return M, cx, cy, (msg.value.decode('utf-8', 'replace') if rc != 0 else None)

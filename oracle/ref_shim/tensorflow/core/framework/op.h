@@ -1,0 +1,2 @@
+#pragma once
+#include "tensorflow/core/framework/op_kernel.h"

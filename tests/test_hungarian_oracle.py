@@ -112,3 +112,59 @@ def test_bitset_rejects_oversize():
   W = np.zeros((1, 65, 3), np.float32)
   _, _, _, info = H.hungarian_bitset(W, return_info=True)
   assert (info['status'] == H.ST_TOO_LARGE).all()
+
+
+needs_ref = pytest.mark.skipif(not H.reference_available(),
+                               reason='oracle/_ref/libhungarian_ref.so is built where /root/reference exists (make -C oracle)')
+
+
+@needs_ref
+@pytest.mark.parametrize('case', _cases(), ids=lambda c: c['name'])
+def test_compiled_reference_reproduces_its_own_test_vectors(case):
+  """oracle/_ref = the reference's own hungarian.cc compiled unmodified against stand-in TF / Eigen headers
+  (oracle/ref_shim).  First make sure that build behaves like the op: it must pass the reference's own tests."""
+  W = np.frombuffer(bytes.fromhex(case['W_f32_hex']), np.float32).reshape(case['shape'])
+  M, cx, cy, fatal = H.hungarian_reference(W)
+  assert fatal is None
+  if case['kind'] == 'known_answer':
+    assert (M == np.array(case['M'], np.float32)).all()
+    if 'cover_x' in case:
+      assert (cx.reshape(-1) == np.array(case['cover_x'], np.float32).reshape(-1)).all()
+      assert (cy.reshape(-1) == np.array(case['cover_y'], np.float32).reshape(-1)).all()
+  else:
+    assert M.sum() == min(W.shape[-2:])
+
+
+@needs_ref
+def test_restatement_equals_the_compiled_reference_bit_for_bit():
+  """The literal C restatement (and the duplicate-free search the CUDA kernel uses) against the REAL reference code
+  on 20k random / degenerate / rectangular problems: matching and both covers identical to the bit; where the
+  reference would abort on its BFS cap (LOG(FATAL), hungarian.cc:124-127) the restatement reports the same."""
+  rng = np.random.default_rng(2026)
+  n = fatal_seen = outer_cap_seen = 0
+  for trial in range(2500):
+    nx, ny = int(rng.integers(1, 25)), int(rng.integers(1, 25))
+    if trial % 50 == 0:
+      nx = ny = int(rng.integers(26, 34))  # large enough for the reference's 1000-pop BFS cap to matter
+    W = _random_weights(rng, trial % 5, 8, nx, ny)
+    for b in range(W.shape[0]):
+      Mr, cxr, cyr, fatal = H.hungarian_reference(W[b])
+      Mo, cxo, cyo, info = H.hungarian(W[b], stop_at_fatal=True, return_info=True)
+      n += 1
+      if fatal is not None:
+        fatal_seen += 1
+        assert int(info['status'][0]) & ~1, ('the restatement must flag what the reference aborts on', fatal)
+        continue
+      # bit 1 = the outer loop ran its 1000 rounds: the reference logs an ERROR and returns the unfinished matching
+      # (hungarian.cc:362-375) - not fatal, and the unfinished matching must be the same one
+      assert int(info['status'][0]) & ~1 == 0
+      outer_cap_seen += int(info['status'][0]) & 1
+      assert np.array_equal(Mr, Mo) and np.array_equal(cxr, cxo) and np.array_equal(cyr, cyo), (trial, b, nx, ny)
+      Mb, cxb, cyb = H.hungarian_bitset(W[b])
+      assert np.array_equal(Mr, Mb) and np.array_equal(cxr, cxb) and np.array_equal(cyr, cyb), (trial, b, nx, ny)
+  assert n == 20000
+  # batched (rank-3) entry of the op
+  W = _random_weights(rng, 2, 6, 9, 12)
+  Mr, cxr, cyr, fatal = H.hungarian_reference(W)
+  Mo, cxo, cyo = H.hungarian(W)
+  assert fatal is None and np.array_equal(Mr, Mo) and np.array_equal(cxr, cxo) and np.array_equal(cyr, cyo)
