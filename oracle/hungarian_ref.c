@@ -2,12 +2,14 @@
  * ORACLE (test infrastructure, never shipped, never on the product path).
  *
  * Plain-C restatement of the reference's `Hungarian` TensorFlow custom op
- * (/root/reference/hungarian.cc).  The reference cannot be compiled in this
- * environment (it needs the TensorFlow 0.12 headers and Eigen, both absent), so
- * this file re-expresses its algorithm function by function with plain arrays.
- * It is PINNED against the reference's own known-answer tests
+ * (/root/reference/hungarian.cc), re-expressing its algorithm function by
+ * function with plain arrays (no TensorFlow, no Eigen).  It is PINNED twice:
+ * against the reference's own known-answer tests
  * (/root/reference/hungarian_tf_tests.py:9-91, fixtures in
- * tests/golden/hungarian_kat.json).
+ * tests/golden/hungarian_kat.json), and against the reference's own
+ * hungarian.cc compiled unmodified over stand-in TensorFlow / Eigen headers
+ * (oracle/_ref/libhungarian_ref.so, see oracle/Makefile) - bit-identical on
+ * 20k random problems (tests/test_hungarian_oracle.py).
  *
  * Everything that decides tie-breaking is kept literal:
  *   - fp32 cover arithmetic, `|cx+cy-w| <= 1e-6` compared in double
