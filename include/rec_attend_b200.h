@@ -331,6 +331,21 @@ int ra_bn_train_block_bwd_f32(const float *raw, const float *dy, const float *ga
 size_t ra_conv3x3_bwd_weight_workspace(int B, int Hin, int Win, int Cin, int Cout, int upsample);
 int ra_conv3x3_bwd_weight_f32(const float *x1, int C1, const float *x2, int C2, const float *d_out, int B, int Hin,
                               int Win, int Cout, int upsample, void *ws, float *dw, float *db, void *stream);
+/* Grouped / shared-input forms used by the training step, where the T decode steps are processed as ONE batch of
+ * G = T groups of B examples (no gradient flows between steps: the canvas is behind tf.stop_gradient,
+ * full_model.py:846-848):
+ *  ra_bn_train_block_bwd_grouped_f32: raw [G,B,H,W,C], dy [G,B,H/p,W/p,C], gamma / beta / mean / var [G,C] (one BN copy
+ *    per group = per decode step, nnlib.py:212-254) -> d_raw [G,B,H,W,C], dgamma / dbeta [G,C].
+ *  ra_conv3x3_bwd_weight_ex_f32: x1_bmod > 0: x1 holds x1_bmod examples shared by every group (example n reads
+ *    x1[n % x1_bmod]) — the step-invariant input channels of the first controller layer. */
+size_t ra_bn_train_block_bwd_grouped_workspace(int G, int B, int H, int W, int C, int pool);
+int ra_bn_train_block_bwd_grouped_f32(const float *raw, const float *dy, const float *gamma, const float *beta,
+                                      const float *mean, const float *var, int G, int B, int H, int W, int C, int pool,
+                                      int relu, float eps, void *ws, float *d_raw, float *dgamma, float *dbeta,
+                                      void *stream);
+int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod, const float *x2, int C2, const float *d_out,
+                                 int B, int Hin, int Win, int Cout, int upsample, void *ws, float *dw, float *db,
+                                 void *stream);
 int ra_filter_flip_transpose_f32(const float *w, int Ci, int Co, float *out, void *stream);
 int ra_subsample2_f32(const float *src, int B, int H, int W, int C, int off, float *dst, void *stream);
 
@@ -381,6 +396,19 @@ int ra_paste_back_bwd_f32(const float *d_out, const float *out, size_t out_bstri
                           void *stream);
 int ra_gaussian_filters_bwd_f32(const float *box, const float *fy, const float *fx, const float *d_fy, const float *d_fx,
                                 int B, int H, int W, int F, float *d_box, void *stream);
+/* Step-batched forms (example n = t * n_inner + b of a [T, n_inner, ...] stack):
+ *  ra_paste_back_bwd_ex_f32: d_out / out of example n at (n % n_inner) * out_bstride + (n / n_inner) * out_ostride
+ *    (a [B,T,H,W] stack read in [T,B] order: out_bstride = T*H*W, out_ostride = H*W).
+ *  ra_gaussian_extract_bwd_ex_f32: xs_bmod > 0: xs holds xs_bmod examples shared by every step (n % xs_bmod). */
+int ra_paste_back_bwd_ex_f32(const float *d_out, const float *out, size_t out_bstride, int n_inner, size_t out_ostride,
+                             const float *patch, const float *fy, const float *fx, const float *gamma, int gamma_stride,
+                             int B, int H, int W, int F, int accumulate, void *ws, float *d_patch, float *d_fy,
+                             float *d_fx, float *d_gamma, void *stream);
+int ra_gaussian_extract_bwd_ex_f32(const float *xs, int Cs, int xs_bmod, const float *canvas, const int32_t *chan_map,
+                                   const float *fy, const float *fx, const float *gamma, int gamma_stride,
+                                   const float *d_patch, const float *x_patch, int patch_cstride, int B, int H, int W,
+                                   int F, int accumulate, void *ws, float *d_fy, float *d_fx, float *d_gamma,
+                                   void *stream);
 
 /* --------------------------------------------------------------------------------------
  * Backward of the controller (full_model.py:668-725) — TensorFlow's autodiff of the soft read-out, the LSTM, the
@@ -494,6 +522,48 @@ int ra_bn_train_block_f32(const float *x, int B, int H, int W, int C, const floa
 int ra_adam_step_f32(float *param, const float *grad, float *m, float *v, const float *wd, size_t n,
                      float grad_scale, float lr, float beta1, float beta2, float eps, float clip, int step_t,
                      void *stream);
+
+/* --------------------------------------------------------------------------------------
+ * Training-step glue (csrc/train.cu) — what sits between the per-block gradients and the optimiser in
+ * `sess.run([loss, train_step])` (runner.py:98-105; full_model.py:1039-1057, box_model.py:635-652).
+ *  ra_param_gather_f32: flat trainable bucket -> every device-side weight image in one launch.  `codes[i]` describes
+ *    destination element i of the concatenation of nseg destination tensors (seg_start [nseg] = first element of each
+ *    segment, seg_dst [nseg] = device pointers; both arrays in DEVICE memory): 0 = constant zero (padding), else
+ *    ((flat index + 1) << 2) | kind with kind 0 = the value, 1 = hi (value rounded to the nearest tf32), 2 = lo =
+ *    value - hi (the two operand images of the 3xTF32 tcgen05 convolution).
+ *  ra_param_scatter_f32: the inverse for gradients (kind ignored, code 0 skipped): flat[index] = src element.
+ *  ra_bn_fold_f32: eval-mode BN + bias folded per (step, channel): scale = gamma / sqrt(ema_var + eps),
+ *    shift = beta - ema_mean * scale + bias * scale (nnlib.py:113-119); gamma .. ema_var, scale, shift [T,C], bias [C].
+ *  ra_weight_decay_f32: out[0] = sum_i wd[i] * param[i]^2 / 2 (nnlib.py:59-61); ws: ra_weight_decay_workspace() bytes.
+ *  ra_sum_groups_f32: dst [n] = sum_g src [G,n].   ra_add_f32: dst += src.
+ *  ra_split_channels_f32: src [npix, C1+C2] -> dst1 [npix,C1] (may be NULL), dst2 [npix,C2] (may be NULL; added to
+ *    when accumulate2 != 0): the input gradient of a layer fed by concat(prev, skip) (nnlib.py:362-367).
+ *  ra_score_bwd_f32: s = sigmoid([h, core] w + b) (full_model.py:821-822): s_out, d_s [B,T]; rows n = t*B + b:
+ *    dpre [T*B], d_h [T*B,Hd] = dpre * w[:Hd], d_core [T*B,Cd] (+)= dpre * w[Hd:] (Cd may be 0: box_model.py:508-511).
+ *  ra_knob_box_bwd_f32: scheduled sampling (full_model.py:760-776): d_box [T*B,6] = d_mixed with its centre / size
+ *    entries scaled by 1 - knob_box[b,t], plus d_pre (may be NULL; the pre-mix filters' share).
+ *  ra_iou_box_coord_bwd_f32: d_box [T*B,6] += gradient of scale * box_loss through modellib.f_iou_box
+ *    (modellib.py:206-238) of the controller's own box record `box` [T*B,RA_BOX_STRIDE] against tl_gt / br_gt [B,T,2]
+ *    with the constant matching match_box [B,T,T] (opt['use_iou_box'], full_model.py:750-754,926-929).
+ * -------------------------------------------------------------------------------------- */
+int ra_param_gather_f32(const float *flat, const int32_t *codes, const long long *seg_start, float *const *seg_dst,
+                        int nseg, long long total, void *stream);
+int ra_param_scatter_f32(float *flat, const int32_t *codes, const long long *seg_start, const float *const *seg_src,
+                         int nseg, long long total, void *stream);
+int ra_bn_fold_f32(const float *gamma, const float *beta, const float *ema_mean, const float *ema_var, const float *bias,
+                   int T, int C, float eps, float *scale, float *shift, void *stream);
+size_t ra_weight_decay_workspace(void);
+int ra_weight_decay_f32(const float *param, const float *wd, size_t n, void *ws, float *out, void *stream);
+int ra_sum_groups_f32(const float *src, int G, size_t n, float *dst, void *stream);
+int ra_add_f32(float *dst, const float *src, size_t n, void *stream);
+int ra_split_channels_f32(const float *src, size_t npix, int C1, int C2, float *dst1, float *dst2, int accumulate2,
+                          void *stream);
+int ra_score_bwd_f32(const float *s_out, const float *d_s, int B, int T, const float *w, int Hd, int Cd, float *dpre,
+                     float *d_h, float *d_core, int accumulate_core, void *stream);
+int ra_knob_box_bwd_f32(const float *d_mixed, const float *d_pre, const float *knob_box, int B, int T, float *d_box,
+                        void *stream);
+int ra_iou_box_coord_bwd_f32(const float *box, const float *tl_gt, const float *br_gt, const float *match_box, int B,
+                             int T, float scale, float *d_box, void *stream);
 
 #ifdef __cplusplus
 }

@@ -62,6 +62,27 @@ def full_model_grads(opt, weights, batch, draws=None, include_weight_decay=True,
   return grads, {k: ({kk: det(vv) for kk, vv in v.items()} if isinstance(v, dict) else det(v)) for k, v in out.items()}
 
 
+def box_model_grads(opt, weights, batch, canvas_noise=None, include_weight_decay=True, frozen=(), model_module=OM,
+                    dtype=torch.float32):
+  """Gradients of the box model's training-mode loss (box_model.py:560-634, optimiser block :635-652) by weight key;
+  same conventions as full_model_grads."""
+  keys = trainable_keys(weights, frozen)
+  leaves = {}
+  for k, v in weights.items():
+    t = torch.as_tensor(np.asarray(v), dtype=dtype).clone()
+    if k in keys:
+      t.requires_grad_(True)
+    leaves[k] = t
+  out = model_module.box_model_forward(opt, leaves, batch, canvas_noise=canvas_noise, phase_train=True)
+  loss = out['loss']
+  if not include_weight_decay:
+    loss = loss - model_module.weight_decay_loss(opt, leaves)
+  g = torch.autograd.grad(loss, [leaves[k] for k in keys], allow_unused=True)
+  grads = {k: (None if gi is None else gi.detach().numpy()) for k, gi in zip(keys, g)}
+  det = lambda v: v.detach() if isinstance(v, torch.Tensor) else v
+  return grads, {k: ({kk: det(vv) for kk, vv in v.items()} if isinstance(v, dict) else det(v)) for k, v in out.items()}
+
+
 def train_step(opt, weights, batch, adam_m, adam_v, global_step, draws=None, frozen=(), world_grads=None):
   """One ``sess.run([loss, train_step])`` (runner.py:98-105): forward + backward + clip + Adam + EMA shadow update.
 

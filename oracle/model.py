@@ -773,6 +773,8 @@ def box_model_forward(opt, weights, batch, canvas_noise=None, phase_train=False)
   model['box_loss'] = -(((iou_box * match_box).sum(dim=(1, 2)) / cnt).sum() / B)
   model['conf_loss'] = f_conf_loss(model['s_out'], match_box)
   model['loss'] = model['box_loss'] + model['conf_loss'] + weight_decay_loss(opt, weights)
+  if ema_out is not None:
+    model['ema_updates'] = ema_out
   return model
 
 

@@ -73,6 +73,21 @@ _SIGNATURES = {
     'ra_controller_head_bwd_f32': [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     'ra_controller_bwd_f32': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'ra_outer_sum_f32': [_P, _Z, _I, _P, _Z, _I, _I, _P, _P, _P],
+    'ra_bn_train_block_bwd_grouped_f32': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
+    'ra_conv3x3_bwd_weight_ex_f32': [_P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
+    'ra_paste_back_bwd_ex_f32': [_P, _P, _Z, _I, _Z, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    'ra_gaussian_extract_bwd_ex_f32': [_P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P,
+                                       _P, _P],
+    'ra_param_gather_f32': [_P, _P, _P, _P, _I, ctypes.c_longlong, _P],
+    'ra_param_scatter_f32': [_P, _P, _P, _P, _I, ctypes.c_longlong, _P],
+    'ra_bn_fold_f32': [_P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],
+    'ra_weight_decay_f32': [_P, _P, _Z, _P, _P, _P],
+    'ra_sum_groups_f32': [_P, _I, _Z, _P, _P],
+    'ra_add_f32': [_P, _P, _Z, _P],
+    'ra_split_channels_f32': [_P, _Z, _I, _I, _P, _P, _I, _P],
+    'ra_score_bwd_f32': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _P, _I, _P],
+    'ra_knob_box_bwd_f32': [_P, _P, _P, _I, _I, _P, _P],
+    'ra_iou_box_coord_bwd_f32': [_P, _P, _P, _P, _I, _I, _F, _P, _P],
     'ra_fg_head_f32': [_P, _Z, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     'ra_adam_step_f32': [_P, _P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _P],
     'ra_postprocess_f32': [_P, _P, _P, _I, _I, _I, _I, ctypes.c_double, _F, _P, _P, _P, _P, _P, _P],
@@ -82,7 +97,8 @@ EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last
                                          'ra_bn_train_workspace', 'ra_fg_head_workspace',
                                          'ra_bn_train_block_bwd_workspace', 'ra_conv3x3_bwd_weight_workspace',
                                          'ra_iou_loss_bwd_workspace', 'ra_paste_back_bwd_workspace',
-                                         'ra_gaussian_extract_bwd_workspace', 'ra_controller_tape_floats'])
+                                         'ra_gaussian_extract_bwd_workspace', 'ra_controller_tape_floats',
+                                         'ra_bn_train_block_bwd_grouped_workspace', 'ra_weight_decay_workspace'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -126,6 +142,10 @@ def lib():
     l.ra_paste_back_bwd_workspace.restype = _Z
     l.ra_gaussian_extract_bwd_workspace.argtypes = [_I, _I, _I, _I]
     l.ra_gaussian_extract_bwd_workspace.restype = _Z
+    l.ra_bn_train_block_bwd_grouped_workspace.argtypes = [_I, _I, _I, _I, _I, _I]
+    l.ra_bn_train_block_bwd_grouped_workspace.restype = _Z
+    l.ra_weight_decay_workspace.argtypes = []
+    l.ra_weight_decay_workspace.restype = _Z
     l.ra_controller_tape_floats.argtypes = [_I, _I, _I, _I]
     l.ra_controller_tape_floats.restype = _Z
     _lib = l

@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(kT) pb_R_kernel(const float *__restrict__ patc
 
 // one CTA per image row y: V, dZ, dV (stored), d_fy[:, y], the row's share of d_gamma
 __global__ void __launch_bounds__(kT) pb_row_kernel(const float *__restrict__ d_out, const float *__restrict__ out,
-                                                    size_t out_bstride, const float *__restrict__ fy,
+                                                    size_t out_bstride, int n_inner, size_t out_ostride,
+                                                    const float *__restrict__ fy,
                                                     const float *__restrict__ R, const float *__restrict__ gamma,
                                                     int gamma_stride, int H, int W, int F, int accumulate,
                                                     float *__restrict__ dV, float *__restrict__ d_fy,
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(kT) pb_row_kernel(const float *__restrict__ d_
   __syncthreads();
   const float g = gamma[(size_t)b * gamma_stride];
   const float *Rb = R + (size_t)b * F * W;
-  const size_t row = (size_t)b * out_bstride + (size_t)y * W;
+  const size_t row = (size_t)(b % n_inner) * out_bstride + (size_t)(b / n_inner) * out_ostride + (size_t)y * W;
   float dg = 0.f;
   for (int x = threadIdx.x; x < W; x += kT) {
     float v = 0.f;
@@ -192,16 +193,13 @@ __global__ void __launch_bounds__(kT) filters_bwd_kernel(const float *__restrict
 //   d_fy[i,y] = sum_{x,c} S[i,x,c] X[y,x,c],   S[i,x,c] = gamma * sum_j G[i,j,c] fx[j,x]
 //   d_gamma   = sum G * x_patch / gamma
 // No gradient flows to X: the image is data and the canvas is behind tf.stop_gradient (full_model.py:846-848).
-__device__ __forceinline__ float x_value(const float *__restrict__ xs, int Cs, const float *__restrict__ canvas,
-                                         size_t pix, int c) {
-  return (c < Cs) ? xs[pix * Cs + c] : canvas[pix];
-}
-
 // thread per (x, c): T[b,i,x,c] for every tap i
-__global__ void __launch_bounds__(kT) ex_T_kernel(const float *__restrict__ xs, int Cs, const float *__restrict__ canvas,
+__global__ void __launch_bounds__(kT) ex_T_kernel(const float *__restrict__ xs, int Cs, int xs_bmod,
+                                                  const float *__restrict__ canvas,
                                                   const float *__restrict__ fy, int H, int W, int F, int D,
                                                   float *__restrict__ T) {
   const int b = blockIdx.y;
+  const int bx = xs_bmod > 0 ? b % xs_bmod : b;
   const int idx = blockIdx.x * kT + threadIdx.x;
   if (idx >= W * D) return;
   const int x = idx / D, c = idx - x * D;
@@ -210,7 +208,7 @@ __global__ void __launch_bounds__(kT) ex_T_kernel(const float *__restrict__ xs, 
   for (int i = 0; i < kMaxF; ++i) acc[i] = 0.f;
   const float *fyb = fy + (size_t)b * F * H;
   for (int y = 0; y < H; ++y) {
-    const float v = x_value(xs, Cs, canvas, ((size_t)b * H + y) * W + x, c);
+    const float v = (c < Cs) ? xs[(((size_t)bx * H + y) * W + x) * Cs + c] : canvas[((size_t)b * H + y) * W + x];
 #pragma unroll
     for (int i = 0; i < kMaxF; ++i)
       if (i < F) acc[i] = fmaf(fyb[(size_t)i * H + y], v, acc[i]);
@@ -281,11 +279,12 @@ __global__ void __launch_bounds__(kT) ex_S_kernel(const float *__restrict__ G, i
 
 // grid (row tiles of kExRows, b): d_fy[b,i,y] (+)= sum_{x,c} S[b,i,x,c] X[b,y,x,c]
 constexpr int kExRows = 8;
-__global__ void __launch_bounds__(kT) ex_dfy_kernel(const float *__restrict__ xs, int Cs,
+__global__ void __launch_bounds__(kT) ex_dfy_kernel(const float *__restrict__ xs, int Cs, int xs_bmod,
                                                     const float *__restrict__ canvas, const float *__restrict__ S, int H,
                                                     int W, int F, int D, int accumulate, float *__restrict__ d_fy) {
   __shared__ float red[32];
   const int y0 = blockIdx.x * kExRows, b = blockIdx.y;
+  const int bx = xs_bmod > 0 ? b % xs_bmod : b;
   const int n = W * D;
   for (int i = 0; i < F; ++i) {
     float acc[kExRows];
@@ -298,7 +297,11 @@ __global__ void __launch_bounds__(kT) ex_dfy_kernel(const float *__restrict__ xs
       const int x = idx / D, c = idx - x * D;
 #pragma unroll
       for (int r = 0; r < kExRows; ++r)
-        if (y0 + r < H) acc[r] = fmaf(x_value(xs, Cs, canvas, ((size_t)b * H + y0 + r) * W + x, c), s, acc[r]);
+        if (y0 + r < H) {
+          const float xv = (c < Cs) ? xs[(((size_t)bx * H + y0 + r) * W + x) * Cs + c]
+                                    : canvas[((size_t)b * H + y0 + r) * W + x];
+          acc[r] = fmaf(xv, s, acc[r]);
+        }
     }
 #pragma unroll
     for (int r = 0; r < kExRows; ++r) {
@@ -335,6 +338,16 @@ extern "C" int ra_paste_back_bwd_f32(const float *d_out, const float *out, size_
                                      const float *fy, const float *fx, const float *gamma, int gamma_stride, int B,
                                      int H, int W, int F, int accumulate, void *ws, float *d_patch, float *d_fy,
                                      float *d_fx, float *d_gamma, void *stream) {
+  return ra_paste_back_bwd_ex_f32(d_out, out, out_bstride, B > 0 ? B : 1, 0, patch, fy, fx, gamma, gamma_stride, B, H, W,
+                                  F, accumulate, ws, d_patch, d_fy, d_fx, d_gamma, stream);
+}
+
+extern "C" int ra_paste_back_bwd_ex_f32(const float *d_out, const float *out, size_t out_bstride, int n_inner,
+                                        size_t out_ostride, const float *patch, const float *fy, const float *fx,
+                                        const float *gamma, int gamma_stride, int B, int H, int W, int F,
+                                        int accumulate, void *ws, float *d_patch, float *d_fy, float *d_fx,
+                                        float *d_gamma, void *stream) {
+  if (n_inner < 1) return RA_ERR_INVALID_ARG;
   if (B < 0 || H < 1 || W < 1 || F < 1 || F > kMaxF || gamma_stride < 1) return RA_ERR_INVALID_ARG;
   if (B == 0) return RA_OK;
   if (!d_out || !out || !fy || !fx || !gamma || !ws || !d_fy || !d_fx || !d_gamma) return RA_ERR_INVALID_ARG;
@@ -348,8 +361,8 @@ extern "C" int ra_paste_back_bwd_f32(const float *d_out, const float *out, size_
   pb_R_kernel<<<dim3(bx, B), kT, psm, s>>>(patch, fx, W, F, R);
   int rc = ra::finish_launch("pb_R_kernel");
   if (rc != RA_OK) return rc;
-  pb_row_kernel<<<dim3(H, B), kT, 0, s>>>(d_out, out, out_bstride, fy, R, gamma, gamma_stride, H, W, F, accumulate, dV,
-                                          d_fy, rows);
+  pb_row_kernel<<<dim3(H, B), kT, 0, s>>>(d_out, out, out_bstride, n_inner, out_ostride, fy, R, gamma, gamma_stride, H,
+                                          W, F, accumulate, dV, d_fy, rows);
   rc = ra::finish_launch("pb_row_kernel");
   if (rc != RA_OK) return rc;
   pb_col_kernel<<<dim3(bx, B), kT, psm, s>>>(dV, fy, patch, H, W, F, accumulate, A, d_fx);
@@ -380,6 +393,17 @@ extern "C" int ra_gaussian_extract_bwd_f32(const float *xs, int Cs, const float 
                                            const float *d_patch, const float *x_patch, int patch_cstride, int B, int H,
                                            int W, int F, int accumulate, void *ws, float *d_fy, float *d_fx,
                                            float *d_gamma, void *stream) {
+  return ra_gaussian_extract_bwd_ex_f32(xs, Cs, 0, canvas, chan_map, fy, fx, gamma, gamma_stride, d_patch, x_patch,
+                                        patch_cstride, B, H, W, F, accumulate, ws, d_fy, d_fx, d_gamma, stream);
+}
+
+extern "C" int ra_gaussian_extract_bwd_ex_f32(const float *xs, int Cs, int xs_bmod, const float *canvas,
+                                              const int32_t *chan_map, const float *fy, const float *fx,
+                                              const float *gamma, int gamma_stride, const float *d_patch,
+                                              const float *x_patch, int patch_cstride, int B, int H, int W, int F,
+                                              int accumulate, void *ws, float *d_fy, float *d_fx, float *d_gamma,
+                                              void *stream) {
+  if (xs_bmod < 0) return RA_ERR_INVALID_ARG;
   const int D = Cs + (canvas ? 1 : 0);
   if (B < 0 || H < 1 || W < 1 || F < 1 || F > kMaxF || Cs < 0 || D < 1 || patch_cstride < D || gamma_stride < 1)
     return RA_ERR_INVALID_ARG;
@@ -391,7 +415,7 @@ extern "C" int ra_gaussian_extract_bwd_f32(const float *xs, int Cs, const float 
   float *T = reinterpret_cast<float *>(ws), *S = T + (size_t)B * F * W * D;
   const int bxc = (W * D + kT - 1) / kT, bx = (W + kT - 1) / kT;
   const size_t gsm = (size_t)F * D * sizeof(float);
-  ex_T_kernel<<<dim3(bxc, B), kT, 0, s>>>(xs, Cs, canvas, fy, H, W, F, D, T);
+  ex_T_kernel<<<dim3(bxc, B), kT, 0, s>>>(xs, Cs, xs_bmod, canvas, fy, H, W, F, D, T);
   int rc = ra::finish_launch("ex_T_kernel");
   if (rc != RA_OK) return rc;
   ex_dfx_kernel<<<dim3(bx, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, T, gamma, gamma_stride, W, F, D, accumulate,
@@ -401,7 +425,8 @@ extern "C" int ra_gaussian_extract_bwd_f32(const float *xs, int Cs, const float 
   ex_S_kernel<<<dim3(bxc, F, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, fx, gamma, gamma_stride, W, F, D, S);
   rc = ra::finish_launch("ex_S_kernel");
   if (rc != RA_OK) return rc;
-  ex_dfy_kernel<<<dim3((H + kExRows - 1) / kExRows, B), kT, 0, s>>>(xs, Cs, canvas, S, H, W, F, D, accumulate, d_fy);
+  ex_dfy_kernel<<<dim3((H + kExRows - 1) / kExRows, B), kT, 0, s>>>(xs, Cs, xs_bmod, canvas, S, H, W, F, D, accumulate,
+                                                                    d_fy);
   rc = ra::finish_launch("ex_dfy_kernel");
   if (rc != RA_OK) return rc;
   ex_dgamma_kernel<<<B, kT, 0, s>>>(d_patch, x_patch, patch_cstride, D, F, gamma, gamma_stride, d_gamma);

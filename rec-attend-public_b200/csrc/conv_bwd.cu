@@ -54,6 +54,14 @@ __global__ void __launch_bounds__(kT) bn_bwd_reduce_kernel(const float *__restri
                                                            const float *__restrict__ mean, const float *__restrict__ var,
                                                            int B, int H, int W, int C, int relu, float eps,
                                                            double *__restrict__ partial) {
+  // group g = blockIdx.y: its own B examples and its own (layer, step) BN copy
+  {
+    const size_t g = blockIdx.y;
+    raw += g * (size_t)B * H * W * C;
+    dy += g * (size_t)B * (H / POOL) * (W / POOL) * C;
+    gamma += g * C; beta += g * C; mean += g * C; var += g * C;
+    partial += g * (size_t)gridDim.x * 2 * C;
+  }
   extern __shared__ double acc_s[];  // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += kT) acc_s[i] = 0.0;
   __syncthreads();
@@ -86,6 +94,9 @@ __global__ void bn_bwd_finalize_kernel(const double *__restrict__ partial, int c
                                        float *__restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  partial += (size_t)blockIdx.y * ctas * 2 * C;
+  dgamma += (size_t)blockIdx.y * C;
+  dbeta += (size_t)blockIdx.y * C;
   double sb = 0.0, sg = 0.0;
   for (int k = 0; k < ctas; ++k) {
     sb += partial[(size_t)k * 2 * C + c];
@@ -103,6 +114,13 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const float *__restric
                                                           const float *__restrict__ dgamma,
                                                           const float *__restrict__ dbeta, int B, int H, int W, int C,
                                                           int relu, float eps, float *__restrict__ d_raw) {
+  {
+    const size_t g = blockIdx.y;
+    raw += g * (size_t)B * H * W * C;
+    d_raw += g * (size_t)B * H * W * C;
+    dy += g * (size_t)B * (H / POOL) * (W / POOL) * C;
+    gamma += g * C; beta += g * C; mean += g * C; var += g * C; dgamma += g * C; dbeta += g * C;
+  }
   const int Ho = H / POOL, Wo = W / POOL;
   const size_t total = (size_t)B * Ho * Wo * C;
   const float n = (float)((size_t)B * H * W);
@@ -141,7 +159,7 @@ constexpr int kWgPix = 32;
 constexpr int kWgCi = 128, kWgCo = 96;
 constexpr int kWgI = kWgCi / 16, kWgJ = kWgCo / 16;
 
-__global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const float *__restrict__ x1, int C1,
+__global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const float *__restrict__ x1, int C1, int x1_bmod,
                                                              const float *__restrict__ x2, int C2,
                                                              const float *__restrict__ g, int B, int Hin, int Win,
                                                              int Cout, int up, int n_ci_blk,
@@ -186,7 +204,12 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const float *__rest
         if (zy >= 0 && zy < Ho && zx >= 0 && zx < Wo && (zy % up) == 0 && (zx % up) == 0) {
           const size_t src = ((size_t)b * Hin + zy / up) * Win + zx / up;
           const int ci = ci0 + c;
-          v = (ci < C1) ? x1[src * C1 + ci] : x2[src * C2 + (ci - C1)];
+          if (ci < C1) {
+            const size_t src1 = ((size_t)(x1_bmod > 0 ? b % x1_bmod : b) * Hin + zy / up) * Win + zx / up;
+            v = x1[src1 * C1 + ci];
+          } else {
+            v = x2[src * C2 + (ci - C1)];
+          }
         }
       }
       xs[p][c] = v;
@@ -273,11 +296,23 @@ extern "C" size_t ra_bn_train_block_bwd_workspace(int B, int H, int W, int C, in
   return (size_t)bwd_ctas((size_t)B * (H / pool) * (W / pool) * C) * 2 * C * sizeof(double);
 }
 
+extern "C" size_t ra_bn_train_block_bwd_grouped_workspace(int G, int B, int H, int W, int C, int pool) {
+  return (size_t)(G < 1 ? 0 : G) * ra_bn_train_block_bwd_workspace(B, H, W, C, pool);
+}
+
 extern "C" int ra_bn_train_block_bwd_f32(const float *raw, const float *dy, const float *gamma, const float *beta,
                                          const float *mean, const float *var, int B, int H, int W, int C, int pool,
                                          int relu, float eps, void *ws, float *d_raw, float *dgamma, float *dbeta,
                                          void *stream) {
-  if (B < 0 || H < 1 || W < 1 || C < 1) return RA_ERR_INVALID_ARG;
+  return ra_bn_train_block_bwd_grouped_f32(raw, dy, gamma, beta, mean, var, 1, B, H, W, C, pool, relu, eps, ws, d_raw,
+                                           dgamma, dbeta, stream);
+}
+
+extern "C" int ra_bn_train_block_bwd_grouped_f32(const float *raw, const float *dy, const float *gamma,
+                                                 const float *beta, const float *mean, const float *var, int G, int B,
+                                                 int H, int W, int C, int pool, int relu, float eps, void *ws,
+                                                 float *d_raw, float *dgamma, float *dbeta, void *stream) {
+  if (B < 0 || H < 1 || W < 1 || C < 1 || G < 1 || G > 65535) return RA_ERR_INVALID_ARG;
   if (pool != 1 && pool != 2) return RA_ERR_UNSUPPORTED;
   if (pool == 2 && ((H | W) & 1)) return RA_ERR_UNSUPPORTED;
   if ((size_t)2 * C * sizeof(double) > 48 * 1024) return RA_ERR_UNSUPPORTED;
@@ -289,20 +324,22 @@ extern "C" int ra_bn_train_block_bwd_f32(const float *raw, const float *dy, cons
   double *partial = reinterpret_cast<double *>(ws);
   const size_t smem = (size_t)2 * C * sizeof(double);
   if (pool == 2)
-    bn_bwd_reduce_kernel<2><<<ctas, kT, smem, s>>>(raw, dy, gamma, beta, mean, var, B, H, W, C, relu, eps, partial);
+    bn_bwd_reduce_kernel<2><<<dim3(ctas, G), kT, smem, s>>>(raw, dy, gamma, beta, mean, var, B, H, W, C, relu, eps,
+                                                            partial);
   else
-    bn_bwd_reduce_kernel<1><<<ctas, kT, smem, s>>>(raw, dy, gamma, beta, mean, var, B, H, W, C, relu, eps, partial);
+    bn_bwd_reduce_kernel<1><<<dim3(ctas, G), kT, smem, s>>>(raw, dy, gamma, beta, mean, var, B, H, W, C, relu, eps,
+                                                            partial);
   int rc = ra::finish_launch("bn_bwd_reduce_kernel");
   if (rc != RA_OK) return rc;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(partial, ctas, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<dim3((C + 127) / 128, G), 128, 0, s>>>(partial, ctas, C, dgamma, dbeta);
   rc = ra::finish_launch("bn_bwd_finalize_kernel");
   if (rc != RA_OK) return rc;
   if (pool == 2)
-    bn_bwd_apply_kernel<2><<<ctas, kT, 0, s>>>(raw, dy, gamma, beta, mean, var, dgamma, dbeta, B, H, W, C, relu, eps,
-                                               d_raw);
+    bn_bwd_apply_kernel<2><<<dim3(ctas, G), kT, 0, s>>>(raw, dy, gamma, beta, mean, var, dgamma, dbeta, B, H, W, C, relu,
+                                                        eps, d_raw);
   else
-    bn_bwd_apply_kernel<1><<<ctas, kT, 0, s>>>(raw, dy, gamma, beta, mean, var, dgamma, dbeta, B, H, W, C, relu, eps,
-                                               d_raw);
+    bn_bwd_apply_kernel<1><<<dim3(ctas, G), kT, 0, s>>>(raw, dy, gamma, beta, mean, var, dgamma, dbeta, B, H, W, C, relu,
+                                                        eps, d_raw);
   return ra::finish_launch("bn_bwd_apply_kernel");
 }
 
@@ -315,6 +352,13 @@ extern "C" size_t ra_conv3x3_bwd_weight_workspace(int B, int Hin, int Win, int C
 extern "C" int ra_conv3x3_bwd_weight_f32(const float *x1, int C1, const float *x2, int C2, const float *d_out, int B,
                                          int Hin, int Win, int Cout, int upsample, void *ws, float *dw, float *db,
                                          void *stream) {
+  return ra_conv3x3_bwd_weight_ex_f32(x1, C1, 0, x2, C2, d_out, B, Hin, Win, Cout, upsample, ws, dw, db, stream);
+}
+
+extern "C" int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod, const float *x2, int C2,
+                                            const float *d_out, int B, int Hin, int Win, int Cout, int upsample,
+                                            void *ws, float *dw, float *db, void *stream) {
+  if (x1_bmod < 0) return RA_ERR_INVALID_ARG;
   if (C1 < 1 || C2 < 0 || B < 0 || Hin < 1 || Win < 1 || Cout < 1 || !dw) return RA_ERR_INVALID_ARG;
   if (upsample != 1 && upsample != 2) return RA_ERR_UNSUPPORTED;
   cudaStream_t s = ra::as_stream(stream);
@@ -331,8 +375,8 @@ extern "C" int ra_conv3x3_bwd_weight_f32(const float *x1, int C1, const float *x
   if ((size_t)n_ci_blk * n_co_blk > 65535) return RA_ERR_UNSUPPORTED;
   float *partial = reinterpret_cast<float *>(ws);
   float *db_partial = partial + (size_t)chunks * 9 * Cin * Cout;
-  conv_bwd_weight_kernel<<<dim3(chunks, 9, n_ci_blk * n_co_blk), kT, 0, s>>>(x1, C1, x2, C2, d_out, B, Hin, Win, Cout,
-                                                                            upsample, n_ci_blk, partial,
+  conv_bwd_weight_kernel<<<dim3(chunks, 9, n_ci_blk * n_co_blk), kT, 0, s>>>(x1, C1, x1_bmod, x2, C2, d_out, B, Hin, Win,
+                                                                            Cout, upsample, n_ci_blk, partial,
                                                                             db ? db_partial : nullptr);
   int rc = ra::finish_launch("conv_bwd_weight_kernel");
   if (rc != RA_OK) return rc;

@@ -14,7 +14,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, params as PM
 from .config import input_depths
 from .synthetic import dcnn_skip_channels
 
@@ -37,27 +37,24 @@ def _fold_bn(weights, scope, layer, T, bias):
   return scale, shift
 
 
-def _bn_params(weights, scope, layer, T, bias):
-  """Per-(layer, step) BN parameters and EMA shadows as [T, C] arrays + the conv bias (training-mode forward)."""
-  out = {'bias': np.asarray(bias, np.float32)}
+def _bn_params(wi, scope, layer, T):
+  """Per-(layer, step) BN parameters and EMA shadows as [T, C] arrays + the conv bias (training-mode forward);
+  `wi(key)` returns the weight with its source indices (params.WI)."""
+  out = {'bias': wi('{}_b_{}'.format(scope, layer))}
   for n in ('gamma', 'beta', 'ema_mean', 'ema_var'):
-    out[n] = np.stack([np.asarray(weights['{}_{}_{}_{}'.format(scope, layer, t, n)], np.float32) for t in range(T)])
+    out[n] = PM.WI.stack([wi('{}_{}_{}_{}'.format(scope, layer, t, n)) for t in range(T)])
   return out
 
 
 def _deconv_to_conv(w):
   """conv2d_transpose filter [kh,kw,Cout,Cin] (nnlib.py:320-325,372-376) -> the HWIO filter of
   the equivalent stride-1 convolution over the (zero-inserted) input: spatial flip + swap."""
-  return np.ascontiguousarray(w[::-1, ::-1].transpose(0, 1, 3, 2)).astype(np.float32)
+  return PM.deconv_to_conv(np.asarray(w, np.float32))
 
 
 def _pad_cin(w_hwio, cin):
   """Zero rows for padded input channels (appended after the real ones)."""
-  if w_hwio.shape[2] == cin:
-    return w_hwio
-  out = np.zeros(w_hwio.shape[:2] + (cin, w_hwio.shape[3]), np.float32)
-  out[:, :, :w_hwio.shape[2]] = w_hwio
-  return out
+  return PM.pad_cin(w_hwio, cin)
 
 
 class _ModelBase(object):
@@ -105,6 +102,10 @@ class _ModelBase(object):
     self.w = None
     self.wd_term = 0.0
     self._bufs = {}
+    self._synced = []      # (device tensor, source index array, kind array) of every weight image (see _dev)
+    self._sync_table = None
+    self._trainer = None
+    self._tape_on = None   # the tape dict while a train_step forward is being enqueued (see train.py)
     self._bn_layers = []   # (device-key prefix, weight-dict scope, layer) of every BN layer
     self._bn_dirty = False  # a training-mode forward has moved the EMA shadows: refold before the next eval forward
     self.n_chains = int(os.environ.get('RA_CHAINS', '1'))  # sub-batch chains of the decode loop (see _chains)
@@ -117,70 +118,110 @@ class _ModelBase(object):
 
   # ------------------------------------------------------------------ weights
   def _dev(self, a):
+    """Host array -> device tensor.  A params.WI (values + source indices) is also REGISTERED: after an optimiser
+    step `sync_weights` rewrites every registered tensor from the flat parameter bucket in one launch."""
+    if isinstance(a, PM.WI):
+      t = torch.from_numpy(np.ascontiguousarray(a.val, dtype=np.float32)).to(self.device)
+      self._synced.append((t, a.idx.reshape(-1), None if a.kind is None else a.kind.reshape(-1)))
+      return t
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+
+  def _wi(self, key):
+    return PM.wi_of(self._raw_weights, self._all_layout, key)
+
+  def _begin_load(self, weights):
+    """Common head of load_weights: host copy of the weight dict, the all-weights index layout, and a clean slate
+    for everything derived from the previous weights (captured CUDA graphs hold raw pointers to the old tensors)."""
+    self._raw_weights = {k: np.asarray(v, np.float32) for k, v in weights.items()}
+    self._all_layout = PM.AllLayout(self._raw_weights)
+    self._synced = []
+    self._sync_table = None
+    self._bn_layers = []
+    self._bn_dirty = False
+    self._trainer = None
+    for b in self._bufs.values():
+      b.pop('graphs', None)
 
   def _load_controller(self, weights):
     T = self.T
     w = {}
     n = len(self.opt['ctrl_cnn_filter_size'])
-    w0 = np.asarray(weights['ctrl_cnn_w_0'], np.float32)
-    if w0.shape[2] != self.D:
-      raise _lib.RecAttendError('ctrl_cnn_w_0 has {} input channels, expected {}'.format(w0.shape[2], self.D))
-    w['ccnn_w0_canvas'] = self._dev(w0[:, :, 3:4, :])
-    c0 = w0.shape[3]
+    w0 = self._wi('ctrl_cnn_w_0')
+    if w0.val.shape[2] != self.D:
+      raise _lib.RecAttendError('ctrl_cnn_w_0 has {} input channels, expected {}'.format(w0.val.shape[2], self.D))
+    w0c = w0.map(lambda a: a[:, :, 3:4, :])
+    w['ccnn_w0_canvas'] = self._dev(w0c)
+    w['ccnn_w0_canvas_idx'] = w0c.idx
+    c0 = w0.val.shape[3]
     w['one_c0'] = torch.ones(c0, device=self.device)
     w['zero_c0'] = torch.zeros(c0, device=self.device)
     h, wd_ = self.H, self.W
-    w['ccnn_w0_static_umma'] = self._pack(w0[:, :, self.static_idx, :], h, wd_, 1)
+    w['ccnn_w0_static_umma'] = self._pack(w0.map(lambda a: a[:, :, self.static_idx, :]), h, wd_, 1)
     for i in range(n):
-      wi = np.asarray(weights['ctrl_cnn_w_%d' % i], np.float32)
       if i > 0:
-        w['ccnn_w%d' % i] = self._pack(wi, h, wd_, self.ctrl_pool[i])
+        w['ccnn_w%d' % i] = self._pack(self._wi('ctrl_cnn_w_%d' % i), h, wd_, self.ctrl_pool[i])
       h, wd_ = h // self.ctrl_pool[i], wd_ // self.ctrl_pool[i]
       sc, sh = _fold_bn(weights, 'ctrl_cnn', i, T, np.asarray(weights['ctrl_cnn_b_%d' % i], np.float32))
       w['ccnn_scale%d' % i] = self._dev(sc)
       w['ccnn_shift%d' % i] = self._dev(sh)
-      self._load_bn(w, 'ccnn', 'ctrl_cnn', i, weights)
+      self._load_bn(w, 'ccnn', 'ctrl_cnn', i)
     gates = 'ifou'  # kernel gate order i, f, o, u
-    w['lstm_wx'] = self._dev(np.stack([weights['ctrl_lstm_w_x' + g] for g in gates]))
-    w['lstm_wh'] = self._dev(np.stack([weights['ctrl_lstm_w_h' + g] for g in gates]))
-    w['lstm_b'] = self._dev(np.stack([weights['ctrl_lstm_b_' + g] for g in gates]))
+    for dst, src in (('lstm_wx', 'ctrl_lstm_w_x'), ('lstm_wh', 'ctrl_lstm_w_h'), ('lstm_b', 'ctrl_lstm_b_')):
+      st = PM.WI.stack([self._wi(src + g) for g in gates])
+      w[dst] = self._dev(st)
+      w[dst + '_idx'] = st.idx
     for k in ('glimpse_mlp_w_0', 'glimpse_mlp_b_0', 'glimpse_mlp_w_1', 'glimpse_mlp_b_1', 'ctrl_mlp_w_0',
               'ctrl_mlp_b_0', 'score_mlp_b_0'):
-      w[k] = self._dev(weights[k])
-    w['score_mlp_w_0'] = self._dev(np.asarray(weights['score_mlp_w_0'], np.float32).reshape(-1))
+      wk = self._wi(k)
+      w[k] = self._dev(wk)
+      w[k + '_idx'] = wk.idx
+    ws = self._wi('score_mlp_w_0').map(lambda a: a.reshape(-1))
+    w['score_mlp_w_0'] = self._dev(ws)
+    w['score_mlp_w_0_idx'] = ws.idx
     if w['glimpse_mlp_w_1'].shape[1] != self.P:
       raise _lib.RecAttendError('glimpse_mlp_w_1 maps to {} positions, the feature map has {}'.format(
           w['glimpse_mlp_w_1'].shape[1], self.P))
     return w
 
-  def _load_bn(self, w, prefix, scope, i, weights):
+  def _load_bn(self, w, prefix, scope, i):
     """Unfolded BN parameters of layer i for the training-mode forward (batch statistics, EMA update in place)."""
-    bp = _bn_params(weights, scope, i, self.T, weights['{}_b_{}'.format(scope, i)])
+    bp = _bn_params(self._wi, scope, i, self.T)
     for n, a in bp.items():
       w['{}_{}{}'.format(prefix, n, i)] = self._dev(a)
-    w['{}_one{}'.format(prefix, i)] = torch.ones(bp['bias'].shape[0], device=self.device)
+      w['{}_{}{}_idx'.format(prefix, n, i)] = a.idx
+    w['{}_one{}'.format(prefix, i)] = torch.ones(bp['bias'].val.shape[0], device=self.device)
     self._bn_layers.append((prefix, scope, i))
 
-  def _pack(self, w_hwio, Hout, Wout, pool):
-    """Register a conv-form HWIO filter for the tcgen05 kernel; the shared-memory image depends on the
+  def _pack(self, wi, Hout, Wout, pool):
+    """Register a conv-form HWIO filter (params.WI) for the tcgen05 kernel; the shared-memory image depends on the
     tile plan (hence on the batch size) and is packed on first use per batch size."""
-    return {'w': np.ascontiguousarray(w_hwio, dtype=np.float32), 'Hout': Hout, 'Wout': Wout, 'pool': pool,
-            'packed': {}}
+    return {'w': np.ascontiguousarray(wi.val, dtype=np.float32), 'idx': wi.idx, 'Hout': Hout, 'Wout': Wout,
+            'pool': pool, 'packed': {}}
+
+  def _w_dev(self, wp):
+    """The plain conv-form filter on the device (CUDA-core convolution, weight-gradient layout)."""
+    if 'w_dev' not in wp:
+      wp['w_dev'] = self._dev(PM.WI(wp['w'], wp['idx']))
+    return wp['w_dev']
+
+  def _wb_dev(self, wp):
+    """The filter of the layer's data-gradient convolution: flipped, channel axes swapped."""
+    if 'wb_dev' not in wp:
+      wp['wb_dev'] = self._dev(PM.WI(wp['w'], wp['idx']).map(PM.flip_transpose))
+    return wp['wb_dev']
 
   def _conv(self, x, wp, scale, shift, pool, relu=True, x2=None, upsample=1, out=None):
     """One conv block on the tensor cores (csrc/conv_umma.cu).  RA_CONV_FP32=1 (diagnostics) runs the same block
     on the CUDA cores in plain fp32 FMA arithmetic (csrc/conv.cu) - the precision reference for the 3xTF32 path."""
     if os.environ.get('RA_CONV_FP32'):
-      if 'w_dev' not in wp:
-        wp['w_dev'] = self._dev(wp['w'])
-      return ops.conv3x3_block(x, wp['w_dev'], scale, shift, pool=pool, relu=relu, x2=x2, upsample=upsample, out=out)
+      return ops.conv3x3_block(x, self._w_dev(wp), scale, shift, pool=pool, relu=relu, x2=x2, upsample=upsample,
+                               out=out)
     B = x.shape[0]
     key = (B, pool)  # the tile plan (hence the packed image) depends on the batch size and on the pooling
     if key not in wp['packed']:
       w = wp['w']
       KC, NPc, nsp, _ = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], pool, B)
-      wp['packed'][key] = self._dev(ops.pack_umma_weights(w, KC, NPc, nsp))
+      wp['packed'][key] = self._dev(PM.pack_umma(PM.WI(w, wp['idx']), KC, NPc, nsp))
     return ops.conv3x3_block_umma(x, wp['packed'][key], wp['w'].shape[3], scale, shift, pool=pool, relu=relu, x2=x2,
                                   upsample=upsample, out=out)
 
@@ -191,22 +232,82 @@ class _ModelBase(object):
     if not train:
       return self._conv(x, wp, w['%s_scale%d' % (prefix, i)][t], w['%s_shift%d' % (prefix, i)][t], pool, relu=relu,
                         x2=x2, upsample=upsample, out=out)
+    tp = self._tape_on
+    raw_out = bm = bv = None
+    if tp is not None:  # train_step: the backward needs the raw conv output and the batch statistics of every layer
+      raw_out, bm, bv = tp['%s_raw%d' % (prefix, i)][t], tp['%s_mean%d' % (prefix, i)][t], tp['%s_var%d' % (prefix, i)][t]
     raw = self._conv(x, wp, w['%s_one%d' % (prefix, i)], w['%s_bias%d' % (prefix, i)], 1, relu=False, x2=x2,
-                     upsample=upsample)
+                     upsample=upsample, out=raw_out)
     y, _, _ = ops.batch_norm_train_block(raw, w['%s_gamma%d' % (prefix, i)][t], w['%s_beta%d' % (prefix, i)][t],
                                          w['%s_ema_mean%d' % (prefix, i)][t], w['%s_ema_var%d' % (prefix, i)][t],
-                                         pool=pool, relu=relu, eps=BN_EPS, out=out)
+                                         pool=pool, relu=relu, eps=BN_EPS, out=out, batch_mean=bm, batch_var=bv)
     return y
 
+  def _act(self, bufs, net, i, t):
+    """Activation buffer of layer i of `net` at step t: the per-step tape slot during a train_step forward (the
+    backward reads every layer's input), else the buffer shared by all steps."""
+    tp = self._tape_on
+    if tp is not None:
+      return tp['%s_out%d' % (net, i)][t]
+    return bufs[net][i]
+
+  def _filt(self, bufs, t):
+    tp = self._tape_on
+    if tp is not None:
+      return tp['fy'][t], tp['fx'][t]
+    return bufs['fy'], bufs['fx']
+
   def _refold_bn(self):
-    """After training-mode forwards: fold the moved EMA shadows back into the eval-mode scale / shift rows."""
+    """After training-mode forwards / optimiser steps: fold gamma, beta, the (moved) EMA shadows and the conv bias
+    back into the eval-mode scale / shift rows (nnlib.py:113-119), on the device."""
     w = self.w
     for prefix, _, i in self._bn_layers:
-      inv = w['%s_gamma%d' % (prefix, i)] * torch.rsqrt(w['%s_ema_var%d' % (prefix, i)] + BN_EPS)
-      w['%s_scale%d' % (prefix, i)].copy_(inv)
-      w['%s_shift%d' % (prefix, i)].copy_(w['%s_beta%d' % (prefix, i)] - w['%s_ema_mean%d' % (prefix, i)] * inv +
-                                           w['%s_bias%d' % (prefix, i)] * inv)
+      g = w['%s_gamma%d' % (prefix, i)]
+      _lib.call('ra_bn_fold_f32', ops._p(g), ops._p(w['%s_beta%d' % (prefix, i)]),
+                ops._p(w['%s_ema_mean%d' % (prefix, i)]), ops._p(w['%s_ema_var%d' % (prefix, i)]),
+                ops._p(w['%s_bias%d' % (prefix, i)]), g.shape[0], g.shape[1], BN_EPS,
+                ops._p(w['%s_scale%d' % (prefix, i)]), ops._p(w['%s_shift%d' % (prefix, i)]), ops._stream())
     self._bn_dirty = False
+
+  def _set_wd_term(self, weights):
+    """The weight-decay part of the loss value (nnlib.py:59-61) lives in a device scalar: an optimiser step
+    recomputes it on the device (ra_weight_decay_f32), captured graphs read the same address."""
+    self.wd_term = self._weight_decay_term(weights)
+    self.w['wd_dev'] = torch.full((1,), float(self.wd_term), device=self.device, dtype=torch.float32)
+
+  def _add_wd(self, scal):
+    """loss += the device-side weight-decay term (the loss block itself is called with 0)."""
+    _lib.call('ra_add_f32', ops._p(scal[_lib.LOSS_NAMES.index('loss'):]), ops._p(self.w['wd_dev']), 1, ops._stream())
+
+  # ------------------------------------------------------------------ optimiser <-> device weight images
+  def sync_weights(self, flat_params, tmap):
+    """Rewrite every registered device weight image from the flat trainable bucket (`optim.AdamOptimizer.params`)
+    in ONE launch of ra_param_gather_f32 - the device-side counterpart of load_weights(export_weights())."""
+    n = len(self._synced)
+    if self._sync_table is None or self._sync_table['n'] != n:
+      codes, starts, ptrs, keep = [], [], [], []
+      total = 0
+      for t, idx, kind in self._synced:
+        code = PM.encode(idx, kind, tmap)
+        if code is None:
+          continue
+        assert code.size == t.numel()
+        codes.append(code)
+        starts.append(total)
+        ptrs.append(t.data_ptr())
+        keep.append(t)
+        total += code.size
+      dev = self.device
+      self._sync_table = {
+          'n': n, 'total': total, 'nseg': len(starts), 'keep': keep,
+          'codes': torch.from_numpy(np.concatenate(codes) if codes else np.zeros(0, np.int32)).to(dev),
+          'starts': torch.tensor(starts, dtype=torch.int64, device=dev),
+          'ptrs': torch.tensor(ptrs, dtype=torch.int64, device=dev),
+      }
+    tb = self._sync_table
+    _lib.call('ra_param_gather_f32', ops._p(flat_params), ops._p(tb['codes']), ops._p(tb['starts']), ops._p(tb['ptrs']),
+              tb['nseg'], tb['total'], ops._stream())
+    self._bn_dirty = True  # gamma / beta / bias moved: refold before the next eval forward
 
   def _weight_decay_term(self, weights):
     """nnlib.py:59-61: sum over conv/mlp/lstm weight matrices of wd * ||w||^2 / 2 (a constant
@@ -221,7 +322,7 @@ class _ModelBase(object):
 
   def export_weights(self):
     """The weights in the reference key schema (TF layouts); the BN EMA shadows reflect every training-mode forward
-    run since load_weights."""
+    run since load_weights, the trainable tensors every train_step."""
     out = {k: np.array(v) for k, v in self._raw_weights.items()}
     if self.w is not None:
       for prefix, scope, i in self._bn_layers:
@@ -229,6 +330,9 @@ class _ModelBase(object):
           a = self.w['%s_%s%d' % (prefix, n, i)].cpu().numpy()
           for t in range(self.T):
             out['{}_{}_{}_{}'.format(scope, i, t, n)] = a[t].copy()
+    if self._trainer is not None:  # the parameters train_step has moved
+      opt_ = self._trainer.optim
+      out.update({k: np.array(v) for k, v in opt_.flat.unflatten(opt_.params.cpu().numpy()).items()})
     return out
 
   # ------------------------------------------------------------------ shared pieces
@@ -309,27 +413,35 @@ class _ModelBase(object):
     """full_model.py:663-725: controller CNN (BN copy t) + glimpse LSTM + head -> box params."""
     w = self.w
     B, H, W = bufs['canvas'].shape
+    tp = self._tape_on
     _lib.TAG = 'ctrl_cnn'
+    if tp is not None:
+      tp['canvas'][t].copy_(bufs['canvas'])  # the canvas this step starts from (glimpse / first-layer gradients)
     if not train:
       ops.canvas_conv(bufs['static_pre'], bufs['canvas'], w['ccnn_w0_canvas'], w['ccnn_scale0'][t],
                       w['ccnn_shift0'][t], pool=self.ctrl_pool[0], relu=True, out=bufs['ccnn'][0])
     else:
       # raw layer-0 output = static part + canvas part + bias at full resolution, then batch-statistics BN
+      raw_out = bm = bv = None
+      if tp is not None:
+        raw_out, bm, bv = tp['ccnn_raw0'][t], tp['ccnn_mean0'][t], tp['ccnn_var0'][t]
       raw0 = ops.canvas_conv(bufs['static_pre'], bufs['canvas'], w['ccnn_w0_canvas'], w['ccnn_one0'], w['ccnn_bias0'],
-                             pool=1, relu=False)
+                             pool=1, relu=False, out=raw_out)
       ops.batch_norm_train_block(raw0, w['ccnn_gamma0'][t], w['ccnn_beta0'][t], w['ccnn_ema_mean0'][t],
                                  w['ccnn_ema_var0'][t], pool=self.ctrl_pool[0], relu=True, eps=BN_EPS,
-                                 out=bufs['ccnn'][0])
-    for i in range(1, len(self.ctrl_pool)):
-      self._block(train, bufs['ccnn'][i - 1], w['ccnn_w%d' % i], 'ccnn', i, t, self.ctrl_pool[i], out=bufs['ccnn'][i])
-    feat = bufs['ccnn'][-1].view(B, self.P, -1)
+                                 out=self._act(bufs, 'ccnn', 0, t), batch_mean=bm, batch_var=bv)
+    n_c = len(self.ctrl_pool)
+    for i in range(1, n_c):
+      self._block(train, self._act(bufs, 'ccnn', i - 1, t), w['ccnn_w%d' % i], 'ccnn', i, t, self.ctrl_pool[i],
+                  out=self._act(bufs, 'ccnn', i, t))
+    feat = self._act(bufs, 'ccnn', n_c - 1, t).view(B, self.P, -1)
     _lib.TAG = 'controller'
     ops.controller_step(feat, w['lstm_wx'], w['lstm_wh'], w['lstm_b'], w['glimpse_mlp_w_0'], w['glimpse_mlp_b_0'],
                         w['glimpse_mlp_w_1'], w['glimpse_mlp_b_1'], w['ctrl_mlp_w_0'], w['ctrl_mlp_b_0'], self.H,
                         self.W, self.F, self.F, self.ctrl_flags, n_iter=self.n_iter, h_out=bufs['h_all'][t],
                         ctrl_out=bufs['ctrl_out_all'][t], glimpse_map=bufs['gmap_all'][t], box=bufs['box_all'][t])
-    ops.get_gaussian_filter(bufs['box_all'][t], self.H, self.W, self.F, fy=bufs['fy'], fx=bufs['fx'],
-                            band=bufs['band'])
+    fy, fx = self._filt(bufs, t)
+    ops.get_gaussian_filter(bufs['box_all'][t], self.H, self.W, self.F, fy=fy, fx=fx, band=bufs['band'])
 
   def _controller_outputs(self, bufs, out):
     box = bufs['box_all'].permute(1, 0, 2)  # [B,T,12]
@@ -376,31 +488,30 @@ class FullModel(_ModelBase):
 
   def load_weights(self, weights):
     T = self.T
-    self._raw_weights = {k: np.asarray(v, np.float32) for k, v in weights.items()}
-    self._bn_layers = []
-    self._bn_dirty = False
+    self._begin_load(weights)
     w = self._load_controller(weights)
     sz = self.F
     for i in range(len(self.attn_pool)):
-      wi = np.asarray(weights['attn_cnn_w_%d' % i], np.float32)
+      wi = self._wi('attn_cnn_w_%d' % i)
       if i == 0:
-        wi = _pad_cin(wi, self.Dp)
+        wi = wi.map(lambda a: _pad_cin(a, self.Dp))
       w['acnn_w%d' % i] = self._pack(wi, sz, sz, self.attn_pool[i])
       sz //= self.attn_pool[i]
       sc, sh = _fold_bn(weights, 'attn_cnn', i, T, np.asarray(weights['attn_cnn_b_%d' % i], np.float32))
       w['acnn_scale%d' % i], w['acnn_shift%d' % i] = self._dev(sc), self._dev(sh)
-      self._load_bn(w, 'acnn', 'attn_cnn', i, weights)
+      self._load_bn(w, 'acnn', 'attn_cnn', i)
     for i in range(len(self.dcnn_pool)):
       sz *= self.dcnn_pool[i]
-      wi = _deconv_to_conv(np.asarray(weights['attn_dcnn_w_%d' % i], np.float32))
+      wi = self._wi('attn_dcnn_w_%d' % i).map(PM.deconv_to_conv)
       if i == len(self.attn_pool) and self.use_skip and self.skip_ch[i] > 0:
-        wi = _pad_cin(wi, wi.shape[2] - self.D + self.Dp)  # its skip input is the padded glimpse
+        cin = wi.val.shape[2] - self.D + self.Dp  # its skip input is the padded glimpse
+        wi = wi.map(lambda a: _pad_cin(a, cin))
       w['adcnn_w%d' % i] = self._pack(wi, sz, sz, 1)
       sc, sh = _fold_bn(weights, 'attn_dcnn', i, T, np.asarray(weights['attn_dcnn_b_%d' % i], np.float32))
       w['adcnn_scale%d' % i], w['adcnn_shift%d' % i] = self._dev(sc), self._dev(sh)
-      self._load_bn(w, 'adcnn', 'attn_dcnn', i, weights)
+      self._load_bn(w, 'adcnn', 'attn_dcnn', i)
     self.w = w
-    self.wd_term = self._weight_decay_term(weights)
+    self._set_wd_term(weights)
     return self
 
   def _alloc(self, B):
@@ -461,31 +572,41 @@ class FullModel(_ModelBase):
     T, H, W, F = self.T, self.H, self.W, self.F
     thw = T * H * W
     fork_score = int(self.n_chains) <= 1  # with sub-batch chains the side streams belong to the chains
+    tp = self._tape_on
+    n_a = len(self.attn_pool)
     for t in range(T):
       self._controller(bufs, t, train)
       box_t = bufs['box_all'][t]
+      fy, fx = self._filt(bufs, t)
       if knob is not None:
         # full_model.py:738-785: the attention-box OUTPUT comes from the controller's own box; then the matched noisy
         # GT box may replace centre / size, and the filters are rebuilt from the mixed box
-        ops.paste_back(None, box_t, bufs['fy'], bufs['fx'], None, attn_box=bufs['attn_box'][:, t], y_out=None,
+        ops.paste_back(None, box_t, fy, fx, None, attn_box=bufs['attn_box'][:, t], y_out=None,
                        out_bstride=thw, band=bufs['band'])
+        if tp is not None:  # the backward of the attention box runs through the PRE-mix box and filters
+          tp['box_pre'][t].copy_(box_t)
+          tp['fy0'][t].copy_(fy)
+          tp['fx0'][t].copy_(fx)
         if self.opt.get('use_iou_box', False):  # coordinate IoU of the (pre-mix) box, full_model.py:750-754
           ops.greedy_iou_box(box_t, knob['tl'], knob['br'], knob['iou_steps'][:, t], T * T, knob['grd'])
         else:
           ops.knob_greedy_box(bufs['attn_box'][:, t], thw, knob['rect'], H, W, knob['iou_steps'][:, t], T * T,
                               knob['grd'])
         ops.knob_mix_box(box_t, knob['grd'], knob['ctr'], knob['size'], knob['knob_box'][:, t], T)
-        ops.get_gaussian_filter(box_t, H, W, F, fy=bufs['fy'], fx=bufs['fx'], band=bufs['band'])
+        ops.get_gaussian_filter(box_t, H, W, F, fy=fy, fx=fx, band=bufs['band'])
       x_patch = bufs['x_patch_all'][t]
       _lib.TAG = 'extract'
-      ops.extract_patch(bufs['xs'], bufs['canvas'], self.chan_map, box_t, bufs['fy'], bufs['fx'], bufs['band'],
+      ops.extract_patch(bufs['xs'], bufs['canvas'], self.chan_map, box_t, fy, fx, bufs['band'],
                         tmp=bufs['extract_tmp'], out=x_patch)
       prev = x_patch
       _lib.TAG = 'attn_cnn'
+      acts = []
       for i, pl in enumerate(self.attn_pool):  # full_model.py:792
-        self._block(train, prev, w['acnn_w%d' % i], 'acnn', i, t, pl, out=bufs['acnn'][i])
-        prev = bufs['acnn'][i]
-      core = bufs['acnn'][-1]
+        dst = self._act(bufs, 'acnn', i, t)
+        self._block(train, prev, w['acnn_w%d' % i], 'acnn', i, t, pl, out=dst)
+        acts.append(dst)
+        prev = dst
+      core = acts[-1]
       # the score head (full_model.py:821-822) feeds only the loss: a parallel graph branch beside the mask head
       score_side = self._side_stream(bufs, 2) if fork_score else None
       if score_side is None:
@@ -494,25 +615,25 @@ class FullModel(_ModelBase):
         with torch.cuda.stream(score_side):
           ops.score(bufs['h_all'][t], core, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
       # full_model.py:797-807: skip list [None, h_acnn[4..0], x_patch]
-      skips = [None] + (bufs['acnn'][::-1][1:] + [x_patch])
+      skips = [None] + (acts[::-1][1:] + [x_patch])
       prev = core
       n_d = len(self.dcnn_pool)
       _lib.TAG = 'attn_dcnn'
       for i, pl in enumerate(self.dcnn_pool):
         sk = skips[i] if (self.use_skip and self.skip_ch[i] > 0) else None
-        dst = bufs['y_patch_all'][t] if i == n_d - 1 else bufs['adcnn'][i]
+        dst = bufs['y_patch_all'][t] if i == n_d - 1 else self._act(bufs, 'adcnn', i, t)
         self._block(train, prev, w['adcnn_w%d' % i], 'adcnn', i, t, 1, x2=sk, upsample=pl, out=dst)
         prev = dst
       _lib.TAG = 'paste_back'
       if knob is None:
-        ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], bufs['canvas'],
+        ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, fy, fx, bufs['canvas'],
                        attn_box=bufs['attn_box'][:, t], y_out=bufs['y_out'][:, t], out_bstride=thw,
                        disable_overwrite=self.disable_overwrite, band=bufs['band'])
       else:
         # the mask goes through the MIXED filters; the canvas write is decided per example by the mask switch, so
         # the fused canvas update runs on a scratch copy and knob_canvas writes the real one (full_model.py:826-845)
         knob['canvas_tmp'].copy_(bufs['canvas'])
-        ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, bufs['fy'], bufs['fx'], knob['canvas_tmp'],
+        ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, fy, fx, knob['canvas_tmp'],
                        attn_box=None, y_out=bufs['y_out'][:, t], out_bstride=thw,
                        disable_overwrite=self.disable_overwrite, band=bufs['band'])
         ops.knob_canvas(knob['grd'], knob['y_gt'], knob['noise'][:, t], T * H * W, knob['knob_segm'][:, t], T,
@@ -601,17 +722,27 @@ class FullModel(_ModelBase):
     if side is not None:
       cur.wait_stream(side)
     scal = ops.loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice, bufs['s_out'], s_gt, area,
-                          o['loss_mix_ratio'], self.wd_term)
+                          o['loss_mix_ratio'], 0.0)
+    self._add_wd(scal)
     out.update({
-        'attn_top_left_gt': tl, 'attn_bot_right_gt': br,
+        '_gt_rect': rect, 'attn_top_left_gt': tl, 'attn_bot_right_gt': br,
         'iou_soft_box_pairwise': iou_box, 'match_box': match_box, 'iou_soft_pairwise': iou_soft, 'match': match,
         'iou_hard_pairwise': iou_hard, 'loss_scalars': scal
     })
     if box_gt is not None:
       out['attn_box_gt'] = box_gt
 
-  def _run(self, bufs, B, with_loss, want_all, train=False, draws=None):
-    """Enqueue one full forward on the current stream; returns the dict of (static) output tensors."""
+  def _run(self, bufs, B, with_loss, want_all, train=False, draws=None, tape=False):
+    """Enqueue one full forward on the current stream; returns the dict of (static) output tensors.
+    tape=True (train_step): the forward records what the backward needs and the backward pass + the scatter of
+    the gradients into the flat bucket are enqueued right behind it."""
+    self._tape_on = bufs['tape'] if tape else None
+    try:
+      return self._run_inner(bufs, B, with_loss, want_all, train, draws, tape)
+    finally:
+      self._tape_on = None
+
+  def _run_inner(self, bufs, B, with_loss, want_all, train, draws, tape):
     st = bufs['static_in']
     gt = self._gt_boxes(bufs, st['y_gt'], want_all) if with_loss else None
     chains = self._chains(B)
@@ -649,7 +780,41 @@ class FullModel(_ModelBase):
       scal = out['loss_scalars']
       for i, k in enumerate(LOSS_KEYS):
         out[k] = scal[i]
+    if tape:
+      from . import train as TR
+      gs = bufs['grads']
+      TR.full_model_backward(self, gs, bufs, B, out, knob)
+      self._trainer.scatter(B, gs.entries)
     return out
+
+  def train_step(self, batch, draws=None, frozen=(), use_graph=True, grad_scale=None):
+    """``sess.run([loss, train_step], feed_dict)`` of runner.py:98-105 for the graph of full_model.py:1039-1057:
+    training-mode forward (batch-statistics BN, EMA shadows moved; scheduled sampling with the supplied `draws`),
+    backward pass, gradient all-reduce over the data-parallel ranks, clip_by_value(-1, 1), Adam(eps 1e-7) with the
+    staircase learning-rate decay, and the device-side refresh of every weight image.  `frozen`: weight keys the
+    freeze_* flags exclude (checkpoint.apply_pretrained); fixed at the first call.
+    Returns the loss scalars of the forward (evaluated BEFORE the update, like the reference's fetch) plus
+    'learn_rate' and 'global_step'."""
+    if self.w is None:
+      raise _lib.RecAttendError('load_weights() first')
+    if self.disable_overwrite:
+      raise _lib.RecAttendError('train_step: disable_overwrite=True is not used by any shipped config (SURVEY §9.7)')
+    if 'y_gt' not in batch or 's_gt' not in batch:
+      raise _lib.RecAttendError('train_step needs y_gt / s_gt')
+    if self._trainer is None:
+      from . import train as TR
+      self._trainer = TR.Trainer(self, frozen=frozen)
+    out = self.forward(batch, phase_train=True, use_graph=use_graph, draws=draws, _tape=True)
+    lr = self._trainer.apply(grad_scale=grad_scale)
+    res = {k: out[k] for k in LOSS_KEYS}
+    res['learn_rate'] = lr
+    res['global_step'] = self._trainer.optim.global_step
+    return res
+
+  @property
+  def optimizer(self):
+    """The AdamOptimizer behind train_step (None before the first step)."""
+    return None if self._trainer is None else self._trainer.optim
 
   def prefetch(self, batch):
     """Start copying the NEXT step's inputs (pinned host memory -> the idle static input set) on a copy
@@ -671,7 +836,7 @@ class FullModel(_ModelBase):
     done.record(cs)
     bufs['prefetched'] = (id(batch), slot, done, y_gt is not None)
 
-  def forward(self, batch, outputs=None, phase_train=False, with_loss=True, use_graph=True, draws=None):
+  def forward(self, batch, outputs=None, phase_train=False, with_loss=True, use_graph=True, draws=None, _tape=False):
     """``sess.run([model[k] for k in outputs], feed_dict)`` of runner.py:98-105.
     Returns a dict of CUDA tensors (all keys when ``outputs`` is None).  The inputs are copied into
     static device buffers; with ``use_graph`` the ~750 kernel launches of the T-step decode + loss block are
@@ -718,27 +883,34 @@ class FullModel(_ModelBase):
     with_loss = bool(with_loss and has_gt)
     want = None if outputs is None else set(outputs)
     want_all = want is None or bool(want & {'x_patch', 'y_out_patch', 'attn_box_gt'})
-    key = (with_loss, want_all, slot, bool(phase_train), draws is not None)
+    key = (with_loss, want_all, slot, bool(phase_train), draws is not None, bool(_tape))
     if phase_train and draws is not None:
       draws = self._stage_draws(bufs, draws)  # static device copies: the captured graph reads the same buffers
+    if _tape and 'tape' not in bufs:
+      from . import train as TR
+      bufs['tape'] = TR.alloc_tape(self, B, full=True)
+      bufs['grads'] = TR._alloc_grads(self, full=True)
     if not use_graph:
-      out = self._run(bufs, B, with_loss, want_all, train=bool(phase_train), draws=draws if phase_train else None)
+      out = self._run(bufs, B, with_loss, want_all, train=bool(phase_train), draws=draws if phase_train else None,
+                      tape=_tape)
     else:
       graphs = bufs.setdefault('graphs', {})
       if key not in graphs:
         # warm-up on a side stream (lazy weight packing, cudaFuncSetAttribute, allocator), then capture
         side = torch.cuda.Stream()
-        side.wait_stream(cur)
         train = bool(phase_train)
         ema_keep = None
         if train:  # the warm-up and the capture run must not move the EMA shadows: only replays count
-          ema_keep = {k: v.clone() for k, v in self.w.items() if '_ema_' in k}
+          ema_keep = {k: v.clone() for k, v in self.w.items()
+                      if '_ema_' in k and isinstance(v, torch.Tensor)}
+        side.wait_stream(cur)  # after the snapshot clones are enqueued on `cur`
         with torch.cuda.stream(side):
-          self._run(bufs, B, with_loss, want_all, train=train, draws=draws if train else None)
+          self._run(bufs, B, with_loss, want_all, train=train, draws=draws if train else None, tape=_tape)
         cur.wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-          static_out = self._run(bufs, B, with_loss, want_all, train=train, draws=draws if train else None)
+          static_out = self._run(bufs, B, with_loss, want_all, train=train, draws=draws if train else None,
+                                 tape=_tape)
         if ema_keep is not None:
           for k, v in ema_keep.items():
             self.w[k].copy_(v)

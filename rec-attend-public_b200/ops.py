@@ -307,7 +307,7 @@ def box_gt_step(attn_box_t, box_bstride, gt_rect, y_gt, noise_t, noise_bstride, 
 
 # ----------------------------------------------------------------------------- training-mode conv block
 def batch_norm_train_block(x_raw, gamma, beta, ema_mean=None, ema_var=None, pool=1, relu=True, eps=1e-3, decay=0.9,
-                           out=None):
+                           out=None, batch_mean=None, batch_var=None):
   """nnlib.batch_norm with phase_train=True (nnlib.py:65-128) + activation + max-pool (nnlib.py:229-253) on the raw
   convolution output x_raw [B,H,W,C] (bias included): batch moments, EMA shadows updated IN PLACE
   (shadow -= (1-decay)(shadow - batch)), y = pool(relu(bn(x))).  Returns (y, batch_mean, batch_var)."""
@@ -320,8 +320,9 @@ def batch_norm_train_block(x_raw, gamma, beta, ema_mean=None, ema_var=None, pool
   ws = torch.empty((n_ws,), device=dev, dtype=torch.float32)
   if out is None:
     out = torch.empty((B, H // pool, W // pool, C), device=dev, dtype=torch.float32)
-  bm = torch.empty((C,), device=dev, dtype=torch.float32)
-  bv = torch.empty((C,), device=dev, dtype=torch.float32)
+  bm = torch.empty((C,), device=dev, dtype=torch.float32) if batch_mean is None else batch_mean
+  bv = torch.empty((C,), device=dev, dtype=torch.float32) if batch_var is None else batch_var
+  _chk(bm, bv)
   _lib.call('ra_bn_train_block_f32', _p(x_raw), B, H, W, C, _p(gamma), _p(beta), float(eps), float(decay), pool,
             1 if relu else 0, _p(ws), _p(ema_mean), _p(ema_var), _p(bm), _p(bv), _p(out), _stream())
   return out, bm, bv

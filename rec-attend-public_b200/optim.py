@@ -106,7 +106,7 @@ class AdamOptimizer(object):
     self.clip = float(opt.get('clip_gradient', 1.0))
     self.global_step = 0  # the reference keeps it as a float variable (full_model.py:587); an int here
 
-  def step(self, grad_flat):
+  def step(self, grad_flat, grad_scale=None):
     """One train_step: all-reduce(SUM) of `grad_flat` in place, then clip + Adam in one launch.
     `grad_flat` = this rank's gradient of the DATA loss of its batch shard, each rank's loss being the mean over its
     own examples (so the average over ranks is the global-batch mean for equal shards)."""
@@ -117,8 +117,12 @@ class AdamOptimizer(object):
     world = all_reduce_sum_(grad_flat)
     lr = learn_rate(self.opt, self.global_step)
     self.global_step += 1
+    # grad_scale: this rank's weight in the global-batch mean AFTER the SUM all-reduce; 1/world for equal shards.
+    # Unequal shards: every rank passes its own shard_size / global_batch BEFORE calling (scale the bucket) - see
+    # dist_util.shard, which refuses uneven splits for training.
+    scale = (1.0 / world) if grad_scale is None else float(grad_scale)
     _lib.call('ra_adam_step_f32', ops._p(self.params), ops._p(grad_flat), ops._p(self.m), ops._p(self.v),
-              ops._p(self.wd), self.params.numel(), 1.0 / world, lr, ADAM_BETA1, ADAM_BETA2, ADAM_EPS, self.clip,
+              ops._p(self.wd), self.params.numel(), scale, lr, ADAM_BETA1, ADAM_BETA2, ADAM_EPS, self.clip,
               self.global_step, ops._stream())
     return lr
 

@@ -1,0 +1,195 @@
+"""GPU parity of the TRAINING STEP (FullModel.train_step / BoxModel.train_step; runner.py:98-105 driving
+full_model.py:1039-1057 / box_model.py:635-652) against the training-step oracle (oracle/grads.py, pinned to the
+reference graph by central differences of the reference's own loss, tests/golden/reference_fd_golden.npz).
+
+What can and cannot be asserted.  The loss is stiff in the controller weights (sigmoid box edges: fp32 and float64
+gradients of the SAME oracle agree only to ~10 % there, tests/test_train_step_oracle.py), so every gradient tensor is
+held to the float64 oracle with the fp32 oracle's own deviation as the yardstick:
+    |g_gpu - g_64| <= max(TOL * scale, K * |g_32 - g_64|)   and   cos(g_gpu, g_64) high.
+The optimiser tail is exact arithmetic on given gradients: parameters after the step are compared BIT FOR BIT with
+oracle.optim.adam_step fed with the GPU's own gradient bucket, and the device weight images after the device-side
+re-pack with a fresh model loaded from the exported weights."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import oracle_fp64, rel_err
+from oracle import grads as OG
+from oracle import model as OM
+from oracle import optim as OO
+
+pytestmark = pytest.mark.gpu
+
+TOL, K = 2e-3, 5.0
+
+
+def _f64(d):
+  return None if d is None else {k: np.asarray(v, np.float64) for k, v in d.items()}
+
+
+def _oracle_grads(opt, weights, batch, draws, box=False, noise=None):
+  O64 = oracle_fp64()
+  torch.set_default_dtype(torch.float64)
+  try:
+    if box:
+      g64, _ = OG.box_model_grads(opt, _f64(weights), _f64(batch), canvas_noise=noise, include_weight_decay=False,
+                                  model_module=O64, dtype=torch.float64)
+    else:
+      g64, _ = OG.full_model_grads(opt, _f64(weights), _f64(batch), draws=_f64(draws), include_weight_decay=False,
+                                   model_module=O64, dtype=torch.float64)
+  finally:
+    torch.set_default_dtype(torch.float32)
+  if box:
+    g32, out32 = OG.box_model_grads(opt, weights, batch, canvas_noise=noise, include_weight_decay=False)
+  else:
+    g32, out32 = OG.full_model_grads(opt, weights, batch, draws=draws, include_weight_decay=False)
+  return g64, g32, out32
+
+
+def _check_grads(gpu, g64, g32, keys):
+  bad = []
+  for k in keys:
+    a, r64, r32 = np.asarray(gpu[k], np.float64), np.asarray(g64[k], np.float64), np.asarray(g32[k], np.float64)
+    assert a.shape == r64.shape, k
+    scale = float(np.abs(r64).max())
+    if scale < 1e-7:  # conv bias in front of a batch-statistics BN: exactly zero gradient, pure round-off
+      if float(np.abs(a).max()) > 1e-4:
+        bad.append((k, 'nonzero', float(np.abs(a).max())))
+      continue
+    e_gpu, e_ref = float(np.abs(a - r64).max()), float(np.abs(r32 - r64).max())
+    cos = float(a.ravel() @ r64.ravel() / max(np.linalg.norm(a) * np.linalg.norm(r64), 1e-30))
+    if not (e_gpu <= max(TOL * scale, K * e_ref) and cos > 0.9):
+      bad.append((k, e_gpu / scale, e_ref / scale, cos))
+  assert not bad, bad
+
+
+def _flat_to_dict(model):
+  tr = model._trainer
+  return tr.optim.flat.unflatten(tr.grad_flat.cpu().numpy())
+
+
+CASES = [
+    ('cvppp', 64, 64, 2, 3, False),
+    ('kitti', 64, 128, 2, 4, False),
+    ('kitti', 64, 128, 2, 4, True),
+    ('cityscapes', 64, 128, 2, 4, True),   # use_iou_box: the box loss reaches the controller through coordinates
+]
+
+
+@pytest.mark.parametrize('arch,H,W,T,B,knob', CASES)
+def test_full_model_gradients(cuda, arch, H, W, T, B, knob):
+  import rec_attend_b200 as ra
+  from rec_attend_b200 import train as TR
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt(arch, H, W, T, use_knob=knob)
+  batch = ra.synthetic.make_batch(opt, B, seed=21)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  draws = None
+  if knob:
+    draws = ra.synthetic.make_knob_draws(opt, B, global_step=9000, seed=3)
+    draws['gt_knob_box'][:, 0] = [1, 0, 1, 0][:B]
+    draws['gt_knob_segm'][:, 0] = [0, 1, 1, 0][:B]
+  g64, g32, out32 = _oracle_grads(opt, weights, batch, draws)
+  model = FullModel(opt).load_weights(weights)
+  model._trainer = TR.Trainer(model)
+  for use_graph in (False, True):
+    out = model.forward(batch, phase_train=True, draws=draws, use_graph=use_graph, _tape=True)
+    torch.cuda.synchronize()
+    gpu = _flat_to_dict(model)
+    keys = model._trainer.optim.flat.keys
+    assert set(keys) == set(k for k in g64)
+    # every trainable element is written by exactly one gradient tensor
+    tb = model._trainer._scatter[B]
+    assert tb['covered'] == model._trainer.optim.params.numel()
+    assert rel_err(out['loss'].cpu().numpy(), out32['loss'].numpy()) < 2e-3
+    _check_grads(gpu, g64, g32, keys)
+
+
+def test_box_model_gradients(cuda):
+  import rec_attend_b200 as ra
+  from rec_attend_b200 import train as TR
+  from rec_attend_b200.box_model import BoxModel
+  for use_iou_box in (False, True):
+    opt = ra.config.box_model_opt(64, 128, 3, use_iou_box=use_iou_box)
+    B = 4
+    batch = ra.synthetic.make_batch(opt, B, seed=5)
+    weights = ra.synthetic.make_weights(opt, seed=77, model='box')
+    noise = np.random.default_rng(1).uniform(0, 0.3, (B, 3, 64, 128)).astype(np.float32)
+    g64, g32, out32 = _oracle_grads(opt, weights, batch, None, box=True, noise=noise)
+    model = BoxModel(opt).load_weights(weights)
+    model._trainer = TR.Trainer(model)
+    out = model.forward(dict(batch, canvas_noise=noise), phase_train=True, _tape=True)
+    torch.cuda.synchronize()
+    assert rel_err(out['loss'].cpu().numpy(), out32['loss'].numpy()) < 2e-3
+    assert model._trainer._scatter[B]['covered'] == model._trainer.optim.params.numel()
+    _check_grads(_flat_to_dict(model), g64, g32, model._trainer.optim.flat.keys)
+
+
+def test_train_step_optimiser_tail_and_device_repack(cuda):
+  """One train_step: parameters == oracle Adam on the GPU's own gradients (bit for bit); the device weight images
+  after ra_param_gather_f32 == a fresh model loaded from the exported weights; EMA shadows moved; the eval forward
+  after the step uses the new weights; loss falls over a few steps on a fixed batch."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt('kitti', 64, 128, 2, use_knob=False)
+  B = 4
+  batch = ra.synthetic.make_batch(opt, B, seed=9)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  model = FullModel(opt).load_weights(weights)
+  ev0 = {k: v.clone() for k, v in model.forward(batch, outputs=['y_out', 'loss']).items()}  # captures an eval graph
+  res = model.train_step(batch)
+  torch.cuda.synchronize()
+  tr = model._trainer
+  flat = tr.optim.flat
+  g = flat.unflatten(tr.grad_flat.cpu().numpy())
+  keys = flat.keys
+  var = {k: np.asarray(weights[k], np.float32) for k in keys}
+  zeros = {k: np.zeros_like(var[k]) for k in keys}
+  wd = {k: (np.float32(opt['weight_decay']) if OG.has_weight_decay(k) else 0.0) for k in keys}
+  lr = OO.learn_rate(opt['base_learn_rate'], opt['learn_rate_decay'], opt['steps_per_learn_rate_decay'], 0)
+  new_var, m1, v1 = OO.adam_step(var, g, zeros, dict(zeros), wd, lr, 1, clip=1.0)
+  got = flat.unflatten(tr.optim.params.cpu().numpy())
+  for k in keys:
+    assert np.array_equal(got[k], new_var[k]), k
+  assert res['global_step'] == 1 and abs(res['learn_rate'] - float(lr)) < 1e-12
+  # exported weights = updated parameters + moved EMA shadows; a fresh model loaded from them must agree with the
+  # device-side re-pack (same eval forward) - and differ from the forward before the step
+  new_w = model.export_weights()
+  for k in keys:
+    assert np.array_equal(new_w[k], new_var[k]), k
+  assert rel_err(new_w['ctrl_cnn_3_1_ema_var'], weights['ctrl_cnn_3_1_ema_var']) > 1e-3
+  ev1 = model.forward(batch, outputs=['y_out', 'loss'])
+  fresh = FullModel(opt).load_weights(new_w).forward(batch, outputs=['y_out', 'loss'])
+  torch.cuda.synchronize()
+  assert rel_err(ev1['y_out'].cpu().numpy(), fresh['y_out'].cpu().numpy()) < 1e-5
+  assert abs(float(ev1['loss']) - float(fresh['loss'])) < 1e-5
+  assert rel_err(ev1['y_out'].cpu().numpy(), ev0['y_out'].cpu().numpy()) > 1e-4
+  # the oracle's eval forward on the exported weights agrees as well
+  ref = OM.full_model_forward(opt, new_w, batch)
+  assert rel_err(ev1['y_out'].cpu().numpy(), ref['y_out'].numpy()) < 1e-3
+  # learning: the training loss on this fixed batch falls
+  first = float(res['loss'])
+  for _ in range(15):
+    res = model.train_step(batch)
+  torch.cuda.synchronize()
+  assert float(res['loss']) < first, (first, float(res['loss']))
+  assert res['global_step'] == 16
+
+
+def test_load_weights_after_graph_capture_uses_new_weights(cuda):
+  """load_weights on a model that has already replayed a CUDA graph must not replay graphs that
+  point at the old weight tensors."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt('cvppp', 64, 64, 2)
+  batch = ra.synthetic.make_batch(opt, 2, seed=1)
+  w1, w2 = ra.synthetic.make_weights(opt, seed=1), ra.synthetic.make_weights(opt, seed=2)
+  model = FullModel(opt).load_weights(w1)
+  a = model.forward(batch)['y_out'].clone()
+  model.forward(batch)
+  model.load_weights(w2)
+  b = model.forward(batch)['y_out'].clone()
+  fresh = FullModel(opt).load_weights(w2).forward(batch)['y_out']
+  torch.cuda.synchronize()
+  assert torch.equal(b, fresh)
+  assert not torch.equal(a, b)
