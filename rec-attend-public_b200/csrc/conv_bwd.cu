@@ -152,92 +152,189 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const float *__restric
 
 // ---------------------------------------------------------------------------------------------- weight gradient
 // dW[t][ci][co] = sum over output pixels (b, Y, X) of Z[b, Y+ky-up, X+kx-up, ci] * G[b, Y, X, co], Z = the zero-padded
-// input, zero-inserted for up = 2 (Z[2y,2x] = x[y,x]; the tap offset is -up, the forward kernel's convention), t = ky*3+kx.  Grid (pixel chunk, tap, channel block); a CTA stages 32 output pixels of G and of
-// the shifted input in shared memory and every thread accumulates an (8 ci) x (6 co) register tile:
-// thread (ti, tj) of the 16 x 16 CTA owns ci = ti + 16*i, co = tj + 16*j inside the channel block of 128 x 96.
-constexpr int kWgPix = 32;
-constexpr int kWgCi = 128, kWgCo = 96;
-constexpr int kWgI = kWgCi / 16, kWgJ = kWgCo / 16;
+// input, zero-inserted for up = 2 (Z[2y,2x] = x[y,x]; the tap offset is -up, the forward kernel's convention), t = ky*3+kx.
+//
+// A CTA walks spatial tiles of kWgTH x kWgTW output pixels (persistent over tiles, grid.x), for one block of CI_B x CO_B
+// channels (grid.y).  Per tile it stages the (TH+2) x (TW+2) input window [slot][CI_B] and the gradient tile
+// [pixel][CO_B] in shared memory; every thread keeps an RI x RJ register tile for ALL NINE taps (9*RI*RJ accumulators):
+// per pixel one vector load of G and nine of the shifted inputs feed 9*RI*RJ FMAs.  Lanes of a warp differ in the
+// output-channel index first, so the input loads are broadcasts and the gradient loads are conflict-free.  Channel blocks
+// narrower than 256 / ((CI_B/RI) * (CO_B/RJ)) threads are replicated over PG pixel groups (each takes every PG-th pixel)
+// and summed through shared memory at the end.  Partials per CTA are added in a fixed order by the finalize kernel:
+// bit-identical from run to run.
+constexpr int kWgTH = 4, kWgTW = 64, kWgTWP = kWgTW + 2;
+constexpr int kWgSlots = (kWgTH + 2) * kWgTWP, kWgPix = kWgTH * kWgTW;
 
-__global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const float *__restrict__ x1, int C1, int x1_bmod,
-                                                             const float *__restrict__ x2, int C2,
-                                                             const float *__restrict__ g, int B, int Hin, int Win,
-                                                             int Cout, int up, int n_ci_blk,
-                                                             float *__restrict__ partial /* [chunks][9][Cin][Cout] */,
-                                                             float *__restrict__ db_partial /* [chunks][Cout] */) {
-  __shared__ float xs[kWgPix][kWgCi + 1];
-  __shared__ float gs[kWgPix][kWgCo + 1];
-  const int Cin = C1 + C2;
-  const int Ho = Hin * up, Wo = Win * up;
-  const int t = blockIdx.y, ky = t / 3, kx = t - ky * 3;
-  const int cb = blockIdx.z, ci_blk = cb % n_ci_blk, co_blk = cb / n_ci_blk;
-  const int ci0 = ci_blk * kWgCi, co0 = co_blk * kWgCo;
-  const int nci = min(kWgCi, Cin - ci0), nco = min(kWgCo, Cout - co0);
-  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
-  float acc[kWgI][kWgJ];
+struct WgParams {
+  const float *x1, *x2, *g;
+  int C1, C2, x1_bmod, N, Hin, Win, Cout, up;
+  int CI_B, CO_B, TI, TJ, PG;  // channel block, threads along ci / co, pixel groups (TI*TJ*PG == 256)
+  int tiles_x, tiles_y, n_tiles, n_ci_blk;
+  float *partial;     // [grid.x][9][Cin][Cout]
+  float *db_partial;  // [grid.x][Cout] or nullptr
+};
+
+template <int RI, int RJ>
+__global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
+  extern __shared__ __align__(16) float wg_smem[];
+  const int CI_B = p.CI_B, CO_B = p.CO_B;
+  float *xs = wg_smem;                          // [kWgSlots][CI_B]
+  float *gs = wg_smem + (size_t)kWgSlots * CI_B;  // [kWgPix][CO_B]
+  const int Cin = p.C1 + p.C2;
+  const int Ho = p.Hin * p.up, Wo = p.Win * p.up;
+  const int ci_blk = blockIdx.y % p.n_ci_blk, co_blk = blockIdx.y / p.n_ci_blk;
+  const int ci0 = ci_blk * CI_B, co0 = co_blk * CO_B;
+  const int nci = min(CI_B, Cin - ci0), nco = min(CO_B, p.Cout - co0);
+  const int tj = threadIdx.x % p.TJ, ti = (threadIdx.x / p.TJ) % p.TI, pg = threadIdx.x / (p.TJ * p.TI);
+  float acc[9][RI][RJ];
 #pragma unroll
-  for (int i = 0; i < kWgI; ++i)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int j = 0; j < kWgJ; ++j) acc[i][j] = 0.f;
-  float db_acc = 0.f;  // threads < nco of the (tap 0, ci block 0) CTAs: column sums of G for the bias gradient
-  const bool do_db = (t == 0 && ci_blk == 0 && db_partial != nullptr);
-  const size_t npix = (size_t)B * Ho * Wo;
-  const size_t per = (npix + gridDim.x - 1) / gridDim.x;
-  const size_t p_begin = (size_t)blockIdx.x * per, p_end = min(npix, p_begin + per);
-  for (size_t p0 = p_begin; p0 < p_end; p0 += kWgPix) {
-    const int np = (int)min((size_t)kWgPix, p_end - p0);
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < kWgPix * nco; idx += kT) {
-      const int p = idx / nco, c = idx - p * nco;
-      gs[p][c] = (p < np) ? g[(p0 + p) * Cout + co0 + c] : 0.f;
-    }
-    for (int idx = threadIdx.x; idx < kWgPix * nci; idx += kT) {
-      const int p = idx / nci, c = idx - p * nci;
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+      for (int j = 0; j < RJ; ++j) acc[t][i][j] = 0.f;
+  float dbv[RJ];
+#pragma unroll
+  for (int j = 0; j < RJ; ++j) dbv[j] = 0.f;
+  const bool do_db = (ci_blk == 0 && p.db_partial != nullptr && ti == 0);
+
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % p.tiles_x;
+    t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int b = t / p.tiles_y;
+    const int y0 = ty * kWgTH, x0 = tx * kWgTW;
+    __syncthreads();  // the previous tile has been consumed
+    // ---- input window: slot (r, c) <-> zero-inserted pixel (y0 - up + r, x0 - up + c)
+    for (int idx = threadIdx.x; idx < kWgSlots * CI_B; idx += kT) {
+      const int slot = idx / CI_B, c = idx - slot * CI_B;
+      const int r = slot / kWgTWP, col = slot - r * kWgTWP;
+      const int zy = y0 - p.up + r, zx = x0 - p.up + col;
       float v = 0.f;
-      if (p < np) {
-        size_t q = p0 + p;
-        const int X = (int)(q % Wo);
-        q /= Wo;
-        const int Y = (int)(q % Ho);
-        const int b = (int)(q / Ho);
-        const int zy = Y + ky - up, zx = X + kx - up;  // coordinate in the zero-inserted input (conv.cu: oy - up + r)
-        if (zy >= 0 && zy < Ho && zx >= 0 && zx < Wo && (zy % up) == 0 && (zx % up) == 0) {
-          const size_t src = ((size_t)b * Hin + zy / up) * Win + zx / up;
-          const int ci = ci0 + c;
-          if (ci < C1) {
-            const size_t src1 = ((size_t)(x1_bmod > 0 ? b % x1_bmod : b) * Hin + zy / up) * Win + zx / up;
-            v = x1[src1 * C1 + ci];
-          } else {
-            v = x2[src * C2 + (ci - C1)];
-          }
+      if (c < nci && zy >= 0 && zy < Ho && zx >= 0 && zx < Wo && (p.up == 1 || (((zy | zx) & 1) == 0))) {
+        const int iy = p.up == 1 ? zy : zy >> 1, ix = p.up == 1 ? zx : zx >> 1;
+        const int ci = ci0 + c;
+        if (ci < p.C1) {
+          const size_t src = ((size_t)(p.x1_bmod > 0 ? b % p.x1_bmod : b) * p.Hin + iy) * p.Win + ix;
+          v = __ldg(p.x1 + src * p.C1 + ci);
+        } else {
+          const size_t src = ((size_t)b * p.Hin + iy) * p.Win + ix;
+          v = __ldg(p.x2 + src * p.C2 + (ci - p.C1));
         }
       }
-      xs[p][c] = v;
+      xs[idx] = v;
+    }
+    // ---- gradient tile
+    for (int idx = threadIdx.x; idx < kWgPix * CO_B; idx += kT) {
+      const int pix = idx / CO_B, c = idx - pix * CO_B;
+      const int py = pix / kWgTW, px = pix - py * kWgTW;
+      const int Y = y0 + py, X = x0 + px;
+      float v = 0.f;
+      if (c < nco && Y < Ho && X < Wo) v = __ldg(p.g + (((size_t)b * Ho + Y) * Wo + X) * p.Cout + co0 + c);
+      gs[idx] = v;
     }
     __syncthreads();
-    for (int p = 0; p < np; ++p) {
-      float xv[kWgI], gv[kWgJ];
+    const float *xb = xs + ti * RI;
+    const float *gb = gs + tj * RJ;
+    for (int pix = pg; pix < kWgPix; pix += p.PG) {
+      const int py = pix / kWgTW, px = pix - py * kWgTW;
+      float gv[RJ];
+      if constexpr (RJ == 2) {  // 8-byte aligned: CO_B and tj * RJ are even
+        const float2 t2 = *reinterpret_cast<const float2 *>(gb + pix * CO_B);
+        gv[0] = t2.x;
+        gv[1] = t2.y;
+      } else {
 #pragma unroll
-      for (int i = 0; i < kWgI; ++i) xv[i] = (ti + 16 * i < nci) ? xs[p][ti + 16 * i] : 0.f;
+        for (int j = 0; j < RJ; ++j) gv[j] = gb[pix * CO_B + j];
+      }
+      if (do_db) {
 #pragma unroll
-      for (int j = 0; j < kWgJ; ++j) gv[j] = (tj + 16 * j < nco) ? gs[p][tj + 16 * j] : 0.f;
+        for (int j = 0; j < RJ; ++j) dbv[j] += gv[j];
+      }
+      const float *xr = xb + (size_t)(py * kWgTWP + px) * CI_B;
 #pragma unroll
-      for (int i = 0; i < kWgI; ++i)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int j = 0; j < kWgJ; ++j) acc[i][j] = fmaf(xv[i], gv[j], acc[i][j]);
+        for (int kx = 0; kx < 3; ++kx) {
+          float xv[RI];
+          if constexpr (RI == 2) {
+            const float2 t2 = *reinterpret_cast<const float2 *>(xr + (ky * kWgTWP + kx) * CI_B);
+            xv[0] = t2.x;
+            xv[1] = t2.y;
+          } else {
+#pragma unroll
+            for (int i = 0; i < RI; ++i) xv[i] = xr[(ky * kWgTWP + kx) * CI_B + i];
+          }
+#pragma unroll
+          for (int i = 0; i < RI; ++i)
+#pragma unroll
+            for (int j = 0; j < RJ; ++j) acc[ky * 3 + kx][i][j] = fmaf(xv[i], gv[j], acc[ky * 3 + kx][i][j]);
+        }
     }
-    if (do_db && threadIdx.x < nco)
-      for (int p = 0; p < np; ++p) db_acc += gs[p][threadIdx.x];
   }
-  float *out = partial + ((size_t)blockIdx.x * 9 + t) * Cin * Cout;
+  // ---- sum the pixel groups through shared memory (fixed order), write this CTA's partial
+  __syncthreads();
+  float *red = wg_smem;  // [PG][9][CI_B][CO_B]  (+ [PG][CO_B] for db)
+  const int blk = 9 * CI_B * CO_B;
 #pragma unroll
-  for (int i = 0; i < kWgI; ++i)
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int j = 0; j < kWgJ; ++j) {
-      const int ci = ti + 16 * i, co = tj + 16 * j;
-      if (ci < nci && co < nco) out[(size_t)(ci0 + ci) * Cout + co0 + co] = acc[i][j];
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+      for (int j = 0; j < RJ; ++j) red[(size_t)pg * blk + (t * CI_B + ti * RI + i) * CO_B + tj * RJ + j] = acc[t][i][j];
+  float *dbred = red + (size_t)p.PG * blk;
+  if (do_db) {
+#pragma unroll
+    for (int j = 0; j < RJ; ++j) dbred[pg * CO_B + tj * RJ + j] = dbv[j];
+  }
+  __syncthreads();
+  float *out = p.partial + (size_t)blockIdx.x * 9 * Cin * p.Cout;
+  for (int idx = threadIdx.x; idx < blk; idx += kT) {
+    const int co = idx % CO_B, r = idx / CO_B, ci = r % CI_B, t = r / CI_B;
+    if (ci >= nci || co >= nco) continue;
+    float s = 0.f;
+    for (int g = 0; g < p.PG; ++g) s += red[(size_t)g * blk + idx];
+    out[((size_t)t * Cin + ci0 + ci) * p.Cout + co0 + co] = s;
+  }
+  if (ci_blk == 0 && p.db_partial != nullptr)
+    for (int co = threadIdx.x; co < nco; co += kT) {
+      float s = 0.f;
+      for (int g = 0; g < p.PG; ++g) s += dbred[g * CO_B + co];
+      p.db_partial[(size_t)blockIdx.x * p.Cout + co0 + co] = s;
     }
-  if (do_db && threadIdx.x < nco) db_partial[(size_t)blockIdx.x * Cout + co0 + threadIdx.x] = db_acc;
+}
+
+// channel blocking of the weight-gradient kernel for a layer shape
+struct WgPlan {
+  int RI, CI_B, CO_B, TI, TJ, PG, n_ci_blk, n_co_blk, ctas;
+  size_t smem;
+};
+
+WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
+  WgPlan w;
+  if (Cin == 1) {  // the canvas channel of the first controller layer: 1 x 16 threads, 16 pixel groups
+    w.RI = 1;
+    w.CI_B = 1;
+    w.CO_B = 16;
+  } else {
+    w.RI = 2;
+    w.CI_B = Cin <= 16 ? 16 : 32;
+    w.CO_B = Cout <= 16 ? 16 : 32;
+  }
+  w.TI = w.CI_B / w.RI;
+  w.TJ = w.CO_B / w.RI;
+  w.PG = kT / (w.TI * w.TJ);
+  w.n_ci_blk = (Cin + w.CI_B - 1) / w.CI_B;
+  w.n_co_blk = (Cout + w.CO_B - 1) / w.CO_B;
+  const size_t stage = ((size_t)kWgSlots * w.CI_B + (size_t)kWgPix * w.CO_B) * sizeof(float);
+  const size_t red = ((size_t)w.PG * 9 * w.CI_B * w.CO_B + (size_t)w.PG * w.CO_B) * sizeof(float);
+  w.smem = stage > red ? stage : red;
+  const size_t n_tiles = (size_t)N * ((Ho + kWgTH - 1) / kWgTH) * ((Wo + kWgTW - 1) / kWgTW);
+  size_t cap = (size_t)ra::kNumSMs * 2 / ((size_t)w.n_ci_blk * w.n_co_blk);
+  if (cap < 16) cap = 16;
+  w.ctas = (int)(n_tiles < cap ? (n_tiles < 1 ? 1 : n_tiles) : cap);
+  return w;
 }
 
 // dw[i] = sum over chunks (fixed order, double); same for db
@@ -280,12 +377,6 @@ __global__ void filter_flip_transpose_kernel(const float *__restrict__ w, int Ci
 int bwd_ctas(size_t total) {
   size_t want = (total + kT - 1) / kT;
   const size_t cap = (size_t)ra::kNumSMs * 4;
-  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-}
-
-int wg_chunks(size_t npix) {
-  size_t want = (npix + 8 * kWgPix - 1) / (8 * kWgPix);  // at least 8 staged tiles per CTA
-  const size_t cap = (size_t)ra::kNumSMs;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
@@ -345,7 +436,7 @@ extern "C" int ra_bn_train_block_bwd_grouped_f32(const float *raw, const float *
 
 extern "C" size_t ra_conv3x3_bwd_weight_workspace(int B, int Hin, int Win, int Cin, int Cout, int upsample) {
   if (B < 1 || Hin < 1 || Win < 1 || Cin < 1 || Cout < 1 || (upsample != 1 && upsample != 2)) return 0;
-  const int chunks = wg_chunks((size_t)B * Hin * upsample * Win * upsample);
+  const int chunks = wg_plan(B, Hin * upsample, Win * upsample, Cin, Cout).ctas;
   return ((size_t)chunks * 9 * Cin * Cout + (size_t)chunks * Cout) * sizeof(float);
 }
 
@@ -369,15 +460,33 @@ extern "C" int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod
     return ra::finish_launch("cudaMemsetAsync(dw)");
   }
   if (!x1 || (C2 > 0 && !x2) || !d_out || !ws) return RA_ERR_INVALID_ARG;
-  const size_t npix = (size_t)B * Hin * upsample * Win * upsample;
-  const int chunks = wg_chunks(npix);
-  const int n_ci_blk = (Cin + kWgCi - 1) / kWgCi, n_co_blk = (Cout + kWgCo - 1) / kWgCo;
-  if ((size_t)n_ci_blk * n_co_blk > 65535) return RA_ERR_UNSUPPORTED;
+  const int Ho = Hin * upsample, Wo = Win * upsample;
+  const WgPlan w = wg_plan(B, Ho, Wo, Cin, Cout);
+  const int chunks = w.ctas;
+  if ((size_t)w.n_ci_blk * w.n_co_blk > 65535) return RA_ERR_UNSUPPORTED;
   float *partial = reinterpret_cast<float *>(ws);
   float *db_partial = partial + (size_t)chunks * 9 * Cin * Cout;
-  conv_bwd_weight_kernel<<<dim3(chunks, 9, n_ci_blk * n_co_blk), kT, 0, s>>>(x1, C1, x1_bmod, x2, C2, d_out, B, Hin, Win,
-                                                                            Cout, upsample, n_ci_blk, partial,
-                                                                            db ? db_partial : nullptr);
+  WgParams p;
+  p.x1 = x1; p.x2 = x2; p.g = d_out;
+  p.C1 = C1; p.C2 = C2; p.x1_bmod = x1_bmod; p.N = B; p.Hin = Hin; p.Win = Win; p.Cout = Cout; p.up = upsample;
+  p.CI_B = w.CI_B; p.CO_B = w.CO_B; p.TI = w.TI; p.TJ = w.TJ; p.PG = w.PG;
+  p.tiles_x = (Wo + kWgTW - 1) / kWgTW;
+  p.tiles_y = (Ho + kWgTH - 1) / kWgTH;
+  p.n_tiles = B * p.tiles_x * p.tiles_y;
+  p.n_ci_blk = w.n_ci_blk;
+  p.partial = partial;
+  p.db_partial = db ? db_partial : nullptr;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_done = true;
+  }
+  const dim3 grid(chunks, w.n_ci_blk * w.n_co_blk);
+  if (w.RI == 2)
+    conv_bwd_weight_kernel<2, 2><<<grid, kT, w.smem, s>>>(p);
+  else
+    conv_bwd_weight_kernel<1, 1><<<grid, kT, w.smem, s>>>(p);
   int rc = ra::finish_launch("conv_bwd_weight_kernel");
   if (rc != RA_OK) return rc;
   const size_t n = (size_t)9 * Cin * Cout;

@@ -152,13 +152,16 @@ def _wgrad(x1, d_out, dw, db=None, x2=None, upsample=1, x1_bmod=0):
 
 def _dgrad(m, wp, d_raw, upsample):
   """Input gradient of the layer: SAME convolution with the flipped / transposed filter (odd positions for the
-  transposed-conv layers).  d_raw [N,Ho,Wo,Cout] -> [N,Ho/up,Wo/up,Cin]."""
-  wb = m._wb_dev(wp)
-  Cin = wb.shape[3]
-  if 'bwd_one' not in wp:
-    wp['bwd_one'] = torch.ones(Cin, device=m.device)
-    wp['bwd_zero'] = torch.zeros(Cin, device=m.device)
-  full = ops.conv3x3_block(d_raw, wb, wp['bwd_one'], wp['bwd_zero'], pool=1, relu=False)
+  transposed-conv layers) - on the tensor cores, like the forward layers (3xTF32; the packed image of the flipped
+  filter is one more registered weight image).  d_raw [N,Ho,Wo,Cout] -> [N,Ho/up,Wo/up,Cin]."""
+  if 'bwd' not in wp:
+    _, Ho, Wo, _ = d_raw.shape
+    wi = PM.WI(wp['w'], wp['idx']).map(PM.flip_transpose)
+    wp['bwd'] = m._pack(wi, Ho, Wo, 1)
+    wp['bwd_one'] = torch.ones(wi.val.shape[3], device=m.device)
+    wp['bwd_zero'] = torch.zeros(wi.val.shape[3], device=m.device)
+  Cin = wp['bwd']['w'].shape[3]
+  full = m._conv(d_raw, wp['bwd'], wp['bwd_one'], wp['bwd_zero'], 1, relu=False)
   if upsample == 1:
     return full
   N, H2, W2, _ = full.shape
