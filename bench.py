@@ -11,6 +11,12 @@ Default workload = BASELINE.json configs[2] (KITTI-arch 256x512, T=20, B=32 per 
 configuration the metric is quoted on; it fits one GPU.  Multi-GPU: one process per GPU
 (torchrun), the batch shards with no data-path collective (eval forward) -> weak scaling.
 
+The same line carries, under "train_step", the TRAINING step of the same workload (taped
+training-mode forward + backward + NCCL all-reduce of the flat gradient bucket + clip/Adam +
+device-side weight re-pack, all inside the timed region) - weak (B per GPU fixed) and strong
+(BASELINE configs[2] as worded: B=32 TOTAL, sharded over the ranks) - and under "strong" the
+eval forward at B=32 total.
+
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the roofline accounting.
 """
 import argparse
@@ -137,11 +143,15 @@ def kernel_algorithmic_work(opt, B, Bc=None):
   }
   # controller CNN: flops per decode step (all 8 layers, as the reference computes them)
   ch = [D] + list(opt['ctrl_cnn_depth'])
-  h, w, fl = H, W, 0.0
+  h, w, fl, fl_umma = H, W, 0.0, 0.0
   for i, pl in enumerate(opt['ctrl_cnn_pool']):
-    fl += 2.0 * h * w * ch[i + 1] * 9 * ch[i]
+    f_i = 2.0 * h * w * ch[i + 1] * 9 * ch[i]
+    fl += f_i
+    if i > 0:  # layer 0 runs as `prepare` (static half, once per forward) + ra_canvas_conv_f32 (per step)
+      fl_umma += f_i
     h, w = h // pl, w // pl
   work['ctrl_cnn_step'] = {'flops': B * fl}  # all chains together: one decode step of the whole batch
+  work['ctrl_cnn_umma_step'] = {'flops': B * fl_umma}  # the layers the tcgen05 group `ctrl_cnn` actually runs
   # first controller layer, per-step half: read static_pre + canvas at full resolution, write the pooled output
   work['ra_canvas_conv_f32'] = {'bytes': Bc * (H * W * (c0 + 1) + (H // p0) * (W // p0) * c0) * 4.0}
   return work
@@ -235,8 +245,11 @@ def run_reference(args):
       'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': args.gpus,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': cfg['name'], 'sample': 'B={} of the workload batch, full T={} decode + loss block'.format(
-          B_sample, cfg['T'])},
+      'config': {'workload': cfg['name'], 'arch': cfg.get('arch'), 'batch_per_gpu': cfg['B'], 'timespan': cfg['T'],
+                 'height': cfg['H'], 'width': cfg['W'], 'parallelism': 'cpu',
+                 'sample': 'throughput measured on B={} examples of the workload batch (full T={} decode + loss block '
+                           'each): masks/s is per-example work, so it is the same metric on a bounded sample'.format(
+                               B_sample, cfg['T'])},
       'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
                        'sample': 'oracle (PyTorch-CPU restatement + C hungarian), B={} x T={} at {}x{}'.format(
                            B_sample, cfg['T'], cfg['H'], cfg['W'])},
@@ -270,10 +283,14 @@ def run_ours(args):
   model = FullModel(opt).load_weights(weights)
   lib = _lib.lib()
 
-  # device-resident inputs for `value`; pinned host copies for `e2e`
+  # device-resident inputs for `value`; pinned host copies for `e2e`.  The {0,1} ground-truth masks travel as
+  # uint8 (the datasets hold PNG masks, data_api/ins_seg_dataset.py:169-172) and are expanded on the device.
+  from rec_attend_b200 import postprocess as PP
   dev_batch = {k: torch.from_numpy(v).cuda() for k, v in batch_np.items()}
-  pinned = {k: torch.from_numpy(v).pin_memory() for k, v in batch_np.items()}
+  host_np = dict(batch_np, y_gt=batch_np['y_gt'].astype('uint8'))
+  pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host_np.items()}
   fetch = ['loss', 'segm_loss', 'box_loss', 'conf_loss', 'iou_soft', 's_out', 'match']
+  fetch_e2e = fetch + ['y_out']
   host_out = {}
 
   def step_device():
@@ -293,14 +310,17 @@ def run_ours(args):
     e2e_state['i'] = i + 1
     if i == 0:
       model.prefetch(cur)
-    out_prev = None
-    out = model.forward(cur, outputs=fetch)
+    out = model.forward(cur, outputs=fetch_e2e)
     model.prefetch(nxt)
-    for k, v in out.items():
+    # what full_model_eval.py:100-125 does with y_out / s_out: confidence-weighted one-label map, on the device
+    pp = PP.postprocess(out['y_out'], out['s_out'], thresh=0.3)
+    res = {k: out[k] for k in fetch}
+    res['label'], res['conf'] = pp['label'], pp['conf']
+    for k, v in res.items():
       if k not in host_out:
         host_out[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
       host_out[k].copy_(v, non_blocking=True)
-    return out
+    return res
 
   def barrier():
     dist_util.barrier()
@@ -332,27 +352,78 @@ def run_ours(args):
   ms_e2e, _ = timed(step_e2e, args.steps)
   clocks = sampler.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and end-to-end)
 
-  # secondary: the TRAINING-mode forward (batch-statistics BN, EMA update, scheduled sampling with explicit draws) -
-  # forward only, the backward pass is not built; 1-GPU runs only, a few steps
-  train_forward = None
-  if world == 1 and not args.no_train_forward:
+  # ---- the TRAINING step of the same workload: taped training-mode forward (batch-statistics BN, EMA update,
+  # scheduled sampling with explicit draws) + backward + NCCL all-reduce(SUM) of the flat gradient bucket + clip / Adam
+  # + device-side re-pack of every weight image, all inside the timed region (FullModel.train_step).
+  import torch.distributed as dist
+
+  def bench_train(Bt, seed_off):
     opt_t = dict(opt, use_knob=True)
+    bt_np = synthetic.make_batch(opt_t, Bt, seed=dist_util.rank_seed(1234, args.config, rank) + seed_off)
+    bt = {k: torch.from_numpy(v).cuda() for k, v in bt_np.items()}
     model_t = FullModel(opt_t).load_weights(weights)
-    draws = synthetic.make_knob_draws(opt_t, B, global_step=0, seed=7)
+    draws = synthetic.make_knob_draws(opt_t, Bt, global_step=0, seed=7 + rank)
 
     def step_train():
-      return model_t.forward(dev_batch, outputs=fetch, phase_train=True, draws=draws)
+      return model_t.train_step(bt, draws=draws)
 
     for _ in range(2):
       step_train()
     n_t = max(2, min(args.steps, 5))
     ms_t, launches_t = timed(step_train, n_t)
-    train_forward = {'value': B * T / (ms_t / n_t / 1e3), 'unit': 'masks/s', 'ms_per_step': ms_t / n_t,
-                     'gpu_launches_per_step': int(launches_t // n_t),
-                     'note': 'training-mode FORWARD only (batch-statistics BN + EMA update + scheduled-sampling knob), '
-                             'one CUDA graph per step; no backward pass yet'}
-    del model_t
+    tr = model_t._trainer
+    # the pieces, each timed alone (CUDA events, max over ranks): forward+backward graph, all-reduce, optimiser tail
+    ms_g, _ = timed(lambda: model_t.forward(bt, phase_train=True, draws=draws, _tape=True), n_t)
+    ms_ar = 0.0
+    if world > 1:
+      ms_ar, _ = timed(lambda: dist.all_reduce(tr.grad_flat, op=dist.ReduceOp.SUM), 20)
+    ms_tail, _ = timed(lambda: tr.apply(), n_t)
+    n0 = lib.ra_launch_count()  # kernels of one step, counted in an eager (un-graphed) step: the graph replays the same
+    model_t.forward(bt, phase_train=True, draws=draws, use_graph=False, _tape=True)
+    tr.apply()
+    torch.cuda.synchronize()
+    launches_eager = int(lib.ra_launch_count() - n0)
+    in_sync = True
+    if world > 1:
+      ref = tr.optim.params.clone()
+      dist.broadcast(ref, src=0)
+      diff = (ref - tr.optim.params).abs().max()
+      dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+      in_sync = bool(float(diff) == 0.0)
+    res = {'batch_per_gpu': Bt, 'global_batch': Bt * world, 'ms_per_step': ms_t / n_t, 'steps': n_t,
+           'value': world * Bt * T / (ms_t / n_t / 1e3), 'unit': 'masks/s',
+           'gpu_launches_per_step': launches_eager,
+           'fwd_bwd_graph_ms': ms_g / n_t, 'allreduce_us': ms_ar / 20 * 1e3,
+           'optimiser_tail_ms': ms_tail / n_t, 'bucket_bytes': int(tr.grad_flat.numel() * 4),
+           'params_in_sync_across_ranks': in_sync, 'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+    del model_t, bt
     torch.cuda.empty_cache()
+    return res
+
+  train_step = None
+  strong = None
+  if not args.no_train_step:
+    train_step = {'weak': bench_train(B, 0),
+                  'step': 'train_step = taped training-mode forward + backward + all-reduce(SUM) of the flat gradient '
+                          'bucket (NCCL, inside the timed region) + clip + Adam + device-side weight re-pack',
+                  'scheduled_sampling': 'use_knob=True, draws for global_step 0'}
+    Bs = cfg['B'] // world
+    if world > 1 and Bs >= 1 and cfg['B'] % world == 0:
+      train_step['strong'] = bench_train(Bs, 500)
+      train_step['strong']['scaling'] = 'strong'
+    else:
+      train_step['strong'] = dict(train_step['weak'], scaling='strong (N=1: identical to weak)')
+    train_step['weak']['scaling'] = 'weak'
+  # eval forward, strong scaling: BASELINE configs[2] as worded - B = 32 TOTAL sharded over the ranks
+  Bs = cfg['B'] // world
+  if world > 1 and Bs >= 1 and cfg['B'] % world == 0:
+    bs_np = synthetic.make_batch(opt, Bs, seed=dist_util.rank_seed(1234, args.config, rank) + 900)
+    bs_dev = {k: torch.from_numpy(v).cuda() for k, v in bs_np.items()}
+    for _ in range(3):
+      model.forward(bs_dev, outputs=fetch)
+    ms_s, _ = timed(lambda: model.forward(bs_dev, outputs=fetch), args.steps)
+    strong = {'scaling': 'strong', 'global_batch': cfg['B'], 'batch_per_gpu': Bs, 'ms_per_step': ms_s / args.steps,
+              'value': cfg['B'] * T / (ms_s / args.steps / 1e3), 'unit': 'masks/s'}
 
   value = dist_util.aggregate_masks_per_sec(world, B, T, ms / args.steps)
   e2e_value = dist_util.aggregate_masks_per_sec(world, B, T, ms_e2e / args.steps)
@@ -367,7 +438,7 @@ def run_ours(args):
     with OpTimer(torch, _lib) as ot:
       # The eager step is enqueued behind a ~60 ms spin kernel: the host runs ahead, so the GPU executes the
       # event / kernel / event triples back to back and the intervals hold no host launch latency.
-      torch.cuda._sleep(int(0.06 * 1.9e9))
+      torch.cuda._sleep(int(0.06 * torch.cuda.get_device_properties(local_rank).clock_rate * 1e3))
       model.forward(dev_batch, outputs=fetch, use_graph=False)  # eager: one C-ABI call per kernel group
     agg = ot.summary()
     launches_per_step = int(lib.ra_launch_count() - n0)
@@ -383,7 +454,8 @@ def run_ours(args):
       gg['ms'] += d['ms']
       gg['n'] += d['n']
     kernels = {}
-    traffic = load_traffic()
+    # the committed ncu capture is of the default workload: no `traffic` claim for any other configuration
+    traffic = load_traffic() if (args.config == 2 and B == cfg['B']) else {}
     for g, d in sorted(groups.items(), key=lambda kv: -kv[1]['ms']):
       ent = {'ms_per_step': round(d['ms'], 4), 'launches': d['n'], 'share': round(d['ms'] / total_ms, 4)}
       tr = entry_traffic(traffic, g)
@@ -397,7 +469,7 @@ def run_ours(args):
     # controller-CNN as a group: flops of the 8 conv layers of one decode step / their time
     ccnn_ms = sum(d['ms'] for k, d in agg.items()
                   if d['entry'] in ('ra_conv3x3_f32', 'ra_conv3x3_umma_f32') and d['tag'] == 'ctrl_cnn')
-    conv_tflops = work['ctrl_cnn_step']['flops'] * T / (ccnn_ms / 1e3) / 1e12 if ccnn_ms > 0 else 0.0
+    conv_tflops = work['ctrl_cnn_umma_step']['flops'] * T / (ccnn_ms / 1e3) / 1e12 if ccnn_ms > 0 else 0.0
     dom = max(groups.items(), key=lambda kv: kv[1]['ms'])[0]
     if dom.startswith('ra_conv3x3'):
       roofline = {
@@ -406,7 +478,8 @@ def run_ours(args):
           'achieved': round(conv_tflops, 3), 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
           'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': entry_traffic(traffic, dom),
           'peak_source': peaks['source'] + ' (cuBLAS bf16 burst)',
-          'note': 'flops = the reference\'s 8 conv layers per decode step (the linear split of layer 0 does fewer); '
+          'note': 'flops = controller-CNN layers 1-7 (the layers this kernel group runs; layer 0 is the linear split '
+                  'prepare + ra_canvas_conv_f32) per decode step x T / their summed CUDA-event time; '
                   'the kernel issues 3 TF32 MMAs per algorithmic MAC (fp32 parity, DESIGN 4.1) and the TF32 dense rate '
                   'is half the bf16 rate, so frac = 1/6 would be a saturated tensor pipe for this formulation'
       }
@@ -436,7 +509,10 @@ def run_ours(args):
                    'graph': 'one CUDA graph per forward ({} sub-batch chain{}); gt-box, hard-IoU and score-head '
                             'kernels on parallel branches'.format(len(chains), '' if len(chains) == 1 else 's')},
         'e2e': {'value': e2e_value, 'unit': 'masks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': ms_e2e / args.steps, 'fetch': fetch,
+                'ms_per_step': ms_e2e / args.steps, 'fetch': fetch + ['label', 'conf'],
+                'inputs': 'x, d_in, y_in fp32; y_gt uint8 {0,1} expanded on the device (ra_u8_to_f32)',
+                'outputs': 'loss scalars, s_out, match + the int32 instance label map [B,H,W] and conf of '
+                           'ra_postprocess_f32 (full_model_eval.py:100-125), D2H inside the timed region',
                 'pipeline': 'H2D of step i+1 overlaps the compute of step i (double-buffered static inputs)'},
         'gpu_launches': launches_per_step * args.steps,
         'gpu_launches_note': '{} kernels of librecattend_b200.so per step (counted in one eager step); the timed '
@@ -446,7 +522,8 @@ def run_ours(args):
         'kernels': kernels,
         'conv_layers': layers,
         'cpu_baseline': cpu_baseline,
-        'train_forward': train_forward,
+        'train_step': train_step,
+        'strong': strong,
     }
     emit(line)
   dist_util.finalize()
@@ -530,7 +607,7 @@ def main():
   ap.add_argument('--batch', type=int, default=0, help='override the per-GPU batch size')
   ap.add_argument('--ref-batch', type=int, default=4, help='batch size of the bounded CPU-baseline sample')
   ap.add_argument('--no-cpu-baseline', action='store_true')
-  ap.add_argument('--no-train-forward', action='store_true', help='skip the secondary training-mode forward timing')
+  ap.add_argument('--no-train-step', action='store_true', help='skip the training-step timing (weak + strong)')
   args = ap.parse_args()
   if args.impl == 'reference':
     return run_reference(args)

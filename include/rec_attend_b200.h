@@ -494,6 +494,11 @@ int ra_postprocess_f32(const float *y_out, const float *s_out, const float *fg, 
 int ra_random_transformation_f32(const float *src, size_t N, int H, int W, int C, int padding, int off_y, int off_x,
                                  int vflip, int hflip, int transpose, float *dst, void *stream);
 
+/* dst[i] = (float)src[i] over n bytes: ground-truth masks handed over as uint8 {0,1} (the datasets store PNG masks,
+ * data_api/ins_seg_dataset.py:169-172; the reference converts on the host before feeding, runner.py:91-96) are
+ * expanded to the fp32 [B,T,H,W] stack of full_model.py:165-194 on the device. */
+int ra_u8_to_f32(const uint8_t *src, size_t n, float *dst, void *stream);
+
 /* --------------------------------------------------------------------------------------
  * Training-mode batch normalisation of one conv block — nnlib.batch_norm with
  * phase_train = True (nnlib.py:65-128) + ReLU + max-pool (nnlib.py:229-253):

@@ -33,6 +33,24 @@ __global__ void __launch_bounds__(256) random_transformation_kernel(const float 
   }
 }
 
+// dst[i] = (float)src[i]: the {0,1} ground-truth masks arrive as bytes (the datasets hold PNG masks,
+// data_api/ins_seg_dataset.py:169-172) and are expanded on the device - a quarter of the host->device traffic.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *__restrict__ src, size_t n, size_t n16,
+                                                        float *__restrict__ dst) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float4 *d = reinterpret_cast<float4 *>(dst) + i * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      d[k] = make_float4((float)(w[k] & 0xffu), (float)((w[k] >> 8) & 0xffu), (float)((w[k] >> 16) & 0xffu),
+                         (float)(w[k] >> 24));
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n16 * 16 + threadIdx.x; i < n; i += blockDim.x) dst[i] = (float)src[i];
+}
+
 }  // namespace
 
 extern "C" int ra_random_transformation_f32(const float *src, size_t N, int H, int W, int C, int padding, int off_y,
@@ -48,4 +66,16 @@ extern "C" int ra_random_transformation_f32(const float *src, size_t N, int H, i
   random_transformation_kernel<<<(unsigned)blocks, 256, 0, ra::as_stream(stream)>>>(src, N, H, W, C, padding, off_y, off_x,
                                                                                    vflip, hflip, transpose, dst);
   return ra::finish_launch("random_transformation_kernel");
+}
+
+extern "C" int ra_u8_to_f32(const uint8_t *src, size_t n, float *dst, void *stream) {
+  if (n == 0) return RA_OK;
+  if (!src || !dst) return RA_ERR_INVALID_ARG;
+  const bool vec = !((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15);
+  const size_t n16 = vec ? n / 16 : 0;
+  size_t blocks = (n16 + 255) / 256;
+  if (blocks > (size_t)ra::kNumSMs * 8) blocks = (size_t)ra::kNumSMs * 8;
+  if (blocks < 1) blocks = 1;
+  u8_to_f32_kernel<<<(unsigned)blocks, 256, 0, ra::as_stream(stream)>>>(src, n, n16, dst);
+  return ra::finish_launch("u8_to_f32_kernel");
 }

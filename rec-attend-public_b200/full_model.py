@@ -337,10 +337,14 @@ class _ModelBase(object):
 
   # ------------------------------------------------------------------ shared pieces
   def _inputs(self, batch):
-    def dev(v):
+    def dev(v, allow_u8=False):
       # host arrays stay on the host here: forward() copies them straight into its static device buffers
       if isinstance(v, np.ndarray):
+        if allow_u8 and v.dtype == np.uint8:
+          return torch.from_numpy(np.ascontiguousarray(v))
         v = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+      if allow_u8 and v.dtype == torch.uint8:
+        return v.contiguous()  # {0,1} masks as bytes: expanded to fp32 on the device (ra_u8_to_f32)
       if v.dtype != torch.float32:
         v = v.float()
       return v.contiguous()
@@ -354,7 +358,7 @@ class _ModelBase(object):
       d_in, y_in = dev(batch['d_in']), dev(batch['y_in'])
       if tuple(d_in.shape) != (B, self.H, self.W, 8) or tuple(y_in.shape) != (B, self.H, self.W, self.nsc):
         raise _lib.RecAttendError('d_in / y_in have the wrong shape')
-    y_gt = dev(batch['y_gt']) if 'y_gt' in batch else None
+    y_gt = dev(batch['y_gt'], allow_u8=True) if 'y_gt' in batch else None
     s_gt = dev(batch['s_gt']) if 's_gt' in batch else None
     return x, d_in, y_in, y_gt, s_gt
 
@@ -368,7 +372,14 @@ class _ModelBase(object):
           continue
         if k not in st:
           st[k] = torch.empty(v.shape, device=self.device, dtype=torch.float32)
-        st[k].copy_(v, non_blocking=True)
+        if v.dtype == torch.uint8:
+          k8 = k + '_u8'
+          if k8 not in st:
+            st[k8] = torch.empty(v.shape, device=self.device, dtype=torch.uint8)
+          st[k8].copy_(v, non_blocking=True)
+          _lib.call('ra_u8_to_f32', ops._p(st[k8]), st[k8].numel(), ops._p(st[k]), ops._stream())
+        else:
+          st[k].copy_(v, non_blocking=True)
     return st
 
   def _buffers(self, B):
