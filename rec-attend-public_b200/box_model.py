@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .full_model import _ModelBase
+from .full_model import _ModelBase, capture_graph
 
 
 class BoxModel(_ModelBase):
@@ -159,9 +159,7 @@ class BoxModel(_ModelBase):
         with torch.cuda.stream(side):
           self._run(bufs, B, noise, train, _tape)
         cur.wait_stream(side)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-          static_out = self._run(bufs, B, noise, train, _tape)
+        g, static_out = capture_graph(lambda: self._run(bufs, B, noise, train, _tape))
         if ema_keep is not None:
           for k, v in ema_keep.items():
             self.w[k].copy_(v)

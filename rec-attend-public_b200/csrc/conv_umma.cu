@@ -54,6 +54,7 @@ constexpr int kTmaWarp = (kEpiThreads + 32 * kMmaWarps + kProdThreads) / 32;  //
 constexpr int kThreads = kEpiThreads + 32 * kMmaWarps + kProdThreads + 32;
 constexpr int kMaxStages = 4;
 constexpr int kStageUnroll = 4;
+constexpr int kKsplitDefault = 8;  // partial accumulators per m-tile used for precision (see make_plan)
 constexpr int kPoolLd = 20;  // floats per staged half-row of a 16-column chunk (16 + 4 padding)
 
 struct UmmaConvParams {
@@ -949,6 +950,24 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
    }
   }
   if (!found) return RA_ERR_UNSUPPORTED;
+  // K split for PRECISION: the TMEM accumulators truncate every fp32 accumulation, a bias proportional to the
+  // accumulator's magnitude and to the number of accumulating instructions.  With k partial
+  // accumulators per m-tile (step q -> accumulator q % k, summed in round-to-nearest fp32 by the epilogue) each one
+  // sees 1/k of the adds at 1/k of the magnitude.  Free TMEM columns are used for it, up to kKsplitMax.
+  {
+    static const int cap = []() {
+      const char *e = getenv("RA_UMMA_KSPLIT");
+      return e ? (atoi(e) < 1 ? 1 : atoi(e)) : kKsplitDefault;
+    }();
+    const int cols_mt = bp.merged ? 2 * bp.NPc : bp.NPc;
+    int ks = 512 / (bp.nbuf * bp.n_mt * cols_mt);
+    const int steps = 9 * (bp.KC / 8) * bp.n_chunks;
+    if (ks > steps) ks = steps;
+    if (ks > cap) ks = cap;
+    if (ks < 1) ks = 1;
+    bp.ksplit = ks;
+    bp.acc_cols = bp.n_mt * ks * cols_mt;
+  }
   *pl = bp;
   return RA_OK;
 }

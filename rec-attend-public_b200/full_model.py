@@ -57,6 +57,24 @@ def _pad_cin(w_hwio, cin):
   return PM.pad_cin(w_hwio, cin)
 
 
+def capture_graph(fn):
+  """Capture fn() in a CUDA graph.  The cyclic garbage collector is held off for the duration: collecting an
+  unreachable model of an earlier run destroys ITS graphs and frees their private pools - a cudaFree that
+  invalidates the capture in progress ("operation not permitted when stream is capturing")."""
+  import gc
+  g = torch.cuda.CUDAGraph()
+  gc.collect()
+  was = gc.isenabled()
+  gc.disable()
+  try:
+    with torch.cuda.graph(g):
+      out = fn()
+  finally:
+    if was:
+      gc.enable()
+  return g, out
+
+
 class _ModelBase(object):
 
   def __init__(self, opt, device=None):
@@ -918,10 +936,8 @@ class FullModel(_ModelBase):
         with torch.cuda.stream(side):
           self._run(bufs, B, with_loss, want_all, train=train, draws=draws if train else None, tape=_tape)
         cur.wait_stream(side)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-          static_out = self._run(bufs, B, with_loss, want_all, train=train, draws=draws if train else None,
-                                 tape=_tape)
+        g, static_out = capture_graph(lambda: self._run(bufs, B, with_loss, want_all, train=train,
+                                                        draws=draws if train else None, tape=_tape))
         if ema_keep is not None:
           for k, v in ema_keep.items():
             self.w[k].copy_(v)

@@ -11,14 +11,11 @@ from oracle import model as OM
 
 pytestmark = pytest.mark.gpu
 
-MODEL_TOL = 1e-3
-# Full-resolution cases (BASELINE sizes): attn_box / y_out / canvas are sigmoid(gamma * v - 5) of a box whose centre
-# is ctrl_out * W/2, so their error is (controller-output error) x (W/2) x (edge slope ~1 per pixel).  The tcgen05
-# accumulators truncate every fp32 accumulation (measured, tools/dbg_parity.py: controller output 2.8e-6 absolute
-# against 6.6e-7 with the CUDA-core fp32 convolutions, which give y_out 1.4e-4), which puts these three tensors at
-# 0.7-1.2e-3 for W = 512.  Everything else stays under 1e-3; the three edge tensors get 2e-3 at full resolution.
-EDGE_KEYS = ('y_out', 'attn_box', 'canvas')
-EDGE_TOL_FULL = 2e-3
+MODEL_TOL = 1e-3  # north_star: 1e-3 relative fp32 on EVERY tensor, at every resolution (no per-tensor escape)
+# attn_box / y_out / canvas are sigmoid(gamma * v - 5) of a box whose centre is ctrl_out * W/2, so their error is
+# (controller-output error) x (W/2) x (edge slope ~1 per pixel).  The tcgen05 accumulators truncate every fp32
+# accumulation; eight partial accumulators per m-tile (K split, csrc/conv_umma.cu make_plan) bring the controller output
+# from 5e-6 to 1.2e-6 absolute and these tensors from 8.5e-4 to 2.4e-4 at 256x512 (profiles/r02b_ksplit_sweep.txt).
 
 FP_KEYS = ['y_out', 's_out', 'attn_box', 'x_patch', 'y_out_patch', 'attn_ctr', 'attn_size', 'attn_top_left',
            'attn_bot_right', 'ctrl_out', 'ctrl_rnn_glimpse_map', 'attn_top_left_gt', 'attn_bot_right_gt',
@@ -32,24 +29,27 @@ HARD_TOL = 5e-3
 SCALAR_KEYS = ['loss', 'box_loss', 'segm_loss', 'conf_loss', 'iou_soft', 'wt_cov_soft', 'unwt_cov_soft', 'count_acc',
                'dic', 'dic_abs']
 
+# Every (case, seed) below is MARGIN-CHECKED (tools/margin_check.py): re-matching the oracle's IoU matrices under 200
+# random relative perturbations of 1e-6 (before f_segm_match's rounding to 1e-6) reproduces the oracle's match and
+# match_box, i.e. the optimal assignments do not hinge on the last digits of a sum over H*W pixels.
 CASES = [
-    # name, arch, H, W, T, B   (first row = BASELINE.json configs[0])
-    ('baseline0_cvppp_128x128_T8_B1', 'cvppp', 128, 128, 8, 1),
-    ('kitti_64x128_T6_B2', 'kitti', 64, 128, 6, 2),
-    ('cityscapes_64x128_T4_B2', 'cityscapes', 64, 128, 4, 2),
-    ('cvppp_overwrite_off_96x96_T5_B3', 'cvppp', 96, 96, 5, 3),
+    # name, arch, H, W, T, B, seed   (first row = BASELINE.json configs[0])
+    ('baseline0_cvppp_128x128_T8_B1', 'cvppp', 128, 128, 8, 1, 1234),
+    ('kitti_64x128_T6_B2', 'kitti', 64, 128, 6, 2, 1234),
+    ('cityscapes_64x128_T4_B2', 'cityscapes', 64, 128, 4, 2, 1234),
+    ('cvppp_overwrite_off_96x96_T5_B3', 'cvppp', 96, 96, 5, 3, 1234),
     # BASELINE.json configs[1..3] at their full resolution and timespan (reduced batch: the CPU oracle is the slow side)
-    ('baseline1_cvppp_256x256_T20_B2', 'cvppp', 256, 256, 20, 2),
-    ('baseline2_kitti_256x512_T20_B3', 'kitti', 256, 512, 20, 3),
-    ('baseline3_cityscapes_512x1024_T32_B1', 'cityscapes', 512, 1024, 32, 1),
+    ('baseline1_cvppp_256x256_T20_B2', 'cvppp', 256, 256, 20, 2, 1234),
+    ('baseline2_kitti_256x512_T20_B3', 'kitti', 256, 512, 20, 3, 2),
+    ('baseline3_cityscapes_512x1024_T32_B1', 'cityscapes', 512, 1024, 32, 1, 4),
 ]
 
 
-def _run(arch, H, W, T, B, **over):
+def _run(arch, H, W, T, B, seed=1234, **over):
   import rec_attend_b200 as ra
   from rec_attend_b200.full_model import FullModel
   opt = ra.config.full_model_opt(arch, H, W, T, **over)
-  batch = ra.synthetic.make_batch(opt, B, seed=1234)
+  batch = ra.synthetic.make_batch(opt, B, seed=seed)
   weights = ra.synthetic.make_weights(opt, seed=4321)
   ref = OM.full_model_forward(opt, weights, batch)
   model = FullModel(opt).load_weights(weights)
@@ -60,16 +60,15 @@ def _run(arch, H, W, T, B, **over):
 
 @pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
 def test_full_model_parity(cuda, case):
-  name, arch, H, W, T, B = case
+  name, arch, H, W, T, B, seed = case
   over = {'disable_overwrite': True} if 'overwrite' in name else {}
-  opt, ref, out = _run(arch, H, W, T, B, **over)
+  opt, ref, out = _run(arch, H, W, T, B, seed=seed, **over)
   worst = {}
   for k in FP_KEYS:
     a, b = out[k].float().cpu().numpy(), ref[k].numpy()
     assert a.shape == b.shape, (k, a.shape, b.shape)
     worst[k] = rel_err(a, b)
-  full = name.startswith('baseline') and H >= 256
-  bad = {k: v for k, v in worst.items() if not v <= (EDGE_TOL_FULL if (full and k in EDGE_KEYS) else MODEL_TOL)}
+  bad = {k: v for k, v in worst.items() if not v <= MODEL_TOL}
   assert not bad, 'fp32 parity beyond tolerance: {}'.format(bad)
   for k in SCALAR_KEYS:
     a, b = float(out[k]), float(ref[k])
@@ -82,25 +81,10 @@ def test_full_model_parity(cuda, case):
     a, b = float(out[k]), float(ref[k])
     assert abs(a - b) <= HARD_TOL * max(1.0, abs(b)), (k, a, b)
   assert (out['attn_box_gt'].cpu().numpy() == ref['attn_box_gt'].numpy()).all()
-  # matchings: bit-exact (the synthetic inputs are margin-checked: re-matching the oracle's
-  # IoU perturbed by the observed fp32 difference must not change the oracle's answer)
-  for mk, ik in (('match', 'iou_soft_pairwise'), ('match_box', 'iou_soft_box_pairwise')):
-    same = (out[mk].cpu().numpy() == ref[mk].numpy()).all()
-    if not same:
-      s_gt = torch.from_numpy(np.asarray(ra_batch_s_gt(opt, B)))
-      stable = (OM.f_segm_match(out[ik].cpu(), s_gt).numpy() == ref[mk].numpy()).all()
-      assert not stable, '{}: kernel matching differs although the weights agree'.format(mk)
-      # The assignments differ because the IoU matrices differ in the last digits and this input has near-ties
-      # ("report the tie-flip rate separately").  The optimal VALUE is continuous in W: both assignments
-      # must be worth the same on the oracle's own weights.
-      w_ref = ref[ik].numpy().astype(np.float64)
-      v_ours = float((w_ref * out[mk].cpu().numpy()).sum())
-      v_ref = float((w_ref * ref[mk].numpy()).sum())
-      flips = int((out[mk].cpu().numpy() != ref[mk].numpy()).sum())
-      assert abs(v_ours - v_ref) <= 1e-4 * max(1.0, abs(v_ref)), (mk, v_ours, v_ref)
-      import warnings
-      warnings.warn('{}: {} entries of the assignment differ between near-tied optima (value {:.6f} vs {:.6f})'.format(
-          mk, flips, v_ours, v_ref))
+  # matchings: BIT-EXACT (the inputs are margin-checked, see CASES)
+  for mk in ('match', 'match_box'):
+    a, b = out[mk].cpu().numpy(), ref[mk].numpy()
+    assert (a == b).all(), '{}: {} entries of the assignment differ'.format(mk, int((a != b).sum()))
 
 
 def ra_batch_s_gt(opt, B):
@@ -108,15 +92,66 @@ def ra_batch_s_gt(opt, B):
   return ra.synthetic.make_batch(opt, B, seed=1234)['s_gt']
 
 
-def test_label_maps_bit_exact(cuda):
-  """argmax_t(y_out * s_out) label maps (utils/postprocess.py:31-52 apply_one_label) agree."""
-  opt, ref, out = _run('kitti', 64, 128, 6, 2)
-  def labels(y, s):
-    v = y * s[:, :, None, None]
-    return np.argmax(v, axis=1) * (v.max(axis=1) > 0.5)
-  la = labels(out['y_out'].cpu().numpy(), out['s_out'].cpu().numpy())
-  lb = labels(ref['y_out'].numpy(), ref['s_out'].numpy())
-  assert (la == lb).mean() > 0.9999
+def _label_margin(y, s, thresh, tol):
+  """Pixels where the oracle's own label decision has a margin: the winning confidence-weighted value is further
+  than tol from the threshold and from the runner-up."""
+  v = (y * s[:, :, None, None]).astype(np.float64)
+  srt = np.sort(v, axis=1)
+  top, second = srt[:, -1], srt[:, -2]
+  return (np.abs(top - thresh) > tol) & ((top - second > tol) | (top <= thresh - tol))
+
+
+LABEL_CASES = [
+    ('baseline1_cvppp_256x256_T20_B2', 'cvppp', 256, 256, 20, 2, 1234),
+    ('baseline2_kitti_256x512_T20_B3', 'kitti', 256, 512, 20, 3, 2),
+    ('baseline3_cityscapes_512x1024_T32_B1', 'cityscapes', 512, 1024, 32, 1, 4),
+    ('kitti_64x128_T6_B2', 'kitti', 64, 128, 6, 2, 1234),
+]
+
+
+@pytest.mark.parametrize('case', LABEL_CASES, ids=[c[0] for c in LABEL_CASES])
+def test_label_maps_bit_exact(cuda, case):
+  """The integer instance label maps (utils/postprocess.py chain of full_model_eval.py:112-125) of the CUDA path -
+  FullModel.forward -> ra_postprocess_f32 - against the oracle's - oracle.model -> oracle.postprocess - on the
+  BASELINE configurations.  Labels are a discontinuous function of y_out * s_out (argmax over T, threshold 0.3):
+  they must be BIT-EXACT on every pixel where the oracle's own decision has a margin of the fp32 parity tolerance
+  (1e-3), the pixels without margin must be a vanishing fraction, and with identical inputs the kernel equals the
+  oracle bit for bit everywhere."""
+  from oracle import postprocess as OP
+  from rec_attend_b200 import postprocess as PP
+  name, arch, H, W, T, B, seed = case
+  opt, ref, out = _run(arch, H, W, T, B, seed=seed)
+  thresh = 0.3
+  y_ref, s_ref = ref['y_out'].numpy(), ref['s_out'].numpy()
+  dense, _, _ = OP.eval_chain(y_ref, s_ref, thresh)  # the reference chain, restated (pinned to the reference module)
+  lab_ref = OP.label_map(dense)
+  lab = PP.postprocess(out['y_out'], out['s_out'], thresh=thresh)['label'].cpu().numpy()
+  margin = _label_margin(y_ref, s_ref, thresh, MODEL_TOL)
+  assert margin.mean() > 0.99, 'too many pixels without a decision margin: {}'.format(1.0 - margin.mean())
+  assert (lab[margin] == lab_ref[margin]).all(), '{} label(s) differ on margin pixels'.format(
+      int((lab[margin] != lab_ref[margin]).sum()))
+  # identical inputs: the kernel is bit-exact everywhere
+  same = PP.postprocess(ref['y_out'].cuda().contiguous(), ref['s_out'].cuda().contiguous(), thresh=thresh)['label']
+  assert (same.cpu().numpy() == lab_ref).all()
+
+
+def test_kitti_full_batch_32_rows_against_oracle_slice(cuda):
+  """The benched configuration itself - KITTI 256x512, T=20, B=32 (the tile plans of the tcgen05 convolution depend
+  on B) - against the oracle on its first four examples (examples are independent in eval mode)."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt('kitti', 256, 512, 20)
+  batch = ra.synthetic.make_batch(opt, 32, seed=1234)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  n = 4
+  ref = OM.full_model_forward(opt, weights, {k: v[:n] for k, v in batch.items()})
+  out = FullModel(opt).load_weights(weights).forward(batch)
+  torch.cuda.synchronize()
+  for k in ('y_out', 's_out', 'attn_box', 'x_patch', 'ctrl_out', 'attn_ctr', 'attn_size', 'iou_soft_pairwise',
+            'iou_soft_box_pairwise', 'canvas'):
+    assert rel_err(out[k][:n].float().cpu().numpy(), ref[k].numpy()) <= MODEL_TOL, k
+  for mk in ('match', 'match_box'):
+    assert (out[mk][:n].cpu().numpy() == ref[mk].numpy()).all(), mk
 
 
 def test_outputs_subset_and_errors(cuda):
