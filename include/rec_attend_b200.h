@@ -551,6 +551,16 @@ int ra_adam_step_f32(float *param, const float *grad, float *m, float *v, const 
  *    (modellib.py:206-238) of the controller's own box record `box` [T*B,RA_BOX_STRIDE] against tl_gt / br_gt [B,T,2]
  *    with the constant matching match_box [B,T,T] (opt['use_iou_box'], full_model.py:750-754,926-929).
  * -------------------------------------------------------------------------------------- */
+ /*  ra_wt_cov_f32: modellib.f_weighted_coverage (modellib.py:268-302) of iou [B,N,M] with GT sizes `area` [B,M] (or, rect
+ *    != NULL, the pixel counts of the filled GT rectangles [B,M,4] on an H x W grid) -> cov[0]; coeff [B,N,M] (may be
+ *    NULL) = the weight of every GT at its first arg-max output, the gradient coefficients ra_iou_loss_bwd_f32 takes in
+ *    place of the matching when segm_loss_fn / box_loss_fn == 'wt_cov' (full_model.py:967,1013-1014).
+ *  ra_loss_select_f32: scal[RA_LOSS_BOX] = -box_cov[0], scal[RA_LOSS_SEGM] = -segm_cov[0] (each optional), total rebuilt
+ *    without the weight-decay term. */
+int ra_wt_cov_f32(const float *iou, const float *area, const float *rect, int H, int W, int B, int N, int M, float *cov,
+                  float *coeff, void *stream);
+int ra_loss_select_f32(float *scal, const float *box_cov, const float *segm_cov, float mix, float segm_coeff,
+                       void *stream);
 int ra_param_gather_f32(const float *flat, const int32_t *codes, const long long *seg_start, float *const *seg_dst,
                         int nseg, long long total, void *stream);
 int ra_param_scatter_f32(float *flat, const int32_t *codes, const long long *seg_start, const float *const *seg_src,

@@ -523,21 +523,26 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False, d
   y_in = _t(batch['y_in']) if add_d_out else None
 
   ema_out = {} if phase_train else None
-  use_knob = bool(phase_train and _opt(opt, 'use_knob', False))
-  if use_knob:
-    if draws is None:
-      raise ValueError('use_knob needs the random draws as inputs')
+  # The knob terms are part of the GRAPH whenever opt['use_knob'] is set (full_model.py:744-759): the per-step IoUs of
+  # the decode loop then feed the box loss in evaluation too (:926-929; with use_iou_box they are the coordinate IoUs
+  # of modellib.f_iou_box, not the pixel IoUs); only the MIXING is switched off by phase_train_f = 0 (:767-776).
+  knob_graph = bool(_opt(opt, 'use_knob', False)) and ('y_gt' in batch)
+  use_knob = bool(phase_train and knob_graph)
+  if knob_graph:
     y_gt_k = _t(batch['y_gt'])
     minpad = opt['padding'] + 4
     # full_model.py:561-580: the clean GT boxes (for the greedy match) and the noisy ones (mixed into the controller)
     tl_gt_k, br_gt_k, box_gt_k = get_gt_box(y_gt_k, padding_ratio=opt['attn_box_padding_ratio'],
                                             center_shift_ratio=0.0, min_padding=minpad)
+    iou_box_steps = []
+  if use_knob:
+    if draws is None:
+      raise ValueError('use_knob needs the random draws as inputs')
     tl_n, br_n, _ = get_gt_box(y_gt_k, padding_ratio=_t(draws['gt_box_pad']),
                                center_shift_ratio=_t(draws['gt_box_ctr_shift']), min_padding=minpad)
     ctr_gt_noise, size_gt_noise = (tl_n + br_n) / 2.0, br_n - tl_n
     knob_box, knob_segm = _t(draws['gt_knob_box']), _t(draws['gt_knob_segm'])
     segm_noise = _t(draws['gt_segm_noise'])
-    iou_box_steps = []
   canvas = torch.zeros(B, H, W, 1)
   n_acnn = len(opt['attn_cnn_filter_size'])
   n_adcnn = len(opt['attn_dcnn_filter_size'])
@@ -560,7 +565,7 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False, d
     c = controller_step(opt, weights, ccnn_inp, tt, ema_out=ema_out)
     ctr, size = c['ctr'], c['size']
     box, f_y, f_x = attn_box_from(opt, ctr, size, c['lg_var'], c['box_lg_gamma'])
-    if use_knob:
+    if knob_graph:
       # full_model.py:744-785: greedy-match the predicted box to a GT box (grd_match_cum stays zero),
       # mix the matched noisy GT box into centre / size where the Bernoulli draw says so, rebuild the filters
       if _opt(opt, 'use_iou_box', False):
@@ -568,6 +573,7 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False, d
       else:
         iou_t = f_inter(box, box_gt_k) / f_union(box, box_gt_k)
       iou_box_steps.append(iou_t.unsqueeze(1))
+    if use_knob:
       grd = f_greedy_match(iou_t, torch.zeros(B, T))
       kb = knob_box[:, tt:tt + 1]
       ctr = kb * (grd.unsqueeze(2) * ctr_gt_noise).sum(1) + (1.0 - kb) * ctr
@@ -633,7 +639,7 @@ def full_model_forward(opt, weights, batch, with_loss=True, phase_train=False, d
   sub = int(np.prod(opt['ctrl_cnn_pool']))
   model['ctrl_rnn_glimpse_map'] = gm.reshape(B, T, gm.shape[2], H // sub, W // sub)
   model['canvas'] = canvas
-  if use_knob:
+  if knob_graph:
     model['iou_soft_box_steps'] = torch.cat(iou_box_steps, 1)  # [B,T(step),T(gt)], full_model.py:926-929
   if ema_out is not None:
     model['ema_updates'] = ema_out
@@ -677,6 +683,8 @@ def full_model_loss(opt, weights, model, y_gt, s_gt):
   cnt_box = torch.clamp(match_box.sum(dim=(1, 2)), min=1.0)
   iou_soft_box = ((iou_box * match_box).sum(dim=(1, 2)) / cnt_box).sum() / B
   r['box_loss'] = -iou_soft_box
+  if _opt(opt, 'box_loss_fn', 'iou') == 'wt_cov':  # full_model.py:967
+    r['box_loss'] = -f_weighted_coverage(iou_box, box_gt)
 
   iou_soft_pw = f_iou_pairwise(model['y_out'], y_gt)  # :983
   match = f_segm_match(iou_soft_pw, s_gt)
@@ -687,6 +695,8 @@ def full_model_loss(opt, weights, model, y_gt, s_gt):
   r['unwt_cov_soft'] = f_unweighted_coverage(iou_soft_pw, cnt)
   r['iou_soft'] = ((iou_soft_pw * match).sum(dim=(1, 2)) / cnt).sum() / B
   r['segm_loss'] = -r['iou_soft']
+  if _opt(opt, 'segm_loss_fn', 'iou') == 'wt_cov':  # full_model.py:1013-1014
+    r['segm_loss'] = -r['wt_cov_soft']
   r['conf_loss'] = f_conf_loss(model['s_out'], match)
   r['loss'] = r['box_loss'] + r['segm_loss'] + opt['loss_mix_ratio'] * r['conf_loss'] + \
       weight_decay_loss(opt, weights)

@@ -238,7 +238,77 @@ __global__ void iou_box_coord_bwd_kernel(const float *__restrict__ box, const fl
   }
 }
 
+// modellib.f_weighted_coverage (modellib.py:268-302): cov = (1/B) sum_b sum_m max_n iou[b,n,m] * wt[b,m],
+// wt = area_m / (sum_m area_m + [area_m == 0]).  Also the gradient coefficients coeff[b,n,m] = wt[b,m] at the FIRST
+// arg-max n (zero elsewhere): handed to ra_iou_loss_bwd_f32 in place of the matching (their sum per example is <= 1, so
+// its 1 / max(1, sum) normalisation is the identity).  area from `area` [B,M], or - rect != NULL - the pixel count of
+// the filled GT rectangle (get_filled_box_idx, modellib.py:704-749: idx >= tl and idx <= br on the pixel grid).
+__global__ void __launch_bounds__(256) wt_cov_kernel(const float *__restrict__ iou, const float *__restrict__ area,
+                                                     const float *__restrict__ rect, int H, int W, int B, int N, int M,
+                                                     float *__restrict__ cov, float *__restrict__ coeff) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float tot = 0.f;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int m = 0; m < M; ++m) {
+        float ar;
+        if (rect != nullptr) {
+          const float *r = rect + ((size_t)b * M + m) * 4;
+          const float y0 = fmaxf(ceilf(r[0]), 0.f), x0 = fmaxf(ceilf(r[1]), 0.f);
+          const float y1 = fminf(floorf(r[2]), (float)(H - 1)), x1 = fminf(floorf(r[3]), (float)(W - 1));
+          ar = fmaxf(y1 - y0 + 1.f, 0.f) * fmaxf(x1 - x0 + 1.f, 0.f);
+        } else {
+          ar = area[(size_t)b * M + m];
+        }
+        if (pass == 0) {
+          tot += ar;
+          continue;
+        }
+        const float wt = ar / (tot + (ar == 0.f ? 1.f : 0.f));
+        float best = -INFINITY;
+        int arg = 0;
+        for (int n = 0; n < N; ++n) {
+          const float v = iou[((size_t)b * N + n) * M + m];
+          if (v > best) {
+            best = v;
+            arg = n;
+          }
+          if (coeff != nullptr) coeff[((size_t)b * N + n) * M + m] = 0.f;
+        }
+        if (coeff != nullptr) coeff[((size_t)b * N + arg) * M + m] = wt;
+        acc += best * wt;
+      }
+  }
+  acc = ra::block_sum(acc, red);
+  if (threadIdx.x == 0) *cov = acc / (float)B;
+}
+
+// segm_loss_fn / box_loss_fn == 'wt_cov' (full_model.py:967,1013-1014): replace the IoU losses of the loss block by
+// the negative weighted coverages and rebuild the total (the weight-decay term is added afterwards by the caller).
+__global__ void loss_select_kernel(float *__restrict__ scal, const float *__restrict__ box_cov,
+                                   const float *__restrict__ segm_cov, float mix, float segm_coeff) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (box_cov != nullptr) scal[RA_LOSS_BOX] = -*box_cov;
+  if (segm_cov != nullptr) scal[RA_LOSS_SEGM] = -*segm_cov;
+  scal[RA_LOSS_TOTAL] = scal[RA_LOSS_BOX] + segm_coeff * scal[RA_LOSS_SEGM] + mix * scal[RA_LOSS_CONF];
+}
+
 }  // namespace
+
+extern "C" int ra_wt_cov_f32(const float *iou, const float *area, const float *rect, int H, int W, int B, int N, int M,
+                             float *cov, float *coeff, void *stream) {
+  if (B < 1 || N < 1 || M < 1 || !iou || !cov || (!area && !rect)) return RA_ERR_INVALID_ARG;
+  wt_cov_kernel<<<1, 256, 0, ra::as_stream(stream)>>>(iou, area, rect, H, W, B, N, M, cov, coeff);
+  return ra::finish_launch("wt_cov_kernel");
+}
+
+extern "C" int ra_loss_select_f32(float *scal, const float *box_cov, const float *segm_cov, float mix, float segm_coeff,
+                                  void *stream) {
+  if (!scal) return RA_ERR_INVALID_ARG;
+  loss_select_kernel<<<1, 32, 0, ra::as_stream(stream)>>>(scal, box_cov, segm_cov, mix, segm_coeff);
+  return ra::finish_launch("loss_select_kernel");
+}
 
 extern "C" int ra_param_gather_f32(const float *flat, const int32_t *codes, const long long *seg_start,
                                    float *const *seg_dst, int nseg, long long total, void *stream) {

@@ -43,9 +43,28 @@ def rank_seed(base, config_idx, rank):
   return base + config_idx + 1000 * rank
 
 
-def shard(global_batch, rank, world):
-  """Contiguous shard [lo, hi) of a global batch over `world` ranks (remainder to the low ranks)."""
+def average_(tensors):
+  """In-place mean over the ranks of a list of same-device tensors (one flattened all-reduce).  No-op for 1 rank."""
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or not tensors:
+    return
+  flat = torch.cat([t.reshape(-1) for t in tensors])
+  dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+  flat /= dist.get_world_size()
+  off = 0
+  for t in tensors:
+    n = t.numel()
+    t.copy_(flat[off:off + n].view_as(t))
+    off += n
+
+
+def shard(global_batch, rank, world, require_equal=False):
+  """Contiguous shard [lo, hi) of a global batch over `world` ranks (remainder to the low ranks).
+  require_equal (TRAINING): the gradient all-reduce averages per-rank means with weight 1/world, which is the
+  global-batch mean only for equal shards - uneven splits are refused instead of silently mis-weighted."""
   q, r = divmod(global_batch, world)
+  if require_equal and r != 0:
+    raise ValueError('global batch {} does not split evenly over {} ranks: pad the batch or pass grad_scale = '
+                     'shard_size / global_batch to train_step on every rank'.format(global_batch, world))
   lo = rank * q + min(rank, r)
   return lo, lo + q + (1 if rank < r else 0)
 

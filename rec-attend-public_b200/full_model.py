@@ -287,6 +287,16 @@ class _ModelBase(object):
                 ops._p(w['%s_scale%d' % (prefix, i)]), ops._p(w['%s_shift%d' % (prefix, i)]), ops._stream())
     self._bn_dirty = False
 
+  def average_ema_across_ranks(self):
+    """Data-parallel training normalises with per-rank batch statistics (all-reduce on gradients only),
+    so the EMA shadows drift apart between ranks while the trained parameters stay identical.  Call this on EVERY
+    rank before a checkpoint / evaluation: the shadows become the mean over ranks (each rank saw an equal share of
+    the global batch), and the eval-mode scale / shift rows are refolded."""
+    from . import dist_util
+    tensors = [self.w['%s_%s%d' % (prefix, n, i)] for prefix, _, i in self._bn_layers for n in ('ema_mean', 'ema_var')]
+    dist_util.average_(tensors)
+    self._bn_dirty = True
+
   def _set_wd_term(self, weights):
     """The weight-decay part of the loss value (nnlib.py:59-61) lives in a device scalar: an optimiser step
     recomputes it on the device (ra_weight_decay_f32), captured graphs read the same address."""
@@ -503,8 +513,9 @@ class FullModel(_ModelBase):
     for k in ('ctrl_add_d_out', 'ctrl_add_y_out', 'attn_add_d_out', 'attn_add_y_out', 'add_y_out'):
       if bool(o.get(k, self.add_d)) != self.add_d:
         raise _lib.RecAttendError('mixed d_out/y_out input flags are not used by any shipped config')
-    if o['segm_loss_fn'] != 'iou' or o['box_loss_fn'] != 'iou':
-      raise _lib.RecAttendError("only the 'iou' losses are supported (SURVEY §9.13)")
+    for k in ('segm_loss_fn', 'box_loss_fn'):
+      if o[k] not in ('iou', 'wt_cov'):  # the other switches are broken in the reference itself
+        raise _lib.RecAttendError("{}: only 'iou' and 'wt_cov' are supported (SURVEY §9.13)".format(k))
     self.attn_pool = list(o['attn_cnn_pool'])
     self.dcnn_pool = list(o['attn_dcnn_pool'])
     self.skip_ch = dcnn_skip_channels(o)
@@ -594,9 +605,10 @@ class FullModel(_ModelBase):
         'canvas_tmp': torch.empty_like(bufs['canvas']),
     }
 
-  def _decode(self, bufs, B, train=False, knob=None):
+  def _decode(self, bufs, B, train=False, knob=None, eval_iou=None):
     """The T-step decode loop, full_model.py:638-848 (eval mode; train=True: batch-statistics BN; knob: the
-    scheduled-sampling state of _knob_setup, training only)."""
+    scheduled-sampling state of _knob_setup, training only; eval_iou = (tl_gt, br_gt, iou_steps, grd): the per-step
+    coordinate IoUs a use_knob + use_iou_box graph feeds to the box loss in evaluation too, :750-754,926-929)."""
     w = self.w
     T, H, W, F = self.T, self.H, self.W, self.F
     thw = T * H * W
@@ -623,6 +635,8 @@ class FullModel(_ModelBase):
                               knob['grd'])
         ops.knob_mix_box(box_t, knob['grd'], knob['ctr'], knob['size'], knob['knob_box'][:, t], T)
         ops.get_gaussian_filter(box_t, H, W, F, fy=fy, fx=fx, band=bufs['band'])
+      if eval_iou is not None:
+        ops.greedy_iou_box(box_t, eval_iou[0], eval_iou[1], eval_iou[2][:, t], T * T, eval_iou[3])
       x_patch = bufs['x_patch_all'][t]
       _lib.TAG = 'extract'
       ops.extract_patch(bufs['xs'], bufs['canvas'], self.chan_map, box_t, fy, fx, bufs['band'],
@@ -752,6 +766,23 @@ class FullModel(_ModelBase):
       cur.wait_stream(side)
     scal = ops.loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice, bufs['s_out'], s_gt, area,
                           o['loss_mix_ratio'], 0.0)
+    if o['segm_loss_fn'] == 'wt_cov' or o['box_loss_fn'] == 'wt_cov':
+      # full_model.py:967,1013-1014: the losses are the negative weighted coverages; the gradient coefficients
+      # (GT weight at the arg-max output) take the place of the matching in the backward pass
+      H_, W_ = self.H, self.W
+      box_cov = segm_cov = None
+      if o['box_loss_fn'] == 'wt_cov':
+        box_cov = torch.empty(1, device=s_gt.device)
+        out['_box_coeff'] = torch.empty_like(iou_box)
+        _lib.call('ra_wt_cov_f32', ops._p(iou_box), ops._p(None), ops._p(rect), H_, W_, B, T, T, ops._p(box_cov),
+                  ops._p(out['_box_coeff']), ops._stream())
+      if o['segm_loss_fn'] == 'wt_cov':
+        segm_cov = torch.empty(1, device=s_gt.device)
+        out['_segm_coeff'] = torch.empty_like(iou_soft)
+        _lib.call('ra_wt_cov_f32', ops._p(iou_soft), ops._p(area), ops._p(None), H_, W_, B, T, T, ops._p(segm_cov),
+                  ops._p(out['_segm_coeff']), ops._stream())
+      _lib.call('ra_loss_select_f32', ops._p(scal), ops._p(box_cov), ops._p(segm_cov), float(o['loss_mix_ratio']), 1.0,
+                ops._stream())
     self._add_wd(scal)
     out.update({
         '_gt_rect': rect, 'attn_top_left_gt': tl, 'attn_bot_right_gt': br,
@@ -776,11 +807,22 @@ class FullModel(_ModelBase):
     gt = self._gt_boxes(bufs, st['y_gt'], want_all) if with_loss else None
     chains = self._chains(B)
     knob = None
+    eval_iou = None
+    o = self.opt
+    if (with_loss and not train and o.get('use_knob', False) and o.get('use_iou_box', False)):
+      # a use_knob graph hands the per-step IoUs of the decode loop to the box loss in evaluation too
+      # (full_model.py:926-929); with use_iou_box those are coordinate IoUs, not the pixel IoUs of attn_box
+      (tl_e, br_e, _, _, _), gt_side = gt
+      if gt_side is not None:
+        torch.cuda.current_stream().wait_stream(gt_side)
+      eval_iou = (tl_e, br_e, torch.empty((B, self.T, self.T), device=self.device, dtype=torch.float32),
+                  torch.empty((B, self.T), device=self.device, dtype=torch.float32))
+      chains = chains[:1] if len(chains) == 1 else [(0, B)]
     if len(chains) == 1 or train:  # batch statistics couple the examples: training mode never splits the batch
       self._prepare(bufs, st['x'], st.get('d_in'), st.get('y_in'))
       if train and draws is not None:
         knob = self._knob_setup(bufs, st['y_gt'], draws)
-      self._decode(bufs, B, train, knob)
+      self._decode(bufs, B, train, knob, eval_iou)
     else:
       cur = torch.cuda.current_stream()
       forked = []
@@ -805,7 +847,8 @@ class FullModel(_ModelBase):
       out['x_patch'] = bufs['x_patch_all'][..., :self.D].permute(1, 0, 2, 3, 4).contiguous()
       out['y_out_patch'] = bufs['y_patch_all'].permute(1, 0, 2, 3, 4).contiguous()
     if with_loss:
-      self._loss(bufs, st['y_gt'], st['s_gt'], out, gt, None if knob is None else knob['iou_steps'])
+      iou_steps = knob['iou_steps'] if knob is not None else (eval_iou[2] if eval_iou is not None else None)
+      self._loss(bufs, st['y_gt'], st['s_gt'], out, gt, iou_steps)
       scal = out['loss_scalars']
       for i, k in enumerate(LOSS_KEYS):
         out[k] = scal[i]
@@ -863,7 +906,9 @@ class FullModel(_ModelBase):
     self._stage_inputs(bufs, slot, {'x': x, 'd_in': d_in, 'y_in': y_in, 'y_gt': y_gt, 's_gt': s_gt}, cs)
     done = torch.cuda.Event()
     done.record(cs)
-    bufs['prefetched'] = (id(batch), slot, done, y_gt is not None)
+    # the batch OBJECT is kept (not its id, which a freed dict could hand to a new one): forward() picks the staged
+    # inputs up only for this very object; it must not be mutated between prefetch() and forward()
+    bufs['prefetched'] = (batch, slot, done, y_gt is not None)
 
   def forward(self, batch, outputs=None, phase_train=False, with_loss=True, use_graph=True, draws=None, _tape=False):
     """``sess.run([model[k] for k in outputs], feed_dict)`` of runner.py:98-105.
@@ -892,7 +937,7 @@ class FullModel(_ModelBase):
     cur = torch.cuda.current_stream()
     pf = None
     for bb in self._bufs.values():
-      if bb.get('prefetched') is not None and bb['prefetched'][0] == id(batch):
+      if bb.get('prefetched') is not None and bb['prefetched'][0] is batch:
         pf, bufs = bb.pop('prefetched'), bb
         bufs['prefetched'] = None
     if pf is not None:

@@ -315,8 +315,12 @@ def full_model_backward(m, gs, bufs, B, out, knob):
   rect, tl_gt, br_gt = out['_gt_rect'], out['attn_top_left_gt'], out['attn_bot_right_gt']
   coord = knob is not None and bool(o.get('use_iou_box', False))
   _lib.TAG = 'bwd_loss'
-  d_y = ops.iou_loss_bwd(bufs['y_out'], match, b_masks=y_gt)
-  d_ab = None if coord else ops.iou_loss_bwd(bufs['attn_box'], match_box, b_rect=rect)
+  # 'wt_cov' losses (full_model.py:967,1013-1014): the gradient coefficients of the weighted coverage replace the
+  # matching (the confidence loss below still uses the matching)
+  d_y = ops.iou_loss_bwd(bufs['y_out'], out.get('_segm_coeff', match), b_masks=y_gt)
+  if coord and '_box_coeff' in out:
+    raise _lib.RecAttendError("box_loss_fn='wt_cov' with use_iou_box + use_knob is not supported")
+  d_ab = None if coord else ops.iou_loss_bwd(bufs['attn_box'], out.get('_box_coeff', match_box), b_rect=rect)
   d_s = ops.conf_loss_bwd(bufs['s_out'], match, scale=float(o['loss_mix_ratio']))
   # ---- mask write and attention box
   _lib.TAG = 'bwd_attn'

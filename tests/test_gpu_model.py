@@ -154,6 +154,30 @@ def test_kitti_full_batch_32_rows_against_oracle_slice(cuda):
     assert (out[mk][:n].cpu().numpy() == ref[mk].numpy()).all(), mk
 
 
+def test_eval_of_a_knob_graph_uses_the_per_step_box_ious(cuda):
+  """with opt['use_knob'] the reference feeds the per-step IoUs of the decode loop to the box loss in
+  evaluation too (full_model.py:926-929); with use_iou_box (run_cityscapes.sh) they are modellib.f_iou_box of the
+  box coordinates, not the pixel IoU of attn_box - so match_box / box_loss of the in-training validation runs follow
+  the coordinate IoU."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt('cityscapes', 64, 128, 4, use_knob=True)
+  assert opt['use_iou_box']
+  batch = ra.synthetic.make_batch(opt, 3, seed=1234)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  ref = OM.full_model_forward(opt, weights, batch)
+  pix = OM.full_model_forward(dict(opt, use_knob=False), weights, batch)
+  assert rel_err(ref['iou_soft_box_pairwise'].numpy(), pix['iou_soft_box_pairwise'].numpy()) > 1e-2  # they do differ
+  for use_graph in (False, True):
+    out = FullModel(opt).load_weights(weights).forward(batch, use_graph=use_graph)
+    torch.cuda.synchronize()
+    assert rel_err(out['iou_soft_box_pairwise'].cpu().numpy(), ref['iou_soft_box_pairwise'].numpy()) <= MODEL_TOL
+    assert (out['match_box'].cpu().numpy() == ref['match_box'].numpy()).all()
+    for k in ('box_loss', 'loss', 'segm_loss'):
+      assert abs(float(out[k]) - float(ref[k])) <= MODEL_TOL, k
+    assert rel_err(out['y_out'].cpu().numpy(), ref['y_out'].numpy()) <= MODEL_TOL
+
+
 def test_outputs_subset_and_errors(cuda):
   import rec_attend_b200 as ra
   from rec_attend_b200 import _lib

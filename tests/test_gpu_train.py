@@ -116,6 +116,33 @@ def test_full_model_gradients(cuda, monkeypatch, arch, H, W, T, B, knob, conv_fp
     _check_grads(gpu, g64, g32, keys, cos_floor)
 
 
+def test_wt_cov_losses_forward_and_gradients(cuda):
+  """segm_loss_fn = box_loss_fn = 'wt_cov' (full_model.py:967,1013-1014): losses are the negative
+  weighted coverages, their gradient reaches the arg-max output of every ground-truth object."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200 import train as TR
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt('kitti', 64, 128, 2, use_knob=False, segm_loss_fn='wt_cov', box_loss_fn='wt_cov')
+  B = 4
+  batch = ra.synthetic.make_batch(opt, B, seed=33)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  g64, g32, out32 = _oracle_grads(opt, weights, batch, None)
+  plain = OM.full_model_forward(dict(opt, segm_loss_fn='iou', box_loss_fn='iou'), weights, batch, phase_train=True)
+  assert abs(float(out32['segm_loss']) - float(plain['segm_loss'])) > 1e-3  # the switch does change the loss
+  model = FullModel(opt).load_weights(weights)
+  model._trainer = TR.Trainer(model)
+  out = model.forward(batch, phase_train=True, _tape=True)
+  torch.cuda.synchronize()
+  for k in ('loss', 'segm_loss', 'box_loss', 'conf_loss'):
+    assert abs(float(out[k]) - float(out32[k])) < 2e-3, (k, float(out[k]), float(out32[k]))
+  _check_grads(_flat_to_dict(model), g64, g32, model._trainer.optim.flat.keys, 0.99)
+  ev = model.forward(batch)  # eval mode reports the same switch
+  ref = OM.full_model_forward(opt, model.export_weights(), batch)
+  torch.cuda.synchronize()
+  for k in ('loss', 'segm_loss', 'box_loss'):
+    assert abs(float(ev[k]) - float(ref[k])) < 2e-3, k
+
+
 def test_box_model_gradients(cuda):
   import rec_attend_b200 as ra
   from rec_attend_b200 import train as TR

@@ -36,6 +36,10 @@ def _worker(rank, world, port, q):
   chk = torch.tensor([float(b['x'].sum())], dtype=torch.float64)
   gathered = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
   torch.distributed.all_gather(gathered, chk)
+  # EMA shadows of a data-parallel run: the mean over ranks, in place, several tensors in one collective
+  ema = [torch.full((3,), float(rank + 1)), torch.full((2, 2), 10.0 * (rank + 1))]
+  dist_util.average_(ema)
+  assert torch.equal(ema[0], torch.full((3,), (1 + world) / 2.0)) and torch.equal(ema[1], torch.full((2, 2), 5.0 * (1 + world)))
   q.put((rank, ms, (lo, hi), [float(g) for g in gathered]))
   dist_util.finalize()
 
@@ -64,6 +68,12 @@ def test_single_process_helpers():
   cover = [dist_util.shard(32, r, 8) for r in range(8)]
   assert cover[0] == (0, 4) and cover[-1] == (28, 32)
   assert dist_util.env_world()[2] >= 1
+  with pytest.raises(ValueError):
+    dist_util.shard(33, 0, 8, require_equal=True)  # training refuses uneven shards (mis-weighted gradient mean)
+  assert dist_util.shard(32, 3, 8, require_equal=True) == (12, 16)
+  t = [torch.ones(2)]
+  dist_util.average_(t)  # single process: no-op
+  assert torch.equal(t[0], torch.ones(2))
 
 
 def _dp_worker(rank, world, port, q):
