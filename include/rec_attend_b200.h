@@ -105,12 +105,16 @@ int ra_canvas_conv_f32(const float *pre, const float *canvas, const float *w, co
  * element [s][ch][tap][c4][r][j] = part(w[tap][ch*KC + 4*c4 + j][s*NPc + (r mod NPc)]), part = hi
  * (w rounded to the nearest tf32) for r < NPc and lo = w - hi for r >= NPc, zero padded,
  * with KC, NPc, n_split, n_chunks given by ra_conv3x3_umma_plan for the layer's (Cin, Cout,
- * un-pooled output size, pool, batch).  Supported: Cout <= 256, even output width.
+ * un-pooled output size, pool, batch).  When the plan reports rowstack = 1 (narrow layers: the three kx taps of a
+ * filter row share one read of the A operand) the image is
+ *   wpack [n_split][n_chunks][3 ky][KC/4][6*NPc][4]
+ * with rows [hi kx0 | hi kx1 | hi kx2 | lo kx0 | lo kx1 | lo kx2] (NPc each).
+ * Supported: Cout <= 256, even output width.
  * -------------------------------------------------------------------------------------- */
 int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc, int *n_split,
-                         int *n_chunks);
-/* Diagnostics: info[18] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
- * acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf of the tile plan. */
+                         int *n_chunks, int *rowstack);
+/* Diagnostics: info[19] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
+ * acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf, rowstack of the tile plan. */
 int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info);
 /* Diagnostics: device buffer of 8 int64 per CTA (148 CTAs max) receiving clock64() stamps of the pipeline
  * phases of the next ra_conv3x3_umma_f32 launches; NULL switches it off. */

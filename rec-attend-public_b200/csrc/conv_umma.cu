@@ -69,6 +69,8 @@ struct UmmaConvParams {
   int up, pool, relu;
   int TH, TW, TWP, n_mt, KC, n_chunks;
   int NPc, n_split, merged;  // output channels per CTA (padded), CTAs along N, stacked-B mode
+  int rowstack;              // the three kx taps of a filter row stacked along N (see issue_chunk_rs)
+  int mt_stride;             // output slots per m-tile: 128, or 126 with rowstack (tiles overlap by two rows of D)
   int slots_alloc;           // input slots allocated per plane
   int tiles_x, tiles_y, n_items;
   int stages;
@@ -279,6 +281,36 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx &c) {
   }
 }
 
+// Row-stacked taps (narrow layers, 6 * NPc <= 256).  A tcgen05.mma with M = 128, K = 8 occupies the tensor core for
+// max(48, N/2) cycles whatever N <= 96 is - the A operand streams from shared memory - so a layer with 16 or 32 output
+// channels pays the A read nine times per k8 step for very little math.  Here the three kx taps of a filter row share
+// ONE read of A: B is stacked along N as [hi kx0 | hi kx1 | hi kx2 | lo kx0 | lo kx1 | lo kx2] (6 NPc columns) and
+//   D'[r, kx * NPc + co] (+)= sum_c A[r + ky * TWP, c] * W[ky, kx, c, co]
+// is accumulated for every A row r; the output of slot s is D'[s, kx=0] + D'[s+1, kx=1] + D'[s+2, kx=2], combined by
+// the epilogue across TMEM lanes (m-tiles overlap by two rows so that all three live in one tile).  Two instructions
+// per (ky, k8) step instead of six: A_hi x [all six blocks], then A_lo x [hi blocks] into the lo half.
+template <int K8N, bool TWO>
+__device__ __forceinline__ void issue_chunk_rs(const IssueCtx &c) {
+  uint32_t jc = 0, a_row = 0, b_row = 0;
+  int q = 0;
+#pragma unroll 1
+  for (int ky = 0; ky < 3; ++ky, a_row += c.TWP, b_row += c.b_tap) {
+#pragma unroll
+    for (int k8 = 0; k8 < K8N; ++k8, ++q) {
+      const uint64_t a_off = (uint64_t)(a_row + (uint32_t)k8 * c.a_k8);
+      const uint64_t b = c.b + (uint64_t)(b_row + (uint32_t)k8 * c.b_k8);
+      const uint32_t flag = (uint32_t)q < c.init_steps ? 0u : 1u;
+      const uint32_t d0 = c.d0 + jc, d1 = c.d1 + jc;
+      umma_tf32(d0, c.a0_hi + a_off, b, c.idesc_2n, flag);
+      if (TWO) umma_tf32(d1, c.a1_hi + a_off, b, c.idesc_2n, flag);
+      umma_tf32(d0 + c.lo_col, c.a0_lo + a_off, b, c.idesc_n, 1u);
+      if (TWO) umma_tf32(d1 + c.lo_col, c.a1_lo + a_off, b, c.idesc_n, 1u);
+      jc += c.cols_mt;
+      if (jc == c.wrap) jc = 0;
+    }
+  }
+}
+
 template <int K8N>
 __device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, bool two) {
   if (merged) {
@@ -306,6 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ __align__(128) unsigned char smem_dyn[];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sc_s[256], sh_s[256];  // folded-BN scale / shift of this CTA's channels
+  __shared__ float xw_s[2 * 4 * 48];  // rowstack epilogue: rows the next warp hands to lanes 30 / 31 (two buffers)
   __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_raw[kMaxStages], bar_tfull[2],
       bar_tempty[2];
   // TMA destinations want 128-byte alignment: round the dynamic window up (the launcher adds the slack)
@@ -617,25 +650,29 @@ __global__ void __launch_bounds__(kThreads, 1)
     {
       const bool leader = elect_one();
       const int mw = warp - kMmaWarp0;
-      const int cols_mt = p.merged ? 2 * p.NPc : p.NPc;
+      const int cols_mt = p.rowstack ? 6 * p.NPc : (p.merged ? 2 * p.NPc : p.NPc);
       IssueCtx c;
-      c.idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NPc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      c.idesc_2n =
-          (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * p.NPc) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // rowstack: idesc_n = the A_lo instruction (3 NPc wide), idesc_2n = the A_hi instruction (6 NPc wide)
+      const uint32_t n_lo = p.rowstack ? 3u * (uint32_t)p.NPc : (uint32_t)p.NPc;
+      const uint32_t n_hi = p.rowstack ? 6u * (uint32_t)p.NPc : 2u * (uint32_t)p.NPc;
+      c.idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((n_lo >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      c.idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((n_hi >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       c.idesc_lo = p.four_term ? c.idesc_2n : c.idesc_n;
       // column offset of the A_lo B_hi correction inside an m-tile's accumulator (0: same half as the main sum)
-      c.lo_col = (p.merged && !p.four_term && getenv_split_corr(p)) ? (uint32_t)p.NPc : 0u;
-      const uint32_t w_plane = (uint32_t)(2 * p.NPc) * 16u;  // bytes between channel planes of the filter image
+      c.lo_col = p.rowstack ? 3u * (uint32_t)p.NPc
+                            : ((p.merged && !p.four_term && getenv_split_corr(p)) ? (uint32_t)p.NPc : 0u);
+      // bytes between channel planes of the filter image
+      const uint32_t w_plane = (uint32_t)((p.rowstack ? 6 : 2) * p.NPc) * 16u;
       c.TWP = (uint32_t)p.TWP;
       c.a_k8 = 2u * (plane_bytes >> 4);                 // A start-address step of one k8 (two channel planes)
       c.b_k8 = 2u * (w_plane >> 4);                     // same for the filter image
-      c.b_tap = (uint32_t)planes * (w_plane >> 4);      // filter image step of one tap
+      c.b_tap = (uint32_t)planes * (w_plane >> 4);      // filter image step of one tap (rowstack: of one filter row)
       c.b_lo = (uint32_t)p.NPc;                         // rows NPc..2NPc-1 of a plane hold the lo part
       c.cols_mt = (uint32_t)cols_mt;
       c.wrap = (uint32_t)(p.ksplit * cols_mt);          // TMEM columns of one m-tile (all its partial accumulators)
       const bool has0 = mw < p.n_mt, has1 = mw + kMmaWarps < p.n_mt;
       const bool merged = p.merged != 0;
-      const uint32_t a_mt0 = (uint32_t)(mw * 128), a_mt1 = (uint32_t)((mw + kMmaWarps) * 128);
+      const uint32_t a_mt0 = (uint32_t)(mw * p.mt_stride), a_mt1 = (uint32_t)((mw + kMmaWarps) * p.mt_stride);
       const int k8n = p.KC / 8;
       int g = 0, t = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
@@ -665,7 +702,15 @@ __global__ void __launch_bounds__(kThreads, 1)
           c.b = make_desc(w_addr, w_plane, 128);
           c.init_steps = ch == 0 ? (uint32_t)p.ksplit : 0u;  // the first MMA into each accumulator overwrites
           if (has0 && leader) {
-            if (k8n == 1)
+            if (p.rowstack) {
+              if (k8n == 1) {
+                if (has1) issue_chunk_rs<1, true>(c); else issue_chunk_rs<1, false>(c);
+              } else if (k8n == 2) {
+                if (has1) issue_chunk_rs<2, true>(c); else issue_chunk_rs<2, false>(c);
+              } else {
+                if (has1) issue_chunk_rs<4, true>(c); else issue_chunk_rs<4, false>(c);
+              }
+            } else if (k8n == 1)
               issue_chunk_k8<1>(c, merged, has1);
             else if (k8n == 2)
               issue_chunk_k8<2>(c, merged, has1);
@@ -683,8 +728,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // =============================== epilogue (warps 0-3) ===============================
-    const int cols_mt = p.merged ? 2 * p.NPc : p.NPc;
+    const int cols_mt = p.rowstack ? 6 * p.NPc : (p.merged ? 2 * p.NPc : p.NPc);
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;  // warp w may touch TMEM lanes [32w, 32w+32)
+    int xw_par = 0;  // rowstack: parity of the cross-warp exchange buffer
     const int slots_out = p.TH * p.TWP;
     const int chain_cols = p.ksplit * cols_mt;  // TMEM columns of one m-tile
     const int co_base = ns * p.NPc;
@@ -700,6 +746,73 @@ __global__ void __launch_bounds__(kThreads, 1)
     // the loads of one (hi half, lo half) pair are in flight together.  Then BN scale/shift (+ ReLU).
     auto load16 = [&](uint32_t acc, int mt, int cb, float *v) {
       uint32_t r0[16], r1[16];
+      if (p.rowstack) {
+        // g[j] = D'[lane, kx block, channel cb + j] (hi half + lo half + K-split partials); the output of this
+        // lane's slot is g(kx=0)[lane] + g(kx=1)[lane + 1] + g(kx=2)[lane + 2].  Lanes 30 / 31 take the rows of the
+        // next warp from shared memory (its lanes 0 / 1 publish them; double-buffered, one barrier per call).
+        float *xw = xw_s + xw_par * (4 * 48);
+        xw_par ^= 1;
+        float g[16];
+        auto load_group = [&](int kx) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[j] = 0.f;
+          for (int ks = 0; ks < p.ksplit; ++ks) {
+            const uint32_t col = acc + (uint32_t)(mt * chain_cols + ks * cols_mt + kx * p.NPc + cb);
+            tmem_ld16_issue(col, r0);
+            tmem_ld16_issue(col + 3u * (uint32_t)p.NPc, r1);
+            tmem_wait16(r0);
+            tmem_wait16(r1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+          }
+        };
+        load_group(0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = g[j];
+        load_group(1);
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xw[warp * 48 + j] = g[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float t = __shfl_down_sync(0xffffffffu, g[j], 1);
+          if (lane != 31) v[j] += t;
+        }
+        load_group(2);
+        if (lane < 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xw[warp * 48 + 16 + lane * 16 + j] = g[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float t = __shfl_down_sync(0xffffffffu, g[j], 2);
+          if (lane < 30) v[j] += t;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        const float *nx = xw + ((warp + 1) & 3) * 48;
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += nx[j] + nx[32 + j];
+        } else if (lane == 30) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += nx[16 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4 *>(sc_s + cb + j);
+          const float4 sh = *reinterpret_cast<const float4 *>(sh_s + cb + j);
+          v[j] = fmaf(v[j], sc.x, sh.x);
+          v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+          v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+          v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        return;
+      }
       const uint32_t base = acc + (uint32_t)(mt * chain_cols + cb);
       tmem_ld16_issue(base, r0);
       if (p.merged) tmem_ld16_issue(base + (uint32_t)p.NPc, r1);
@@ -752,13 +865,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (p.pool == 2) {
         for (int cb = 0; cb < cb_end; cb += 16) {
           for (int mt = 0; mt < p.n_mt; ++mt) {
-            const int s = mt * 128 + tid;
+            const int s = mt * p.mt_stride + tid;
             float v[16];
             load16(acc, mt, cb, v);
             // horizontal max with the next slot (same image row: TW, x0 are even so pairs do not straddle)
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_down_sync(0xffffffffu, v[j], 1));
-            if ((lane & 1) == 0 && s < slots_out) {
+            if ((lane & 1) == 0 && s < slots_out && tid < p.mt_stride) {
               float *dst = pool_s + (size_t)(s >> 1) * kPoolLd;
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
@@ -795,10 +908,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       } else {
         for (int mt = 0; mt < p.n_mt; ++mt) {
-          const int s = mt * 128 + tid;
+          const int s = mt * p.mt_stride + tid;
           const int oy_l = s / p.TWP, ox_l = s - oy_l * p.TWP;
           const int oy = it.y0 + oy_l, ox = it.x0 + ox_l;
-          const bool valid = s < slots_out && ox_l < p.TW && oy < p.Hout && ox < p.Wout;
+          const bool valid = s < slots_out && tid < p.mt_stride && ox_l < p.TW && oy < p.Hout && ox < p.Wout;
           float *dst_px = p.y + (((size_t)it.b * p.Hout + oy) * p.Wout + ox) * p.Cout + co_base;
           for (int cb = 0; cb < cb_end; cb += 16) {
             float v[16];
@@ -836,6 +949,7 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // Tile plan shared by the launcher and the weight packer (through ra_conv3x3_umma_plan).
 struct Plan {
   int KC, NP, NPc, n_split, merged, TH, TW, TWP, n_mt, slots_alloc, n_chunks, stages, acc_cols, stage_bytes;
+  int rowstack, mt_stride;
   int ksplit, nbuf;
   int w_resident, w_res_bytes, grid;
   size_t smem_bytes;
@@ -861,13 +975,28 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
    for (int merged = 1; merged >= 0; --merged) {
     // merged: [B_hi; B_lo] stacked along N, one MMA (N' = 2 NPc <= 256) reads A_hi once; 2 instead of 3 MMAs
     if (merged && 2 * NPc > 256) continue;
-    const int cols_mt = merged ? 2 * NPc : NPc;
+    // 0 (default): off, 1: by the cost model, 2: on every narrow layer (calibration).  MEASURED on B200
+    // (tools/rowstack_ab.py, profiles/r02c_rowstack_ab.txt): results identical to 1e-6, the MMA phase shrinks 3x, but
+    // the epilogue reads three times the TMEM columns and becomes the bound - controller layer 1 takes 141 us instead
+    // of 82 us, the 48x48-patch layers gain nothing (they are fill / drain latency) - so the mode stays opt-in until the
+    // epilogue is spread over more warps.
+    static const int rs_mode = []() {
+      const char *e = getenv("RA_UMMA_ROWSTACK");
+      return e == nullptr ? 0 : atoi(e);
+    }();
+    const bool rs_ok = merged && 6 * NPc <= 256 && rs_mode != 0;
+    // rowstack: the three kx taps of a filter row stacked along N (6 NPc columns), see issue_chunk_rs
+   for (int rs = rs_ok ? 1 : 0; rs >= 0; --rs) {
+    if (rs_mode == 2 && !rs && NP <= 32) continue;  // calibration: narrow layers run row-stacked or not at all
+    const int cols_mt = rs ? 6 * NPc : (merged ? 2 * NPc : NPc);
+    const int mt_stride = rs ? 126 : 128;
     const int mt_max = 512 / cols_mt;  // all 512 TMEM columns, single accumulator buffer
     if (mt_max < 1) continue;
-    const double n_mma = merged ? 2.0 : 3.0;  // instructions per (tap, k8) step and m-tile, one dependent chain
+    const double n_mma = (merged || rs) ? 2.0 : 3.0;  // instructions per step and m-tile, one dependent chain
     // tensor-core time of one M=128 x K=8 instruction: max(~48, N/2) cycles (tools/umma_rate.cu)
     const double hw_n = NPc / 2 > 48 ? NPc / 2 : 48.0, hw_2n = NPc > 48 ? (double)NPc : 48.0;
-    const double hw_cycles = merged ? hw_2n + hw_n : 3.0 * hw_n;
+    const double hw_rs = (3.0 * NPc > 48 ? 3.0 * NPc : 48.0) + (1.5 * NPc > 48 ? 1.5 * NPc : 48.0);
+    const double hw_cycles = rs ? hw_rs : (merged ? hw_2n + hw_n : 3.0 * hw_n);
     for (int KC = 8; KC <= 32; KC *= 2) {
       if (KC > 8 && KC / 2 >= Cin) continue;
       const int planes = KC / 4;
@@ -878,7 +1007,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
         if (TW & 1) break;
         const int TWP = TW + 2;
         for (int TH = (pool == 2 ? 2 : 1); TH <= Hout; TH += (pool == 2 ? 2 : 1)) {
-          const int n_mt = (TH * TWP + 127) / 128;
+          const int n_mt = (TH * TWP + mt_stride - 1) / mt_stride;
           if (n_mt > mt_max || n_mt > 2 * kMmaWarps) break;  // each MMA warp owns at most two m-tiles
           const int slots_alloc = round_up(n_mt * 128 + 2 * TWP + 2, 8);  // planes stay 128-byte aligned (TMA)
           const size_t in_bytes = (size_t)2 * planes * slots_alloc * 16;
@@ -900,7 +1029,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
             if (fixed + 2 * stage_bytes > smem_cap) continue;
             int st = (int)((smem_cap - fixed) / stage_bytes);
             if (st > kMaxStages) st = kMaxStages;
-            const double per_tap = (double)9 * (KC / 8) * n_chunks;  // (tap, k8) steps per tile
+            const double per_tap = (double)(rs ? 3 : 9) * (KC / 8) * n_chunks;  // (tap | filter row, k8) steps per tile
             const double step_tc = n_mt * hw_cycles;  // tensor-core occupancy of one step
             // issue: ~75 cycles per instruction for a warp that owns one m-tile, ~50 with two (tools/conv_timeline.py)
             const int mt_warp = (n_mt + kMmaWarps - 1) / kMmaWarps;
@@ -908,7 +1037,8 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
             const double step = step_tc > step_issue ? step_tc : step_issue;
             const double mma_item = per_tap * step;
             const double prod_item = (double)n_chunks * stage_bytes / kProdBytesPerCycle;
-            const double epi_item = 500.0 + n_mt * (NPc / 16) * (merged ? 550.0 : 450.0);  // measured: slow (TMEM latency)
+            // measured: slow (TMEM latency); rowstack reads three times the columns and exchanges rows between lanes
+            const double epi_item = 500.0 + n_mt * (NPc / 16) * (rs ? 1500.0 : (merged ? 550.0 : 450.0));
             double item = mma_item > prod_item ? mma_item : prod_item;
             if (nbuf == 1)
               item += epi_item;  // single accumulator buffer: the next tile's MMAs wait for the epilogue
@@ -926,6 +1056,8 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
               bp.NPc = NPc;
               bp.n_split = n_split;
               bp.merged = merged;
+              bp.rowstack = rs;
+              bp.mt_stride = mt_stride;
               bp.TH = TH;
               bp.TW = TW;
               bp.TWP = TWP;
@@ -948,6 +1080,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
       }
     }
    }
+   }
   }
   if (!found) return RA_ERR_UNSUPPORTED;
   // K split for PRECISION: the TMEM accumulators truncate every fp32 accumulation, a bias proportional to the
@@ -959,9 +1092,9 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
       const char *e = getenv("RA_UMMA_KSPLIT");
       return e ? (atoi(e) < 1 ? 1 : atoi(e)) : kKsplitDefault;
     }();
-    const int cols_mt = bp.merged ? 2 * bp.NPc : bp.NPc;
+    const int cols_mt = bp.rowstack ? 6 * bp.NPc : (bp.merged ? 2 * bp.NPc : bp.NPc);
     int ks = 512 / (bp.nbuf * bp.n_mt * cols_mt);
-    const int steps = 9 * (bp.KC / 8) * bp.n_chunks;
+    const int steps = (bp.rowstack ? 3 : 9) * (bp.KC / 8) * bp.n_chunks;
     if (ks > steps) ks = steps;
     if (ks > cap) ks = cap;
     if (ks < 1) ks = 1;
@@ -986,6 +1119,8 @@ int make_plan_forced(int Cin, int Cout, int Hout, int Wout, int pool, int B, Pla
   bp.NPc = NP / n_split;
   bp.n_split = n_split;
   bp.merged = bp.NPc <= 64 ? 1 : 0;
+  bp.rowstack = 0;
+  bp.mt_stride = 128;
   const int cols_mt = bp.merged ? 2 * bp.NPc : bp.NPc;
   bp.TH = TH;
   bp.TW = TW;
@@ -1099,7 +1234,7 @@ extern "C" int ra_debug_conv_timeline(long long *device_buf) {
 
 // Plan query for the host-side weight packer.
 extern "C" int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc,
-                                    int *n_split, int *n_chunks) {
+                                    int *n_split, int *n_chunks, int *rowstack) {
   Plan pl;
   const int rc = make_plan_forced(Cin, Cout, Hout, Wout, pool, B, &pl);
   if (rc != RA_OK) return rc;
@@ -1107,20 +1242,21 @@ extern "C" int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int p
   if (NPc) *NPc = pl.NPc;
   if (n_split) *n_split = pl.n_split;
   if (n_chunks) *n_chunks = pl.n_chunks;
+  if (rowstack) *rowstack = pl.rowstack;
   return RA_OK;
 }
 
-// Full plan dump (diagnostics / DESIGN.md tables): info[18] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages,
+// Full plan dump (diagnostics / DESIGN.md tables): info[19] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages,
 // merged, w_resident, grid, smem_bytes, acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf.
 extern "C" int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info) {
   Plan pl;
   const int rc = make_plan_forced(Cin, Cout, Hout, Wout, pool, B, &pl);
   if (rc != RA_OK) return rc;
   if (!info) return RA_ERR_INVALID_ARG;
-  const int v[18] = {pl.KC, pl.NPc, pl.n_split, pl.n_chunks, pl.TH, pl.TW, pl.n_mt, pl.stages, pl.merged,
+  const int v[19] = {pl.KC, pl.NPc, pl.n_split, pl.n_chunks, pl.TH, pl.TW, pl.n_mt, pl.stages, pl.merged,
                      pl.w_resident, pl.grid, (int)pl.smem_bytes, pl.acc_cols, pl.stage_bytes, pl.w_res_bytes,
-                     pl.slots_alloc, pl.ksplit, pl.nbuf};
-  for (int i = 0; i < 18; ++i) info[i] = v[i];
+                     pl.slots_alloc, pl.ksplit, pl.nbuf, pl.rowstack};
+  for (int i = 0; i < 19; ++i) info[i] = v[i];
   return RA_OK;
 }
 
@@ -1163,6 +1299,8 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   p.NPc = pl.NPc;
   p.n_split = pl.n_split;
   p.merged = pl.merged;
+  p.rowstack = pl.rowstack;
+  p.mt_stride = pl.mt_stride;
   p.slots_alloc = pl.slots_alloc;
   p.stages = pl.stages;
   p.w_resident = pl.w_resident;
@@ -1180,7 +1318,7 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   p.dbg = g_conv_dbg;
   // ---- TMA feed: needs channel counts that are multiples of 4 (16-byte global strides) and boxes <= 256
   const bool no_tma = getenv("RA_CONV_NO_TMA") != nullptr;  // diagnostics: plain-load producers everywhere
-  constexpr size_t kSmemMax = 224 * 1024;  // + ~2.3 KB static shared memory <= 227 KB
+  constexpr size_t kSmemMax = 222 * 1024;  // + ~3.8 KB static shared memory <= 227 KB
   p.tma = 0;
   p.RW = upsample == 2 ? p.TW / 2 + 1 : p.TWP;
   p.RH = upsample == 2 ? p.TH / 2 + 2 : p.TH + 2;

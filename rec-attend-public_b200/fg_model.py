@@ -115,8 +115,8 @@ class FgModel(object):
       if not os.environ.get('RA_CONV_FP32'):
         w = L['w']
         try:
-          KC, NPc, nsp, _ = ops.umma_plan(w.shape[2], w.shape[3], L['Hout'], L['Wout'], L['pool'], B)
-          packed = self._dev(ops.pack_umma_weights(w, KC, NPc, nsp))
+          KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], L['Hout'], L['Wout'], L['pool'], B)
+          packed = self._dev(ops.pack_umma_weights(w, KC, NPc, nsp, rs))
         except _lib.RecAttendError:
           packed = None  # no tile plan for this shape (RA_ERR_UNSUPPORTED): fp32 kernel below
       if packed is None and 'w_dev' not in L:

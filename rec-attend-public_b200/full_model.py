@@ -238,8 +238,8 @@ class _ModelBase(object):
     key = (B, pool)  # the tile plan (hence the packed image) depends on the batch size and on the pooling
     if key not in wp['packed']:
       w = wp['w']
-      KC, NPc, nsp, _ = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], pool, B)
-      wp['packed'][key] = self._dev(PM.pack_umma(PM.WI(w, wp['idx']), KC, NPc, nsp))
+      KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], pool, B)
+      wp['packed'][key] = self._dev(PM.pack_umma(PM.WI(w, wp['idx']), KC, NPc, nsp, rs))
     return ops.conv3x3_block_umma(x, wp['packed'][key], wp['w'].shape[3], scale, shift, pool=pool, relu=relu, x2=x2,
                                   upsample=upsample, out=out)
 

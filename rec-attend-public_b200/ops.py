@@ -102,40 +102,32 @@ def canvas_conv(pre, canvas, w, scale, shift, pool=1, relu=True, out=None):
 
 
 def umma_plan(Cin, Cout, Hout, Wout, pool, B):
-  """(KC, NPc, n_split, n_chunks) of the tcgen05 conv kernel for one layer shape and batch size."""
-  kc, npc, nsp, nch = _c.c_int(0), _c.c_int(0), _c.c_int(0), _c.c_int(0)
+  """(KC, NPc, n_split, n_chunks, rowstack) of the tcgen05 conv kernel for one layer shape and batch size; the
+  filter image must be packed for exactly this plan (pack_umma_weights / params.pack_umma)."""
+  kc, npc, nsp, nch, rs = _c.c_int(0), _c.c_int(0), _c.c_int(0), _c.c_int(0), _c.c_int(0)
   _lib.call('ra_conv3x3_umma_plan', Cin, Cout, Hout, Wout, pool, B, _c.byref(kc), _c.byref(npc), _c.byref(nsp),
-            _c.byref(nch))
-  return kc.value, npc.value, nsp.value, nch.value
+            _c.byref(nch), _c.byref(rs))
+  return kc.value, npc.value, nsp.value, nch.value, rs.value
 
 
 def umma_plan_info(Cin, Cout, Hout, Wout, pool, B):
   """The full tile plan of the tcgen05 conv kernel as a dict (diagnostics)."""
-  info = (_c.c_int * 18)()
+  info = (_c.c_int * 19)()
   _lib.call('ra_conv3x3_umma_plan_info', Cin, Cout, Hout, Wout, pool, B, info)
   keys = ['KC', 'NPc', 'n_split', 'n_chunks', 'TH', 'TW', 'n_mt', 'stages', 'merged', 'w_resident', 'grid',
-          'smem_bytes', 'acc_cols', 'stage_bytes', 'w_res_bytes', 'slots_alloc', 'ksplit', 'nbuf']
+          'smem_bytes', 'acc_cols', 'stage_bytes', 'w_res_bytes', 'slots_alloc', 'ksplit', 'nbuf', 'rowstack']
   return dict(zip(keys, list(info)))
 
 
-def pack_umma_weights(w_hwio, KC, NPc, n_split):
+def pack_umma_weights(w_hwio, KC, NPc, n_split, rowstack=0):
   """HWIO conv filter [3,3,Cin,Cout] (numpy) -> the kernel's shared-memory image
   [n_split][n_chunks][9][KC/4][2*NPc][4]: rows 0..NPc-1 = hi (w rounded to the nearest tf32),
-  rows NPc..2NPc-1 = lo = w - hi (exact)."""
+  rows NPc..2NPc-1 = lo = w - hi (exact); rowstack: [n_split][n_chunks][3][KC/4][6*NPc][4] with rows
+  [hi kx0 | hi kx1 | hi kx2 | lo kx0 | lo kx1 | lo kx2] (values only; params.pack_umma also carries the indices)."""
   import numpy as np
+  from . import params as PM
   w = np.asarray(w_hwio, np.float32)
-  _, _, Cin, Cout = w.shape
-  n_chunks = (Cin + KC - 1) // KC
-  NP = NPc * n_split
-  wp = np.zeros((9, n_chunks * KC, NP), np.float32)
-  wp[:, :Cin, :Cout] = w.reshape(9, Cin, Cout)
-  hi = ((wp.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)  # round to nearest tf32
-  lo = wp - hi
-
-  def lay(a):  # [9, chunks*KC, NP] -> [n_split, chunks, 9, KC/4, NPc, 4]
-    return a.reshape(9, n_chunks, KC // 4, 4, n_split, NPc).transpose(4, 1, 0, 2, 5, 3)
-
-  return np.ascontiguousarray(np.concatenate([lay(hi), lay(lo)], axis=4))
+  return PM.pack_umma(PM.WI(w, np.zeros(w.shape, np.int64)), KC, NPc, n_split, rowstack).val
 
 
 def conv3x3_block_umma(x, wpack, Cout, scale, shift, pool=1, relu=True, x2=None, upsample=1, out=None):

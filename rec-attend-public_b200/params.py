@@ -99,11 +99,18 @@ def tf32_hi(a):
   return ((a.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
-def pack_umma(wi, KC, NPc, n_split):
+def pack_umma(wi, KC, NPc, n_split, rowstack=0):
   """WI of an HWIO filter -> WI of the packed image [n_split][n_chunks][9][KC/4][2*NPc][4] with per-element kinds:
-  rows 0..NPc-1 = hi (w rounded to the nearest tf32), rows NPc..2NPc-1 = lo = w - hi (exact)."""
+  rows 0..NPc-1 = hi (w rounded to the nearest tf32), rows NPc..2NPc-1 = lo = w - hi (exact).
+  rowstack (narrow layers, csrc/conv_umma.cu issue_chunk_rs): [n_split][n_chunks][3 ky][KC/4][6*NPc][4] with rows
+  [hi kx0 | hi kx1 | hi kx2 | lo kx0 | lo kx1 | lo kx2]."""
   v = umma_layout(wi.val, KC, NPc, n_split)
   i = umma_layout(wi.idx, KC, NPc, n_split)
+  if rowstack:
+    def stack(a):  # [ns, nch, 9 = (ky, kx), pl, NPc, 4] -> [ns, nch, ky, pl, kx * NPc, 4]
+      ns, nch, _, pl, npc, four = a.shape
+      return a.reshape(ns, nch, 3, 3, pl, npc, four).transpose(0, 1, 2, 4, 3, 5, 6).reshape(ns, nch, 3, pl, 3 * npc, four)
+    v, i = stack(v), stack(i)
   hi = tf32_hi(v)
   lo = (v - hi).astype(np.float32)
   val = np.ascontiguousarray(np.concatenate([hi, lo], axis=4))

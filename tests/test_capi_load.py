@@ -64,20 +64,31 @@ def test_synthetic_batch_contract():
 
 def test_umma_plan_and_weight_packing():
   from rec_attend_b200 import ops
-  KC, NPc, nsp, nch = ops.umma_plan(64, 96, 12, 12, 2, 32)
-  assert KC in (8, 16, 32) and NPc * nsp == 96 and nch == 64 // KC
+  KC, NPc, nsp, nch, rs = ops.umma_plan(64, 96, 12, 12, 2, 32)
+  assert KC in (8, 16, 32) and NPc * nsp == 96 and nch == 64 // KC and rs == 0  # 6 * NPc > 256: no row stacking
   rng = np.random.default_rng(0)
   w = rng.standard_normal((3, 3, 13, 40)).astype(np.float32)
   for B in (1, 32):
-    KC, NPc, nsp, nch = ops.umma_plan(13, 40, 48, 48, 1, B)
+    KC, NPc, nsp, nch, rs = ops.umma_plan(13, 40, 48, 48, 1, B)
     assert NPc * nsp == 48 and NPc % 16 == 0
     wp = ops.pack_umma_weights(w, KC, NPc, nsp)
     assert wp.shape == (nsp, nch, 9, KC // 4, 2 * NPc, 4)
+    if rs:  # narrow split: the plan wants the row-stacked image
+      assert ops.pack_umma_weights(w, KC, NPc, nsp, rs).shape == (nsp, nch, 3, KC // 4, 6 * NPc, 4)
     hi, lo = wp[:, :, :, :, :NPc], wp[:, :, :, :, NPc:]
     # hi + lo reproduces w exactly; hi has at most 11 significant mantissa bits
     rec = (hi + lo).transpose(2, 1, 3, 5, 0, 4).reshape(9, nch * KC, nsp * NPc)
     assert (rec[:, :13, :40] == w.reshape(9, 13, 40)).all() and (rec[:, 13:] == 0).all() and (rec[:, :, 40:] == 0).all()
     assert (np.ascontiguousarray(hi).view(np.uint32) & np.uint32(0x1FFF) == 0).all()
+  # the row-stacked image (narrow layers, RA_UMMA_ROWSTACK): the three kx taps of a filter row along N
+  KC, NPc, nsp, nch, rs = ops.umma_plan(16, 16, 128, 256, 2, 32)
+  assert NPc == 16 and rs in (0, 1)
+  w16 = rng.standard_normal((3, 3, 16, 16)).astype(np.float32)
+  st = ops.pack_umma_weights(w16, KC, NPc, nsp, 1)
+  assert st.shape == (nsp, nch, 3, KC // 4, 6 * NPc, 4)
+  rec = st[..., :3 * NPc, :] + st[..., 3 * NPc:, :]  # hi + lo: [ns, nch, ky, pl, kx*NPc + co, 4]
+  rec = rec.reshape(nsp, nch, 3, KC // 4, 3, NPc, 4).transpose(2, 4, 1, 3, 6, 0, 5).reshape(3, 3, nch * KC, nsp * NPc)
+  assert (rec[:, :, :16, :16] == w16).all()
   with pytest.raises(Exception):
     ops.umma_plan(8, 8, 7, 7, 1, 1)  # odd output width is not supported
 

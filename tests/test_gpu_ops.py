@@ -505,8 +505,8 @@ def test_conv3x3_block_umma(ops, case):
     ref = torch.relu(ref)
   if pool == 2:
     ref = OM.max_pool_same(ref, 2)
-  KC, NPc, nsp, nch = ops.umma_plan(Cin, Cout, H * up, W * up, pool, B)
-  wp = ops.pack_umma_weights(w, KC, NPc, nsp)
+  KC, NPc, nsp, nch, rs = ops.umma_plan(Cin, Cout, H * up, W * up, pool, B)
+  wp = ops.pack_umma_weights(w, KC, NPc, nsp, rs)
   assert wp.shape == (nsp, nch, 9, KC // 4, 2 * NPc, 4)
   out = ops.conv3x3_block_umma(_g(x1), _g(wp), Cout, _g(scale), _g(shift), pool=pool, relu=bool(relu),
                                x2=None if x2 is None else _g(x2), upsample=up)
@@ -658,8 +658,8 @@ def test_conv_block_train_mode(ops):
   b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
   p = {'gamma': rng.uniform(0.5, 1.5, Cout).astype(np.float32), 'beta': rng.standard_normal(Cout).astype(np.float32),
        'ema_mean': np.zeros(Cout, np.float32), 'ema_var': np.ones(Cout, np.float32)}
-  KC, NPc, nsp, _ = ops.umma_plan(Cin, Cout, H, W, 1, B)
-  wp = _g(ops.pack_umma_weights(w, KC, NPc, nsp))
+  KC, NPc, nsp, _, rs = ops.umma_plan(Cin, Cout, H, W, 1, B)
+  wp = _g(ops.pack_umma_weights(w, KC, NPc, nsp, rs))
   y, bm, bv = ops.conv3x3_block_train(_g(x), wp, _g(b), _g(p['gamma']), _g(p['beta']), pool=pool)
   raw = OM.conv2d_same(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b))
   normed, mean, var, _, _ = OM.batch_norm_train(raw, {k: torch.from_numpy(v) for k, v in p.items()})
@@ -707,3 +707,21 @@ def test_random_transformation_errors(ops):
     ops.random_transformation(x, 2, (5, 0))                            # offset > 2*padding
   with pytest.raises(_lib.RecAttendError):
     ops.random_transformation(x, 2, (1, 1), hflip=True, d=torch.zeros((1, 8, 12, 8), device='cuda'))
+
+
+def test_rowstack_mode_matches_fp32_conv(cuda):
+  """The opt-in row-stacked-taps mode of the tcgen05 convolution (RA_UMMA_ROWSTACK=2: three kx taps share one read of
+  the A operand, lanes combined in the epilogue) against the CUDA-core fp32 convolution on every narrow KITTI layer
+  shape, pooled / transposed / skip-concatenated / odd-sized.  The mode is read once per process: subprocess."""
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ, RA_UMMA_ROWSTACK='2')
+  out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'rowstack_ab.py')], env=env, capture_output=True,
+                       text=True, timeout=600)
+  assert out.returncode == 0, out.stderr[-2000:]
+  rows = [l for l in out.stdout.splitlines() if l.startswith('mode 2 ') and ' err ' in l]
+  assert len(rows) >= 12 and sum("'rowstack': 1" in l for l in rows) >= 10
+  for l in rows:
+    assert float(l.split(' err ')[1].split()[0]) < 1e-5, l

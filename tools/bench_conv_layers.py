@@ -31,7 +31,7 @@ def time_layer(shape, force):
   x1 = torch.from_numpy(rng.standard_normal((B, H, W, C1)).astype(np.float32)).cuda()
   x2 = torch.from_numpy(rng.standard_normal((B, H, W, C2)).astype(np.float32)).cuda() if C2 else None
   w = rng.standard_normal((3, 3, C1 + C2, Cout)).astype(np.float32)
-  wp = torch.from_numpy(ops.pack_umma_weights(w, info['KC'], info['NPc'], info['n_split'])).cuda()
+  wp = torch.from_numpy(ops.pack_umma_weights(w, info['KC'], info['NPc'], info['n_split'], info['rowstack'])).cuda()
   sc = torch.ones(Cout, device='cuda'); sh = torch.zeros(Cout, device='cuda')
   out = ops.conv3x3_block_umma(x1, wp, Cout, sc, sh, pool=pool, x2=x2, upsample=up)
   flush = torch.empty(64 << 20, device='cuda')
