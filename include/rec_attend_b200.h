@@ -403,16 +403,19 @@ int ra_gaussian_filters_bwd_f32(const float *box, const float *fy, const float *
 /* Step-batched forms (example n = t * n_inner + b of a [T, n_inner, ...] stack):
  *  ra_paste_back_bwd_ex_f32: d_out / out of example n at (n % n_inner) * out_bstride + (n / n_inner) * out_ostride
  *    (a [B,T,H,W] stack read in [T,B] order: out_bstride = T*H*W, out_ostride = H*W).
- *  ra_gaussian_extract_bwd_ex_f32: xs_bmod > 0: xs holds xs_bmod examples shared by every step (n % xs_bmod). */
+ *  ra_gaussian_extract_bwd_ex_f32: xs_bmod > 0: xs holds xs_bmod examples shared by every step (n % xs_bmod).
+ *  box (both; may be NULL) = the [B,RA_BOX_STRIDE] records the filters were built from by ra_gaussian_filters_f32:
+ *    the kernels then only walk the support bands of the taps (entries outside are exact zeros) - the work is
+ *    proportional to the attended window instead of the image. */
 int ra_paste_back_bwd_ex_f32(const float *d_out, const float *out, size_t out_bstride, int n_inner, size_t out_ostride,
                              const float *patch, const float *fy, const float *fx, const float *gamma, int gamma_stride,
-                             int B, int H, int W, int F, int accumulate, void *ws, float *d_patch, float *d_fy,
-                             float *d_fx, float *d_gamma, void *stream);
+                             const float *box, int B, int H, int W, int F, int accumulate, void *ws, float *d_patch,
+                             float *d_fy, float *d_fx, float *d_gamma, void *stream);
 int ra_gaussian_extract_bwd_ex_f32(const float *xs, int Cs, int xs_bmod, const float *canvas, const int32_t *chan_map,
                                    const float *fy, const float *fx, const float *gamma, int gamma_stride,
-                                   const float *d_patch, const float *x_patch, int patch_cstride, int B, int H, int W,
-                                   int F, int accumulate, void *ws, float *d_fy, float *d_fx, float *d_gamma,
-                                   void *stream);
+                                   const float *box, const float *d_patch, const float *x_patch, int patch_cstride,
+                                   int B, int H, int W, int F, int accumulate, void *ws, float *d_fy, float *d_fx,
+                                   float *d_gamma, void *stream);
 
 /* --------------------------------------------------------------------------------------
  * Backward of the controller (full_model.py:668-725) — TensorFlow's autodiff of the soft read-out, the LSTM, the

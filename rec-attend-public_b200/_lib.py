@@ -75,9 +75,10 @@ _SIGNATURES = {
     'ra_outer_sum_f32': [_P, _Z, _I, _P, _Z, _I, _I, _P, _P, _P],
     'ra_bn_train_block_bwd_grouped_f32': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     'ra_conv3x3_bwd_weight_ex_f32': [_P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
-    'ra_paste_back_bwd_ex_f32': [_P, _P, _Z, _I, _Z, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
-    'ra_gaussian_extract_bwd_ex_f32': [_P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P,
-                                       _P, _P],
+    'ra_paste_back_bwd_ex_f32': [_P, _P, _Z, _I, _Z, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P,
+                                 _P],
+    'ra_gaussian_extract_bwd_ex_f32': [_P, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P,
+                                       _P, _P, _P],
     'ra_param_gather_f32': [_P, _P, _P, _P, _I, ctypes.c_longlong, _P],
     'ra_param_scatter_f32': [_P, _P, _P, _P, _I, ctypes.c_longlong, _P],
     'ra_bn_fold_f32': [_P, _P, _P, _P, _P, _I, _I, _F, _P, _P, _P],

@@ -23,15 +23,22 @@ constexpr int kMaxF = 64;
 constexpr int kT = 256;
 
 // R[b,i,x] = sum_j P[b,i,j] fx[b,j,x]   (P == nullptr: ones)
-__global__ void __launch_bounds__(kT) pb_R_kernel(const float *__restrict__ patch, const float *__restrict__ fx, int W,
-                                                  int F, float *__restrict__ R) {
+__global__ void __launch_bounds__(kT) pb_R_kernel(const float *__restrict__ patch, const float *__restrict__ fx,
+                                                  const float *__restrict__ box, int box_stride, int W, int F,
+                                                  float *__restrict__ R) {
   extern __shared__ float P_s[];  // [F][F]
   const int b = blockIdx.y;
+  int xlo = 0, xhi = W - 1;
+  if (box != nullptr) ra::band_union(box + (size_t)b * box_stride, 1, F, W, &xlo, &xhi);
+  {
+    const int c0 = blockIdx.x * kT;
+    if (c0 > xhi || c0 + kT - 1 < xlo) return;  // whole CTA outside the box columns: R is never read there
+  }
   if (patch != nullptr)
     for (int i = threadIdx.x; i < F * F; i += kT) P_s[i] = patch[(size_t)b * F * F + i];
   __syncthreads();
   const int x = blockIdx.x * kT + threadIdx.x;
-  if (x >= W) return;
+  if (x >= W || x < xlo || x > xhi) return;
   const float *fxb = fx + (size_t)b * F * W + x;
   float *Rb = R + (size_t)b * F * W + x;
   if (patch == nullptr) {
@@ -52,22 +59,37 @@ __global__ void __launch_bounds__(kT) pb_row_kernel(const float *__restrict__ d_
                                                     size_t out_bstride, int n_inner, size_t out_ostride,
                                                     const float *__restrict__ fy,
                                                     const float *__restrict__ R, const float *__restrict__ gamma,
-                                                    int gamma_stride, int H, int W, int F, int accumulate,
+                                                    int gamma_stride, const float *__restrict__ box, int box_stride,
+                                                    int H, int W, int F, int accumulate,
                                                     float *__restrict__ dV, float *__restrict__ d_fy,
                                                     float *__restrict__ dgamma_rows) {
   __shared__ float fy_s[kMaxF];
   __shared__ float red[32];
   __shared__ float dfy_s[kMaxF];
   const int y = blockIdx.x, b = blockIdx.y;
+  // Only the box region matters: V = Fy P Fx^T vanishes outside the union bands, and every product below carries a
+  // filter entry that is an exact zero there.
+  int xlo = 0, xhi = W - 1, ylo = 0, yhi = H - 1;
+  if (box != nullptr) {
+    ra::band_union(box + (size_t)b * box_stride, 0, F, H, &ylo, &yhi);
+    ra::band_union(box + (size_t)b * box_stride, 1, F, W, &xlo, &xhi);
+  }
+  if (y < ylo || y > yhi) {  // no tap reaches this row: no contribution to d_gamma, d_fy[:, y] = 0
+    if (threadIdx.x == 0) dgamma_rows[(size_t)b * H + y] = 0.f;
+    if (!accumulate)
+      for (int i = threadIdx.x; i < F; i += kT) d_fy[((size_t)b * F + i) * H + y] = 0.f;
+    return;
+  }
   for (int i = threadIdx.x; i < F; i += kT) fy_s[i] = fy[((size_t)b * F + i) * H + y];
   __syncthreads();
   const float g = gamma[(size_t)b * gamma_stride];
   const float *Rb = R + (size_t)b * F * W;
   const size_t row = (size_t)(b % n_inner) * out_bstride + (size_t)(b / n_inner) * out_ostride + (size_t)y * W;
   float dg = 0.f;
-  for (int x = threadIdx.x; x < W; x += kT) {
+  for (int x = xlo + threadIdx.x; x <= xhi; x += kT) {
     float v = 0.f;
-    for (int i = 0; i < F; ++i) v = fmaf(fy_s[i], Rb[(size_t)i * W + x], v);
+    for (int i = 0; i < F; ++i)
+      if (fy_s[i] != 0.f) v = fmaf(fy_s[i], Rb[(size_t)i * W + x], v);
     const float o = out[row + x];
     const float dz = d_out[row + x] * o * (1.0f - o);
     dg = fmaf(dz, v, dg);
@@ -77,8 +99,13 @@ __global__ void __launch_bounds__(kT) pb_row_kernel(const float *__restrict__ d_
   if (threadIdx.x == 0) dgamma_rows[(size_t)b * H + y] = dg;
   __syncthreads();  // this row of dV is complete (written by this CTA only)
   for (int i = 0; i < F; ++i) {
+    if (fy_s[i] == 0.f) {  // outside this tap's band: d_fy[i, y] only ever multiplies the zero filter entry
+      if (threadIdx.x == 0) dfy_s[i] = 0.f;
+      continue;  // (uniform: fy_s is shared)
+    }
     float s = 0.f;
-    for (int x = threadIdx.x; x < W; x += kT) s = fmaf(dV[((size_t)b * H + y) * W + x], Rb[(size_t)i * W + x], s);
+    for (int x = xlo + threadIdx.x; x <= xhi; x += kT)
+      s = fmaf(dV[((size_t)b * H + y) * W + x], Rb[(size_t)i * W + x], s);
     s = ra::block_sum(s, red);
     if (threadIdx.x == 0) dfy_s[i] = s;
   }
@@ -91,20 +118,39 @@ __global__ void __launch_bounds__(kT) pb_row_kernel(const float *__restrict__ d_
 
 // thread per column x: A[:, x] = Fy^T dV[:, x] in registers, stored; d_fx[:, x] = P^T A[:, x]
 __global__ void __launch_bounds__(kT) pb_col_kernel(const float *__restrict__ dV, const float *__restrict__ fy,
-                                                    const float *__restrict__ patch, int H, int W, int F,
+                                                    const float *__restrict__ patch, const float *__restrict__ box,
+                                                    int box_stride, int H, int W, int F,
                                                     int accumulate, float *__restrict__ A, float *__restrict__ d_fx) {
   extern __shared__ float P_s[];  // [F][F]
   const int b = blockIdx.y;
+  int xlo = 0, xhi = W - 1, ylo = 0, yhi = H - 1;
+  if (box != nullptr) {
+    ra::band_union(box + (size_t)b * box_stride, 0, F, H, &ylo, &yhi);
+    ra::band_union(box + (size_t)b * box_stride, 1, F, W, &xlo, &xhi);
+  }
+  const int x = blockIdx.x * kT + threadIdx.x;
+  {
+    const int c0 = blockIdx.x * kT;
+    if (c0 > xhi || c0 + kT - 1 < xlo) {  // no tap reaches these columns: d_fx[:, x] = 0, A is never read there
+      if (!accumulate && x < W)
+        for (int j = 0; j < F; ++j) d_fx[((size_t)b * F + j) * W + x] = 0.f;
+      return;
+    }
+  }
   if (patch != nullptr)
     for (int i = threadIdx.x; i < F * F; i += kT) P_s[i] = patch[(size_t)b * F * F + i];
   __syncthreads();
-  const int x = blockIdx.x * kT + threadIdx.x;
   if (x >= W) return;
+  if (x < xlo || x > xhi) {
+    if (!accumulate)
+      for (int j = 0; j < F; ++j) d_fx[((size_t)b * F + j) * W + x] = 0.f;
+    return;
+  }
   float acc[kMaxF];
 #pragma unroll
   for (int i = 0; i < kMaxF; ++i) acc[i] = 0.f;
   const float *fyb = fy + (size_t)b * F * H;
-  for (int y = 0; y < H; ++y) {
+  for (int y = ylo; y <= yhi; ++y) {
     const float v = dV[((size_t)b * H + y) * W + x];
     if (v == 0.f) continue;
 #pragma unroll
@@ -126,7 +172,8 @@ __global__ void __launch_bounds__(kT) pb_col_kernel(const float *__restrict__ dV
 
 // d_P[b,i,j] = sum_x A[b,i,x] fx[b,j,x]: one warp per (i, j); d_gamma[b] = sum of the row shares (CTA 0)
 __global__ void __launch_bounds__(kT) pb_dP_kernel(const float *__restrict__ A, const float *__restrict__ fx,
-                                                   const float *__restrict__ dgamma_rows, int H, int W, int F,
+                                                   const float *__restrict__ dgamma_rows,
+                                                   const float *__restrict__ box, int box_stride, int H, int W, int F,
                                                    float *__restrict__ d_patch, float *__restrict__ d_gamma) {
   __shared__ float red[32];
   const int b = blockIdx.y;
@@ -142,8 +189,10 @@ __global__ void __launch_bounds__(kT) pb_dP_kernel(const float *__restrict__ A, 
   if (ij >= F * F) return;
   const int i = ij / F, j = ij - i * F;
   const float *Ai = A + ((size_t)b * F + i) * W, *fj = fx + ((size_t)b * F + j) * W;
+  int xlo = 0, xhi = W - 1;
+  if (box != nullptr) ra::tap_band(box + (size_t)b * box_stride, 1, j, F, W, &xlo, &xhi);
   float s = 0.f;
-  for (int x = lane; x < W; x += 32) s = fmaf(Ai[x], fj[x], s);
+  for (int x = xlo + lane; x <= xhi; x += 32) s = fmaf(Ai[x], fj[x], s);
   s = ra::warp_sum(s);
   if (lane == 0) d_patch[(size_t)b * F * F + ij] = s;
 }
@@ -193,123 +242,161 @@ __global__ void __launch_bounds__(kT) filters_bwd_kernel(const float *__restrict
 //   d_fy[i,y] = sum_{x,c} S[i,x,c] X[y,x,c],   S[i,x,c] = gamma * sum_j G[i,j,c] fx[j,x]
 //   d_gamma   = sum G * x_patch / gamma
 // No gradient flows to X: the image is data and the canvas is behind tf.stop_gradient (full_model.py:846-848).
-// thread per (x, c): T[b,i,x,c] for every tap i
-__global__ void __launch_bounds__(kT) ex_T_kernel(const float *__restrict__ xs, int Cs, int xs_bmod,
-                                                  const float *__restrict__ canvas,
-                                                  const float *__restrict__ fy, int H, int W, int F, int D,
-                                                  float *__restrict__ T) {
-  const int b = blockIdx.y;
-  const int bx = xs_bmod > 0 ? b % xs_bmod : b;
-  const int idx = blockIdx.x * kT + threadIdx.x;
-  if (idx >= W * D) return;
-  const int x = idx / D, c = idx - x * D;
-  float acc[kMaxF];
-#pragma unroll
-  for (int i = 0; i < kMaxF; ++i) acc[i] = 0.f;
-  const float *fyb = fy + (size_t)b * F * H;
-  for (int y = 0; y < H; ++y) {
-    const float v = (c < Cs) ? xs[(((size_t)bx * H + y) * W + x) * Cs + c] : canvas[((size_t)b * H + y) * W + x];
-#pragma unroll
-    for (int i = 0; i < kMaxF; ++i)
-      if (i < F) acc[i] = fmaf(fyb[(size_t)i * H + y], v, acc[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < kMaxF; ++i)
-    if (i < F) T[(((size_t)b * F + i) * W + x) * D + c] = acc[i];
+// Band-limited: fy[i, :] is non-zero only on tap i's y-band, fx[j, :] on tap j's x-band (ra::tap_band), so
+//   T[i,x,c]  is needed for x in the union x-band and sums over y in band_i,
+//   d_fx[j,x] is needed for x in band_j only (outside it multiplies the zero filter entry in the filter backward),
+//   S[i,x,c]  sums over the taps j whose band holds x,  d_fy[i,y] is needed for y in band_i only.
+// box == nullptr: dense filters of unknown origin - every range is the full axis.
+__device__ __forceinline__ void axis_union(const float *box, int b, int axis, int F, int L, int *lo, int *hi) {
+  *lo = 0;
+  *hi = L - 1;
+  if (box != nullptr) ra::band_union(box + (size_t)b * RA_BOX_STRIDE, axis, F, L, lo, hi);
+}
+__device__ __forceinline__ void axis_tap(const float *box, int b, int axis, int t, int F, int L, int *lo, int *hi) {
+  *lo = 0;
+  *hi = L - 1;
+  if (box != nullptr) ra::tap_band(box + (size_t)b * RA_BOX_STRIDE, axis, t, F, L, lo, hi);
 }
 
-// grid (x blocks, b): d_fx[b,:,x] (+)= gamma * sum_{i,c} G[b,i,:,ch(c)] T[b,i,x,c];  G rows staged per tap i
-__global__ void __launch_bounds__(kT) ex_dfx_kernel(const float *__restrict__ G, int cstride,
-                                                    const int *__restrict__ chan_map, const float *__restrict__ T,
-                                                    const float *__restrict__ gamma, int gamma_stride, int W, int F,
-                                                    int D, int accumulate, float *__restrict__ d_fx) {
-  extern __shared__ float G_s[];  // [F (j)][D] of the current tap i, source-channel order
-  const int b = blockIdx.y;
-  const int x = blockIdx.x * kT + threadIdx.x;
-  float acc[kMaxF];
+// grid ((x,c) chunks, tap groups of kExIB, b): T[b,i,x,c] = sum_{y in band_i} fy[i,y] X[y,x,c], x in the union x-band
+constexpr int kExIB = 4;
+__global__ void __launch_bounds__(kT) ex_T_kernel(const float *__restrict__ xs, int Cs, int xs_bmod,
+                                                  const float *__restrict__ canvas, const float *__restrict__ fy,
+                                                  const float *__restrict__ box, int H, int W, int F, int D,
+                                                  float *__restrict__ T) {
+  const int b = blockIdx.z;
+  const int bx = xs_bmod > 0 ? b % xs_bmod : b;
+  const int i0 = blockIdx.y * kExIB;
+  int xlo, xhi;
+  axis_union(box, b, 1, F, W, &xlo, &xhi);
+  const int idx = blockIdx.x * kT + threadIdx.x;  // (x - xlo, c)
+  const int nxc = (xhi - xlo + 1) * D;
+  if (blockIdx.x * kT >= nxc) return;
+  int ylo = H, yhi = -1;
 #pragma unroll
-  for (int j = 0; j < kMaxF; ++j) acc[j] = 0.f;
-  for (int i = 0; i < F; ++i) {
-    __syncthreads();
-    for (int k = threadIdx.x; k < F * D; k += kT) {
-      const int j = k / D, c = k - j * D;
-      G_s[k] = G[(((size_t)b * F + i) * F + j) * cstride + chan_map[c]];
-    }
-    __syncthreads();
-    if (x < W) {
-      const float *Ti = T + (((size_t)b * F + i) * W + x) * D;
-      for (int c = 0; c < D; ++c) {
-        const float t = Ti[c];
-#pragma unroll
-        for (int j = 0; j < kMaxF; ++j)
-          if (j < F) acc[j] = fmaf(G_s[j * D + c], t, acc[j]);
+  for (int k = 0; k < kExIB; ++k)
+    if (i0 + k < F) {
+      int lo, hi;
+      axis_tap(box, b, 0, i0 + k, F, H, &lo, &hi);
+      if (hi >= lo) {
+        ylo = min(ylo, lo);
+        yhi = max(yhi, hi);
       }
     }
-  }
-  if (x >= W) return;
-  const float g = gamma[(size_t)b * gamma_stride];
+  if (idx >= nxc) return;
+  const int x = xlo + idx / D, c = idx % D;
+  float acc[kExIB];
 #pragma unroll
-  for (int j = 0; j < kMaxF; ++j)
-    if (j < F) {
-      float *dst = d_fx + ((size_t)b * F + j) * W + x;
-      *dst = accumulate ? fmaf(g, acc[j], *dst) : g * acc[j];
-    }
+  for (int k = 0; k < kExIB; ++k) acc[k] = 0.f;
+  const float *fyb = fy + ((size_t)b * F + i0) * H;
+  for (int y = ylo; y <= yhi; ++y) {
+    const float v = (c < Cs) ? __ldg(xs + (((size_t)bx * H + y) * W + x) * Cs + c) : __ldg(canvas + ((size_t)b * H + y) * W + x);
+#pragma unroll
+    for (int k = 0; k < kExIB; ++k)
+      if (i0 + k < F) acc[k] = fmaf(__ldg(fyb + (size_t)k * H + y), v, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < kExIB; ++k)
+    if (i0 + k < F) T[(((size_t)b * F + i0 + k) * W + x) * D + c] = acc[k];
 }
 
-// grid ((x,c) blocks, i, b): S[b,i,x,c] = gamma * sum_j G[b,i,j,ch(c)] fx[b,j,x]
-__global__ void __launch_bounds__(kT) ex_S_kernel(const float *__restrict__ G, int cstride,
-                                                  const int *__restrict__ chan_map, const float *__restrict__ fx,
-                                                  const float *__restrict__ gamma, int gamma_stride, int W, int F, int D,
-                                                  float *__restrict__ S) {
-  extern __shared__ float G_s[];  // [F (j)][D]
-  const int i = blockIdx.y, b = blockIdx.z;
+// grid (j, b): d_fx[b,j,x] (+)= gamma * sum_{i,c} G[b,i,j,ch(c)] T[b,i,x,c] for x in band_j (zero elsewhere); one warp
+// per column x, lanes over the (i, c) pairs
+__global__ void __launch_bounds__(kT) ex_dfx_kernel(const float *__restrict__ G, int cstride,
+                                                    const int *__restrict__ chan_map, const float *__restrict__ T,
+                                                    const float *__restrict__ gamma, int gamma_stride,
+                                                    const float *__restrict__ box, int W, int F, int D, int accumulate,
+                                                    float *__restrict__ d_fx) {
+  extern __shared__ float G_s[];  // [F (i)][D] of tap j, source-channel order
+  const int j = blockIdx.x, b = blockIdx.y;
+  for (int k = threadIdx.x; k < F * D; k += kT) {
+    const int i = k / D, c = k - i * D;
+    G_s[k] = G[(((size_t)b * F + i) * F + j) * cstride + chan_map[c]];
+  }
+  __syncthreads();
+  int xlo, xhi;
+  axis_tap(box, b, 1, j, F, W, &xlo, &xhi);
+  const float g = gamma[(size_t)b * gamma_stride];
+  float *dst = d_fx + ((size_t)b * F + j) * W;
+  if (!accumulate)
+    for (int x = threadIdx.x; x < W; x += kT)
+      if (x < xlo || x > xhi) dst[x] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int x = xlo + warp; x <= xhi; x += kT / 32) {
+    float s = 0.f;
+    for (int k = lane; k < F * D; k += 32) {
+      const int i = k / D, c = k - i * D;
+      s = fmaf(G_s[k], T[(((size_t)b * F + i) * W + x) * D + c], s);
+    }
+    s = ra::warp_sum(s);
+    if (lane == 0) dst[x] = accumulate ? fmaf(g, s, dst[x]) : g * s;
+  }
+}
+
+// grid (i, b): S[x,c] = gamma * sum_{j: x in band_j} G[b,i,j,ch(c)] fx[b,j,x] in shared memory (x in the union x-band,
+// processed in chunks), then d_fy[b,i,y] (+)= sum_{x,c} S[x,c] X[b,y,x,c] for y in band_i (zero elsewhere): one warp
+// per row y, partial sums over the chunks accumulated in registers of the owning warp.
+constexpr int kExChunk = 128;  // columns per shared-memory chunk
+__global__ void __launch_bounds__(kT) ex_dfy_kernel(const float *__restrict__ xs, int Cs, int xs_bmod,
+                                                    const float *__restrict__ canvas, const float *__restrict__ G,
+                                                    int cstride, const int *__restrict__ chan_map,
+                                                    const float *__restrict__ fx, const float *__restrict__ gamma,
+                                                    int gamma_stride, const float *__restrict__ box, int H, int W, int F,
+                                                    int D, int accumulate, float *__restrict__ d_fy) {
+  extern __shared__ float sm[];  // G_s [F (j)][D] | S_s [kExChunk][D] | band_s [F][2] (ints)
+  float *G_s = sm, *S_s = sm + F * D;
+  int *band_s = reinterpret_cast<int *>(S_s + kExChunk * D);
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int bx = xs_bmod > 0 ? b % xs_bmod : b;
   for (int k = threadIdx.x; k < F * D; k += kT) {
     const int j = k / D, c = k - j * D;
     G_s[k] = G[(((size_t)b * F + i) * F + j) * cstride + chan_map[c]];
   }
-  __syncthreads();
-  const int idx = blockIdx.x * kT + threadIdx.x;
-  if (idx >= W * D) return;
-  const int x = idx / D, c = idx - x * D;
-  const float *fxb = fx + (size_t)b * F * W + x;
-  float s = 0.f;
-  for (int j = 0; j < F; ++j) s = fmaf(G_s[j * D + c], fxb[(size_t)j * W], s);
-  S[(((size_t)b * F + i) * W) * D + idx] = gamma[(size_t)b * gamma_stride] * s;
-}
-
-// grid (row tiles of kExRows, b): d_fy[b,i,y] (+)= sum_{x,c} S[b,i,x,c] X[b,y,x,c]
-constexpr int kExRows = 8;
-__global__ void __launch_bounds__(kT) ex_dfy_kernel(const float *__restrict__ xs, int Cs, int xs_bmod,
-                                                    const float *__restrict__ canvas, const float *__restrict__ S, int H,
-                                                    int W, int F, int D, int accumulate, float *__restrict__ d_fy) {
-  __shared__ float red[32];
-  const int y0 = blockIdx.x * kExRows, b = blockIdx.y;
-  const int bx = xs_bmod > 0 ? b % xs_bmod : b;
-  const int n = W * D;
-  for (int i = 0; i < F; ++i) {
-    float acc[kExRows];
+  for (int j = threadIdx.x; j < F; j += kT) axis_tap(box, b, 1, j, F, W, &band_s[2 * j], &band_s[2 * j + 1]);
+  int xlo, xhi, ylo, yhi;
+  axis_union(box, b, 1, F, W, &xlo, &xhi);
+  axis_tap(box, b, 0, i, F, H, &ylo, &yhi);
+  float *dst = d_fy + ((size_t)b * F + i) * H;
+  if (!accumulate)
+    for (int y = threadIdx.x; y < H; y += kT)
+      if (y < ylo || y > yhi) dst[y] = 0.f;
+  const float g = gamma[(size_t)b * gamma_stride];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kRowsPerWarp = 8;  // rows y = ylo + warp + 8 * r, r < kRowsPerWarp  (bands are narrower than 64 rows;
+  float acc[kRowsPerWarp];         //  wider ones take more passes below)
+  for (int ybase = ylo; ybase <= yhi; ybase += kRowsPerWarp * (kT / 32)) {
 #pragma unroll
-    for (int r = 0; r < kExRows; ++r) acc[r] = 0.f;
-    const float *Si = S + ((size_t)b * F + i) * n;
-    for (int idx = threadIdx.x; idx < n; idx += kT) {
-      const float s = Si[idx];
-      if (s == 0.f) continue;
-      const int x = idx / D, c = idx - x * D;
+    for (int r = 0; r < kRowsPerWarp; ++r) acc[r] = 0.f;
+    for (int x0 = xlo; x0 <= xhi; x0 += kExChunk) {
+      const int nx = min(kExChunk, xhi - x0 + 1);
+      __syncthreads();  // G_s / band_s ready; the previous chunk has been consumed
+      for (int k = threadIdx.x; k < nx * D; k += kT) {
+        const int x = x0 + k / D, c = k % D;
+        float s = 0.f;
+        for (int j = 0; j < F; ++j)
+          if (x >= band_s[2 * j] && x <= band_s[2 * j + 1]) s = fmaf(G_s[j * D + c], __ldg(fx + ((size_t)b * F + j) * W + x), s);
+        S_s[k] = g * s;
+      }
+      __syncthreads();
 #pragma unroll
-      for (int r = 0; r < kExRows; ++r)
-        if (y0 + r < H) {
-          const float xv = (c < Cs) ? xs[(((size_t)bx * H + y0 + r) * W + x) * Cs + c]
-                                    : canvas[((size_t)b * H + y0 + r) * W + x];
-          acc[r] = fmaf(xv, s, acc[r]);
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        const int y = ybase + warp + (kT / 32) * r;
+        if (y > yhi) continue;
+        float s = 0.f;
+        for (int k = lane; k < nx * D; k += 32) {
+          const int x = x0 + k / D, c = k % D;
+          const float xv = (c < Cs) ? __ldg(xs + (((size_t)bx * H + y) * W + x) * Cs + c)
+                                    : __ldg(canvas + ((size_t)b * H + y) * W + x);
+          s = fmaf(S_s[k], xv, s);
         }
+        acc[r] += s;
+      }
     }
 #pragma unroll
-    for (int r = 0; r < kExRows; ++r) {
-      const float v = ra::block_sum(acc[r], red);
-      if (threadIdx.x == 0 && y0 + r < H) {
-        float *dst = d_fy + ((size_t)b * F + i) * H + y0 + r;
-        *dst = accumulate ? (*dst + v) : v;
-      }
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int y = ybase + warp + (kT / 32) * r;
+      const float v = ra::warp_sum(acc[r]);
+      if (y <= yhi && lane == 0) dst[y] = accumulate ? (dst[y] + v) : v;
     }
   }
 }
@@ -338,16 +425,17 @@ extern "C" int ra_paste_back_bwd_f32(const float *d_out, const float *out, size_
                                      const float *fy, const float *fx, const float *gamma, int gamma_stride, int B,
                                      int H, int W, int F, int accumulate, void *ws, float *d_patch, float *d_fy,
                                      float *d_fx, float *d_gamma, void *stream) {
-  return ra_paste_back_bwd_ex_f32(d_out, out, out_bstride, B > 0 ? B : 1, 0, patch, fy, fx, gamma, gamma_stride, B, H, W,
-                                  F, accumulate, ws, d_patch, d_fy, d_fx, d_gamma, stream);
+  return ra_paste_back_bwd_ex_f32(d_out, out, out_bstride, B > 0 ? B : 1, 0, patch, fy, fx, gamma, gamma_stride, nullptr,
+                                  B, H, W, F, accumulate, ws, d_patch, d_fy, d_fx, d_gamma, stream);
 }
 
 extern "C" int ra_paste_back_bwd_ex_f32(const float *d_out, const float *out, size_t out_bstride, int n_inner,
                                         size_t out_ostride, const float *patch, const float *fy, const float *fx,
-                                        const float *gamma, int gamma_stride, int B, int H, int W, int F,
-                                        int accumulate, void *ws, float *d_patch, float *d_fy, float *d_fx,
+                                        const float *gamma, int gamma_stride, const float *box, int B, int H, int W,
+                                        int F, int accumulate, void *ws, float *d_patch, float *d_fy, float *d_fx,
                                         float *d_gamma, void *stream) {
   if (n_inner < 1) return RA_ERR_INVALID_ARG;
+  const int box_stride = RA_BOX_STRIDE;
   if (B < 0 || H < 1 || W < 1 || F < 1 || F > kMaxF || gamma_stride < 1) return RA_ERR_INVALID_ARG;
   if (B == 0) return RA_OK;
   if (!d_out || !out || !fy || !fx || !gamma || !ws || !d_fy || !d_fx || !d_gamma) return RA_ERR_INVALID_ARG;
@@ -358,18 +446,19 @@ extern "C" int ra_paste_back_bwd_ex_f32(const float *d_out, const float *out, si
   float *R = dV + (size_t)B * H * W, *A = R + (size_t)B * F * W, *rows = A + (size_t)B * F * W;
   const size_t psm = (size_t)F * F * sizeof(float);
   const int bx = (W + kT - 1) / kT;
-  pb_R_kernel<<<dim3(bx, B), kT, psm, s>>>(patch, fx, W, F, R);
+  pb_R_kernel<<<dim3(bx, B), kT, psm, s>>>(patch, fx, box, box_stride, W, F, R);
   int rc = ra::finish_launch("pb_R_kernel");
   if (rc != RA_OK) return rc;
-  pb_row_kernel<<<dim3(H, B), kT, 0, s>>>(d_out, out, out_bstride, n_inner, out_ostride, fy, R, gamma, gamma_stride, H,
-                                          W, F, accumulate, dV, d_fy, rows);
+  pb_row_kernel<<<dim3(H, B), kT, 0, s>>>(d_out, out, out_bstride, n_inner, out_ostride, fy, R, gamma, gamma_stride, box,
+                                          box_stride, H, W, F, accumulate, dV, d_fy, rows);
   rc = ra::finish_launch("pb_row_kernel");
   if (rc != RA_OK) return rc;
-  pb_col_kernel<<<dim3(bx, B), kT, psm, s>>>(dV, fy, patch, H, W, F, accumulate, A, d_fx);
+  pb_col_kernel<<<dim3(bx, B), kT, psm, s>>>(dV, fy, patch, box, box_stride, H, W, F, accumulate, A, d_fx);
   rc = ra::finish_launch("pb_col_kernel");
   if (rc != RA_OK) return rc;
   const int pairs = d_patch ? F * F : 1;
-  pb_dP_kernel<<<dim3((pairs + kT / 32 - 1) / (kT / 32), B), kT, 0, s>>>(A, fx, rows, H, W, F, d_patch, d_gamma);
+  pb_dP_kernel<<<dim3((pairs + kT / 32 - 1) / (kT / 32), B), kT, 0, s>>>(A, fx, rows, box, box_stride, H, W, F, d_patch,
+                                                                         d_gamma);
   return ra::finish_launch("pb_dP_kernel");
 }
 
@@ -393,16 +482,16 @@ extern "C" int ra_gaussian_extract_bwd_f32(const float *xs, int Cs, const float 
                                            const float *d_patch, const float *x_patch, int patch_cstride, int B, int H,
                                            int W, int F, int accumulate, void *ws, float *d_fy, float *d_fx,
                                            float *d_gamma, void *stream) {
-  return ra_gaussian_extract_bwd_ex_f32(xs, Cs, 0, canvas, chan_map, fy, fx, gamma, gamma_stride, d_patch, x_patch,
-                                        patch_cstride, B, H, W, F, accumulate, ws, d_fy, d_fx, d_gamma, stream);
+  return ra_gaussian_extract_bwd_ex_f32(xs, Cs, 0, canvas, chan_map, fy, fx, gamma, gamma_stride, nullptr, d_patch,
+                                        x_patch, patch_cstride, B, H, W, F, accumulate, ws, d_fy, d_fx, d_gamma, stream);
 }
 
 extern "C" int ra_gaussian_extract_bwd_ex_f32(const float *xs, int Cs, int xs_bmod, const float *canvas,
                                               const int32_t *chan_map, const float *fy, const float *fx,
-                                              const float *gamma, int gamma_stride, const float *d_patch,
-                                              const float *x_patch, int patch_cstride, int B, int H, int W, int F,
-                                              int accumulate, void *ws, float *d_fy, float *d_fx, float *d_gamma,
-                                              void *stream) {
+                                              const float *gamma, int gamma_stride, const float *box,
+                                              const float *d_patch, const float *x_patch, int patch_cstride, int B,
+                                              int H, int W, int F, int accumulate, void *ws, float *d_fy, float *d_fx,
+                                              float *d_gamma, void *stream) {
   if (xs_bmod < 0) return RA_ERR_INVALID_ARG;
   const int D = Cs + (canvas ? 1 : 0);
   if (B < 0 || H < 1 || W < 1 || F < 1 || F > kMaxF || Cs < 0 || D < 1 || patch_cstride < D || gamma_stride < 1)
@@ -410,23 +499,21 @@ extern "C" int ra_gaussian_extract_bwd_ex_f32(const float *xs, int Cs, int xs_bm
   if (B == 0) return RA_OK;
   if ((Cs > 0 && !xs) || !chan_map || !fy || !fx || !gamma || !d_patch || !x_patch || !ws || !d_fy || !d_fx || !d_gamma)
     return RA_ERR_INVALID_ARG;
-  if (B > 65535 || (size_t)F * D * sizeof(float) > 48 * 1024) return RA_ERR_UNSUPPORTED;
+  if (B > 65535 || ((size_t)F * D + (size_t)kExChunk * D + 2 * F) * sizeof(float) > 48 * 1024) return RA_ERR_UNSUPPORTED;
   cudaStream_t s = ra::as_stream(stream);
-  float *T = reinterpret_cast<float *>(ws), *S = T + (size_t)B * F * W * D;
-  const int bxc = (W * D + kT - 1) / kT, bx = (W + kT - 1) / kT;
+  float *T = reinterpret_cast<float *>(ws);
+  const int bxc = (W * D + kT - 1) / kT;
   const size_t gsm = (size_t)F * D * sizeof(float);
-  ex_T_kernel<<<dim3(bxc, B), kT, 0, s>>>(xs, Cs, xs_bmod, canvas, fy, H, W, F, D, T);
+  ex_T_kernel<<<dim3(bxc, (F + kExIB - 1) / kExIB, B), kT, 0, s>>>(xs, Cs, xs_bmod, canvas, fy, box, H, W, F, D, T);
   int rc = ra::finish_launch("ex_T_kernel");
   if (rc != RA_OK) return rc;
-  ex_dfx_kernel<<<dim3(bx, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, T, gamma, gamma_stride, W, F, D, accumulate,
-                                             d_fx);
+  ex_dfx_kernel<<<dim3(F, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, T, gamma, gamma_stride, box, W, F, D,
+                                            accumulate, d_fx);
   rc = ra::finish_launch("ex_dfx_kernel");
   if (rc != RA_OK) return rc;
-  ex_S_kernel<<<dim3(bxc, F, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, fx, gamma, gamma_stride, W, F, D, S);
-  rc = ra::finish_launch("ex_S_kernel");
-  if (rc != RA_OK) return rc;
-  ex_dfy_kernel<<<dim3((H + kExRows - 1) / kExRows, B), kT, 0, s>>>(xs, Cs, xs_bmod, canvas, S, H, W, F, D, accumulate,
-                                                                    d_fy);
+  const size_t ysm = gsm + (size_t)kExChunk * D * sizeof(float) + (size_t)2 * F * sizeof(int);
+  ex_dfy_kernel<<<dim3(F, B), kT, ysm, s>>>(xs, Cs, xs_bmod, canvas, d_patch, patch_cstride, chan_map, fx, gamma,
+                                            gamma_stride, box, H, W, F, D, accumulate, d_fy);
   rc = ra::finish_launch("ex_dfy_kernel");
   if (rc != RA_OK) return rc;
   ex_dgamma_kernel<<<B, kT, 0, s>>>(d_patch, x_patch, patch_cstride, D, F, gamma, gamma_stride, d_gamma);

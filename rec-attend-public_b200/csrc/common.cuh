@@ -95,6 +95,56 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- support bands of the Gaussian attention filters (csrc/gauss.cu build_filters_kernel) ----------------------
+// Filter entries whose exponent is below -kBandCut are stored as exact zeros, so tap t of an axis is non-zero only
+// inside [mu_t - R, mu_t + R], R = sqrt(2 var kBandCut) + 1.  Consumers recompute (supersets of) the bands from the
+// box record instead of reading them: no memory traffic, no dependence on a band buffer of another step.
+constexpr float kBandCut = 30.0f;
+
+// Superset of the union of the F taps' bands along one axis (taps are monotone in t); two extra pixels absorb the
+// fast-math error.  Empty: lo > hi.  NaN boxes keep the full range.
+__device__ __forceinline__ void band_union(const float *__restrict__ bo, int axis, int F, int L, int *lo_out,
+                                           int *hi_out) {
+  const float ctr = bo[RA_BOX_CTR_Y + axis];
+  const float size = bo[RA_BOX_SIZE_Y + axis];
+  const float var = __expf(bo[RA_BOX_LGVAR_Y + axis]);
+  const float step = (size + 1.0f) / (float)F;
+  const float half = (float)(F - 1) / 2.0f;
+  const float R = __fsqrt_rn(2.0f * var * kBandCut) * 1.0001f + 1.0f;
+  const float m0 = ctr - step * half, m1 = ctr + step * half;
+  float lo = floorf(fminf(m0, m1) - R) - 2.0f, hi = ceilf(fmaxf(m0, m1) + R) + 2.0f;
+  int ilo = 0, ihi = L - 1;
+  if (lo == lo && hi == hi) {
+    lo = fminf(fmaxf(lo, 0.f), (float)L);
+    hi = fmaxf(fminf(hi, (float)(L - 1)), -1.f);
+    ilo = (int)lo;
+    ihi = (int)hi;
+  }
+  *lo_out = ilo;
+  *hi_out = ihi;
+}
+
+// Superset (by two pixels) of the band of ONE tap.
+__device__ __forceinline__ void tap_band(const float *__restrict__ bo, int axis, int t, int F, int L, int *lo_out,
+                                         int *hi_out) {
+  const float ctr = bo[RA_BOX_CTR_Y + axis];
+  const float size = bo[RA_BOX_SIZE_Y + axis];
+  const float var = __expf(bo[RA_BOX_LGVAR_Y + axis]);
+  const float step = (size + 1.0f) / (float)F;
+  const float mu = ctr + step * ((float)t - (float)(F - 1) / 2.0f);
+  const float R = __fsqrt_rn(2.0f * var * kBandCut) * 1.0001f + 1.0f;
+  float lo = floorf(mu - R) - 2.0f, hi = ceilf(mu + R) + 2.0f;
+  int ilo = 0, ihi = L - 1;
+  if (lo == lo && hi == hi) {
+    lo = fminf(fmaxf(lo, 0.f), (float)L);
+    hi = fmaxf(fminf(hi, (float)(L - 1)), -1.f);
+    ilo = (int)lo;
+    ihi = (int)hi;
+  }
+  *lo_out = ilo;
+  *hi_out = ihi;
+}
+
 // streaming (read-once) loads: keep them out of L1
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
   return __ldcs(reinterpret_cast<const float4 *>(p));

@@ -460,7 +460,7 @@ def conf_loss_bwd(s_out, match, scale=1.0):
 
 
 # ----------------------------------------------------------------------------- backward of the attention write
-def paste_back_bwd(d_out, out, box, fy, fx, gamma_index, patch=None, d_fy=None, d_fx=None):
+def paste_back_bwd(d_out, out, box, fy, fx, gamma_index, patch=None, d_fy=None, d_fx=None, band=True):
   """Gradient of out = sigmoid(gamma * (Fy P Fx^T) - 5) (full_model.py:738-741, :810-814): d_out, out [B,H,W]
   (contiguous), box [B,RA_BOX_STRIDE], fy [B,F,H], fx [B,F,W], gamma_index = _lib.BOX_GAMMA_Y or BOX_GAMMA_BOX,
   patch [B,F,F] or None (= ones).  Passing d_fy / d_fx accumulates into them (the filters have several consumers).
@@ -477,12 +477,15 @@ def paste_back_bwd(d_out, out, box, fy, fx, gamma_index, patch=None, d_fy=None, 
   d_gamma = torch.empty(B, device=dev, dtype=torch.float32)
   ws = _ws(_lib.lib().ra_paste_back_bwd_workspace(B, H, W, F), dev)
   gamma = box.view(-1)[gamma_index:]
-  _lib.call('ra_paste_back_bwd_f32', _p(d_out), _p(out), H * W, _p(patch), _p(fy), _p(fx), _p(gamma), box.shape[1],
-            B, H, W, F, acc, _p(ws), _p(d_patch), _p(d_fy), _p(d_fx), _p(d_gamma), _stream())
+  # band=True: fy / fx were built from `box` by get_gaussian_filter (exact zeros outside the taps' support bands), so
+  # the kernels only walk the bands; band=False walks the full axes (filters of any origin)
+  _lib.call('ra_paste_back_bwd_ex_f32', _p(d_out), _p(out), H * W, max(B, 1), 0, _p(patch), _p(fy), _p(fx), _p(gamma),
+            box.shape[1], _p(box if band else None), B, H, W, F, acc, _p(ws), _p(d_patch), _p(d_fy), _p(d_fx),
+            _p(d_gamma), _stream())
   return d_patch, d_fy, d_fx, d_gamma
 
 
-def extract_patch_bwd(d_patch, x_patch, xs, canvas, chan_map, box, fy, fx, d_fy=None, d_fx=None):
+def extract_patch_bwd(d_patch, x_patch, xs, canvas, chan_map, box, fy, fx, d_fy=None, d_fx=None, band=True):
   """Gradient of the glimpse x_patch = gamma_attn * Fy^T X Fx (ops.extract_patch; full_model.py:788-789) w.r.t. the
   filters and the gain: d_patch, x_patch [B,F,F,cstride]; xs / canvas / chan_map as in the forward call.
   Passing d_fy / d_fx accumulates into them.  Returns (d_fy, d_fx, d_gamma [B])."""
@@ -499,9 +502,9 @@ def extract_patch_bwd(d_patch, x_patch, xs, canvas, chan_map, box, fy, fx, d_fy=
   d_gamma = torch.empty(B, device=dev, dtype=torch.float32)
   ws = _ws(_lib.lib().ra_gaussian_extract_bwd_workspace(B, W, F, D), dev)
   gamma = box.view(-1)[_lib.BOX_GAMMA_ATTN:]
-  _lib.call('ra_gaussian_extract_bwd_f32', _p(xs), Cs, _p(canvas), _p(chan_map), _p(fy), _p(fx), _p(gamma),
-            box.shape[1], _p(d_patch), _p(x_patch), d_patch.shape[3], B, H, W, F, acc, _p(ws), _p(d_fy), _p(d_fx),
-            _p(d_gamma), _stream())
+  _lib.call('ra_gaussian_extract_bwd_ex_f32', _p(xs), Cs, 0, _p(canvas), _p(chan_map), _p(fy), _p(fx), _p(gamma),
+            box.shape[1], _p(box if band else None), _p(d_patch), _p(x_patch), d_patch.shape[3], B, H, W, F, acc,
+            _p(ws), _p(d_fy), _p(d_fx), _p(d_gamma), _stream())
   return d_fy, d_fx, d_gamma
 
 

@@ -192,9 +192,10 @@ def _outer_sum(A, a_stride, n_in, D, d_stride, n_out, R, dW, db=None):
             ops._stream())
 
 
-def _paste_back_bwd(d_out, out, B, T, H, W, patch, fy, fx, gamma, d_fy=None, d_fx=None):
+def _paste_back_bwd(d_out, out, B, T, H, W, patch, fy, fx, gamma, box, d_fy=None, d_fx=None):
   """Step-batched paste-back backward: d_out / out [B,T,H,W] read in [T,B] order; patch [N,F,F] or None;
-  fy [N,F,H], fx [N,F,W]; gamma = view starting at the gain slot of the [N,RA_BOX_STRIDE] box records."""
+  fy [N,F,H], fx [N,F,W]; gamma = view starting at the gain slot of the [N,RA_BOX_STRIDE] box records `box` the
+  filters were built from (the kernels only walk the taps' support bands)."""
   N = T * B
   F = fy.shape[1]
   dev = fy.device
@@ -205,8 +206,8 @@ def _paste_back_bwd(d_out, out, B, T, H, W, patch, fy, fx, gamma, d_fy=None, d_f
   d_gamma = _empty((N,), dev)
   ws = ops._ws(_lib.lib().ra_paste_back_bwd_workspace(N, H, W, F), dev)
   _lib.call('ra_paste_back_bwd_ex_f32', ops._p(d_out), ops._p(out), T * H * W, B, H * W, ops._p(patch), ops._p(fy),
-            ops._p(fx), ops._p(gamma), _lib.BOX_STRIDE, N, H, W, F, acc, ops._p(ws), ops._p(d_patch), ops._p(d_fy),
-            ops._p(d_fx), ops._p(d_gamma), ops._stream())
+            ops._p(fx), ops._p(gamma), _lib.BOX_STRIDE, ops._p(box), N, H, W, F, acc, ops._p(ws), ops._p(d_patch),
+            ops._p(d_fy), ops._p(d_fx), ops._p(d_gamma), ops._stream())
   return d_patch, d_fy, d_fx, d_gamma
 
 
@@ -329,15 +330,15 @@ def full_model_backward(m, gs, bufs, B, out, knob):
   box_head = tp['box_pre'].view(N, _lib.BOX_STRIDE) if knob is not None else box
   gam = lambda b_, slot: b_.view(-1)[slot:]
   d_P, d_fy, d_fx, dg_y = _paste_back_bwd(d_y, bufs['y_out'], B, T, H, W, bufs['y_patch_all'].view(N, F, F), fy, fx,
-                                          gam(box, _lib.BOX_GAMMA_Y))
+                                          gam(box, _lib.BOX_GAMMA_Y), box)
   d_fy0 = d_fx0 = None
   if knob is None:
     _, d_fy, d_fx, dg_box = _paste_back_bwd(d_ab, bufs['attn_box'], B, T, H, W, None, fy, fx,
-                                            gam(box, _lib.BOX_GAMMA_BOX), d_fy=d_fy, d_fx=d_fx)
+                                            gam(box, _lib.BOX_GAMMA_BOX), box, d_fy=d_fy, d_fx=d_fx)
   elif not coord:
     fy0, fx0 = tp['fy0'].view(N, F, H), tp['fx0'].view(N, F, W)
     _, d_fy0, d_fx0, dg_box = _paste_back_bwd(d_ab, bufs['attn_box'], B, T, H, W, None, fy0, fx0,
-                                              gam(box_head, _lib.BOX_GAMMA_BOX))
+                                              gam(box_head, _lib.BOX_GAMMA_BOX), box_head)
   else:
     dg_box = torch.zeros(N, device=dev)
   # ---- deconv mask head, last layer first
@@ -388,8 +389,9 @@ def full_model_backward(m, gs, bufs, B, out, knob):
   dg_attn = _empty((N,), dev)
   ws = ops._ws(_lib.lib().ra_gaussian_extract_bwd_workspace(N, W, F, m.D), dev)
   _lib.call('ra_gaussian_extract_bwd_ex_f32', ops._p(bufs['xs']), m.Cs, B, ops._p(tp['canvas']), ops._p(m.chan_map),
-            ops._p(fy), ops._p(fx), ops._p(gam(box, _lib.BOX_GAMMA_ATTN)), _lib.BOX_STRIDE, ops._p(d_xpatch),
-            ops._p(x_patch), Dp, N, H, W, F, 1, ops._p(ws), ops._p(d_fy), ops._p(d_fx), ops._p(dg_attn), ops._stream())
+            ops._p(fy), ops._p(fx), ops._p(gam(box, _lib.BOX_GAMMA_ATTN)), _lib.BOX_STRIDE, ops._p(box),
+            ops._p(d_xpatch), ops._p(x_patch), Dp, N, H, W, F, 1, ops._p(ws), ops._p(d_fy), ops._p(d_fx),
+            ops._p(dg_attn), ops._stream())
   d_box = ops.gaussian_filters_bwd(box, fy, fx, d_fy, d_fx)
   if knob is not None:
     d_pre = None if coord else ops.gaussian_filters_bwd(box_head, fy0, fx0, d_fy0, d_fx0)
@@ -425,7 +427,7 @@ def box_model_backward(m, gs, bufs, B, out):
   else:
     d_ab = ops.iou_loss_bwd(bufs['attn_box'], match_box, b_rect=out['_gt_rect'])
     _, d_fy, d_fx, dg_box = _paste_back_bwd(d_ab, bufs['attn_box'], B, T, H, W, None, fy, fx,
-                                            box.view(-1)[_lib.BOX_GAMMA_BOX:])
+                                            box.view(-1)[_lib.BOX_GAMMA_BOX:], box)
     d_box = ops.gaussian_filters_bwd(box, fy, fx, d_fy, d_fx)
   Hd = m.Hd
   dpre, d_h = _empty((N,), dev), _empty((N, Hd), dev)
