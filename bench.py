@@ -197,6 +197,12 @@ class OpTimer(object):
         # args: x1,C1,x2,C2,wpack,scale,shift,B,Hin,Win,Cout,up,pool,relu,y,stream
         key = '{}:conv3x3_umma[{}x{} {}+{}->{} up{} pool{}]'.format(tag, args[8], args[9], args[1], args[3], args[10],
                                                                   args[11], args[12])
+      if name == 'ra_conv3x3_bwd_weight_ex_f32':
+        # args: x1,C1,x1_bmod,x2,C2,d_out,B,Hin,Win,Cout,up,ws,dw,db,stream
+        key = 'wgrad[N{} {}x{} {}+{}->{} up{}]'.format(args[6], args[7], args[8], args[1], args[4], args[9], args[10])
+      if name == 'ra_bn_train_block_bwd_grouped_f32':
+        # args: raw,dy,gamma,beta,mean,var,G,B,H,W,C,pool,...
+        key = 'bn_bwd[G{} B{} {}x{}x{} pool{}]'.format(args[6], args[7], args[8], args[9], args[10], args[11])
       d = agg.setdefault(key, {'entry': name, 'tag': tag, 'ms': 0.0, 'n': 0})
       d['ms'] += e0.elapsed_time(e1)
       d['n'] += 1

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const float *__restric
 // dW[t][ci][co] = sum over output pixels (b, Y, X) of Z[b, Y+ky-up, X+kx-up, ci] * G[b, Y, X, co], Z = the zero-padded
 // input, zero-inserted for up = 2 (Z[2y,2x] = x[y,x]; the tap offset is -up, the forward kernel's convention), t = ky*3+kx.
 //
-// A CTA walks spatial tiles of kWgTH x kWgTW output pixels (persistent over tiles, grid.x), for one block of CI_B x CO_B
+// A CTA walks spatial tiles of TH x kWgTW output pixels (persistent over tiles, grid.x), for one block of CI_B x CO_B
 // channels (grid.y).  Per tile it stages the (TH+2) x (TW+2) input window [slot][CI_B] and the gradient tile
 // [pixel][CO_B] in shared memory; every thread keeps an RI x RJ register tile for ALL NINE taps (9*RI*RJ accumulators):
 // per pixel one vector load of G and nine of the shifted inputs feed 9*RI*RJ FMAs.  Lanes of a warp differ in the
@@ -162,24 +162,33 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_kernel(const float *__restric
 // narrower than 256 / ((CI_B/RI) * (CO_B/RJ)) threads are replicated over PG pixel groups (each takes every PG-th pixel)
 // and summed through shared memory at the end.  Partials per CTA are added in a fixed order by the finalize kernel:
 // bit-identical from run to run.
-constexpr int kWgTH = 4, kWgTW = 64, kWgTWP = kWgTW + 2;
-constexpr int kWgSlots = (kWgTH + 2) * kWgTWP, kWgPix = kWgTH * kWgTW;
+constexpr int kWgTWMax = 64;
 
 struct WgParams {
   const float *x1, *x2, *g;
   int C1, C2, x1_bmod, N, Hin, Win, Cout, up;
   int CI_B, CO_B, TI, TJ, PG;  // channel block, threads along ci / co, pixel groups (TI*TJ*PG == 256)
+  int TH, TW;                  // tile rows x columns (TW = 64 / 32 / 16 by the map width; TH * TW = 256 or 128 pixels)
+  int vec_x, vec_g;            // 16-byte cp.async staging of the input window / the gradient tile (channel counts % 4
+                               // == 0, aligned pointers); both stages are double buffered either way
   int tiles_x, tiles_y, n_tiles, n_ci_blk;
   float *partial;     // [grid.x][9][Cin][Cout]
   float *db_partial;  // [grid.x][Cout] or nullptr
 };
 
+__device__ __forceinline__ void cp_async16(float *dst_smem, const float *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int bytes = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
 template <int RI, int RJ>
 __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
   extern __shared__ __align__(16) float wg_smem[];
   const int CI_B = p.CI_B, CO_B = p.CO_B;
-  float *xs = wg_smem;                          // [kWgSlots][CI_B]
-  float *gs = wg_smem + (size_t)kWgSlots * CI_B;  // [kWgPix][CO_B]
+  const int kWgTW = p.TW, kWgTWP = p.TW + 2;  // (runtime; the names are kept from the fixed-tile version)
+  const int n_slots = (p.TH + 2) * kWgTWP, n_pix = p.TH * kWgTW;
+  const int stage_floats = n_slots * CI_B + n_pix * CO_B;  // [slots][CI_B] then [pixels][CO_B]
   const int Cin = p.C1 + p.C2;
   const int Ho = p.Hin * p.up, Wo = p.Win * p.up;
   const int ci_blk = blockIdx.y % p.n_ci_blk, co_blk = blockIdx.y / p.n_ci_blk;
@@ -198,52 +207,88 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
   for (int j = 0; j < RJ; ++j) dbv[j] = 0.f;
   const bool do_db = (ci_blk == 0 && p.db_partial != nullptr && ti == 0);
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  // Stage one tile: input window, slot (r, c) <-> zero-inserted pixel (y0 - up + r, x0 - up + c), and gradient tile.
+  auto stage = [&](int tile, float *xs, float *gs) {
     int t = tile;
     const int tx = t % p.tiles_x;
     t /= p.tiles_x;
     const int ty = t % p.tiles_y;
     const int b = t / p.tiles_y;
-    const int y0 = ty * kWgTH, x0 = tx * kWgTW;
-    __syncthreads();  // the previous tile has been consumed
-    // ---- input window: slot (r, c) <-> zero-inserted pixel (y0 - up + r, x0 - up + c)
-    for (int idx = threadIdx.x; idx < kWgSlots * CI_B; idx += kT) {
-      const int slot = idx / CI_B, c = idx - slot * CI_B;
-      const int r = slot / kWgTWP, col = slot - r * kWgTWP;
-      const int zy = y0 - p.up + r, zx = x0 - p.up + col;
-      float v = 0.f;
-      if (c < nci && zy >= 0 && zy < Ho && zx >= 0 && zx < Wo && (p.up == 1 || (((zy | zx) & 1) == 0))) {
+    const int y0 = ty * p.TH, x0 = tx * kWgTW;
+    const int b1 = p.x1_bmod > 0 ? b % p.x1_bmod : b;
+    if (p.vec_x) {
+      const int c4n = CI_B >> 2;
+      for (int u = threadIdx.x; u < n_slots * c4n; u += kT) {
+        const int slot = u / c4n, c = (u - slot * c4n) << 2;
+        const int r = slot / kWgTWP, col = slot - r * kWgTWP;
+        const int zy = y0 - p.up + r, zx = x0 - p.up + col;
+        bool ok = c < nci && zy >= 0 && zy < Ho && zx >= 0 && zx < Wo && (p.up == 1 || (((zy | zx) & 1) == 0));
         const int iy = p.up == 1 ? zy : zy >> 1, ix = p.up == 1 ? zx : zx >> 1;
         const int ci = ci0 + c;
-        if (ci < p.C1) {
-          const size_t src = ((size_t)(p.x1_bmod > 0 ? b % p.x1_bmod : b) * p.Hin + iy) * p.Win + ix;
-          v = __ldg(p.x1 + src * p.C1 + ci);
-        } else {
-          const size_t src = ((size_t)b * p.Hin + iy) * p.Win + ix;
-          v = __ldg(p.x2 + src * p.C2 + (ci - p.C1));
+        const float *src = p.x1;
+        if (ok) {
+          if (ci < p.C1)
+            src = p.x1 + (((size_t)b1 * p.Hin + iy) * p.Win + ix) * p.C1 + ci;
+          else
+            src = p.x2 + (((size_t)b * p.Hin + iy) * p.Win + ix) * p.C2 + (ci - p.C1);
         }
+        cp_async16(xs + slot * CI_B + c, src, ok);
       }
-      xs[idx] = v;
+    } else {
+      for (int idx = threadIdx.x; idx < n_slots * CI_B; idx += kT) {
+        const int slot = idx / CI_B, c = idx - slot * CI_B;
+        const int r = slot / kWgTWP, col = slot - r * kWgTWP;
+        const int zy = y0 - p.up + r, zx = x0 - p.up + col;
+        float v = 0.f;
+        if (c < nci && zy >= 0 && zy < Ho && zx >= 0 && zx < Wo && (p.up == 1 || (((zy | zx) & 1) == 0))) {
+          const int iy = p.up == 1 ? zy : zy >> 1, ix = p.up == 1 ? zx : zx >> 1;
+          const int ci = ci0 + c;
+          if (ci < p.C1)
+            v = __ldg(p.x1 + (((size_t)b1 * p.Hin + iy) * p.Win + ix) * p.C1 + ci);
+          else
+            v = __ldg(p.x2 + (((size_t)b * p.Hin + iy) * p.Win + ix) * p.C2 + (ci - p.C1));
+        }
+        xs[idx] = v;
+      }
     }
-    // ---- gradient tile
-    for (int idx = threadIdx.x; idx < kWgPix * CO_B; idx += kT) {
-      const int pix = idx / CO_B, c = idx - pix * CO_B;
-      const int py = pix / kWgTW, px = pix - py * kWgTW;
-      const int Y = y0 + py, X = x0 + px;
-      float v = 0.f;
-      if (c < nco && Y < Ho && X < Wo) v = __ldg(p.g + (((size_t)b * Ho + Y) * Wo + X) * p.Cout + co0 + c);
-      gs[idx] = v;
+    if (p.vec_g) {
+      const int o4n = CO_B >> 2;
+      for (int u = threadIdx.x; u < n_pix * o4n; u += kT) {
+        const int pix = u / o4n, c = (u - pix * o4n) << 2;
+        const int py = pix / kWgTW, px = pix - py * kWgTW;
+        const int Y = y0 + py, X = x0 + px;
+        const bool ok = c < nco && Y < Ho && X < Wo;
+        const float *src = ok ? p.g + (((size_t)b * Ho + Y) * Wo + X) * p.Cout + co0 + c : p.g;
+        cp_async16(gs + pix * CO_B + c, src, ok);
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < n_pix * CO_B; idx += kT) {
+        const int pix = idx / CO_B, c = idx - pix * CO_B;
+        const int py = pix / kWgTW, px = pix - py * kWgTW;
+        const int Y = y0 + py, X = x0 + px;
+        float v = 0.f;
+        if (c < nco && Y < Ho && X < Wo) v = __ldg(p.g + (((size_t)b * Ho + Y) * Wo + X) * p.Cout + co0 + c);
+        gs[idx] = v;
+      }
     }
-    __syncthreads();
+  };
+
+  auto compute = [&](const float *xs, const float *gs) {
     const float *xb = xs + ti * RI;
     const float *gb = gs + tj * RJ;
-    for (int pix = pg; pix < kWgPix; pix += p.PG) {
+    for (int pix = pg; pix < n_pix; pix += p.PG) {
       const int py = pix / kWgTW, px = pix - py * kWgTW;
       float gv[RJ];
       if constexpr (RJ == 2) {  // 8-byte aligned: CO_B and tj * RJ are even
         const float2 t2 = *reinterpret_cast<const float2 *>(gb + pix * CO_B);
         gv[0] = t2.x;
         gv[1] = t2.y;
+      } else if constexpr (RJ == 4) {
+        const float4 t4 = *reinterpret_cast<const float4 *>(gb + pix * CO_B);
+        gv[0] = t4.x;
+        gv[1] = t4.y;
+        gv[2] = t4.z;
+        gv[3] = t4.w;
       } else {
 #pragma unroll
         for (int j = 0; j < RJ; ++j) gv[j] = gb[pix * CO_B + j];
@@ -272,6 +317,27 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
             for (int j = 0; j < RJ; ++j) acc[ky * 3 + kx][i][j] = fmaf(xv[i], gv[j], acc[ky * 3 + kx][i][j]);
         }
     }
+  };
+
+  {
+    // two shared-memory stages: the copies of tile k+1 (cp.async where the layout allows it) are issued before tile k
+    // is multiplied
+    int buf = 0;
+    int tile = blockIdx.x;
+    if (tile < p.n_tiles) stage(tile, wg_smem, wg_smem + n_slots * CI_B);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
+      const int nxt = tile + gridDim.x;
+      float *nb = wg_smem + (buf ^ 1) * stage_floats;
+      if (nxt < p.n_tiles) stage(nxt, nb, nb + n_slots * CI_B);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the newest group has landed
+      __syncthreads();
+      const float *cb = wg_smem + buf * stage_floats;
+      compute(cb, cb + n_slots * CI_B);
+      __syncthreads();  // this stage may be overwritten by the copies issued in the next iteration
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   // ---- sum the pixel groups through shared memory (fixed order), write this CTA's partial
   __syncthreads();
@@ -307,30 +373,36 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
 
 // channel blocking of the weight-gradient kernel for a layer shape
 struct WgPlan {
-  int RI, CI_B, CO_B, TI, TJ, PG, n_ci_blk, n_co_blk, ctas;
+  int RI, RJ, CI_B, CO_B, TI, TJ, PG, n_ci_blk, n_co_blk, ctas, TH, TW;
   size_t smem;
 };
 
 WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
   WgPlan w;
-  if (Cin == 1) {  // the canvas channel of the first controller layer: 1 x 16 threads, 16 pixel groups
+  if (Cin == 1) {  // the canvas channel of the first controller layer: 1 x 4 threads (4 channels each), 64 pixel groups
     w.RI = 1;
+    w.RJ = 4;
     w.CI_B = 1;
     w.CO_B = 16;
   } else {
-    w.RI = 2;
+    w.RI = w.RJ = 2;
     w.CI_B = Cin <= 16 ? 16 : 32;
     w.CO_B = Cout <= 16 ? 16 : 32;
   }
   w.TI = w.CI_B / w.RI;
-  w.TJ = w.CO_B / w.RI;
+  w.TJ = w.CO_B / w.RJ;
   w.PG = kT / (w.TI * w.TJ);
   w.n_ci_blk = (Cin + w.CI_B - 1) / w.CI_B;
   w.n_co_blk = (Cout + w.CO_B - 1) / w.CO_B;
-  const size_t stage = ((size_t)kWgSlots * w.CI_B + (size_t)kWgPix * w.CO_B) * sizeof(float);
+  // tile: as wide as the map allows (64 / 32 / 16 columns), 256 pixels - 128 for the 32-wide channel blocks, whose two
+  // stages must fit twice per SM
+  w.TW = Wo > 32 ? 64 : (Wo > 16 ? 32 : 16);
+  const int pix = (w.CI_B > 16 || w.CO_B > 16) ? 128 : 256;
+  w.TH = pix / w.TW;
+  const size_t stage = ((size_t)(w.TH + 2) * (w.TW + 2) * w.CI_B + (size_t)w.TH * w.TW * w.CO_B) * sizeof(float);
   const size_t red = ((size_t)w.PG * 9 * w.CI_B * w.CO_B + (size_t)w.PG * w.CO_B) * sizeof(float);
-  w.smem = stage > red ? stage : red;
-  const size_t n_tiles = (size_t)N * ((Ho + kWgTH - 1) / kWgTH) * ((Wo + kWgTW - 1) / kWgTW);
+  w.smem = 2 * stage > red ? 2 * stage : red;
+  const size_t n_tiles = (size_t)N * ((Ho + w.TH - 1) / w.TH) * ((Wo + w.TW - 1) / w.TW);
   size_t cap = (size_t)ra::kNumSMs * 2 / ((size_t)w.n_ci_blk * w.n_co_blk);
   if (cap < 16) cap = 16;
   w.ctas = (int)(n_tiles < cap ? (n_tiles < 1 ? 1 : n_tiles) : cap);
@@ -470,23 +542,28 @@ extern "C" int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod
   p.x1 = x1; p.x2 = x2; p.g = d_out;
   p.C1 = C1; p.C2 = C2; p.x1_bmod = x1_bmod; p.N = B; p.Hin = Hin; p.Win = Win; p.Cout = Cout; p.up = upsample;
   p.CI_B = w.CI_B; p.CO_B = w.CO_B; p.TI = w.TI; p.TJ = w.TJ; p.PG = w.PG;
-  p.tiles_x = (Wo + kWgTW - 1) / kWgTW;
-  p.tiles_y = (Ho + kWgTH - 1) / kWgTH;
+  p.tiles_x = (Wo + w.TW - 1) / w.TW;
+  p.TW = w.TW;
+  p.TH = w.TH;
+  p.tiles_y = (Ho + w.TH - 1) / w.TH;
+  p.vec_x = ((C1 & 3) == 0 && (C2 & 3) == 0 && (w.CI_B & 3) == 0 &&
+             ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15) == 0) ? 1 : 0;
+  p.vec_g = ((Cout & 3) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) ? 1 : 0;
   p.n_tiles = B * p.tiles_x * p.tiles_y;
   p.n_ci_blk = w.n_ci_blk;
   p.partial = partial;
   p.db_partial = db ? db_partial : nullptr;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv_bwd_weight_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(conv_bwd_weight_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     attr_done = true;
   }
   const dim3 grid(chunks, w.n_ci_blk * w.n_co_blk);
   if (w.RI == 2)
     conv_bwd_weight_kernel<2, 2><<<grid, kT, w.smem, s>>>(p);
   else
-    conv_bwd_weight_kernel<1, 1><<<grid, kT, w.smem, s>>>(p);
+    conv_bwd_weight_kernel<1, 4><<<grid, kT, w.smem, s>>>(p);
   int rc = ra::finish_launch("conv_bwd_weight_kernel");
   if (rc != RA_OK) return rc;
   const size_t n = (size_t)9 * Cin * Cout;
