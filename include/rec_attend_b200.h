@@ -536,6 +536,20 @@ int ra_adam_step_f32(float *param, const float *grad, float *m, float *v, const 
                      void *stream);
 
 /* --------------------------------------------------------------------------------------
+ * Pairwise soft + hard IoU on the tcgen05 tensor cores, one pass over the masks (csrc/iou_umma.cu) —
+ * modellib.f_iou(a, g, pairwise=True) (modellib.py:104-155) for the matching (full_model.py:983) together with
+ * f_iou / f_dice of the thresholded masks a > hard_thr (full_model.py:1063-1081, modellib.py:71-101).
+ * a, g [B,T,H,W] contiguous (g = ground-truth masks), N = M = T <= 127, H*W % 32 == 0, 16-byte aligned;
+ * iou_soft / iou_hard / dice_hard [B,T,T] (each may be NULL).  K-major GEMM over the pixels: TMA (SWIZZLE_128B) ->
+ * hi / lo tf32 split of a + thresholded copy in shared memory -> tcgen05.mma kind::tf32, accumulators in TMEM, row /
+ * column sums through a row of ones; partial block diagonals per pixel slice summed in a fixed order.
+ * ws: ra_pairwise_iou_umma_workspace() bytes (0: shape not supported - use ra_pairwise_iou_f32).
+ * -------------------------------------------------------------------------------------- */
+size_t ra_pairwise_iou_umma_workspace(int B, int T, int H, int W);
+int ra_pairwise_iou_umma_f32(const float *a, const float *g, int B, int T, int H, int W, float hard_thr, void *ws,
+                             float *iou_soft, float *iou_hard, float *dice_hard, void *stream);
+
+/* --------------------------------------------------------------------------------------
  * Training-step glue (csrc/train.cu) — what sits between the per-block gradients and the optimiser in
  * `sess.run([loss, train_step])` (runner.py:98-105; full_model.py:1039-1057, box_model.py:635-652).
  *  ra_param_gather_f32: flat trainable bucket -> every device-side weight image in one launch.  `codes[i]` describes

@@ -89,6 +89,7 @@ _SIGNATURES = {
     'ra_score_bwd_f32': [_P, _P, _I, _I, _P, _I, _I, _P, _P, _P, _I, _P],
     'ra_knob_box_bwd_f32': [_P, _P, _P, _I, _I, _P, _P],
     'ra_iou_box_coord_bwd_f32': [_P, _P, _P, _P, _I, _I, _F, _P, _P],
+    'ra_pairwise_iou_umma_f32': [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     'ra_wt_cov_f32': [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     'ra_loss_select_f32': [_P, _P, _P, _F, _F, _P],
     'ra_u8_to_f32': [_P, _Z, _P, _P],
@@ -102,7 +103,8 @@ EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last
                                          'ra_bn_train_block_bwd_workspace', 'ra_conv3x3_bwd_weight_workspace',
                                          'ra_iou_loss_bwd_workspace', 'ra_paste_back_bwd_workspace',
                                          'ra_gaussian_extract_bwd_workspace', 'ra_controller_tape_floats',
-                                         'ra_bn_train_block_bwd_grouped_workspace', 'ra_weight_decay_workspace'])
+                                         'ra_bn_train_block_bwd_grouped_workspace', 'ra_weight_decay_workspace',
+                                         'ra_pairwise_iou_umma_workspace'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -148,6 +150,8 @@ def lib():
     l.ra_gaussian_extract_bwd_workspace.restype = _Z
     l.ra_bn_train_block_bwd_grouped_workspace.argtypes = [_I, _I, _I, _I, _I, _I]
     l.ra_bn_train_block_bwd_grouped_workspace.restype = _Z
+    l.ra_pairwise_iou_umma_workspace.argtypes = [_I, _I, _I, _I]
+    l.ra_pairwise_iou_umma_workspace.restype = _Z
     l.ra_weight_decay_workspace.argtypes = []
     l.ra_weight_decay_workspace.restype = _Z
     l.ra_controller_tape_floats.argtypes = [_I, _I, _I, _I]

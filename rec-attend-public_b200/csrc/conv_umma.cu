@@ -331,6 +331,9 @@ __device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, b
     if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64();                          \
   } while (0)
 
+// RS: the row-stacked-taps variant (opt-in, see make_plan) is a separate instantiation, so that the default kernel
+// carries none of its registers / shared memory.
+template <bool RS>
 __global__ void __launch_bounds__(kThreads, 1)
     conv3x3_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant__ CUtensorMap tm1,
                         const __grid_constant__ CUtensorMap tm2) {
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ __align__(128) unsigned char smem_dyn[];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sc_s[256], sh_s[256];  // folded-BN scale / shift of this CTA's channels
-  __shared__ float xw_s[2 * 4 * 48];  // rowstack epilogue: rows the next warp hands to lanes 30 / 31 (two buffers)
+  __shared__ float xw_s[RS ? 2 * 4 * 48 : 1];  // rowstack epilogue: rows the next warp hands to lanes 30 / 31
   __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_raw[kMaxStages], bar_tfull[2],
       bar_tempty[2];
   // TMA destinations want 128-byte alignment: round the dynamic window up (the launcher adds the slack)
@@ -650,19 +653,19 @@ __global__ void __launch_bounds__(kThreads, 1)
     {
       const bool leader = elect_one();
       const int mw = warp - kMmaWarp0;
-      const int cols_mt = p.rowstack ? 6 * p.NPc : (p.merged ? 2 * p.NPc : p.NPc);
+      const int cols_mt = RS ? 6 * p.NPc : (p.merged ? 2 * p.NPc : p.NPc);
       IssueCtx c;
       // rowstack: idesc_n = the A_lo instruction (3 NPc wide), idesc_2n = the A_hi instruction (6 NPc wide)
-      const uint32_t n_lo = p.rowstack ? 3u * (uint32_t)p.NPc : (uint32_t)p.NPc;
-      const uint32_t n_hi = p.rowstack ? 6u * (uint32_t)p.NPc : 2u * (uint32_t)p.NPc;
+      const uint32_t n_lo = RS ? 3u * (uint32_t)p.NPc : (uint32_t)p.NPc;
+      const uint32_t n_hi = RS ? 6u * (uint32_t)p.NPc : 2u * (uint32_t)p.NPc;
       c.idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((n_lo >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       c.idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((n_hi >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       c.idesc_lo = p.four_term ? c.idesc_2n : c.idesc_n;
       // column offset of the A_lo B_hi correction inside an m-tile's accumulator (0: same half as the main sum)
-      c.lo_col = p.rowstack ? 3u * (uint32_t)p.NPc
+      c.lo_col = RS ? 3u * (uint32_t)p.NPc
                             : ((p.merged && !p.four_term && getenv_split_corr(p)) ? (uint32_t)p.NPc : 0u);
       // bytes between channel planes of the filter image
-      const uint32_t w_plane = (uint32_t)((p.rowstack ? 6 : 2) * p.NPc) * 16u;
+      const uint32_t w_plane = (uint32_t)((RS ? 6 : 2) * p.NPc) * 16u;
       c.TWP = (uint32_t)p.TWP;
       c.a_k8 = 2u * (plane_bytes >> 4);                 // A start-address step of one k8 (two channel planes)
       c.b_k8 = 2u * (w_plane >> 4);                     // same for the filter image
@@ -702,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           c.b = make_desc(w_addr, w_plane, 128);
           c.init_steps = ch == 0 ? (uint32_t)p.ksplit : 0u;  // the first MMA into each accumulator overwrites
           if (has0 && leader) {
-            if (p.rowstack) {
+            if constexpr (RS) {
               if (k8n == 1) {
                 if (has1) issue_chunk_rs<1, true>(c); else issue_chunk_rs<1, false>(c);
               } else if (k8n == 2) {
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // =============================== epilogue (warps 0-3) ===============================
-    const int cols_mt = p.rowstack ? 6 * p.NPc : (p.merged ? 2 * p.NPc : p.NPc);
+    const int cols_mt = RS ? 6 * p.NPc : (p.merged ? 2 * p.NPc : p.NPc);
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;  // warp w may touch TMEM lanes [32w, 32w+32)
     int xw_par = 0;  // rowstack: parity of the cross-warp exchange buffer
     const int slots_out = p.TH * p.TWP;
@@ -746,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // the loads of one (hi half, lo half) pair are in flight together.  Then BN scale/shift (+ ReLU).
     auto load16 = [&](uint32_t acc, int mt, int cb, float *v) {
       uint32_t r0[16], r1[16];
-      if (p.rowstack) {
+      if constexpr (RS) {
         // g[j] = D'[lane, kx block, channel cb + j] (hi half + lo half + K-split partials); the output of this
         // lane's slot is g(kx=0)[lane] + g(kx=1)[lane + 1] + g(kx=2)[lane + 2].  Lanes 30 / 31 take the rows of the
         // next warp from shared memory (its lanes 0 / 1 publish them; double-buffered, one barrier per call).
@@ -1318,7 +1321,8 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   p.dbg = g_conv_dbg;
   // ---- TMA feed: needs channel counts that are multiples of 4 (16-byte global strides) and boxes <= 256
   const bool no_tma = getenv("RA_CONV_NO_TMA") != nullptr;  // diagnostics: plain-load producers everywhere
-  constexpr size_t kSmemMax = 222 * 1024;  // + ~3.8 KB static shared memory <= 227 KB
+  // + static shared memory (2.3 KB; 3.8 KB in the rowstack variant) <= 227 KB
+  const size_t kSmemMax = (size_t)(pl.rowstack ? 222 : 224) * 1024;
   p.tma = 0;
   p.RW = upsample == 2 ? p.TW / 2 + 1 : p.TWP;
   p.RH = upsample == 2 ? p.TH / 2 + 2 : p.TH + 2;
@@ -1358,7 +1362,9 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+        cudaFuncSetAttribute(conv3x3_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
     if (e != cudaSuccess) {
       ra::set_last_error("cudaFuncSetAttribute(conv3x3_umma_kernel)", e);
       return RA_ERR_CUDA;
@@ -1366,7 +1372,7 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
     // diagnostics: pin the SM shared-memory carve-out to its maximum for every launch of this kernel, so that
     // consecutive layers with different dynamic sizes never trigger a carve-out reconfiguration
     if (getenv("RA_CONV_CARVEOUT") != nullptr)
-      (void)cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+      (void)cudaFuncSetAttribute(conv3x3_umma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
@@ -1389,13 +1395,17 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel, p, tm1, tm2);
+    cudaError_t e = p.rowstack ? cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<true>, p, tm1, tm2)
+                               : cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<false>, p, tm1, tm2);
     if (e != cudaSuccess) {
       ra::set_last_error("cudaLaunchKernelEx(conv3x3_umma_kernel)", e);
       return RA_ERR_CUDA;
     }
   } else {
-    conv3x3_umma_kernel<<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
+    if (p.rowstack)
+      conv3x3_umma_kernel<true><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
+    else
+      conv3x3_umma_kernel<false><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
   }
   return ra::finish_launch("conv3x3_umma_kernel");
 }

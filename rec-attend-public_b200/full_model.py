@@ -742,24 +742,34 @@ class FullModel(_ModelBase):
     _lib.TAG = 'loss'
     cur = torch.cuda.current_stream()
     (tl, br, box_gt, rect, area), gt_side = gt
-    # the hard-IoU statistics (full_model.py:1063-1081) do not feed the matching: a parallel branch
-    side = self._side_stream(bufs, 1)  # the chains have joined: their streams are free again
-    if side is None:
-      iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
-    else:
-      with torch.cuda.stream(side):
+    B, T = s_gt.shape
+    # both matchings (boxes, masks) in ONE launch of 2B warps: they are independent and latency-bound
+    iou_both = torch.empty((2 * B, T, T), device=s_gt.device, dtype=torch.float32)
+    # soft IoU (matching) + hard IoU / DICE (statistics, full_model.py:1063-1081) in one pass over y_out and y_gt on
+    # the tensor cores; shapes outside that kernel's range take the CUDA-core kernel twice (the hard statistics do
+    # not feed the matching: a parallel branch)
+    side = None
+    fused = None
+    if not os.environ.get('RA_IOU_NO_UMMA'):
+      fused = ops.f_iou_soft_hard(bufs['y_out'], y_gt, hard_threshold=0.5, out_soft=iou_both[B:])
+    if fused is None:
+      side = self._side_stream(bufs, 1)  # the chains have joined: their streams are free again
+      if side is None:
         iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
+      else:
+        with torch.cuda.stream(side):
+          iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
     if gt_side is not None:
       cur.wait_stream(gt_side)
-    # both matchings (boxes, masks) in ONE launch of 2B warps: they are independent and latency-bound
-    B, T = s_gt.shape
-    iou_both = torch.empty((2 * B, T, T), device=s_gt.device, dtype=torch.float32)
     if iou_box_steps is None:
       iou_box = ops.f_iou(bufs['attn_box'], None, b_rect=rect, out=iou_both[:B])
     else:  # use_knob: the per-step IoUs of the decode loop (full_model.py:926-929)
       iou_both[:B].copy_(iou_box_steps)
       iou_box = iou_both[:B]
-    iou_soft = ops.f_iou(bufs['y_out'], y_gt, out=iou_both[B:])
+    if fused is None:
+      iou_soft = ops.f_iou(bufs['y_out'], y_gt, out=iou_both[B:])
+    else:
+      iou_soft, iou_hard, dice = fused
     match_both = ops.f_segm_match(iou_both, torch.cat([s_gt, s_gt], 0))
     match_box, match = match_both[:B], match_both[B:]
     if side is not None:

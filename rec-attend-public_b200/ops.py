@@ -278,6 +278,29 @@ def f_iou(a, b=None, pairwise=True, b_rect=None, hard_threshold=0.0, want_dice=F
   return iou
 
 
+def f_iou_soft_hard(a, b, hard_threshold=0.5, out_soft=None):
+  """modellib.f_iou(a, b, pairwise=True) (modellib.py:138-153) of the soft masks AND f_iou / f_dice of the thresholded
+  masks a > hard_threshold (full_model.py:1063-1081) in ONE pass over a and b, on the tensor cores
+  (ra_pairwise_iou_umma_f32).  a, b [B,T,H,W].  Returns (iou_soft, iou_hard, dice_hard) [B,T,T], or None when the
+  shape is outside the kernel's range (T > 127, H*W % 32 != 0): the caller falls back to f_iou."""
+  _chk(a, b)
+  B, T, H, W = a.shape
+  if tuple(b.shape) != (B, T, H, W):
+    return None
+  n_ws = _lib.lib().ra_pairwise_iou_umma_workspace(B, T, H, W)
+  if n_ws == 0:
+    return None
+  dev = a.device
+  ws = torch.empty((n_ws // 4,), device=dev, dtype=torch.float32)
+  out = [torch.empty((B, T, T), device=dev, dtype=torch.float32) for _ in range(3)]
+  if out_soft is not None:
+    assert tuple(out_soft.shape) == (B, T, T) and out_soft.is_contiguous()
+    out[0] = out_soft
+  _lib.call('ra_pairwise_iou_umma_f32', _p(a), _p(b), B, T, H, W, float(hard_threshold), _p(ws), _p(out[0]), _p(out[1]),
+            _p(out[2]), _stream())
+  return tuple(out)
+
+
 def loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice_hard, s_out, s_gt, gt_area, loss_mix_ratio,
                weight_decay_term, segm_coeff=1.0):
   """full_model.py:942-1081 scalars -> dict keyed like the reference's model dict."""

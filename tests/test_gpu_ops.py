@@ -725,3 +725,30 @@ def test_rowstack_mode_matches_fp32_conv(cuda):
   assert len(rows) >= 12 and sum("'rowstack': 1" in l for l in rows) >= 10
   for l in rows:
     assert float(l.split(' err ')[1].split()[0]) < 1e-5, l
+
+
+@pytest.mark.parametrize('B,T,H,W', [(3, 5, 16, 32), (7, 20, 32, 64), (2, 32, 64, 64), (32, 20, 64, 128), (1, 127, 8, 32)])
+def test_iou_soft_hard_tensor_core(cuda, B, T, H, W):
+  """ra_pairwise_iou_umma_f32 (tcgen05 K-major GEMM over the pixels, hi / lo split of the soft masks) against the
+  oracle's f_iou_pairwise / f_dice_pairwise and against the CUDA-core kernel."""
+  from rec_attend_b200 import ops
+  rng = np.random.default_rng(B * 100 + T)
+  a = rng.random((B, T, H, W)).astype(np.float32) ** 3
+  g = (rng.random((B, T, H, W)) > 0.7).astype(np.float32)
+  g[:, -1] = 0.0  # an empty ground-truth slot
+  res = ops.f_iou_soft_hard(_g(a), _g(g), hard_threshold=0.5)
+  assert res is not None
+  soft, hard, dice = [t.cpu().numpy() for t in res]
+  at, gt = torch.from_numpy(a), torch.from_numpy(g)
+  ref_soft = OM.f_iou_pairwise(at, gt).numpy()
+  ah = (at > 0.5).float()
+  ref_hard = OM.f_iou_pairwise(ah, gt).numpy()
+  ref_dice = OM.f_dice_pairwise(ah, gt).numpy()
+  assert rel_err(soft, ref_soft) < 2e-5
+  assert rel_err(hard, ref_hard) < 2e-5
+  assert rel_err(dice, ref_dice) < 2e-5
+  if T <= 64:
+    old = ops.f_iou(_g(a), _g(g)).cpu().numpy()
+    assert rel_err(soft, old) < 2e-5
+  # H*W % 32 != 0: outside the kernel's range, the caller falls back to f_iou
+  assert ops.f_iou_soft_hard(_g(a[:, :, :H - 1, :W - 1].copy()), _g(g[:, :, :H - 1, :W - 1].copy())) is None
