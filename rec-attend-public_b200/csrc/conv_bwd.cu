@@ -90,20 +90,33 @@ __global__ void __launch_bounds__(kT) bn_bwd_reduce_kernel(const float *__restri
   for (int i = threadIdx.x; i < 2 * C; i += kT) partial[(size_t)blockIdx.x * 2 * C + i] = acc_s[i];
 }
 
-__global__ void bn_bwd_finalize_kernel(const double *__restrict__ partial, int ctas, int C, float *__restrict__ dgamma,
-                                       float *__restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// one CTA per (channel, group): the per-CTA partials are added by 128 threads (strided, then a fixed tree) in double
+__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double *__restrict__ partial, int ctas, int C,
+                                                              float *__restrict__ dgamma, float *__restrict__ dbeta) {
+  __shared__ double sb_s[128], sg_s[128];
+  const int c = blockIdx.x;
   partial += (size_t)blockIdx.y * ctas * 2 * C;
   dgamma += (size_t)blockIdx.y * C;
   dbeta += (size_t)blockIdx.y * C;
   double sb = 0.0, sg = 0.0;
-  for (int k = 0; k < ctas; ++k) {
+  for (int k = threadIdx.x; k < ctas; k += 128) {
     sb += partial[(size_t)k * 2 * C + c];
     sg += partial[(size_t)k * 2 * C + C + c];
   }
-  dbeta[c] = (float)sb;
-  dgamma[c] = (float)sg;
+  sb_s[threadIdx.x] = sb;
+  sg_s[threadIdx.x] = sg;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sb_s[threadIdx.x] += sb_s[threadIdx.x + o];
+      sg_s[threadIdx.x] += sg_s[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    dbeta[c] = (float)sb_s[0];
+    dgamma[c] = (float)sg_s[0];
+  }
 }
 
 // pass B: d_raw for every element of the window of every pooled output
@@ -494,7 +507,7 @@ extern "C" int ra_bn_train_block_bwd_grouped_f32(const float *raw, const float *
                                                             partial);
   int rc = ra::finish_launch("bn_bwd_reduce_kernel");
   if (rc != RA_OK) return rc;
-  bn_bwd_finalize_kernel<<<dim3((C + 127) / 128, G), 128, 0, s>>>(partial, ctas, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<dim3(C, G), 128, 0, s>>>(partial, ctas, C, dgamma, dbeta);
   rc = ra::finish_launch("bn_bwd_finalize_kernel");
   if (rc != RA_OK) return rc;
   if (pool == 2)

@@ -271,21 +271,59 @@ __global__ void controller_bwd_kernel(const float *__restrict__ feat, int P, int
 }
 
 // dW[i][o] = sum_r A[r*a_stride + i] * D[r*d_stride + o]; db[o] = sum_r D[r*d_stride + o]  (fixed order over r)
-__global__ void outer_sum_kernel(const float *__restrict__ A, size_t a_stride, int n_in, const float *__restrict__ D,
-                                 size_t d_stride, int n_out, int R, float *__restrict__ dW, float *__restrict__ db) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t n = (size_t)n_in * n_out;
-  if (idx < n) {
-    const int i = (int)(idx / n_out), o = (int)(idx - (size_t)i * n_out);
-    float s = 0.f;
-    for (int r = 0; r < R; ++r) s = fmaf(A[(size_t)r * a_stride + i], D[(size_t)r * d_stride + o], s);
-    dW[idx] = s;
+// dW [n_in, n_out] = sum_r A_r^T D_r as a tiled product: a CTA owns a 64 x 64 tile of dW and walks the R rows in
+// chunks of 16 staged in shared memory; every thread keeps a 4 x 4 register tile.  One pass over the rows in a fixed
+// order: bit-identical from run to run.  db = column sums of D (CTAs of the first tile row).
+constexpr int kOsT = 64, kOsR = 16;
+__global__ void __launch_bounds__(256) outer_sum_kernel(const float *__restrict__ A, size_t a_stride, int n_in,
+                                                        const float *__restrict__ D, size_t d_stride, int n_out, int R,
+                                                        float *__restrict__ dW, float *__restrict__ db) {
+  __shared__ float a_s[kOsR][kOsT + 4];
+  __shared__ float d_s[kOsR][kOsT + 4];
+  const int i0 = blockIdx.y * kOsT, o0 = blockIdx.x * kOsT;
+  const int ti = threadIdx.x / 16, to = threadIdx.x % 16;  // rows 4*ti.., columns 4*to..
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  float dbv[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool do_db = db != nullptr && blockIdx.y == 0 && ti == 0;
+  for (int r0 = 0; r0 < R; r0 += kOsR) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kOsR * kOsT; idx += 256) {
+      const int rr = idx / kOsT, c = idx - rr * kOsT;
+      const int r = r0 + rr;
+      a_s[rr][c] = (r < R && i0 + c < n_in) ? A[(size_t)r * a_stride + i0 + c] : 0.f;
+      d_s[rr][c] = (r < R && o0 + c < n_out) ? D[(size_t)r * d_stride + o0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < kOsR; ++rr) {
+      const float4 av = *reinterpret_cast<const float4 *>(&a_s[rr][4 * ti]);
+      const float4 dv = *reinterpret_cast<const float4 *>(&d_s[rr][4 * to]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], d4[b], acc[a][b]);
+      if (do_db) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dbv[b] += d4[b];
+      }
+    }
   }
-  if (db != nullptr && idx < (size_t)n_out) {
-    float s = 0.f;
-    for (int r = 0; r < R; ++r) s += D[(size_t)r * d_stride + idx];
-    db[idx] = s;
-  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + 4 * ti + a, o = o0 + 4 * to + b;
+      if (i < n_in && o < n_out) dW[(size_t)i * n_out + o] = acc[a][b];
+    }
+  if (do_db)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (o0 + 4 * to + b < n_out) db[o0 + 4 * to + b] = dbv[b];
 }
 
 bool dims_ok(int P, int Cf, int Hd, int n_iter) {
@@ -356,9 +394,7 @@ extern "C" int ra_outer_sum_f32(const float *A, size_t a_stride, int n_in, const
                                 int R, float *dW, float *db, void *stream) {
   if (n_in < 1 || n_out < 1 || R < 0 || !dW) return RA_ERR_INVALID_ARG;
   if (R > 0 && (!A || !D)) return RA_ERR_INVALID_ARG;
-  const size_t n = (size_t)n_in * n_out;
-  const size_t threads = n > (size_t)n_out ? n : (size_t)n_out;
-  outer_sum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ra::as_stream(stream)>>>(A, a_stride, n_in, D, d_stride,
-                                                                                         n_out, R, dW, db);
+  const dim3 grid((n_out + kOsT - 1) / kOsT, (n_in + kOsT - 1) / kOsT);
+  outer_sum_kernel<<<grid, 256, 0, ra::as_stream(stream)>>>(A, a_stride, n_in, D, d_stride, n_out, R, dW, db);
   return ra::finish_launch("outer_sum_kernel");
 }
