@@ -42,6 +42,7 @@ def load_peaks():
 
 # C-ABI entry point -> the CUDA kernels it launches (names as ncu prints them), for `traffic`
 ENTRY_KERNELS = {
+    'ra_conv3x3_umma_chain_run': ['conv3x3_umma_chain_kernel'],
     'ra_gaussian_extract_f32': ['extract_rows_kernel<4>', 'extract_cols_kernel'],
     'ra_paste_back_f32': ['paste_back_kernel'],
     'ra_pairwise_iou_f32': ['pairwise_iou_kernel'],
@@ -454,7 +455,7 @@ def run_ours(args):
     groups = {}
     for key, d in agg.items():
       g = d['entry']
-      if g in ('ra_conv3x3_f32', 'ra_conv3x3_umma_f32'):
+      if g in ('ra_conv3x3_f32', 'ra_conv3x3_umma_f32', 'ra_conv3x3_umma_chain_run'):
         g = g + ':' + d['tag']
       gg = groups.setdefault(g, {'ms': 0.0, 'n': 0})
       gg['ms'] += d['ms']
@@ -474,12 +475,14 @@ def run_ours(args):
       kernels[g] = ent
     # controller-CNN as a group: flops of the 8 conv layers of one decode step / their time
     ccnn_ms = sum(d['ms'] for k, d in agg.items()
-                  if d['entry'] in ('ra_conv3x3_f32', 'ra_conv3x3_umma_f32') and d['tag'] == 'ctrl_cnn')
+                  if d['entry'] in ('ra_conv3x3_f32', 'ra_conv3x3_umma_f32', 'ra_conv3x3_umma_chain_run') and
+                  d['tag'] == 'ctrl_cnn')
     conv_tflops = work['ctrl_cnn_umma_step']['flops'] * T / (ccnn_ms / 1e3) / 1e12 if ccnn_ms > 0 else 0.0
     dom = max(groups.items(), key=lambda kv: kv[1]['ms'])[0]
     if dom.startswith('ra_conv3x3'):
       roofline = {
-          'kernel': 'conv3x3_umma_kernel (controller CNN layers, tcgen05 kind::tf32 x3 split; group = ' + dom + ')',
+          'kernel': 'conv3x3_umma (controller CNN layers 1-7, tcgen05 kind::tf32 x3 split, one persistent chain launch '
+                    'per decode step; group = ' + dom + ')',
           'bound': 'tensor',
           'achieved': round(conv_tflops, 3), 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
           'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': entry_traffic(traffic, dom),

@@ -116,6 +116,29 @@ int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B,
 /* Diagnostics: info[19] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
  * acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf, rowstack of the tile plan. */
 int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info);
+/* A CHAIN of conv layers in ONE launch (the 6 + 7 layers of the patch network of a decode step, full_model.py:792-807;
+ * controller layers 1-7, :663): a persistent grid of one CTA per SM runs the layers back to back with a grid-wide
+ * barrier between them instead of paying CTA start-up, TMEM allocation and pipeline fill / drain per launch.
+ *  ra_conv3x3_umma_chain_prepare: layers[n_layers <= 16] with the arguments of ra_conv3x3_umma_f32 (HOST array; all
+ *    data pointers are device pointers) -> builds every layer's tile plan and tensor maps into desc_host (HOST memory
+ *    of ra_conv3x3_umma_chain_desc_bytes(n_layers) bytes: the blob travels as the kernel's argument);
+ *    *grid_out / *smem_out = launch geometry for the run call.  Layer l+1 may read what layer l wrote.
+ *  ra_conv3x3_umma_chain_run: one launch on `stream`; counter_dev = 16 device uint32 (one barrier counter per layer
+ *    boundary, zeroed here).  Results are identical to n_layers calls of ra_conv3x3_umma_f32. */
+typedef struct {
+  const float *x1;
+  int C1;
+  const float *x2;
+  int C2;
+  const float *wpack, *scale, *shift;
+  int B, Hin, Win, Cout, upsample, pool, relu;
+  float *y;
+} ra_conv_layer_t;
+size_t ra_conv3x3_umma_chain_desc_bytes(int n_layers);
+int ra_conv3x3_umma_chain_prepare(const ra_conv_layer_t *layers, int n_layers, void *desc_host, int *grid_out,
+                                  size_t *smem_out);
+int ra_conv3x3_umma_chain_run(const void *desc_host, int n_layers, int grid, size_t smem_bytes,
+                              unsigned int *counter_dev, void *stream);
 /* Diagnostics: device buffer of 8 int64 per CTA (148 CTAs max) receiving clock64() stamps of the pipeline
  * phases of the next ra_conv3x3_umma_f32 launches; NULL switches it off. */
 int ra_debug_conv_timeline(long long *device_buf);

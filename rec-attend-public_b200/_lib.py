@@ -39,6 +39,8 @@ _SIGNATURES = {
     'ra_conv3x3_umma_plan': [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     'ra_conv3x3_umma_plan_info': [_I, _I, _I, _I, _I, _I, _P],
     'ra_debug_conv_timeline': [_P],
+    'ra_conv3x3_umma_chain_prepare': [_P, _I, _P, _P, _P],
+    'ra_conv3x3_umma_chain_run': [_P, _I, _I, _Z, _P, _P],
     'ra_conv3x3_umma_f32': [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'ra_controller_step_f32': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P,
                                _P, _P, _P, _P],
@@ -104,7 +106,7 @@ EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last
                                          'ra_iou_loss_bwd_workspace', 'ra_paste_back_bwd_workspace',
                                          'ra_gaussian_extract_bwd_workspace', 'ra_controller_tape_floats',
                                          'ra_bn_train_block_bwd_grouped_workspace', 'ra_weight_decay_workspace',
-                                         'ra_pairwise_iou_umma_workspace'])
+                                         'ra_pairwise_iou_umma_workspace', 'ra_conv3x3_umma_chain_desc_bytes'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -152,6 +154,8 @@ def lib():
     l.ra_bn_train_block_bwd_grouped_workspace.restype = _Z
     l.ra_pairwise_iou_umma_workspace.argtypes = [_I, _I, _I, _I]
     l.ra_pairwise_iou_umma_workspace.restype = _Z
+    l.ra_conv3x3_umma_chain_desc_bytes.argtypes = [_I]
+    l.ra_conv3x3_umma_chain_desc_bytes.restype = _Z
     l.ra_weight_decay_workspace.argtypes = []
     l.ra_weight_decay_workspace.restype = _Z
     l.ra_controller_tape_floats.argtypes = [_I, _I, _I, _I]

@@ -88,6 +88,7 @@ struct UmmaConvParams {
   int split_corr;   // merged mode: accumulate A_lo B_hi in the second accumulator half (RA_UMMA_JOINT_CORR=1: first)
   int four_term;    // merged mode: the A_lo instruction also spans [B_hi; B_lo] (adds the lo x lo partial product)
   int pdl;          // launched with programmatic stream serialization: griddepcontrol.wait before touching activations
+  int grid;         // CTAs that serve this layer (= gridDim.x of a single-layer launch; <= gridDim.x inside a chain)
   long long *dbg;   // optional per-CTA timeline (ra_debug_conv_timeline), 8 slots per CTA
 };
 
@@ -133,6 +134,10 @@ __device__ __forceinline__ void umma_commit(uint32_t mbar) {
 
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_inval(uint32_t mbar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
@@ -331,14 +336,18 @@ __device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, b
     if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64();                          \
   } while (0)
 
+// One conv layer, run by a whole CTA (all roles).  `tm1` / `tm2` point at tensor maps in kernel-parameter space (single
+// launch) or in global memory (chain).  CHAIN: the layer is one of several run back to back by a persistent grid: TMEM
+// is allocated by the caller (`tmem_base_in`), the mbarriers of the previous layer are invalidated before they are
+// initialised again, `first` marks the layer that performs the programmatic-dependent-launch handshake.
 // RS: the row-stacked-taps variant (opt-in, see make_plan) is a separate instantiation, so that the default kernel
 // carries none of its registers / shared memory.
-template <bool RS>
-__global__ void __launch_bounds__(kThreads, 1)
-    conv3x3_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant__ CUtensorMap tm1,
-                        const __grid_constant__ CUtensorMap tm2) {
+template <bool RS, bool CHAIN>
+__device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtensorMap &tm1, const CUtensorMap &tm2,
+                                           unsigned char *smem_dyn, uint32_t tmem_base_in, bool first,
+                                           const unsigned int *chain_counter = nullptr,
+                                           unsigned int chain_target = 0u) {
   if (threadIdx.x == 0) RA_DBG(0);
-  extern __shared__ __align__(128) unsigned char smem_dyn[];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sc_s[256], sh_s[256];  // folded-BN scale / shift of this CTA's channels
   __shared__ float xw_s[RS ? 2 * 4 * 48 : 1];  // rowstack epilogue: rows the next warp hands to lanes 30 / 31
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   unsigned char *stage_base = smem_raw + p.w_res_bytes;  // [resident filter image][stages][pool tile]
   float *pool_s = reinterpret_cast<float *>(stage_base + (size_t)p.stages * p.stage_bytes);
   const int ns = blockIdx.x % p.n_split;
-  const int tile0 = blockIdx.x / p.n_split, tile_step = gridDim.x / p.n_split;
+  const int tile0 = blockIdx.x / p.n_split, tile_step = p.grid / p.n_split;
   const int n_tiles = p.n_items / p.n_split;
 
   // Barriers are initialised by the TMA warp, which (TMA mode) fires the first `stages` loads right away - before
@@ -365,6 +374,17 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == kTmaWarp) {
     const bool leader = elect_one();
     if (leader) {
+      if (CHAIN && !first) {  // the previous layer's barriers: every wait on them has completed (CTA-wide sync)
+        for (int s = 0; s < kMaxStages; ++s) {
+          mbar_inval(smem_u32(&bar_full[s]));
+          mbar_inval(smem_u32(&bar_empty[s]));
+          mbar_inval(smem_u32(&bar_raw[s]));
+        }
+        for (int s = 0; s < 2; ++s) {
+          mbar_inval(smem_u32(&bar_tfull[s]));
+          mbar_inval(smem_u32(&bar_tempty[s]));
+        }
+      }
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(smem_u32(&bar_full[s]), kProdThreads);
         mbar_init(smem_u32(&bar_empty[s]), kMmaWarps);
@@ -384,7 +404,19 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       // the activations are the previous kernel's output: wait for it (programmatic dependent launch) here, and
       // only here - every other access to dependent memory is ordered after these loads
-      if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+      if (p.pdl && first) asm volatile("griddepcontrol.wait;" ::: "memory");
+      if (CHAIN && !first) {
+        // split grid barrier: every CTA ARRIVED when it finished the previous layer (chain kernel loop); only this
+        // warp WAITS, and only now - the barrier set-up above, the TMEM / filter / scale-shift loads of the other
+        // warps overlap the tail of the previous layer on slower SMs
+        // (every lane polls and the loop exit is warp-uniform: the TMA instructions below want a converged warp)
+        unsigned int seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(chain_counter) : "memory");
+        } while (__any_sync(0xffffffffu, seen < chain_target));
+        asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic-proxy stores -> our TMA reads
+        __syncwarp();
+      }
       const uint32_t w_bytes = p.w_resident ? 0u : (uint32_t)w_chunk_floats * 4u;
       const uint32_t tx_bytes = (uint32_t)planes * (uint32_t)(p.RW * p.RH) * 16u + w_bytes;
       const uint32_t dst_plane = p.up == 2 ? (uint32_t)p.raw_plane_bytes : plane_bytes;
@@ -418,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       tma_prologue = g;
     }
   }
-  if (warp == 0) {
+  if (!CHAIN && warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -447,12 +479,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);  // uniform register
+  const uint32_t tmem_base = CHAIN ? tmem_base_in : __shfl_sync(0xffffffffu, tmem_base_s, 0);  // uniform register
   const int slots_in = (p.TH + 2) * p.TWP + 2;  // slots that carry real (or zero-padding) data
   if (threadIdx.x == 0) RA_DBG(1);  // setup done (barriers, TMEM, resident filters)
   // programmatic dependent launch: the next kernel of the stream may start its own setup on SMs this grid has
   // left; it still waits (griddepcontrol.wait) for this grid to complete before it reads our output
-  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (p.pdl && first) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == kTmaWarp) {
     // =============================== TMA issuer ===============================
@@ -492,6 +524,15 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           __syncwarp();
         }
+      }
+      if (CHAIN) {
+        // Drain: the MMA warps release every stage with an asynchronous tcgen05.commit -> mbarrier arrive.  Nobody waits
+        // for the LAST release of a stage inside a layer, and the next layer re-initialises these barriers right after
+        // the CTA-wide sync: an arrival still in flight would land on the fresh barrier.  Wait for all of them here.
+        const int first_pending = g > p.stages ? g - p.stages : 0;
+        for (int gg = first_pending; gg < g; ++gg)
+          mbar_wait(smem_u32(&bar_empty[gg % p.stages]), (uint32_t)((gg / p.stages) & 1));
+        __syncwarp();
       }
     }
   } else if (warp >= kMmaWarp0 + kMmaWarps && p.tma) {
@@ -548,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp >= kMmaWarp0 + kMmaWarps) {
     // =============================== producers (plain-load mode) ===============================
     const int ptid = tid - (kEpiThreads + 32 * kMmaWarps);
-    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous kernel's output
+    if (p.pdl && first) asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous kernel's output
     int g = 0;  // running (tile, chunk) counter
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       const Item it = decode_tile(p, tile);
@@ -939,9 +980,85 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
 
+  if (CHAIN) __threadfence();  // this layer's outputs are read by other CTAs after the grid barrier
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (threadIdx.x == 0) RA_DBG(7);  // all roles done
+  if (!CHAIN && warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+template <bool RS>
+__global__ void __launch_bounds__(kThreads, 1)
+    conv3x3_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant__ CUtensorMap tm1,
+                        const __grid_constant__ CUtensorMap tm2) {
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  conv_layer<RS, false>(p, tm1, tm2, smem_dyn, 0u, true);
+}
+
+// A CHAIN of conv layers in one launch: the patch network of a decode step (6 + 7 layers) or controller layers 1-7.
+// Every layer of those stacks is a 15-30 us launch for 1-2 us of tensor work (pipeline fill / drain, CTA start-up, TMEM
+// allocation); here a persistent grid of one CTA per SM runs the layers back to back with a grid-wide barrier between
+// them: TMEM is allocated once, the next layer's barrier set-up and filter load start the moment the barrier opens.
+// Layer l is served by the first layers[l].p.grid CTAs (its own tile plan); the others only take part in the barrier.
+// All CTAs are co-resident (grid <= number of SMs, one CTA per SM), so the spin barrier cannot deadlock: kernels of
+// other graph branches that hold an SM finish on their own.
+struct ChainLayer {
+  UmmaConvParams p;
+  CUtensorMap tm1, tm2;
+};
+constexpr int kChainMax = 16;
+// The whole chain travels as ONE kernel argument (kernel parameters may be up to 32 KB since CUDA 12.1): the layer
+// parameters are then read through the constant bank and the tensor maps live in parameter space, exactly like in the
+// single-layer kernel - descriptors in global memory made every field a load in the MMA-issue and epilogue loops.
+struct ChainArgs {
+  ChainLayer layers[kChainMax];
+  int n_layers;
+  unsigned int *counter;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_chain_kernel(const __grid_constant__ ChainArgs args) {
+  const ChainLayer *layers = args.layers;
+  const int n_layers = args.n_layers;
+  unsigned int *counter = args.counter;
+  const int pdl = 0;
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  __shared__ uint32_t chain_tmem_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&chain_tmem_s)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = chain_tmem_s;
+  for (int l = 0; l < n_layers; ++l) {
+    const ChainLayer &L = layers[l];
+    if ((int)blockIdx.x < L.p.grid) {
+      // (layers fed by plain loads instead of TMA have no single waiting warp: they would need a full barrier - the
+      // prepare call refuses them)
+      // (one counter per layer boundary: CTAs that sit a layer out arrive for it at once, which must not count towards
+      // the barriers of other layers)
+      conv_layer<false, true>(L.p, L.tm1, L.tm2, smem_dyn, tmem_base, l == 0, counter + (l > 0 ? l - 1 : 0), gridDim.x);
+    } else if (l == 0 && pdl) {
+      // idle in the first layer: still take part in the programmatic-dependent-launch handshake
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
+    if (l + 1 < n_layers) {
+      // ARRIVE at the grid barrier of layer l (conv_layer ended with __threadfence + __syncthreads: this CTA's stores
+      // are ordered before the increment); the wait happens inside the next layer, right before its first TMA load
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter + l, 1u);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
@@ -1263,14 +1380,21 @@ extern "C" int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, 
   return RA_OK;
 }
 
-extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int C2, const float *wpack,
-                                   const float *scale, const float *shift, int B, int Hin, int Win, int Cout,
-                                   int upsample, int pool, int relu, float *y, void *stream) {
+namespace {
+
+// Tile plan, kernel parameters and tensor maps of one layer (shared by the single-layer launch and the chain).
+// Returns RA_OK with *empty = true for an empty batch.
+int build_layer(const float *x1, int C1, const float *x2, int C2, const float *wpack, const float *scale,
+                const float *shift, int B, int Hin, int Win, int Cout, int upsample, int pool, int relu, float *y,
+                UmmaConvParams *pp, CUtensorMap *tm1p, CUtensorMap *tm2p, Plan *plp, size_t *smem_out, bool *empty) {
+  UmmaConvParams &p = *pp;
+  CUtensorMap &tm1 = *tm1p, &tm2 = *tm2p;
+  Plan &pl = *plp;
+  *empty = false;
   if (!x1 || !wpack || !scale || !shift || !y || C1 < 1 || C2 < 0 || (C2 > 0 && !x2) || B < 0 || Hin < 1 || Win < 1 ||
       Cout < 1)
     return RA_ERR_INVALID_ARG;
   if ((upsample != 1 && upsample != 2) || (pool != 1 && pool != 2)) return RA_ERR_UNSUPPORTED;
-  UmmaConvParams p;
   p.x1 = x1;
   p.x2 = x2;
   p.wpack = wpack;
@@ -1289,8 +1413,10 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   p.up = upsample;
   p.pool = pool;
   p.relu = relu;
-  if (B == 0) return RA_OK;
-  Plan pl;
+  if (B == 0) {
+    *empty = true;
+    return RA_OK;
+  }
   const int rc = make_plan_forced(p.Cin, Cout, p.Hout, p.Wout, pool, B, &pl);
   if (rc != RA_OK) return rc;
   p.TH = pl.TH;
@@ -1329,7 +1455,6 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   p.raw_plane_bytes = 0;
   p.raw_off = 0;
   size_t smem_bytes = pl.smem_bytes;
-  CUtensorMap tm1, tm2;
   memset(&tm1, 0, sizeof(tm1));
   memset(&tm2, 0, sizeof(tm2));
   if (!no_tma && p.vec4 && p.RW <= 256 && p.RH <= 256 && (reinterpret_cast<uintptr_t>(x1) & 15) == 0 &&
@@ -1358,16 +1483,26 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
       smem_bytes = pl.smem_bytes;
     }
   }
-  smem_bytes += 128;  // alignment slack (the kernel rounds its window up to 128 bytes)
+  p.grid = pl.grid;
+  p.pdl = 0;
+  p.four_term = getenv("RA_UMMA_4TERM") != nullptr ? 1 : 0;
+  p.split_corr = getenv("RA_UMMA_JOINT_CORR") == nullptr ? 1 : 0;
+  *smem_out = smem_bytes + 128;  // alignment slack (the kernel rounds its window up to 128 bytes)
+  return RA_OK;
+}
+
+bool conv_attrs() {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
         cudaFuncSetAttribute(conv3x3_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_umma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
       ra::set_last_error("cudaFuncSetAttribute(conv3x3_umma_kernel)", e);
-      return RA_ERR_CUDA;
+      return false;
     }
     // diagnostics: pin the SM shared-memory carve-out to its maximum for every launch of this kernel, so that
     // consecutive layers with different dynamic sizes never trigger a carve-out reconfiguration
@@ -1376,13 +1511,33 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
                                  (int)cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
+  return true;
+}
+
+bool conv_use_pdl() {
   static const bool use_pdl = []() {
     const char *e = getenv("RA_CONV_PDL");
     return e == nullptr || atoi(e) != 0;
   }();
+  return use_pdl;
+}
+
+}  // namespace
+
+extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int C2, const float *wpack,
+                                   const float *scale, const float *shift, int B, int Hin, int Win, int Cout,
+                                   int upsample, int pool, int relu, float *y, void *stream) {
+  UmmaConvParams p;
+  CUtensorMap tm1, tm2;
+  Plan pl;
+  size_t smem_bytes = 0;
+  bool empty = false;
+  const int brc = build_layer(x1, C1, x2, C2, wpack, scale, shift, B, Hin, Win, Cout, upsample, pool, relu, y, &p, &tm1,
+                              &tm2, &pl, &smem_bytes, &empty);
+  if (brc != RA_OK || empty) return brc;
+  if (!conv_attrs()) return RA_ERR_CUDA;
+  const bool use_pdl = conv_use_pdl();
   p.pdl = use_pdl ? 1 : 0;
-  p.four_term = getenv("RA_UMMA_4TERM") != nullptr ? 1 : 0;
-  p.split_corr = getenv("RA_UMMA_JOINT_CORR") == nullptr ? 1 : 0;
   if (use_pdl) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1408,4 +1563,56 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
       conv3x3_umma_kernel<false><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
   }
   return ra::finish_launch("conv3x3_umma_kernel");
+}
+
+// ---- chain of layers in one launch ------------------------------------------------------------------------------
+extern "C" size_t ra_conv3x3_umma_chain_desc_bytes(int n_layers) {
+  return (n_layers < 1 || n_layers > kChainMax) ? 0 : sizeof(ChainArgs);
+}
+
+extern "C" int ra_conv3x3_umma_chain_prepare(const ra_conv_layer_t *layers, int n_layers, void *desc_host, int *grid_out,
+                                             size_t *smem_out) {
+  if (!layers || n_layers < 1 || n_layers > kChainMax || !desc_host || !grid_out || !smem_out) return RA_ERR_INVALID_ARG;
+  ChainArgs *args = static_cast<ChainArgs *>(desc_host);
+  memset(args, 0, sizeof(ChainArgs));
+  int grid = 1;
+  size_t smem = 0;
+  int rc = RA_OK;
+  for (int l = 0; l < n_layers && rc == RA_OK; ++l) {
+    const ra_conv_layer_t &L = layers[l];
+    Plan pl;
+    size_t sb = 0;
+    bool empty = false;
+    rc = build_layer(L.x1, L.C1, L.x2, L.C2, L.wpack, L.scale, L.shift, L.B, L.Hin, L.Win, L.Cout, L.upsample, L.pool,
+                     L.relu, L.y, &args->layers[l].p, &args->layers[l].tm1, &args->layers[l].tm2, &pl, &sb, &empty);
+    // (the chain runs the default variant, and its split grid barrier waits in the TMA warp)
+    if (rc == RA_OK && (empty || pl.rowstack || (l > 0 && !args->layers[l].p.tma))) rc = RA_ERR_UNSUPPORTED;
+    if (rc != RA_OK) break;
+    args->layers[l].p.dbg = nullptr;
+    args->layers[l].p.pdl = 0;  // the chain is launched behind a memset node, without the programmatic-launch attribute
+    if (pl.grid > grid) grid = pl.grid;
+    if (sb > smem) smem = sb;
+  }
+  if (rc == RA_OK && grid > ra::kNumSMs) rc = RA_ERR_UNSUPPORTED;  // the spin barrier needs co-resident CTAs
+  args->n_layers = n_layers;
+  *grid_out = grid;
+  *smem_out = smem;
+  return rc;
+}
+
+extern "C" int ra_conv3x3_umma_chain_run(const void *desc_host, int n_layers, int grid, size_t smem_bytes,
+                                         unsigned int *counter_dev, void *stream) {
+  if (!desc_host || n_layers < 1 || n_layers > kChainMax || grid < 1 || grid > ra::kNumSMs || !counter_dev)
+    return RA_ERR_INVALID_ARG;
+  if (!conv_attrs()) return RA_ERR_CUDA;
+  cudaStream_t s = ra::as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(counter_dev, 0, kChainMax * sizeof(unsigned int), s);
+  if (e != cudaSuccess) {
+    ra::set_last_error("cudaMemsetAsync(chain counter)", e);
+    return RA_ERR_CUDA;
+  }
+  ChainArgs args = *static_cast<const ChainArgs *>(desc_host);  // (copied into the launch / the graph node)
+  args.counter = counter_dev;
+  conv3x3_umma_chain_kernel<<<grid, kThreads, smem_bytes, s>>>(args);
+  return ra::finish_launch("conv3x3_umma_chain_kernel");
 }

@@ -159,6 +159,7 @@ class _ModelBase(object):
     self._trainer = None
     for b in self._bufs.values():
       b.pop('graphs', None)
+      b.pop('chains', None)  # conv chains hold the old weight pointers in their device-side descriptors
 
   def _load_controller(self, weights):
     T = self.T
@@ -234,14 +235,31 @@ class _ModelBase(object):
     if os.environ.get('RA_CONV_FP32'):
       return ops.conv3x3_block(x, self._w_dev(wp), scale, shift, pool=pool, relu=relu, x2=x2, upsample=upsample,
                                out=out)
-    B = x.shape[0]
-    key = (B, pool)  # the tile plan (hence the packed image) depends on the batch size and on the pooling
+    return ops.conv3x3_block_umma(x, self._packed(wp, x.shape[0], pool), wp['w'].shape[3], scale, shift, pool=pool,
+                                  relu=relu, x2=x2, upsample=upsample, out=out)
+
+  def _packed(self, wp, B, pool):
+    """The tcgen05 filter image of a registered filter for batch size B (packed on first use: the tile plan, hence
+    the image, depends on the batch size and on the pooling)."""
+    key = (B, pool)
     if key not in wp['packed']:
       w = wp['w']
       KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], pool, B)
       wp['packed'][key] = self._dev(PM.pack_umma(PM.WI(w, wp['idx']), KC, NPc, nsp, rs))
-    return ops.conv3x3_block_umma(x, wp['packed'][key], wp['w'].shape[3], scale, shift, pool=pool, relu=relu, x2=x2,
-                                  upsample=upsample, out=out)
+    return wp['packed'][key]
+
+  def _use_chain(self):
+    """RA_CHAIN=1 (opt-in): eval mode runs a whole conv stack of a decode step (controller layers 1-7; the 6 + 7
+    patch-network layers) as ONE launch of a persistent grid (ops.ConvChain; bit-identical results).  MEASURED on B200
+    (KITTI B=32): the summed conv time falls from 11.3 ms (one eager launch per layer) to 9.8 ms, but inside the CUDA
+    graph the per-layer launches already overlap through programmatic dependent launch (8.4 ms effective) and the
+    chain cannot overlap with its neighbours: 17.4 ms per step against 15.7 ms - so one launch per layer stays the
+    default (profiles/r02f_chain.txt)."""
+    return (bool(os.environ.get('RA_CHAIN')) and not os.environ.get('RA_CONV_FP32') and int(self.n_chains) <= 1)
+
+  def _chain_spec(self, x, wp, scale, shift, pool, relu=True, x2=None, upsample=1, out=None):
+    return {'x': x, 'x2': x2, 'wpack': self._packed(wp, x.shape[0], pool), 'Cout': wp['w'].shape[3], 'scale': scale,
+            'shift': shift, 'pool': pool, 'relu': relu, 'upsample': upsample, 'out': out}
 
   def _block(self, train, x, wp, prefix, i, t, pool, relu=True, x2=None, upsample=1, out=None):
     """One nn.cnn / nn.dcnn layer.  Eval: conv with the folded EMA batch norm in its epilogue.  Training
@@ -470,9 +488,17 @@ class _ModelBase(object):
                                  w['ccnn_ema_var0'][t], pool=self.ctrl_pool[0], relu=True, eps=BN_EPS,
                                  out=self._act(bufs, 'ccnn', 0, t), batch_mean=bm, batch_var=bv)
     n_c = len(self.ctrl_pool)
-    for i in range(1, n_c):
-      self._block(train, self._act(bufs, 'ccnn', i - 1, t), w['ccnn_w%d' % i], 'ccnn', i, t, self.ctrl_pool[i],
-                  out=self._act(bufs, 'ccnn', i, t))
+    if not train and self._use_chain() and 'ccnn' in bufs and isinstance(bufs.get('chains', {}), dict):
+      chains = bufs.setdefault('chains', {})
+      if ('ctrl', t) not in chains:  # (built in the warm-up pass, outside graph capture)
+        chains[('ctrl', t)] = ops.ConvChain([
+            self._chain_spec(bufs['ccnn'][i - 1], w['ccnn_w%d' % i], w['ccnn_scale%d' % i][t], w['ccnn_shift%d' % i][t],
+                             self.ctrl_pool[i], out=bufs['ccnn'][i]) for i in range(1, n_c)])
+      chains[('ctrl', t)].run()
+    else:
+      for i in range(1, n_c):
+        self._block(train, self._act(bufs, 'ccnn', i - 1, t), w['ccnn_w%d' % i], 'ccnn', i, t, self.ctrl_pool[i],
+                    out=self._act(bufs, 'ccnn', i, t))
     feat = self._act(bufs, 'ccnn', n_c - 1, t).view(B, self.P, -1)
     _lib.TAG = 'controller'
     ops.controller_step(feat, w['lstm_wx'], w['lstm_wh'], w['lstm_b'], w['glimpse_mlp_w_0'], w['glimpse_mlp_b_0'],
@@ -641,32 +667,53 @@ class FullModel(_ModelBase):
       _lib.TAG = 'extract'
       ops.extract_patch(bufs['xs'], bufs['canvas'], self.chan_map, box_t, fy, fx, bufs['band'],
                         tmp=bufs['extract_tmp'], out=x_patch)
-      prev = x_patch
       _lib.TAG = 'attn_cnn'
-      acts = []
-      for i, pl in enumerate(self.attn_pool):  # full_model.py:792
-        dst = self._act(bufs, 'acnn', i, t)
-        self._block(train, prev, w['acnn_w%d' % i], 'acnn', i, t, pl, out=dst)
-        acts.append(dst)
-        prev = dst
+      n_d = len(self.dcnn_pool)
+      chain_mode = (not train) and self._use_chain()
+      acts = [self._act(bufs, 'acnn', i, t) for i in range(n_a)]
       core = acts[-1]
-      # the score head (full_model.py:821-822) feeds only the loss: a parallel graph branch beside the mask head
+      # full_model.py:797-807: skip list [None, h_acnn[4..0], x_patch]
+      skips = [None] + (acts[::-1][1:] + [x_patch])
+      dsts = [bufs['y_patch_all'][t] if i == n_d - 1 else self._act(bufs, 'adcnn', i, t) for i in range(n_d)]
+      if chain_mode:
+        # the whole patch network of this step - attention CNN (full_model.py:792) and deconv mask head (:797-807) -
+        # as ONE persistent launch
+        _lib.TAG = 'patch_net'
+        chains = bufs.setdefault('chains', {})
+        if ('patch', t) not in chains:
+          layers = []
+          prev = x_patch
+          for i, pl in enumerate(self.attn_pool):
+            layers.append(self._chain_spec(prev, w['acnn_w%d' % i], w['acnn_scale%d' % i][t], w['acnn_shift%d' % i][t],
+                                           pl, out=acts[i]))
+            prev = acts[i]
+          for i, pl in enumerate(self.dcnn_pool):
+            sk = skips[i] if (self.use_skip and self.skip_ch[i] > 0) else None
+            layers.append(self._chain_spec(prev, w['adcnn_w%d' % i], w['adcnn_scale%d' % i][t],
+                                           w['adcnn_shift%d' % i][t], 1, x2=sk, upsample=pl, out=dsts[i]))
+            prev = dsts[i]
+          chains[('patch', t)] = ops.ConvChain(layers)
+        chains[('patch', t)].run()
+      else:
+        prev = x_patch
+        for i, pl in enumerate(self.attn_pool):  # full_model.py:792
+          self._block(train, prev, w['acnn_w%d' % i], 'acnn', i, t, pl, out=acts[i])
+          prev = acts[i]
+      # the score head (full_model.py:821-822) feeds only the loss: a parallel graph branch beside the mask head /
+      # the paste-back
       score_side = self._side_stream(bufs, 2) if fork_score else None
       if score_side is None:
         ops.score(bufs['h_all'][t], core, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
       else:
         with torch.cuda.stream(score_side):
           ops.score(bufs['h_all'][t], core, w['score_mlp_w_0'], w['score_mlp_b_0'], bufs['s_out'][:, t], T)
-      # full_model.py:797-807: skip list [None, h_acnn[4..0], x_patch]
-      skips = [None] + (acts[::-1][1:] + [x_patch])
-      prev = core
-      n_d = len(self.dcnn_pool)
-      _lib.TAG = 'attn_dcnn'
-      for i, pl in enumerate(self.dcnn_pool):
-        sk = skips[i] if (self.use_skip and self.skip_ch[i] > 0) else None
-        dst = bufs['y_patch_all'][t] if i == n_d - 1 else self._act(bufs, 'adcnn', i, t)
-        self._block(train, prev, w['adcnn_w%d' % i], 'adcnn', i, t, 1, x2=sk, upsample=pl, out=dst)
-        prev = dst
+      if not chain_mode:
+        prev = core
+        _lib.TAG = 'attn_dcnn'
+        for i, pl in enumerate(self.dcnn_pool):
+          sk = skips[i] if (self.use_skip and self.skip_ch[i] > 0) else None
+          self._block(train, prev, w['adcnn_w%d' % i], 'adcnn', i, t, 1, x2=sk, upsample=pl, out=dsts[i])
+          prev = dsts[i]
       _lib.TAG = 'paste_back'
       if knob is None:
         ops.paste_back(bufs['y_patch_all'][t].view(B, F, F), box_t, fy, fx, bufs['canvas'],

@@ -144,6 +144,49 @@ def conv3x3_block_umma(x, wpack, Cout, scale, shift, pool=1, relu=True, x2=None,
   return out
 
 
+class _ConvLayerSpec(_c.Structure):
+  """ra_conv_layer_t of include/rec_attend_b200.h."""
+  _fields_ = [('x1', _c.c_void_p), ('C1', _c.c_int), ('x2', _c.c_void_p), ('C2', _c.c_int), ('wpack', _c.c_void_p),
+              ('scale', _c.c_void_p), ('shift', _c.c_void_p), ('B', _c.c_int), ('Hin', _c.c_int), ('Win', _c.c_int),
+              ('Cout', _c.c_int), ('upsample', _c.c_int), ('pool', _c.c_int), ('relu', _c.c_int), ('y', _c.c_void_p)]
+
+
+class ConvChain(object):
+  """Several conv3x3_block_umma layers run by ONE launch of a persistent grid (ra_conv3x3_umma_chain_*): the patch
+  network of a decode step, controller layers 1-7.  `layers`: list of dicts with the arguments of conv3x3_block_umma
+  (x, wpack, Cout, scale, shift, pool, relu, x2, upsample, out - `out` is required).  The tile plans and tensor maps are
+  built here (host side; construct it once, outside the timed path); `run()` is one launch on the current
+  stream.  The tensors are kept alive by the object."""
+
+  def __init__(self, layers):
+    n = len(layers)
+    arr = (_ConvLayerSpec * n)()
+    self._keep = []
+    dev = layers[0]['x'].device
+    for i, L in enumerate(layers):
+      x, x2, out = L['x'], L.get('x2'), L['out']
+      _chk(x, L['wpack'], L['scale'], L['shift'], x2, out)
+      B, H, W, C1 = x.shape
+      up, pool = L.get('upsample', 1), L.get('pool', 1)
+      assert tuple(out.shape) == (B, H * up // pool, W * up // pool, L['Cout']), (i, tuple(out.shape))
+      arr[i] = _ConvLayerSpec(x.data_ptr(), C1, 0 if x2 is None else x2.data_ptr(), 0 if x2 is None else x2.shape[3],
+                              L['wpack'].data_ptr(), L['scale'].data_ptr(), L['shift'].data_ptr(), B, H, W, L['Cout'],
+                              up, pool, 1 if L.get('relu', True) else 0, out.data_ptr())
+      self._keep.extend([x, x2, out, L['wpack'], L['scale'], L['shift']])
+    self.n = n
+    nbytes = int(_lib.lib().ra_conv3x3_umma_chain_desc_bytes(n))
+    if nbytes == 0:
+      raise _lib.RecAttendError('conv chain: unsupported number of layers {}'.format(n))
+    self.desc = _c.create_string_buffer(nbytes)  # host blob: plans + tensor maps, passed as the kernel argument
+    self.counter = torch.zeros(16, device=dev, dtype=torch.int32)  # one barrier counter per layer boundary
+    grid, smem = _c.c_int(0), _c.c_size_t(0)
+    _lib.call('ra_conv3x3_umma_chain_prepare', _c.byref(arr), n, self.desc, _c.byref(grid), _c.byref(smem))
+    self.grid, self.smem = grid.value, smem.value
+
+  def run(self):
+    _lib.call('ra_conv3x3_umma_chain_run', self.desc, self.n, self.grid, self.smem, _p(self.counter), _stream())
+
+
 def concat_channels(a, b=None, c=None, out=None):
   _chk(a, b, c, out)
   B, H, W, Ca = a.shape

@@ -752,3 +752,47 @@ def test_iou_soft_hard_tensor_core(cuda, B, T, H, W):
     assert rel_err(soft, old) < 2e-5
   # H*W % 32 != 0: outside the kernel's range, the caller falls back to f_iou
   assert ops.f_iou_soft_hard(_g(a[:, :, :H - 1, :W - 1].copy()), _g(g[:, :, :H - 1, :W - 1].copy())) is None
+
+
+def test_conv_chain_equals_layer_by_layer(cuda):
+  """ra_conv3x3_umma_chain_*: the six attention-CNN layers and the first deconv layers of the KITTI patch network (skip
+  connections, transposed conv, pooling) in ONE persistent launch with grid barriers between the layers == the same
+  layers launched one by one (bit for bit: the same tile plans and kernels)."""
+  from rec_attend_b200 import ops
+  rng = np.random.default_rng(11)
+  B = 8
+  spec = [  # C1, C2 (skip = index of an earlier output or None), Cout, up, pool, size_in
+      (16, None, 16, 1, 1), (16, None, 32, 1, 2), (32, None, 32, 1, 1), (32, None, 64, 1, 2), (64, None, 64, 1, 1),
+      (64, None, 96, 1, 2), (96, None, 64, 2, 1), (64, 4, 64, 1, 1), (64, 3, 32, 2, 1), (32, 2, 32, 1, 1)]
+  x0 = _g(rng.standard_normal((B, 48, 48, 16)).astype(np.float32))
+  acts = [x0]
+  layers = []
+  for C1, skip, Cout, up, pool in spec:
+    x = acts[-1]
+    x2 = acts[skip + 1] if skip is not None else None
+    Bx, H, W, _ = x.shape
+    Cin = C1 + (0 if x2 is None else x2.shape[3])
+    assert x.shape[3] == C1 and (x2 is None or tuple(x2.shape[1:3]) == (H, W))
+    KC, NPc, nsp, _, rs = ops.umma_plan(Cin, Cout, H * up, W * up, pool, B)
+    w = (rng.standard_normal((3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(np.float32)
+    out = torch.empty((B, H * up // pool, W * up // pool, Cout), device='cuda')
+    layers.append({'x': x, 'x2': x2, 'wpack': _g(ops.pack_umma_weights(w, KC, NPc, nsp, rs)), 'Cout': Cout,
+                   'scale': _g(rng.uniform(0.5, 1.5, Cout).astype(np.float32)),
+                   'shift': _g(rng.standard_normal(Cout).astype(np.float32) * 0.1), 'pool': pool, 'relu': True,
+                   'upsample': up, 'out': out})
+    acts.append(out)
+  chain = ops.ConvChain(layers)
+  chain.run()
+  torch.cuda.synchronize()
+  got = [L['out'].clone() for L in layers]
+  for L in layers:
+    L['out'].zero_()
+  for L in layers:
+    ops.conv3x3_block_umma(L['x'], L['wpack'], L['Cout'], L['scale'], L['shift'], pool=L['pool'], relu=True, x2=L['x2'],
+                           upsample=L['upsample'], out=L['out'])
+  torch.cuda.synchronize()
+  for i, L in enumerate(layers):
+    assert torch.equal(got[i], L['out']), i
+  chain.run()  # a second run (barrier counter reset) gives the same again
+  torch.cuda.synchronize()
+  assert torch.equal(got[-1], layers[-1]['out'])
