@@ -225,15 +225,78 @@ __global__ void __launch_bounds__(256) controller_kernel(CtrlParams p) {
 // state, MLP activations and logits are exchanged through distributed shared memory.
 // CTA r also owns example r for the per-example work (read-out, softmax, head).
 // ------------------------------------------------------------------------------------------
+#ifdef RA_CTRL_PROF
+__device__ unsigned long long g_ctrl_prof[64];
+#define CTRL_PROF(i)                                                                   \
+  do {                                                                                 \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                         \
+      unsigned long long t_;                                                           \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                           \
+      g_ctrl_prof[i] = t_;                                                             \
+    }                                                                                  \
+  } while (0)
+#else
+#define CTRL_PROF(i) do {} while (0)
+#endif
 constexpr int kCl = 8;
 constexpr int kHd2 = 256;
 constexpr int kCf2 = 64;
 constexpr int kUnits = kHd2 / kCl;     // 32 hidden units per CTA
 constexpr int kKin = kCf2 + kHd2;      // 320 LSTM inputs
 
+// Cluster exchange primitives.  The CTAs of a cluster hand each other x, h, the MLP activations and the logits through
+// distributed shared memory.  A cluster-wide barrier per hand-over costs ~2 us here (barrier.cluster with release /
+// acquire semantics compiles to MEMBAR.ALL.GPU + CCTL.IVALL around the hardware barrier), four times per glimpse
+// iteration; instead every receiving buffer has an mbarrier and the senders deliver data and completion together
+// (st.async / cp.async.bulk shared::cta -> shared::cluster with mbarrier::complete_tx::bytes), so a CTA waits exactly
+// for the bytes it is going to read and nothing else.
+__device__ __forceinline__ uint32_t cl_smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t addr, int rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(rank));
+  return out;
+}
+__device__ __forceinline__ void cl_st_async(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void cl_bulk_push(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   remote_dst),
+               "r"(local_src), "r"(bytes), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void cl_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_arm(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "CL_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra CL_DONE_%=;\n\t"
+      "bra CL_WAIT_%=;\n\t"
+      "CL_DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// Hand-over protocol of one buffer and one phase: local stores + remote sends, then `cl_handover`: the block barrier
+// publishes the local part, one thread arms the mbarrier with the bytes the peers deliver (the transaction count may
+// run negative until then, the phase cannot complete before the arming arrival), everyone waits for the phase.
+__device__ __forceinline__ void cl_handover(uint32_t bar, uint32_t remote_bytes, uint32_t parity) {
+  __syncthreads();
+  if (threadIdx.x == 0) cl_mbar_arm(bar, remote_bytes);
+  cl_mbar_wait(bar, parity);
+}
+
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cluster_kernel(CtrlParams p, int B) {
-  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
-  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
+  CTRL_PROF(0);
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int r = (int)cluster.block_rank();
@@ -243,7 +306,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
   const int PS = (P + kCl - 1) / kCl;  // glimpse-map positions per CTA
   const int tid = threadIdx.x;
 
-  float *wg_s = smem;                          // [320][128]  (k, q*32+u)
+  float *wg_s = smem;                          // [320][32][4]  (k, u, gate q): one float4 per (input, unit)
   float *w0_s = wg_s + kKin * 4 * kUnits;      // [256][32]
   float *x_s = w0_s + kHd2 * kUnits;           // [64][8]
   float *h_s = x_s + kCf2 * kCl;               // [2][256][8]
@@ -254,206 +317,330 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
   float *part_s = b0_s + kUnits;               // [256]
   float *red_s = part_s + 256;                 // [32]
   float *out_s = red_s + 32;                   // [16]
+  __shared__ __align__(8) unsigned long long bars[4];  // x, h, t (MLP activations), lg (logits): one phase per iteration
+  const uint32_t bar_x = cl_smem_u32(&bars[0]), bar_h = cl_smem_u32(&bars[1]), bar_t = cl_smem_u32(&bars[2]),
+                 bar_lg = cl_smem_u32(&bars[3]);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) cl_mbar_init(cl_smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
-  // ---- one-time loads: my slice of the weights (float4 along the hidden-unit index, 8 loads in flight)
+  // ---- one-time loads: my slice of the weights, as asynchronous copies (cp.async) so that all 168 loads of a thread
+  // are in flight at once - the staging is bound by L2 latency, not bandwidth.  The gate weights are scattered
+  // element-wise into the [k][unit][gate] order (global reads stay coalesced along the unit index).
+  // The weights are not produced by the kernel in front of this one (the last controller convolution), so under
+  // programmatic dependent launch they are staged BEFORE griddepcontrol.wait, while that kernel drains.
   {
-    constexpr int kU = 8;
-    const int n4 = kKin * 4 * kUnits / 4;  // float4 items of wg_s
-    for (int base = tid; base < n4; base += 256 * kU) {
-      float4 v[kU];
-#pragma unroll
-      for (int u8 = 0; u8 < kU; ++u8) {
-        const int i4 = base + u8 * 256;
-        v[u8] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i4 < n4) {
-          const int col = (i4 * 4) % (4 * kUnits), k = (i4 * 4) / (4 * kUnits);
-          const int q = col / kUnits, u = col % kUnits;
-          const int j = r * kUnits + u;
-          v[u8] = (k < kCf2) ? __ldg(reinterpret_cast<const float4 *>(p.wx + ((size_t)q * kCf2 + k) * kHd2 + j))
-                             : __ldg(reinterpret_cast<const float4 *>(p.wh + ((size_t)q * kHd2 + (k - kCf2)) * kHd2 + j));
-        }
-      }
-#pragma unroll
-      for (int u8 = 0; u8 < kU; ++u8) {
-        const int i4 = base + u8 * 256;
-        if (i4 < n4) *reinterpret_cast<float4 *>(wg_s + i4 * 4) = v[u8];
-      }
+    const uint32_t wg_base = cl_smem_u32(wg_s), w0_base = cl_smem_u32(w0_s);
+    for (int i = tid; i < kKin * 4 * kUnits; i += 256) {
+      const int u = i % kUnits, q = (i / kUnits) % 4, k = i / (4 * kUnits);
+      const int j = r * kUnits + u;
+      const float *src = (k < kCf2) ? p.wx + ((size_t)q * kCf2 + k) * kHd2 + j
+                                    : p.wh + ((size_t)q * kHd2 + (k - kCf2)) * kHd2 + j;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(wg_base + (uint32_t)(((k * kUnits + u) * 4 + q) * 4)),
+                   "l"(src)
+                   : "memory");
     }
-    const int m4 = kHd2 * kUnits / 4;  // float4 items of w0_s
-    for (int base = tid; base < m4; base += 256 * kU) {
-      float4 v[kU];
-#pragma unroll
-      for (int u8 = 0; u8 < kU; ++u8) {
-        const int i4 = base + u8 * 256;
-        v[u8] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i4 < m4) {
-          const int u = (i4 * 4) % kUnits, k = (i4 * 4) / kUnits;
-          v[u8] = __ldg(reinterpret_cast<const float4 *>(p.gw0 + (size_t)k * kHd2 + r * kUnits + u));
-        }
-      }
-#pragma unroll
-      for (int u8 = 0; u8 < kU; ++u8) {
-        const int i4 = base + u8 * 256;
-        if (i4 < m4) *reinterpret_cast<float4 *>(w0_s + i4 * 4) = v[u8];
-      }
+    for (int i4 = tid; i4 < kHd2 * kUnits / 4; i4 += 256) {
+      const int u = (i4 * 4) % kUnits, k = (i4 * 4) / kUnits;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(w0_base + (uint32_t)(i4 * 16)),
+                   "l"(p.gw0 + (size_t)k * kHd2 + r * kUnits + u)
+                   : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   if (tid < 4 * kUnits) bg_s[tid] = __ldg(p.bg + (tid / kUnits) * kHd2 + r * kUnits + (tid % kUnits));
   if (tid < kUnits) b0_s[tid] = __ldg(p.gb0 + r * kUnits + tid);
   for (int i = tid; i < 2 * kHd2 * kCl; i += 256) h_s[i] = 0.f;  // full_model.py:674
   for (int i = tid; i < PS * kCl; i += 256) lg_s[i] = 1.0f / (float)P;  // full_model.py:676-677
   float c_state = 0.f;  // cell state of (unit tid%32, example tid/32)
+  CTRL_PROF(1);
+  ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results (feat) are visible
+  ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   cluster.sync();
+  CTRL_PROF(2);
 
   const float *feat = p.feat + (size_t)(own ? e_glob : 0) * P * kCf2;
   for (int it = 0; it < p.n_iter; ++it) {
     const float *h_cur = h_s + (it & 1) * kHd2 * kCl;
     float *h_nxt_local = h_s + ((it + 1) & 1) * kHd2 * kCl;
+    const uint32_t ph = (uint32_t)(it & 1);
 
     // ---- step 1 (owner): glimpse map out, read-out x = sum_p feat[p][:] * map[p]; broadcast x
     if (own)
       for (int i = tid; i < P; i += 256) p.gmap_out[((size_t)e_glob * p.n_iter + it) * P + i] = lg_s[i];
     {
-      const int c = tid % kCf2, sl = tid / kCf2;  // 4 slices over p
-      float a = 0.f;
+      // 16 slices over p x 16 channel quads: a warp reads two whole feature rows (512 contiguous bytes) per load and
+      // every thread keeps 8 independent 16-byte loads in flight - the 128 KB of features do not fit in what is left of
+      // L1 beside the weights, so every glimpse iteration streams them from L2 and the loop is bound by load latency.
+      // The partial sums go through the hidden-state buffer this iteration will overwrite in step 2.
+      const int c4 = tid % (kCf2 / 4), sl = tid / (kCf2 / 4);
+      constexpr int kSl = 256 / (kCf2 / 4);  // 16
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (own) {
-        // 8 independent loads in flight (the first iteration of a launch reads feat from L2, not L1)
-        float a4[8];
+        float4 a4[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a4[j] = 0.f;
+        for (int j = 0; j < 8; ++j) a4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 *f4 = reinterpret_cast<const float4 *>(feat) + c4;
         int q = sl;
-        for (; q + 28 < P; q += 32) {
-          float f[8];
+        for (; q + 7 * kSl < P; q += 8 * kSl) {
+          float4 f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __ldg(feat + (size_t)(q + 4 * j) * kCf2 + c);
+          for (int j = 0; j < 8; ++j) f[j] = __ldg(f4 + (size_t)(q + kSl * j) * (kCf2 / 4));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a4[j] = fmaf(f[j], lg_s[q + 4 * j], a4[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float m = lg_s[q + kSl * j];
+            a4[j].x = fmaf(f[j].x, m, a4[j].x);
+            a4[j].y = fmaf(f[j].y, m, a4[j].y);
+            a4[j].z = fmaf(f[j].z, m, a4[j].z);
+            a4[j].w = fmaf(f[j].w, m, a4[j].w);
+          }
         }
-        for (; q < P; q += 4) a4[0] = fmaf(__ldg(feat + (size_t)q * kCf2 + c), lg_s[q], a4[0]);
-        a = ((a4[0] + a4[1]) + (a4[2] + a4[3])) + ((a4[4] + a4[5]) + (a4[6] + a4[7]));
+        for (; q < P; q += kSl) {
+          const float4 f = __ldg(f4 + (size_t)q * (kCf2 / 4));
+          const float m = lg_s[q];
+          a4[0].x = fmaf(f.x, m, a4[0].x);
+          a4[0].y = fmaf(f.y, m, a4[0].y);
+          a4[0].z = fmaf(f.z, m, a4[0].z);
+          a4[0].w = fmaf(f.w, m, a4[0].w);
+        }
+        a.x = ((a4[0].x + a4[1].x) + (a4[2].x + a4[3].x)) + ((a4[4].x + a4[5].x) + (a4[6].x + a4[7].x));
+        a.y = ((a4[0].y + a4[1].y) + (a4[2].y + a4[3].y)) + ((a4[4].y + a4[5].y) + (a4[6].y + a4[7].y));
+        a.z = ((a4[0].z + a4[1].z) + (a4[2].z + a4[3].z)) + ((a4[4].z + a4[5].z) + (a4[6].z + a4[7].z));
+        a.w = ((a4[0].w + a4[1].w) + (a4[2].w + a4[3].w)) + ((a4[4].w + a4[5].w) + (a4[6].w + a4[7].w));
       }
-      part_s[tid] = a;
+      *reinterpret_cast<float4 *>(h_nxt_local + sl * kCf2 + c4 * 4) = a;  // [16 slices][64 channels]
       __syncthreads();
       if (tid < kCf2) {
-        const float x = (part_s[tid] + part_s[tid + 64]) + (part_s[tid + 128] + part_s[tid + 192]);
+        float x = 0.f;
 #pragma unroll
-        for (int d = 0; d < kCl; ++d) cluster.map_shared_rank(x_s, d)[tid * kCl + r] = x;
+        for (int j = 0; j < kSl; j += 4)
+          x += (h_nxt_local[j * kCf2 + tid] + h_nxt_local[(j + 1) * kCf2 + tid]) +
+               (h_nxt_local[(j + 2) * kCf2 + tid] + h_nxt_local[(j + 3) * kCf2 + tid]);
+        x_s[tid * kCl + r] = x;
+        const uint32_t dst = cl_smem_u32(x_s + tid * kCl + r);
+#pragma unroll
+        for (int d = 1; d < kCl; ++d) {
+          const int peer = (r + d) % kCl;
+          cl_st_async(cl_mapa(dst, peer), x, cl_mapa(bar_x, peer));
+        }
       }
     }
-    cluster.sync();
+    cl_handover(bar_x, (kCl - 1) * kCf2 * 4, ph);
+    CTRL_PROF(3 + it * 5);
 
     // ---- step 2: LSTM gates of my 32 units for the 8 examples (nnlib.py:641-647)
+    // [8 x 320] x [320 x 128] per CTA.  A lane owns ONE hidden unit: its four gate weights of input k are one float4 and
+    // are applied to all 8 examples (32 accumulators), so every weight is read from shared memory exactly once.  Warp w
+    // covers units [8 (w & 3), +8) and the k-half (w >> 2); its four quarter-warps interleave k (k = 4 i + quarter), so
+    // the 8-example vectors of four consecutive inputs are one conflict-free 128-byte read.  The quarters are combined
+    // by a transposing shuffle reduction (each lane ends with one gate x 8 examples), the halves through t_s.
     {
-      const int col = tid % (4 * kUnits), kh = tid / (4 * kUnits);  // 2 halves of the 320 inputs
-      float acc[kCl];
+      const int lane = tid & 31, wid = tid >> 5;
+      const int ug = wid & 3, kh = wid >> 2, qq = lane >> 3, ul = lane & 7;
+      const int ucol = ug * 8 + ul;
+      float acc[32];
 #pragma unroll
-      for (int e = 0; e < kCl; ++e) acc[e] = 0.f;
-      const int k0 = kh * (kKin / 2);
-#pragma unroll 4
-      for (int k = k0; k < k0 + kKin / 2; ++k) {
-        const float w = wg_s[k * (4 * kUnits) + col];
-        const float *v = (k < kCf2) ? (x_s + k * kCl) : (h_cur + (k - kCf2) * kCl);
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      const float *hv = h_cur - kCf2 * kCl;  // so that input k >= 64 indexes hv[k * 8]
+      const int kbase = kh * (kKin / 2) + qq;
+#pragma unroll 2
+      for (int i = 0; i < kKin / 8; ++i) {
+        const int k = kbase + 4 * i;
+        const float4 w = *reinterpret_cast<const float4 *>(wg_s + ((size_t)k * kUnits + ucol) * 4);
+        const float *v = ((k < kCf2) ? x_s : hv) + k * kCl;
         const float4 v0 = *reinterpret_cast<const float4 *>(v);
         const float4 v1 = *reinterpret_cast<const float4 *>(v + 4);
-        acc[0] = fmaf(w, v0.x, acc[0]);
-        acc[1] = fmaf(w, v0.y, acc[1]);
-        acc[2] = fmaf(w, v0.z, acc[2]);
-        acc[3] = fmaf(w, v0.w, acc[3]);
-        acc[4] = fmaf(w, v1.x, acc[4]);
-        acc[5] = fmaf(w, v1.y, acc[5]);
-        acc[6] = fmaf(w, v1.z, acc[6]);
-        acc[7] = fmaf(w, v1.w, acc[7]);
-      }
-      float *gp = t_s + (size_t)kh * (4 * kUnits) * kCl + col * kCl;  // [kh][col][e]
+        const float ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int e = 0; e < kCl; ++e) gp[e] = acc[e];
+        for (int q = 0; q < 4; ++q) {
+          acc[q * 8 + 0] = fmaf(ws[q], v0.x, acc[q * 8 + 0]);
+          acc[q * 8 + 1] = fmaf(ws[q], v0.y, acc[q * 8 + 1]);
+          acc[q * 8 + 2] = fmaf(ws[q], v0.z, acc[q * 8 + 2]);
+          acc[q * 8 + 3] = fmaf(ws[q], v0.w, acc[q * 8 + 3]);
+          acc[q * 8 + 4] = fmaf(ws[q], v1.x, acc[q * 8 + 4]);
+          acc[q * 8 + 5] = fmaf(ws[q], v1.y, acc[q * 8 + 5]);
+          acc[q * 8 + 6] = fmaf(ws[q], v1.z, acc[q * 8 + 6]);
+          acc[q * 8 + 7] = fmaf(ws[q], v1.w, acc[q * 8 + 7]);
+        }
+      }
+      if (it == 1) CTRL_PROF(42);
+      // quarters 0/1 keep gates 0,1 and quarters 2/3 gates 2,3; then even quarters the lower gate, odd the upper one
+      float r1[16], r2[8];
+      const bool up1 = (lane & 16) != 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float send = up1 ? acc[i] : acc[16 + i];
+        const float keep = up1 ? acc[16 + i] : acc[i];
+        r1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+      const bool up2 = (lane & 8) != 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float send = up2 ? r1[i] : r1[8 + i];
+        const float keep = up2 ? r1[8 + i] : r1[i];
+        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      float *gp = t_s + ((size_t)(kh * 4 + qq) * kCl) * kUnits + ucol;  // [k-half][gate][example][unit]
+#pragma unroll
+      for (int e = 0; e < kCl; ++e) gp[e * kUnits] = r2[e];
+      if (it == 1) CTRL_PROF(43);
       __syncthreads();
+      if (it == 1) CTRL_PROF(44);
       const int u = tid % kUnits, e = tid / kUnits;
       float g[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int cq = q * kUnits + u;
-        g[q] = (t_s[cq * kCl + e] + t_s[(4 * kUnits + cq) * kCl + e]) + bg_s[cq];
-      }
+      for (int q = 0; q < 4; ++q)
+        g[q] = (t_s[((size_t)q * kCl + e) * kUnits + u] + t_s[((size_t)(4 + q) * kCl + e) * kUnits + u]) +
+               bg_s[q * kUnits + u];
       const float gi = ra::sigmoidf_acc(g[0]);
       const float gf = ra::sigmoidf_acc(g[1]);
       const float go = ra::sigmoidf_acc(g[2]);
       const float uu = tanhf(g[3]);
       c_state = gf * c_state + gi * uu;
       const float hn = go * tanhf(c_state);
-      const int off = (int)(h_nxt_local - smem) + (r * kUnits + u) * kCl + e;
-#pragma unroll
-      for (int d = 0; d < kCl; ++d) cluster.map_shared_rank(smem, d)[off] = hn;
+      if (it == 1) CTRL_PROF(45);
+      // my block [32 units][8 examples] is 1 KB contiguous in every CTA's h buffer: one bulk push per peer
+      float *blk = h_nxt_local + (size_t)r * kUnits * kCl;
+      blk[u * kCl + e] = hn;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid >= 1 && tid < kCl) {
+        const int peer = (r + tid) % kCl;
+        cl_bulk_push(cl_mapa(cl_smem_u32(blk), peer), cl_smem_u32(blk), kUnits * kCl * 4, cl_mapa(bar_h, peer));
+      }
+      if (it == 1) CTRL_PROF(46);
     }
-    cluster.sync();
+    cl_handover(bar_h, (kCl - 1) * kUnits * kCl * 4, ph);
+    CTRL_PROF(4 + it * 5);
     if (it == p.n_iter - 1) break;  // the last glimpse map is dead compute (full_model.py:686-688)
     const float *h_new = h_nxt_local;
 
     // ---- step 3: glimpse MLP layer 0, my 32 columns x 8 examples: relu(h W0 + b0)
+    // lane = column, warp = a 32-input slice, every weight applied to all 8 examples; the slices are combined through
+    // the hidden-state buffer that died in step 2.
     {
-      const int u = tid % kUnits, e = tid / kUnits;
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < kHd2; k += 2) {
-        a0 = fmaf(h_new[k * kCl + e], w0_s[k * kUnits + u], a0);
-        a1 = fmaf(h_new[(k + 1) * kCl + e], w0_s[(k + 1) * kUnits + u], a1);
-      }
-      const float tv = fmaxf((a0 + a1) + b0_s[u], 0.f);
-      const int off = (int)(t_s - smem) + (r * kUnits + u) * kCl + e;
+      const int lane = tid & 31, wid = tid >> 5;
+      float acc[kCl];
 #pragma unroll
-      for (int d = 0; d < kCl; ++d) cluster.map_shared_rank(smem, d)[off] = tv;
+      for (int e = 0; e < kCl; ++e) acc[e] = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < kHd2 / 8; ++i) {
+        const int k = wid * (kHd2 / 8) + i;
+        const float w = w0_s[k * kUnits + lane];
+        const float4 v0 = *reinterpret_cast<const float4 *>(h_new + k * kCl);
+        const float4 v1 = *reinterpret_cast<const float4 *>(h_new + k * kCl + 4);
+        acc[0] = fmaf(v0.x, w, acc[0]);
+        acc[1] = fmaf(v0.y, w, acc[1]);
+        acc[2] = fmaf(v0.z, w, acc[2]);
+        acc[3] = fmaf(v0.w, w, acc[3]);
+        acc[4] = fmaf(v1.x, w, acc[4]);
+        acc[5] = fmaf(v1.y, w, acc[5]);
+        acc[6] = fmaf(v1.z, w, acc[6]);
+        acc[7] = fmaf(v1.w, w, acc[7]);
+      }
+      float *scr = h_s + (it & 1) * kHd2 * kCl;  // [8 slices][8 examples][32 columns]
+#pragma unroll
+      for (int e = 0; e < kCl; ++e) scr[((size_t)wid * kCl + e) * kUnits + lane] = acc[e];
+      __syncthreads();
+      const int u = tid % kUnits, e = tid / kUnits;
+      float a = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; w8 += 2)
+        a += scr[((size_t)w8 * kCl + e) * kUnits + u] + scr[((size_t)(w8 + 1) * kCl + e) * kUnits + u];
+      const float tv = fmaxf(a + b0_s[u], 0.f);
+      __syncthreads();  // step 4 reuses scr after the cluster barrier, but keep the block-level hazard explicit
+      float *blk = t_s + (size_t)r * kUnits * kCl;
+      blk[u * kCl + e] = tv;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid >= 1 && tid < kCl) {
+        const int peer = (r + tid) % kCl;
+        cl_bulk_push(cl_mapa(cl_smem_u32(blk), peer), cl_smem_u32(blk), kUnits * kCl * 4, cl_mapa(bar_t, peer));
+      }
     }
-    cluster.sync();
+    cl_handover(bar_t, (kCl - 1) * kUnits * kCl * 4, ph);
+    CTRL_PROF(5 + it * 5);
 
     // ---- step 4: glimpse MLP layer 1 logits for my PS positions x 8 examples -> owner CTAs
-    // The weights come straight from global memory (no shared memory left for them): 8 independent loads are kept
-    // in flight, and when the CTA has at most 128 outputs the 256 inputs are split over two thread halves.
-    if (PS * kCl <= 128) {
-      const int o = tid & 127, kh = tid >> 7;
-      const int pos = o % PS, e = o / PS;
-      const int gp = r * PS + pos;
-      const bool live = o < PS * kCl && gp < P;
-      float a = 0.f;
-      if (live) {
-        const float *wq = p.gw1 + gp;
-        float a8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a8[j] = 0.f;
-        const int k0 = kh * (kHd2 / 2);
-        for (int k = k0; k < k0 + kHd2 / 2; k += 8) {
-          float wv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) wv[j] = __ldg(wq + (size_t)(k + j) * P);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a8[j] = fmaf(t_s[(k + j) * kCl + e], wv[j], a8[j]);
-        }
-        a = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
-      }
-      part_s[tid] = a;
-      __syncthreads();
-      if (live && kh == 0) cluster.map_shared_rank(lg_s, e)[gp] = (part_s[o] + part_s[o + 128]) + __ldg(p.gb1 + gp);
-    } else {
-      for (int o = tid; o < PS * kCl; o += 256) {
-        const int pos = o % PS, e = o / PS;
+    // The weights come straight from L2 (no shared memory left for them), each element exactly once per CTA: a thread
+    // owns one position and one slice of the 256 inputs, keeps 8 independent loads in flight and applies every weight
+    // to all 8 examples; the slices are combined through the dead hidden-state buffer of this iteration.
+    {
+      const int KS = (PS <= 64) ? 4 : (PS <= 128) ? 2 : 1;  // input slices; PS * KS <= 256 when PS <= 256
+      const int klen = kHd2 / KS;
+      float *scr = h_s + (it & 1) * kHd2 * kCl;             // h_cur: dead after step 2, [KS][PS][8] <= 2048 floats
+      for (int pbase = 0; pbase < PS; pbase += 256) {       // PS > 256 (very large maps): several passes, KS == 1
+        const int o = tid, np = min(PS - pbase, 256);
+        const int pos = pbase + o % np, ks = o / np;
         const int gp = r * PS + pos;
-        if (gp < P) {
-          const float *wq = p.gw1 + gp;
-          float a8[8];
+        const bool live = ks < KS && gp < P;
+        float acc[kCl];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a8[j] = 0.f;
-          for (int k = 0; k < kHd2; k += 8) {
+        for (int e = 0; e < kCl; ++e) acc[e] = 0.f;
+        if (live) {
+          const float *wq = p.gw1 + gp;
+          const int k0 = ks * klen;
+          for (int k = k0; k < k0 + klen; k += 8) {
             float wv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) wv[j] = __ldg(wq + (size_t)(k + j) * P);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a8[j] = fmaf(t_s[(k + j) * kCl + e], wv[j], a8[j]);
+            for (int j = 0; j < 8; ++j) {
+              const float4 t0 = *reinterpret_cast<const float4 *>(t_s + (k + j) * kCl);
+              const float4 t1 = *reinterpret_cast<const float4 *>(t_s + (k + j) * kCl + 4);
+              acc[0] = fmaf(t0.x, wv[j], acc[0]);
+              acc[1] = fmaf(t0.y, wv[j], acc[1]);
+              acc[2] = fmaf(t0.z, wv[j], acc[2]);
+              acc[3] = fmaf(t0.w, wv[j], acc[3]);
+              acc[4] = fmaf(t1.x, wv[j], acc[4]);
+              acc[5] = fmaf(t1.y, wv[j], acc[5]);
+              acc[6] = fmaf(t1.z, wv[j], acc[6]);
+              acc[7] = fmaf(t1.w, wv[j], acc[7]);
+            }
           }
-          cluster.map_shared_rank(lg_s, e)[gp] =
-              (((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]))) + __ldg(p.gb1 + gp);
+        }
+        if (KS == 1) {
+          if (live) {
+            const float bias = __ldg(p.gb1 + gp);
+            const uint32_t dst = cl_smem_u32(lg_s + gp);
+#pragma unroll
+            for (int e = 0; e < kCl; ++e) {
+              if (e == r)
+                lg_s[gp] = acc[e] + bias;
+              else
+                cl_st_async(cl_mapa(dst, e), acc[e] + bias, cl_mapa(bar_lg, e));
+            }
+          }
+        } else {
+          if (ks < KS) {
+            float *dst = scr + ((size_t)ks * np + (pos - pbase)) * kCl;
+            *reinterpret_cast<float4 *>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4 *>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+          }
+          __syncthreads();
+          for (int o2 = tid; o2 < np * kCl; o2 += 256) {
+            const int e = o2 / np, ps = o2 % np;
+            const int gq = r * PS + pbase + ps;
+            if (gq < P) {
+              float v = scr[(size_t)ps * kCl + e];
+              for (int s2 = 1; s2 < KS; ++s2) v += scr[((size_t)s2 * np + ps) * kCl + e];
+              v += __ldg(p.gb1 + gq);
+              if (e == r)
+                lg_s[gq] = v;
+              else
+                cl_st_async(cl_mapa(cl_smem_u32(lg_s + gq), e), v, cl_mapa(bar_lg, e));
+            }
+          }
         }
       }
     }
-    cluster.sync();
+    {
+      const int n_own = max(0, min(PS, P - r * PS));  // my own positions are plain local stores
+      cl_handover(bar_lg, (uint32_t)(P - n_own) * 4u, ph);
+    }
+    CTRL_PROF(6 + it * 5);
 
     // ---- step 5 (owner): softmax over the P positions (full_model.py:350-352)
     {
@@ -470,6 +657,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
       for (int q = tid; q < P; q += 256) lg_s[q] = lg_s[q] / lsum;
       __syncthreads();
     }
+    CTRL_PROF(7 + it * 5);
   }
 
   // ---- head (owner): ctrl_out = h Wc + bc, box parameters
@@ -487,11 +675,19 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(256) controller_cl
   __syncthreads();
   if (own && tid < 9) p.ctrl_out[(size_t)e_glob * 9 + tid] = out_s[tid];
   if (own && tid == 0) write_box(p, out_s, p.box_out + (size_t)e_glob * RA_BOX_STRIDE);
+  CTRL_PROF(40);
   cluster.sync();  // no CTA may exit while its shared memory can still be written remotely
+  CTRL_PROF(41);
 }
 
 
 }  // namespace
+
+#ifdef RA_CTRL_PROF
+extern "C" int ra_debug_ctrl_prof(unsigned long long *host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_ctrl_prof, sizeof(unsigned long long) * 64) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int ra_controller_step_f32(const float *feat, int B, int P, int Cf, int Hd, int n_iter,
                                       const float *lstm_wx, const float *lstm_wh, const float *lstm_b,
@@ -532,11 +728,12 @@ extern "C" int ra_controller_step_f32(const float *feat, int B, int P, int Cf, i
     const int PS = (P + kCl - 1) / kCl;
     const size_t smem2 = ((size_t)kKin * 4 * kUnits + kHd2 * kUnits + kCf2 * kCl + 3 * kHd2 * kCl + PS * kCl +
                           4 * kUnits + kUnits + 256 + 32 + 16) * sizeof(float);
-    if (smem2 <= 227 * 1024) {
+    constexpr size_t kDynMax = 227 * 1024 - 64;  // the kernel also holds 32 bytes of static shared memory (mbarriers)
+    if (smem2 <= kDynMax) {
       static bool attr2 = false;
       if (!attr2) {
         cudaError_t e = cudaFuncSetAttribute(controller_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             227 * 1024);
+                                             (int)kDynMax);
         if (e != cudaSuccess) {
           ra::set_last_error("cudaFuncSetAttribute(controller_cluster_kernel)", e);
           return RA_ERR_CUDA;

@@ -320,6 +320,12 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
             const float2 t2 = *reinterpret_cast<const float2 *>(xr + (ky * kWgTWP + kx) * CI_B);
             xv[0] = t2.x;
             xv[1] = t2.y;
+          } else if constexpr (RI == 4) {  // 16-byte aligned: CI_B and ti * RI are multiples of 4
+            const float4 t4 = *reinterpret_cast<const float4 *>(xr + (ky * kWgTWP + kx) * CI_B);
+            xv[0] = t4.x;
+            xv[1] = t4.y;
+            xv[2] = t4.z;
+            xv[3] = t4.w;
           } else {
 #pragma unroll
             for (int i = 0; i < RI; ++i) xv[i] = xr[(ky * kWgTWP + kx) * CI_B + i];
@@ -398,7 +404,10 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
     w.CI_B = 1;
     w.CO_B = 16;
   } else {
-    w.RI = w.RJ = 2;
+    // 4 x 4 register tiles: 144 FMAs per 10 16-byte shared-memory reads and one pixel's index arithmetic - the 2 x 2
+    // version (RA_WGRAD_TILE=2) spends as many issue slots on loads and addresses as on FMAs
+    static const int tile = getenv("RA_WGRAD_TILE") ? atoi(getenv("RA_WGRAD_TILE")) : 4;
+    w.RI = w.RJ = (tile == 2) ? 2 : 4;
     w.CI_B = Cin <= 16 ? 16 : 32;
     w.CO_B = Cout <= 16 ? 16 : 32;
   }
@@ -410,13 +419,14 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
   // tile: as wide as the map allows (64 / 32 / 16 columns), 256 pixels - 128 for the 32-wide channel blocks, whose two
   // stages must fit twice per SM
   w.TW = Wo > 32 ? 64 : (Wo > 16 ? 32 : 16);
-  const int pix = (w.CI_B > 16 || w.CO_B > 16) ? 128 : 256;
+  const int pix = (w.RI != 4 && (w.CI_B > 16 || w.CO_B > 16)) ? 128 : 256;
   w.TH = pix / w.TW;
   const size_t stage = ((size_t)(w.TH + 2) * (w.TW + 2) * w.CI_B + (size_t)w.TH * w.TW * w.CO_B) * sizeof(float);
   const size_t red = ((size_t)w.PG * 9 * w.CI_B * w.CO_B + (size_t)w.PG * w.CO_B) * sizeof(float);
   w.smem = 2 * stage > red ? 2 * stage : red;
   const size_t n_tiles = (size_t)N * ((Ho + w.TH - 1) / w.TH) * ((Wo + w.TW - 1) / w.TW);
-  size_t cap = (size_t)ra::kNumSMs * 2 / ((size_t)w.n_ci_blk * w.n_co_blk);
+  // resident CTAs per SM: 2 (register / shared-memory bound), 1 for the 4 x 4 tiles (~180 registers per thread)
+  size_t cap = (size_t)ra::kNumSMs * (w.RI == 4 ? 1 : 2) / ((size_t)w.n_ci_blk * w.n_co_blk);
   if (cap < 16) cap = 16;
   w.ctas = (int)(n_tiles < cap ? (n_tiles < 1 ? 1 : n_tiles) : cap);
   return w;
@@ -569,12 +579,15 @@ extern "C" int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(conv_bwd_weight_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_bwd_weight_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     attr_done = true;
   }
   const dim3 grid(chunks, w.n_ci_blk * w.n_co_blk);
   if (w.RI == 2)
     conv_bwd_weight_kernel<2, 2><<<grid, kT, w.smem, s>>>(p);
+  else if (w.RI == 4)
+    conv_bwd_weight_kernel<4, 4><<<grid, kT, w.smem, s>>>(p);
   else
     conv_bwd_weight_kernel<1, 4><<<grid, kT, w.smem, s>>>(p);
   int rc = ra::finish_launch("conv_bwd_weight_kernel");

@@ -790,8 +790,24 @@ class FullModel(_ModelBase):
     cur = torch.cuda.current_stream()
     (tl, br, box_gt, rect, area), gt_side = gt
     B, T = s_gt.shape
-    # both matchings (boxes, masks) in ONE launch of 2B warps: they are independent and latency-bound
     iou_both = torch.empty((2 * B, T, T), device=s_gt.device, dtype=torch.float32)
+    # The box branch (pixel IoU of the attention boxes against the GT rectangles -> Hungarian) does not depend on the
+    # mask branch (soft IoU -> Hungarian): inside a captured graph it runs as a parallel branch, so the two
+    # latency-bound matchings (one warp per example) overlap each other and the mask IoU.
+    def box_branch():
+      if iou_box_steps is None:
+        ib = ops.f_iou(bufs['attn_box'], None, b_rect=rect, out=iou_both[:B])
+      else:  # use_knob: the per-step IoUs of the decode loop (full_model.py:926-929)
+        iou_both[:B].copy_(iou_box_steps)
+        ib = iou_both[:B]
+      return ib, ops.f_segm_match(ib, s_gt)
+
+    box_side = self._side_stream(bufs, 2)
+    if box_side is not None:
+      with torch.cuda.stream(box_side):
+        if gt_side is not None:
+          box_side.wait_stream(gt_side)
+        iou_box, match_box = box_branch()
     # soft IoU (matching) + hard IoU / DICE (statistics, full_model.py:1063-1081) in one pass over y_out and y_gt on
     # the tensor cores; shapes outside that kernel's range take the CUDA-core kernel twice (the hard statistics do
     # not feed the matching: a parallel branch)
@@ -806,19 +822,16 @@ class FullModel(_ModelBase):
       else:
         with torch.cuda.stream(side):
           iou_hard, dice = ops.f_iou(bufs['y_out'], y_gt, hard_threshold=0.5, want_dice=True)
-    if gt_side is not None:
-      cur.wait_stream(gt_side)
-    if iou_box_steps is None:
-      iou_box = ops.f_iou(bufs['attn_box'], None, b_rect=rect, out=iou_both[:B])
-    else:  # use_knob: the per-step IoUs of the decode loop (full_model.py:926-929)
-      iou_both[:B].copy_(iou_box_steps)
-      iou_box = iou_both[:B]
-    if fused is None:
       iou_soft = ops.f_iou(bufs['y_out'], y_gt, out=iou_both[B:])
     else:
       iou_soft, iou_hard, dice = fused
-    match_both = ops.f_segm_match(iou_both, torch.cat([s_gt, s_gt], 0))
-    match_box, match = match_both[:B], match_both[B:]
+    if gt_side is not None:
+      cur.wait_stream(gt_side)
+    match = ops.f_segm_match(iou_soft, s_gt)
+    if box_side is None:
+      iou_box, match_box = box_branch()
+    else:
+      cur.wait_stream(box_side)
     if side is not None:
       cur.wait_stream(side)
     scal = ops.loss_block(iou_box, match_box, iou_soft, match, iou_hard, dice, bufs['s_out'], s_gt, area,
