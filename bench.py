@@ -204,6 +204,9 @@ class OpTimer(object):
       if name == 'ra_bn_train_block_bwd_grouped_f32':
         # args: raw,dy,gamma,beta,mean,var,G,B,H,W,C,pool,...
         key = 'bn_bwd[G{} B{} {}x{}x{} pool{}]'.format(args[6], args[7], args[8], args[9], args[10], args[11])
+      if name == 'ra_bn_train_block_f32':
+        # args: x,B,H,W,C,gamma,beta,eps,decay,pool,relu,...
+        key = 'bn_fwd[B{} {}x{}x{} pool{}]'.format(args[1], args[2], args[3], args[4], args[9])
       d = agg.setdefault(key, {'entry': name, 'tag': tag, 'ms': 0.0, 'n': 0})
       d['ms'] += e0.elapsed_time(e1)
       d['n'] += 1

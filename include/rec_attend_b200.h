@@ -468,6 +468,12 @@ int ra_controller_bwd_f32(const float *feat, int B, int P, int Cf, int Hd, int n
                           float *dA1, float *dLog, void *stream);
 int ra_outer_sum_f32(const float *A, size_t a_stride, int n_in, const float *D, size_t d_stride, int n_out, int R,
                      float *dW, float *db, void *stream);
+/* The same sum with the rows split over up to 32 chunks of CTAs (a [64,256] gradient over 3200 rows is 4 CTAs
+ * otherwise); ws = ra_outer_sum_workspace(n_in, n_out, R) bytes of scratch for the per-chunk partials (0: no split
+ * needed, ws may be NULL), which are added in chunk order - deterministic. */
+size_t ra_outer_sum_workspace(int n_in, int n_out, int R);
+int ra_outer_sum_ex_f32(const float *A, size_t a_stride, int n_in, const float *D, size_t d_stride, int n_out, int R,
+                        void *ws, float *dW, float *db, void *stream);
 
 /* --------------------------------------------------------------------------------------
  * Foreground / orientation FCN head + loss block — fg_model.py:174-236 (the

@@ -75,6 +75,7 @@ _SIGNATURES = {
     'ra_controller_head_bwd_f32': [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P],
     'ra_controller_bwd_f32': [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'ra_outer_sum_f32': [_P, _Z, _I, _P, _Z, _I, _I, _P, _P, _P],
+    'ra_outer_sum_ex_f32': [_P, _Z, _I, _P, _Z, _I, _I, _P, _P, _P, _P],
     'ra_bn_train_block_bwd_grouped_f32': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     'ra_conv3x3_bwd_weight_ex_f32': [_P, _I, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     'ra_paste_back_bwd_ex_f32': [_P, _P, _Z, _I, _Z, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P,
@@ -106,7 +107,8 @@ EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last
                                          'ra_iou_loss_bwd_workspace', 'ra_paste_back_bwd_workspace',
                                          'ra_gaussian_extract_bwd_workspace', 'ra_controller_tape_floats',
                                          'ra_bn_train_block_bwd_grouped_workspace', 'ra_weight_decay_workspace',
-                                         'ra_pairwise_iou_umma_workspace', 'ra_conv3x3_umma_chain_desc_bytes'])
+                                         'ra_pairwise_iou_umma_workspace', 'ra_conv3x3_umma_chain_desc_bytes',
+                                         'ra_outer_sum_workspace'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -154,6 +156,8 @@ def lib():
     l.ra_bn_train_block_bwd_grouped_workspace.restype = _Z
     l.ra_pairwise_iou_umma_workspace.argtypes = [_I, _I, _I, _I]
     l.ra_pairwise_iou_umma_workspace.restype = _Z
+    l.ra_outer_sum_workspace.argtypes = [_I, _I, _I]
+    l.ra_outer_sum_workspace.restype = _Z
     l.ra_conv3x3_umma_chain_desc_bytes.argtypes = [_I]
     l.ra_conv3x3_umma_chain_desc_bytes.restype = _Z
     l.ra_weight_decay_workspace.argtypes = []

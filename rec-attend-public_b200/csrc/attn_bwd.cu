@@ -116,57 +116,115 @@ __global__ void __launch_bounds__(kT) pb_row_kernel(const float *__restrict__ d_
   }
 }
 
-// thread per column x: A[:, x] = Fy^T dV[:, x] in registers, stored; d_fx[:, x] = P^T A[:, x]
+// Column pass as two small tiled GEMMs per (example, 128-column tile):
+//   A[i,x]    = sum_{y in union y-band} fy[i,y] dV[y,x]     (F x 128 tile, rows staged 32 at a time in shared memory)
+//   d_fx[j,x] = sum_i P[i,j] A[i,x]                          (A tile kept in shared memory)
+// 256 threads = 8 tap groups x 32 column quads; a thread owns kPcTI taps x 4 columns (F <= 8 * kPcTI = 64).
+constexpr int kPcTX = 128, kPcTY = 32, kPcTI = 8;
+constexpr int kPcFS = kMaxF + 4;  // row stride of fy_s: 16-byte aligned rows, 4-way instead of 32-way conflicts on the fill
 __global__ void __launch_bounds__(kT) pb_col_kernel(const float *__restrict__ dV, const float *__restrict__ fy,
                                                     const float *__restrict__ patch, const float *__restrict__ box,
                                                     int box_stride, int H, int W, int F,
                                                     int accumulate, float *__restrict__ A, float *__restrict__ d_fx) {
-  extern __shared__ float P_s[];  // [F][F]
+  extern __shared__ __align__(16) float pc_sm[];
+  float *P_s = pc_sm;                      // [F][F]  (patch != nullptr)
+  float *fy_s = P_s + kMaxF * kMaxF;       // [kPcTY][kPcFS]   fy_s[yy][i]
+  float *dv_s = fy_s + kPcTY * kPcFS;      // [kPcTY][kPcTX]
+  float *A_s = dv_s + kPcTY * kPcTX;       // [kMaxF][kPcTX]
   const int b = blockIdx.y;
+  const int x0 = blockIdx.x * kPcTX;
   int xlo = 0, xhi = W - 1, ylo = 0, yhi = H - 1;
   if (box != nullptr) {
     ra::band_union(box + (size_t)b * box_stride, 0, F, H, &ylo, &yhi);
     ra::band_union(box + (size_t)b * box_stride, 1, F, W, &xlo, &xhi);
   }
-  const int x = blockIdx.x * kT + threadIdx.x;
-  {
-    const int c0 = blockIdx.x * kT;
-    if (c0 > xhi || c0 + kT - 1 < xlo) {  // no tap reaches these columns: d_fx[:, x] = 0, A is never read there
-      if (!accumulate && x < W)
-        for (int j = 0; j < F; ++j) d_fx[((size_t)b * F + j) * W + x] = 0.f;
-      return;
-    }
+  if (x0 > xhi || x0 + kPcTX - 1 < xlo) {  // no tap reaches these columns: d_fx[:, x] = 0, A is never read there
+    if (!accumulate)
+      for (int k = threadIdx.x; k < F * kPcTX; k += kT) {
+        const int j = k / kPcTX, x = x0 + k % kPcTX;
+        if (x < W) d_fx[((size_t)b * F + j) * W + x] = 0.f;
+      }
+    return;
   }
   if (patch != nullptr)
     for (int i = threadIdx.x; i < F * F; i += kT) P_s[i] = patch[(size_t)b * F * F + i];
-  __syncthreads();
-  if (x >= W) return;
-  if (x < xlo || x > xhi) {
-    if (!accumulate)
-      for (int j = 0; j < F; ++j) d_fx[((size_t)b * F + j) * W + x] = 0.f;
-    return;
-  }
-  float acc[kMaxF];
+  const int tg = threadIdx.x / 32, xq = threadIdx.x % 32;  // taps [tg * kPcTI, +kPcTI), columns x0 + 4 xq ..
+  float acc[kPcTI][4];
 #pragma unroll
-  for (int i = 0; i < kMaxF; ++i) acc[i] = 0.f;
+  for (int t = 0; t < kPcTI; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
   const float *fyb = fy + (size_t)b * F * H;
-  for (int y = ylo; y <= yhi; ++y) {
-    const float v = dV[((size_t)b * H + y) * W + x];
-    if (v == 0.f) continue;
+  const float *dvb = dV + (size_t)b * H * W;
+  for (int y0 = ylo; y0 <= yhi; y0 += kPcTY) {
+    const int ny = min(kPcTY, yhi - y0 + 1);
+    __syncthreads();
+    for (int k = threadIdx.x; k < kPcTY * kMaxF; k += kT) {
+      const int i = k / kPcTY, yy = k % kPcTY;  // consecutive threads walk y: coalesced rows of fy
+      fy_s[yy * kPcFS + i] = (i < F && yy < ny) ? fyb[(size_t)i * H + y0 + yy] : 0.f;
+    }
+    for (int k = threadIdx.x; k < kPcTY * kPcTX; k += kT) {
+      const int yy = k / kPcTX, xx = k % kPcTX;
+      const int x = x0 + xx;
+      dv_s[k] = (yy < ny && x >= xlo && x <= xhi) ? dvb[(size_t)(y0 + yy) * W + x] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int yy = 0; yy < kPcTY; ++yy) {
+      const float4 v = *reinterpret_cast<const float4 *>(dv_s + yy * kPcTX + 4 * xq);
+      const float4 f0 = *reinterpret_cast<const float4 *>(fy_s + yy * kPcFS + tg * kPcTI);
+      const float4 f1 = *reinterpret_cast<const float4 *>(fy_s + yy * kPcFS + tg * kPcTI + 4);
+      const float fv[kPcTI] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-    for (int i = 0; i < kMaxF; ++i)
-      if (i < F) acc[i] = fmaf(fyb[(size_t)i * H + y], v, acc[i]);
+      for (int t = 0; t < kPcTI; ++t) {
+        acc[t][0] = fmaf(fv[t], v.x, acc[t][0]);
+        acc[t][1] = fmaf(fv[t], v.y, acc[t][1]);
+        acc[t][2] = fmaf(fv[t], v.z, acc[t][2]);
+        acc[t][3] = fmaf(fv[t], v.w, acc[t][3]);
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < kMaxF; ++i)
-    if (i < F) A[((size_t)b * F + i) * W + x] = acc[i];
-  for (int j = 0; j < F; ++j) {
-    float s = 0.f;
+  for (int t = 0; t < kPcTI; ++t) {
+    const int i = tg * kPcTI + t;
+    *reinterpret_cast<float4 *>(A_s + i * kPcTX + 4 * xq) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    if (i < F) {
+      float *dst = A + ((size_t)b * F + i) * W + x0 + 4 * xq;
 #pragma unroll
-    for (int i = 0; i < kMaxF; ++i)
-      if (i < F) s = (patch != nullptr) ? fmaf(P_s[i * F + j], acc[i], s) : (s + acc[i]);
-    float *dst = d_fx + ((size_t)b * F + j) * W + x;
-    *dst = accumulate ? (*dst + s) : s;
+      for (int c = 0; c < 4; ++c)
+        if (x0 + 4 * xq + c < W) dst[c] = acc[t][c];
+    }
+  }
+  __syncthreads();
+  // d_fx tile: thread owns taps j in [tg * kPcTI, +kPcTI) x the same 4 columns
+#pragma unroll
+  for (int t = 0; t < kPcTI; ++t)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+  for (int i = 0; i < F; ++i) {
+    const float4 av = *reinterpret_cast<const float4 *>(A_s + i * kPcTX + 4 * xq);
+#pragma unroll
+    for (int t = 0; t < kPcTI; ++t) {
+      const int j = tg * kPcTI + t;
+      const float pv = (patch != nullptr) ? ((j < F) ? P_s[i * F + j] : 0.f) : 1.0f;
+      acc[t][0] = fmaf(pv, av.x, acc[t][0]);
+      acc[t][1] = fmaf(pv, av.y, acc[t][1]);
+      acc[t][2] = fmaf(pv, av.z, acc[t][2]);
+      acc[t][3] = fmaf(pv, av.w, acc[t][3]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < kPcTI; ++t) {
+    const int j = tg * kPcTI + t;
+    if (j >= F) continue;
+    float *dst = d_fx + ((size_t)b * F + j) * W + x0 + 4 * xq;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int x = x0 + 4 * xq + c;
+      if (x >= W) continue;
+      const float v = (x >= xlo && x <= xhi) ? acc[t][c] : 0.f;
+      dst[c] = accumulate ? (dst[c] + v) : v;
+    }
   }
 }
 
@@ -401,6 +459,98 @@ __global__ void __launch_bounds__(kT) ex_dfy_kernel(const float *__restrict__ xs
   }
 }
 
+// ---- d_fy by the other contraction order (used when H <= W, so that U fits the second half of the workspace):
+//   U[b,y,j,c] = sum_{x in band_j} X[b,y,x,c] fx[b,j,x]        (the forward's column pass applied to the image rows)
+//   d_fy[b,i,y] = gamma * sum_{j,c} G[b,i,j,ch(c)] U[b,y,j,c]   for y in band_i
+// U costs |rows| * sum_j |band_j| * D MACs per example and is shared by all F taps i, where the S formulation rebuilds
+// an [x,c] plane of F-term sums for every (example, tap).
+// grid (H, B): one CTA per image row inside the union y-band; slab [x][c] of the row in shared memory.
+__global__ void __launch_bounds__(kT) ex_U_kernel(const float *__restrict__ xs, int Cs, int xs_bmod,
+                                                  const float *__restrict__ canvas, const float *__restrict__ fx,
+                                                  const float *__restrict__ box, int H, int W, int F, int D,
+                                                  float *__restrict__ U) {
+  extern __shared__ float sm[];  // slab [nx][D] | band_s [F][2]
+  const int y = blockIdx.x, b = blockIdx.y;
+  int ylo, yhi, xlo, xhi;
+  axis_union(box, b, 0, F, H, &ylo, &yhi);
+  if (y < ylo || y > yhi) return;  // no tap reads this row
+  axis_union(box, b, 1, F, W, &xlo, &xhi);
+  const int nx = xhi - xlo + 1;
+  if (nx <= 0) return;
+  float *slab = sm;
+  int *band_s = reinterpret_cast<int *>(sm + (size_t)W * D);
+  for (int j = threadIdx.x; j < F; j += kT) axis_tap(box, b, 1, j, F, W, &band_s[2 * j], &band_s[2 * j + 1]);
+  const int bx = xs_bmod > 0 ? b % xs_bmod : b;
+  if (Cs > 0) {
+    const float *row = xs + (((size_t)bx * H + y) * W + xlo) * Cs;
+    for (int k = threadIdx.x; k < nx * Cs; k += kT) {
+      const int x = k / Cs, c = k - x * Cs;
+      slab[x * D + c] = __ldg(row + k);
+    }
+  }
+  if (D > Cs) {
+    const float *row = canvas + ((size_t)b * H + y) * W + xlo;
+    for (int x = threadIdx.x; x < nx; x += kT) slab[x * D + Cs] = __ldg(row + x);
+  }
+  __syncthreads();
+  const float *fxb = fx + (size_t)b * F * W;
+  float *dst = U + ((size_t)b * H + y) * F * D;
+  for (int idx = threadIdx.x; idx < F * D; idx += kT) {
+    const int j = idx / D, c = idx - j * D;
+    const int lo = max(band_s[2 * j], xlo), hi = min(band_s[2 * j + 1], xhi);
+    const float *fj = fxb + (size_t)j * W;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int x = lo;
+    for (; x + 3 <= hi; x += 4) {
+      a0 = fmaf(slab[(x - xlo) * D + c], __ldg(fj + x), a0);
+      a1 = fmaf(slab[(x + 1 - xlo) * D + c], __ldg(fj + x + 1), a1);
+      a2 = fmaf(slab[(x + 2 - xlo) * D + c], __ldg(fj + x + 2), a2);
+      a3 = fmaf(slab[(x + 3 - xlo) * D + c], __ldg(fj + x + 3), a3);
+    }
+    for (; x <= hi; ++x) a0 = fmaf(slab[(x - xlo) * D + c], __ldg(fj + x), a0);
+    dst[idx] = (a0 + a1) + (a2 + a3);
+  }
+}
+
+// grid (i, b): d_fy[b,i,y] (+)= gamma * <G[b,i,:,:], U[b,y,:,:]> for y in band_i (zero elsewhere); one warp per row.
+__global__ void __launch_bounds__(kT) ex_dfy_from_U_kernel(const float *__restrict__ G, int cstride,
+                                                           const int *__restrict__ chan_map, const float *__restrict__ U,
+                                                           const float *__restrict__ gamma, int gamma_stride,
+                                                           const float *__restrict__ box, int H, int F, int D,
+                                                           int accumulate, float *__restrict__ d_fy) {
+  extern __shared__ float G_s[];  // [F (j)][D], source-channel order
+  const int i = blockIdx.x, b = blockIdx.y;
+  for (int k = threadIdx.x; k < F * D; k += kT) {
+    const int j = k / D, c = k - j * D;
+    G_s[k] = G[(((size_t)b * F + i) * F + j) * cstride + chan_map[c]];
+  }
+  int ylo, yhi, ulo, uhi;
+  axis_tap(box, b, 0, i, F, H, &ylo, &yhi);
+  axis_union(box, b, 0, F, H, &ulo, &uhi);  // rows outside the union were not produced (band_i lies inside it)
+  ylo = max(ylo, ulo);
+  yhi = min(yhi, uhi);
+  float *dst = d_fy + ((size_t)b * F + i) * H;
+  if (!accumulate)
+    for (int y = threadIdx.x; y < H; y += kT)
+      if (y < ylo || y > yhi) dst[y] = 0.f;
+  __syncthreads();
+  const float g = gamma[(size_t)b * gamma_stride];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = F * D;
+  for (int y = ylo + warp; y <= yhi; y += kT / 32) {
+    const float *u = U + ((size_t)b * H + y) * n;
+    float s0 = 0.f, s1 = 0.f;
+    int k = lane;
+    for (; k + 32 < n; k += 64) {
+      s0 = fmaf(G_s[k], __ldg(u + k), s0);
+      s1 = fmaf(G_s[k + 32], __ldg(u + k + 32), s1);
+    }
+    for (; k < n; k += 32) s0 = fmaf(G_s[k], __ldg(u + k), s0);
+    const float v = g * ra::warp_sum(s0 + s1);
+    if (lane == 0) dst[y] = accumulate ? (dst[y] + v) : v;
+  }
+}
+
 // d_gamma[b] = sum G * x_patch / gamma over the D real channels
 __global__ void __launch_bounds__(kT) ex_dgamma_kernel(const float *__restrict__ G, const float *__restrict__ x_patch,
                                                        int cstride, int D, int F, const float *__restrict__ gamma,
@@ -453,7 +603,17 @@ extern "C" int ra_paste_back_bwd_ex_f32(const float *d_out, const float *out, si
                                           box_stride, H, W, F, accumulate, dV, d_fy, rows);
   rc = ra::finish_launch("pb_row_kernel");
   if (rc != RA_OK) return rc;
-  pb_col_kernel<<<dim3(bx, B), kT, psm, s>>>(dV, fy, patch, box, box_stride, H, W, F, accumulate, A, d_fx);
+  {
+    const size_t csm = ((size_t)kMaxF * kMaxF + (size_t)kPcTY * kPcFS + (size_t)kPcTY * kPcTX + (size_t)kMaxF * kPcTX) *
+                       sizeof(float);  // 74 KB
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(pb_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm);
+      attr_done = true;
+    }
+    pb_col_kernel<<<dim3((W + kPcTX - 1) / kPcTX, B), kT, csm, s>>>(dV, fy, patch, box, box_stride, H, W, F, accumulate,
+                                                                     A, d_fx);
+  }
   rc = ra::finish_launch("pb_col_kernel");
   if (rc != RA_OK) return rc;
   const int pairs = d_patch ? F * F : 1;
@@ -511,11 +671,31 @@ extern "C" int ra_gaussian_extract_bwd_ex_f32(const float *xs, int Cs, int xs_bm
                                             accumulate, d_fx);
   rc = ra::finish_launch("ex_dfx_kernel");
   if (rc != RA_OK) return rc;
-  const size_t ysm = gsm + (size_t)kExChunk * D * sizeof(float) + (size_t)2 * F * sizeof(int);
-  ex_dfy_kernel<<<dim3(F, B), kT, ysm, s>>>(xs, Cs, xs_bmod, canvas, d_patch, patch_cstride, chan_map, fx, gamma,
-                                            gamma_stride, box, H, W, F, D, accumulate, d_fy);
-  rc = ra::finish_launch("ex_dfy_kernel");
-  if (rc != RA_OK) return rc;
+  const size_t usm = (size_t)W * D * sizeof(float) + (size_t)2 * F * sizeof(int);
+  if (H <= W && usm <= 160 * 1024 && getenv("RA_EX_DFY_S") == nullptr) {
+    if (usm > 48 * 1024) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(ex_U_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_done = true;
+      }
+    }
+    // U [B,H,F,D] lives in the second half of the workspace (B*F*W*D floats >= B*H*F*D when H <= W)
+    float *U = T + (size_t)B * F * W * D;
+    ex_U_kernel<<<dim3(H, B), kT, usm, s>>>(xs, Cs, xs_bmod, canvas, fx, box, H, W, F, D, U);
+    rc = ra::finish_launch("ex_U_kernel");
+    if (rc != RA_OK) return rc;
+    ex_dfy_from_U_kernel<<<dim3(F, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, U, gamma, gamma_stride, box, H, F,
+                                                     D, accumulate, d_fy);
+    rc = ra::finish_launch("ex_dfy_from_U_kernel");
+    if (rc != RA_OK) return rc;
+  } else {
+    const size_t ysm = gsm + (size_t)kExChunk * D * sizeof(float) + (size_t)2 * F * sizeof(int);
+    ex_dfy_kernel<<<dim3(F, B), kT, ysm, s>>>(xs, Cs, xs_bmod, canvas, d_patch, patch_cstride, chan_map, fx, gamma,
+                                              gamma_stride, box, H, W, F, D, accumulate, d_fy);
+    rc = ra::finish_launch("ex_dfy_kernel");
+    if (rc != RA_OK) return rc;
+  }
   ex_dgamma_kernel<<<B, kT, 0, s>>>(d_patch, x_patch, patch_cstride, D, F, gamma, gamma_stride, d_gamma);
   return ra::finish_launch("ex_dgamma_kernel");
 }

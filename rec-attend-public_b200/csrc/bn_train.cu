@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float *__r
     ctr[e] = center_s[cg * V + e];
     acc[e] = 0.f;
   }
-  // four independent loads in flight per thread (the big first-layer tensors are streamed from HBM)
-  constexpr int U = 4;
+  // eight independent loads in flight per thread (the big first-layer tensors are streamed from HBM)
+  constexpr int U = 8;
   const size_t stride = (size_t)gridDim.x * lanes;
   for (size_t p0 = (size_t)blockIdx.x * lanes + pl; pl < lanes && p0 < npix; p0 += U * stride) {
     float v[U][V];
@@ -172,7 +172,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
 int bn_ctas(size_t npix, int C) {
   const int lanes = kBnThreads / ((C & 3) ? C : C / 4);
   size_t want = (npix + lanes - 1) / lanes;
-  const size_t cap = (size_t)ra::kNumSMs;  // one CTA per SM at most: every CTA of the next pass re-reduces these partials
+  // every CTA of the next pass re-reduces these partials (ctas x C floats from L2), so their count is bounded by the
+  // channel count: 4 CTAs per SM for the wide 16-channel maps (which need the loads in flight to stream from HBM), one
+  // per SM from 64 channels on
+  size_t per_sm = (size_t)64 / (size_t)(C < 16 ? 16 : C);
+  if (per_sm < 1) per_sm = 1;
+  const size_t cap = (size_t)ra::kNumSMs * per_sm;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 

@@ -90,6 +90,164 @@ __global__ void __launch_bounds__(kT) bn_bwd_reduce_kernel(const float *__restri
   for (int i = threadIdx.x; i < 2 * C; i += kT) partial[(size_t)blockIdx.x * 2 * C + i] = acc_s[i];
 }
 
+// ---- float4 versions (C % 4 == 0, 16-byte aligned tensors, C / 4 divides 256): a thread owns one channel quad for the
+// whole launch (its BN parameters live in registers), walks pooled pixels with a fixed stride and keeps its partial sums
+// in registers (double); the CTA adds them in a fixed order - no atomics, no per-element index arithmetic.
+template <int POOL>
+__device__ __forceinline__ void pool_relu_route4(const float *__restrict__ raw, int W, int C, size_t base,
+                                                 const float inv[4], const float shift[4], int relu, const float4 dy4,
+                                                 float g[4], int pos[4], float rbest[4], float4 win[POOL * POOL]) {
+  float best[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    best[e] = -INFINITY;
+    rbest[e] = 0.f;
+    pos[e] = 0;
+  }
+#pragma unroll
+  for (int py = 0; py < POOL; ++py)
+#pragma unroll
+    for (int px = 0; px < POOL; ++px)
+      win[py * POOL + px] = __ldg(reinterpret_cast<const float4 *>(raw + base + ((size_t)py * W + px) * C));
+#pragma unroll
+  for (int q = 0; q < POOL * POOL; ++q) {
+    const float r4[4] = {win[q].x, win[q].y, win[q].z, win[q].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float z = fmaf(r4[e], inv[e], shift[e]);
+      if (z > best[e]) {  // strict: the first maximum wins
+        best[e] = z;
+        pos[e] = q;
+        rbest[e] = r4[e];
+      }
+    }
+  }
+  const float d4[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) g[e] = (relu && !(best[e] > 0.f)) ? 0.f : d4[e];
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(kT) bn_bwd_reduce4_kernel(const float *__restrict__ raw, const float *__restrict__ dy,
+                                                            const float *__restrict__ gamma,
+                                                            const float *__restrict__ beta,
+                                                            const float *__restrict__ mean,
+                                                            const float *__restrict__ var, int B, int H, int W, int C,
+                                                            int relu, float eps, double *__restrict__ partial) {
+  {
+    const size_t g = blockIdx.y;
+    raw += g * (size_t)B * H * W * C;
+    dy += g * (size_t)B * (H / POOL) * (W / POOL) * C;
+    gamma += g * C; beta += g * C; mean += g * C; var += g * C;
+    partial += g * (size_t)gridDim.x * 2 * C;
+  }
+  __shared__ double red_s[kT * 8];
+  const int cg_n = C >> 2, lanes = kT / cg_n;
+  const int cg = threadIdx.x % cg_n, pl = threadIdx.x / cg_n;
+  const int Ho = H / POOL, Wo = W / POOL;
+  const size_t npix = (size_t)B * Ho * Wo;
+  float inv[4], shift[4], mu[4], rstd[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = cg * 4 + e;
+    mu[e] = mean[c];
+    rstd[e] = rsqrtf(var[c] + eps);
+    inv[e] = gamma[c] * rstd[e];
+    shift[e] = beta[c] - mu[e] * inv[e];
+  }
+  double sb[4] = {0.0, 0.0, 0.0, 0.0}, sg[4] = {0.0, 0.0, 0.0, 0.0};
+  for (size_t p = (size_t)blockIdx.x * lanes + pl; p < npix; p += (size_t)gridDim.x * lanes) {
+    const int ox = (int)(p % Wo);
+    const size_t q = p / Wo;
+    const int oy = (int)(q % Ho);
+    const int b = (int)(q / Ho);
+    const size_t base = (((size_t)b * H + (size_t)oy * POOL) * W + (size_t)ox * POOL) * C + cg * 4;
+    const float4 dy4 = __ldg(reinterpret_cast<const float4 *>(dy + p * C + cg * 4));
+    float g[4], rb[4];
+    int pos[4];
+    float4 win[POOL * POOL];
+    pool_relu_route4<POOL>(raw, W, C, base, inv, shift, relu, dy4, g, pos, rb, win);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float xhat = (rb[e] - mu[e]) * rstd[e];
+      sb[e] += (double)g[e];
+      sg[e] += (double)(g[e] * xhat);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    red_s[threadIdx.x * 8 + e] = sb[e];
+    red_s[threadIdx.x * 8 + 4 + e] = sg[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kT) {  // i = which * C + c
+    const int which = i / C, c = i - which * C;
+    double t = 0.0;
+    for (int l = 0; l < lanes; ++l) t += red_s[(l * cg_n + (c >> 2)) * 8 + which * 4 + (c & 3)];
+    partial[(size_t)blockIdx.x * 2 * C + i] = t;
+  }
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(kT) bn_bwd_apply4_kernel(const float *__restrict__ raw, const float *__restrict__ dy,
+                                                           const float *__restrict__ gamma,
+                                                           const float *__restrict__ beta,
+                                                           const float *__restrict__ mean, const float *__restrict__ var,
+                                                           const float *__restrict__ dgamma,
+                                                           const float *__restrict__ dbeta, int B, int H, int W, int C,
+                                                           int relu, float eps, float *__restrict__ d_raw) {
+  {
+    const size_t g = blockIdx.y;
+    raw += g * (size_t)B * H * W * C;
+    d_raw += g * (size_t)B * H * W * C;
+    dy += g * (size_t)B * (H / POOL) * (W / POOL) * C;
+    gamma += g * C; beta += g * C; mean += g * C; var += g * C; dgamma += g * C; dbeta += g * C;
+  }
+  const int cg_n = C >> 2, lanes = kT / cg_n;
+  const int cg = threadIdx.x % cg_n, pl = threadIdx.x / cg_n;
+  const int Ho = H / POOL, Wo = W / POOL;
+  const size_t npix = (size_t)B * Ho * Wo;
+  const float n = (float)((size_t)B * H * W);
+  float inv[4], shift[4], mu[4], rstd[4], db[4], dg[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = cg * 4 + e;
+    mu[e] = mean[c];
+    rstd[e] = rsqrtf(var[c] + eps);
+    inv[e] = gamma[c] * rstd[e];
+    shift[e] = beta[c] - mu[e] * inv[e];
+    db[e] = dbeta[c];
+    dg[e] = dgamma[c];
+  }
+  for (size_t p = (size_t)blockIdx.x * lanes + pl; p < npix; p += (size_t)gridDim.x * lanes) {
+    const int ox = (int)(p % Wo);
+    const size_t q = p / Wo;
+    const int oy = (int)(q % Ho);
+    const int b = (int)(q / Ho);
+    const size_t base = (((size_t)b * H + (size_t)oy * POOL) * W + (size_t)ox * POOL) * C + cg * 4;
+    const float4 dy4 = __ldg(reinterpret_cast<const float4 *>(dy + p * C + cg * 4));
+    float g[4], rb[4];
+    int pos[4];
+    float4 win[POOL * POOL];
+    pool_relu_route4<POOL>(raw, W, C, base, inv, shift, relu, dy4, g, pos, rb, win);
+#pragma unroll
+    for (int py = 0; py < POOL; ++py)
+#pragma unroll
+      for (int px = 0; px < POOL; ++px) {
+        const int w = py * POOL + px;
+        const float r4[4] = {win[w].x, win[w].y, win[w].z, win[w].w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xhat = (r4[e] - mu[e]) * rstd[e];
+          const float dbn = (w == pos[e]) ? g[e] : 0.f;
+          o[e] = inv[e] / n * (n * dbn - db[e] - xhat * dg[e]);
+        }
+        *reinterpret_cast<float4 *>(d_raw + base + ((size_t)py * W + px) * C) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+  }
+}
+
 // one CTA per (channel, group): the per-CTA partials are added by 128 threads (strided, then a fixed tree) in double
 __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double *__restrict__ partial, int ctas, int C,
                                                               float *__restrict__ dgamma, float *__restrict__ dbeta) {
@@ -509,23 +667,41 @@ extern "C" int ra_bn_train_block_bwd_grouped_f32(const float *raw, const float *
   const int ctas = bwd_ctas(total);
   double *partial = reinterpret_cast<double *>(ws);
   const size_t smem = (size_t)2 * C * sizeof(double);
-  if (pool == 2)
+  // float4 path: whole channel quads per thread (every conv layer of the model but the 1-channel mask layer)
+  const bool vec4 = (C & 3) == 0 && (kT % (C >> 2)) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(dy) |
+                      reinterpret_cast<uintptr_t>(d_raw)) & 15) == 0 && getenv("RA_BN_BWD_SCALAR") == nullptr;
+  if (vec4) {
+    if (pool == 2)
+      bn_bwd_reduce4_kernel<2><<<dim3(ctas, G), kT, 0, s>>>(raw, dy, gamma, beta, mean, var, B, H, W, C, relu, eps, partial);
+    else
+      bn_bwd_reduce4_kernel<1><<<dim3(ctas, G), kT, 0, s>>>(raw, dy, gamma, beta, mean, var, B, H, W, C, relu, eps, partial);
+  } else if (pool == 2) {
     bn_bwd_reduce_kernel<2><<<dim3(ctas, G), kT, smem, s>>>(raw, dy, gamma, beta, mean, var, B, H, W, C, relu, eps,
                                                             partial);
-  else
+  } else {
     bn_bwd_reduce_kernel<1><<<dim3(ctas, G), kT, smem, s>>>(raw, dy, gamma, beta, mean, var, B, H, W, C, relu, eps,
                                                             partial);
+  }
   int rc = ra::finish_launch("bn_bwd_reduce_kernel");
   if (rc != RA_OK) return rc;
   bn_bwd_finalize_kernel<<<dim3(C, G), 128, 0, s>>>(partial, ctas, C, dgamma, dbeta);
   rc = ra::finish_launch("bn_bwd_finalize_kernel");
   if (rc != RA_OK) return rc;
-  if (pool == 2)
+  if (vec4) {
+    if (pool == 2)
+      bn_bwd_apply4_kernel<2><<<dim3(ctas, G), kT, 0, s>>>(raw, dy, gamma, beta, mean, var, dgamma, dbeta, B, H, W, C,
+                                                           relu, eps, d_raw);
+    else
+      bn_bwd_apply4_kernel<1><<<dim3(ctas, G), kT, 0, s>>>(raw, dy, gamma, beta, mean, var, dgamma, dbeta, B, H, W, C,
+                                                           relu, eps, d_raw);
+  } else if (pool == 2) {
     bn_bwd_apply_kernel<2><<<dim3(ctas, G), kT, 0, s>>>(raw, dy, gamma, beta, mean, var, dgamma, dbeta, B, H, W, C, relu,
                                                         eps, d_raw);
-  else
+  } else {
     bn_bwd_apply_kernel<1><<<dim3(ctas, G), kT, 0, s>>>(raw, dy, gamma, beta, mean, var, dgamma, dbeta, B, H, W, C, relu,
                                                         eps, d_raw);
+  }
   return ra::finish_launch("bn_bwd_apply_kernel");
 }
 

@@ -168,6 +168,21 @@ __global__ void controller_head_bwd_kernel(const float *__restrict__ ctrl_out, c
   d[8] = fixed ? 0.f : dg[2] * bo[RA_BOX_GAMMA_Y];
 }
 
+// lane-strided partial dot product of a global row with a shared-memory vector; warp_row_dot adds the warp reduction
+__device__ __forceinline__ float warp_row_partial(const float *__restrict__ row, const float *v_s, int n, int lane) {
+  float s0 = 0.f, s1 = 0.f;
+  int q = lane;
+  for (; q + 32 < n; q += 64) {
+    s0 = fmaf(__ldg(row + q), v_s[q], s0);
+    s1 = fmaf(__ldg(row + q + 32), v_s[q + 32], s1);
+  }
+  if (q < n) s0 = fmaf(__ldg(row + q), v_s[q], s0);
+  return s0 + s1;
+}
+__device__ __forceinline__ float warp_row_dot(const float *__restrict__ row, const float *v_s, int n, int lane) {
+  return ra::warp_sum(warp_row_partial(row, v_s, n, lane));
+}
+
 __global__ void controller_bwd_kernel(const float *__restrict__ feat, int P, int Cf, int Hd, int n_iter,
                                       const float *__restrict__ wx, const float *__restrict__ wh,
                                       const float *__restrict__ w0, const float *__restrict__ w1,
@@ -178,6 +193,7 @@ __global__ void controller_bwd_kernel(const float *__restrict__ feat, int P, int
   __shared__ float dh_s[kMaxHd], dc_s[kMaxHd], dpre_s[4 * kMaxHd], dmap_s[kMaxP], dlog_s[kMaxP], da1_s[kMaxHd],
       dgl_s[kMaxCf], red[32];
   const int b = blockIdx.x, j = threadIdx.x, nt = blockDim.x;
+  const int lane = j & 31, warp = j >> 5, nw = nt >> 5;
   const TapeLayout L{P, Cf, Hd};
   const float *fb = feat + (size_t)b * P * Cf;
   float *dfb = d_feat + (size_t)b * P * Cf;
@@ -205,18 +221,20 @@ __global__ void controller_bwd_kernel(const float *__restrict__ feat, int P, int
         dLog_k[p] = v;
       }
       __syncthreads();
-      for (int m = j; m < Hd; m += nt) {  // layer 1 (linear) then relu of layer 0
-        float s = 0.f;
-        for (int p = 0; p < P; ++p) s = fmaf(w1[(size_t)m * P + p], dlog_s[p], s);
+      // Every matrix-vector product below walks ROWS of a row-major weight matrix: one warp per row, lanes along the
+      // row (coalesced 128-byte reads), warp reduction - a thread per row would touch 32 different sectors per load.
+      for (int m = warp; m < Hd; m += nw) {  // layer 1 (linear) then relu of layer 0
+        float s = warp_row_dot(w1 + (size_t)m * P, dlog_s, P, lane);
         s = (rec[L.o_a1() + m] > 0.f) ? s : 0.f;
-        da1_s[m] = s;
-        dA1_k[m] = s;
+        if (lane == 0) {
+          da1_s[m] = s;
+          dA1_k[m] = s;
+        }
       }
       __syncthreads();
-      for (int m = j; m < Hd; m += nt) {  // a1 = relu(h_k W0 + b0): dh_k += W0 da1pre
-        float s = 0.f;
-        for (int q = 0; q < Hd; ++q) s = fmaf(w0[(size_t)m * Hd + q], da1_s[q], s);
-        dh_s[m] += s;
+      for (int m = warp; m < Hd; m += nw) {  // a1 = relu(h_k W0 + b0): dh_k += W0 da1pre
+        const float s = warp_row_dot(w0 + (size_t)m * Hd, da1_s, Hd, lane);
+        if (lane == 0) dh_s[m] += s;
       }
       __syncthreads();
     } else {  // the glimpse MLP of the last iteration is dead code (full_model.py:686-688)
@@ -244,27 +262,26 @@ __global__ void controller_bwd_kernel(const float *__restrict__ feat, int P, int
       dc_s[m] = dc * gf;  // dc_{k-1}
     }
     __syncthreads();
-    for (int m = j; m < Hd; m += nt) {  // dh_{k-1} = sum_g Wh[g] dpre_g
+    for (int m = warp; m < Hd; m += nw) {  // dh_{k-1} = sum_g Wh[g] dpre_g
       float s = 0.f;
-      for (int g = 0; g < 4; ++g)
-        for (int q = 0; q < Hd; ++q) s = fmaf(wh[((size_t)g * Hd + m) * Hd + q], dpre_s[g * Hd + q], s);
-      dh_s[m] = s;
+      for (int g = 0; g < 4; ++g) s += warp_row_partial(wh + ((size_t)g * Hd + m) * Hd, dpre_s + g * Hd, Hd, lane);
+      s = ra::warp_sum(s);
+      if (lane == 0) dh_s[m] = s;
     }
-    for (int c = j; c < Cf; c += nt) {  // dglimpse_k = sum_g Wx[g] dpre_g
+    for (int c = warp; c < Cf; c += nw) {  // dglimpse_k = sum_g Wx[g] dpre_g
       float s = 0.f;
-      for (int g = 0; g < 4; ++g)
-        for (int q = 0; q < Hd; ++q) s = fmaf(wx[((size_t)g * Cf + c) * Hd + q], dpre_s[g * Hd + q], s);
-      dgl_s[c] = s;
+      for (int g = 0; g < 4; ++g) s += warp_row_partial(wx + ((size_t)g * Cf + c) * Hd, dpre_s + g * Hd, Hd, lane);
+      s = ra::warp_sum(s);
+      if (lane == 0) dgl_s[c] = s;
     }
     __syncthreads();
     for (int i = j; i < P * Cf; i += nt) {  // glimpse = sum_p feat[p,:] map_k[p]
       const int p = i / Cf, c = i - p * Cf;
       dfb[i] = fmaf(rec[L.o_map() + p], dgl_s[c], dfb[i]);
     }
-    for (int p = j; p < P; p += nt) {  // gradient of map_k (used by iteration k-1; map_0 is a constant)
-      float s = 0.f;
-      for (int c = 0; c < Cf; ++c) s = fmaf(fb[(size_t)p * Cf + c], dgl_s[c], s);
-      dmap_s[p] = s;
+    for (int p = warp; p < P; p += nw) {  // gradient of map_k (used by iteration k-1; map_0 is a constant)
+      const float s = warp_row_dot(fb + (size_t)p * Cf, dgl_s, Cf, lane);
+      if (lane == 0) dmap_s[p] = s;
     }
     __syncthreads();
   }
@@ -275,9 +292,21 @@ __global__ void controller_bwd_kernel(const float *__restrict__ feat, int P, int
 // chunks of 16 staged in shared memory; every thread keeps a 4 x 4 register tile.  One pass over the rows in a fixed
 // order: bit-identical from run to run.  db = column sums of D (CTAs of the first tile row).
 constexpr int kOsT = 64, kOsR = 16;
+// grid.z > 1: row chunks of `rows_per_chunk` rows; chunk z writes its partial products to dW + z * n_in * n_out (and
+// db + z * n_out) - the caller passes the workspace there and outer_sum_finalize_kernel adds the chunks in order.
 __global__ void __launch_bounds__(256) outer_sum_kernel(const float *__restrict__ A, size_t a_stride, int n_in,
                                                         const float *__restrict__ D, size_t d_stride, int n_out, int R,
-                                                        float *__restrict__ dW, float *__restrict__ db) {
+                                                        int rows_per_chunk, float *__restrict__ dW,
+                                                        float *__restrict__ db) {
+  {
+    const int z = blockIdx.z;
+    const int rbeg = z * rows_per_chunk;
+    A += (size_t)rbeg * a_stride;
+    D += (size_t)rbeg * d_stride;
+    R = max(0, min(R - rbeg, rows_per_chunk));
+    dW += (size_t)z * n_in * n_out;
+    if (db != nullptr) db += (size_t)z * n_out;
+  }
   __shared__ float a_s[kOsR][kOsT + 4];
   __shared__ float d_s[kOsR][kOsT + 4];
   const int i0 = blockIdx.y * kOsT, o0 = blockIdx.x * kOsT;
@@ -324,6 +353,25 @@ __global__ void __launch_bounds__(256) outer_sum_kernel(const float *__restrict_
 #pragma unroll
     for (int b = 0; b < 4; ++b)
       if (o0 + 4 * to + b < n_out) db[o0 + 4 * to + b] = dbv[b];
+}
+
+// out[i] = sum over the chunks (fixed order)
+__global__ void outer_sum_finalize_kernel(const float *__restrict__ part, int chunks, size_t n, float *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = part[i];
+  for (int k = 1; k < chunks; ++k) s += part[(size_t)k * n + i];
+  out[i] = s;
+}
+
+// row chunks of the outer-sum launch: enough CTAs to cover the machine twice, at most 32 chunks, at least 64 rows each
+int outer_sum_chunks(int n_in, int n_out, int R) {
+  const int tiles = ((n_out + kOsT - 1) / kOsT) * ((n_in + kOsT - 1) / kOsT);
+  int z = (2 * ra::kNumSMs + tiles - 1) / tiles;
+  if (z > 32) z = 32;
+  const int zmax = R / 64;
+  if (z > zmax) z = zmax;
+  return z < 1 ? 1 : z;
 }
 
 bool dims_ok(int P, int Cf, int Hd, int n_iter) {
@@ -390,11 +438,39 @@ extern "C" int ra_controller_bwd_f32(const float *feat, int B, int P, int Cf, in
   return ra::finish_launch("controller_bwd_kernel");
 }
 
-extern "C" int ra_outer_sum_f32(const float *A, size_t a_stride, int n_in, const float *D, size_t d_stride, int n_out,
-                                int R, float *dW, float *db, void *stream) {
+extern "C" size_t ra_outer_sum_workspace(int n_in, int n_out, int R) {
+  if (n_in < 1 || n_out < 1 || R < 1) return 0;
+  const int z = outer_sum_chunks(n_in, n_out, R);
+  return z > 1 ? (size_t)z * ((size_t)n_in * n_out + n_out) * sizeof(float) : 0;
+}
+
+extern "C" int ra_outer_sum_ex_f32(const float *A, size_t a_stride, int n_in, const float *D, size_t d_stride,
+                                   int n_out, int R, void *ws, float *dW, float *db, void *stream) {
   if (n_in < 1 || n_out < 1 || R < 0 || !dW) return RA_ERR_INVALID_ARG;
   if (R > 0 && (!A || !D)) return RA_ERR_INVALID_ARG;
-  const dim3 grid((n_out + kOsT - 1) / kOsT, (n_in + kOsT - 1) / kOsT);
-  outer_sum_kernel<<<grid, 256, 0, ra::as_stream(stream)>>>(A, a_stride, n_in, D, d_stride, n_out, R, dW, db);
-  return ra::finish_launch("outer_sum_kernel");
+  cudaStream_t s = ra::as_stream(stream);
+  const int z = ws ? outer_sum_chunks(n_in, n_out, R) : 1;
+  const dim3 grid((n_out + kOsT - 1) / kOsT, (n_in + kOsT - 1) / kOsT, z);
+  if (z == 1) {
+    outer_sum_kernel<<<grid, 256, 0, s>>>(A, a_stride, n_in, D, d_stride, n_out, R, R, dW, db);
+    return ra::finish_launch("outer_sum_kernel");
+  }
+  int rows = (R + z - 1) / z;
+  rows = (rows + kOsR - 1) / kOsR * kOsR;
+  float *pw = reinterpret_cast<float *>(ws);
+  float *pb = pw + (size_t)z * n_in * n_out;
+  outer_sum_kernel<<<grid, 256, 0, s>>>(A, a_stride, n_in, D, d_stride, n_out, R, rows, pw, db ? pb : nullptr);
+  int rc = ra::finish_launch("outer_sum_kernel");
+  if (rc != RA_OK) return rc;
+  const size_t n = (size_t)n_in * n_out;
+  outer_sum_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pw, z, n, dW);
+  rc = ra::finish_launch("outer_sum_finalize_kernel");
+  if (rc != RA_OK || !db) return rc;
+  outer_sum_finalize_kernel<<<(n_out + 255) / 256, 256, 0, s>>>(pb, z, (size_t)n_out, db);
+  return ra::finish_launch("outer_sum_finalize_kernel(db)");
+}
+
+extern "C" int ra_outer_sum_f32(const float *A, size_t a_stride, int n_in, const float *D, size_t d_stride, int n_out,
+                                int R, float *dW, float *db, void *stream) {
+  return ra_outer_sum_ex_f32(A, a_stride, n_in, D, d_stride, n_out, R, nullptr, dW, db, stream);
 }

@@ -614,7 +614,10 @@ def outer_sum(A, a_stride, n_in, D, d_stride, n_out, R, want_bias=True):
   dev = D.device
   dW = torch.empty((n_in, n_out), device=dev, dtype=torch.float32)
   db = torch.empty(n_out, device=dev, dtype=torch.float32) if want_bias else None
-  _lib.call('ra_outer_sum_f32', _p(A), a_stride, n_in, _p(D), d_stride, n_out, R, _p(dW), _p(db), _stream())
+  nb = _lib.lib().ra_outer_sum_workspace(n_in, n_out, R)  # > 0: the rows are split over chunks of CTAs
+  ws = _ws(nb, dev) if nb else None
+  _lib.call('ra_outer_sum_ex_f32', _p(A), a_stride, n_in, _p(D), d_stride, n_out, R, _p(ws), _p(dW), _p(db),
+            _stream())
   return dW, db
 
 

@@ -188,8 +188,10 @@ def _add(dst, src):
 
 
 def _outer_sum(A, a_stride, n_in, D, d_stride, n_out, R, dW, db=None):
-  _lib.call('ra_outer_sum_f32', ops._p(A), a_stride, n_in, ops._p(D), d_stride, n_out, R, ops._p(dW), ops._p(db),
-            ops._stream())
+  nb = _lib.lib().ra_outer_sum_workspace(n_in, n_out, R)  # > 0: the rows are split over chunks of CTAs
+  ws = ops._ws(nb, dW.device) if nb else None
+  _lib.call('ra_outer_sum_ex_f32', ops._p(A), a_stride, n_in, ops._p(D), d_stride, n_out, R, ops._p(ws), ops._p(dW),
+            ops._p(db), ops._stream())
 
 
 def _paste_back_bwd(d_out, out, B, T, H, W, patch, fy, fx, gamma, box, d_fy=None, d_fx=None):

@@ -796,3 +796,30 @@ def test_conv_chain_equals_layer_by_layer(cuda):
   chain.run()  # a second run (barrier counter reset) gives the same again
   torch.cuda.synchronize()
   assert torch.equal(got[-1], layers[-1]['out'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n_in,n_out,R,bias', [(64, 256, 3200, True), (256, 256, 3200, False), (320, 9, 640, True),
+                                               (17, 130, 100, True), (256, 1, 640, True), (64, 64, 63, False)])
+def test_outer_sum_row_chunks(cuda, n_in, n_out, R, bias):
+  """ra_outer_sum_ex_f32 (rows split over chunks of CTAs, partials added in chunk order) against a float64 product,
+  against the single-chunk entry, and bit-identical from run to run."""
+  from rec_attend_b200 import _lib, ops, train as TR
+  g = torch.Generator().manual_seed(n_in * 1000 + n_out + R)
+  a_stride, d_stride = n_in + 3, n_out + 5  # rows live inside wider records, like the controller tape
+  A = torch.randn((R, a_stride), generator=g).cuda()
+  D = torch.randn((R, d_stride), generator=g).cuda()
+  ref = A[:, :n_in].double().t() @ D[:, :n_out].double()
+  dW = torch.empty((n_in, n_out), device='cuda')
+  db = torch.empty((n_out,), device='cuda') if bias else None
+  TR._outer_sum(A, a_stride, n_in, D, d_stride, n_out, R, dW, db)
+  assert rel_err(dW.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+  if bias:
+    assert rel_err(db.cpu().numpy(), D[:, :n_out].double().sum(0).cpu().numpy()) < 1e-5
+  dW2 = torch.empty_like(dW)
+  TR._outer_sum(A, a_stride, n_in, D, d_stride, n_out, R, dW2, None)
+  assert torch.equal(dW, dW2)
+  one = torch.empty_like(dW)
+  _lib.call('ra_outer_sum_f32', ops._p(A), a_stride, n_in, ops._p(D), d_stride, n_out, R, ops._p(one), ops._p(None),
+            ops._stream())
+  assert rel_err(one.cpu().numpy(), ref.cpu().numpy()) < 1e-5

@@ -36,8 +36,8 @@ if [[ $STAGES == *f* ]]; then
     python tools/ncu_target.py --reps 2 > gpurun_out/${TAG}_ncu_step.log 2>&1
   echo "ncu step exit $?"
   ncu -i /tmp/${TAG}_step.ncu-rep --page raw --csv > gpurun_out/${TAG}_step_full_raw.csv 2>&1
-  K2='regex:conv_bwd_weight_kernel|bn_bwd_apply|bn_bwd_reduce|ex_T_kernel|ex_dfy_kernel|pb_row_kernel|controller_bwd_kernel|bn_train'
-  timeout 900 ncu --set full --clock-control none -k "$K2" -s 400 -c 30 -o /tmp/${TAG}_train -f \
+  K2='regex:conv_bwd_weight_kernel|bn_bwd_apply|bn_bwd_reduce|ex_T_kernel|ex_dfy_kernel|ex_dfx_kernel|pb_row_kernel|pb_col_kernel|controller_bwd_kernel|outer_sum_kernel'
+  timeout 900 ncu --set full --clock-control none -k "$K2" -s 0 -c 70 -o /tmp/${TAG}_train -f \
     python tools/ncu_target.py --train --reps 1 --batch 8 > gpurun_out/${TAG}_ncu_train.log 2>&1
   echo "ncu train exit $?"
   ncu -i /tmp/${TAG}_train.ncu-rep --page raw --csv > gpurun_out/${TAG}_train_full_raw.csv 2>&1

@@ -52,6 +52,6 @@ for key, d in agg.items():
   gg['n'] += d['n']
 res['eager_kernel_ms'] = sum(d['ms'] for d in groups.values())
 res['per_shape'] = {k: round(d['ms'], 3) for k, d in sorted(agg.items(), key=lambda kv: -kv[1]['ms'])
-                    if k.startswith(('wgrad', 'bn_bwd'))}
+                    if k.startswith(('wgrad', 'bn_bwd', 'bn_fwd'))}
 res['groups'] = {k: {'ms': round(v['ms'], 3), 'n': v['n']} for k, v in sorted(groups.items(), key=lambda kv: -kv[1]['ms'])[:40]}
 print(json.dumps(res, indent=1))
