@@ -484,8 +484,8 @@ def run_ours(args):
     dom = max(groups.items(), key=lambda kv: kv[1]['ms'])[0]
     if dom.startswith('ra_conv3x3'):
       roofline = {
-          'kernel': 'conv3x3_umma (controller CNN layers 1-7, tcgen05 kind::tf32 x3 split, one persistent chain launch '
-                    'per decode step; group = ' + dom + ')',
+          'kernel': 'conv3x3_umma (controller CNN layers 1-7, tcgen05 kind::tf32 x3 split, persistent grid, one launch '
+                    'per layer chained by programmatic dependent launch; group = ' + dom + ')',
           'bound': 'tensor',
           'achieved': round(conv_tflops, 3), 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
           'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': entry_traffic(traffic, dom),
