@@ -372,10 +372,19 @@ def run_ours(args):
     bt_np = synthetic.make_batch(opt_t, Bt, seed=dist_util.rank_seed(1234, args.config, rank) + seed_off)
     bt = {k: torch.from_numpy(v).cuda() for k, v in bt_np.items()}
     model_t = FullModel(opt_t).load_weights(weights)
-    draws = synthetic.make_knob_draws(opt_t, Bt, global_step=0, seed=7 + rank)
+    # the scheduled-sampling draws are drawn ON the device, fresh every step and inside the timed region, like the
+    # reference's tf.random_uniform nodes (full_model.py:573-579,608-610,836-837): B*T*H*W floats of canvas noise
+    dev_name = 'cuda:%d' % torch.cuda.current_device()
+    draw_no = [0]
+
+    def new_draws():
+      draw_no[0] += 1
+      return synthetic.make_knob_draws(opt_t, Bt, global_step=0, seed=7 + rank + 1000 * draw_no[0], device=dev_name)
+
+    draws = new_draws()
 
     def step_train():
-      return model_t.train_step(bt, draws=draws)
+      return model_t.train_step(bt, draws=new_draws())
 
     for _ in range(2):
       step_train()
@@ -416,7 +425,8 @@ def run_ours(args):
     train_step = {'weak': bench_train(B, 0),
                   'step': 'train_step = taped training-mode forward + backward + all-reduce(SUM) of the flat gradient '
                           'bucket (NCCL, inside the timed region) + clip + Adam + device-side weight re-pack',
-                  'scheduled_sampling': 'use_knob=True, draws for global_step 0'}
+                  'scheduled_sampling': 'use_knob=True, knob probabilities of global_step 0; fresh draws every step, '
+                                        'generated on the device inside the timed region'}
     Bs = cfg['B'] // world
     if world > 1 and Bs >= 1 and cfg['B'] % world == 0:
       train_step['strong'] = bench_train(Bs, 500)

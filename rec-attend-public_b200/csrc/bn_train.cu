@@ -20,9 +20,23 @@ __device__ __forceinline__ void reduce_partials(const float *__restrict__ partia
   const int tid = threadIdx.x;
   const int groups = kBnThreads / C;
   const int c = tid % C, j = tid / C;
-  double s = 0.0;
-  if (j < groups)
-    for (int k = j; k < ctas; k += groups) s += (double)partial[(size_t)k * C + c];
+  // four independent accumulators: the loads of a thread's partials overlap instead of forming one dependent chain
+  // (every CTA of the next pass runs this before it can start streaming)
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (j < groups) {
+    int k = j;
+    for (; k + 3 * groups < ctas; k += 4 * groups) {
+      const float p0 = __ldg(partial + (size_t)k * C + c), p1 = __ldg(partial + (size_t)(k + groups) * C + c);
+      const float p2 = __ldg(partial + (size_t)(k + 2 * groups) * C + c);
+      const float p3 = __ldg(partial + (size_t)(k + 3 * groups) * C + c);
+      s0 += (double)p0;
+      s1 += (double)p1;
+      s2 += (double)p2;
+      s3 += (double)p3;
+    }
+    for (; k < ctas; k += groups) s0 += (double)__ldg(partial + (size_t)k * C + c);
+  }
+  const double s = (s0 + s1) + (s2 + s3);
   scratch[tid] = s;
   __syncthreads();
   if (tid < C) {
@@ -171,7 +185,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
 
 int bn_ctas(size_t npix, int C) {
   const int lanes = kBnThreads / ((C & 3) ? C : C / 4);
-  size_t want = (npix + lanes - 1) / lanes;
+  // at least 16 pixels per thread (two rounds of 8 loads in flight): the small patch-network maps get a few dozen
+  // CTAs, whose partials the next pass re-reduces in no time
+  size_t want = (npix + (size_t)lanes * 16 - 1) / ((size_t)lanes * 16);
   // every CTA of the next pass re-reduces these partials (ctas x C floats from L2), so their count is bounded by the
   // channel count: 4 CTAs per SM for the wide 16-channel maps (which need the loads in flight to stream from HBM), one
   // per SM from 64 channels on

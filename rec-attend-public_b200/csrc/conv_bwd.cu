@@ -339,6 +339,7 @@ struct WgParams {
   const float *x1, *x2, *g;
   int C1, C2, x1_bmod, N, Hin, Win, Cout, up;
   int CI_B, CO_B, TI, TJ, PG;  // channel block, threads along ci / co, pixel groups (TI*TJ*PG == 256)
+  int stages;                  // shared-memory stages of the tile pipeline (2..4)
   int TH, TW;                  // tile rows x columns (TW = 64 / 32 / 16 by the map width; TH * TW = 256 or 128 pixels)
   int vec_x, vec_g;            // 16-byte cp.async staging of the input window / the gradient tile (channel counts % 4
                                // == 0, aligned pointers); both stages are double buffered either way
@@ -351,6 +352,12 @@ __device__ __forceinline__ void cp_async16(float *dst_smem, const float *src, bo
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
   const int bytes = valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int bytes = valid ? 4 : 0;  // src-size 0: the destination word is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
 template <int RI, int RJ>
@@ -410,16 +417,18 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
         const int slot = idx / CI_B, c = idx - slot * CI_B;
         const int r = slot / kWgTWP, col = slot - r * kWgTWP;
         const int zy = y0 - p.up + r, zx = x0 - p.up + col;
-        float v = 0.f;
-        if (c < nci && zy >= 0 && zy < Ho && zx >= 0 && zx < Wo && (p.up == 1 || (((zy | zx) & 1) == 0))) {
+        // 4-byte cp.async: asynchronous like the vector path, so the deeper pipeline really overlaps
+        const bool ok = c < nci && zy >= 0 && zy < Ho && zx >= 0 && zx < Wo && (p.up == 1 || (((zy | zx) & 1) == 0));
+        const float *src = p.x1;
+        if (ok) {
           const int iy = p.up == 1 ? zy : zy >> 1, ix = p.up == 1 ? zx : zx >> 1;
           const int ci = ci0 + c;
           if (ci < p.C1)
-            v = __ldg(p.x1 + (((size_t)b1 * p.Hin + iy) * p.Win + ix) * p.C1 + ci);
+            src = p.x1 + (((size_t)b1 * p.Hin + iy) * p.Win + ix) * p.C1 + ci;
           else
-            v = __ldg(p.x2 + (((size_t)b * p.Hin + iy) * p.Win + ix) * p.C2 + (ci - p.C1));
+            src = p.x2 + (((size_t)b * p.Hin + iy) * p.Win + ix) * p.C2 + (ci - p.C1);
         }
-        xs[idx] = v;
+        cp_async4(xs + idx, src, ok);
       }
     }
     if (p.vec_g) {
@@ -447,8 +456,12 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
   auto compute = [&](const float *xs, const float *gs) {
     const float *xb = xs + ti * RI;
     const float *gb = gs + tj * RJ;
-    for (int pix = pg; pix < n_pix; pix += p.PG) {
-      const int py = pix / kWgTW, px = pix - py * kWgTW;
+    // pixel pg, pg + PG, ...: PG and the tile width are powers of two, so the walk is a row-major double loop without
+    // a division per pixel (PG <= TW: every row, columns pg, pg + PG, ..; PG > TW: one column, every (PG / TW)-th row)
+    const int px_step = p.PG <= kWgTW ? p.PG : kWgTW, py_step = p.PG <= kWgTW ? 1 : p.PG / kWgTW;
+    for (int py = pg / kWgTW; py < p.TH; py += py_step)
+    for (int px = pg % kWgTW; px < kWgTW; px += px_step) {
+      const int pix = py * kWgTW + px;
       float gv[RJ];
       if constexpr (RJ == 2) {  // 8-byte aligned: CO_B and tj * RJ are even
         const float2 t2 = *reinterpret_cast<const float2 *>(gb + pix * CO_B);
@@ -497,20 +510,30 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
   };
 
   {
-    // two shared-memory stages: the copies of tile k+1 (cp.async where the layout allows it) are issued before tile k
-    // is multiplied
-    int buf = 0;
-    int tile = blockIdx.x;
-    if (tile < p.n_tiles) stage(tile, wg_smem, wg_smem + n_slots * CI_B);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
-      const int nxt = tile + gridDim.x;
-      float *nb = wg_smem + (buf ^ 1) * stage_floats;
-      if (nxt < p.n_tiles) stage(nxt, nb, nb + n_slots * CI_B);
+    // p.stages shared-memory stages (2..4): the copies of tiles k+1 .. k+stages-1 (cp.async where the layout allows it)
+    // are in flight while tile k is multiplied.  Two are enough for the register-tiled channel blocks (a tile is ~3 us
+    // of FMAs); the 1-channel canvas layer is bandwidth-bound and needs the deeper queue to keep HBM busy.
+    const int S = p.stages;
+    auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
+    for (int st = 0; st < S - 1; ++st) {
+      float *nb = wg_smem + st * stage_floats;
+      if (tile_of(st) < p.n_tiles) stage(tile_of(st), nb, nb + n_slots * CI_B);
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the newest group has landed
+    }
+    for (int it = 0; tile_of(it) < p.n_tiles; ++it) {
+      const int nxt = it + S - 1;
+      float *nb = wg_smem + (nxt % S) * stage_floats;
+      if (tile_of(nxt) < p.n_tiles) stage(tile_of(nxt), nb, nb + n_slots * CI_B);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      // everything but the newest S-1 groups has landed
+      if (S == 2)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else if (S == 3)
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else
+        asm volatile("cp.async.wait_group 3;" ::: "memory");
       __syncthreads();
-      const float *cb = wg_smem + buf * stage_floats;
+      const float *cb = wg_smem + (it % S) * stage_floats;
       compute(cb, cb + n_slots * CI_B);
       __syncthreads();  // this stage may be overwritten by the copies issued in the next iteration
     }
@@ -550,7 +573,7 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
 
 // channel blocking of the weight-gradient kernel for a layer shape
 struct WgPlan {
-  int RI, RJ, CI_B, CO_B, TI, TJ, PG, n_ci_blk, n_co_blk, ctas, TH, TW;
+  int RI, RJ, CI_B, CO_B, TI, TJ, PG, n_ci_blk, n_co_blk, ctas, TH, TW, stages;
   size_t smem;
 };
 
@@ -581,7 +604,8 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
   w.TH = pix / w.TW;
   const size_t stage = ((size_t)(w.TH + 2) * (w.TW + 2) * w.CI_B + (size_t)w.TH * w.TW * w.CO_B) * sizeof(float);
   const size_t red = ((size_t)w.PG * 9 * w.CI_B * w.CO_B + (size_t)w.PG * w.CO_B) * sizeof(float);
-  w.smem = 2 * stage > red ? 2 * stage : red;
+  w.stages = (w.CI_B == 1) ? 4 : 2;
+  w.smem = w.stages * stage > red ? w.stages * stage : red;
   const size_t n_tiles = (size_t)N * ((Ho + w.TH - 1) / w.TH) * ((Wo + w.TW - 1) / w.TW);
   // resident CTAs per SM: 2 (register / shared-memory bound), 1 for the 4 x 4 tiles (~180 registers per thread)
   size_t cap = (size_t)ra::kNumSMs * (w.RI == 4 ? 1 : 2) / ((size_t)w.n_ci_blk * w.n_co_blk);
@@ -744,6 +768,7 @@ extern "C" int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod
   p.tiles_x = (Wo + w.TW - 1) / w.TW;
   p.TW = w.TW;
   p.TH = w.TH;
+  p.stages = w.stages;
   p.tiles_y = (Ho + w.TH - 1) / w.TH;
   p.vec_x = ((C1 & 3) == 0 && (C2 & 3) == 0 && (w.CI_B & 3) == 0 &&
              ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) & 15) == 0) ? 1 : 0;

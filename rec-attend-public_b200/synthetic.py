@@ -172,15 +172,35 @@ def knob_probability(opt, global_step, offset_key):
   return np.minimum(np.float32(1.0), p * scale.astype(np.float32)).astype(np.float32)
 
 
-def make_knob_draws(opt, batch_size, global_step=0, seed=99):
+def make_knob_draws(opt, batch_size, global_step=0, seed=99, device=None):
   """The random draws of one training step of the scheduled-sampling knob as explicit arrays (TensorFlow's streams
   cannot be reproduced): Bernoulli box / mask switches (full_model.py:608-610,622-624), the padding
-  ratio and centre shift of the noisy GT boxes (:573-579) and the per-step canvas noise (:836-837)."""
-  rng = np.random.default_rng(seed)
+  ratio and centre shift of the noisy GT boxes (:573-579) and the per-step canvas noise (:836-837).
+  device=None: numpy arrays from a seeded numpy generator (parity tests: the oracle and the CUDA path see the same
+  bits).  device='cuda...': torch tensors drawn ON the device, like the reference's tf.random_uniform nodes inside
+  the graph - a training loop must not ship B*T*H*W floats of noise over PCIe every step."""
   B, T, H, W = batch_size, opt['timespan'], opt['inp_height'], opt['inp_width']
   pb = knob_probability(opt, global_step, 'knob_box_offset').reshape(1, T)
   ps = knob_probability(opt, global_step, 'knob_segm_offset').reshape(1, T)
   r = opt['attn_box_padding_ratio']
+  if device is not None:
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+
+    def uni(shape, lo, hi):
+      return torch.rand(shape, generator=g, device=device, dtype=torch.float32) * (hi - lo) + lo
+
+    pb_d = torch.from_numpy(pb.astype(np.float32)).to(device)
+    ps_d = torch.from_numpy(ps.astype(np.float32)).to(device)
+    return {
+        'gt_knob_box': (uni((B, T), 0.0, 1.0) <= pb_d).to(torch.float32),
+        'gt_knob_segm': (uni((B, T), 0.0, 1.0) <= ps_d).to(torch.float32),
+        'gt_box_pad': uni((B, T, 1), r - opt['gt_box_pad_noise'], r + opt['gt_box_pad_noise']),
+        'gt_box_ctr_shift': uni((B, T, 2), -opt['gt_box_ctr_noise'], opt['gt_box_ctr_noise']),
+        'gt_segm_noise': uni((B, T, H, W), 0.0, opt['gt_segm_noise']),
+    }
+  rng = np.random.default_rng(seed)
   return {
       'gt_knob_box': (rng.random((B, T)) <= pb).astype(np.float32),
       'gt_knob_segm': (rng.random((B, T)) <= ps).astype(np.float32),

@@ -231,3 +231,32 @@ def test_load_weights_after_graph_capture_uses_new_weights(cuda):
   torch.cuda.synchronize()
   assert torch.equal(b, fresh)
   assert not torch.equal(a, b)
+
+
+def test_device_side_knob_draws(cuda):
+  """synthetic.make_knob_draws(device=...) draws the scheduled-sampling randoms on the device (the reference's
+  tf.random_uniform nodes): right shapes / ranges, reproducible per seed, and a train_step fed with them gives the
+  same loss as one fed with their host copies (no dependence on where the draws live)."""
+  import rec_attend_b200 as ra
+  from rec_attend_b200.full_model import FullModel
+  opt = ra.config.full_model_opt('kitti', 64, 128, 3, use_knob=True)
+  B, T, H, W = 2, 3, 64, 128
+  d = ra.synthetic.make_knob_draws(opt, B, global_step=9000, seed=5, device='cuda')
+  d2 = ra.synthetic.make_knob_draws(opt, B, global_step=9000, seed=5, device='cuda')
+  ref = ra.synthetic.make_knob_draws(opt, B, global_step=9000, seed=5)
+  assert set(d) == set(ref)
+  for k in ref:
+    assert d[k].is_cuda and d[k].dtype == torch.float32 and tuple(d[k].shape) == ref[k].shape, k
+    assert torch.equal(d[k], d2[k]), k
+  assert set(np.unique(d['gt_knob_box'].cpu().numpy())) <= {0.0, 1.0}
+  r = opt['attn_box_padding_ratio']
+  assert float(d['gt_box_pad'].min()) >= r - opt['gt_box_pad_noise'] - 1e-6
+  assert float(d['gt_box_pad'].max()) <= r + opt['gt_box_pad_noise'] + 1e-6
+  assert float(d['gt_segm_noise'].min()) >= 0.0 and float(d['gt_segm_noise'].max()) <= opt['gt_segm_noise'] + 1e-6
+  assert 0.3 * opt['gt_segm_noise'] < float(d['gt_segm_noise'].mean()) < 0.7 * opt['gt_segm_noise']
+  batch = ra.synthetic.make_batch(opt, B, seed=21)
+  weights = ra.synthetic.make_weights(opt, seed=4321)
+  host = {k: v.cpu().numpy() for k, v in d.items()}
+  la = FullModel(opt).load_weights(weights).train_step(batch, draws=d)['loss']
+  lb = FullModel(opt).load_weights(weights).train_step(batch, draws=host)['loss']
+  assert float(la) == float(lb)

@@ -23,7 +23,7 @@ cfg = config.BASELINE_CONFIGS[args.config]
 opt = dict(config.baseline_opt(args.config), use_knob=bool(args.knob))
 B = args.batch or cfg['B']
 batch = {k: torch.from_numpy(v).cuda() for k, v in synthetic.make_batch(opt, B).items()}
-draws = synthetic.make_knob_draws(opt, B, global_step=0, seed=7) if args.knob else None
+draws = synthetic.make_knob_draws(opt, B, global_step=0, seed=7, device='cuda') if args.knob else None
 model = FullModel(opt).load_weights(synthetic.make_weights(opt))
 for _ in range(2):
   model.train_step(batch, draws=draws)
@@ -37,6 +37,16 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / args.steps
 res = {'workload': cfg['name'], 'B': B, 'knob': args.knob, 'train_step_ms': ms, 'masks_per_s': B * cfg['T'] / ms * 1e3,
        'loss': float(r['loss']), 'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+# the same step without the CUDA graph (host-launched): separates graph replay cost from kernel time
+for _ in range(1):
+  model.train_step(batch, draws=draws, use_graph=False)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(args.steps):
+  model.train_step(batch, draws=draws, use_graph=False)
+e1.record()
+torch.cuda.synchronize()
+res['train_step_eager_ms'] = e0.elapsed_time(e1) / args.steps
 lib = _lib.lib()
 n0 = lib.ra_launch_count()
 with bench.OpTimer(torch, _lib) as ot:
