@@ -98,16 +98,23 @@ __global__ void __launch_bounds__(kT) pb_row_kernel(const float *__restrict__ d_
   dg = ra::block_sum(dg, red);
   if (threadIdx.x == 0) dgamma_rows[(size_t)b * H + y] = dg;
   __syncthreads();  // this row of dV is complete (written by this CTA only)
-  for (int i = 0; i < F; ++i) {
-    if (fy_s[i] == 0.f) {  // outside this tap's band: d_fy[i, y] only ever multiplies the zero filter entry
-      if (threadIdx.x == 0) dfy_s[i] = 0.f;
-      continue;  // (uniform: fy_s is shared)
-    }
+  // d_fy[i, y] = sum_x dV[y, x] R[i, x]: one warp per in-band tap (lanes along x, coalesced rows of R), no block barrier
+  // per tap.  Outside a tap's band d_fy[i, y] only ever multiplies the zero filter entry.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float *dvr = dV + ((size_t)b * H + y) * W;
+  for (int i = warp; i < F; i += kT / 32) {
     float s = 0.f;
-    for (int x = xlo + threadIdx.x; x <= xhi; x += kT)
-      s = fmaf(dV[((size_t)b * H + y) * W + x], Rb[(size_t)i * W + x], s);
-    s = ra::block_sum(s, red);
-    if (threadIdx.x == 0) dfy_s[i] = s;
+    if (fy_s[i] != 0.f) {  // warp-uniform
+      float s0 = 0.f, s1 = 0.f;
+      int x = xlo + lane;
+      for (; x + 32 <= xhi; x += 64) {
+        s0 = fmaf(dvr[x], Rb[(size_t)i * W + x], s0);
+        s1 = fmaf(dvr[x + 32], Rb[(size_t)i * W + x + 32], s1);
+      }
+      if (x <= xhi) s0 = fmaf(dvr[x], Rb[(size_t)i * W + x], s0);
+      s = ra::warp_sum(s0 + s1);
+    }
+    if (lane == 0) dfy_s[i] = s;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < F; i += kT) {

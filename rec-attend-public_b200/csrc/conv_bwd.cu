@@ -360,8 +360,12 @@ __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, boo
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
-template <int RI, int RJ>
-__global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
+// NKY = filter rows per CTA: 3 (all nine taps, grid.z = 1) or 1 (three taps, grid.z = 3: a third of the accumulators,
+// so two CTAs fit an SM and twice the warps hide the shared-memory latency; the tiles are staged once per filter row)
+template <int RI, int RJ, int NKY>
+__global__ void __launch_bounds__(kT, NKY == 1 ? 2 : 1) conv_bwd_weight_kernel(const WgParams p) {
+  constexpr int NT = NKY * 3;
+  const int ky0 = (int)blockIdx.z * NKY;
   extern __shared__ __align__(16) float wg_smem[];
   const int CI_B = p.CI_B, CO_B = p.CO_B;
   const int kWgTW = p.TW, kWgTWP = p.TW + 2;  // (runtime; the names are kept from the fixed-tile version)
@@ -373,9 +377,9 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
   const int ci0 = ci_blk * CI_B, co0 = co_blk * CO_B;
   const int nci = min(CI_B, Cin - ci0), nco = min(CO_B, p.Cout - co0);
   const int tj = threadIdx.x % p.TJ, ti = (threadIdx.x / p.TJ) % p.TI, pg = threadIdx.x / (p.TJ * p.TI);
-  float acc[9][RI][RJ];
+  float acc[NT][RI][RJ];
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < NT; ++t)
 #pragma unroll
     for (int i = 0; i < RI; ++i)
 #pragma unroll
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
   float dbv[RJ];
 #pragma unroll
   for (int j = 0; j < RJ; ++j) dbv[j] = 0.f;
-  const bool do_db = (ci_blk == 0 && p.db_partial != nullptr && ti == 0);
+  const bool do_db = (ci_blk == 0 && blockIdx.z == 0 && p.db_partial != nullptr && ti == 0);
 
   // Stage one tile: input window, slot (r, c) <-> zero-inserted pixel (y0 - up + r, x0 - up + c), and gradient tile.
   auto stage = [&](int tile, float *xs, float *gs) {
@@ -483,23 +487,23 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
       }
       const float *xr = xb + (size_t)(py * kWgTWP + px) * CI_B;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int ky = 0; ky < NKY; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           float xv[RI];
           if constexpr (RI == 2) {
-            const float2 t2 = *reinterpret_cast<const float2 *>(xr + (ky * kWgTWP + kx) * CI_B);
+            const float2 t2 = *reinterpret_cast<const float2 *>(xr + ((ky0 + ky) * kWgTWP + kx) * CI_B);
             xv[0] = t2.x;
             xv[1] = t2.y;
           } else if constexpr (RI == 4) {  // 16-byte aligned: CI_B and ti * RI are multiples of 4
-            const float4 t4 = *reinterpret_cast<const float4 *>(xr + (ky * kWgTWP + kx) * CI_B);
+            const float4 t4 = *reinterpret_cast<const float4 *>(xr + ((ky0 + ky) * kWgTWP + kx) * CI_B);
             xv[0] = t4.x;
             xv[1] = t4.y;
             xv[2] = t4.z;
             xv[3] = t4.w;
           } else {
 #pragma unroll
-            for (int i = 0; i < RI; ++i) xv[i] = xr[(ky * kWgTWP + kx) * CI_B + i];
+            for (int i = 0; i < RI; ++i) xv[i] = xr[((ky0 + ky) * kWgTWP + kx) * CI_B + i];
           }
 #pragma unroll
           for (int i = 0; i < RI; ++i)
@@ -541,10 +545,10 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
   }
   // ---- sum the pixel groups through shared memory (fixed order), write this CTA's partial
   __syncthreads();
-  float *red = wg_smem;  // [PG][9][CI_B][CO_B]  (+ [PG][CO_B] for db)
-  const int blk = 9 * CI_B * CO_B;
+  float *red = wg_smem;  // [PG][NT][CI_B][CO_B]  (+ [PG][CO_B] for db)
+  const int blk = NT * CI_B * CO_B;
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int t = 0; t < NT; ++t)
 #pragma unroll
     for (int i = 0; i < RI; ++i)
 #pragma unroll
@@ -561,9 +565,9 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
     if (ci >= nci || co >= nco) continue;
     float s = 0.f;
     for (int g = 0; g < p.PG; ++g) s += red[(size_t)g * blk + idx];
-    out[((size_t)t * Cin + ci0 + ci) * p.Cout + co0 + co] = s;
+    out[((size_t)(ky0 * 3 + t) * Cin + ci0 + ci) * p.Cout + co0 + co] = s;
   }
-  if (ci_blk == 0 && p.db_partial != nullptr)
+  if (ci_blk == 0 && blockIdx.z == 0 && p.db_partial != nullptr)
     for (int co = threadIdx.x; co < nco; co += kT) {
       float s = 0.f;
       for (int g = 0; g < p.PG; ++g) s += dbred[g * CO_B + co];
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(kT) conv_bwd_weight_kernel(const WgParams p) {
 
 // channel blocking of the weight-gradient kernel for a layer shape
 struct WgPlan {
-  int RI, RJ, CI_B, CO_B, TI, TJ, PG, n_ci_blk, n_co_blk, ctas, TH, TW, stages;
+  int RI, RJ, CI_B, CO_B, TI, TJ, PG, n_ci_blk, n_co_blk, ctas, TH, TW, stages, nky;
   size_t smem;
 };
 
@@ -592,6 +596,10 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
     w.CI_B = Cin <= 16 ? 16 : 32;
     w.CO_B = Cout <= 16 ? 16 : 32;
   }
+  {
+    static const int nky_env = getenv("RA_WGRAD_NKY") ? atoi(getenv("RA_WGRAD_NKY")) : 1;
+    w.nky = (w.RI == 4 && nky_env == 1) ? 1 : 3;
+  }
   w.TI = w.CI_B / w.RI;
   w.TJ = w.CO_B / w.RJ;
   w.PG = kT / (w.TI * w.TJ);
@@ -600,15 +608,17 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
   // tile: as wide as the map allows (64 / 32 / 16 columns), 256 pixels - 128 for the 32-wide channel blocks, whose two
   // stages must fit twice per SM
   w.TW = Wo > 32 ? 64 : (Wo > 16 ? 32 : 16);
-  const int pix = (w.RI != 4 && (w.CI_B > 16 || w.CO_B > 16)) ? 128 : 256;
+  // 256 pixels per tile; 128 for the 32-wide channel blocks when two CTAs (two stages each) must fit an SM
+  const int pix = ((w.RI != 4 || w.nky == 1) && (w.CI_B > 16 || w.CO_B > 16)) ? 128 : 256;
   w.TH = pix / w.TW;
   const size_t stage = ((size_t)(w.TH + 2) * (w.TW + 2) * w.CI_B + (size_t)w.TH * w.TW * w.CO_B) * sizeof(float);
-  const size_t red = ((size_t)w.PG * 9 * w.CI_B * w.CO_B + (size_t)w.PG * w.CO_B) * sizeof(float);
+  const size_t red = ((size_t)w.PG * w.nky * 3 * w.CI_B * w.CO_B + (size_t)w.PG * w.CO_B) * sizeof(float);
   w.stages = (w.CI_B == 1) ? 4 : 2;
   w.smem = w.stages * stage > red ? w.stages * stage : red;
   const size_t n_tiles = (size_t)N * ((Ho + w.TH - 1) / w.TH) * ((Wo + w.TW - 1) / w.TW);
   // resident CTAs per SM: 2 (register / shared-memory bound), 1 for the 4 x 4 tiles (~180 registers per thread)
-  size_t cap = (size_t)ra::kNumSMs * (w.RI == 4 ? 1 : 2) / ((size_t)w.n_ci_blk * w.n_co_blk);
+  size_t cap = (size_t)ra::kNumSMs * ((w.RI == 4 && w.nky == 3) ? 1 : 2) /
+               ((size_t)w.n_ci_blk * w.n_co_blk * (size_t)(3 / w.nky));
   if (cap < 16) cap = 16;
   w.ctas = (int)(n_tiles < cap ? (n_tiles < 1 ? 1 : n_tiles) : cap);
   return w;
@@ -779,18 +789,21 @@ extern "C" int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod
   p.db_partial = db ? db_partial : nullptr;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(conv_bwd_weight_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    cudaFuncSetAttribute(conv_bwd_weight_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv_bwd_weight_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<1, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     attr_done = true;
   }
-  const dim3 grid(chunks, w.n_ci_blk * w.n_co_blk);
+  const dim3 grid(chunks, w.n_ci_blk * w.n_co_blk, 3 / w.nky);
   if (w.RI == 2)
-    conv_bwd_weight_kernel<2, 2><<<grid, kT, w.smem, s>>>(p);
+    conv_bwd_weight_kernel<2, 2, 3><<<grid, kT, w.smem, s>>>(p);
+  else if (w.RI == 4 && w.nky == 1)
+    conv_bwd_weight_kernel<4, 4, 1><<<grid, kT, w.smem, s>>>(p);
   else if (w.RI == 4)
-    conv_bwd_weight_kernel<4, 4><<<grid, kT, w.smem, s>>>(p);
+    conv_bwd_weight_kernel<4, 4, 3><<<grid, kT, w.smem, s>>>(p);
   else
-    conv_bwd_weight_kernel<1, 4><<<grid, kT, w.smem, s>>>(p);
+    conv_bwd_weight_kernel<1, 4, 3><<<grid, kT, w.smem, s>>>(p);
   int rc = ra::finish_launch("conv_bwd_weight_kernel");
   if (rc != RA_OK) return rc;
   const size_t n = (size_t)9 * Cin * Cout;

@@ -17,6 +17,7 @@ from rec_attend_b200.full_model import FullModel  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--eval', action='store_true')
 ap.add_argument('--config', type=int, default=2)
+ap.add_argument('--dump-step', type=int, default=-1, help='print the kernel sequence of this decode step')
 args = ap.parse_args()
 cfg = config.BASELINE_CONFIGS[args.config]
 opt = dict(config.baseline_opt(args.config), use_knob=not args.eval)
@@ -71,3 +72,12 @@ for e in ev:
 print('kernel time by name:')
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
   print('  %9.1f us  x%-5d %s' % (t, n, k))
+
+if args.dump_step >= 0:
+  starts = [i for i, e in enumerate(ev) if 'controller_cluster_kernel' in e['name']]
+  if args.dump_step + 1 < len(starts):
+    a, b = starts[args.dump_step], starts[args.dump_step + 1]
+    t0 = ev[a]['ts']
+    print('decode step %d: start (us, relative), duration, end, kernel' % args.dump_step)
+    for e in ev[a - 8:b + 1]:
+      print('  %9.2f  %8.2f  %9.2f  %s' % (e['ts'] - t0, e['dur'], e['ts'] + e['dur'] - t0, short(e['name'])))
