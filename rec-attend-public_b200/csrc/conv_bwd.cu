@@ -597,7 +597,9 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
     w.CO_B = Cout <= 16 ? 16 : 32;
   }
   {
-    static const int nky_env = getenv("RA_WGRAD_NKY") ? atoi(getenv("RA_WGRAD_NKY")) : 1;
+    // MEASURED (KITTI B=32): three taps per CTA at two CTAs per SM is slower - 33.5 ms against 22.0 ms for all the
+    // weight gradients: the tiles are staged three times and the FMA : load ratio falls to 12 : 1.  Opt-in only.
+    static const int nky_env = getenv("RA_WGRAD_NKY") ? atoi(getenv("RA_WGRAD_NKY")) : 3;
     w.nky = (w.RI == 4 && nky_env == 1) ? 1 : 3;
   }
   w.TI = w.CI_B / w.RI;
