@@ -13,11 +13,63 @@ namespace {
 constexpr int kBnThreads = 256;
 constexpr int kBnMaxC = 256;
 
-// Sum the per-CTA partials of every channel with the whole CTA (fixed order, double): thread t takes channel t % C and
-// every (kBnThreads / C)-th partial, a second step adds the groups.  out_s[c] = sum / npix.  Needs C <= kBnThreads.
+// Sum the per-CTA partials of every channel with the whole CTA, in double, in a fixed order; out_s[c] = sum / npix.
+// Every CTA of the next pass runs this before it can start streaming, so it is built for latency:
+//  * fast path (C % 4 == 0 and C / 4 divides 32): the [ctas][C] array is read as float4, four independent loads per
+//    thread and round - a thread always meets the same channel quad -, then lanes holding the same quad are combined
+//    with shuffles and the 8 warps through shared memory: one L2 round trip per 4096 partial quads instead of a
+//    dependent chain of ctas / groups loads;
+//  * general path: thread t takes channel t % C and every (kBnThreads / C)-th partial.  Needs C <= kBnThreads.
+__device__ __forceinline__ double shfl_xor_double(double v, int mask) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+  hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+  return __hiloint2double(hi, lo);
+}
+
 __device__ __forceinline__ void reduce_partials(const float *__restrict__ partial, int ctas, int C, double inv_npix,
                                                 float *out_s, double *scratch /* [kBnThreads] */) {
   const int tid = threadIdx.x;
+  const int q_n = C >> 2;
+  if ((C & 3) == 0 && q_n <= 32 && (32 % q_n) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const float4 *p4 = reinterpret_cast<const float4 *>(partial);
+    const int n4 = ctas * q_n;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < n4; i += kBnThreads * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = i + u * kBnThreads;
+        v[u] = idx < n4 ? __ldg(p4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[0] += (double)v[u].x;
+        a[1] += (double)v[u].y;
+        a[2] += (double)v[u].z;
+        a[3] += (double)v[u].w;
+      }
+    }
+    // lanes l, l + q_n, l + 2 q_n, .. hold the same channel quad (256 and 32 are multiples of q_n)
+    for (int m = 16; m >= q_n; m >>= 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] += shfl_xor_double(a[e], m);
+    }
+    __syncthreads();  // scratch may still be read by a previous call
+    if (lane < q_n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) scratch[warp * C + lane * 4 + e] = a[e];  // 8 * C <= 8 * 128 doubles?  see below
+    }
+    __syncthreads();
+    if (tid < C) {
+      double t = 0.0;
+      for (int w = 0; w < kBnThreads / 32; ++w) t += scratch[w * C + tid];
+      out_s[tid] = (float)(t * inv_npix);
+    }
+    __syncthreads();
+    return;
+  }
   const int groups = kBnThreads / C;
   const int c = tid % C, j = tid / C;
   // four independent accumulators: the loads of a thread's partials overlap instead of forming one dependent chain
@@ -55,7 +107,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_partial_kernel(const float *__r
                                                                 float *__restrict__ partial) {
   __shared__ float center_s[kBnMaxC];
   __shared__ float red_s[kBnThreads * 4];
-  __shared__ double dbl_s[kBnThreads];
+  __shared__ double dbl_s[kBnThreads * 4];
   const int tid = threadIdx.x;
   const int cg_n = C / V;
   if (POW == 2) {  // the mean, from the first pass's partial sums
@@ -127,7 +179,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
                                                               float *__restrict__ ema_var, float *__restrict__ batch_mean,
                                                               float *__restrict__ batch_var, float *__restrict__ y) {
   __shared__ float inv_s[kBnMaxC], sh_s[kBnMaxC], mean_s[kBnMaxC], var_s[kBnMaxC];
-  __shared__ double dbl_s[kBnThreads];
+  __shared__ double dbl_s[kBnThreads * 4];
   const int tid = threadIdx.x;
   const size_t npix = (size_t)B * H * W;
   reduce_partials(sum_partial, ctas, C, 1.0 / (double)npix, mean_s, dbl_s);

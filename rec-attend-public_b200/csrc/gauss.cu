@@ -146,20 +146,20 @@ __global__ void __launch_bounds__(128) extract_rows_kernel(const float *__restri
   for (int k = 0; k < IB; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float *sp = src + ((size_t)b * H + ylo) * rowlen + e0;
   int yy = 0;
-  for (; yy + 2 <= ny; yy += 2) {
-    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(sp + (size_t)yy * rowlen));
-    const float4 v1 = __ldg(reinterpret_cast<const float4 *>(sp + (size_t)(yy + 1) * rowlen));
+  for (; yy + 4 <= ny; yy += 4) {  // four independent row loads in flight
+    float4 v[4];
 #pragma unroll
-    for (int k = 0; k < IB; ++k) {
-      const float w0 = wsm[k * H + yy], w1 = wsm[k * H + yy + 1];
-      acc[k].x = fmaf(w0, v0.x, acc[k].x);
-      acc[k].y = fmaf(w0, v0.y, acc[k].y);
-      acc[k].z = fmaf(w0, v0.z, acc[k].z);
-      acc[k].w = fmaf(w0, v0.w, acc[k].w);
-      acc[k].x = fmaf(w1, v1.x, acc[k].x);
-      acc[k].y = fmaf(w1, v1.y, acc[k].y);
-      acc[k].z = fmaf(w1, v1.z, acc[k].z);
-      acc[k].w = fmaf(w1, v1.w, acc[k].w);
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4 *>(sp + (size_t)(yy + u) * rowlen));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < IB; ++k) {
+        const float w0 = wsm[k * H + yy + u];
+        acc[k].x = fmaf(w0, v[u].x, acc[k].x);
+        acc[k].y = fmaf(w0, v[u].y, acc[k].y);
+        acc[k].z = fmaf(w0, v[u].z, acc[k].z);
+        acc[k].w = fmaf(w0, v[u].w, acc[k].w);
+      }
     }
   }
   for (; yy < ny; ++yy) {
@@ -433,7 +433,10 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
   if (F > kMaxF || (W % 4) != 0) return RA_ERR_UNSUPPORTED;
   if (B == 0) return RA_OK;
   cudaStream_t s = ra::as_stream(stream);
-  constexpr int IB = 4;
+  // taps per CTA of the row pass.  MEASURED: 8 taps per CTA (half the CTAs re-reading the same image rows, RA_EXTRACT_IB=8)
+  // is no faster - 1.05 vs 1.01 ms per forward at KITTI B=32: the wider union of the taps' row bands costs what the
+  // re-reads save.
+  static const int IB = (getenv("RA_EXTRACT_IB") && atoi(getenv("RA_EXTRACT_IB")) == 8) ? 8 : 4;
   const int groups = (F + IB - 1) / IB;
   float *tmp_s = tmp;
   float *tmp_c = tmp + (size_t)B * F * W * Cs;
@@ -443,8 +446,11 @@ extern "C" int ra_gaussian_extract_f32(const float *xs, int Cs, const float *can
     const int nx_s = Cs > 0 ? (W * Cs / 4 + 127) / 128 : 0;
     const int nx_c = canvas != nullptr ? (W / 4 + 127) / 128 : 0;
     dim3 grid(nx_s + nx_c, groups, B);
-    const cudaError_t le = ra::launch_pdl(extract_rows_kernel<IB>, grid, dim3(128), smem_rows, s, xs, Cs, canvas, H, W, fy,
-                                          band, box, F, tmp_s, tmp_c, nx_s);
+    const cudaError_t le =
+        IB == 4 ? ra::launch_pdl(extract_rows_kernel<4>, grid, dim3(128), smem_rows, s, xs, Cs, canvas, H, W, fy, band, box,
+                                 F, tmp_s, tmp_c, nx_s)
+                : ra::launch_pdl(extract_rows_kernel<8>, grid, dim3(128), smem_rows, s, xs, Cs, canvas, H, W, fy, band, box,
+                                 F, tmp_s, tmp_c, nx_s);
     if (le != cudaSuccess) {
       ra::set_last_error("cudaLaunchKernelEx(extract_rows_kernel)", le);
       return RA_ERR_CUDA;
