@@ -348,17 +348,37 @@ __global__ void __launch_bounds__(kT) ex_T_kernel(const float *__restrict__ xs, 
         yhi = max(yhi, hi);
       }
     }
+  // the CTA's filter rows over its union band in shared memory (every thread needs all of them), then four independent
+  // image loads in flight per round - the loop is bound by load latency, not arithmetic
+  extern __shared__ float ext_w[];  // [kExIB][H]
+  const int ny = max(yhi - ylo + 1, 0);
+  for (int u = threadIdx.x; u < kExIB * ny; u += kT) {
+    const int k = u / ny, yy = u - k * ny;
+    ext_w[k * H + yy] = (i0 + k < F) ? __ldg(fy + ((size_t)b * F + i0 + k) * H + ylo + yy) : 0.f;
+  }
+  __syncthreads();
   if (idx >= nxc) return;
   const int x = xlo + idx / D, c = idx % D;
   float acc[kExIB];
 #pragma unroll
   for (int k = 0; k < kExIB; ++k) acc[k] = 0.f;
-  const float *fyb = fy + ((size_t)b * F + i0) * H;
-  for (int y = ylo; y <= yhi; ++y) {
-    const float v = (c < Cs) ? __ldg(xs + (((size_t)bx * H + y) * W + x) * Cs + c) : __ldg(canvas + ((size_t)b * H + y) * W + x);
+  const bool from_xs = c < Cs;
+  const float *src = from_xs ? xs + (((size_t)bx * H + ylo) * W + x) * Cs + c : canvas + ((size_t)b * H + ylo) * W + x;
+  const size_t ystride = from_xs ? (size_t)W * Cs : (size_t)W;
+  int yy = 0;
+  for (; yy + 4 <= ny; yy += 4) {
+    float v[4];
 #pragma unroll
-    for (int k = 0; k < kExIB; ++k)
-      if (i0 + k < F) acc[k] = fmaf(__ldg(fyb + (size_t)k * H + y), v, acc[k]);
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(src + (size_t)(yy + u) * ystride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < kExIB; ++k) acc[k] = fmaf(ext_w[k * H + yy + u], v[u], acc[k]);
+  }
+  for (; yy < ny; ++yy) {
+    const float v = __ldg(src + (size_t)yy * ystride);
+#pragma unroll
+    for (int k = 0; k < kExIB; ++k) acc[k] = fmaf(ext_w[k * H + yy], v, acc[k]);
   }
 #pragma unroll
   for (int k = 0; k < kExIB; ++k)
@@ -671,7 +691,8 @@ extern "C" int ra_gaussian_extract_bwd_ex_f32(const float *xs, int Cs, int xs_bm
   float *T = reinterpret_cast<float *>(ws);
   const int bxc = (W * D + kT - 1) / kT;
   const size_t gsm = (size_t)F * D * sizeof(float);
-  ex_T_kernel<<<dim3(bxc, (F + kExIB - 1) / kExIB, B), kT, 0, s>>>(xs, Cs, xs_bmod, canvas, fy, box, H, W, F, D, T);
+  ex_T_kernel<<<dim3(bxc, (F + kExIB - 1) / kExIB, B), kT, (size_t)kExIB * H * sizeof(float), s>>>(xs, Cs, xs_bmod, canvas,
+                                                                                                   fy, box, H, W, F, D, T);
   int rc = ra::finish_launch("ex_T_kernel");
   if (rc != RA_OK) return rc;
   ex_dfx_kernel<<<dim3(F, B), kT, gsm, s>>>(d_patch, patch_cstride, chan_map, T, gamma, gamma_stride, box, W, F, D,

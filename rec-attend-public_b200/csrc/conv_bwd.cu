@@ -575,6 +575,82 @@ __global__ void __launch_bounds__(kT, NKY == 1 ? 2 : 1) conv_bwd_weight_kernel(c
     }
 }
 
+// ---- single input channel (the canvas channel of the first controller layer: [N,H,W,1] x [N,H,W,Cout], N = T*B).
+// 36 FMAs per 16 + 4 bytes: bandwidth-bound, so no shared-memory tiles: a thread owns one output-channel quad and walks
+// runs of 8 consecutive pixels of an image row - eight independent 16-byte gradient loads in flight, the 3 x 10 input
+// window of the run in registers - and keeps its 9 x 4 sums in registers; the CTA adds its threads in a fixed order and
+// writes one partial, summed by conv_bwd_weight_finalize_kernel like the tiled kernel's.  Needs Cout % 4 == 0, Cout <= 64.
+constexpr int kC1Run = 8;
+__global__ void __launch_bounds__(kT) conv_bwd_weight_c1_kernel(const float *__restrict__ x, int x_bmod,
+                                                                const float *__restrict__ g, int N, int H, int W, int Cout,
+                                                                float *__restrict__ partial, float *__restrict__ db_partial) {
+  extern __shared__ float c1_sm[];  // [lanes][Cout / 4][40]
+  const int q_n = Cout >> 2, lanes = kT / q_n;
+  const int q = threadIdx.x % q_n, pl = threadIdx.x / q_n;
+  float acc[9][4], dbv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+  const int runs_per_row = (W + kC1Run - 1) / kC1Run;
+  const long long n_runs = (long long)N * H * runs_per_row;
+  for (long long r = (long long)blockIdx.x * lanes + pl; pl < lanes && r < n_runs; r += (long long)gridDim.x * lanes) {
+    const int xr = (int)(r % runs_per_row) * kC1Run;
+    const long long row = r / runs_per_row;  // n * H + y
+    const int y = (int)(row % H);
+    const long long n = row / H;
+    const long long nx = x_bmod > 0 ? n % x_bmod : n;
+    float4 gv[kC1Run];
+    const float *gp = g + ((size_t)row * W + xr) * Cout + q * 4;
+#pragma unroll
+    for (int i = 0; i < kC1Run; ++i)
+      gv[i] = (xr + i < W) ? __ldg(reinterpret_cast<const float4 *>(gp + (size_t)i * Cout)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float win[3][kC1Run + 2];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      const float *xp = x + ((size_t)nx * H + (yy < 0 ? 0 : (yy >= H ? H - 1 : yy))) * W;
+      const bool row_ok = yy >= 0 && yy < H;
+#pragma unroll
+      for (int i = 0; i < kC1Run + 2; ++i) {
+        const int xx = xr + i - 1;
+        win[ky][i] = (row_ok && xx >= 0 && xx < W) ? __ldg(xp + xx) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kC1Run; ++i) {
+      const float g4[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dbv[e] += g4[e];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[ky * 3 + kx][e] = fmaf(win[ky][i + kx], g4[e], acc[ky * 3 + kx][e]);
+    }
+  }
+  float *mine = c1_sm + ((size_t)pl * q_n + q) * 40;
+  if (pl < lanes) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mine[t * 4 + e] = acc[t][e];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) mine[36 + e] = dbv[e];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 10 * Cout; o += kT) {  // o = t * Cout + co, t == 9: the bias gradient
+    const int t = o / Cout, co = o - t * Cout;
+    float sum = 0.f;
+    for (int l = 0; l < lanes; ++l) sum += c1_sm[((size_t)l * q_n + (co >> 2)) * 40 + t * 4 + (co & 3)];
+    if (t < 9)
+      partial[(size_t)blockIdx.x * 9 * Cout + o] = sum;
+    else if (db_partial != nullptr)
+      db_partial[(size_t)blockIdx.x * Cout + co] = sum;
+  }
+}
+
 // channel blocking of the weight-gradient kernel for a layer shape
 struct WgPlan {
   int RI, RJ, CI_B, CO_B, TI, TJ, PG, n_ci_blk, n_co_blk, ctas, TH, TW, stages, nky;
@@ -773,6 +849,25 @@ extern "C" int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod
   if ((size_t)w.n_ci_blk * w.n_co_blk > 65535) return RA_ERR_UNSUPPORTED;
   float *partial = reinterpret_cast<float *>(ws);
   float *db_partial = partial + (size_t)chunks * 9 * Cin * Cout;
+  if (Cin == 1 && upsample == 1 && (Cout & 3) == 0 && Cout <= 64 && (kT % (Cout >> 2)) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && getenv("RA_WGRAD_C1_TILED") == nullptr) {
+    const size_t c1_smem = (size_t)kT * 40 * sizeof(float);
+    static bool c1_attr = false;
+    if (!c1_attr) {
+      cudaFuncSetAttribute(conv_bwd_weight_c1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c1_smem);
+      c1_attr = true;
+    }
+    conv_bwd_weight_c1_kernel<<<chunks, kT, c1_smem, s>>>(x1, x1_bmod, d_out, B, Hin, Win, Cout, partial,
+                                                          db ? db_partial : nullptr);
+    int rc1 = ra::finish_launch("conv_bwd_weight_c1_kernel");
+    if (rc1 != RA_OK) return rc1;
+    const size_t n1 = (size_t)9 * Cout;
+    conv_bwd_weight_finalize_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, s>>>(partial, chunks, n1, dw);
+    rc1 = ra::finish_launch("conv_bwd_weight_finalize_kernel");
+    if (rc1 != RA_OK || !db) return rc1;
+    conv_bwd_weight_finalize_kernel<<<(Cout + 255) / 256, 256, 0, s>>>(db_partial, chunks, (size_t)Cout, db);
+    return ra::finish_launch("conv_bwd_weight_finalize_kernel(db)");
+  }
   WgParams p;
   p.x1 = x1; p.x2 = x2; p.g = d_out;
   p.C1 = C1; p.C2 = C2; p.x1_bmod = x1_bmod; p.N = B; p.Hin = Hin; p.Win = Win; p.Cout = Cout; p.up = upsample;

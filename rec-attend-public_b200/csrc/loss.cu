@@ -407,7 +407,81 @@ __global__ void score_kernel(const float *__restrict__ h, int Hd, const float *_
 // for all H*W pixels: 1.27 ms per launch at 256x512, B = 32.)
 constexpr int kBgChunks = 16;  // row chunks per example
 
+// One pass over the chunk's pixels: a thread walks COLUMNS (x = tid, tid + 256, ..), so which rectangles contain its
+// column is a bit mask computed once per column; which contain the row is a per-row mask in shared memory; the T sums
+// live in registers.  (The first single-kernel version made ceil(T / 8) passes with four compares per pixel and
+// rectangle: 72 us per launch at 256x512, B = 32.)
+constexpr int kBgMaxT = 32;
 __global__ void __launch_bounds__(256) box_gt_partial_kernel(const float *__restrict__ attn_box, size_t box_bstride,
+                                                             const float *__restrict__ gt_rect, int T, int H, int W,
+                                                             float *__restrict__ partial /* [B][kBgChunks][T+1] */) {
+  extern __shared__ float sm[];  // rc_s [T][4] | ymask_s [rows] (as uint) | red_s [8][kBgMaxT + 1]
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int rows = (H + kBgChunks - 1) / kBgChunks;
+  float *rc_s = sm;
+  unsigned *ymask_s = reinterpret_cast<unsigned *>(sm + 4 * T);
+  float *red_s = sm + 4 * T + rows;
+  for (int i = threadIdx.x; i < T * 4; i += blockDim.x) rc_s[i] = gt_rect[(size_t)b * T * 4 + i];
+  __syncthreads();
+  const int y0 = ch * rows, y1 = min(H, y0 + rows);
+  for (int r = threadIdx.x; r < y1 - y0; r += blockDim.x) {
+    const float fy = (float)(y0 + r);
+    unsigned m = 0;
+    for (int k = 0; k < T; ++k) m |= (fy >= rc_s[k * 4 + 0] && fy <= rc_s[k * 4 + 2]) ? (1u << k) : 0u;
+    ymask_s[r] = m;
+  }
+  __syncthreads();
+  const float *bx = attn_box + (size_t)b * box_bstride + (size_t)y0 * W;
+  float *out = partial + ((size_t)b * kBgChunks + ch) * (T + 1);
+  float acc[kBgMaxT];
+#pragma unroll
+  for (int k = 0; k < kBgMaxT; ++k) acc[k] = 0.f;
+  float tot = 0.f;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const float fx = (float)x;
+    unsigned xm = 0;
+    for (int k = 0; k < T; ++k) xm |= (fx >= rc_s[k * 4 + 1] && fx <= rc_s[k * 4 + 3]) ? (1u << k) : 0u;
+    int r = 0;
+    for (; r + 4 <= y1 - y0; r += 4) {  // four independent loads in flight
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = bx[(size_t)(r + u) * W + x];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        tot += v[u];
+        const unsigned m = xm & ymask_s[r + u];
+#pragma unroll
+        for (int k = 0; k < kBgMaxT; ++k) acc[k] += ((m >> k) & 1u) ? v[u] : 0.f;
+      }
+    }
+    for (; r < y1 - y0; ++r) {
+      const float v = bx[(size_t)r * W + x];
+      tot += v;
+      const unsigned m = xm & ymask_s[r];
+#pragma unroll
+      for (int k = 0; k < kBgMaxT; ++k) acc[k] += ((m >> k) & 1u) ? v : 0.f;
+    }
+  }
+  // warp sums, then the 8 warps through shared memory (fixed order)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kBgMaxT; ++k) {
+    const float s1 = ra::warp_sum(acc[k]);
+    if (lane == 0) red_s[warp * (kBgMaxT + 1) + k] = s1;
+  }
+  tot = ra::warp_sum(tot);
+  if (lane == 0) red_s[warp * (kBgMaxT + 1) + kBgMaxT] = tot;
+  __syncthreads();
+  for (int k = threadIdx.x; k <= T; k += blockDim.x) {
+    const int src = k < T ? k : kBgMaxT;
+    float s1 = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s1 += red_s[w * (kBgMaxT + 1) + src];
+    out[k] = s1;
+  }
+}
+
+// T > kBgMaxT (up to 64 rectangles): ceil(T / 8) passes over the chunk, eight sums per pass
+__global__ void __launch_bounds__(256) box_gt_partial_wide_kernel(const float *__restrict__ attn_box, size_t box_bstride,
                                                              const float *__restrict__ gt_rect, int T, int H, int W,
                                                              float *__restrict__ partial /* [B][kBgChunks][T+1] */) {
   extern __shared__ float sm[];  // rc_s [T][4]
@@ -482,8 +556,13 @@ __global__ void box_gt_finalize_kernel(const float *__restrict__ partial, const 
 // grd_ws doubles as the workspace of the partial sums: it must hold B * max(T, kBgChunks * (T + 1)) floats
 int box_gt_iou_launch(const float *attn_box, size_t box_bstride, const float *gt_rect, int B, int T, int H, int W,
                       float *iou_t, int iou_bstride, float *grd, float *partial, cudaStream_t s) {
-  box_gt_partial_kernel<<<dim3(kBgChunks, B), 256, (size_t)(4 * T) * sizeof(float), s>>>(attn_box, box_bstride, gt_rect, T,
-                                                                                       H, W, partial);
+  if (T > kBgMaxT) {
+    box_gt_partial_wide_kernel<<<dim3(kBgChunks, B), 256, (size_t)(4 * T) * sizeof(float), s>>>(attn_box, box_bstride,
+                                                                                              gt_rect, T, H, W, partial);
+  } else {
+    const size_t bg_smem = ((size_t)4 * T + (H + kBgChunks - 1) / kBgChunks + 8 * (kBgMaxT + 1)) * sizeof(float);
+    box_gt_partial_kernel<<<dim3(kBgChunks, B), 256, bg_smem, s>>>(attn_box, box_bstride, gt_rect, T, H, W, partial);
+  }
   int rc = ra::finish_launch("box_gt_partial_kernel");
   if (rc != RA_OK) return rc;
   box_gt_finalize_kernel<<<B, 64, 0, s>>>(partial, gt_rect, T, H, W, iou_t, iou_bstride, grd);
