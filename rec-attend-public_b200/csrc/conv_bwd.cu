@@ -363,7 +363,7 @@ __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src, boo
 // NKY = filter rows per CTA: 3 (all nine taps, grid.z = 1) or 1 (three taps, grid.z = 3: a third of the accumulators,
 // so two CTAs fit an SM and twice the warps hide the shared-memory latency; the tiles are staged once per filter row)
 template <int RI, int RJ, int NKY>
-__global__ void __launch_bounds__(kT, NKY == 1 ? 2 : 1) conv_bwd_weight_kernel(const WgParams p) {
+__global__ void __launch_bounds__(kT, (NKY == 1 || RI * RJ <= 8) ? 2 : 1) conv_bwd_weight_kernel(const WgParams p) {
   constexpr int NT = NKY * 3;
   const int ky0 = (int)blockIdx.z * NKY;
   extern __shared__ __align__(16) float wg_smem[];
@@ -668,7 +668,8 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
     // 4 x 4 register tiles: 144 FMAs per 10 16-byte shared-memory reads and one pixel's index arithmetic - the 2 x 2
     // version (RA_WGRAD_TILE=2) spends as many issue slots on loads and addresses as on FMAs
     static const int tile = getenv("RA_WGRAD_TILE") ? atoi(getenv("RA_WGRAD_TILE")) : 4;
-    w.RI = w.RJ = (tile == 2) ? 2 : 4;
+    w.RI = (tile == 2) ? 2 : 4;
+    w.RJ = (tile == 2 || tile == 42) ? 2 : 4;  // 42: 4 x 2 tiles, half the accumulators, two CTAs per SM (experiment)
     w.CI_B = Cin <= 16 ? 16 : 32;
     w.CO_B = Cout <= 16 ? 16 : 32;
   }
@@ -676,7 +677,7 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
     // MEASURED (KITTI B=32): three taps per CTA at two CTAs per SM is slower - 33.5 ms against 22.0 ms for all the
     // weight gradients: the tiles are staged three times and the FMA : load ratio falls to 12 : 1.  Opt-in only.
     static const int nky_env = getenv("RA_WGRAD_NKY") ? atoi(getenv("RA_WGRAD_NKY")) : 3;
-    w.nky = (w.RI == 4 && nky_env == 1) ? 1 : 3;
+    w.nky = (w.RI == 4 && w.RJ == 4 && nky_env == 1) ? 1 : 3;
   }
   w.TI = w.CI_B / w.RI;
   w.TJ = w.CO_B / w.RJ;
@@ -687,7 +688,7 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
   // stages must fit twice per SM
   w.TW = Wo > 32 ? 64 : (Wo > 16 ? 32 : 16);
   // 256 pixels per tile; 128 for the 32-wide channel blocks when two CTAs (two stages each) must fit an SM
-  const int pix = ((w.RI != 4 || w.nky == 1) && (w.CI_B > 16 || w.CO_B > 16)) ? 128 : 256;
+  const int pix = ((w.RI != 4 || w.RJ != 4 || w.nky == 1) && (w.CI_B > 16 || w.CO_B > 16)) ? 128 : 256;
   w.TH = pix / w.TW;
   const size_t stage = ((size_t)(w.TH + 2) * (w.TW + 2) * w.CI_B + (size_t)w.TH * w.TW * w.CO_B) * sizeof(float);
   const size_t red = ((size_t)w.PG * w.nky * 3 * w.CI_B * w.CO_B + (size_t)w.PG * w.CO_B) * sizeof(float);
@@ -695,7 +696,7 @@ WgPlan wg_plan(int N, int Ho, int Wo, int Cin, int Cout) {
   w.smem = w.stages * stage > red ? w.stages * stage : red;
   const size_t n_tiles = (size_t)N * ((Ho + w.TH - 1) / w.TH) * ((Wo + w.TW - 1) / w.TW);
   // resident CTAs per SM: 2 (register / shared-memory bound), 1 for the 4 x 4 tiles (~180 registers per thread)
-  size_t cap = (size_t)ra::kNumSMs * ((w.RI == 4 && w.nky == 3) ? 1 : 2) /
+  size_t cap = (size_t)ra::kNumSMs * ((w.RI == 4 && w.RJ == 4 && w.nky == 3) ? 1 : 2) /
                ((size_t)w.n_ci_blk * w.n_co_blk * (size_t)(3 / w.nky));
   if (cap < 16) cap = 16;
   w.ctas = (int)(n_tiles < cap ? (n_tiles < 1 ? 1 : n_tiles) : cap);
@@ -889,12 +890,15 @@ extern "C" int ra_conv3x3_bwd_weight_ex_f32(const float *x1, int C1, int x1_bmod
     cudaFuncSetAttribute(conv_bwd_weight_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     cudaFuncSetAttribute(conv_bwd_weight_kernel<4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_bwd_weight_kernel<4, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(conv_bwd_weight_kernel<4, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     cudaFuncSetAttribute(conv_bwd_weight_kernel<1, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
     attr_done = true;
   }
   const dim3 grid(chunks, w.n_ci_blk * w.n_co_blk, 3 / w.nky);
   if (w.RI == 2)
     conv_bwd_weight_kernel<2, 2, 3><<<grid, kT, w.smem, s>>>(p);
+  else if (w.RI == 4 && w.RJ == 2)
+    conv_bwd_weight_kernel<4, 2, 3><<<grid, kT, w.smem, s>>>(p);
   else if (w.RI == 4 && w.nky == 1)
     conv_bwd_weight_kernel<4, 4, 1><<<grid, kT, w.smem, s>>>(p);
   else if (w.RI == 4)
