@@ -823,3 +823,64 @@ def test_outer_sum_row_chunks(cuda, n_in, n_out, R, bias):
   _lib.call('ra_outer_sum_f32', ops._p(A), a_stride, n_in, ops._p(D), d_stride, n_out, R, ops._p(one), ops._p(None),
             ops._stream())
   assert rel_err(one.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,T,H,W', [(2, 20, 64, 128), (3, 32, 40, 72), (2, 40, 32, 64), (1, 7, 33, 50)])
+def test_box_gt_step_many_boxes(ops, B, T, H, W):
+  """ra_box_gt_step_f32 with up to 32 GT boxes (single-pass kernel: per-column / per-row rectangle masks, sums in
+  registers), more than 32 (multi-pass fallback) and ragged sizes, against the oracle's f_inter / f_union on the filled
+  GT boxes."""
+  rng = np.random.default_rng(100 + T)
+  y_gt, _ = _masks(rng, B, T, H, W)
+  tl, br, boxgt, rect, _ = ops.get_gt_box(_g(y_gt), padding_ratio=0.2, min_padding=4.0)
+  attn = rng.random((B, 1, H, W)).astype(np.float32)
+  canvas = torch.zeros((B, H, W), device='cuda')
+  iou_t = torch.zeros((B, T), device='cuda')
+  grd = torch.zeros((B, T), device='cuda')
+  ops.box_gt_step(_g(attn), H * W, rect, _g(y_gt), None, 0, iou_t, T, grd, canvas)
+  a = torch.from_numpy(attn)
+  bg = boxgt.cpu()
+  ref_iou = OM.f_inter(a, bg) / OM.f_union(a, bg)
+  assert rel_err(iou_t.cpu().numpy(), ref_iou.numpy()) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,H,W,Cout,bias', [(3, 16, 24, 16, True), (2, 9, 11, 8, False), (5, 32, 64, 16, True),
+                                             (2, 7, 13, 64, True), (2, 8, 8, 6, True)])
+def test_bwd_weight_single_input_channel(cuda, B, H, W, Cout, bias):
+  """Weight gradient with ONE input channel (the canvas channel of the first controller layer): the bandwidth-bound
+  register kernel (Cout % 4 == 0; ragged widths, image borders) and the tiled fallback (Cout = 6) against autograd."""
+  from rec_attend_b200 import ops
+  rng = np.random.default_rng(B * 100 + W)
+  x = rng.standard_normal((B, H, W, 1)).astype(np.float32)
+  g = rng.standard_normal((B, H, W, Cout)).astype(np.float32)
+  xt, wt = torch.from_numpy(x), torch.randn(3, 3, 1, Cout, requires_grad=True)
+  bt = torch.zeros(Cout, requires_grad=True)
+  y = OM.conv2d_same(xt, wt, bt)
+  gw, gb = torch.autograd.grad(y, [wt, bt], torch.from_numpy(g))
+  dw, db = ops.conv3x3_bwd_weight(_g(x), _g(g), want_db=bias)
+  assert rel_err(dw.cpu().numpy(), gw.numpy()) < 1e-5
+  if bias:
+    assert rel_err(db.cpu().numpy(), gb.numpy()) < 1e-5
+  dw2, _ = ops.conv3x3_bwd_weight(_g(x), _g(g), want_db=False)
+  assert torch.equal(dw, dw2)  # fixed summation order
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('C', [4, 8, 16, 32, 64, 128, 96, 12, 1])
+def test_batch_norm_train_channel_counts(ops, C):
+  """Batch moments for every channel-count class of the partial reduction (float4 + shuffle path for C / 4 dividing 32,
+  the general path for 96 / 12 / 1 channels) against float64 moments."""
+  rng = np.random.default_rng(C)
+  B, H, W = 3, 20, 28
+  x = (rng.standard_normal((B, H, W, C)) * 2.0 + rng.standard_normal(C) * 3.0).astype(np.float32)
+  gamma = rng.uniform(0.5, 1.5, C).astype(np.float32)
+  beta = rng.standard_normal(C).astype(np.float32)
+  y, mean, var = ops.batch_norm_train_block(_g(x), _g(gamma), _g(beta), pool=1, relu=False)
+  x64 = x.astype(np.float64).reshape(-1, C)
+  m64, v64 = x64.mean(0), x64.var(0)
+  assert rel_err(mean.cpu().numpy(), m64) < 1e-5
+  assert rel_err(var.cpu().numpy(), v64) < 1e-5
+  ref = (x64 - m64) / np.sqrt(v64 + 1e-3) * gamma + beta
+  assert rel_err(y.cpu().numpy().reshape(-1, C), ref) < 1e-4
