@@ -235,12 +235,26 @@ __global__ void __launch_bounds__(256) extract_cols_kernel(const float *__restri
 }
 
 // ------------------------------------------------------------------ paste-back
-constexpr int kPbTY = 8;      // rows per tile
+constexpr int kPbTY = 8;      // rows per tile.  MEASURED (tools/pb_prof.py): 16 rows per tile (half the CTAs pay the patch load + Fy^T P
+                              // prologue) is no faster - 23.1 vs 22.1 us per launch
 constexpr int kPbTX = 128;    // columns per tile
 constexpr int kPbTilesY = 1;  // consecutive row tiles served by one CTA.  MEASURED: 4 tiles per CTA (fewer, fatter CTAs,
                               // patch loaded once) is slower - 54 us vs 37 us per launch at 256x512, B=32 - because
                               // the tiles inside the box serialise within a CTA; 1 keeps them spread over the SMs.
 
+#ifdef RA_PB_PROF
+__device__ unsigned long long g_pb_prof[4096 * 8];
+#define PB_PROF(i)                                                                                         \
+  do {                                                                                                     \
+    if (threadIdx.x == 0) {                                                                                \
+      unsigned long long t_;                                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                               \
+      g_pb_prof[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) % 4096 * 8 + (i)] = t_;   \
+    }                                                                                                      \
+  } while (0)
+#else
+#define PB_PROF(i) do {} while (0)
+#endif
 __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict__ patch,
                                                          const float *__restrict__ fy, const float *__restrict__ fx,
                                                          const int *__restrict__ band,
@@ -248,8 +262,10 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
                                                          int disable_overwrite, float *__restrict__ attn_box,
                                                          float *__restrict__ y_out, size_t out_bstride,
                                                          float *__restrict__ canvas) {
+  PB_PROF(0);
   ra::pdl_wait();     // PDL: the previous kernel of the stream has completed, its results are visible
   ra::pdl_trigger();  // the next kernel may be scheduled (it waits the same way)
+  PB_PROF(1);
   __shared__ float P_s[kMaxF * kMaxF];       // patch [F][F]
   __shared__ float wy_s[kPbTY][kMaxF];       // fy[i][y] for the tile rows
   __shared__ float t2_s[kPbTY][kMaxF + 1];   // sum_i fy[i][y] P[i][j]
@@ -314,6 +330,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
           }
         }
       }
+      PB_PROF(7);
       continue;
     }
 
@@ -338,6 +355,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
       jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
     }
     const float g_box = bo[RA_BOX_GAMMA_BOX], g_y = bo[RA_BOX_GAMMA_Y];
+    PB_PROF(2);
     __syncthreads();  // the previous tile's readers of wy_s / t2_s / sy_s are done
     if (has_patch && !p_loaded) {
       for (int idx = tid; idx < F * F; idx += blockDim.x) P_s[idx] = patch[(size_t)b * F * F + idx];
@@ -349,6 +367,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
       wy_s[ty][i] = (y < H) ? fy[((size_t)b * F + i) * H + y] : 0.f;
     }
     __syncthreads();
+    PB_PROF(3);
     if (has_patch) {
       for (int idx = tid; idx < kPbTY * F; idx += blockDim.x) {
         const int ty = idx / F, j = idx - ty * F;
@@ -363,6 +382,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
       sy_s[tid] = a;
     }
     __syncthreads();
+    PB_PROF(4);
 
     float acc[kRows];
 #pragma unroll
@@ -370,6 +390,13 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
     float sx = 0.f;
     if (x < W) {
       const float *fxp = fx + (size_t)b * F * W + x;
+      // the canvas values of the epilogue are requested before the tap loop: their L2 / HBM round trip overlaps it
+      float cvp[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const int y = y0 + rh * kRows + r;
+        cvp[r] = (has_patch && y < H) ? canvas[(size_t)b * H * W + (size_t)y * W + x] : 0.f;
+      }
       // four filter loads in flight per round (same summation order as the plain loop).  MEASURED: staging these Fx
       // rows in shared memory (24 KB per CTA, coalesced loads) is slower - 45 us vs 34 us per launch - the lost
       // occupancy costs more than the dependent L2 round trips.
@@ -387,6 +414,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
           }
         }
       }
+      PB_PROF(5);
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         const int y = y0 + rh * kRows + r;
@@ -396,7 +424,7 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
           attn_box[(size_t)b * out_bstride + pix] = ra::sigmoidf_acc(g_box * (sy_s[rh * kRows + r] * sx) - 5.0f);
         if (has_patch) {  // full_model.py:810-818, 845
           const size_t cpix = (size_t)b * H * W + pix;
-          const float cv = canvas[cpix];
+          const float cv = cvp[r];
           float v = ra::sigmoidf_acc(g_y * acc[r] - 5.0f);
           if (disable_overwrite) v *= (1.0f - cv);
           y_out[(size_t)b * out_bstride + pix] = v;
@@ -404,10 +432,21 @@ __global__ void __launch_bounds__(256) paste_back_kernel(const float *__restrict
         }
       }
     }
+    PB_PROF(6);
   }
 }
 
 }  // namespace
+
+#ifdef RA_PB_PROF
+extern "C" int ra_debug_pb_prof(unsigned long long *host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_pb_prof, sizeof(unsigned long long) * 4096 * 8) == cudaSuccess ? 0 : 1;
+}
+extern "C" int ra_debug_pb_prof_clear() {
+  static unsigned long long z[4096 * 8];
+  return cudaMemcpyToSymbol(g_pb_prof, z, sizeof(z)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int ra_gaussian_filters_f32(const float *box, int B, int H, int W, int F, float *fy, float *fx,
                                        int32_t *band, void *stream) {
