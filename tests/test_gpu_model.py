@@ -254,8 +254,9 @@ def test_sub_batch_chains_agree(cuda, use_graph):
 from conftest import oracle_fp64 as _oracle_fp64  # noqa: E402
 
 
-def test_training_mode_forward_batch_stat_bn(cuda):
-  """phase_train=True, use_knob=False: batch-statistics BN in every conv block, EMA shadows moved in place
+@pytest.mark.parametrize('H,W,T,B', [(64, 128, 3, 4), (256, 512, 2, 2)])
+def test_training_mode_forward_batch_stat_bn(cuda, H, W, T, B):
+  """phase_train=True, use_knob=False (second case: the BASELINE configs[2] resolution): batch-statistics BN in every conv block, EMA shadows moved in place
   (nnlib.py:96-119), against the oracle's training-mode forward.
 
   With batch statistics and random weights the decode loop amplifies round-off ~10x per step - the fp32 oracle
@@ -264,9 +265,8 @@ def test_training_mode_forward_batch_stat_bn(cuda):
   below 1e-3 of the scale or within 10x the fp32 oracle's own distance."""
   import rec_attend_b200 as ra
   from rec_attend_b200.full_model import FullModel
-  T = 3
-  opt = ra.config.full_model_opt('kitti', 64, 128, T, use_knob=False)
-  batch = ra.synthetic.make_batch(opt, 4, seed=5)
+  opt = ra.config.full_model_opt('kitti', H, W, T, use_knob=False)
+  batch = ra.synthetic.make_batch(opt, B, seed=5)
   weights = ra.synthetic.make_weights(opt, seed=4321)
   ref = OM.full_model_forward(opt, weights, batch, phase_train=True)
   O64 = _oracle_fp64()
@@ -294,7 +294,8 @@ def test_training_mode_forward_batch_stat_bn(cuda):
   assert len(ref['ema_updates']) == (8 + 6 + 7) * T * 2
   worst = max(rel_err(new_w[k], v.numpy()) for k, v in ref['ema_updates'].items())
   assert worst <= 2e-3, worst
-  assert rel_err(new_w['ctrl_cnn_3_2_ema_var'], weights['ctrl_cnn_3_2_ema_var']) > 1e-3  # the shadows did move
+  kk = 'ctrl_cnn_3_%d_ema_var' % (T - 1)
+  assert rel_err(new_w[kk], weights[kk]) > 1e-3  # the shadows did move
   # eval forward after training: uses the moved shadows (refolded), like the oracle fed with the exported weights
   ref_eval = OM.full_model_forward(opt, new_w, batch)
   out_eval = model.forward(batch)

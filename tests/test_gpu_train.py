@@ -76,6 +76,7 @@ CASES = [
     ('kitti', 64, 128, 2, 4, True, False),
     ('kitti', 64, 128, 2, 4, True, True),
     ('cityscapes', 64, 128, 2, 4, True, False),   # use_iou_box: the box loss reaches the controller through coordinates
+    ('kitti', 256, 512, 2, 2, True, False),       # BASELINE configs[2] resolution (tile plans depend on the map sizes)
 ]
 
 

@@ -17,6 +17,7 @@ from rec_attend_b200.full_model import FullModel  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--eval', action='store_true')
 ap.add_argument('--config', type=int, default=2)
+ap.add_argument('--by-grid', default='', help='substring of kernel names to break down by launch grid')
 ap.add_argument('--dump-step', type=int, default=-1, help='print the kernel sequence of this decode step')
 args = ap.parse_args()
 cfg = config.BASELINE_CONFIGS[args.config]
@@ -81,3 +82,14 @@ if args.dump_step >= 0:
     print('decode step %d: start (us, relative), duration, end, kernel' % args.dump_step)
     for e in ev[a - 8:b + 1]:
       print('  %9.2f  %8.2f  %9.2f  %s' % (e['ts'] - t0, e['dur'], e['ts'] + e['dur'] - t0, short(e['name'])))
+
+if args.by_grid:
+  byg = collections.defaultdict(lambda: [0, 0.0])
+  for e in ev:
+    if args.by_grid in e['name']:
+      k = (short(e['name']), tuple(e.get('args', {}).get('grid', [])))
+      byg[k][0] += 1
+      byg[k][1] += e['dur']
+  print('kernels matching %r by grid:' % args.by_grid)
+  for k, (n, t) in sorted(byg.items(), key=lambda kv: -kv[1][1])[:40]:
+    print('  %9.1f us  x%-4d avg %7.2f us  %-34s grid %s' % (t, n, t / n, k[0], k[1]))
