@@ -498,6 +498,11 @@ int ra_outer_sum_ex_f32(const float *A, size_t a_stride, int n_in, const float *
 size_t ra_fg_head_workspace(void);
 int ra_fg_head_f32(const float *logits, size_t npix, int nsc, int nori, const float *y_gt, const float *d_gt,
                    int loss_is_bce, float *y_out, float *d_out, float *y_hard, float *out, void *ws, void *stream);
+/* Gradient of loss = foreground_loss [+ orientation_ce] (fg_model.py:223-250) at the logits: d_logits [npix, nsc+nori].
+ * y_out / d_out = the head's outputs, ws = the workspace ra_fg_head_f32 filled on the same inputs (it holds the global
+ * sums the IoU loss and the masked cross-entropy divide by).  Training mode of the FCN. */
+int ra_fg_head_bwd_f32(const float *y_out, const float *d_out, size_t npix, int nsc, int nori, const float *y_gt,
+                       const float *d_gt, int loss_is_bce, const void *ws, float *d_logits, void *stream);
 
 /* --------------------------------------------------------------------------------------
  * Instance-label post-processing — utils/postprocess.py as chained by

@@ -83,6 +83,26 @@ def box_model_grads(opt, weights, batch, canvas_noise=None, include_weight_decay
   return grads, {k: ({kk: det(vv) for kk, vv in v.items()} if isinstance(v, dict) else det(v)) for k, v in out.items()}
 
 
+def fg_model_grads(opt, weights, batch, model_module=OM, dtype=torch.float32):
+  """Gradients of the foreground / orientation FCN's training-mode loss (fg_model.py:174-250: batch-statistics BN,
+  loss = foreground loss [+ orientation cross-entropy]) by weight key, WITHOUT the weight-decay term (the optimiser
+  adds wd * w, like for the instance model).  The reference minimises total_loss with Adam and no gradient clipping
+  (fg_model.py:258-265)."""
+  keys = trainable_keys(weights)
+  leaves = {}
+  for k, v in weights.items():
+    t = torch.as_tensor(np.asarray(v), dtype=dtype).clone()
+    if k in keys:
+      t.requires_grad_(True)
+    leaves[k] = t
+  b = {k: torch.as_tensor(np.asarray(v), dtype=dtype) for k, v in batch.items()}
+  out = model_module.fg_model_forward(opt, leaves, b, phase_train=True)
+  g = torch.autograd.grad(out['loss'], [leaves[k] for k in keys], allow_unused=True)
+  grads = {k: (None if gi is None else gi.detach().numpy()) for k, gi in zip(keys, g)}
+  det = lambda v: v.detach() if isinstance(v, torch.Tensor) else v
+  return grads, {k: ({kk: det(vv) for kk, vv in v.items()} if isinstance(v, dict) else det(v)) for k, v in out.items()}
+
+
 def train_step(opt, weights, batch, adam_m, adam_v, global_step, draws=None, frozen=(), world_grads=None):
   """One ``sess.run([loss, train_step])`` (runner.py:98-105): forward + backward + clip + Adam + EMA shadow update.
 

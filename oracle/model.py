@@ -881,4 +881,6 @@ def fg_model_forward(opt, weights, batch, phase_train=False):
     correct = (d_out.argmax(dim=3) == d_gt.argmax(dim=3)).float()
     model['orientation_acc'] = (correct * y_gt_mask[..., 0]).sum() / y_gt_mask.sum()
   model['loss'] = loss
+  if ema_out is not None:
+    model['ema_updates'] = ema_out  # the moved EMA shadows of a training-mode forward (nnlib.py:104-108)
   return model

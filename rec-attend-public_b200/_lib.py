@@ -97,6 +97,7 @@ _SIGNATURES = {
     'ra_loss_select_f32': [_P, _P, _P, _F, _F, _P],
     'ra_u8_to_f32': [_P, _Z, _P, _P],
     'ra_fg_head_f32': [_P, _Z, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
+    'ra_fg_head_bwd_f32': [_P, _P, _Z, _I, _I, _P, _P, _I, _P, _P, _P],
     'ra_adam_step_f32': [_P, _P, _P, _P, _P, _Z, _F, _F, _F, _F, _F, _F, _I, _P],
     'ra_postprocess_f32': [_P, _P, _P, _I, _I, _I, _I, ctypes.c_double, _F, _P, _P, _P, _P, _P, _P],
 }

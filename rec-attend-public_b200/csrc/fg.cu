@@ -156,6 +156,63 @@ __global__ void fg_finalize_kernel(const double *__restrict__ partial, int nbloc
   }
 }
 
+// Gradient of loss = foreground_loss [+ orientation_ce] (fg_model.py:223-240) at the logits, one pass over the pixels.
+// The global sums the IoU loss and the masked cross-entropy divide by are re-read from the per-CTA partials the forward
+// head (ra_fg_head_f32 on the same inputs) left in its workspace - every CTA adds them in the same fixed order.
+//   nsc == 1:  y = sigmoid(z);  'iou': dL/dy = -(g U - I (1 - g)) / U^2,  U = sum y + sum g - I + 1e-5 (f_iou_all);
+//              'bce': dL/dy = (-g / (y + 1e-5) + (1 - g) / (1 - y + 1e-5)) / npix;            dz = dL/dy y (1 - y)
+//   nsc  > 1:  y = softmax(z);  'iou' over classes 1..: as above per class (0 for class 0);  else f_ce: -g / (y + 1e-5) / npix;
+//              dz_c = y_c (dL/dy_c - sum_k y_k dL/dy_k)
+//   orientation: d = softmax(zo);  dL/dd_c = -mask dg_c / (d_c + 1e-5) / sum(mask);  softmax backward.
+__global__ void __launch_bounds__(kFgThreads) fg_head_bwd_kernel(const float *__restrict__ y_out,
+                                                                 const float *__restrict__ d_out, size_t npix, int nsc,
+                                                                 int nori, const float *__restrict__ y_gt,
+                                                                 const float *__restrict__ d_gt, int loss_is_bce,
+                                                                 const double *__restrict__ partial, int nblocks,
+                                                                 float *__restrict__ d_logits) {
+  __shared__ double tot_s[kFgAcc];
+  if (threadIdx.x < kFgAcc) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * kFgAcc + threadIdx.x];
+    tot_s[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const float I = (float)tot_s[0], So = (float)tot_s[1], Sg = (float)tot_s[2], M = (float)tot_s[7];
+  const float U = So + Sg - I + 1e-5f;
+  const float inv_npix = 1.0f / (float)npix;
+  const int C = nsc + nori;
+  const int c0 = (nsc == 1) ? 0 : 1;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+    float *dz = d_logits + p * C;
+    float mask = 0.f;
+    if (nsc == 1) {
+      const float y = y_out[p], g = y_gt[p];
+      mask = g;
+      const float dy = loss_is_bce ? (-g / (y + 1e-5f) + (1.f - g) / (1.f - y + 1e-5f)) * inv_npix
+                                   : -(g * U - I * (1.f - g)) / (U * U);
+      dz[0] = dy * y * (1.f - y);
+    } else {
+      float dy[kFgMaxC], dot = 0.f;
+      for (int c = 0; c < nsc; ++c) {
+        const float y = y_out[p * nsc + c], g = y_gt[p * nsc + c];
+        if (c >= c0) mask = fmaxf(mask, g);
+        dy[c] = loss_is_bce ? -g / (y + 1e-5f) * inv_npix : (c >= c0 ? -(g * U - I * (1.f - g)) / (U * U) : 0.f);
+        dot = fmaf(y, dy[c], dot);
+      }
+      for (int c = 0; c < nsc; ++c) dz[c] = y_out[p * nsc + c] * (dy[c] - dot);
+    }
+    if (nori > 0) {
+      float dd[kFgMaxC], dot = 0.f;
+      for (int c = 0; c < nori; ++c) {
+        const float d = d_out[p * nori + c];
+        dd[c] = -mask * d_gt[p * nori + c] / (d + 1e-5f) / M;
+        dot = fmaf(d, dd[c], dot);
+      }
+      for (int c = 0; c < nori; ++c) dz[nsc + c] = d_out[p * nori + c] * (dd[c] - dot);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" size_t ra_fg_head_workspace(void) { return (size_t)kFgBlocks * kFgAcc * sizeof(double); }
@@ -177,4 +234,19 @@ extern "C" int ra_fg_head_f32(const float *logits, size_t npix, int nsc, int nor
   if (rc != RA_OK || y_gt == nullptr) return rc;
   fg_finalize_kernel<<<1, 32, 0, s>>>(partial, blocks, (double)npix, nori > 0 ? 1 : 0, loss_is_bce, out);
   return ra::finish_launch("fg_finalize_kernel");
+}
+
+extern "C" int ra_fg_head_bwd_f32(const float *y_out, const float *d_out, size_t npix, int nsc, int nori,
+                                  const float *y_gt, const float *d_gt, int loss_is_bce, const void *ws, float *d_logits,
+                                  void *stream) {
+  if (nsc < 1 || nori < 0 || nsc > kFgMaxC || nori > kFgMaxC) return RA_ERR_INVALID_ARG;
+  if (!y_out || !y_gt || !ws || !d_logits || (nori > 0 && (!d_out || !d_gt))) return RA_ERR_INVALID_ARG;
+  if (npix == 0) return RA_OK;
+  size_t want = (npix + kFgThreads - 1) / kFgThreads;
+  const int blocks = (int)(want < (size_t)kFgBlocks ? want : (size_t)kFgBlocks);  // the forward head's grid
+  fg_head_bwd_kernel<<<blocks, kFgThreads, 0, ra::as_stream(stream)>>>(y_out, d_out, npix, nsc, nori, y_gt, d_gt,
+                                                                       loss_is_bce,
+                                                                       reinterpret_cast<const double *>(ws), blocks,
+                                                                       d_logits);
+  return ra::finish_launch("fg_head_bwd_kernel");
 }
