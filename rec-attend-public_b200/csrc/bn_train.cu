@@ -27,8 +27,11 @@ __device__ __forceinline__ double shfl_xor_double(double v, int mask) {
   return __hiloint2double(hi, lo);
 }
 
+// COHERENT: the partials were written by other CTAs of the SAME launch (fused kernel below): read them through L2
+// (ld.global.cg), not through the non-coherent path.
+template <bool COHERENT = false>
 __device__ __forceinline__ void reduce_partials(const float *__restrict__ partial, int ctas, int C, double inv_npix,
-                                                float *out_s, double *scratch /* [kBnThreads] */) {
+                                                float *out_s, double *scratch /* [kBnThreads * 4] */) {
   const int tid = threadIdx.x;
   const int q_n = C >> 2;
   if ((C & 3) == 0 && q_n <= 32 && (32 % q_n) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0) {
@@ -41,7 +44,7 @@ __device__ __forceinline__ void reduce_partials(const float *__restrict__ partia
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int idx = i + u * kBnThreads;
-        v[u] = idx < n4 ? __ldg(p4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u] = idx < n4 ? (COHERENT ? __ldcg(p4 + idx) : __ldg(p4 + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -78,15 +81,15 @@ __device__ __forceinline__ void reduce_partials(const float *__restrict__ partia
   if (j < groups) {
     int k = j;
     for (; k + 3 * groups < ctas; k += 4 * groups) {
-      const float p0 = __ldg(partial + (size_t)k * C + c), p1 = __ldg(partial + (size_t)(k + groups) * C + c);
-      const float p2 = __ldg(partial + (size_t)(k + 2 * groups) * C + c);
-      const float p3 = __ldg(partial + (size_t)(k + 3 * groups) * C + c);
+      const float p0 = __ldcg(partial + (size_t)k * C + c), p1 = __ldcg(partial + (size_t)(k + groups) * C + c);
+      const float p2 = __ldcg(partial + (size_t)(k + 2 * groups) * C + c);
+      const float p3 = __ldcg(partial + (size_t)(k + 3 * groups) * C + c);
       s0 += (double)p0;
       s1 += (double)p1;
       s2 += (double)p2;
       s3 += (double)p3;
     }
-    for (; k < ctas; k += groups) s0 += (double)__ldg(partial + (size_t)k * C + c);
+    for (; k < ctas; k += groups) s0 += (double)__ldcg(partial + (size_t)k * C + c);
   }
   const double s = (s0 + s1) + (s2 + s3);
   scratch[tid] = s;
@@ -235,6 +238,151 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const float *__res
   }
 }
 
+// ---- small maps (the patch network, the last controller layers): ONE launch.  A CTA owns whole output rows; their
+// input rows are one contiguous chunk that is copied to shared memory once (cp.async) and serves all three passes -
+// channel sums, centred squared sums, normalise + ReLU + pool - with a grid barrier after each of the two reductions
+// (all CTAs are co-resident: grid <= number of SMs, one CTA per SM).  One read of x instead of three, one launch instead
+// of three.  Needs C % 4 == 0, C / 4 dividing 256, 16-byte aligned x, the slice in <= kBnFusedSmem bytes.
+constexpr size_t kBnFusedSmem = 180 * 1024;
+
+__device__ __forceinline__ void bn_grid_barrier(unsigned int *counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    unsigned long long polls = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      // all CTAs are co-resident by construction; a bounded wait turns a violated assumption (e.g. two such kernels
+      // sharing the SMs from concurrent streams) into an error instead of a hung device
+      if (++polls > (1ull << 31)) __trap();
+    } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(kBnThreads, 1) bn_fused_kernel(const float *__restrict__ x, int B, int H, int W, int C,
+                                                                 const float *__restrict__ gamma,
+                                                                 const float *__restrict__ beta, float eps, float decay,
+                                                                 int relu, float *__restrict__ sum_p,
+                                                                 float *__restrict__ sq_p, unsigned int *counters,
+                                                                 float *__restrict__ ema_mean, float *__restrict__ ema_var,
+                                                                 float *__restrict__ batch_mean,
+                                                                 float *__restrict__ batch_var, float *__restrict__ y) {
+  extern __shared__ __align__(16) float xs_s[];  // my input rows [rows_in][W][C]
+  __shared__ float mean_s[kBnMaxC], var_s[kBnMaxC], inv_s[kBnMaxC], sh_s[kBnMaxC];
+  __shared__ float red_s[kBnThreads * 4];
+  __shared__ double dbl_s[kBnThreads * 4];
+  const int tid = threadIdx.x;
+  const int Ho = H / POOL, Wo = W / POOL;
+  const int rows_out_total = B * Ho;
+  const int rows_per = (rows_out_total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int r0 = min((int)blockIdx.x * rows_per, rows_out_total), r1 = min(r0 + rows_per, rows_out_total);
+  const size_t row_floats = (size_t)W * C;
+  const int rows_in = (r1 - r0) * POOL;
+  const float *src = x + (size_t)r0 * POOL * row_floats;
+  const int n4 = (int)((size_t)rows_in * row_floats / 4);
+  {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(xs_s);
+    for (int i = tid; i < n4; i += kBnThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)i * 16u), "l"(src + (size_t)i * 4)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  const int cg_n = C >> 2, lanes = kBnThreads / cg_n;
+  const int cg = tid % cg_n, pl = tid / cg_n;
+  const int npix_mine = rows_in * W;
+  const double inv_npix = 1.0 / (double)((size_t)B * H * W);
+  const float4 *x4 = reinterpret_cast<const float4 *>(xs_s);
+  // ---- pass 1 / pass 2: per-thread sums over its pixels (fixed stride), CTA sum in a fixed order, per-CTA partial
+  for (int pass = 0; pass < 2; ++pass) {
+    float4 ctr = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pass == 1) ctr = make_float4(mean_s[cg * 4], mean_s[cg * 4 + 1], mean_s[cg * 4 + 2], mean_s[cg * 4 + 3]);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = pl; p < npix_mine; p += lanes) {
+      const float4 v = x4[p * cg_n + cg];
+      if (pass == 0) {
+        a.x += v.x;
+        a.y += v.y;
+        a.z += v.z;
+        a.w += v.w;
+      } else {
+        const float dx = v.x - ctr.x, dy = v.y - ctr.y, dz = v.z - ctr.z, dw = v.w - ctr.w;
+        a.x = fmaf(dx, dx, a.x);
+        a.y = fmaf(dy, dy, a.y);
+        a.z = fmaf(dz, dz, a.z);
+        a.w = fmaf(dw, dw, a.w);
+      }
+    }
+    *reinterpret_cast<float4 *>(red_s + tid * 4) = a;
+    __syncthreads();
+    float *part = (pass == 0 ? sum_p : sq_p) + (size_t)blockIdx.x * C;
+    for (int c = tid; c < C; c += kBnThreads) {
+      const int g = c >> 2, e = c & 3;
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red_s[(l * cg_n + g) * 4 + e];
+      part[c] = s;
+    }
+    bn_grid_barrier(counters + pass, gridDim.x);
+    reduce_partials<true>(pass == 0 ? sum_p : sq_p, (int)gridDim.x, C, inv_npix, pass == 0 ? mean_s : var_s, dbl_s);
+  }
+  for (int c = tid; c < C; c += kBnThreads) {
+    const float mean = mean_s[c], var = var_s[c];
+    const float inv = gamma[c] * rsqrtf(var + eps);
+    inv_s[c] = inv;
+    sh_s[c] = beta[c] - mean * inv;
+    if (blockIdx.x == 0) {
+      if (batch_mean != nullptr) batch_mean[c] = mean;
+      if (batch_var != nullptr) batch_var[c] = var;
+      if (ema_mean != nullptr) ema_mean[c] = ema_mean[c] - (1.0f - decay) * (ema_mean[c] - mean);
+      if (ema_var != nullptr) ema_var[c] = ema_var[c] - (1.0f - decay) * (ema_var[c] - var);
+    }
+  }
+  __syncthreads();
+  // ---- normalise + ReLU + pool out of shared memory
+  const int n_out = (r1 - r0) * Wo * cg_n;
+  float4 *y4 = reinterpret_cast<float4 *>(y + (size_t)r0 * Wo * C);
+  for (int idx = tid; idx < n_out; idx += kBnThreads) {
+    const int g = idx % cg_n;
+    const int opix = idx / cg_n;
+    const int ox = opix % Wo, orow = opix / Wo;
+    const float4 inv = *reinterpret_cast<const float4 *>(inv_s + g * 4), sh = *reinterpret_cast<const float4 *>(sh_s + g * 4);
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int py = 0; py < POOL; ++py)
+#pragma unroll
+      for (int px = 0; px < POOL; ++px) {
+        const float4 v = x4[((orow * POOL + py) * W + ox * POOL + px) * cg_n + g];
+        best.x = fmaxf(best.x, fmaf(v.x, inv.x, sh.x));
+        best.y = fmaxf(best.y, fmaf(v.y, inv.y, sh.y));
+        best.z = fmaxf(best.z, fmaf(v.z, inv.z, sh.z));
+        best.w = fmaxf(best.w, fmaf(v.w, inv.w, sh.w));
+      }
+    if (relu) best = make_float4(fmaxf(best.x, 0.f), fmaxf(best.y, 0.f), fmaxf(best.z, 0.f), fmaxf(best.w, 0.f));
+    y4[idx] = best;
+  }
+}
+
+// grid of the fused kernel, or 0 when the shape does not qualify
+int bn_fused_ctas(const float *x, int B, int H, int W, int C, int pool) {
+  if ((C & 3) != 0 || (kBnThreads % (C >> 2)) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 0;
+  // MEASURED (KITTI B=32 training step, in-graph): 11-12 us per block against ~14 us for the three launches - the two
+  // grid barriers (atomics + polling over 148 CTAs + the partial reduction) cost what the saved passes gain: 80.4 ->
+  // 80.1 ms per step.  Not worth a spin-waiting kernel on the default path: opt-in (RA_BN_FUSED=1).
+  if (getenv("RA_BN_FUSED") == nullptr) return 0;
+  const int rows_out = B * (H / pool);
+  const int ctas = rows_out < ra::kNumSMs ? rows_out : ra::kNumSMs;
+  if (ctas < 1) return 0;
+  const int rows_per = (rows_out + ctas - 1) / ctas;
+  const size_t bytes = (size_t)rows_per * pool * W * C * sizeof(float);
+  return bytes <= kBnFusedSmem ? ctas : 0;
+}
+
 int bn_ctas(size_t npix, int C) {
   const int lanes = kBnThreads / ((C & 3) ? C : C / 4);
   // at least 16 pixels per thread (two rounds of 8 loads in flight): the small patch-network maps get a few dozen
@@ -253,7 +401,11 @@ int bn_ctas(size_t npix, int C) {
 
 extern "C" size_t ra_bn_train_workspace(int B, int H, int W, int C) {
   if (B < 1 || H < 1 || W < 1 || C < 1 || C > kBnMaxC) return 0;
-  return (size_t)2 * bn_ctas((size_t)B * H * W, C) * C;  // floats: per-CTA sums, then per-CTA centred squared sums
+  // floats: per-CTA sums, then per-CTA centred squared sums (three-pass kernels: bn_ctas CTAs; fused kernel: <= one per
+  // SM), then the two barrier counters of the fused kernel
+  size_t ctas = (size_t)bn_ctas((size_t)B * H * W, C);
+  if (ctas < (size_t)ra::kNumSMs) ctas = (size_t)ra::kNumSMs;
+  return (size_t)2 * ctas * C + 4;
 }
 
 extern "C" int ra_bn_train_block_f32(const float *x, int B, int H, int W, int C, const float *gamma, const float *beta,
@@ -266,6 +418,30 @@ extern "C" int ra_bn_train_block_f32(const float *x, int B, int H, int W, int C,
   if (!x || !gamma || !beta || !workspace || !y) return RA_ERR_INVALID_ARG;
   cudaStream_t s = ra::as_stream(stream);
   const size_t npix = (size_t)B * H * W;
+  const int fctas = bn_fused_ctas(x, B, H, W, C, pool);
+  if (fctas > 0) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(bn_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBnFusedSmem);
+      cudaFuncSetAttribute(bn_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBnFusedSmem);
+      attr_done = true;
+    }
+    size_t wctas = (size_t)bn_ctas(npix, C);
+    if (wctas < (size_t)ra::kNumSMs) wctas = (size_t)ra::kNumSMs;
+    float *f_sum = workspace, *f_sq = workspace + (size_t)fctas * C;
+    unsigned int *counters = reinterpret_cast<unsigned int *>(workspace + (size_t)2 * wctas * C);
+    cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), s);
+    const int rows_out = B * (H / pool);
+    const int rows_per = (rows_out + fctas - 1) / fctas;
+    const size_t smem = (size_t)rows_per * pool * W * C * sizeof(float);
+    if (pool == 2)
+      bn_fused_kernel<2><<<fctas, kBnThreads, smem, s>>>(x, B, H, W, C, gamma, beta, eps, decay, relu, f_sum, f_sq, counters,
+                                                        ema_mean, ema_var, batch_mean, batch_var, y);
+    else
+      bn_fused_kernel<1><<<fctas, kBnThreads, smem, s>>>(x, B, H, W, C, gamma, beta, eps, decay, relu, f_sum, f_sq, counters,
+                                                        ema_mean, ema_var, batch_mean, batch_var, y);
+    return ra::finish_launch("bn_fused_kernel");
+  }
   const int ctas = bn_ctas(npix, C);
   float *sum_p = workspace, *sq_p = workspace + (size_t)ctas * C;
   const bool vec = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;

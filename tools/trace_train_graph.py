@@ -17,12 +17,13 @@ from rec_attend_b200.full_model import FullModel  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--eval', action='store_true')
 ap.add_argument('--config', type=int, default=2)
+ap.add_argument('--batch', type=int, default=0)
 ap.add_argument('--by-grid', default='', help='substring of kernel names to break down by launch grid')
 ap.add_argument('--dump-step', type=int, default=-1, help='print the kernel sequence of this decode step')
 args = ap.parse_args()
 cfg = config.BASELINE_CONFIGS[args.config]
 opt = dict(config.baseline_opt(args.config), use_knob=not args.eval)
-B = cfg['B']
+B = args.batch or cfg['B']
 batch = {k: torch.from_numpy(v).cuda() for k, v in synthetic.make_batch(opt, B).items()}
 draws = None if args.eval else synthetic.make_knob_draws(opt, B, global_step=0, seed=7, device='cuda')
 model = FullModel(opt).load_weights(synthetic.make_weights(opt))
