@@ -884,3 +884,30 @@ def test_batch_norm_train_channel_counts(ops, C):
   assert rel_err(var.cpu().numpy(), v64) < 1e-5
   ref = (x64 - m64) / np.sqrt(v64 + 1e-3) * gamma + beta
   assert rel_err(y.cpu().numpy().reshape(-1, C), ref) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,H,W,C,pool', [(32, 48, 48, 16, 1), (4, 24, 24, 32, 2), (3, 12, 12, 64, 1), (2, 16, 32, 64, 2),
+                                          (5, 6, 6, 8, 1)])
+def test_batch_norm_fused_small_map_kernel(ops, monkeypatch, B, H, W, C, pool):
+  """The opt-in one-launch batch norm (RA_BN_FUSED=1: slice resident in shared memory, two grid barriers) against the
+  three-launch path and float64 moments; EMA shadows moved alike."""
+  rng = np.random.default_rng(B * 1000 + C)
+  x = (rng.standard_normal((B, H, W, C)) * 1.5 + rng.standard_normal(C)).astype(np.float32)
+  gamma = rng.uniform(0.5, 1.5, C).astype(np.float32)
+  beta = rng.standard_normal(C).astype(np.float32)
+  em0, ev0 = rng.standard_normal(C).astype(np.float32), rng.uniform(0.5, 1.5, C).astype(np.float32)
+  res = {}
+  for mode in ('three', 'fused'):
+    if mode == 'fused':
+      monkeypatch.setenv('RA_BN_FUSED', '1')
+    else:
+      monkeypatch.delenv('RA_BN_FUSED', raising=False)
+    em, ev = _g(em0.copy()), _g(ev0.copy())
+    y, mean, var = ops.batch_norm_train_block(_g(x), _g(gamma), _g(beta), em, ev, pool=pool, relu=True)
+    torch.cuda.synchronize()
+    res[mode] = [t.cpu().numpy() for t in (y, mean, var, em, ev)]
+  for a, b in zip(res['three'], res['fused']):
+    assert rel_err(b, a) < 1e-5
+  x64 = x.astype(np.float64).reshape(-1, C)
+  assert rel_err(res['fused'][1], x64.mean(0)) < 1e-5 and rel_err(res['fused'][2], x64.var(0)) < 1e-5
