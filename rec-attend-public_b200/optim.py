@@ -8,8 +8,8 @@ sorted key order.  A training step then needs exactly one collective and one ker
   grads (flat, this rank's shard of the batch)  --NCCL all-reduce(SUM)-->  x 1/world  -->  ra_adam_step_f32
   (weight-decay gradient, clip to [-1, 1], Adam with eps 1e-7, TF-0.12 form)
 
-Clip-after-average keeps the reference's global-batch semantics.  The backward pass that PRODUCES the gradients is
-not built yet; this module is the tail of the step and is tested on given gradients.
+Clip-after-average keeps the reference's global-batch semantics.  The gradients come from the backward pass of
+`train.py` (FullModel / BoxModel.train_step) or `fg_model.py`; this module is the tail of the step.
 """
 import math
 
