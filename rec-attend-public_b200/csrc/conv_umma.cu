@@ -35,6 +35,7 @@
 // two filter parts are stacked along N ([B_hi; B_lo], one MMA with N' = 2N reads A_hi once) and
 // summed in the epilogue; small feature maps split N over CTAs to fill the 148 SMs.
 #include <cuda.h>  // CUtensorMap and its enums only; the encoder is fetched with cudaGetDriverEntryPoint
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -87,6 +88,7 @@ struct UmmaConvParams {
   int raw_off;      // up == 2 only: offset of that landing zone inside a stage
   int split_corr;   // merged mode: accumulate A_lo B_hi in the second accumulator half (RA_UMMA_JOINT_CORR=1: first)
   int four_term;    // merged mode: the A_lo instruction also spans [B_hi; B_lo] (adds the lo x lo partial product)
+  int f16;          // fp16 hi / lo operand split (experiment, RA_UMMA_F16): kind::f16, K = 16 per instruction
   int pdl;          // launched with programmatic stream serialization: griddepcontrol.wait before touching activations
   int grid;         // CTAs that serve this layer (= gridDim.x of a single-layer launch; <= gridDim.x inside a chain)
   long long *dbg;   // optional per-CTA timeline (ra_debug_conv_timeline), 8 slots per CTA
@@ -115,6 +117,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// kind::f16 (fp16 operands, fp32 accumulate): the same shared-memory operand rows (32 bytes) hold K = 16 elements.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void umma_k(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if (F16)
+    umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate);
+  else
+    umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
 }
 
 // One lane of a converged warp (always the same one for a full mask).
@@ -242,7 +265,7 @@ struct IssueCtx {
 // moves from ordinary integer arithmetic.  Taps are a rolled loop - fully unrolled variants made the kernel 335 KB
 // of code and every launch paid the instruction-cache misses; the k8 steps and the warp's one or two m-tiles (TWO)
 // are unrolled.  Step q accumulates into partial accumulator q % ksplit (column offset jc, wraps at wrap).
-template <int K8N, bool MERGED, bool TWO>
+template <int K8N, bool MERGED, bool TWO, bool F16 = false>
 __device__ __forceinline__ void issue_chunk(const IssueCtx &c) {
   uint32_t jc = 0, a_row = 0, b_tap = 0;
   int q = 0;
@@ -266,10 +289,10 @@ __device__ __forceinline__ void issue_chunk(const IssueCtx &c) {
           // the tensor core truncates every fp32 accumulation, a bias proportional to the accumulator's magnitude,
           // so the full-magnitude half D[:, 0:N] should see one add per step, not two (tools/dbg_parity.py:
           // controller output error vs the fp32 oracle with both corrections in one half / split).
-          umma_tf32(d0, a0h, b_hi, c.idesc_2n, flag);
-          if (TWO) umma_tf32(d1, a1h, b_hi, c.idesc_2n, flag);
-          umma_tf32(d0 + c.lo_col, a0l, b_hi, c.idesc_lo, 1u);
-          if (TWO) umma_tf32(d1 + c.lo_col, a1l, b_hi, c.idesc_lo, 1u);
+          umma_k<F16>(d0, a0h, b_hi, c.idesc_2n, flag);
+          if (TWO) umma_k<F16>(d1, a1h, b_hi, c.idesc_2n, flag);
+          umma_k<F16>(d0 + c.lo_col, a0l, b_hi, c.idesc_lo, 1u);
+          if (TWO) umma_k<F16>(d1 + c.lo_col, a1l, b_hi, c.idesc_lo, 1u);
         } else {
           const uint64_t b_lo = b_hi + (uint64_t)c.b_lo;
           umma_tf32(d0, a0h, b_hi, c.idesc_n, flag);
@@ -317,7 +340,14 @@ __device__ __forceinline__ void issue_chunk_rs(const IssueCtx &c) {
 }
 
 template <int K8N>
-__device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, bool two) {
+__device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, bool two, bool f16 = false) {
+  if (f16) {  // merged only (make_plan)
+    if (two)
+      issue_chunk<K8N, true, true, true>(c);
+    else
+      issue_chunk<K8N, true, false, true>(c);
+    return;
+  }
   if (merged) {
     if (two)
       issue_chunk<K8N, true, true>(c);
@@ -335,6 +365,60 @@ __device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, b
   do {                                                                                                 \
     if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64();                          \
   } while (0)
+
+// fp16 split of one landed stage (TMA-mode converters, RA_UMMA_F16): the two fp32 channel quads (planes 2k, 2k+1) of a
+// slot become ONE 16-byte unit of 8 halves; hi = fp16(x) is written over plane 2k, lo' = fp16((x - hi) * 2^11) over plane
+// 2k+1 (the scale keeps lo' out of the fp16 subnormals; its products are accumulated in their own TMEM columns and scaled
+// back by the epilogue).  In place: every (k, slot) pair is read and written by one thread.
+
+__device__ __forceinline__ void convert_stage_f16(float4 *hi4, const float4 *raw4, int raw_plane4, int planes, int box_slots,
+                                               int slots_alloc, int up, int TWP, int RW, int y0, int x0, int cx, int cy,
+                                               int ptid) {
+  constexpr int U = 2;
+  const int n_conv16 = (planes / 2) * box_slots;
+  for (int base = ptid; base < n_conv16; base += kProdThreads * U) {
+    float4 va[U], vb[U];
+    int dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * kProdThreads;
+      dst[u] = -1;
+      va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < n_conv16) {
+        const int k = idx / box_slots, slot = idx - k * box_slots;
+        dst[u] = 2 * k * slots_alloc + slot;
+        if (up == 1) {
+          va[u] = hi4[dst[u]];
+          vb[u] = hi4[dst[u] + slots_alloc];
+        } else {
+          const int r = slot / TWP, col = slot - r * TWP;
+          const int vy = y0 - 2 + r, vx = x0 - 2 + col;  // zero-inserted (virtual) pixel
+          if (((vy | vx) & 1) == 0) {
+            const int off = ((vy >> 1) - cy) * RW + ((vx >> 1) - cx);
+            va[u] = raw4[2 * k * raw_plane4 + off];
+            vb[u] = raw4[(2 * k + 1) * raw_plane4 + off];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (dst[u] < 0) continue;
+      const float x[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half h0 = __float2half_rn(x[2 * j]), h1 = __float2half_rn(x[2 * j + 1]);
+        const __half l0 = __float2half_rn((x[2 * j] - __half2float(h0)) * 2048.0f);
+        const __half l1 = __float2half_rn((x[2 * j + 1] - __half2float(h1)) * 2048.0f);
+        h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      reinterpret_cast<uint4 *>(hi4)[dst[u]] = make_uint4(h[0], h[1], h[2], h[3]);
+      reinterpret_cast<uint4 *>(hi4)[dst[u] + slots_alloc] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
 
 // One conv layer, run by a whole CTA (all roles).  `tm1` / `tm2` point at tensor maps in kernel-parameter space (single
 // launch) or in global memory (chain).  CHAIN: the layer is one of several run back to back by a persistent grid: TMEM
@@ -361,7 +445,8 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
   const int planes = p.KC / 4;
   const uint32_t plane_bytes = (uint32_t)p.slots_alloc * 16u;
   const int in_floats = planes * p.slots_alloc * 4;  // one of hi / lo
-  const int w_chunk_floats = 9 * planes * 2 * p.NPc * 4;
+  // filter image of one chunk: [9 taps][planes][2 NPc rows][16 bytes]; fp16 mode: a plane is 8 channels, not 4
+  const int w_chunk_floats = 9 * (p.f16 ? planes / 2 : planes) * 2 * p.NPc * 4;
   unsigned char *stage_base = smem_raw + p.w_res_bytes;  // [resident filter image][stages][pool tile]
   float *pool_s = reinterpret_cast<float *>(stage_base + (size_t)p.stages * p.stage_bytes);
   const int ns = blockIdx.x % p.n_split;
@@ -552,6 +637,10 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         float4 *lo4 = hi4 + in_floats / 4;
         const float4 *raw4 = reinterpret_cast<const float4 *>(st + p.raw_off);
         const int raw_plane4 = p.raw_plane_bytes >> 4;
+        if (p.f16) {
+          convert_stage_f16(hi4, raw4, raw_plane4, planes, box_slots, p.slots_alloc, p.up, p.TWP, p.RW, it.y0, it.x0, cx, cy,
+                            ptid);
+        } else
         for (int base = ptid; base < n_conv; base += kProdThreads * kStageUnroll) {
           float4 v[kStageUnroll];
           int dst[kStageUnroll];
@@ -699,8 +788,10 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       // rowstack: idesc_n = the A_lo instruction (3 NPc wide), idesc_2n = the A_hi instruction (6 NPc wide)
       const uint32_t n_lo = RS ? 3u * (uint32_t)p.NPc : (uint32_t)p.NPc;
       const uint32_t n_hi = RS ? 6u * (uint32_t)p.NPc : 2u * (uint32_t)p.NPc;
-      c.idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((n_lo >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      c.idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((n_hi >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const bool f16 = !RS && p.f16 != 0;
+      const uint32_t fmt = f16 ? 0u : 2u;  // a / b format: F16 = 0, TF32 = 2; c format F32
+      c.idesc_n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((n_lo >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      c.idesc_2n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((n_hi >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       c.idesc_lo = p.four_term ? c.idesc_2n : c.idesc_n;
       // column offset of the A_lo B_hi correction inside an m-tile's accumulator (0: same half as the main sum)
       c.lo_col = RS ? 3u * (uint32_t)p.NPc
@@ -708,16 +799,18 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       // bytes between channel planes of the filter image
       const uint32_t w_plane = (uint32_t)((RS ? 6 : 2) * p.NPc) * 16u;
       c.TWP = (uint32_t)p.TWP;
-      c.a_k8 = 2u * (plane_bytes >> 4);                 // A start-address step of one k8 (two channel planes)
+      // A start-address step of one K step: two 4-channel planes (tf32, K = 8) or four (fp16, K = 16: two 8-channel units
+      // that sit in planes 2k / 2k + 2)
+      c.a_k8 = (f16 ? 4u : 2u) * (plane_bytes >> 4);
       c.b_k8 = 2u * (w_plane >> 4);                     // same for the filter image
-      c.b_tap = (uint32_t)planes * (w_plane >> 4);      // filter image step of one tap (rowstack: of one filter row)
+      c.b_tap = (uint32_t)(f16 ? planes / 2 : planes) * (w_plane >> 4);  // filter image step of one tap (rowstack: of one filter row)
       c.b_lo = (uint32_t)p.NPc;                         // rows NPc..2NPc-1 of a plane hold the lo part
       c.cols_mt = (uint32_t)cols_mt;
       c.wrap = (uint32_t)(p.ksplit * cols_mt);          // TMEM columns of one m-tile (all its partial accumulators)
       const bool has0 = mw < p.n_mt, has1 = mw + kMmaWarps < p.n_mt;
       const bool merged = p.merged != 0;
       const uint32_t a_mt0 = (uint32_t)(mw * p.mt_stride), a_mt1 = (uint32_t)((mw + kMmaWarps) * p.mt_stride);
-      const int k8n = p.KC / 8;
+      const int k8n = f16 ? p.KC / 16 : p.KC / 8;
       int g = 0, t = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
         const int buf = p.nbuf == 2 ? (t & 1) : 0;
@@ -735,8 +828,9 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           // Descriptors differ only in the start-address field (bits 0-13, 16-byte units): a tap, a k8 step, an
           // m-tile are small additive constants.
           const uint32_t a_hi = smem_u32(stage_base + (size_t)s * p.stage_bytes);
-          const uint64_t dA = make_desc(a_hi, plane_bytes, 128);
-          const uint64_t lo_off = (uint64_t)(((uint32_t)in_floats * 4u) >> 4);
+          // fp16: the K-adjacent core matrices (8-channel units) are two fp32 planes apart; lo' sits one plane behind hi
+          const uint64_t dA = make_desc(a_hi, f16 ? 2u * plane_bytes : plane_bytes, 128);
+          const uint64_t lo_off = f16 ? (uint64_t)(plane_bytes >> 4) : (uint64_t)(((uint32_t)in_floats * 4u) >> 4);
           c.a0_hi = dA + (uint64_t)a_mt0;
           c.a1_hi = dA + (uint64_t)a_mt1;
           c.a0_lo = c.a0_hi + lo_off;
@@ -755,11 +849,11 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
                 if (has1) issue_chunk_rs<4, true>(c); else issue_chunk_rs<4, false>(c);
               }
             } else if (k8n == 1)
-              issue_chunk_k8<1>(c, merged, has1);
+              issue_chunk_k8<1>(c, merged, has1, f16);
             else if (k8n == 2)
-              issue_chunk_k8<2>(c, merged, has1);
+              issue_chunk_k8<2>(c, merged, has1, f16);
             else
-              issue_chunk_k8<4>(c, merged, has1);
+              issue_chunk_k8<4>(c, merged, has1, f16);
           }
           __syncwarp();
           if (leader) umma_commit(smem_u32(&bar_empty[s]));  // the stage may be refilled once these MMAs have read it
@@ -861,10 +955,12 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       tmem_ld16_issue(base, r0);
       if (p.merged) tmem_ld16_issue(base + (uint32_t)p.NPc, r1);
       tmem_wait16(r0);
+      // fp16 mode: the second half holds the 2^11-scaled corrections (fmaf with 1.0 is the plain sum, bit for bit)
+      const float lo_scale = p.f16 ? 4.8828125e-4f : 1.0f;
       if (p.merged) {
         tmem_wait16(r1);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r1[j]), lo_scale, __uint_as_float(r0[j]));
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
@@ -878,7 +974,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         if (p.merged) {
           tmem_wait16(r1);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r1[j]), lo_scale, v[j]);
         }
       }
 #pragma unroll
@@ -1070,6 +1166,7 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 struct Plan {
   int KC, NP, NPc, n_split, merged, TH, TW, TWP, n_mt, slots_alloc, n_chunks, stages, acc_cols, stage_bytes;
   int rowstack, mt_stride;
+  int f16;  // fp16 hi / lo operand split (RA_UMMA_F16, experiment): merged mode, KC % 16 == 0, TMA feed only
   int ksplit, nbuf;
   int w_resident, w_res_bytes, grid;
   size_t smem_bytes;
@@ -1117,11 +1214,20 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
     const double hw_n = NPc / 2 > 48 ? NPc / 2 : 48.0, hw_2n = NPc > 48 ? (double)NPc : 48.0;
     const double hw_rs = (3.0 * NPc > 48 ? 3.0 * NPc : 48.0) + (1.5 * NPc > 48 ? 1.5 * NPc : 48.0);
     const double hw_cycles = rs ? hw_rs : (merged ? hw_2n + hw_n : 3.0 * hw_n);
+    // RA_UMMA_F16 (experiment, eval only): 1 = fp16 hi / lo split where the cost model likes it, 2 = wherever it is
+    // possible.  kind::f16 consumes K = 16 per instruction at the cost of a kind::tf32 one (tools/umma_kind_rate.cu):
+    // half the instructions per channel chunk.
+    static const int f16_mode = []() {
+      const char *e = getenv("RA_UMMA_F16");
+      return e == nullptr ? 0 : atoi(e);
+    }();
     for (int KC = 8; KC <= 32; KC *= 2) {
       if (KC > 8 && KC / 2 >= Cin) continue;
+      const int f16 = (f16_mode != 0 && merged && !rs && KC % 16 == 0 && (Cin % 4) == 0) ? 1 : 0;
+      if (f16_mode == 2 && merged && !rs && !f16 && Cin > 8 && (Cin % 4) == 0) continue;
       const int planes = KC / 4;
       const int n_chunks = (Cin + KC - 1) / KC;
-      const size_t w_chunk_bytes = (size_t)9 * planes * 2 * NPc * 16;
+      const size_t w_chunk_bytes = (size_t)9 * (f16 ? planes / 2 : planes) * 2 * NPc * 16;
       const size_t w_total = w_chunk_bytes * n_chunks;
       for (int TW = Wout; TW >= 2; TW = (TW % 2 == 0 ? TW / 2 : 0)) {
         if (TW & 1) break;
@@ -1149,7 +1255,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
             if (fixed + 2 * stage_bytes > smem_cap) continue;
             int st = (int)((smem_cap - fixed) / stage_bytes);
             if (st > kMaxStages) st = kMaxStages;
-            const double per_tap = (double)(rs ? 3 : 9) * (KC / 8) * n_chunks;  // (tap | filter row, k8) steps per tile
+            const double per_tap = (double)(rs ? 3 : 9) * (f16 ? KC / 16 : KC / 8) * n_chunks;  // (tap | filter row, k) steps per tile
             const double step_tc = n_mt * hw_cycles;  // tensor-core occupancy of one step
             // issue: ~75 cycles per instruction for a warp that owns one m-tile, ~50 with two (tools/conv_timeline.py)
             const int mt_warp = (n_mt + kMmaWarps - 1) / kMmaWarps;
@@ -1177,6 +1283,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
               bp.n_split = n_split;
               bp.merged = merged;
               bp.rowstack = rs;
+              bp.f16 = f16;
               bp.mt_stride = mt_stride;
               bp.TH = TH;
               bp.TW = TW;
@@ -1214,7 +1321,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
     }();
     const int cols_mt = bp.rowstack ? 6 * bp.NPc : (bp.merged ? 2 * bp.NPc : bp.NPc);
     int ks = 512 / (bp.nbuf * bp.n_mt * cols_mt);
-    const int steps = (bp.rowstack ? 3 : 9) * (bp.KC / 8) * bp.n_chunks;
+    const int steps = (bp.rowstack ? 3 : 9) * (bp.f16 ? bp.KC / 16 : bp.KC / 8) * bp.n_chunks;
     if (ks > steps) ks = steps;
     if (ks > cap) ks = cap;
     if (ks < 1) ks = 1;
@@ -1240,6 +1347,7 @@ int make_plan_forced(int Cin, int Cout, int Hout, int Wout, int pool, int B, Pla
   bp.n_split = n_split;
   bp.merged = bp.NPc <= 64 ? 1 : 0;
   bp.rowstack = 0;
+  bp.f16 = 0;
   bp.mt_stride = 128;
   const int cols_mt = bp.merged ? 2 * bp.NPc : bp.NPc;
   bp.TH = TH;
@@ -1362,7 +1470,7 @@ extern "C" int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int p
   if (NPc) *NPc = pl.NPc;
   if (n_split) *n_split = pl.n_split;
   if (n_chunks) *n_chunks = pl.n_chunks;
-  if (rowstack) *rowstack = pl.rowstack;
+  if (rowstack) *rowstack = pl.rowstack | (pl.f16 << 1);  // layout flags of the packed filter image: bit 0 row-stacked, bit 1 fp16
   return RA_OK;
 }
 
@@ -1375,7 +1483,7 @@ extern "C" int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, 
   if (!info) return RA_ERR_INVALID_ARG;
   const int v[19] = {pl.KC, pl.NPc, pl.n_split, pl.n_chunks, pl.TH, pl.TW, pl.n_mt, pl.stages, pl.merged,
                      pl.w_resident, pl.grid, (int)pl.smem_bytes, pl.acc_cols, pl.stage_bytes, pl.w_res_bytes,
-                     pl.slots_alloc, pl.ksplit, pl.nbuf, pl.rowstack};
+                     pl.slots_alloc, pl.ksplit, pl.nbuf, pl.rowstack | (pl.f16 << 1)};
   for (int i = 0; i < 19; ++i) info[i] = v[i];
   return RA_OK;
 }
@@ -1429,6 +1537,7 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
   p.n_split = pl.n_split;
   p.merged = pl.merged;
   p.rowstack = pl.rowstack;
+  p.f16 = pl.f16;
   p.mt_stride = pl.mt_stride;
   p.slots_alloc = pl.slots_alloc;
   p.stages = pl.stages;
@@ -1482,6 +1591,10 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
       p.raw_off = 0;
       smem_bytes = pl.smem_bytes;
     }
+  }
+  if (p.f16 && !p.tma) {  // the fp16 split lives in the TMA-mode converters only; the filter image is already packed for it
+    ra::set_last_error("conv3x3_umma: RA_UMMA_F16 needs the TMA feed (channel counts % 4 == 0, aligned tensors)", cudaSuccess);
+    return RA_ERR_UNSUPPORTED;
   }
   p.grid = pl.grid;
   p.pdl = 0;
