@@ -116,6 +116,16 @@ int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B,
 /* Diagnostics: info[19] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
  * acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf, rowstack of the tile plan. */
 int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info);
+/* Filter image of a plan whose layout flags (`rowstack` of ra_conv3x3_umma_plan) have bit 1 set (fp16 hi / lo operand
+ * split, RA_UMMA_F16): v [rows][KC/4][NPc][4] fp32 = the filter in the operand order of one half of the tf32 image
+ * (rows = n_split * n_chunks * 9), out [rows][KC/8][2*NPc][8 halves] (the same number of bytes as v): rows 0..NPc-1 of a
+ * plane = fp16(w) of 8 consecutive input channels, rows NPc..2NPc-1 = fp16((w - hi) * 2^11).  Device pointers. */
+/* Operand format of the tile plans made from now on: 0 = 3xTF32 (default), 1 = fp16 hi / lo split on the layers whose
+ * plan allows it (merged accumulator halves, 16-channel chunks, TMA feed), 2 = the same, forcing 16-channel chunks.
+ * Initial value: environment variable RA_UMMA_F16.  Returns the previous mode (mode < 0: query only).  Filter images are
+ * packed per plan: set this before a model packs its filters. */
+int ra_conv3x3_umma_set_f16(int mode);
+int ra_umma_pack_f16(const float *v, long long rows, int KC, int NPc, float *out, void *stream);
 /* A CHAIN of conv layers in ONE launch (the 6 + 7 layers of the patch network of a decode step, full_model.py:792-807;
  * controller layers 1-7, :663): a persistent grid of one CTA per SM runs the layers back to back with a grid-wide
  * barrier between them instead of paying CTA start-up, TMEM allocation and pipeline fill / drain per launch.

@@ -38,6 +38,7 @@ _SIGNATURES = {
     'ra_canvas_conv_f32': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     'ra_conv3x3_umma_plan': [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     'ra_conv3x3_umma_plan_info': [_I, _I, _I, _I, _I, _I, _P],
+    'ra_umma_pack_f16': [_P, ctypes.c_longlong, _I, _I, _P, _P],
     'ra_debug_conv_timeline': [_P],
     'ra_conv3x3_umma_chain_prepare': [_P, _I, _P, _P, _P],
     'ra_conv3x3_umma_chain_run': [_P, _I, _I, _Z, _P, _P],
@@ -109,7 +110,7 @@ EXPORTED = sorted(list(_SIGNATURES) + ['ra_version', 'ra_device_count', 'ra_last
                                          'ra_gaussian_extract_bwd_workspace', 'ra_controller_tape_floats',
                                          'ra_bn_train_block_bwd_grouped_workspace', 'ra_weight_decay_workspace',
                                          'ra_pairwise_iou_umma_workspace', 'ra_conv3x3_umma_chain_desc_bytes',
-                                         'ra_outer_sum_workspace'])
+                                         'ra_outer_sum_workspace', 'ra_conv3x3_umma_set_f16'])
 
 _lib = None
 TAG = ''  # set by the model code so that bench.py can attribute kernel time to a sub-network
@@ -132,6 +133,8 @@ def lib():
       fn.argtypes = args
       fn.restype = _I
     l.ra_version.restype = _I
+    l.ra_conv3x3_umma_set_f16.argtypes = [_I]
+    l.ra_conv3x3_umma_set_f16.restype = _I
     l.ra_device_count.restype = _I
     l.ra_last_error.restype = ctypes.c_char_p
     l.ra_launch_count.restype = ctypes.c_ulonglong

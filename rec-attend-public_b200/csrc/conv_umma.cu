@@ -339,9 +339,9 @@ __device__ __forceinline__ void issue_chunk_rs(const IssueCtx &c) {
   }
 }
 
-template <int K8N>
-__device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, bool two, bool f16 = false) {
-  if (f16) {  // merged only (make_plan)
+template <int K8N, bool F16 = false>
+__device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, bool two) {
+  if constexpr (F16) {  // merged only (make_plan)
     if (two)
       issue_chunk<K8N, true, true, true>(c);
     else
@@ -426,7 +426,7 @@ __device__ __forceinline__ void convert_stage_f16(float4 *hi4, const float4 *raw
 // initialised again, `first` marks the layer that performs the programmatic-dependent-launch handshake.
 // RS: the row-stacked-taps variant (opt-in, see make_plan) is a separate instantiation, so that the default kernel
 // carries none of its registers / shared memory.
-template <bool RS, bool CHAIN>
+template <bool RS, bool CHAIN, bool F16 = false>
 __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtensorMap &tm1, const CUtensorMap &tm2,
                                            unsigned char *smem_dyn, uint32_t tmem_base_in, bool first,
                                            const unsigned int *chain_counter = nullptr,
@@ -446,7 +446,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
   const uint32_t plane_bytes = (uint32_t)p.slots_alloc * 16u;
   const int in_floats = planes * p.slots_alloc * 4;  // one of hi / lo
   // filter image of one chunk: [9 taps][planes][2 NPc rows][16 bytes]; fp16 mode: a plane is 8 channels, not 4
-  const int w_chunk_floats = 9 * (p.f16 ? planes / 2 : planes) * 2 * p.NPc * 4;
+  const int w_chunk_floats = 9 * (F16 ? planes / 2 : planes) * 2 * p.NPc * 4;
   unsigned char *stage_base = smem_raw + p.w_res_bytes;  // [resident filter image][stages][pool tile]
   float *pool_s = reinterpret_cast<float *>(stage_base + (size_t)p.stages * p.stage_bytes);
   const int ns = blockIdx.x % p.n_split;
@@ -637,7 +637,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         float4 *lo4 = hi4 + in_floats / 4;
         const float4 *raw4 = reinterpret_cast<const float4 *>(st + p.raw_off);
         const int raw_plane4 = p.raw_plane_bytes >> 4;
-        if (p.f16) {
+        if constexpr (F16) {
           convert_stage_f16(hi4, raw4, raw_plane4, planes, box_slots, p.slots_alloc, p.up, p.TWP, p.RW, it.y0, it.x0, cx, cy,
                             ptid);
         } else
@@ -788,7 +788,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       // rowstack: idesc_n = the A_lo instruction (3 NPc wide), idesc_2n = the A_hi instruction (6 NPc wide)
       const uint32_t n_lo = RS ? 3u * (uint32_t)p.NPc : (uint32_t)p.NPc;
       const uint32_t n_hi = RS ? 6u * (uint32_t)p.NPc : 2u * (uint32_t)p.NPc;
-      const bool f16 = !RS && p.f16 != 0;
+      constexpr bool f16 = F16;
       const uint32_t fmt = f16 ? 0u : 2u;  // a / b format: F16 = 0, TF32 = 2; c format F32
       c.idesc_n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((n_lo >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       c.idesc_2n = (1u << 4) | (fmt << 7) | (fmt << 10) | ((n_hi >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -849,11 +849,11 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
                 if (has1) issue_chunk_rs<4, true>(c); else issue_chunk_rs<4, false>(c);
               }
             } else if (k8n == 1)
-              issue_chunk_k8<1>(c, merged, has1, f16);
+              issue_chunk_k8<1, F16>(c, merged, has1);
             else if (k8n == 2)
-              issue_chunk_k8<2>(c, merged, has1, f16);
+              issue_chunk_k8<2, F16>(c, merged, has1);
             else
-              issue_chunk_k8<4>(c, merged, has1, f16);
+              issue_chunk_k8<4, F16>(c, merged, has1);
           }
           __syncwarp();
           if (leader) umma_commit(smem_u32(&bar_empty[s]));  // the stage may be refilled once these MMAs have read it
@@ -956,7 +956,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       if (p.merged) tmem_ld16_issue(base + (uint32_t)p.NPc, r1);
       tmem_wait16(r0);
       // fp16 mode: the second half holds the 2^11-scaled corrections (fmaf with 1.0 is the plain sum, bit for bit)
-      const float lo_scale = p.f16 ? 4.8828125e-4f : 1.0f;
+      constexpr float lo_scale = F16 ? 4.8828125e-4f : 1.0f;
       if (p.merged) {
         tmem_wait16(r1);
 #pragma unroll
@@ -1085,12 +1085,13 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
   }
 }
 
-template <bool RS>
+// F16: the fp16 hi / lo operand split (RA_UMMA_F16 plans) - like RS a separate instantiation.
+template <bool RS, bool F16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
     conv3x3_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant__ CUtensorMap tm1,
                         const __grid_constant__ CUtensorMap tm2) {
   extern __shared__ __align__(128) unsigned char smem_dyn[];
-  conv_layer<RS, false>(p, tm1, tm2, smem_dyn, 0u, true);
+  conv_layer<RS, false, F16>(p, tm1, tm2, smem_dyn, 0u, true);
 }
 
 // A CHAIN of conv layers in one launch: the patch network of a decode step (6 + 7 layers) or controller layers 1-7.
@@ -1162,6 +1163,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_chain_kernel(const _
 
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// Operand format of the merged-mode layers: 0 = 3xTF32 (default), 1 / 2 = fp16 hi / lo split (see make_plan).  Taken from
+// RA_UMMA_F16 on first use; ra_conv3x3_umma_set_f16 overrides it (filter images packed for the old mode become invalid).
+int g_f16_mode = -1;
+int umma_f16_mode() {
+  if (g_f16_mode < 0) {
+    const char *e = getenv("RA_UMMA_F16");
+    g_f16_mode = e == nullptr ? 0 : atoi(e);
+    if (g_f16_mode < 0 || g_f16_mode > 2) g_f16_mode = 0;
+  }
+  return g_f16_mode;
+}
+
 // Tile plan shared by the launcher and the weight packer (through ra_conv3x3_umma_plan).
 struct Plan {
   int KC, NP, NPc, n_split, merged, TH, TW, TWP, n_mt, slots_alloc, n_chunks, stages, acc_cols, stage_bytes;
@@ -1217,10 +1230,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
     // RA_UMMA_F16 (experiment, eval only): 1 = fp16 hi / lo split where the cost model likes it, 2 = wherever it is
     // possible.  kind::f16 consumes K = 16 per instruction at the cost of a kind::tf32 one (tools/umma_kind_rate.cu):
     // half the instructions per channel chunk.
-    static const int f16_mode = []() {
-      const char *e = getenv("RA_UMMA_F16");
-      return e == nullptr ? 0 : atoi(e);
-    }();
+    const int f16_mode = umma_f16_mode();
     for (int KC = 8; KC <= 32; KC *= 2) {
       if (KC > 8 && KC / 2 >= Cin) continue;
       const int f16 = (f16_mode != 0 && merged && !rs && KC % 16 == 0 && (Cin % 4) == 0) ? 1 : 0;
@@ -1453,6 +1463,46 @@ bool activation_map(const float *x, int C, int W, int H, int B, int RW, int RH, 
 
 }  // namespace
 
+// fp16 hi / lo filter image (RA_UMMA_F16 plans): v [rows][KC/4][NPc][4] = the fp32 filter in the operand order of one half
+// of the tf32 image (params.umma_layout; rows = n_split * n_chunks * 9 taps)  ->  out [rows][KC/8][2 NPc][8 halves]: rows
+// 0..NPc-1 of a plane hold hi = fp16(w) of 8 consecutive input channels, rows NPc..2NPc-1 lo' = fp16((w - hi) * 2^11) -
+// the same split convert_stage_f16 applies to the activations.
+__global__ void __launch_bounds__(256) umma_pack_f16_kernel(const float4 *__restrict__ v, long long n, int planes8, int NPc,
+                                                            uint4 *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (row, 8-channel plane, filter row)
+  if (i >= n) return;
+  const int r = (int)(i % NPc);
+  const long long rk = i / NPc;  // row * planes8 + k
+  const float4 a = v[(2 * rk) * NPc + r], b = v[(2 * rk + 1) * NPc + r];
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half h0 = __float2half_rn(x[2 * j]), h1 = __float2half_rn(x[2 * j + 1]);
+    const __half l0 = __float2half_rn((x[2 * j] - __half2float(h0)) * 2048.0f);
+    const __half l1 = __float2half_rn((x[2 * j + 1] - __half2float(h1)) * 2048.0f);
+    h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  out[rk * 2 * NPc + r] = make_uint4(h[0], h[1], h[2], h[3]);
+  out[rk * 2 * NPc + NPc + r] = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+extern "C" int ra_conv3x3_umma_set_f16(int mode) {
+  const int prev = umma_f16_mode();
+  if (mode >= 0 && mode <= 2) g_f16_mode = mode;
+  return prev;
+}
+
+extern "C" int ra_umma_pack_f16(const float *v, long long rows, int KC, int NPc, float *out, void *stream) {
+  if (!v || !out || rows < 0 || KC < 16 || (KC % 16) != 0 || NPc <= 0) return RA_ERR_INVALID_ARG;
+  const long long n = rows * (KC / 8) * NPc;
+  if (n == 0) return RA_OK;
+  umma_pack_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ra::as_stream(stream)>>>(
+      reinterpret_cast<const float4 *>(v), n, KC / 8, NPc, reinterpret_cast<uint4 *>(out));
+  return ra::finish_launch("umma_pack_f16_kernel");
+}
+
 // Diagnostics: when set, every conv3x3_umma CTA writes 8 clock64() stamps (start, setup done, first stage
 // staged, producers done, first MMA issuable, MMAs issued, first accumulator complete, all done).
 extern "C" int ra_debug_conv_timeline(long long *device_buf) {
@@ -1600,6 +1650,10 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
   p.pdl = 0;
   p.four_term = getenv("RA_UMMA_4TERM") != nullptr ? 1 : 0;
   p.split_corr = getenv("RA_UMMA_JOINT_CORR") == nullptr ? 1 : 0;
+  if (p.f16) {  // the corrections are 2^11-scaled: they must live in their own accumulator half, and lo' x lo' is not formed
+    p.four_term = 0;
+    p.split_corr = 1;
+  }
   *smem_out = smem_bytes + 128;  // alignment slack (the kernel rounds its window up to 128 bytes)
   return RA_OK;
 }
@@ -1611,6 +1665,8 @@ bool conv_attrs() {
         cudaFuncSetAttribute(conv3x3_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_umma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
@@ -1664,6 +1720,7 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = p.rowstack ? cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<true>, p, tm1, tm2)
+                    : p.f16    ? cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<false, true>, p, tm1, tm2)
                                : cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<false>, p, tm1, tm2);
     if (e != cudaSuccess) {
       ra::set_last_error("cudaLaunchKernelEx(conv3x3_umma_kernel)", e);
@@ -1672,6 +1729,8 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   } else {
     if (p.rowstack)
       conv3x3_umma_kernel<true><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
+    else if (p.f16)
+      conv3x3_umma_kernel<false, true><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
     else
       conv3x3_umma_kernel<false><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
   }
@@ -1699,7 +1758,7 @@ extern "C" int ra_conv3x3_umma_chain_prepare(const ra_conv_layer_t *layers, int 
     rc = build_layer(L.x1, L.C1, L.x2, L.C2, L.wpack, L.scale, L.shift, L.B, L.Hin, L.Win, L.Cout, L.upsample, L.pool,
                      L.relu, L.y, &args->layers[l].p, &args->layers[l].tm1, &args->layers[l].tm2, &pl, &sb, &empty);
     // (the chain runs the default variant, and its split grid barrier waits in the TMA warp)
-    if (rc == RA_OK && (empty || pl.rowstack || (l > 0 && !args->layers[l].p.tma))) rc = RA_ERR_UNSUPPORTED;
+    if (rc == RA_OK && (empty || pl.rowstack || pl.f16 || (l > 0 && !args->layers[l].p.tma))) rc = RA_ERR_UNSUPPORTED;
     if (rc != RA_OK) break;
     args->layers[l].p.dbg = nullptr;
     args->layers[l].p.pdl = 0;  // the chain is launched behind a memset node, without the programmatic-launch attribute

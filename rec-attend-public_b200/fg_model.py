@@ -126,7 +126,7 @@ class FgModel(object):
         w = L['w']
         try:
           KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], L['Hout'], L['Wout'], L['pool'], B)
-          packed = self._dev(ops.pack_umma_weights(w, KC, NPc, nsp, rs))
+          packed = ops.umma_filter_image(w, KC, NPc, nsp, rs, self.device)
         except _lib.RecAttendError:
           packed = None  # no tile plan for this shape (RA_ERR_UNSUPPORTED): fp32 kernel below
       if packed is None and 'w_dev' not in L:

@@ -121,6 +121,7 @@ class _ModelBase(object):
     self.wd_term = 0.0
     self._bufs = {}
     self._synced = []      # (device tensor, source index array, kind array) of every weight image (see _dev)
+    self._f16_images = []  # (fp32 source, fp16 hi / lo filter image, KC, NPc) of every RA_UMMA_F16 layer (see _packed)
     self._sync_table = None
     self._trainer = None
     self._tape_on = None   # the tape dict while a train_step forward is being enqueued (see train.py)
@@ -153,6 +154,7 @@ class _ModelBase(object):
     self._raw_weights = {k: np.asarray(v, np.float32) for k, v in weights.items()}
     self._all_layout = PM.AllLayout(self._raw_weights)
     self._synced = []
+    self._f16_images = []
     self._sync_table = None
     self._bn_layers = []
     self._bn_dirty = False
@@ -245,7 +247,13 @@ class _ModelBase(object):
     if key not in wp['packed']:
       w = wp['w']
       KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], pool, B)
-      wp['packed'][key] = self._dev(PM.pack_umma(PM.WI(w, wp['idx']), KC, NPc, nsp, rs))
+      if rs & 2:  # fp16 hi / lo split (RA_UMMA_F16): the registered tensor is the fp32 source, the image is made from it
+        src = self._dev(PM.umma_f16_source(PM.WI(w, wp['idx']), KC, NPc, nsp))
+        img = ops.umma_pack_f16(src, KC, NPc)
+        self._f16_images.append((src, img, KC, NPc))
+        wp['packed'][key] = img
+      else:
+        wp['packed'][key] = self._dev(PM.pack_umma(PM.WI(w, wp['idx']), KC, NPc, nsp, rs))
     return wp['packed'][key]
 
   def _use_chain(self):
@@ -353,6 +361,8 @@ class _ModelBase(object):
     tb = self._sync_table
     _lib.call('ra_param_gather_f32', ops._p(flat_params), ops._p(tb['codes']), ops._p(tb['starts']), ops._p(tb['ptrs']),
               tb['nseg'], tb['total'], ops._stream())
+    for src, img, KC, NPc in self._f16_images:
+      ops.umma_pack_f16(src, KC, NPc, out=img)
     self._bn_dirty = True  # gamma / beta / bias moved: refold before the next eval forward
 
   def _weight_decay_term(self, weights):

@@ -126,8 +126,40 @@ def pack_umma_weights(w_hwio, KC, NPc, n_split, rowstack=0):
   [hi kx0 | hi kx1 | hi kx2 | lo kx0 | lo kx1 | lo kx2] (values only; params.pack_umma also carries the indices)."""
   import numpy as np
   from . import params as PM
+  if rowstack & 2:
+    raise _lib.RecAttendError('fp16 hi / lo plan (RA_UMMA_F16): the filter image is made on the device, use '
+                              'umma_filter_image')
   w = np.asarray(w_hwio, np.float32)
   return PM.pack_umma(PM.WI(w, np.zeros(w.shape, np.int64)), KC, NPc, n_split, rowstack).val
+
+
+def umma_set_f16(mode):
+  """Operand format of the tile plans made from now on (0 = 3xTF32, 1 / 2 = fp16 hi / lo split); returns the previous
+  mode; mode < 0 only queries."""
+  return _lib.lib().ra_conv3x3_umma_set_f16(int(mode))
+
+
+def umma_pack_f16(src, KC, NPc, out=None):
+  """Device tensor src [..., KC/4, NPc, 4] fp32 (params.umma_f16_source) -> the fp16 hi / lo filter image of an
+  RA_UMMA_F16 plan (same byte size, carried as a float32 tensor of raw bits)."""
+  _chk(src, out)
+  if out is None:
+    out = torch.empty_like(src)
+  rows = src.numel() // (KC * NPc)
+  _lib.call('ra_umma_pack_f16', _p(src), rows, KC, NPc, _p(out), _stream())
+  return out
+
+
+def umma_filter_image(w_hwio, KC, NPc, n_split, flags, device):
+  """HWIO filter (numpy) -> the device-side filter image for a plan with layout `flags` (bit 0 row-stacked taps, bit 1
+  fp16 hi / lo split) as given by umma_plan."""
+  import numpy as np
+  from . import params as PM
+  w = np.asarray(w_hwio, np.float32)
+  if flags & 2:
+    src = PM.umma_f16_source(PM.WI(w, np.zeros(w.shape, np.int64)), KC, NPc, n_split).val
+    return umma_pack_f16(torch.from_numpy(src).to(device), KC, NPc)
+  return torch.from_numpy(pack_umma_weights(w, KC, NPc, n_split, flags & 1)).to(device)
 
 
 def conv3x3_block_umma(x, wpack, Cout, scale, shift, pool=1, relu=True, x2=None, upsample=1, out=None):

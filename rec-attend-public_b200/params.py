@@ -120,6 +120,24 @@ def pack_umma(wi, KC, NPc, n_split, rowstack=0):
   return WI(val, idx, kind)
 
 
+def umma_f16_source(wi, KC, NPc, n_split):
+  """WI of an HWIO filter -> WI of the fp32 SOURCE of the fp16 hi / lo filter image (plans whose layout flags have
+  bit 1 set, RA_UMMA_F16): [n_split][n_chunks][9][KC/4][NPc][4], plain values (no kinds).  The image itself is made from
+  it on the device by ra_umma_pack_f16 (ops.umma_pack_f16), at load time and after every optimiser step."""
+  return WI(np.ascontiguousarray(umma_layout(wi.val, KC, NPc, n_split)),
+            np.ascontiguousarray(umma_layout(wi.idx, KC, NPc, n_split)))
+
+
+def pack_umma_f16_reference(v):
+  """numpy model of ra_umma_pack_f16 (tests): v [..., KC/4, NPc, 4] fp32 -> [..., KC/8, 2 NPc, 8] float16."""
+  v = np.asarray(v, np.float32)
+  lead, (pl, npc, _) = v.shape[:-3], v.shape[-3:]
+  x = v.reshape(lead + (pl // 2, 2, npc, 4)).swapaxes(-3, -2).reshape(lead + (pl // 2, npc, 8))
+  hi = x.astype(np.float16)
+  lo = ((x - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+  return np.concatenate([hi, lo], axis=-2)
+
+
 def to_train_map(all_layout, flat_params):
   """Vector m of length numel+1: m[0] = 0 (the zero constant), m[1 + all position] = 1 + position in the TRAINABLE
   flat bucket (`optim.FlatParams`), or -1 for tensors that are not trained (EMA shadows, frozen nets)."""

@@ -506,14 +506,50 @@ def test_conv3x3_block_umma(ops, case):
   if pool == 2:
     ref = OM.max_pool_same(ref, 2)
   KC, NPc, nsp, nch, rs = ops.umma_plan(Cin, Cout, H * up, W * up, pool, B)
-  wp = ops.pack_umma_weights(w, KC, NPc, nsp, rs)
-  assert wp.shape == (nsp, nch, 9, KC // 4, 2 * NPc, 4)
-  out = ops.conv3x3_block_umma(_g(x1), _g(wp), Cout, _g(scale), _g(shift), pool=pool, relu=bool(relu),
+  if rs & 2:  # fp16 hi / lo plan (test_conv3x3_block_umma_f16): the image is made on the device
+    wp = ops.umma_filter_image(w, KC, NPc, nsp, rs, 'cuda')
+    assert wp.numel() == nsp * nch * 9 * KC * NPc
+  else:
+    wp = ops.pack_umma_weights(w, KC, NPc, nsp, rs)
+    assert wp.shape == (nsp, nch, 9, KC // 4, 2 * NPc, 4)
+    wp = _g(wp)
+  out = ops.conv3x3_block_umma(_g(x1), wp, Cout, _g(scale), _g(shift), pool=pool, relu=bool(relu),
                                x2=None if x2 is None else _g(x2), upsample=up)
   torch.cuda.synchronize()
   assert tuple(out.shape) == tuple(ref.shape)
-  # 3xTF32: ~2^-21 per product; 1e-5 of the tensor scale leaves margin
+  # 3xTF32 / fp16 hi + lo: ~2^-21 per product; 1e-5 of the tensor scale leaves margin
   assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5
+  return rs
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('case', UMMA_CASES)
+def test_conv3x3_block_umma_f16(ops, case, mode):
+  """The fp16 hi / lo operand split (kind::f16, K = 16 per instruction; ra_conv3x3_umma_set_f16 / RA_UMMA_F16): same
+  layers, same bound - hi = fp16(x) and lo' = fp16((x - hi) * 2^11) carry 11 + 11 significand bits like the two tf32 parts.
+  Layers whose plan does not take the split (wide N, channel counts the TMA feed cannot serve) run as before."""
+  B, H, W, C1, C2, Cout, up, pool, relu = case
+  prev = ops.umma_set_f16(mode)
+  try:
+    if (C1 % 4) or (C2 % 4):  # no TMA feed: the split must not be planned for a layer that cannot run it ...
+      rs = ops.umma_plan(C1 + C2, Cout, H * up, W * up, pool, B)[4]
+      if rs & 2:
+        pytest.skip('fp16 plan needs channel counts % 4 == 0 on both inputs (loud RA_ERR_UNSUPPORTED otherwise)')
+    rs = test_conv3x3_block_umma(ops, case)
+  finally:
+    ops.umma_set_f16(prev)
+  if mode == 2 and Cout <= 64 and (C1 + C2) >= 16 and (C1 % 4) == 0 and (C2 % 4) == 0:
+    assert rs & 2, 'mode 2 must take the fp16 split on every merged-mode layer with >= 16 input channels'
+
+
+def test_umma_pack_f16(ops):
+  """ra_umma_pack_f16 against its numpy model, bit for bit."""
+  from rec_attend_b200 import params as PM
+  rng = np.random.default_rng(5)
+  v = (rng.standard_normal((2, 3, 9, 8, 24, 4)) * np.exp(rng.uniform(-12, 3, (2, 3, 9, 8, 24, 4)))).astype(np.float32)
+  img = ops.umma_pack_f16(_g(v), 32, 24).cpu().numpy()
+  ref = PM.pack_umma_f16_reference(v)
+  assert np.array_equal(img.view(np.uint16).reshape(ref.shape), ref.view(np.uint16))
 
 
 @pytest.mark.parametrize('bulk', [True, False])
