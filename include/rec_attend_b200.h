@@ -113,6 +113,12 @@ int ra_canvas_conv_f32(const float *pre, const float *canvas, const float *w, co
  * -------------------------------------------------------------------------------------- */
 int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc, int *n_split,
                          int *n_chunks, int *rowstack);
+/* The same for a layer whose input is the channel concatenation [x1 (C1) | x2 (C2)] (C2 = 0: ra_conv3x3_umma_plan with
+ * Cin = C1): the fp16 operand split (ra_conv3x3_umma_set_f16) feeds the kernel in 16-channel TMA boxes, which must not
+ * straddle the two inputs - such layers keep the 3xTF32 plan.  ra_conv3x3_umma_f32 plans with the (C1, C2) it is given:
+ * pack the filter image for THIS plan when C2 > 0. */
+int ra_conv3x3_umma_plan_split(int C1, int C2, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc,
+                               int *n_split, int *n_chunks, int *rowstack);
 /* Diagnostics: info[19] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages, merged, w_resident, grid, smem_bytes,
  * acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf, rowstack of the tile plan. */
 int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info);
@@ -120,8 +126,9 @@ int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, i
  * split, RA_UMMA_F16): v [rows][KC/4][NPc][4] fp32 = the filter in the operand order of one half of the tf32 image
  * (rows = n_split * n_chunks * 9), out [rows][KC/8][2*NPc][8 halves] (the same number of bytes as v): rows 0..NPc-1 of a
  * plane = fp16(w) of 8 consecutive input channels, rows NPc..2NPc-1 = fp16((w - hi) * 2^11).  Device pointers. */
-/* Operand format of the tile plans made from now on: 0 = 3xTF32 (default), 1 = fp16 hi / lo split on the layers whose
- * plan allows it (merged accumulator halves, 16-channel chunks, TMA feed), 2 = the same, forcing 16-channel chunks.
+/* Operand format of the tile plans made from now on: 1 (default) = fp16 hi / lo split on the layers whose plan allows it
+ * (<= 64 output channels per CTA, 16-channel chunks, TMA feed in 16-channel boxes), 0 = 3xTF32 everywhere, 2 = like 1,
+ * forcing 16-channel chunks.  Both formats meet the same error bound (11 + 11 significand bits per operand).
  * Initial value: environment variable RA_UMMA_F16.  Returns the previous mode (mode < 0: query only).  Filter images are
  * packed per plan: set this before a model packs its filters. */
 int ra_conv3x3_umma_set_f16(int mode);

@@ -37,6 +37,7 @@ _SIGNATURES = {
     'ra_conv3x3_f32': [_P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     'ra_canvas_conv_f32': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P],
     'ra_conv3x3_umma_plan': [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    'ra_conv3x3_umma_plan_split': [_I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     'ra_conv3x3_umma_plan_info': [_I, _I, _I, _I, _I, _I, _P],
     'ra_umma_pack_f16': [_P, ctypes.c_longlong, _I, _I, _P, _P],
     'ra_debug_conv_timeline': [_P],

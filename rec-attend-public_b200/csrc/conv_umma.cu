@@ -47,12 +47,19 @@
 
 namespace {
 
-constexpr int kEpiThreads = 128;   // warps 0-3
+// Warp roles.  The epilogue is the longest stage of the pipeline on the large layers (tools/conv_timeline.py wait
+// accounting, profiles/r04f_*: 81 % of controller layer 1 with four epilogue warps, the MMA warps waiting for free
+// accumulators), so it is run by TWO groups of four warps: a warp may read the TMEM lanes [32 (w % 4), +32), group A = warps
+// 0-3 takes the even m-tiles of a tile, group B = warps 15-18 the odd ones.
+constexpr int kEpiThreads = 128;   // one epilogue group: warps 0-3 (A), warps 15-18 (B)
+constexpr int kEpiAll = 2 * kEpiThreads;
 constexpr int kMmaWarp0 = 4;       // warps 4-7: one issuing lane each, m-tiles dealt round-robin
 constexpr int kMmaWarps = 4;
-constexpr int kProdThreads = 256;  // warps 8-15
-constexpr int kTmaWarp = (kEpiThreads + 32 * kMmaWarps + kProdThreads) / 32;  // warp 16
-constexpr int kThreads = kEpiThreads + 32 * kMmaWarps + kProdThreads + 32;
+constexpr int kProdThreads = 224;  // warps 8-14 (seven: 20 warps = 5 per SM sub-partition keep 96 registers per thread)
+constexpr int kProdWarp0 = kMmaWarp0 + kMmaWarps;
+constexpr int kEpiWarpB0 = kProdWarp0 + kProdThreads / 32;  // warp 15 (group B = warps 15-18: lane quarters 3, 0, 1, 2)
+constexpr int kTmaWarp = kEpiWarpB0 + kEpiThreads / 32;      // warp 19
+constexpr int kThreads = 32 * (kTmaWarp + 1);                // 640
 constexpr int kMaxStages = 4;
 constexpr int kStageUnroll = 4;
 constexpr int kKsplitDefault = 8;  // partial accumulators per m-tile used for precision (see make_plan)
@@ -361,61 +368,94 @@ __device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, b
   }
 }
 
+// Wait accounting of the timeline (slots 8-14: cycles the TMA warp waited for a free stage, the converters for a landed
+// box, MMA warp 0 for a staged chunk / for a free accumulator, the epilogue for a complete accumulator; cycles the epilogue /
+// the converters were busy): who starves whom.
+#define RA_WAIT(mbar, parity, acc)            \
+  do {                                        \
+    if ((F16 && !CHAIN && p.dbg != nullptr)) {                   \
+      const long long t0_ = clock64();        \
+      mbar_wait(mbar, parity);                \
+      (acc) += clock64() - t0_;               \
+    } else {                                  \
+      mbar_wait(mbar, parity);                \
+    }                                         \
+  } while (0)
+#define RA_DBG_PUT(slot, v)                                                            \
+  do {                                                                                 \
+    if ((F16 && !CHAIN && p.dbg != nullptr)) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = (long long)(v);    \
+  } while (0)
 #define RA_DBG(slot)                                                                                   \
   do {                                                                                                 \
-    if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = clock64();                          \
+    if ((!CHAIN && p.dbg != nullptr)) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64();                          \
   } while (0)
 
-// fp16 split of one landed stage (TMA-mode converters, RA_UMMA_F16): the two fp32 channel quads (planes 2k, 2k+1) of a
-// slot become ONE 16-byte unit of 8 halves; hi = fp16(x) is written over plane 2k, lo' = fp16((x - hi) * 2^11) over plane
-// 2k+1 (the scale keeps lo' out of the fp16 subnormals; its products are accumulated in their own TMEM columns and scaled
-// back by the epilogue).  In place: every (k, slot) pair is read and written by one thread.
+// hi / lo' of two activations, each packed as a half2 (first value in the low half).  The conversion pipe is the narrow one
+// (a cvt per value made the converters the second-longest stage), so hi is formed in fp32 with integer / FMA-pipe work -
+// x rounded to 11 significant bits, which IS an fp16 number for 2^-14 <= |x| < 65504; below, x rounded to the fp16
+// subnormal grid 2^-24 by the add-and-subtract trick - and only the two packing conversions (exact for hi) remain.
+__device__ __forceinline__ float f16_hi_part(float x) {
+  const float big = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  const float small = (x + 0.75f) - 0.75f;  // multiples of 2^-24 (ulp of [0.5, 1))
+  return fabsf(x) < 6.103515625e-5f ? small : big;
+}
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t &h, uint32_t &l) {
+  const float ha = f16_hi_part(a), hb = f16_hi_part(b);
+  const __half2 hh = __floats2half2_rn(ha, hb);
+  const __half2 ll = __floats2half2_rn((a - ha) * 2048.0f, (b - hb) * 2048.0f);
+  h = *reinterpret_cast<const uint32_t *>(&hh);
+  l = *reinterpret_cast<const uint32_t *>(&ll);
+}
 
-__device__ __forceinline__ void convert_stage_f16(float4 *hi4, const float4 *raw4, int raw_plane4, int planes, int box_slots,
-                                               int slots_alloc, int up, int TWP, int RW, int y0, int x0, int cx, int cy,
-                                               int ptid) {
+// fp16 split of one landed stage (TMA-mode converters of the fp16 variant).  The activations land PIXEL-MAJOR: one TMA box
+// per 16-channel group, 64 bytes per pixel, SWIZZLE_64B (the 16-byte unit u of pixel `off` sits at unit u ^ ((off >> 1) & 3)
+// of its 64-byte row: zones are 512-byte aligned) - a box row of 64 bytes instead of the 16 bytes of the 4-channel planes,
+// which the TMA unit serves at ~4 cycles per row whatever its length (the 16-byte rows bound controller layers 1 / 3 / 5 at
+// ~4 bytes per cycle and SM).  The two fp32 quads of an 8-channel unit become 8 halves: hi = fp16(x) goes to plane 2k of the
+// operand region, lo' = fp16((x - hi) * 2^11) to plane 2k + 1 (the scale keeps lo' out of the fp16 subnormals; its products
+// are accumulated in their own TMEM columns and scaled back by the epilogue).  Slot-fastest thread order: the swizzle makes
+// the reads of 8 consecutive pixels conflict-free, the writes are consecutive 16-byte units.
+__device__ __forceinline__ void convert_stage_f16(uint4 *hi4, const uint4 *zone4, int zone_units, int planes, int box_slots,
+                                                  int slots_alloc, int up, int TWP, int RW, int y0, int x0, int cx, int cy,
+                                                  int ptid) {
   constexpr int U = 2;
   const int n_conv16 = (planes / 2) * box_slots;
   for (int base = ptid; base < n_conv16; base += kProdThreads * U) {
-    float4 va[U], vb[U];
+    uint4 va[U], vb[U];
     int dst[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int idx = base + u * kProdThreads;
       dst[u] = -1;
-      va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      va[u] = vb[u] = make_uint4(0u, 0u, 0u, 0u);
       if (idx < n_conv16) {
         const int k = idx / box_slots, slot = idx - k * box_slots;
         dst[u] = 2 * k * slots_alloc + slot;
-        if (up == 1) {
-          va[u] = hi4[dst[u]];
-          vb[u] = hi4[dst[u] + slots_alloc];
-        } else {
+        int off = slot;  // up == 1: the box is the tile with its halo, RW == TWP
+        if (up != 1) {
           const int r = slot / TWP, col = slot - r * TWP;
           const int vy = y0 - 2 + r, vx = x0 - 2 + col;  // zero-inserted (virtual) pixel
-          if (((vy | vx) & 1) == 0) {
-            const int off = ((vy >> 1) - cy) * RW + ((vx >> 1) - cx);
-            va[u] = raw4[2 * k * raw_plane4 + off];
-            vb[u] = raw4[(2 * k + 1) * raw_plane4 + off];
-          }
+          off = ((vy | vx) & 1) == 0 ? ((vy >> 1) - cy) * RW + ((vx >> 1) - cx) : -1;
+        }
+        if (off >= 0) {
+          const uint4 *row = zone4 + (k >> 1) * zone_units + off * 4;
+          const int sw = (off >> 1) & 3, h2 = (k & 1) * 2;
+          va[u] = row[h2 ^ sw];
+          vb[u] = row[(h2 + 1) ^ sw];
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (dst[u] < 0) continue;
-      const float x[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+      const float x[8] = {__uint_as_float(va[u].x), __uint_as_float(va[u].y), __uint_as_float(va[u].z),
+                          __uint_as_float(va[u].w), __uint_as_float(vb[u].x), __uint_as_float(vb[u].y),
+                          __uint_as_float(vb[u].z), __uint_as_float(vb[u].w)};
       uint32_t h[4], l[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const __half h0 = __float2half_rn(x[2 * j]), h1 = __float2half_rn(x[2 * j + 1]);
-        const __half l0 = __float2half_rn((x[2 * j] - __half2float(h0)) * 2048.0f);
-        const __half l1 = __float2half_rn((x[2 * j + 1] - __half2float(h1)) * 2048.0f);
-        h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-      }
-      reinterpret_cast<uint4 *>(hi4)[dst[u]] = make_uint4(h[0], h[1], h[2], h[3]);
-      reinterpret_cast<uint4 *>(hi4)[dst[u] + slots_alloc] = make_uint4(l[0], l[1], l[2], l[3]);
+      for (int j = 0; j < 4; ++j) split_f16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
+      hi4[dst[u]] = make_uint4(h[0], h[1], h[2], h[3]);
+      hi4[dst[u] + slots_alloc] = make_uint4(l[0], l[1], l[2], l[3]);
     }
   }
 }
@@ -438,13 +478,18 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
   __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_raw[kMaxStages], bar_tfull[2],
       bar_tempty[2];
   // TMA destinations want 128-byte alignment: round the dynamic window up (the launcher adds the slack)
-  unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+  // (fp16 variant: 1024 bytes - its swizzled landing zones are addressed by absolute shared-memory address bits)
+  constexpr uint32_t kAlign = F16 ? 1024u : 128u;
+  unsigned char *smem_raw = smem_dyn + ((kAlign - (smem_u32(smem_dyn) & (kAlign - 1u))) & (kAlign - 1u));
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler, too
   const int planes = p.KC / 4;
   const uint32_t plane_bytes = (uint32_t)p.slots_alloc * 16u;
   const int in_floats = planes * p.slots_alloc * 4;  // one of hi / lo
+  // offset of the filter slice inside a stage: behind the hi and lo activation planes; the fp16 split keeps hi and lo' in
+  // alternating planes of ONE such region (8 halves take the 16 bytes of 4 floats)
+  const uint32_t w_off = (F16 ? 1u : 2u) * (uint32_t)in_floats * 4u;
   // filter image of one chunk: [9 taps][planes][2 NPc rows][16 bytes]; fp16 mode: a plane is 8 channels, not 4
   const int w_chunk_floats = 9 * (F16 ? planes / 2 : planes) * 2 * p.NPc * 4;
   unsigned char *stage_base = smem_raw + p.w_res_bytes;  // [resident filter image][stages][pool tile]
@@ -477,7 +522,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(smem_u32(&bar_tfull[s]), kMmaWarps);
-        mbar_init(smem_u32(&bar_tempty[s]), kEpiThreads);
+        mbar_init(smem_u32(&bar_tempty[s]), RS ? kEpiThreads : kEpiAll);  // (rowstack: group A only)
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -504,7 +549,10 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       }
       const uint32_t w_bytes = p.w_resident ? 0u : (uint32_t)w_chunk_floats * 4u;
       const uint32_t tx_bytes = (uint32_t)planes * (uint32_t)(p.RW * p.RH) * 16u + w_bytes;
-      const uint32_t dst_plane = p.up == 2 ? (uint32_t)p.raw_plane_bytes : plane_bytes;
+      // one box per 4-channel plane (16-byte rows), or - fp16 variant - per 16-channel group (64-byte rows, landing zone)
+      const uint32_t dst_plane = (F16 || p.up == 2) ? (uint32_t)p.raw_plane_bytes : plane_bytes;
+      constexpr int box_c = F16 ? 16 : 4;
+      const int n_boxes = F16 ? p.KC / 16 : planes;
       int g = 0;
       for (int tile = tile0; tile < n_tiles && g < p.stages; tile += tile_step) {
         const Item it = decode_tile(p, tile);
@@ -514,9 +562,9 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           const uint32_t st = smem_u32(stage_base + (size_t)g * p.stage_bytes);  // first pass: stage g, all empty
           const uint32_t bar = smem_u32(&bar_raw[g]);
           if (leader) mbar_arrive_expect_tx(bar, tx_bytes);
-          const uint32_t dst0 = p.up == 2 ? st + (uint32_t)p.raw_off : st;
-          for (int pl = 0; pl < planes; ++pl) {
-            const int cc = ch * p.KC + 4 * pl;
+          const uint32_t dst0 = (F16 || p.up == 2) ? st + (uint32_t)p.raw_off : st;
+          for (int pl = 0; pl < n_boxes; ++pl) {
+            const int cc = ch * p.KC + box_c * pl;
             const uint32_t dst = dst0 + (uint32_t)pl * dst_plane;
             if (cc < p.C1 || p.C2 == 0) {
               if (leader) tma_load_4d(dst, &tm1, cc, cx, cy, it.b, bar);
@@ -526,7 +574,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           }
           if (!p.w_resident) {
             const float *wsrc = p.wpack + ((size_t)ns * p.n_chunks + ch) * w_chunk_floats;
-            if (leader) bulk_load(st + 2u * (uint32_t)in_floats * 4u, wsrc, w_bytes, bar);
+            if (leader) bulk_load(st + w_off, wsrc, w_bytes, bar);
           }
           __syncwarp();
           if (g == 0 && leader) RA_DBG(2);  // first stage requested
@@ -578,8 +626,12 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       const bool leader = elect_one();
       const uint32_t w_bytes = p.w_resident ? 0u : (uint32_t)w_chunk_floats * 4u;
       const uint32_t tx_bytes = (uint32_t)planes * (uint32_t)(p.RW * p.RH) * 16u + w_bytes;
-      const uint32_t dst_plane = p.up == 2 ? (uint32_t)p.raw_plane_bytes : plane_bytes;
+      // one box per 4-channel plane (16-byte rows), or - fp16 variant - per 16-channel group (64-byte rows, landing zone)
+      const uint32_t dst_plane = (F16 || p.up == 2) ? (uint32_t)p.raw_plane_bytes : plane_bytes;
+      constexpr int box_c = F16 ? 16 : 4;
+      const int n_boxes = F16 ? p.KC / 16 : planes;
       int g = 0;
+      long long w_tma = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_step) {
         const Item it = decode_tile(p, tile);
         // first input pixel of the box (negative / past-the-end coordinates are zero-filled = SAME padding)
@@ -588,13 +640,13 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
           if (g < tma_prologue) continue;  // requested before the setup barrier
           const int s = g % p.stages;
-          mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)(((g / p.stages) & 1) ^ 1));
+          RA_WAIT(smem_u32(&bar_empty[s]), (uint32_t)(((g / p.stages) & 1) ^ 1), w_tma);
           const uint32_t st = smem_u32(stage_base + (size_t)s * p.stage_bytes);
           const uint32_t bar = smem_u32(&bar_raw[s]);
           if (leader) mbar_arrive_expect_tx(bar, tx_bytes);
-          const uint32_t dst0 = p.up == 2 ? st + (uint32_t)p.raw_off : st;
-          for (int pl = 0; pl < planes; ++pl) {
-            const int cc = ch * p.KC + 4 * pl;
+          const uint32_t dst0 = (F16 || p.up == 2) ? st + (uint32_t)p.raw_off : st;
+          for (int pl = 0; pl < n_boxes; ++pl) {
+            const int cc = ch * p.KC + box_c * pl;
             const uint32_t dst = dst0 + (uint32_t)pl * dst_plane;
             // channels past Cin (padding planes) fall outside the map and come back as zeros
             if (cc < p.C1 || p.C2 == 0) {
@@ -605,11 +657,12 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           }
           if (!p.w_resident) {
             const float *wsrc = p.wpack + ((size_t)ns * p.n_chunks + ch) * w_chunk_floats;
-            if (leader) bulk_load(st + 2u * (uint32_t)in_floats * 4u, wsrc, w_bytes, bar);
+            if (leader) bulk_load(st + w_off, wsrc, w_bytes, bar);
           }
           __syncwarp();
         }
       }
+      if (leader) RA_DBG_PUT(8, w_tma);
       if (CHAIN) {
         // Drain: the MMA warps release every stage with an asynchronous tcgen05.commit -> mbarrier arrive.  Nobody waits
         // for the LAST release of a stage inside a layer, and the next layer re-initialises these barriers right after
@@ -620,26 +673,28 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         __syncwarp();
       }
     }
-  } else if (warp >= kMmaWarp0 + kMmaWarps && p.tma) {
+  } else if (warp >= kProdWarp0 && warp < kEpiWarpB0 && p.tma) {
     // =============================== converters (TMA mode) ===============================
     const int ptid = tid - (kEpiThreads + 32 * kMmaWarps);
     const int box_slots = (p.TH + 2) * p.TWP;  // slots the taps of real output pixels can touch
     const int n_conv = planes * box_slots;
     int g = 0;
+    long long w_conv = 0, b_conv = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       const Item it = decode_tile(p, tile);
       const int cx = (it.x0 >> 1) - 1, cy = (it.y0 - 1) >> 1;  // up == 2: origin of the landed box
       for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
         const int s = g % p.stages;
-        mbar_wait(smem_u32(&bar_raw[s]), (uint32_t)((g / p.stages) & 1));
+        RA_WAIT(smem_u32(&bar_raw[s]), (uint32_t)((g / p.stages) & 1), w_conv);
+        const long long tb_ = (F16 && !CHAIN && p.dbg != nullptr) ? clock64() : 0;
         unsigned char *st = stage_base + (size_t)s * p.stage_bytes;
         float4 *hi4 = reinterpret_cast<float4 *>(st);
         float4 *lo4 = hi4 + in_floats / 4;
         const float4 *raw4 = reinterpret_cast<const float4 *>(st + p.raw_off);
         const int raw_plane4 = p.raw_plane_bytes >> 4;
         if constexpr (F16) {
-          convert_stage_f16(hi4, raw4, raw_plane4, planes, box_slots, p.slots_alloc, p.up, p.TWP, p.RW, it.y0, it.x0, cx, cy,
-                            ptid);
+          convert_stage_f16(reinterpret_cast<uint4 *>(st), reinterpret_cast<const uint4 *>(st + p.raw_off), raw_plane4, planes,
+                            box_slots, p.slots_alloc, p.up, p.TWP, p.RW, it.y0, it.x0, cx, cy, ptid);
         } else
         for (int base = ptid; base < n_conv; base += kProdThreads * kStageUnroll) {
           float4 v[kStageUnroll];
@@ -672,10 +727,15 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (tensor core)
         mbar_arrive(smem_u32(&bar_full[s]));
+        if (F16 && !CHAIN && p.dbg != nullptr) b_conv += clock64() - tb_;
       }
     }
-    if (ptid == 0) RA_DBG(3);  // converters done
-  } else if (warp >= kMmaWarp0 + kMmaWarps) {
+    if (ptid == 0) {
+      RA_DBG(3);  // converters done
+      RA_DBG_PUT(9, w_conv);
+      RA_DBG_PUT(14, b_conv);
+    }
+  } else if (warp >= kProdWarp0 && warp < kEpiWarpB0) {
     // =============================== producers (plain-load mode) ===============================
     const int ptid = tid - (kEpiThreads + 32 * kMmaWarps);
     if (p.pdl && first) asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous kernel's output
@@ -772,7 +832,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       }
     }
     if (ptid == 0) RA_DBG(3);  // producers done
-  } else if (warp >= kMmaWarp0) {
+  } else if (warp >= kMmaWarp0 && warp < kProdWarp0) {
     // =============================== MMA issuers ===============================
     // tcgen05.mma takes its operands from UNIFORM registers.  Issued from an `if (lane == 0)` region the compiler
     // cannot prove them warp-uniform and wraps every MMA in an ELECT / R2UR.BROADCAST loop (~185 cycles per
@@ -812,17 +872,18 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       const uint32_t a_mt0 = (uint32_t)(mw * p.mt_stride), a_mt1 = (uint32_t)((mw + kMmaWarps) * p.mt_stride);
       const int k8n = f16 ? p.KC / 16 : p.KC / 8;
       int g = 0, t = 0;
+      long long w_full = 0, w_tempty = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
         const int buf = p.nbuf == 2 ? (t & 1) : 0;
         const uint32_t use = p.nbuf == 2 ? (uint32_t)(t >> 1) : (uint32_t)t;
-        mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);
+        RA_WAIT(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u, w_tempty);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols);
         c.d0 = acc + (uint32_t)mw * c.wrap;
         c.d1 = acc + (uint32_t)(mw + kMmaWarps) * c.wrap;
         for (int ch = 0; ch < p.n_chunks; ++ch, ++g) {
           const int s = g % p.stages;
-          mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((g / p.stages) & 1));
+          RA_WAIT(smem_u32(&bar_full[s]), (uint32_t)((g / p.stages) & 1), w_full);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (g == 0 && mw == 0 && leader) RA_DBG(4);  // first MMA can issue
           // Descriptors differ only in the start-address field (bits 0-13, 16-byte units): a tap, a k8 step, an
@@ -836,7 +897,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           c.a0_lo = c.a0_hi + lo_off;
           c.a1_lo = c.a1_hi + lo_off;
           const uint32_t w_addr = p.w_resident ? smem_u32(smem_raw) + (uint32_t)ch * (uint32_t)w_chunk_floats * 4u
-                                               : a_hi + 2u * (uint32_t)in_floats * 4u;
+                                               : a_hi + w_off;
           c.b = make_desc(w_addr, w_plane, 128);
           c.init_steps = ch == 0 ? (uint32_t)p.ksplit : 0u;  // the first MMA into each accumulator overwrites
           if (has0 && leader) {
@@ -862,23 +923,35 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         if (leader) umma_commit(smem_u32(&bar_tfull[buf]));  // accumulators of this tile are complete
         __syncwarp();
       }
-      if (mw == 0 && leader) RA_DBG(5);  // all MMAs issued
+      if (mw == 0 && leader) {
+        RA_DBG(5);  // all MMAs issued
+        RA_DBG_PUT(10, w_full);
+        RA_DBG_PUT(11, w_tempty);
+      }
     }
-  } else {
-    // =============================== epilogue (warps 0-3) ===============================
+  } else if (!(RS && warp >= kEpiWarpB0)) {
+    // =============================== epilogue (warps 0-3 and 15-18) ===============================
+    // eg: the group (it takes the m-tiles eg, eg + 2, ...; rowstack: group A alone), et: thread within the group = TMEM lane /
+    // slot within an m-tile, e2: thread within the whole epilogue (loops shared by both groups)
+    constexpr int kGroups = RS ? 1 : 2;
+    constexpr int kEpiN = RS ? kEpiThreads : kEpiAll;
+    const int eg = warp >= kEpiWarpB0 ? 1 : 0;
+    const int wq = warp & 3;
+    const int et = wq * 32 + lane;
+    const int e2 = eg * kEpiThreads + et;
     const int cols_mt = RS ? 6 * p.NPc : (p.merged ? 2 * p.NPc : p.NPc);
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;  // warp w may touch TMEM lanes [32w, 32w+32)
+    const uint32_t lane_sel = (uint32_t)(wq * 32) << 16;  // warp w may touch TMEM lanes [32 (w % 4), +32)
     int xw_par = 0;  // rowstack: parity of the cross-warp exchange buffer
     const int slots_out = p.TH * p.TWP;
     const int chain_cols = p.ksplit * cols_mt;  // TMEM columns of one m-tile
     const int co_base = ns * p.NPc;
     // folded-BN scale / shift of this CTA's channels: once into shared memory (padded channels: 0)
-    for (int i = tid; i < p.NPc; i += kEpiThreads) {
+    for (int i = e2; i < p.NPc; i += kEpiN) {
       const int co = co_base + i;
       sc_s[i] = co < p.Cout ? __ldg(p.scale + co) : 0.f;
       sh_s[i] = co < p.Cout ? __ldg(p.shift + co) : 0.f;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiN) : "memory");
 
     // v[16] <- columns cb..cb+15 of m-tile mt: sum of the merged halves and of the K-split partial accumulators;
     // the loads of one (hi half, lo half) pair are in flight together.  Then BN scale/shift (+ ReLU).
@@ -993,37 +1066,39 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
     };
 
     int t = 0;
+    long long w_tfull = 0, b_epi = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
       const Item it = decode_tile(p, tile);
       const int buf = p.nbuf == 2 ? (t & 1) : 0;
       const uint32_t use = p.nbuf == 2 ? (uint32_t)(t >> 1) : (uint32_t)t;
-      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+      RA_WAIT(smem_u32(&bar_tfull[buf]), use & 1u, w_tfull);
+      const long long te_ = (F16 && !CHAIN && p.dbg != nullptr) ? clock64() : 0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (t == 0 && tid == 0) RA_DBG(6);  // first accumulator complete
+      if (t == 0 && e2 == 0) RA_DBG(6);  // first accumulator complete
       const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols) + lane_sel;
       const int cb_end = (p.Cout - co_base) < p.NPc ? (p.Cout - co_base) : p.NPc;  // real channels of this split
       if (p.pool == 2) {
         for (int cb = 0; cb < cb_end; cb += 16) {
-          for (int mt = 0; mt < p.n_mt; ++mt) {
-            const int s = mt * p.mt_stride + tid;
+          for (int mt = eg; mt < p.n_mt; mt += kGroups) {
+            const int s = mt * p.mt_stride + et;
             float v[16];
             load16(acc, mt, cb, v);
             // horizontal max with the next slot (same image row: TW, x0 are even so pairs do not straddle)
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_down_sync(0xffffffffu, v[j], 1));
-            if ((lane & 1) == 0 && s < slots_out && tid < p.mt_stride) {
+            if ((lane & 1) == 0 && s < slots_out && et < p.mt_stride) {
               float *dst = pool_s + (size_t)(s >> 1) * kPoolLd;
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiN) : "memory");
           // vertical max + store of this 16-channel chunk: pooled pixel (py, px) <- staged half-rows of
           // slots (2py)*TWP+2px and +TWP
           const int ph = p.TH / 2, pw = p.TW / 2;
           const int Ho = p.Hout / 2, Wo = p.Wout / 2;
-          for (int idx = tid; idx < ph * pw * 4; idx += kEpiThreads) {
+          for (int idx = e2; idx < ph * pw * 4; idx += kEpiN) {
             const int c4 = idx & 3;
             const int pix = idx >> 2;
             const int py = pix / pw, px = pix - py * pw;
@@ -1044,14 +1119,14 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
                 if (co + j < p.Cout) dst[j] = tt[j];
             }
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiN) : "memory");
         }
       } else {
-        for (int mt = 0; mt < p.n_mt; ++mt) {
-          const int s = mt * p.mt_stride + tid;
+        for (int mt = eg; mt < p.n_mt; mt += kGroups) {
+          const int s = mt * p.mt_stride + et;
           const int oy_l = s / p.TWP, ox_l = s - oy_l * p.TWP;
           const int oy = it.y0 + oy_l, ox = it.x0 + ox_l;
-          const bool valid = s < slots_out && tid < p.mt_stride && ox_l < p.TW && oy < p.Hout && ox < p.Wout;
+          const bool valid = s < slots_out && et < p.mt_stride && ox_l < p.TW && oy < p.Hout && ox < p.Wout;
           float *dst_px = p.y + (((size_t)it.b * p.Hout + oy) * p.Wout + ox) * p.Cout + co_base;
           for (int cb = 0; cb < cb_end; cb += 16) {
             float v[16];
@@ -1073,6 +1148,11 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&bar_tempty[buf]));
+      if (F16 && !CHAIN && p.dbg != nullptr) b_epi += clock64() - te_;
+    }
+    if (e2 == 0) {
+      RA_DBG_PUT(12, w_tfull);
+      RA_DBG_PUT(13, b_epi);
     }
   }
 
@@ -1163,14 +1243,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_umma_chain_kernel(const _
 
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-// Operand format of the merged-mode layers: 0 = 3xTF32 (default), 1 / 2 = fp16 hi / lo split (see make_plan).  Taken from
-// RA_UMMA_F16 on first use; ra_conv3x3_umma_set_f16 overrides it (filter images packed for the old mode become invalid).
+// Operand format of the merged-mode layers (N <= 64 output channels per CTA): 1 (default) = fp16 hi / lo split wherever
+// the layer can be fed in 16-channel TMA boxes, 0 = 3xTF32 everywhere, 2 = like 1 but never an 8-channel chunk (calibration).
+// Taken from RA_UMMA_F16 on first use; ra_conv3x3_umma_set_f16 overrides it (filter images packed for the old mode become
+// invalid).  MEASURED (tools/f16_ab.py, profiles/r04*): same error against the fp64 convolution / the CPU oracle as 3xTF32
+// (slightly lower), the KITTI eval forward 14.9 -> 13.1 ms with the 4-channel-plane feed, and see DESIGN 4.1 for the
+// 16-channel-box feed.
 int g_f16_mode = -1;
 int umma_f16_mode() {
   if (g_f16_mode < 0) {
     const char *e = getenv("RA_UMMA_F16");
-    g_f16_mode = e == nullptr ? 0 : atoi(e);
-    if (g_f16_mode < 0 || g_f16_mode > 2) g_f16_mode = 0;
+    g_f16_mode = e == nullptr ? 1 : atoi(e);
+    if (g_f16_mode < 0 || g_f16_mode > 2) g_f16_mode = 1;
   }
   return g_f16_mode;
 }
@@ -1179,7 +1263,8 @@ int umma_f16_mode() {
 struct Plan {
   int KC, NP, NPc, n_split, merged, TH, TW, TWP, n_mt, slots_alloc, n_chunks, stages, acc_cols, stage_bytes;
   int rowstack, mt_stride;
-  int f16;  // fp16 hi / lo operand split (RA_UMMA_F16, experiment): merged mode, KC % 16 == 0, TMA feed only
+  int f16;  // fp16 hi / lo operand split (ra_conv3x3_umma_set_f16): merged mode, KC % 16 == 0, TMA feed in 16-channel boxes
+  int zone_bytes;  // f16: the landing zone of the 64-byte-per-pixel boxes the planner counted into stage_bytes
   int ksplit, nbuf;
   int w_resident, w_res_bytes, grid;
   size_t smem_bytes;
@@ -1188,7 +1273,16 @@ struct Plan {
 // Cost model (cycles per CTA), calibrated with tools/umma_rate.cu, tools/conv_timeline.py and the ncu captures
 // under profiles/: a tcgen05.mma with M=128, K=8 occupies the tensor core for max(48, N/2) cycles (the A operand
 // streams from shared memory) and one issuing warp sustains an instruction every 50-75 cycles.
-int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) {
+// fp16 split: can the layer be fed in 16-channel TMA boxes?  (16-byte global strides; a box must not straddle the two inputs
+// of a channel concatenation; channels past Cin are zero-filled by the TMA unit)
+bool f16_feasible(int C1, int C2) {
+  return umma_f16_mode() != 0 && getenv("RA_CONV_NO_TMA") == nullptr && (C1 % 4) == 0 && (C2 % 4) == 0 &&
+         (C2 == 0 || (C1 % 16) == 0);
+}
+
+int make_plan(int C1, int C2, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) {
+  const int Cin = C1 + C2;
+  const bool f16_ok = f16_feasible(C1, C2);
   const int NP = round_up(Cout, 16);
   if (NP > 256) return RA_ERR_UNSUPPORTED;
   if ((Wout & 1) || Wout < 2) return RA_ERR_UNSUPPORTED;
@@ -1233,8 +1327,8 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
     const int f16_mode = umma_f16_mode();
     for (int KC = 8; KC <= 32; KC *= 2) {
       if (KC > 8 && KC / 2 >= Cin) continue;
-      const int f16 = (f16_mode != 0 && merged && !rs && KC % 16 == 0 && (Cin % 4) == 0) ? 1 : 0;
-      if (f16_mode == 2 && merged && !rs && !f16 && Cin > 8 && (Cin % 4) == 0) continue;
+      const int f16 = (f16_ok && merged && !rs && KC % 16 == 0) ? 1 : 0;
+      if (f16_mode == 2 && f16_ok && merged && !rs && !f16 && Cin > 8) continue;
       const int planes = KC / 4;
       const int n_chunks = (Cin + KC - 1) / KC;
       const size_t w_chunk_bytes = (size_t)9 * (f16 ? planes / 2 : planes) * 2 * NPc * 16;
@@ -1246,7 +1340,11 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
           const int n_mt = (TH * TWP + mt_stride - 1) / mt_stride;
           if (n_mt > mt_max || n_mt > 2 * kMmaWarps) break;  // each MMA warp owns at most two m-tiles
           const int slots_alloc = round_up(n_mt * 128 + 2 * TWP + 2, 8);  // planes stay 128-byte aligned (TMA)
-          const size_t in_bytes = (size_t)2 * planes * slots_alloc * 16;
+          if (f16 && (TWP > 256 || TH + 2 > 256)) continue;  // TMA box extents
+          // fp16: hi / lo' share one region; the boxes land pixel-major in a zone behind it (counted at its stride-1 size;
+          // + alignment of the zone inside the stage)
+          const size_t zone_bytes = f16 ? (size_t)(KC / 16) * round_up(TWP * (TH + 2) * 64, 512) + 512 : 0;
+          const size_t in_bytes = (size_t)(f16 ? 1 : 2) * planes * slots_alloc * 16 + zone_bytes;
           const size_t pool_bytes = pool == 2 ? (size_t)(n_mt * 64) * kPoolLd * 4 : 0;
           const int tiles = ((Wout + TW - 1) / TW) * ((Hout + TH - 1) / TH) * B;
           int grid_t = ra::kNumSMs / n_split;  // CTAs per channel split
@@ -1294,6 +1392,7 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
               bp.merged = merged;
               bp.rowstack = rs;
               bp.f16 = f16;
+              bp.zone_bytes = (int)zone_bytes;
               bp.mt_stride = mt_stride;
               bp.TH = TH;
               bp.TW = TW;
@@ -1343,9 +1442,10 @@ int make_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) 
 }
 
 // Calibration hook (tools/bench_conv_layers.py): RA_UMMA_FORCE="KC,TH,TW,n_split,resident" overrides the search.
-int make_plan_forced(int Cin, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) {
+int make_plan_forced(int C1, int C2, int Cout, int Hout, int Wout, int pool, int B, Plan *pl) {
+  const int Cin = C1 + C2;
   const char *f = getenv("RA_UMMA_FORCE");
-  if (f == nullptr) return make_plan(Cin, Cout, Hout, Wout, pool, B, pl);
+  if (f == nullptr) return make_plan(C1, C2, Cout, Hout, Wout, pool, B, pl);
   int KC = 8, TH = 2, TW = 2, n_split = 1, resident = 0;
   if (sscanf(f, "%d,%d,%d,%d,%d", &KC, &TH, &TW, &n_split, &resident) != 5) return RA_ERR_INVALID_ARG;
   const int NP = round_up(Cout, 16);
@@ -1357,7 +1457,7 @@ int make_plan_forced(int Cin, int Cout, int Hout, int Wout, int pool, int B, Pla
   bp.n_split = n_split;
   bp.merged = bp.NPc <= 64 ? 1 : 0;
   bp.rowstack = 0;
-  bp.f16 = 0;
+  bp.f16 = (f16_feasible(C1, C2) && bp.merged && KC % 16 == 0 && TW + 2 <= 256 && TH + 2 <= 256) ? 1 : 0;
   bp.mt_stride = 128;
   const int cols_mt = bp.merged ? 2 * bp.NPc : bp.NPc;
   bp.TH = TH;
@@ -1373,8 +1473,9 @@ int make_plan_forced(int Cin, int Cout, int Hout, int Wout, int pool, int B, Pla
   bp.n_chunks = (Cin + KC - 1) / KC;
   bp.acc_cols = bp.n_mt * bp.ksplit * cols_mt;
   const int planes = KC / 4;
-  const size_t in_bytes = (size_t)2 * planes * bp.slots_alloc * 16;
-  const size_t w_chunk = (size_t)9 * planes * 2 * bp.NPc * 16;
+  bp.zone_bytes = bp.f16 ? (KC / 16) * round_up(bp.TWP * (TH + 2) * 64, 512) + 512 : 0;
+  const size_t in_bytes = (size_t)(bp.f16 ? 1 : 2) * planes * bp.slots_alloc * 16 + bp.zone_bytes;
+  const size_t w_chunk = (size_t)9 * (bp.f16 ? planes / 2 : planes) * 2 * bp.NPc * 16;
   const size_t pool_bytes = pool == 2 ? (size_t)(bp.n_mt * 64) * kPoolLd * 4 : 0;
   const size_t stage_bytes = in_bytes + (resident ? 0 : w_chunk);
   const size_t fixed = pool_bytes + (resident ? w_chunk * bp.n_chunks : 0);
@@ -1418,26 +1519,27 @@ EncodeTiledFn tensor_map_encoder() {
 
 struct MapKey {
   const void *ptr;
-  int C, W, H, B, RW, RH;
+  int C, W, H, B, RW, RH, box_c;
   bool operator==(const MapKey &o) const {
-    return ptr == o.ptr && C == o.C && W == o.W && H == o.H && B == o.B && RW == o.RW && RH == o.RH;
+    return ptr == o.ptr && C == o.C && W == o.W && H == o.H && B == o.B && RW == o.RW && RH == o.RH && box_c == o.box_c;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey &k) const {
     uint64_t h = reinterpret_cast<uintptr_t>(k.ptr);
-    const int v[6] = {k.C, k.W, k.H, k.B, k.RW, k.RH};
-    for (int i = 0; i < 6; ++i) h = h * 0x9E3779B97F4A7C15ull + (uint64_t)v[i];
+    const int v[7] = {k.C, k.W, k.H, k.B, k.RW, k.RH, k.box_c};
+    for (int i = 0; i < 7; ++i) h = h * 0x9E3779B97F4A7C15ull + (uint64_t)v[i];
     return (size_t)h;
   }
 };
 
 // 4-D tiled map over an NHWC fp32 activation: dims (C, W, H, B) innermost first, box = 4 channels x RW x RH x 1
 // pixel block = one channel plane of the shared-memory tile.  No swizzle, zero fill out of bounds.
-bool activation_map(const float *x, int C, int W, int H, int B, int RW, int RH, CUtensorMap *out) {
+// box_c = 16 (fp16 variant): 16 channels = 64-byte rows, pixel-major, SWIZZLE_64B (see convert_stage_f16).
+bool activation_map(const float *x, int C, int W, int H, int B, int RW, int RH, int box_c, CUtensorMap *out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  const MapKey key{x, C, W, H, B, RW, RH};
+  const MapKey key{x, C, W, H, B, RW, RH, box_c};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) {
@@ -1448,11 +1550,12 @@ bool activation_map(const float *x, int C, int W, int H, int B, int RW, int RH, 
   if (enc == nullptr) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  const cuuint32_t box[4] = {4, (cuuint32_t)RW, (cuuint32_t)RH, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)RW, (cuuint32_t)RH, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMap tm;
   const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   if (cache.size() > 4096) cache.clear();
@@ -1503,18 +1606,21 @@ extern "C" int ra_umma_pack_f16(const float *v, long long rows, int KC, int NPc,
   return ra::finish_launch("umma_pack_f16_kernel");
 }
 
-// Diagnostics: when set, every conv3x3_umma CTA writes 8 clock64() stamps (start, setup done, first stage
-// staged, producers done, first MMA issuable, MMAs issued, first accumulator complete, all done).
+// Diagnostics: when set, every conv3x3_umma CTA writes 16 slots: 8 clock64() stamps (start, setup done, first stage
+// staged, producers done, first MMA issuable, MMAs issued, first accumulator complete, all done) and the wait accounting
+// of RA_WAIT (8 TMA warp waiting for a free stage, 9 converters waiting for a box, 10 / 11 MMA warp 0 waiting for a staged
+// chunk / a free accumulator, 12 epilogue waiting for an accumulator, 13 epilogue busy, 14 converters busy; cycles).
 extern "C" int ra_debug_conv_timeline(long long *device_buf) {
   g_conv_dbg = device_buf;
   return RA_OK;
 }
 
 // Plan query for the host-side weight packer.
-extern "C" int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc,
-                                    int *n_split, int *n_chunks, int *rowstack) {
+extern "C" int ra_conv3x3_umma_plan_split(int C1, int C2, int Cout, int Hout, int Wout, int pool, int B, int *KC,
+                                          int *NPc, int *n_split, int *n_chunks, int *rowstack) {
+  if (C1 < 1 || C2 < 0) return RA_ERR_INVALID_ARG;
   Plan pl;
-  const int rc = make_plan_forced(Cin, Cout, Hout, Wout, pool, B, &pl);
+  const int rc = make_plan_forced(C1, C2, Cout, Hout, Wout, pool, B, &pl);
   if (rc != RA_OK) return rc;
   if (KC) *KC = pl.KC;
   if (NPc) *NPc = pl.NPc;
@@ -1524,11 +1630,16 @@ extern "C" int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int p
   return RA_OK;
 }
 
+extern "C" int ra_conv3x3_umma_plan(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *KC, int *NPc,
+                                    int *n_split, int *n_chunks, int *rowstack) {
+  return ra_conv3x3_umma_plan_split(Cin, 0, Cout, Hout, Wout, pool, B, KC, NPc, n_split, n_chunks, rowstack);
+}
+
 // Full plan dump (diagnostics / DESIGN.md tables): info[19] = KC, NPc, n_split, n_chunks, TH, TW, n_mt, stages,
 // merged, w_resident, grid, smem_bytes, acc_cols, stage_bytes, w_res_bytes, slots_alloc, ksplit, nbuf.
 extern "C" int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, int B, int *info) {
   Plan pl;
-  const int rc = make_plan_forced(Cin, Cout, Hout, Wout, pool, B, &pl);
+  const int rc = make_plan_forced(Cin, 0, Cout, Hout, Wout, pool, B, &pl);
   if (rc != RA_OK) return rc;
   if (!info) return RA_ERR_INVALID_ARG;
   const int v[19] = {pl.KC, pl.NPc, pl.n_split, pl.n_chunks, pl.TH, pl.TW, pl.n_mt, pl.stages, pl.merged,
@@ -1575,7 +1686,7 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
     *empty = true;
     return RA_OK;
   }
-  const int rc = make_plan_forced(p.Cin, Cout, p.Hout, p.Wout, pool, B, &pl);
+  const int rc = make_plan_forced(C1, C2, Cout, p.Hout, p.Wout, pool, B, &pl);
   if (rc != RA_OK) return rc;
   p.TH = pl.TH;
   p.TW = pl.TW;
@@ -1620,7 +1731,19 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
       (C2 == 0 || (reinterpret_cast<uintptr_t>(x2) & 15) == 0) && (reinterpret_cast<uintptr_t>(wpack) & 15) == 0) {
     bool ok = true;
     int stages = pl.stages, stage_bytes = pl.stage_bytes;
-    if (upsample == 2) {
+    if (pl.f16) {
+      // fp16 variant: every stage = [hi / lo' operand planes][filter slice][pad][landing zone: one 64-byte-per-pixel box per
+      // 16-channel group], zones 512-byte aligned (SWIZZLE_64B pattern; the kernel aligns its window to 1024 bytes)
+      ok = C2 == 0 || (C1 % 16) == 0;
+      p.raw_plane_bytes = round_up(p.RW * p.RH * 64, 512);
+      p.raw_off = round_up(pl.stage_bytes - pl.zone_bytes, 512);
+      stage_bytes = p.raw_off + (p.KC / 16) * p.raw_plane_bytes;
+      p.w_res_bytes = round_up(pl.w_res_bytes, 512);
+      const size_t fixed = pl.smem_bytes - (size_t)pl.stages * pl.stage_bytes - pl.w_res_bytes + p.w_res_bytes;
+      while (stages > 2 && fixed + (size_t)stages * stage_bytes > kSmemMax - 1024) --stages;
+      ok = ok && fixed + (size_t)stages * stage_bytes <= kSmemMax - 1024;
+      if (ok) smem_bytes = fixed + (size_t)stages * stage_bytes;
+    } else if (upsample == 2) {
       // landing zone of the low-resolution box, appended to every stage; drop stages if it does not fit
       p.raw_plane_bytes = round_up(p.RW * p.RH * 16, 128);
       p.raw_off = pl.stage_bytes;
@@ -1630,8 +1753,9 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
       ok = fixed + (size_t)stages * stage_bytes <= kSmemMax - 128;
       if (ok) smem_bytes = fixed + (size_t)stages * stage_bytes;
     }
-    ok = ok && activation_map(x1, C1, Win, Hin, B, p.RW, p.RH, &tm1);
-    ok = ok && (C2 == 0 || activation_map(x2, C2, Win, Hin, B, p.RW, p.RH, &tm2));
+    const int box_c = pl.f16 ? 16 : 4;
+    ok = ok && activation_map(x1, C1, Win, Hin, B, p.RW, p.RH, box_c, &tm1);
+    ok = ok && (C2 == 0 || activation_map(x2, C2, Win, Hin, B, p.RW, p.RH, box_c, &tm2));
     if (ok) {
       p.tma = 1;
       p.stages = stages;
@@ -1639,11 +1763,13 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
     } else {
       p.raw_plane_bytes = 0;
       p.raw_off = 0;
+      p.w_res_bytes = pl.w_res_bytes;
       smem_bytes = pl.smem_bytes;
     }
   }
   if (p.f16 && !p.tma) {  // the fp16 split lives in the TMA-mode converters only; the filter image is already packed for it
-    ra::set_last_error("conv3x3_umma: RA_UMMA_F16 needs the TMA feed (channel counts % 4 == 0, aligned tensors)", cudaSuccess);
+    ra::set_last_error("conv3x3_umma: the fp16 plan needs the TMA feed (16-byte aligned tensors; C1 % 16 == 0 for a "
+                       "channel concatenation - plan it with ra_conv3x3_umma_plan_split)", cudaSuccess);
     return RA_ERR_UNSUPPORTED;
   }
   p.grid = pl.grid;
@@ -1654,7 +1780,7 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
     p.four_term = 0;
     p.split_corr = 1;
   }
-  *smem_out = smem_bytes + 128;  // alignment slack (the kernel rounds its window up to 128 bytes)
+  *smem_out = smem_bytes + (p.f16 ? 1024 : 128);  // alignment slack (the kernel rounds its window up to 128 / 1024 bytes)
   return RA_OK;
 }
 

@@ -120,12 +120,13 @@ class FgModel(object):
     """One fused layer.  tcgen05 kernel when the layer shape has a tile plan, else the CUDA-core fp32 kernel
     (also with RA_CONV_FP32=1, the precision reference)."""
     B = x.shape[0]
+    C2 = 0 if x2 is None else int(x2.shape[3])
     if B not in L['packed']:
       packed = None
       if not os.environ.get('RA_CONV_FP32'):
         w = L['w']
         try:
-          KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], L['Hout'], L['Wout'], L['pool'], B)
+          KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], L['Hout'], L['Wout'], L['pool'], B, C2=C2)
           packed = ops.umma_filter_image(w, KC, NPc, nsp, rs, self.device)
         except _lib.RecAttendError:
           packed = None  # no tile plan for this shape (RA_ERR_UNSUPPORTED): fp32 kernel below

@@ -237,16 +237,17 @@ class _ModelBase(object):
     if os.environ.get('RA_CONV_FP32'):
       return ops.conv3x3_block(x, self._w_dev(wp), scale, shift, pool=pool, relu=relu, x2=x2, upsample=upsample,
                                out=out)
-    return ops.conv3x3_block_umma(x, self._packed(wp, x.shape[0], pool), wp['w'].shape[3], scale, shift, pool=pool,
+    return ops.conv3x3_block_umma(x, self._packed(wp, x.shape[0], pool, x2), wp['w'].shape[3], scale, shift, pool=pool,
                                   relu=relu, x2=x2, upsample=upsample, out=out)
 
-  def _packed(self, wp, B, pool):
+  def _packed(self, wp, B, pool, x2=None):
     """The tcgen05 filter image of a registered filter for batch size B (packed on first use: the tile plan, hence
-    the image, depends on the batch size and on the pooling)."""
-    key = (B, pool)
+    the image, depends on the batch size, on the pooling and on how the input channels split over x1 / x2)."""
+    C2 = 0 if x2 is None else int(x2.shape[3])
+    key = (B, pool, C2)
     if key not in wp['packed']:
       w = wp['w']
-      KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], pool, B)
+      KC, NPc, nsp, _, rs = ops.umma_plan(w.shape[2], w.shape[3], wp['Hout'], wp['Wout'], pool, B, C2=C2)
       if rs & 2:  # fp16 hi / lo split (RA_UMMA_F16): the registered tensor is the fp32 source, the image is made from it
         src = self._dev(PM.umma_f16_source(PM.WI(w, wp['idx']), KC, NPc, nsp))
         img = ops.umma_pack_f16(src, KC, NPc)
@@ -263,10 +264,12 @@ class _ModelBase(object):
     graph the per-layer launches already overlap through programmatic dependent launch (8.4 ms effective) and the
     chain cannot overlap with its neighbours: 17.4 ms per step against 15.7 ms - so one launch per layer stays the
     default (profiles/r02f_chain.txt)."""
-    return (bool(os.environ.get('RA_CHAIN')) and not os.environ.get('RA_CONV_FP32') and int(self.n_chains) <= 1)
+    # (the chain kernel runs the 3xTF32 variant only: it also needs RA_UMMA_F16=0)
+    return (bool(os.environ.get('RA_CHAIN')) and not os.environ.get('RA_CONV_FP32') and int(self.n_chains) <= 1
+            and ops.umma_set_f16(-1) == 0)
 
   def _chain_spec(self, x, wp, scale, shift, pool, relu=True, x2=None, upsample=1, out=None):
-    return {'x': x, 'x2': x2, 'wpack': self._packed(wp, x.shape[0], pool), 'Cout': wp['w'].shape[3], 'scale': scale,
+    return {'x': x, 'x2': x2, 'wpack': self._packed(wp, x.shape[0], pool, x2), 'Cout': wp['w'].shape[3], 'scale': scale,
             'shift': shift, 'pool': pool, 'relu': relu, 'upsample': upsample, 'out': out}
 
   def _block(self, train, x, wp, prefix, i, t, pool, relu=True, x2=None, upsample=1, out=None):

@@ -101,12 +101,14 @@ def canvas_conv(pre, canvas, w, scale, shift, pool=1, relu=True, out=None):
   return out
 
 
-def umma_plan(Cin, Cout, Hout, Wout, pool, B):
-  """(KC, NPc, n_split, n_chunks, rowstack) of the tcgen05 conv kernel for one layer shape and batch size; the
-  filter image must be packed for exactly this plan (pack_umma_weights / params.pack_umma)."""
+def umma_plan(Cin, Cout, Hout, Wout, pool, B, C2=0):
+  """(KC, NPc, n_split, n_chunks, layout flags) of the tcgen05 conv kernel for one layer shape and batch size; the
+  filter image must be packed for exactly this plan (umma_filter_image / pack_umma_weights / params.pack_umma).
+  C2: channels of the second input when the layer reads a concatenation [x1 | x2] (Cin = C1 + C2).  Flags: bit 0
+  row-stacked taps, bit 1 fp16 hi / lo split."""
   kc, npc, nsp, nch, rs = _c.c_int(0), _c.c_int(0), _c.c_int(0), _c.c_int(0), _c.c_int(0)
-  _lib.call('ra_conv3x3_umma_plan', Cin, Cout, Hout, Wout, pool, B, _c.byref(kc), _c.byref(npc), _c.byref(nsp),
-            _c.byref(nch), _c.byref(rs))
+  _lib.call('ra_conv3x3_umma_plan_split', Cin - C2, C2, Cout, Hout, Wout, pool, B, _c.byref(kc), _c.byref(npc),
+            _c.byref(nsp), _c.byref(nch), _c.byref(rs))
   return kc.value, npc.value, nsp.value, nch.value, rs.value
 
 

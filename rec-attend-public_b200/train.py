@@ -161,7 +161,14 @@ def _dgrad(m, wp, d_raw, upsample):
     wp['bwd_one'] = torch.ones(wi.val.shape[3], device=m.device)
     wp['bwd_zero'] = torch.zeros(wi.val.shape[3], device=m.device)
   Cin = wp['bwd']['w'].shape[3]
-  full = m._conv(d_raw, wp['bwd'], wp['bwd_one'], wp['bwd_zero'], 1, relu=False)
+  # gradients span many orders of magnitude below 1: they keep the 3xTF32 operands (8-bit exponent); the fp16 hi / lo split
+  # of the forward layers would lose the small ones (fp16 subnormals).  The plan - and with it the packed image of the
+  # flipped filter - is made at this call, under mode 0.
+  prev = ops.umma_set_f16(0)
+  try:
+    full = m._conv(d_raw, wp['bwd'], wp['bwd_one'], wp['bwd_zero'], 1, relu=False)
+  finally:
+    ops.umma_set_f16(prev)
   if upsample == 1:
     return full
   N, H2, W2, _ = full.shape

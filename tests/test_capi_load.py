@@ -62,10 +62,37 @@ def test_synthetic_batch_contract():
   assert b['y_gt'].sum(1).max() <= 1.0, 'instances are disjoint'
 
 
+def test_umma_f16_plans():
+  """The operand-format switch and the 16-channel-box feasibility rule of the fp16 hi / lo split (host logic only)."""
+  from rec_attend_b200 import ops
+  prev = ops.umma_set_f16(1)
+  try:
+    assert ops.umma_set_f16(-1) == 1
+    assert ops.umma_plan(16, 16, 128, 256, 2, 32)[4] & 2          # narrow layer: fp16 split
+    assert ops.umma_plan(32, 32, 24, 24, 1, 32, C2=16)[4] & 2     # concatenation on a 16-channel boundary
+    assert not ops.umma_plan(16, 16, 48, 48, 1, 32, C2=8)[4] & 2  # 8 + 8: a box would straddle the two inputs
+    assert not ops.umma_plan(13, 16, 48, 48, 1, 32)[4] & 2        # no TMA feed at all
+    assert not ops.umma_plan(64, 256, 12, 12, 1, 32)[0:5][4] & 2 or ops.umma_plan(64, 256, 12, 12, 1, 32)[1] <= 64
+    ops.umma_set_f16(0)
+    assert ops.umma_plan(16, 16, 128, 256, 2, 32)[4] & 2 == 0
+  finally:
+    ops.umma_set_f16(prev)
+  with pytest.raises(Exception):
+    ops.pack_umma_weights(np.zeros((3, 3, 16, 16), np.float32), 16, 16, 1, 2)  # fp16 images are made on the device
+
+
 def test_umma_plan_and_weight_packing():
   from rec_attend_b200 import ops
+  prev = ops.umma_set_f16(0)  # the host-packed (3xTF32) image
+  try:
+    _umma_plan_and_weight_packing(ops)
+  finally:
+    ops.umma_set_f16(prev)
+
+
+def _umma_plan_and_weight_packing(ops):
   KC, NPc, nsp, nch, rs = ops.umma_plan(64, 96, 12, 12, 2, 32)
-  assert KC in (8, 16, 32) and NPc * nsp == 96 and nch == 64 // KC and rs == 0  # 6 * NPc > 256: no row stacking
+  assert KC in (8, 16, 32) and NPc * nsp == 96 and nch == 64 // KC and not rs & 1  # 6 * NPc > 256: no row stacking
   rng = np.random.default_rng(0)
   w = rng.standard_normal((3, 3, 13, 40)).astype(np.float32)
   for B in (1, 32):
@@ -82,7 +109,7 @@ def test_umma_plan_and_weight_packing():
     assert (np.ascontiguousarray(hi).view(np.uint32) & np.uint32(0x1FFF) == 0).all()
   # the row-stacked image (narrow layers, RA_UMMA_ROWSTACK): the three kx taps of a filter row along N
   KC, NPc, nsp, nch, rs = ops.umma_plan(16, 16, 128, 256, 2, 32)
-  assert NPc == 16 and rs in (0, 1)
+  assert NPc == 16 and rs in (0, 1, 2)  # 2: the fp16 hi / lo split (default operand format of narrow layers)
   w16 = rng.standard_normal((3, 3, 16, 16)).astype(np.float32)
   st = ops.pack_umma_weights(w16, KC, NPc, nsp, 1)
   assert st.shape == (nsp, nch, 3, KC // 4, 6 * NPc, 4)

@@ -11,7 +11,7 @@ def make(shape):
   rng = np.random.default_rng(0)
   x = torch.from_numpy(rng.standard_normal((B, H, W, C1)).astype(np.float32)).cuda()
   w = rng.standard_normal((3, 3, C1, Cout)).astype(np.float32)
-  wp = torch.from_numpy(ops.pack_umma_weights(w, info['KC'], info['NPc'], info['n_split'], info['rowstack'])).cuda()
+  wp = ops.umma_filter_image(w, info['KC'], info['NPc'], info['n_split'], info['rowstack'], 'cuda')
   sc = torch.ones(Cout, device='cuda'); sh = torch.zeros(Cout, device='cuda')
   out = ops.conv3x3_block_umma(x, wp, Cout, sc, sh, pool=pool)
   return (x, wp, Cout, sc, sh, pool, out), info

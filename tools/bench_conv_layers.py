@@ -7,14 +7,20 @@ from rec_attend_b200 import ops, _lib
 
 LAYERS = {  # name: (B, H, W, C1, C2, Cout, up, pool)
     'ctrl_L1': (32, 128, 256, 16, 0, 16, 1, 2),
+    'ctrl_L2': (32, 64, 128, 16, 0, 32, 1, 1),
     'ctrl_L3': (32, 64, 128, 32, 0, 32, 1, 2),
+    'ctrl_L4': (32, 32, 64, 32, 0, 64, 1, 1),
     'ctrl_L5': (32, 32, 64, 64, 0, 64, 1, 2),
+    'ctrl_L6': (32, 16, 32, 64, 0, 64, 1, 1),
     'ctrl_L7': (32, 16, 32, 64, 0, 64, 1, 2),
     'attn_L1': (32, 48, 48, 16, 0, 32, 1, 2),
     'attn_L5': (32, 12, 12, 64, 0, 96, 1, 2),
     'dcnn_L2': (32, 12, 12, 64, 64, 32, 2, 1),
     'dcnn_L4': (32, 24, 24, 32, 32, 16, 2, 1),
 }
+
+
+_inputs = {}
 
 
 def time_layer(shape, force):
@@ -27,17 +33,24 @@ def time_layer(shape, force):
     info = ops.umma_plan_info(C1 + C2, Cout, H * up, W * up, pool, B)
   except _lib.RecAttendError:
     return None, None
-  rng = np.random.default_rng(0)
-  x1 = torch.from_numpy(rng.standard_normal((B, H, W, C1)).astype(np.float32)).cuda()
-  x2 = torch.from_numpy(rng.standard_normal((B, H, W, C2)).astype(np.float32)).cuda() if C2 else None
-  w = rng.standard_normal((3, 3, C1 + C2, Cout)).astype(np.float32)
-  wp = torch.from_numpy(ops.pack_umma_weights(w, info['KC'], info['NPc'], info['n_split'], info['rowstack'])).cuda()
+  if shape not in _inputs:  # inputs made once per layer (on the device: the sweep is hundreds of plans)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    _inputs.clear()
+    _inputs[shape] = (torch.randn((B, H, W, C1), device='cuda', generator=g),
+                      torch.randn((B, H, W, C2), device='cuda', generator=g) if C2 else None,
+                      np.random.default_rng(0).standard_normal((3, 3, C1 + C2, Cout)).astype(np.float32),
+                      torch.empty(64 << 20, device='cuda'))
+  x1, x2, w, flush = _inputs[shape]
+  wp = ops.umma_filter_image(w, info['KC'], info['NPc'], info['n_split'], info['rowstack'], 'cuda')
   sc = torch.ones(Cout, device='cuda'); sh = torch.zeros(Cout, device='cuda')
-  out = ops.conv3x3_block_umma(x1, wp, Cout, sc, sh, pool=pool, x2=x2, upsample=up)
-  flush = torch.empty(64 << 20, device='cuda')
+  try:
+    out = ops.conv3x3_block_umma(x1, wp, Cout, sc, sh, pool=pool, x2=x2, upsample=up)
+  except _lib.RecAttendError:
+    return None, None  # e.g. an fp16 plan whose tile the TMA feed cannot serve
   ts = []
   for _ in range(5):
     flush.zero_()
+    torch.cuda._sleep(150000)  # the launch is queued behind a busy GPU: the events see the kernel, not the host call
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     ops.conv3x3_block_umma(x1, wp, Cout, sc, sh, pool=pool, x2=x2, upsample=up, out=out)
@@ -46,14 +59,21 @@ def time_layer(shape, force):
   return min(ts), info
 
 
+# BCL_LAYERS=ctrl_L1,ctrl_L3 restricts the sweep; BCL_F16=0/1/2 sets the operand format (default: the library's)
+if os.environ.get('BCL_F16'):
+  ops.umma_set_f16(int(os.environ['BCL_F16']))
+KCS = tuple(int(k) for k in os.environ.get('BCL_KC', '8,16,32').split(','))
+only = [n for n in os.environ.get('BCL_LAYERS', '').split(',') if n]
 for name, shape in LAYERS.items():
+  if only and name not in only:
+    continue
   B, H, W, C1, C2, Cout, up, pool = shape
   Ho, Wo = H * up, W * up
   t, info = time_layer(shape, None)
-  print('%s auto: %.1f us  %s' % (name, t, {k: info[k] for k in ('KC', 'TH', 'TW', 'n_split', 'w_resident', 'n_mt', 'stages', 'grid')}))
+  print('%s auto: %.1f us  %s' % (name, t, {k: info[k] for k in ('KC', 'TH', 'TW', 'n_split', 'w_resident', 'n_mt', 'stages', 'grid', 'rowstack')}), flush=True)
   res = []
   tws = sorted({Wo, Wo // 2, Wo // 4, 32, 16} & {w for w in (Wo, Wo // 2, Wo // 4, 32, 16, 64) if 2 <= w <= Wo and w % 2 == 0})
-  for KC, TW, nsp, resd in itertools.product((8, 16, 32), tws, (1, 2, 4), (0, 1)):
+  for KC, TW, nsp, resd in itertools.product(KCS, tws, (1, 2, 4), (0, 1)):
     for TH in (2, 4, 6, 8, 12, 16, 24, 32):
       if TH > Ho:
         continue
@@ -61,6 +81,6 @@ for name, shape in LAYERS.items():
       if t is not None:
         res.append((t, KC, TH, TW, nsp, resd, info['n_mt'], info['stages'], info['grid']))
   res.sort()
-  for r in res[:6]:
+  for r in res[:8]:
     print('   %.1f us KC=%d TH=%d TW=%d nsplit=%d res=%d n_mt=%d stages=%d grid=%d' % r)
   print('   ... worst %.1f us, %d configs' % (res[-1][0], len(res)))

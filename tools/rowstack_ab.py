@@ -22,7 +22,7 @@ for name, (B, H, W, C1, C2, Cout, up, pool) in LAYERS.items():
   x1 = torch.from_numpy(rng.standard_normal((B, H, W, C1)).astype(np.float32)).cuda()
   x2 = torch.from_numpy(rng.standard_normal((B, H, W, C2)).astype(np.float32)).cuda() if C2 else None
   w = (rng.standard_normal((3, 3, C1 + C2, Cout)) / np.sqrt(9 * (C1 + C2))).astype(np.float32)
-  wp = torch.from_numpy(ops.pack_umma_weights(w, info['KC'], info['NPc'], info['n_split'], info['rowstack'])).cuda()
+  wp = ops.umma_filter_image(w, info['KC'], info['NPc'], info['n_split'], info['rowstack'], 'cuda')
   sc = torch.from_numpy(rng.uniform(0.5, 1.5, Cout).astype(np.float32)).cuda()
   sh = torch.from_numpy(rng.standard_normal(Cout).astype(np.float32)).cuda()
   out = ops.conv3x3_block_umma(x1, wp, Cout, sc, sh, pool=pool, x2=x2, upsample=up)
