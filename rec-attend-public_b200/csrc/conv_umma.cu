@@ -955,8 +955,13 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
 
     // v[16] <- columns cb..cb+15 of m-tile mt: sum of the merged halves and of the K-split partial accumulators;
     // the loads of one (hi half, lo half) pair are in flight together.  Then BN scale/shift (+ ReLU).
-    auto load16 = [&](uint32_t acc, int mt, int cb, float *v) {
-      uint32_t r0[16], r1[16];
+    // Software pipeline: TMEM reads are slow (64 bytes per cycle and SM, a round trip of ~1000 cycles per load pair while the
+    // tensor core accumulates into the other buffer: profiles/r04h_timeline_f16.txt) and they were the larger half of the
+    // epilogue; with one partial accumulator (ksplit == 1: every large layer) the loads of the NEXT call (nmt, ncb; nmt < 0:
+    // none) are issued into r0 / r1 as soon as this call has combined them into v, and fly during BN / pooling / stores.
+    uint32_t r0[16], r1[16];
+    bool pre = false;  // r0 / r1 already hold the (in-flight) loads of the coming call
+    auto load16 = [&](uint32_t acc, int mt, int cb, float *v, int nmt, int ncb) {
       if constexpr (RS) {
         // g[j] = D'[lane, kx block, channel cb + j] (hi half + lo half + K-split partials); the output of this
         // lane's slot is g(kx=0)[lane] + g(kx=1)[lane + 1] + g(kx=2)[lane + 2].  Lanes 30 / 31 take the rows of the
@@ -1025,8 +1030,10 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         return;
       }
       const uint32_t base = acc + (uint32_t)(mt * chain_cols + cb);
-      tmem_ld16_issue(base, r0);
-      if (p.merged) tmem_ld16_issue(base + (uint32_t)p.NPc, r1);
+      if (!pre) {
+        tmem_ld16_issue(base, r0);
+        if (p.merged) tmem_ld16_issue(base + (uint32_t)p.NPc, r1);
+      }
       tmem_wait16(r0);
       // fp16 mode: the second half holds the 2^11-scaled corrections (fmaf with 1.0 is the plain sum, bit for bit)
       constexpr float lo_scale = F16 ? 4.8828125e-4f : 1.0f;
@@ -1037,6 +1044,12 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
+      }
+      pre = p.ksplit == 1 && nmt >= 0;
+      if (pre) {
+        const uint32_t nb = acc + (uint32_t)(nmt * chain_cols + ncb);
+        tmem_ld16_issue(nb, r0);
+        if (p.merged) tmem_ld16_issue(nb + (uint32_t)p.NPc, r1);
       }
       for (int ks = 1; ks < p.ksplit; ++ks) {  // partial accumulators of the K split
         tmem_ld16_issue(base + (uint32_t)(ks * cols_mt), r0);
@@ -1066,13 +1079,11 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
     };
 
     int t = 0;
-    long long w_tfull = 0, b_epi = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
       const Item it = decode_tile(p, tile);
       const int buf = p.nbuf == 2 ? (t & 1) : 0;
       const uint32_t use = p.nbuf == 2 ? (uint32_t)(t >> 1) : (uint32_t)t;
-      RA_WAIT(smem_u32(&bar_tfull[buf]), use & 1u, w_tfull);
-      const long long te_ = (F16 && !CHAIN && p.dbg != nullptr) ? clock64() : 0;
+      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (t == 0 && e2 == 0) RA_DBG(6);  // first accumulator complete
       const uint32_t acc = tmem_base + (uint32_t)(buf * p.acc_cols) + lane_sel;
@@ -1082,7 +1093,11 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           for (int mt = eg; mt < p.n_mt; mt += kGroups) {
             const int s = mt * p.mt_stride + et;
             float v[16];
-            load16(acc, mt, cb, v);
+            {
+              const bool more = mt + kGroups < p.n_mt;  // then the same chunk of my next m-tile, else the next chunk
+              const bool nxt = more || cb + 16 < cb_end;
+              load16(acc, mt, cb, v, nxt ? (more ? mt + kGroups : eg) : -1, more ? cb : cb + 16);
+            }
             // horizontal max with the next slot (same image row: TW, x0 are even so pairs do not straddle)
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], __shfl_down_sync(0xffffffffu, v[j], 1));
@@ -1130,7 +1145,11 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           float *dst_px = p.y + (((size_t)it.b * p.Hout + oy) * p.Wout + ox) * p.Cout + co_base;
           for (int cb = 0; cb < cb_end; cb += 16) {
             float v[16];
-            load16(acc, mt, cb, v);  // (warp-collective: every lane takes part, valid or not)
+            {
+              const bool more = cb + 16 < cb_end;  // then the next chunk of this m-tile, else my next m-tile
+              const bool nxt = more || mt + kGroups < p.n_mt;
+              load16(acc, mt, cb, v, nxt ? (more ? mt : mt + kGroups) : -1, more ? cb + 16 : 0);
+            }  // (warp-collective: every lane takes part, valid or not)
             if (!valid) continue;
             float *dst = dst_px + cb;
             if ((p.Cout & 3) == 0) {
@@ -1148,11 +1167,6 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(smem_u32(&bar_tempty[buf]));
-      if (F16 && !CHAIN && p.dbg != nullptr) b_epi += clock64() - te_;
-    }
-    if (e2 == 0) {
-      RA_DBG_PUT(12, w_tfull);
-      RA_DBG_PUT(13, b_epi);
     }
   }
 
@@ -1609,7 +1623,7 @@ extern "C" int ra_umma_pack_f16(const float *v, long long rows, int KC, int NPc,
 // Diagnostics: when set, every conv3x3_umma CTA writes 16 slots: 8 clock64() stamps (start, setup done, first stage
 // staged, producers done, first MMA issuable, MMAs issued, first accumulator complete, all done) and the wait accounting
 // of RA_WAIT (8 TMA warp waiting for a free stage, 9 converters waiting for a box, 10 / 11 MMA warp 0 waiting for a staged
-// chunk / a free accumulator, 12 epilogue waiting for an accumulator, 13 epilogue busy, 14 converters busy; cycles).
+// chunk / a free accumulator, 14 converters busy; cycles; fp16 variant only).
 extern "C" int ra_debug_conv_timeline(long long *device_buf) {
   g_conv_dbg = device_buf;
   return RA_OK;

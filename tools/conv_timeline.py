@@ -54,7 +54,7 @@ for name, (B, H, W, C1, C2, Cout, up, pool) in LAYERS.items():
    print('   median cycles since CTA start: ' + ', '.join('%s=%d' % (n, np.median(rel[:, i])) for i, n in enumerate(names)))
    print('   max   cycles since CTA start: ' + ', '.join('%s=%d' % (n, rel[:, i].max()) for i, n in enumerate(names)))
    print('   CTA start spread (cycles): %d' % (d[:, 0].max() - d[:, 0].min()))
-   wn = ['tma_wait_free_stage', 'conv_wait_box', 'mma_wait_chunk', 'mma_wait_acc', 'epi_wait_acc', 'epi_busy', 'conv_busy']
+   wn = ['tma_wait_free_stage', 'conv_wait_box', 'mma_wait_chunk', 'mma_wait_acc', '-', '-', 'conv_busy']
    print('   median wait / busy cycles: ' + ', '.join('%s=%d' % (n, np.median(d16[:, 8 + i])) for i, n in enumerate(wn)))
 
 print('sum over layers (us):', total)
