@@ -390,19 +390,13 @@ __device__ __forceinline__ void issue_chunk_k8(const IssueCtx &c, bool merged, b
     if ((!CHAIN && p.dbg != nullptr)) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64();                          \
   } while (0)
 
-// hi / lo' of two activations, each packed as a half2 (first value in the low half).  The conversion pipe is the narrow one
-// (a cvt per value made the converters the second-longest stage), so hi is formed in fp32 with integer / FMA-pipe work -
-// x rounded to 11 significant bits, which IS an fp16 number for 2^-14 <= |x| < 65504; below, x rounded to the fp16
-// subnormal grid 2^-24 by the add-and-subtract trick - and only the two packing conversions (exact for hi) remain.
-__device__ __forceinline__ float f16_hi_part(float x) {
-  const float big = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-  const float small = (x + 0.75f) - 0.75f;  // multiples of 2^-24 (ulp of [0.5, 1))
-  return fabsf(x) < 6.103515625e-5f ? small : big;
-}
+// hi / lo' of two activations, each packed as a half2 (first value in the low half): hi = fp16(x), lo' = fp16((x - hi) * 2^11).
+// Two packing conversions and two unpacking adds per pair (F2FP.PACK_AB / HADD2.F32: ALU / FMA pipe); a formulation that
+// built hi with integer rounding to save conversions cost 2.5x the instructions and made the converters slower (r04g / r04i).
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t &h, uint32_t &l) {
-  const float ha = f16_hi_part(a), hb = f16_hi_part(b);
-  const __half2 hh = __floats2half2_rn(ha, hb);
-  const __half2 ll = __floats2half2_rn((a - ha) * 2048.0f, (b - hb) * 2048.0f);
+  const __half2 hh = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
   h = *reinterpret_cast<const uint32_t *>(&hh);
   l = *reinterpret_cast<const uint32_t *>(&ll);
 }
@@ -419,43 +413,43 @@ __device__ __forceinline__ void convert_stage_f16(uint4 *hi4, const uint4 *zone4
                                                   int slots_alloc, int up, int TWP, int RW, int y0, int x0, int cx, int cy,
                                                   int ptid) {
   constexpr int U = 2;
-  const int n_conv16 = (planes / 2) * box_slots;
-  for (int base = ptid; base < n_conv16; base += kProdThreads * U) {
-    uint4 va[U], vb[U];
-    int dst[U];
+  for (int k = 0; k < planes / 2; ++k) {  // 8-channel units of the chunk (no division in the slot loop)
+    const uint4 *zone = zone4 + (k >> 1) * zone_units;
+    uint4 *hi_k = hi4 + 2 * k * slots_alloc;
+    const int h2 = (k & 1) * 2;
+    for (int base = ptid; base < box_slots; base += kProdThreads * U) {
+      uint4 va[U], vb[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = base + u * kProdThreads;
-      dst[u] = -1;
-      va[u] = vb[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (idx < n_conv16) {
-        const int k = idx / box_slots, slot = idx - k * box_slots;
-        dst[u] = 2 * k * slots_alloc + slot;
-        int off = slot;  // up == 1: the box is the tile with its halo, RW == TWP
-        if (up != 1) {
-          const int r = slot / TWP, col = slot - r * TWP;
-          const int vy = y0 - 2 + r, vx = x0 - 2 + col;  // zero-inserted (virtual) pixel
-          off = ((vy | vx) & 1) == 0 ? ((vy >> 1) - cy) * RW + ((vx >> 1) - cx) : -1;
-        }
-        if (off >= 0) {
-          const uint4 *row = zone4 + (k >> 1) * zone_units + off * 4;
-          const int sw = (off >> 1) & 3, h2 = (k & 1) * 2;
-          va[u] = row[h2 ^ sw];
-          vb[u] = row[(h2 + 1) ^ sw];
+      for (int u = 0; u < U; ++u) {
+        const int slot = base + u * kProdThreads;
+        va[u] = vb[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (slot < box_slots) {
+          int off = slot;  // up == 1: the box is the tile with its halo, RW == TWP
+          if (up != 1) {
+            const int r = slot / TWP, col = slot - r * TWP;
+            const int vy = y0 - 2 + r, vx = x0 - 2 + col;  // zero-inserted (virtual) pixel
+            off = ((vy | vx) & 1) == 0 ? ((vy >> 1) - cy) * RW + ((vx >> 1) - cx) : -1;
+          }
+          if (off >= 0) {
+            const uint4 *row = zone + off * 4;
+            const int sw = (off >> 1) & 3;
+            va[u] = row[h2 ^ sw];
+            vb[u] = row[(h2 + 1) ^ sw];
+          }
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (dst[u] < 0) continue;
-      const float x[8] = {__uint_as_float(va[u].x), __uint_as_float(va[u].y), __uint_as_float(va[u].z),
-                          __uint_as_float(va[u].w), __uint_as_float(vb[u].x), __uint_as_float(vb[u].y),
-                          __uint_as_float(vb[u].z), __uint_as_float(vb[u].w)};
-      uint32_t h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) split_f16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
-      hi4[dst[u]] = make_uint4(h[0], h[1], h[2], h[3]);
-      hi4[dst[u] + slots_alloc] = make_uint4(l[0], l[1], l[2], l[3]);
+      for (int u = 0; u < U; ++u) {
+        const int slot = base + u * kProdThreads;
+        if (slot >= box_slots) continue;
+        uint32_t h[4], l[4];
+        split_f16x2(__uint_as_float(va[u].x), __uint_as_float(va[u].y), h[0], l[0]);
+        split_f16x2(__uint_as_float(va[u].z), __uint_as_float(va[u].w), h[1], l[1]);
+        split_f16x2(__uint_as_float(vb[u].x), __uint_as_float(vb[u].y), h[2], l[2]);
+        split_f16x2(__uint_as_float(vb[u].z), __uint_as_float(vb[u].w), h[3], l[3]);
+        hi_k[slot] = make_uint4(h[0], h[1], h[2], h[3]);
+        hi_k[slot + slots_alloc] = make_uint4(l[0], l[1], l[2], l[3]);
+      }
     }
   }
 }
@@ -961,7 +955,8 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
     // none) are issued into r0 / r1 as soon as this call has combined them into v, and fly during BN / pooling / stores.
     uint32_t r0[16], r1[16];
     bool pre = false;  // r0 / r1 already hold the (in-flight) loads of the coming call
-    auto load16 = [&](uint32_t acc, int mt, int cb, float *v, int nmt, int ncb) {
+    // relu_now = false: the caller applies the ReLU itself (pooling layers: after the max, on a quarter of the values)
+    auto load16 = [&](uint32_t acc, int mt, int cb, float *v, int nmt, int ncb, bool relu_now) {
       if constexpr (RS) {
         // g[j] = D'[lane, kx block, channel cb + j] (hi half + lo half + K-split partials); the output of this
         // lane's slot is g(kx=0)[lane] + g(kx=1)[lane + 1] + g(kx=2)[lane + 2].  Lanes 30 / 31 take the rows of the
@@ -1023,7 +1018,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
           v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
         }
-        if (p.relu) {
+        if (p.relu && relu_now) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
         }
@@ -1072,7 +1067,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
         v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
       }
-      if (p.relu) {
+      if (p.relu && relu_now) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       }
@@ -1096,7 +1091,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
             {
               const bool more = mt + kGroups < p.n_mt;  // then the same chunk of my next m-tile, else the next chunk
               const bool nxt = more || cb + 16 < cb_end;
-              load16(acc, mt, cb, v, nxt ? (more ? mt + kGroups : eg) : -1, more ? cb : cb + 16);
+              load16(acc, mt, cb, v, nxt ? (more ? mt + kGroups : eg) : -1, more ? cb : cb + 16, false);
             }
             // horizontal max with the next slot (same image row: TW, x0 are even so pairs do not straddle)
 #pragma unroll
@@ -1113,10 +1108,12 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           // slots (2py)*TWP+2px and +TWP
           const int ph = p.TH / 2, pw = p.TW / 2;
           const int Ho = p.Hout / 2, Wo = p.Wout / 2;
+          const int pw_shift = (pw & (pw - 1)) == 0 ? 31 - __clz(pw) : -1;  // tile widths are mostly powers of two
+          const float floor_v = p.relu ? 0.f : -INFINITY;  // ReLU commutes with the max
           for (int idx = e2; idx < ph * pw * 4; idx += kEpiN) {
             const int c4 = idx & 3;
             const int pix = idx >> 2;
-            const int py = pix / pw, px = pix - py * pw;
+            const int py = pw_shift >= 0 ? pix >> pw_shift : pix / pw, px = pix - py * pw;
             const int gy = (it.y0 >> 1) + py, gx = (it.x0 >> 1) + px;
             const int co = co_base + cb + c4 * 4;
             if (gy >= Ho || gx >= Wo || co >= p.Cout) continue;
@@ -1124,7 +1121,8 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
             const float4 va = *reinterpret_cast<const float4 *>(pool_s + (size_t)(s0 >> 1) * kPoolLd + c4 * 4);
             const float4 vc =
                 *reinterpret_cast<const float4 *>(pool_s + (size_t)((s0 + p.TWP) >> 1) * kPoolLd + c4 * 4);
-            const float4 m = make_float4(fmaxf(va.x, vc.x), fmaxf(va.y, vc.y), fmaxf(va.z, vc.z), fmaxf(va.w, vc.w));
+            const float4 m = make_float4(fmaxf(fmaxf(va.x, vc.x), floor_v), fmaxf(fmaxf(va.y, vc.y), floor_v),
+                                         fmaxf(fmaxf(va.z, vc.z), floor_v), fmaxf(fmaxf(va.w, vc.w), floor_v));
             float *dst = p.y + (((size_t)it.b * Ho + gy) * Wo + gx) * p.Cout + co;
             if ((p.Cout & 3) == 0) {
               *reinterpret_cast<float4 *>(dst) = m;
@@ -1148,7 +1146,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
             {
               const bool more = cb + 16 < cb_end;  // then the next chunk of this m-tile, else my next m-tile
               const bool nxt = more || mt + kGroups < p.n_mt;
-              load16(acc, mt, cb, v, nxt ? (more ? mt : mt + kGroups) : -1, more ? cb + 16 : 0);
+              load16(acc, mt, cb, v, nxt ? (more ? mt : mt + kGroups) : -1, more ? cb + 16 : 0, true);
             }  // (warp-collective: every lane takes part, valid or not)
             if (!valid) continue;
             float *dst = dst_px + cb;
