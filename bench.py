@@ -513,16 +513,19 @@ def run_ours(args):
     dom = max(groups.items(), key=lambda kv: kv[1]['ms'])[0]
     if dom.startswith('ra_conv3x3'):
       roofline = {
-          'kernel': 'conv3x3_umma (controller CNN layers 1-7, tcgen05 kind::tf32 x3 split, persistent grid, one launch '
-                    'per layer chained by programmatic dependent launch; group = ' + dom + ')',
+          'kernel': 'conv3x3_umma (controller CNN layers 1-7, tcgen05 kind::f16 hi/lo operand split - 3 fp16 MACs per '
+                    'fp32 MAC, persistent grid, one launch per layer chained by programmatic dependent launch; group = ' +
+                    dom + ')',
           'bound': 'tensor',
           'achieved': round(conv_tflops, 3), 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
           'frac': round(conv_tflops / peaks['bf16_tflops'], 5), 'traffic': entry_traffic(traffic, dom),
           'peak_source': peaks['source'] + ' (cuBLAS bf16 burst)',
           'note': 'flops = controller-CNN layers 1-7 (the layers this kernel group runs; layer 0 is the linear split '
                   'prepare + ra_canvas_conv_f32) per decode step x T / their summed CUDA-event time; '
-                  'the kernel issues 3 TF32 MMAs per algorithmic MAC (fp32 parity, DESIGN 4.1) and the TF32 dense rate '
-                  'is half the bf16 rate, so frac = 1/6 would be a saturated tensor pipe for this formulation'
+                  'the kernel issues 3 fp16 MACs (hi x hi, hi x lo, lo x hi) per algorithmic MAC for fp32 parity '
+                  '(DESIGN 4.1), so frac = 1/3 would be a saturated tensor pipe for this formulation; the layers have '
+                  '16-64 output channels and the kernel is bound by its epilogue / operand conversion, not by the tensor '
+                  'pipe (profiles/r04j_*)'
       }
     else:
       k = kernels[dom]
