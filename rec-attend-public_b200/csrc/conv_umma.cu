@@ -199,7 +199,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x4000;\n\t"  // suspend-time hint: fewer re-polls
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done)
         : "r"(mbar), "r"(parity)
