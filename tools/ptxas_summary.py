@@ -51,7 +51,7 @@ def ptxas():
 
 
 MNEMONICS = [
-    ('UTCHMMA', 'tcgen05.mma (kind::tf32) issued from one thread'),
+    ('UTCHMMA', 'tcgen05.mma (kind::f16 / kind::tf32), one issuing thread'),
     ('UTCBAR', 'tcgen05.commit -> mbarrier'),
     ('LDTM', 'tcgen05.ld (TMEM -> registers)'),
     ('UTCATOMSWS', 'tcgen05.alloc / dealloc (TMEM columns)'),
