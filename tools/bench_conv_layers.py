@@ -13,10 +13,13 @@ LAYERS = {  # name: (B, H, W, C1, C2, Cout, up, pool)
     'ctrl_L5': (32, 32, 64, 64, 0, 64, 1, 2),
     'ctrl_L6': (32, 16, 32, 64, 0, 64, 1, 1),
     'ctrl_L7': (32, 16, 32, 64, 0, 64, 1, 2),
-    'attn_L1': (32, 48, 48, 16, 0, 32, 1, 2),
-    'attn_L5': (32, 12, 12, 64, 0, 96, 1, 2),
-    'dcnn_L2': (32, 12, 12, 64, 64, 32, 2, 1),
-    'dcnn_L4': (32, 24, 24, 32, 32, 16, 2, 1),
+    'attn_L0': (32, 48, 48, 16, 0, 16, 1, 1), 'attn_L1': (32, 48, 48, 16, 0, 32, 1, 2),
+    'attn_L2': (32, 24, 24, 32, 0, 32, 1, 1), 'attn_L3': (32, 24, 24, 32, 0, 64, 1, 2),
+    'attn_L4': (32, 12, 12, 64, 0, 64, 1, 1), 'attn_L5': (32, 12, 12, 64, 0, 96, 1, 2),
+    'dcnn_L0': (32, 6, 6, 96, 0, 64, 2, 1), 'dcnn_L1': (32, 12, 12, 64, 64, 64, 1, 1),
+    'dcnn_L2': (32, 12, 12, 64, 64, 32, 2, 1), 'dcnn_L3': (32, 24, 24, 32, 32, 32, 1, 1),
+    'dcnn_L4': (32, 24, 24, 32, 32, 16, 2, 1), 'dcnn_L5': (32, 48, 48, 16, 16, 16, 1, 1),
+    'dcnn_L6': (32, 48, 48, 16, 16, 1, 1, 1),
 }
 
 
@@ -30,7 +33,7 @@ def time_layer(shape, force):
   else:
     os.environ['RA_UMMA_FORCE'] = force
   try:
-    info = ops.umma_plan_info(C1 + C2, Cout, H * up, W * up, pool, B)
+    info = ops.umma_plan_info(C1 + C2, Cout, H * up, W * up, pool, B)  # (C2 > 0 layers here have C1 % 16 == 0: same plan)
   except _lib.RecAttendError:
     return None, None
   if shape not in _inputs:  # inputs made once per layer (on the device: the sweep is hundreds of plans)
