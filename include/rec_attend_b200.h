@@ -129,6 +129,8 @@ int ra_conv3x3_umma_plan_info(int Cin, int Cout, int Hout, int Wout, int pool, i
 /* Operand format of the tile plans made from now on: 1 (default) = fp16 hi / lo split on the layers whose plan allows it
  * (<= 64 output channels per CTA, 16-channel chunks, TMA feed in 16-channel boxes), 0 = 3xTF32 everywhere, 2 = like 1,
  * forcing 16-channel chunks.  Both formats meet the same error bound (11 + 11 significand bits per operand).
+ * + 4 (modes 5, 6): the tensor core also folds the 2^11-scaled correction half of every accumulator into its main half at
+ * the end of a tile (tcgen05.mma with the correction columns as TMEM A operand): the epilogue reads half the columns.
  * Initial value: environment variable RA_UMMA_F16.  Returns the previous mode (mode < 0: query only).  Filter images are
  * packed per plan: set this before a model packs its filters. */
 int ra_conv3x3_umma_set_f16(int mode);

@@ -95,7 +95,10 @@ struct UmmaConvParams {
   int raw_off;      // up == 2 only: offset of that landing zone inside a stage
   int split_corr;   // merged mode: accumulate A_lo B_hi in the second accumulator half (RA_UMMA_JOINT_CORR=1: first)
   int four_term;    // merged mode: the A_lo instruction also spans [B_hi; B_lo] (adds the lo x lo partial product)
-  int f16;          // fp16 hi / lo operand split (experiment, RA_UMMA_F16): kind::f16, K = 16 per instruction
+  int f16;          // fp16 hi / lo operand split (ra_conv3x3_umma_set_f16): kind::f16, K = 16 per instruction
+  int fold;         // f16: the tensor core adds the 2^11-scaled correction half into the main half at the end of a tile
+                    // (kind::tf32 MMAs with the correction columns as TMEM A operand and 2^-11 I as B): the epilogue reads
+                    // N columns per m-tile instead of 2N
   int pdl;          // launched with programmatic stream serialization: griddepcontrol.wait before touching activations
   int grid;         // CTAs that serve this layer (= gridDim.x of a single-layer launch; <= gridDim.x inside a chain)
   long long *dbg;   // optional per-CTA timeline (ra_debug_conv_timeline), 8 slots per CTA
@@ -138,6 +141,20 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TENSOR MEMORY (columns a_tmem.. of the CTA's allocation: lane = row, one 32-bit column per K element),
+// B from shared memory: D[128 x N] (+)= A[128 x 8] B[8 x N].
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <bool F16>
 __device__ __forceinline__ void umma_k(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                        uint32_t accumulate) {
@@ -460,7 +477,7 @@ __device__ __forceinline__ void convert_stage_f16(uint4 *hi4, const uint4 *zone4
 // initialised again, `first` marks the layer that performs the programmatic-dependent-launch handshake.
 // RS: the row-stacked-taps variant (opt-in, see make_plan) is a separate instantiation, so that the default kernel
 // carries none of its registers / shared memory.
-template <bool RS, bool CHAIN, bool F16 = false>
+template <bool RS, bool CHAIN, bool F16 = false, bool FOLD = false>
 __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtensorMap &tm1, const CUtensorMap &tm2,
                                            unsigned char *smem_dyn, uint32_t tmem_base_in, bool first,
                                            const unsigned int *chain_counter = nullptr,
@@ -600,6 +617,17 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
         const int idx = base + u * kThreads;
         if (idx < n4) dstw[idx] = t[u];
       }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  // fold (fp16 variant): B = 2^-11 I in the K-major operand layout [NPc / 4 planes][NPc rows][4 floats], behind the pool tile
+  float *fold_s = pool_s + (p.pool == 2 ? p.n_mt * 64 * kPoolLd : 0);
+  if (F16 && FOLD) {
+    for (int i = tid; i < (p.NPc / 4) * p.NPc; i += kThreads) {
+      const int pl = i / p.NPc, row = i - pl * p.NPc;
+      const int hit = row - 4 * pl;  // the k index (0..3) of this plane that equals the row, if any
+      reinterpret_cast<float4 *>(fold_s)[i] = make_float4(hit == 0 ? 4.8828125e-4f : 0.f, hit == 1 ? 4.8828125e-4f : 0.f,
+                                                          hit == 2 ? 4.8828125e-4f : 0.f, hit == 3 ? 4.8828125e-4f : 0.f);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -914,6 +942,21 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
           if (leader) umma_commit(smem_u32(&bar_empty[s]));  // the stage may be refilled once these MMAs have read it
           __syncwarp();
         }
+        if (F16 && FOLD && has0 && leader) {
+          // main half += 2^-11 x correction half, on the tensor core (in order behind the tile's accumulations)
+          const uint64_t idb = make_desc(smem_u32(fold_s), (uint32_t)p.NPc * 16u, 128);
+          const uint32_t idesc_f = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)p.NPc >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+          for (int half = 0; half < (has1 ? 2 : 1); ++half) {
+            const uint32_t dm = half ? c.d1 : c.d0;
+            for (int ks = 0; ks < p.ksplit; ++ks) {
+              const uint32_t dk = dm + (uint32_t)(ks * cols_mt);
+              for (int j = 0; j < p.NPc / 8; ++j)
+                umma_tf32_ts(dk, dk + (uint32_t)(p.NPc + 8 * j), idb + (uint64_t)(2 * j * p.NPc), idesc_f, 1u);
+            }
+          }
+        }
+        __syncwarp();
         if (leader) umma_commit(smem_u32(&bar_tfull[buf]));  // accumulators of this tile are complete
         __syncwarp();
       }
@@ -953,6 +996,8 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
     // tensor core accumulates into the other buffer: profiles/r04h_timeline_f16.txt) and they were the larger half of the
     // epilogue; with one partial accumulator (ksplit == 1: every large layer) the loads of the NEXT call (nmt, ncb; nmt < 0:
     // none) are issued into r0 / r1 as soon as this call has combined them into v, and fly during BN / pooling / stores.
+// (fold: the tensor core has already added the second half)
+#define two_halves (p.merged && !(F16 && FOLD))
     uint32_t r0[16], r1[16];
     bool pre = false;  // r0 / r1 already hold the (in-flight) loads of the coming call
     // relu_now = false: the caller applies the ReLU itself (pooling layers: after the max, on a quarter of the values)
@@ -1027,12 +1072,12 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       const uint32_t base = acc + (uint32_t)(mt * chain_cols + cb);
       if (!pre) {
         tmem_ld16_issue(base, r0);
-        if (p.merged) tmem_ld16_issue(base + (uint32_t)p.NPc, r1);
+        if (two_halves) tmem_ld16_issue(base + (uint32_t)p.NPc, r1);
       }
       tmem_wait16(r0);
       // fp16 mode: the second half holds the 2^11-scaled corrections (fmaf with 1.0 is the plain sum, bit for bit)
       constexpr float lo_scale = F16 ? 4.8828125e-4f : 1.0f;
-      if (p.merged) {
+      if (two_halves) {
         tmem_wait16(r1);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r1[j]), lo_scale, __uint_as_float(r0[j]));
@@ -1044,15 +1089,15 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       if (pre) {
         const uint32_t nb = acc + (uint32_t)(nmt * chain_cols + ncb);
         tmem_ld16_issue(nb, r0);
-        if (p.merged) tmem_ld16_issue(nb + (uint32_t)p.NPc, r1);
+        if (two_halves) tmem_ld16_issue(nb + (uint32_t)p.NPc, r1);
       }
       for (int ks = 1; ks < p.ksplit; ++ks) {  // partial accumulators of the K split
         tmem_ld16_issue(base + (uint32_t)(ks * cols_mt), r0);
-        if (p.merged) tmem_ld16_issue(base + (uint32_t)(ks * cols_mt + p.NPc), r1);
+        if (two_halves) tmem_ld16_issue(base + (uint32_t)(ks * cols_mt + p.NPc), r1);
         tmem_wait16(r0);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r0[j]);
-        if (p.merged) {
+        if (two_halves) {
           tmem_wait16(r1);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = fmaf(__uint_as_float(r1[j]), lo_scale, v[j]);
@@ -1073,6 +1118,7 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
       }
     };
 
+#undef two_halves
     int t = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
       const Item it = decode_tile(p, tile);
@@ -1178,12 +1224,13 @@ __device__ __forceinline__ void conv_layer(const UmmaConvParams &p, const CUtens
 }
 
 // F16: the fp16 hi / lo operand split (RA_UMMA_F16 plans) - like RS a separate instantiation.
-template <bool RS, bool F16 = false>
+// FOLD: F16 + the correction half folded on the tensor core (mode + 4): one more instantiation.
+template <bool RS, bool F16 = false, bool FOLD = false>
 __global__ void __launch_bounds__(kThreads, 1)
     conv3x3_umma_kernel(const __grid_constant__ UmmaConvParams p, const __grid_constant__ CUtensorMap tm1,
                         const __grid_constant__ CUtensorMap tm2) {
   extern __shared__ __align__(128) unsigned char smem_dyn[];
-  conv_layer<RS, false, F16>(p, tm1, tm2, smem_dyn, 0u, true);
+  conv_layer<RS, false, F16, FOLD>(p, tm1, tm2, smem_dyn, 0u, true);
 }
 
 // A CHAIN of conv layers in one launch: the patch network of a decode step (6 + 7 layers) or controller layers 1-7.
@@ -1261,15 +1308,19 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // invalid).  MEASURED (tools/f16_ab.py, profiles/r04*): same error against the fp64 convolution / the CPU oracle as 3xTF32
 // (slightly lower), the KITTI eval forward 14.9 -> 13.1 ms with the 4-channel-plane feed, and see DESIGN 4.1 for the
 // 16-channel-box feed.
+// + 4 (modes 5 / 6): the tensor core folds the correction half into the main half at the end of a tile (UmmaConvParams::fold;
+// correct, TMEM reads halved, measured no faster - the layers are bound by shared-memory bandwidth, DESIGN 4.1 - so off by default).
 int g_f16_mode = -1;
-int umma_f16_mode() {
+int umma_f16_raw() {
   if (g_f16_mode < 0) {
     const char *e = getenv("RA_UMMA_F16");
     g_f16_mode = e == nullptr ? 1 : atoi(e);
-    if (g_f16_mode < 0 || g_f16_mode > 2) g_f16_mode = 1;
+    if (g_f16_mode < 0 || g_f16_mode > 6 || (g_f16_mode & 3) == 3 || g_f16_mode == 4) g_f16_mode = 1;
   }
   return g_f16_mode;
 }
+int umma_f16_mode() { return umma_f16_raw() & 3; }
+bool umma_fold_mode() { return (umma_f16_raw() & 4) != 0; }
 
 // Tile plan shared by the launcher and the weight packer (through ra_conv3x3_umma_plan).
 struct Plan {
@@ -1604,8 +1655,8 @@ __global__ void __launch_bounds__(256) umma_pack_f16_kernel(const float4 *__rest
 }
 
 extern "C" int ra_conv3x3_umma_set_f16(int mode) {
-  const int prev = umma_f16_mode();
-  if (mode >= 0 && mode <= 2) g_f16_mode = mode;
+  const int prev = umma_f16_raw();
+  if (mode >= 0 && mode <= 6 && (mode & 3) != 3 && mode != 4) g_f16_mode = mode;
   return prev;
 }
 
@@ -1779,6 +1830,14 @@ int build_layer(const float *x1, int C1, const float *x2, int C2, const float *w
       smem_bytes = pl.smem_bytes;
     }
   }
+  p.fold = 0;
+  if (p.f16 && p.tma) {
+    const size_t id_bytes = (size_t)(p.NPc / 4) * p.NPc * 16;
+    if (umma_fold_mode() && smem_bytes + id_bytes <= kSmemMax - 1024) {
+      p.fold = 1;
+      smem_bytes += id_bytes;
+    }
+  }
   if (p.f16 && !p.tma) {  // the fp16 split lives in the TMA-mode converters only; the filter image is already packed for it
     ra::set_last_error("conv3x3_umma: the fp16 plan needs the TMA feed (16-byte aligned tensors; C1 % 16 == 0 for a "
                        "channel concatenation - plan it with ra_conv3x3_umma_plan_split)", cudaSuccess);
@@ -1805,6 +1864,9 @@ bool conv_attrs() {
       e = cudaFuncSetAttribute(conv3x3_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv3x3_umma_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               224 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv3x3_umma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
@@ -1858,6 +1920,7 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = p.rowstack ? cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<true>, p, tm1, tm2)
+                    : p.fold   ? cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<false, true, true>, p, tm1, tm2)
                     : p.f16    ? cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<false, true>, p, tm1, tm2)
                                : cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<false>, p, tm1, tm2);
     if (e != cudaSuccess) {
@@ -1867,6 +1930,8 @@ extern "C" int ra_conv3x3_umma_f32(const float *x1, int C1, const float *x2, int
   } else {
     if (p.rowstack)
       conv3x3_umma_kernel<true><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
+    else if (p.fold)
+      conv3x3_umma_kernel<false, true, true><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
     else if (p.f16)
       conv3x3_umma_kernel<false, true><<<pl.grid, kThreads, smem_bytes, ra::as_stream(stream)>>>(p, tm1, tm2);
     else

@@ -266,7 +266,7 @@ class _ModelBase(object):
     default (profiles/r02f_chain.txt)."""
     # (the chain kernel runs the 3xTF32 variant only: it also needs RA_UMMA_F16=0)
     return (bool(os.environ.get('RA_CHAIN')) and not os.environ.get('RA_CONV_FP32') and int(self.n_chains) <= 1
-            and ops.umma_set_f16(-1) == 0)
+            and (ops.umma_set_f16(-1) & 3) == 0)
 
   def _chain_spec(self, x, wp, scale, shift, pool, relu=True, x2=None, upsample=1, out=None):
     return {'x': x, 'x2': x2, 'wpack': self._packed(wp, x.shape[0], pool, x2), 'Cout': wp['w'].shape[3], 'scale': scale,

@@ -136,8 +136,8 @@ def pack_umma_weights(w_hwio, KC, NPc, n_split, rowstack=0):
 
 
 def umma_set_f16(mode):
-  """Operand format of the tile plans made from now on (0 = 3xTF32, 1 / 2 = fp16 hi / lo split); returns the previous
-  mode; mode < 0 only queries."""
+  """Operand format of the tile plans made from now on (0 = 3xTF32, 1 / 2 = fp16 hi / lo split, + 4 = correction half
+  folded on the tensor core); returns the previous mode; mode < 0 only queries."""
   return _lib.lib().ra_conv3x3_umma_set_f16(int(mode))
 
 

@@ -522,11 +522,12 @@ def test_conv3x3_block_umma(ops, case):
   return rs
 
 
-@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('mode', [1, 2, 5])
 @pytest.mark.parametrize('case', UMMA_CASES)
 def test_conv3x3_block_umma_f16(ops, case, mode):
   """The fp16 hi / lo operand split (kind::f16, K = 16 per instruction; ra_conv3x3_umma_set_f16 / RA_UMMA_F16): same
   layers, same bound - hi = fp16(x) and lo' = fp16((x - hi) * 2^11) carry 11 + 11 significand bits like the two tf32 parts.
+  Mode 5 = mode 1 + the correction half folded into the main half by the tensor core (A operand from tensor memory).
   Layers whose plan does not take the split (wide N, channel counts the TMA feed cannot serve) run as before."""
   B, H, W, C1, C2, Cout, up, pool, relu = case
   prev = ops.umma_set_f16(mode)
@@ -537,7 +538,7 @@ def test_conv3x3_block_umma_f16(ops, case, mode):
   feedable = (C1 % 4) == 0 and (C2 % 4) == 0 and (C2 == 0 or C1 % 16 == 0)  # 16-channel TMA boxes
   if not feedable:
     assert not rs & 2, 'the fp16 split was planned for a layer the TMA feed cannot serve'
-  if mode == 2 and Cout <= 64 and (C1 + C2) >= 16 and feedable:
+  if (mode & 3) == 2 and Cout <= 64 and (C1 + C2) >= 16 and feedable:
     assert rs & 2, 'mode 2 must take the fp16 split on every merged-mode layer with >= 16 input channels'
 
 
