@@ -524,8 +524,9 @@ def run_ours(args):
                   'prepare + ra_canvas_conv_f32) per decode step x T / their summed CUDA-event time; '
                   'the kernel issues 3 fp16 MACs (hi x hi, hi x lo, lo x hi) per algorithmic MAC for fp32 parity '
                   '(DESIGN 4.1), so frac = 1/3 would be a saturated tensor pipe for this formulation; the layers have '
-                  '16-64 output channels and the kernel is bound by its epilogue / operand conversion, not by the tensor '
-                  'pipe (profiles/r04j_*)'
+                  '16-64 output channels and the kernel is bound by shared-memory bandwidth (every filter tap re-reads the '
+                  'A operand; operand conversion and pooling go through shared memory too), not by the tensor pipe '
+                  '(DESIGN 4.1, profiles/r04j_*, r04s_*)'
       }
     else:
       k = kernels[dom]
