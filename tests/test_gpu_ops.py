@@ -479,11 +479,16 @@ UMMA_CASES = [
 def test_conv3x3_block_umma_plain_loads(ops, case, monkeypatch):
   """The same layers with the TMA feed switched off (the path layers with odd channel counts take)."""
   monkeypatch.setenv('RA_CONV_NO_TMA', '1')
-  test_conv3x3_block_umma(ops, case)
+  _run_umma_case(ops, case)
 
 
 @pytest.mark.parametrize('case', UMMA_CASES)
 def test_conv3x3_block_umma(ops, case):
+  _run_umma_case(ops, case)
+
+
+def _run_umma_case(ops, case):
+  """One layer against the fp32 convolution of the oracle; returns the layout flags of the plan it ran."""
   B, H, W, C1, C2, Cout, up, pool, relu = case
   rng = np.random.default_rng(hash(case) % 2**31)
   x1 = rng.standard_normal((B, H, W, C1)).astype(np.float32)
@@ -532,7 +537,7 @@ def test_conv3x3_block_umma_f16(ops, case, mode):
   B, H, W, C1, C2, Cout, up, pool, relu = case
   prev = ops.umma_set_f16(mode)
   try:
-    rs = test_conv3x3_block_umma(ops, case)
+    rs = _run_umma_case(ops, case)
   finally:
     ops.umma_set_f16(prev)
   feedable = (C1 % 4) == 0 and (C2 % 4) == 0 and (C2 == 0 or C1 % 16 == 0)  # 16-channel TMA boxes
