@@ -58,3 +58,39 @@ def test_transforms_commute_with_indices():
   assert st.val.shape[0] == 4 and np.array_equal(flat_all[st.idx - 1], st.val)
   hi = PM.tf32_hi(wi.val)
   assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.abs(wi.val - hi).max() <= np.abs(wi.val).max() * 2.0**-11
+
+
+def test_f16_filter_image_source_and_numpy_model():
+  """fp16 hi / lo filter images (the default operand format of the narrow conv layers): the registered fp32 source
+  rebuilds from the trainable bucket through the gather codes, and the numpy model of ra_umma_pack_f16 - hi = fp16(w),
+  lo' = fp16((w - hi) * 2^11), rows [hi | lo'] per 8-channel plane - reproduces w to 2^-21 of its magnitude (2^-24 + the
+  fp16 subnormal step / 2^11 in absolute terms for tiny weights)."""
+  opt, w = _weights()
+  lay = PM.AllLayout(w)
+  fp = FlatParams(w)
+  tmap = PM.to_train_map(lay, fp)
+  flat_train = fp.flatten(w)
+  for key, KC, NPc, nsp in (('ctrl_cnn_w_1', 16, 16, 1), ('ctrl_cnn_w_3', 32, 32, 1), ('attn_dcnn_w_1', 32, 32, 2)):
+    wi = PM.wi_of(w, lay, key)
+    if key.startswith('attn_dcnn'):
+      wi = wi.map(PM.deconv_to_conv)
+    src = PM.umma_f16_source(wi, KC, NPc, nsp)
+    Cin, Cout = wi.val.shape[2], wi.val.shape[3]
+    nch = (Cin + KC - 1) // KC
+    assert src.val.shape == (nsp, nch, 9, KC // 4, NPc, 4) and src.kind is None
+    code = PM.encode(src.idx, None, tmap)
+    assert np.array_equal(PM.gather_reference(flat_train, code).reshape(src.val.shape), src.val)
+    img = PM.pack_umma_f16_reference(src.val)
+    assert img.shape == (nsp, nch, 9, KC // 8, 2 * NPc, 8) and img.dtype == np.float16
+    hi, lo = img[..., :NPc, :].astype(np.float64), img[..., NPc:, :].astype(np.float64)
+    # back to [.., KC/4, NPc, 4]: halves 0-3 of plane k are fp32 plane 2k, halves 4-7 plane 2k + 1
+    rec = (hi + lo / 2048.0).reshape(nsp, nch, 9, KC // 8, NPc, 2, 4).swapaxes(-3, -2).reshape(src.val.shape)
+    err = np.abs(rec - src.val.astype(np.float64))
+    assert (err <= np.abs(src.val) * 2.0 ** -21 + 2.0 ** -35).all()
+  # dynamic range: values down to the fp16 subnormals keep an absolute error of 2^-36, large ones 2^-22 relative
+  x = (np.random.default_rng(3).standard_normal((1, 1, 9, 4, 16, 4)) *
+       np.exp(np.random.default_rng(4).uniform(-20, 8, (1, 1, 9, 4, 16, 4)))).astype(np.float32)
+  img = PM.pack_umma_f16_reference(x)
+  rec = (img[..., :16, :].astype(np.float64) + img[..., 16:, :].astype(np.float64) / 2048.0)
+  rec = rec.reshape(1, 1, 9, 2, 16, 2, 4).swapaxes(-3, -2).reshape(x.shape)
+  assert (np.abs(rec - x) <= np.abs(x) * 2.0 ** -21 + 2.0 ** -35).all()
